@@ -1,0 +1,196 @@
+"""OBJ / MTL loading (reference: src/objloader.js:9-20,58-116,144-268).
+
+Restates `parseObjFile`'s semantics: fan triangulation of every `f` line,
+`v/vt/vn` index triples, the `minArea` filter on `Triangle.area`, one
+`Primitive` per triangle sharing `transform` / `inv_transform`, and the
+`makeMaterial` quirk (src/objloader.js:16-19: the Fresnel / path-tracing
+branch lacks `return`, so MTL materials are always `PhongMaterial`).
+
+Parsing is split in two so that meshes can be committed as compact derived
+fixtures (`scenes/data/*.npz`; `/root/reference` is absent on the GPU box):
+`parse_obj_text` -> `ParsedObj` (arrays), `triangles_from_parsed` -> Primitives.
+"""
+from __future__ import annotations
+
+import math
+import os
+import re
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .jsmath import Vec, Mat4
+from .geometry import Triangle
+from .materials import (MaterialColor, ScaledMaterialColor, PhongMaterial)
+from .world import Primitive
+
+_SKIP = re.compile(r"^\s*($|#)")
+_IDX = re.compile(r"(\d+)(?:/(\d*)(?:/(\d+))?)?")
+
+
+def _parse_float(tok: str) -> float:
+    """Number.parseFloat: longest numeric prefix, NaN if none."""
+    m = re.match(r"\s*[+-]?(\d+\.?\d*([eE][+-]?\d+)?|\.\d+([eE][+-]?\d+)?|Infinity)", tok)
+    if not m:
+        return math.nan
+    s = m.group(0).strip()
+    return float(s.replace("Infinity", "inf"))
+
+
+@dataclass
+class ParsedObj:
+    positions: np.ndarray            # (P,4) f32
+    texcoords: np.ndarray            # (T,3) f32
+    normals: np.ndarray              # (N,4) f32
+    faces: np.ndarray                # (F,3,3) int32: per corner (v, vt, vn); -1 = absent
+    face_material: np.ndarray        # (F,) int32 index into material_names; -1 = default
+    material_names: list = field(default_factory=list)
+    mtllibs: list = field(default_factory=list)
+
+    def save(self, path):
+        np.savez_compressed(path, positions=self.positions, texcoords=self.texcoords, normals=self.normals,
+                            faces=self.faces, face_material=self.face_material,
+                            material_names=np.array(self.material_names, dtype="U"),
+                            mtllibs=np.array(self.mtllibs, dtype="U"))
+
+    @staticmethod
+    def load(path):
+        z = np.load(path, allow_pickle=False)
+        return ParsedObj(z["positions"], z["texcoords"], z["normals"], z["faces"], z["face_material"],
+                         [str(s) for s in z["material_names"]], [str(s) for s in z["mtllibs"]])
+
+
+def parse_obj_text(data: str) -> ParsedObj:
+    """The geometry half of parseObjFile (src/objloader.js:149-238): already
+    fan-triangulated (`for i = 2..`: [0, i-1, i], :190-191)."""
+    positions, textures, normals, faces, fmat = [], [], [], [], []
+    names, mtllibs = [], []
+    cur = -1
+    for l in data.split("\n"):
+        if _SKIP.match(l):
+            continue
+        t = re.findall(r"\S+", l)
+        if t[0] == "mtllib":
+            mtllibs.append(t[1])
+            continue
+        if t[0] == "usemtl":
+            if t[1] not in names:
+                names.append(t[1])
+            cur = names.index(t[1])
+            continue
+        if t[0] == "f":
+            idx = []
+            for tok in t[1:]:
+                m = _IDX.search(tok)
+                tri = []
+                for g in m.groups():
+                    tri.append(int(g) - 1 if g not in (None, "") else -1)
+                idx.append(tri)
+            for i in range(2, len(idx)):
+                faces.append([idx[0], idx[i - 1], idx[i]])
+                fmat.append(cur)
+            continue
+        nums = [_parse_float(x) for x in t[1:]]
+        if t[0] == "v":
+            positions.append([nums[0], nums[1], nums[2], 1 if len(t) < 5 else nums[3]])
+        elif t[0] == "vt":
+            g = lambda i: (nums[i] if i < len(nums) and nums[i] == nums[i] else 0) or 0
+            textures.append([nums[0], g(1), g(2)])
+        elif t[0] == "vn":
+            normals.append([nums[0], nums[1], nums[2], 0])
+        elif t[0] in ("s", "o", "g", "vp"):
+            continue
+        else:
+            raise ValueError('Error while attempting to parse obj file on line "%s"' % l)
+    return ParsedObj(np.asarray(positions, dtype=np.float32).reshape(-1, 4),
+                     np.asarray(textures, dtype=np.float32).reshape(-1, 3),
+                     np.asarray(normals, dtype=np.float32).reshape(-1, 4),
+                     np.asarray(faces, dtype=np.int32).reshape(-1, 3, 3),
+                     np.asarray(fmat, dtype=np.int32), names, mtllibs)
+
+
+def triangles_from_parsed(parsed: ParsedObj, defaultMaterial=None, transform=None, minArea=0.0, materials=None):
+    """The triangle-building half of parseObjFile (src/objloader.js:188-206)."""
+    transform = transform if transform is not None else Mat4.identity()
+    inv_transform = Mat4.inverse(transform)
+    pos = [Vec(p) for p in parsed.positions.tolist()]
+    tex = [Vec(p) for p in parsed.texcoords.tolist()]
+    nrm = [Vec(p) for p in parsed.normals.tolist()]
+    faces = parsed.faces.tolist()
+    fmat = parsed.face_material.tolist()
+    triangles = []
+    for f, mi in zip(faces, fmat):
+        data = {}
+        if all(c[1] >= 0 for c in f):
+            data["UV"] = [tex[c[1]] for c in f]
+        if all(c[2] >= 0 for c in f):
+            data["normal"] = [nrm[c[2]] for c in f]
+        tri = Triangle([pos[c[0]] for c in f], data)
+        if tri.area >= minArea:
+            mat = defaultMaterial
+            if mi >= 0:
+                name = parsed.material_names[mi]
+                if not materials or name not in materials:
+                    raise ValueError("No material defined with name: " + name)
+                mat = materials[name]
+            triangles.append(Primitive(tri, mat, transform, inv_transform))
+    return triangles
+
+
+# -- MTL (src/objloader.js:1-20,58-116) --------------------------------------
+def _make_material_color(a, b, default=None):
+    default = default if default is not None else Vec.of(0, 0, 0)
+    if isinstance(a, MaterialColor):
+        return ScaledMaterialColor(a, b) if b else a
+    if a or b:
+        # MaterialColor.coerce(a, b) with a undefined and b a Vec -> Solid(b)
+        return MaterialColor.coerce2(a, b) if b is not None else MaterialColor.coerce(a)
+    return MaterialColor.coerce(default)
+
+
+def _make_material(d):
+    ambient = _make_material_color(d.get("map_Ka"), d.get("Ka"))
+    diffuse = _make_material_color(d.get("map_Kd"), d.get("Kd"))
+    specular = _make_material_color(d.get("map_Ks"), d.get("Ks"))
+    smoothness = d.get("Ns") or 0
+    # src/objloader.js:16-19 constructs the Fresnel/path material without
+    # returning it; every MTL material is a PhongMaterial.
+    return PhongMaterial(Vec.of(1, 1, 1), ambient, diffuse, specular, smoothness)
+
+
+def parse_mtl_text(text: str):
+    ret, curr, name = {}, None, None
+    for l in text.split("\n"):
+        if _SKIP.match(l):
+            continue
+        t = re.findall(r"\S+", l)
+        if t[0] == "newmtl":
+            if curr is not None:        # `if (curr)`: {} is truthy in JS
+                ret[name] = _make_material(curr)
+            name, curr = t[1], {}
+            continue
+        vals = [t[0]] + [(_parse_float(x) if _parse_float(x) == _parse_float(x) else x) for x in t[1:]]
+        if vals[0] in ("Ka", "Kd", "Ks", "Ke", "Tf"):
+            curr[vals[0]] = Vec.of(vals[1], vals[2], vals[3])
+        elif vals[0] in ("Ns", "Ni", "illum", "d", "Tr"):
+            curr[vals[0]] = vals[1]
+        elif vals[0] in ("map_Ka", "map_Kd", "map_Ks"):
+            raise NotImplementedError("TextureMaterialColor (src/materials.js:77-131) is SURVEY §8(f) 'next'")
+        else:
+            raise ValueError("Unsupported material parameter: " + vals[0])
+    if curr is not None:
+        ret[name] = _make_material(curr)
+    return ret
+
+
+def loadObjFile(filename, defaultMaterial=None, transform=None, minArea=0.00001):
+    """src/objloader.js:240-247 (synchronous; returns the Primitive list)."""
+    with open(filename, "r", encoding="utf8") as fh:
+        text = fh.read()
+    parsed = parse_obj_text(text)
+    prefix = filename[: filename.rfind("/") + 1] if filename.rfind("/") > 0 else ""
+    materials = {}
+    for lib in parsed.mtllibs:
+        with open(prefix + lib, "r", encoding="utf8") as fh:
+            materials.update(parse_mtl_text(fh.read()))
+    return triangles_from_parsed(parsed, defaultMaterial, transform, minArea, materials)

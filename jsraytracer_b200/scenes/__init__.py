@@ -1,0 +1,359 @@
+"""Transcriptions of the reference's demo scenes (reference: tests/*/test.mjs).
+
+Each function mirrors one `configureTest(callback)` and returns the object the
+reference passes to the callback: `{renderer, width, height}`.  The only
+additions are keyword overrides the BASELINE configs need (SURVEY.md §8:
+1920x1080 needs `aspect=16/9`; spp / resolution / camera overrides) and a
+`renderer_cls` hook so the same scene can be bound to `CUDARenderer`.
+
+Meshes come from `scenes/data/*.npz` — arrays derived from the reference's OBJ
+assets by tools/import_reference_assets.py (the assets themselves are not on
+the GPU box).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+from ..jsmath import Vec, Mat, Mat4
+from ..geometry import Plane, UnitBox, Sphere, Square, Circle, Cylinder, Triangle
+from ..sdf import (SDFGeometry, UnionSDF, IntersectionSDF, DifferenceSDF, SmoothUnionSDF, SmoothIntersectionSDF,
+                   SmoothDifferenceSDF, RoundSDF, SphereSDF, BoxSDF, TetrahedronSDF, TransformSDF,
+                   RecursiveTransformUnionSDF, SDFTransformerSequence, SDFRecursiveTransformer,
+                   SDFMatrixTransformer, SDFReflectionTransformer, SDFInfiniteRepetitionTransformer)
+from ..materials import (CheckerboardMaterialColor, PhongMaterial, FresnelPhongMaterial, PhongPathTracingMaterial,
+                         SimplePointLight, RandomSampleAreaLight)
+from ..world import World, Primitive, Aggregate, BVHAggregate
+from ..cameras import PerspectiveCamera, DepthOfFieldPerspectiveCamera
+from ..renderers import SimpleRenderer, IncrementalMultisamplingRenderer
+from ..objloader import ParsedObj, triangles_from_parsed
+
+PI = math.pi
+INF = math.inf
+DATA_DIR = os.path.join(os.path.dirname(__file__), "data")
+
+
+def load_mesh(name, defaultMaterial=None, transform=None, minArea=0.00001):
+    """`loadObjFile("../assets/<name>.obj", ...)` (src/objloader.js:240-247)."""
+    parsed = ParsedObj.load(os.path.join(DATA_DIR, name + ".npz"))
+    return triangles_from_parsed(parsed, defaultMaterial, transform, minArea)
+
+
+def _boxball_camera_transform():
+    return (Mat4.identity().times(Mat4.translation([-6, 1, 0]))
+            .times(Mat4.rotation(-0.6, Vec.of(0, 1, 0)))
+            .times(Mat4.rotation(-0.2, Vec.of(1, 0, 0))))
+
+
+def _make_camera(transform, aspect, dof):
+    if dof:
+        return DepthOfFieldPerspectiveCamera(PI / 4, aspect, transform, dof[0], dof[1])
+    return PerspectiveCamera(PI / 4, aspect, transform)
+
+
+def _finish(objects, lights, camera, renderer_cls, spp, depth, width, height, bg=None):
+    world = World(objects, lights) if bg is None else World(objects, lights, bg)
+    if renderer_cls is SimpleRenderer:
+        renderer = SimpleRenderer(world, camera, depth)
+    else:
+        renderer = renderer_cls(world, camera, spp, depth)
+    return {"renderer": renderer, "width": width, "height": height}
+
+
+def _checker_floor(material_cls, args, y=-1):
+    return Primitive(Plane(), material_cls(*args),
+                     Mat4.translation([0, y, 0]).times(Mat4.rotation(PI / 2, Vec.of(1, 0, 0))))
+
+
+def _point_light_default():
+    return [SimplePointLight(Vec.of(10, 7, 10, 1), Vec.of(1, 1, 1), 5000)]
+
+
+# tests/BoxBall/test.mjs ------------------------------------------------------
+def BoxBall(aspect=1, width=600, height=600, spp=16, depth=4, dof=None,
+            renderer_cls=IncrementalMultisamplingRenderer):
+    camera = _make_camera(_boxball_camera_transform(), aspect, dof)
+    objects = [
+        _checker_floor(PhongMaterial, (CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0, 0, 0)),
+                                       0.1, 0.4, 0.6, 100, 0.5)),
+        Primitive(UnitBox(), PhongMaterial(Vec.of(1, 0, 0), 0.2, 0.4, 0.6, 100, 0.5),
+                  Mat4.translation([1.2, 0.2, -7, 1]).times(Mat4.scale(2))),
+        Primitive(Sphere(), PhongMaterial(Vec.of(0, 0, 1), 0.2, 0.4, 0.6, 100, 0.5),
+                  Mat4.translation([-2, 0.3, -9])),
+    ]
+    return _finish(objects, _point_light_default(), camera, renderer_cls, spp, depth, width, height)
+
+
+# tests/BoxBall_DOF/test.mjs ---------------------------------------------------
+def BoxBall_DOF(aspect=1, width=600, height=600, spp=64, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    return BoxBall(aspect, width, height, spp, depth, dof=(9.2, 0.2), renderer_cls=renderer_cls)
+
+
+# tests/BoxBall_path/test.mjs --------------------------------------------------
+def BoxBall_path(aspect=1, width=600, height=600, spp=128, depth=4, dof=None,
+                 renderer_cls=IncrementalMultisamplingRenderer):
+    camera = _make_camera(_boxball_camera_transform(), aspect, dof)
+    objects = [
+        _checker_floor(PhongPathTracingMaterial, (CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0, 0, 0)),
+                                                  0.1, 0.4, 0.6, 10)),
+        Primitive(UnitBox(), PhongPathTracingMaterial(Vec.of(1, 0, 0), 0.2, 0.4, 0.6, 10000),
+                  Mat4.translation([1.2, 0.2, -7, 1]).times(Mat4.scale(2))),
+        Primitive(Sphere(), PhongPathTracingMaterial(Vec.of(0, 0, 1), 0.2, 0.4, 0.6, 100),
+                  Mat4.translation([-2, 0.3, -9])),
+    ]
+    return _finish(objects, _point_light_default(), camera, renderer_cls, spp, depth, width, height)
+
+
+# tests/ASimpleScene/test.mjs --------------------------------------------------
+def ASimpleScene(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([0.5, -0.5, 4]))
+    lights = [SimplePointLight(Vec.of(10, 7, 10, 1), Vec.of(1, 1, 1), 10000)]
+    X, Y = Vec.of(1, 0, 0), Vec.of(0, 1, 0)
+    objects = [
+        Primitive(Plane(), PhongMaterial(Vec.of(0.5, 0.5, 0.5), 0.1, 0.4, 0.6, 100, 0.5),
+                  Mat4.translation([0, -1, 0]).times(Mat4.rotation(PI / 2, X))),
+        Primitive(UnitBox(), PhongMaterial(Vec.of(1, 0.1, 0.1), 0.2, 0.4, 0.6, 100, 0.5),
+                  Mat4.translation([0.75, 0.4, -7]).times(Mat4.rotation(0.35, Y)).times(Mat4.scale(2.5))),
+        Primitive(Sphere(), PhongMaterial(Vec.of(0.1, 0.1, 1), 0.2, 0.4, 0.6, 100, 0.5),
+                  Mat4.translation([-2.7, 1.3, -10]).times(Mat4.scale(2))),
+        Primitive(Cylinder(), PhongMaterial(Vec.of(0.1, 0.8, 0.1), 0.1, 0.3, 0.4, 100, 0.5),
+                  Mat4.translation([2.55, -0.1, -3]).times(Mat4.rotation(PI / 2, X)).times(Mat4.scale(0.75))),
+        Primitive(Circle(), PhongMaterial(Vec.of(1, 1, 1), 0.2, 0.4, 0.6, 100, 0.5),
+                  Mat4.translation([2.55, 1.5, -4]).times(Mat4.rotation(-0.2, Y)).times(Mat4.rotation(0.6, X))
+                  .times(Mat4.scale(1))),
+        Primitive(Square(), PhongMaterial(Vec.of(1, 0.1, 1), 0.2, 0.4, 0.6, 100, 0.5),
+                  Mat4.translation([0.7, 6.3, -20]).times(Mat4.rotation(0.4, X)).times(Mat4.rotation(0, Y))
+                  .times(Mat4.scale(6))),
+    ]
+    return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+# tests/spheres010/test.mjs ----------------------------------------------------
+def spheres010(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([-7, 0.5, 4]))
+    lights = [SimplePointLight(Vec.of(10, 7, 10, 1), Vec.of(1, 1, 1), 10000)]
+    objects = [Primitive(Plane(), PhongMaterial(Vec.of(0.5, 0.5, 0.5), 0.1, 0.4, 0.6, 100, 0.5),
+                         Mat4.translation([0, -6, 0]).times(Mat4.rotation(PI / 2, Vec.of(1, 0, 0))))]
+    for i in range(5):
+        for j in range(2):
+            for k in range(1):
+                objects.append(Primitive(Sphere(), PhongMaterial(Vec.of(0.1, 0.1, 1), 0.2, 0.4, 0.6, 100, 0.5),
+                                         Mat4.translation([-11 + 2 * i, -3.7 + 2 * j, -12 - 2 * k])))
+    return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+# tests/refraction_path/test.mjs -----------------------------------------------
+def refraction_path(aspect=1, width=600, height=600, spp=256, depth=7, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.identity().times(Mat4.translation([-7, 1.5, 0]))
+                               .times(Mat4.rotation(-0.6, Vec.of(0, 1, 0))).times(Mat4.rotation(-0.15, Vec.of(1, 0, 0))))
+    lights = [SimplePointLight(Vec.of(-3, 10, -4, 1), Vec.of(1, 1, 1), 300),
+              SimplePointLight(Vec.of(3, 10, -20, 1), Vec.of(1, 1, 1), 10000)]
+    objects = [
+        # (the reference passes an 8th argument, 1.0, that the constructor ignores)
+        _checker_floor(PhongPathTracingMaterial, (CheckerboardMaterialColor(Vec.of(0.8, 0.8, 0.8), Vec.of(0.5, 0.5, 0.5)),
+                                                  0.01, 0.8, 0, 0, INF, 0)),
+        Primitive(Sphere(), PhongPathTracingMaterial(Vec.of(0.827, 0.412, 0.424), 0.1, 0.2, 0.9, 100, 1.3, 1.0),
+                  Mat4.translation([-2.5, 0, -5.5])),
+        Primitive(Sphere(), PhongPathTracingMaterial(Vec.of(0.255, 0.506, 0.498), 0.1, 0.2, 0.9, 100, 1.3, 1.0),
+                  Mat4.translation([-2, 1, -11]).times(Mat4.scale(2))),
+        Primitive(Sphere(), PhongPathTracingMaterial(Vec.of(0.655, 0.78, 0.388), 0.1, 0.2, 0.9, 100, 1.3, 1.0),
+                  Mat4.translation([4, 2, -12]).times(Mat4.scale(3))),
+    ]
+    return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height, bg=Vec.of(0.5, 0.5, 0.5))
+
+
+# tests/refraction/test.mjs ----------------------------------------------------
+def refraction(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.identity().times(Mat4.translation([-7, 1.5, 0]))
+                               .times(Mat4.rotation(-0.6, Vec.of(0, 1, 0))).times(Mat4.rotation(-0.15, Vec.of(1, 0, 0))))
+    lights = [SimplePointLight(Vec.of(-1, 100, -3, 1), Vec.of(1, 1, 1), 150000),
+              SimplePointLight(Vec.of(3, 3, -20, 1), Vec.of(1, 1, 1), 1000)]
+    objects = [
+        _checker_floor(PhongMaterial, (CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0.5, 0.5, 0.5)),
+                                       0.1, 0.4, 0.6, 2, 0.5)),
+        Primitive(Sphere(), FresnelPhongMaterial(Vec.of(0.827, 0.412, 0.424), 0.1, 0.4, 0.9, 100, 1.3),
+                  Mat4.translation([-3, 0, -5])),
+        Primitive(Sphere(), FresnelPhongMaterial(Vec.of(0.255, 0.506, 0.498), 0.1, 0.4, 0.9, 100, 1.3),
+                  Mat4.translation([-2, 1, -10]).times(Mat4.scale(2))),
+        Primitive(Sphere(), FresnelPhongMaterial(Vec.of(0.655, 0.78, 0.388), 0.1, 0.4, 0.9, 100, 1.3),
+                  Mat4.translation([5, 2, -12]).times(Mat4.scale(3))),
+    ]
+    return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height, bg=Vec.of(0.5, 0.5, 0.5))
+
+
+# tests/cornell_box_path/test.mjs ----------------------------------------------
+def cornell_box_path(aspect=1, width=600, height=600, spp=128, depth=8, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([0, 5, 15]))
+    X, Y = Vec.of(1, 0, 0), Vec.of(0, 1, 0)
+    lights = [RandomSampleAreaLight(Square(), Mat4.translation([0, 10, 0]).times(Mat4.rotation(-PI / 2, X))
+                                    .times(Mat4.scale([1, 1, 1])), Vec.of(1, 1, 1), 2000, 4)]
+    PT = PhongPathTracingMaterial
+    objects = [
+        Primitive(Plane(), PT(CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0.1, 0.1, 0.1)), 0, 0.4, 0.4, 10),
+                  Mat4.rotation(PI / 2, X)),
+        Primitive(Square(), PT(Vec.of(1, 1, 1), 0, 0.4), Mat4.translation([0, 5, -5]).times(Mat4.scale([10, 10, 1]))),
+        Primitive(Square(), PT(Vec.of(1, 0.1, 0.1), 0, 0.4),
+                  Mat4.translation([5, 5, 0]).times(Mat4.scale([1, 10, 10])).times(Mat4.rotation(PI / 2, Y))),
+        Primitive(Square(), PT(Vec.of(0.1, 1, 0.1), 0, 0.4),
+                  Mat4.translation([-5, 5, 0]).times(Mat4.scale([1, 10, 10])).times(Mat4.rotation(-PI / 2, Y))),
+    ]
+    ceilingmaterial = PT(Vec.of(1, 1, 1), 0, 0.4)
+    ceiling_thickness = 1
+    cto = 10 + (ceiling_thickness - 1) / 2
+    objects += [
+        Primitive(Square(), ceilingmaterial, Mat4.translation([0, 10 + ceiling_thickness / 2, 0])
+                  .times(Mat4.scale([2, 1, 2])).times(Mat4.rotation(PI / 2, X))),
+        Primitive(UnitBox(), ceilingmaterial, Mat4.translation([0, cto, 3]).times(Mat4.scale([10, ceiling_thickness, 4]))),
+        Primitive(UnitBox(), ceilingmaterial, Mat4.translation([0, cto, -3]).times(Mat4.scale([10, ceiling_thickness, 4]))),
+        Primitive(UnitBox(), ceilingmaterial, Mat4.translation([3, cto, 0]).times(Mat4.scale([4, ceiling_thickness, 2]))),
+        Primitive(UnitBox(), ceilingmaterial, Mat4.translation([-3, cto, 0]).times(Mat4.scale([4, ceiling_thickness, 2]))),
+        Primitive(Sphere(), PT(Vec.of(1, 1, 1), 0, 0.1, 0.8, 10), Mat4.translation([1.75, 2, -1]).times(Mat4.scale(2))),
+        Primitive(Sphere(), PT(Vec.of(1, 1, 1), 0, 0.1, 0.9, 10, 2), Mat4.translation([-3, 1.2, 1.5])),
+        Primitive(UnitBox(), PT(Vec.of(0.1, 0.1, 1), 0, 0.9),
+                  Mat4.translation([-2, 4, -2]).times(Mat4.rotation(-PI / 4, Y)).times(Mat4.scale([2, 8, 2]))),
+    ]
+    return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+# tests/bunny_path/test.mjs, tests/bunny/test.mjs --------------------------------
+def _bunny_camera(aspect):
+    return PerspectiveCamera(PI / 4, aspect, Mat4.translation([0, 2, 0]).times(Mat4.rotation(-0.2, Vec.of(1, 0, 0))))
+
+
+def bunny_path(aspect=1, width=600, height=600, spp=128, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = _bunny_camera(aspect)
+    lights = [SimplePointLight(Vec.of(-15, 5, 12, 1), Vec.of(1, 1, 1), 5000),
+              SimplePointLight(Vec.of(1, 5, -8, 1), Vec.of(0.8, 0.8, 1), 5000)]
+    objs = [_checker_floor(PhongPathTracingMaterial,
+                           (CheckerboardMaterialColor(Vec.of(0.8, 0.8, 0.8), Vec.of(0.2, 0.2, 0.2)), 0.3, 0.4, 0.6, 100),
+                           y=1)]
+    triangles = load_mesh("bunny2", FresnelPhongMaterial(Vec.of(0.8, 1, 0.8), 0.1, 0.4, 0.6, 10, 1.3))
+    objs.append(BVHAggregate.build(triangles, Mat4.translation([-0.6, 1, -4])))
+    return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+def bunny(aspect=1, width=600, height=600, spp=1, depth=4, renderer_cls=SimpleRenderer):
+    camera = _bunny_camera(aspect)
+    lights = [SimplePointLight(Vec.of(-15, 5, 12, 1), Vec.of(1, 1, 1), 5000),
+              SimplePointLight(Vec.of(1, 5, -8, 1), Vec.of(0.8, 0.8, 1), 1000)]
+    objs = [_checker_floor(PhongMaterial, (CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0, 0, 0)),
+                                           0.3, 0.4, 0.6, 100, 0.5), y=1)]
+    triangles = load_mesh("bunny2", FresnelPhongMaterial(Vec.of(0.8, 1, 0.8), 0.1, 0.4, 0.6, 10, 1.3))
+    objs.append(BVHAggregate.build(triangles, Mat4.translation([-0.6, 1, -4])))
+    return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+# tests/dragon/test.mjs ----------------------------------------------------------
+def dragon(aspect=1, width=600, height=600, spp=8, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = _bunny_camera(aspect)
+    lights = [SimplePointLight(Vec.of(-15, 10, 12, 1), Vec.of(1, 1, 1), 5000)]
+    objs = [_checker_floor(PhongMaterial, (CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0, 0, 0)),
+                                           0.3, 0.4, 0.6, 100, 0.5), y=1)]
+    triangles = load_mesh("dragon", PhongMaterial(Vec.of(0.3884335160255432, 1, 0.8839936256408691),
+                                                  0.01, 0.8, 0.2, 32, 0.5))
+    objs.append(BVHAggregate.build(triangles, Mat4.translation([0, 1, -4]).times(Mat4.rotation(0.3, Vec.of(0, 1, 0)))
+                                   .times(Mat4.scale(0.175))))
+    return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height, bg=Vec.of(0, 0, 0))
+
+
+# tests/AHollowTetrahedron/test.mjs (shared kdtree between two BVHAggregates) ----
+def AHollowTetrahedron(aspect=1, width=600, height=600, spp=1, depth=4, renderer_cls=SimpleRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.identity())
+    lights = [SimplePointLight(Vec.of(10, 5, 10, 1), Vec.of(1, 0.87, 0), 5000)]
+    objects = [Primitive(Plane(), PhongMaterial(Vec.of(0.7, 0.7, 1), 0.1, 0.4, 0.6, 100, 0.2),
+                         Mat4.translation([0, -1, 0]).times(Mat4.rotation(PI / 2, Vec.of(1, 0, 0))))]
+    trans1 = Mat4.translation([0.5, -1.5, -5]).times(Mat4.rotation(0.3, Vec.of(0, 1, 0))).times(Mat4.scale(0.3))
+    trans2 = Mat4.translation([0.5, -1.5, -8]).times(Mat4.rotation(-0.5, Vec.of(0, 1, 0))).times(Mat4.scale(0.3))
+    triangles = load_mesh("hollow_tetrahedron", PhongMaterial(Vec.of(1, 0.7, 0.7), 0.1, 0.4, 0.6, 100, 0.4))
+    bvh1 = BVHAggregate.build(triangles, trans1)
+    bvh2 = BVHAggregate(triangles, bvh1.kdtree, trans2)
+    objects += [bvh1, bvh2]
+    return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+# tests/SDF_*/test.mjs -------------------------------------------------------------
+def _sdf_scene(sdf_prims, aspect, width, height, spp, depth, dof, renderer_cls):
+    camera = _make_camera(_boxball_camera_transform(), aspect, dof)
+    objects = [_checker_floor(PhongMaterial, (CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0, 0, 0)),
+                                              0.1, 0.4, 0.6, 100, 0.5))] + sdf_prims
+    return _finish(objects, _point_light_default(), camera, renderer_cls, spp, depth, width, height)
+
+
+def SDF_Simple(aspect=1, width=600, height=600, spp=16, depth=4, dof=None, renderer_cls=IncrementalMultisamplingRenderer):
+    prim = Primitive(SDFGeometry(SphereSDF(), 100000, 0.0001, 100000),
+                     PhongMaterial(Vec.of(0.1, 0.1, 1), 0.2, 0.4, 0.6, 100, 0.5), Mat4.translation([-2, 0.3, -9]))
+    return _sdf_scene([prim], aspect, width, height, spp, depth, dof, renderer_cls)
+
+
+def SDF_BoxBall(aspect=1, width=600, height=600, spp=16, depth=4, dof=None, renderer_cls=IncrementalMultisamplingRenderer):
+    prim = Primitive(SDFGeometry(UnionSDF(
+        TransformSDF(BoxSDF(1, Vec.of(1, 0.1, 0.1)), SDFMatrixTransformer(Mat4.translation([1.2, 0.2, -7]))),
+        TransformSDF(SphereSDF(1, Vec.of(0.1, 0.1, 1)), SDFMatrixTransformer(Mat4.translation([-2, 0.3, -9])))),
+        128, 0.00001, 100), PhongMaterial(Vec.of(1, 1, 1), 0.2, 0.4, 0.6, 100, 0.5))
+    return _sdf_scene([prim], aspect, width, height, spp, depth, dof, renderer_cls)
+
+
+def SDF_Combinations(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.identity().times(Mat4.translation([-6, 5, 0]))
+                               .times(Mat4.rotation(-0.61, Vec.of(0, 1, 0))).times(Mat4.rotation(-0.37, Vec.of(1, 0, 0))))
+    objects = [_checker_floor(PhongMaterial, (CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0, 0, 0)),
+                                              0.1, 0.4, 0.6, 100, 0.5))]
+    box = TransformSDF(BoxSDF(Vec.of(1, 0.5, 1), Vec.of(0.1, 0.1, 1)), SDFMatrixTransformer(Mat4.translation([0, 0.2, 0])))
+    ball = TransformSDF(SphereSDF(0.75, Vec.of(1, 0.1, 0.1)), SDFMatrixTransformer(Mat4.translation([0, 0.7, 0])))
+    mat = lambda: PhongMaterial(Vec.of(1, 1, 1), 0.2, 0.4, 0.6, 100, 0.5)
+    for cls, pos in ((UnionSDF, [2, 0, -7]), (IntersectionSDF, [-0.5, 0, -7]), (DifferenceSDF, [-3, 0, -7]),
+                     (SmoothUnionSDF, [2, 3, -7]), (SmoothIntersectionSDF, [-0.5, 3, -7]),
+                     (SmoothDifferenceSDF, [-3, 3, -7])):
+        objects.append(Primitive(SDFGeometry(cls(box, ball), 128, 0.00001, 100), mat(), Mat4.translation(pos)))
+    return _finish(objects, _point_light_default(), camera, renderer_cls, spp, depth, width, height)
+
+
+def SDF_Menger(aspect=1, width=600, height=600, spp=16, depth=4, dof=None, renderer_cls=IncrementalMultisamplingRenderer):
+    scale = 3
+    prim = Primitive(
+        SDFGeometry(
+            DifferenceSDF(
+                BoxSDF(1),
+                RecursiveTransformUnionSDF(
+                    UnionSDF(BoxSDF(Vec.of(INF, 1 / scale, 1 / scale)),
+                             BoxSDF(Vec.of(1 / scale, INF, 1 / scale)),
+                             BoxSDF(Vec.of(1 / scale, 1 / scale, INF))),
+                    SDFTransformerSequence(SDFMatrixTransformer(Mat4.scale(1 / scale)),
+                                           SDFInfiniteRepetitionTransformer(Vec.of(2, 2, 2))),
+                    6)),
+            300, 0.00001, 100),
+        PhongMaterial(Vec.of(0.1, 0.1, 1), 0.2, 0.4, 0.6, 100, 0.15),
+        Mat4.translation([-3.5, 0.5, -3.5]).times(Mat4.rotationY(-0.15)))
+    return _sdf_scene([prim], aspect, width, height, spp, depth, dof, renderer_cls)
+
+
+def SDF_Sierpinski(aspect=1, width=600, height=600, spp=16, depth=4, dof=None,
+                   renderer_cls=IncrementalMultisamplingRenderer):
+    tv = TetrahedronSDF.vertices[0]
+    prim = Primitive(
+        SDFGeometry(
+            TransformSDF(
+                TetrahedronSDF(),
+                SDFRecursiveTransformer(
+                    SDFTransformerSequence(
+                        SDFMatrixTransformer(Mat4.translation(tv).times(Mat4.scale(0.5))
+                                             .times(Mat4.translation(tv.times(-1)))),
+                        *[SDFReflectionTransformer(tv.minus(TetrahedronSDF.vertices[i]), TetrahedronSDF.vertices[i])
+                          for i in (1, 2, 3)]),
+                    10)),
+            300, 0.001, 100),
+        PhongMaterial(Vec.of(0.1, 0.1, 1), 0.2, 0.4, 0.6, 100, 0.15),
+        Mat4.translation([-4.25, 0.5, -2.5]).times(Mat4.rotationY(1.0)).times(Mat4.rotationX(-1.5))
+        .times(Mat4.scale(0.75)))
+    return _sdf_scene([prim], aspect, width, height, spp, depth, dof, renderer_cls)
+
+
+REGISTRY = {f.__name__: f for f in (
+    BoxBall, BoxBall_DOF, BoxBall_path, ASimpleScene, spheres010, refraction, refraction_path, cornell_box_path,
+    bunny, bunny_path, dragon, AHollowTetrahedron, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
+    SDF_Sierpinski)}
+
+
+def configure(name, **overrides):
+    """`import(test.mjs).configureTest(cb)`: returns `{renderer, width, height}`."""
+    return REGISTRY[name](**overrides)

@@ -1,0 +1,134 @@
+"""TEST INFRASTRUCTURE — ctypes wrapper of the CPU restatement oracle
+(oracle/oracle.cpp).  Import only from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  PARITY UNPINNED (see
+oracle_math.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+COUNTER_NAMES = ["rays_primary", "rays_secondary", "rays_shadow",
+                 "bvh_nodes_primary", "bvh_nodes_secondary", "bvh_nodes_shadow",
+                 "bvh_prims_primary", "bvh_prims_secondary", "bvh_prims_shadow",
+                 "top_tests_primary", "top_tests_secondary", "top_tests_shadow",
+                 "sdf_evals_primary", "sdf_evals_secondary", "sdf_evals_shadow", "shaded_hits"]
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_load.restype = C.c_void_p
+        L.orc_load.argtypes = [C.c_char_p, C.c_size_t]
+        L.orc_free.argtypes = [C.c_void_p]
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_primary_hits.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_resolve_rgba8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_kat_intersect.restype = C.c_double
+        L.orc_kat_intersect.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+        L.orc_kat_material_data.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_kat_fresnel.restype = C.c_double
+        L.orc_kat_fresnel.argtypes = [C.c_double, C.c_double, C.c_int, C.c_void_p]
+        L.orc_kat_fmod.restype = C.c_double
+        L.orc_kat_fmod.argtypes = [C.c_double, C.c_double]
+        L.orc_kat_rng.restype = C.c_double
+        L.orc_kat_rng.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.orc_sdf_probe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_cast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def default_threads():
+    return max(1, len(os.sched_getaffinity(0)))
+
+
+class OracleScene:
+    """A scene loaded from the serializer wire format (JSON text)."""
+
+    def __init__(self, json_text):
+        if isinstance(json_text, str):
+            json_text = json_text.encode("utf8")
+        self._L = lib()
+        self._h = self._L.orc_load(json_text, len(json_text))
+        if not self._h:
+            raise RuntimeError("oracle: " + self._L.orc_last_error().decode())
+        info = (C.c_int * 8)()
+        self._L.orc_info(self._h, info)
+        (self.width, self.height, self.samplesPerPixel, self.maxRecursionDepth, self.nprims, self.jitter,
+         self.nlights, self.ntop) = list(info)
+
+    def close(self):
+        if self._h:
+            self._L.orc_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def primary_hits(self, width=None, height=None, threads=None):
+        W, H = width or self.width, height or self.height
+        ids = np.empty(W * H, dtype=np.int32)
+        t = np.empty(W * H, dtype=np.float64)
+        cnt = np.zeros(16, dtype=np.uint64)
+        rc = self._L.orc_primary_hits(self._h, W, H, ids.ctypes.data, t.ctypes.data, threads or default_threads(),
+                                      cnt.ctypes.data)
+        if rc:
+            raise RuntimeError("oracle: " + self._L.orc_last_error().decode())
+        return ids.reshape(H, W), t.reshape(H, W), dict(zip(COUNTER_NAMES, cnt.tolist()))
+
+    def render(self, n_passes, first_pass=0, seed=1, jitter=True, x_offset=0, x_delt=1, width=None, height=None,
+               threads=None, accum=None):
+        """Returns (sum buffer (H,W,3) f32, counters dict)."""
+        W, H = width or self.width, height or self.height
+        if accum is None:
+            accum = np.zeros((H, W, 3), dtype=np.float32)
+        cnt = np.zeros(16, dtype=np.uint64)
+        rc = self._L.orc_render(self._h, W, H, first_pass, n_passes, seed, 0 if jitter else 1, x_offset, x_delt,
+                                accum.ctypes.data, threads or default_threads(), cnt.ctypes.data)
+        if rc:
+            raise RuntimeError("oracle: " + self._L.orc_last_error().decode())
+        return accum, dict(zip(COUNTER_NAMES, cnt.tolist()))
+
+    def sdf_probe(self, prim_id, p):
+        p = np.asarray(p, dtype=np.float64)
+        dist = C.c_double()
+        out = np.zeros(8, dtype=np.float64)
+        rc = self._L.orc_sdf_probe(self._h, prim_id, p.ctypes.data, C.byref(dist), out.ctypes.data)
+        if rc:
+            raise RuntimeError("oracle: " + self._L.orc_last_error().decode())
+        return dist.value, out
+
+    def cast(self, o, d, min_d=0.0, max_d=float("inf"), shadow=False):
+        o = np.asarray(o, dtype=np.float64)
+        d = np.asarray(d, dtype=np.float64)
+        t = C.c_double()
+        pid = self._L.orc_cast(self._h, o.ctypes.data, d.ctypes.data, min_d, max_d, int(shadow), C.byref(t))
+        return pid, t.value
+
+
+def resolve_rgba8(accum, passes):
+    H, W, _ = accum.shape
+    out = np.zeros((H, W, 4), dtype=np.uint8)
+    a = np.ascontiguousarray(accum, dtype=np.float32)
+    lib().orc_resolve_rgba8(a.ctypes.data, H * W, passes, out.ctypes.data)
+    return out
