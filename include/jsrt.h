@@ -1,0 +1,148 @@
+/* libjsrt — C ABI of the B200-native render path for alitteneker/jsraytracer.
+ *
+ * The reference has no FFI or plugin interface: its render
+ * path is `renderer.render(img, timelimit, callback, x_offset, x_delt)`
+ * (src/renderers.js:10,70) called from a web worker (src/worker.js:30-32) that
+ * then posts `img.imgdata` back (src/worker.js:31,37).  A `CUDARenderer` class
+ * next to those renderers binds the entry points below (N-API addon under Node,
+ * ctypes in this repository's Python host mirror); INTEGRATION.md shows both.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host
+ * buffer; the library owns device memory behind the opaque handles.  Functions
+ * returning int return 0 on success and non-zero on failure, with the message
+ * available from jsrt_last_error() on the calling thread (the reference's
+ * convention is `throw "<string>"`, e.g. src/aggregates.js:39; the binding turns
+ * the message into a thrown Error).  A scene handle must be used from one
+ * thread at a time.  There is no CPU fallback: every entry point that renders
+ * fails if no CUDA device is present.
+ */
+#ifndef JSRT_H
+#define JSRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JSRT_FORMAT_JSON 0      /* JSON.stringify(new Serializer(test).plain())   tests/test_to_json.js:36 */
+#define JSRT_FORMAT_MSGPACK 1   /* msgpack.encode(plain)                          tests/test_to_json.js:38 */
+
+/* jsrt_render flags */
+#define JSRT_FLAG_NO_JITTER 1   /* SimpleRenderer sampling: pixel corner, no jitter (src/renderers.js:21-25) */
+
+typedef struct jsrt_scene jsrt_scene;
+
+/* Number of CUDA devices visible to the process (0 if none / no driver). */
+int jsrt_device_count(void);
+
+/* Replaces: worker.js:23-26 (each worker rebuilding the scene from test.mjs).
+ * Parses the serializer blob `{renderer:{world,camera,maxRecursionDepth
+ * [,samplesPerPixel]},width,height}` (src/serializer.js:4-63), flattens it
+ * (BVH nodes in reference visit order, triangle constants, material / light
+ * tables, SDF bytecode) and uploads it to device `devices[0]`.  One process
+ * drives one GPU (multi-GPU = one process per GPU, scene replicated, passes
+ * sharded); ndev must be 1.  Returns NULL on failure. */
+jsrt_scene* jsrt_scene_create(const uint8_t* blob, size_t len, int format, const int* devices, int ndev);
+
+/* Parse + flatten only (no CUDA calls): lets hosts without a GPU validate a
+ * blob.  Rendering calls on such a handle fail. */
+jsrt_scene* jsrt_scene_create_host(const uint8_t* blob, size_t len, int format);
+
+void jsrt_scene_destroy(jsrt_scene*);
+
+/* Re-uploads the flattened scene arrays host->device (what a second scene of
+ * the same size would cost); used by the end-to-end benchmark leg. */
+int jsrt_scene_upload(jsrt_scene*);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*) for all work of
+ * this scene; NULL restores the scene's own stream. */
+int jsrt_scene_set_stream(jsrt_scene*, void* cuda_stream);
+
+/* Replaces: IncrementalMultisamplingRenderer.render's pass / column / row loops
+ * (src/renderers.js:87-98) and SimpleRenderer.render (:21-26).
+ * Renders passes [first_pass, first_pass + n_passes) of every pixel whose
+ * column px satisfies px >= x_offset && (px - x_offset) % x_delt == 0 (the
+ * web-worker striping, src/renderers.js:21,88) and adds the samples into the
+ * HBM-resident accumulation buffer.  `seed` keys the counter-based RNG that
+ * stands in for Math.random().  Asynchronous on the scene's stream. */
+int jsrt_render(jsrt_scene*, int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags);
+
+/* Zeroes the accumulation buffer and the pass counter (`buffer` in src/renderers.js:81-86). */
+int jsrt_reset_accum(jsrt_scene*);
+
+/* Blocks until all queued work of this scene has finished. */
+int jsrt_synchronize(jsrt_scene*);
+
+/* Replaces: PixelBuffer.setColor on `buffer[px][py].times(1/(iter+1))`
+ * (src/renderers.js:98, src/pixelbuffer.js:39-49): out[(y*W+x)*4+c] =
+ * round(255*clamp(sum/passes, 0, 1)), alpha 255; pixels never rendered
+ * (column striping) are written as 0,0,0,0 like a fresh ImageData.
+ * `out` holds W*H*4 bytes.  Synchronous (device->host copy). */
+int jsrt_resolve_rgba8(jsrt_scene*, uint8_t* out);
+
+/* Reads the raw accumulation buffer: out = W*H*4 floats (sum r, g, b, sample
+ * count per pixel); *passes = passes accumulated since the last reset. */
+int jsrt_read_accum(jsrt_scene*, float* out, int* passes);
+
+/* Device pointer of the W*H float4 accumulation buffer (for NCCL reductions
+ * across GPUs issued by the host process). */
+void* jsrt_accum_device_ptr(jsrt_scene*);
+/* Adds `passes` to the pass counter after the host reduced other GPUs' buffers into this one. */
+int jsrt_add_passes(jsrt_scene*, int passes);
+
+/* Parity probe: un-jittered pinhole/DOF-less primary rays through every pixel
+ * (SimpleRenderer sampling); prim_id[y*W+x] = index of the hit Primitive in a
+ * depth-first walk of world.objects descending into Aggregate.objects (-1 =
+ * miss), t = hit distance in ray-parameter units. */
+int jsrt_primary_hits(jsrt_scene*, int32_t* prim_id, float* t);
+
+typedef struct jsrt_info {
+    int width, height, samples_per_pixel, max_depth;
+    int jitter;                 /* renderer class samples with jitter */
+    int n_top, n_prims, n_ext_prims, n_nodes, n_tris, n_materials, n_lights, n_sdfs, n_sdf_instrs;
+    int light_samples;          /* shadow rays per shaded hit */
+    int fanout;                 /* 1 or 2 children per shaded hit */
+    int max_bvh_depth;
+    int batch_samples;          /* camera samples per wavefront batch */
+    uint64_t scene_bytes;       /* flattened scene bytes resident on the device */
+    uint64_t queue_bytes;       /* wavefront queue bytes */
+} jsrt_info;
+int jsrt_scene_info(jsrt_scene*, jsrt_info*);
+
+typedef struct jsrt_stats {
+    uint64_t rays_primary, rays_secondary, rays_shadow;   /* World.cast calls, src/world.js:28-30 */
+    uint64_t shaded_hits;
+    uint64_t launches;                                    /* kernel launches issued */
+    uint64_t camera_samples;
+    double ms_generate, ms_extend, ms_shade, ms_shadow;   /* filled only when profiling is on */
+} jsrt_stats;
+/* Counters accumulated since the last jsrt_stats_reset; synchronises the scene's stream. */
+int jsrt_stats_get(jsrt_scene*, jsrt_stats*);
+int jsrt_stats_reset(jsrt_scene*);
+/* Per-kernel CUDA-event timing (adds event records around every launch). */
+int jsrt_set_profiling(jsrt_scene*, int on);
+
+const char* jsrt_last_error(void);
+
+/* ---- scene-build helper (host only) --------------------
+ * BVHAggregateNode.build / split_objects (src/aggregates.js:65-185) over n
+ * object boxes given as the reference stores them (centre, half_size, min, max;
+ * 3 floats each).  Same topology as the reference's JS build. */
+typedef struct jsrt_bvh jsrt_bvh;
+typedef struct jsrt_bvh_node {
+    int32_t depth, is_leaf, obj_first, obj_count, lesser, greater;
+    float center[4], half_size[4], min[4], max[4];
+} jsrt_bvh_node;
+jsrt_bvh* jsrt_bvh_build(int n, const float* center, const float* half_size, const float* bmin, const float* bmax,
+                         double max_depth, int min_node_size);
+int jsrt_bvh_node_count(const jsrt_bvh*);
+int jsrt_bvh_leaf_object_count(const jsrt_bvh*);
+int jsrt_bvh_copy(const jsrt_bvh*, jsrt_bvh_node* nodes, int32_t* leaf_objects);
+void jsrt_bvh_free(jsrt_bvh*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JSRT_H */

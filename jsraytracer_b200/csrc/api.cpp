@@ -1,0 +1,108 @@
+// C ABI of libjsrt (include/jsrt.h).  Thin: argument checks, exception -> error
+// code + thread-local message, handle ownership.
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/jsrt.h"
+#include "host_scene.h"
+#include "render.h"
+
+using namespace jsrt;
+
+struct jsrt_scene {
+    HostScene host;
+    std::unique_ptr<Renderer> renderer;   // null for host-only handles
+};
+
+static thread_local std::string g_error;
+
+static int failWith(const std::exception& e) { g_error = e.what(); return 1; }
+static int needDevice(jsrt_scene* s) {
+    if (!s) { g_error = "jsrt: null scene handle"; return 1; }
+    if (!s->renderer) { g_error = "jsrt: scene was created without a CUDA device (jsrt_scene_create_host); there is no CPU fallback"; return 1; }
+    return 0;
+}
+#define JSRT_TRY(body) try { body; return 0; } catch (const std::exception& e) { return failWith(e); }
+
+static size_t queueBudget() {
+    if (const char* e = getenv("JSRT_QUEUE_BYTES")) { const double v = atof(e); if (v >= 1e6) return (size_t)v; }
+    return (size_t)12 << 30;
+}
+
+extern "C" {
+
+const char* jsrt_last_error(void) { return g_error.c_str(); }
+
+int jsrt_device_count(void) { return deviceCount(); }
+
+jsrt_scene* jsrt_scene_create_host(const uint8_t* blob, size_t len, int format) {
+    try {
+        std::unique_ptr<jsrt_scene> s(new jsrt_scene);
+        WireDoc doc(blob, len, format);
+        flattenScene(doc, s->host);
+        return s.release();
+    } catch (const std::exception& e) { failWith(e); return nullptr; }
+}
+
+jsrt_scene* jsrt_scene_create(const uint8_t* blob, size_t len, int format, const int* devices, int ndev) {
+    try {
+        if (ndev > 1) fail("jsrt: one scene handle drives one GPU; create one per process/device (ndev must be 1)");
+        const int dev = (devices && ndev == 1) ? devices[0] : 0;
+        const int have = deviceCount();
+        if (have <= 0) fail("jsrt: no CUDA device available; this library has no CPU fallback");
+        if (dev < 0 || dev >= have) fail("jsrt: CUDA device index out of range");
+        std::unique_ptr<jsrt_scene> s(jsrt_scene_create_host(blob, len, format));
+        if (!s) return nullptr;
+        s->renderer.reset(new Renderer(s->host, dev, queueBudget()));
+        return s.release();
+    } catch (const std::exception& e) { failWith(e); return nullptr; }
+}
+
+void jsrt_scene_destroy(jsrt_scene* s) { delete s; }
+
+int jsrt_scene_upload(jsrt_scene* s) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->upload()) }
+int jsrt_scene_set_stream(jsrt_scene* s, void* st) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->setStream(st)) }
+
+int jsrt_render(jsrt_scene* s, int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags) {
+    if (needDevice(s)) return 1;
+    if (n_passes < 0 || first_pass < 0) { g_error = "jsrt: negative pass range"; return 1; }
+    JSRT_TRY(s->renderer->render(first_pass, n_passes, seed, x_offset, x_delt, flags))
+}
+int jsrt_reset_accum(jsrt_scene* s) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->resetAccum()) }
+int jsrt_synchronize(jsrt_scene* s) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->synchronize()) }
+int jsrt_resolve_rgba8(jsrt_scene* s, uint8_t* out) { if (needDevice(s)) return 1; if (!out) { g_error = "jsrt: null output buffer"; return 1; } JSRT_TRY(s->renderer->resolve(out)) }
+int jsrt_read_accum(jsrt_scene* s, float* out, int* passes) { if (needDevice(s)) return 1; if (!out) { g_error = "jsrt: null output buffer"; return 1; } JSRT_TRY(s->renderer->readAccum(out, passes)) }
+void* jsrt_accum_device_ptr(jsrt_scene* s) { return (s && s->renderer) ? s->renderer->accumPtr() : nullptr; }
+int jsrt_add_passes(jsrt_scene* s, int n) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->addPasses(n)) }
+int jsrt_primary_hits(jsrt_scene* s, int32_t* prim_id, float* t) { if (needDevice(s)) return 1; if (!prim_id || !t) { g_error = "jsrt: null output buffer"; return 1; } JSRT_TRY(s->renderer->primaryHits(prim_id, t)) }
+
+int jsrt_scene_info(jsrt_scene* s, jsrt_info* o) {
+    if (!s || !o) { g_error = "jsrt: null argument"; return 1; }
+    const HostScene& h = s->host;
+    memset(o, 0, sizeof *o);
+    o->width = h.width; o->height = h.height; o->samples_per_pixel = h.samples_per_pixel; o->max_depth = h.max_depth; o->jitter = h.jitter;
+    o->n_top = (int)h.tops.size(); o->n_prims = (int)h.prims.size(); o->n_ext_prims = h.ext_prim_count; o->n_nodes = (int)h.nodes.size();
+    o->n_tris = (int)h.tris.size(); o->n_materials = (int)h.materials.size(); o->n_lights = (int)h.lights.size();
+    o->n_sdfs = (int)h.sdfs.size(); o->n_sdf_instrs = (int)h.sdf_code.size(); o->light_samples = h.light_samples; o->fanout = h.fanout;
+    o->max_bvh_depth = h.max_bvh_depth;
+    if (s->renderer) { o->batch_samples = s->renderer->batchSamples(); o->scene_bytes = s->renderer->sceneBytes(); o->queue_bytes = s->renderer->queueBytes(); }
+    return 0;
+}
+
+int jsrt_stats_get(jsrt_scene* s, jsrt_stats* o) {
+    if (needDevice(s)) return 1;
+    try {
+        RenderStats r; s->renderer->getStats(r);
+        memset(o, 0, sizeof *o);
+        o->rays_primary = r.rays_primary; o->rays_secondary = r.rays_secondary; o->rays_shadow = r.rays_shadow; o->shaded_hits = r.shaded_hits;
+        o->launches = r.launches; o->camera_samples = r.camera_samples;
+        o->ms_generate = r.ms[0]; o->ms_extend = r.ms[1]; o->ms_shade = r.ms[2]; o->ms_shadow = r.ms[3];
+        return 0;
+    } catch (const std::exception& e) { return failWith(e); }
+}
+int jsrt_stats_reset(jsrt_scene* s) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->resetStats()) }
+int jsrt_set_profiling(jsrt_scene* s, int on) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->setProfiling(on != 0)) }
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+// Host-side product of flattening the serializer graph (scene_flatten.cpp).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "scene_types.h"
+#include "wire.h"
+
+namespace jsrt {
+
+struct HostScene {
+    int width = 0, height = 0, samples_per_pixel = 1, max_depth = 3;
+    bool jitter = true;                 // false for SimpleRenderer (src/renderers.js:21-25)
+    std::string renderer_type;
+    Camera camera{};
+    float bg[4] = {0, 0, 0, 0};
+
+    std::vector<Top> tops;
+    std::vector<Prim> prims;
+    std::vector<Xform> xforms;          // xforms[0] is the identity
+    std::vector<BvhNode> nodes;
+    std::vector<Tri> tris;
+    std::vector<TriShade> tri_shade;    // parallel to tris when any triangle has vertex data, else empty
+    std::vector<float> boxes;           // 8 floats per non-unit AABB geometry: centre xyz_, half xyz_
+    std::vector<Material> materials;
+    std::vector<Light> lights;
+    std::vector<SdfProgram> sdfs;
+    std::vector<SdfInstr> sdf_code;
+
+    int ext_prim_count = 0;             // number of distinct reference Primitives (prim_id range)
+    int light_samples = 0;              // sum of samples over lights = shadow rays per shaded hit
+    int fanout = 1;                     // 2 if any material can spawn both a reflection and a transmission child
+    int max_bvh_depth = 0;
+};
+
+void flattenScene(const WireDoc& doc, HostScene& out);
+
+// SDF tree -> bytecode (sdf_compile.cpp).  Returns the index of the new program.
+int compileSdf(const WireDoc& doc, const Val* sdf_geometry, HostScene& out);
+
+}  // namespace jsrt

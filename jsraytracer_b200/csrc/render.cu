@@ -1,0 +1,525 @@
+// Wavefront renderer: generate / extend / shade / shadow kernels over ray queues
+// that live in HBM, plus the accumulation buffer and its 8-bit resolve.
+//
+// Replaces the reference's per-pixel recursion
+//   IncrementalMultisamplingRenderer.render -> World.color -> Primitive.color ->
+//   Material.color -> World.color ...   (src/renderers.js:87-98, src/world.js:31-41,
+//   src/materials.js:271-333)
+// with level-synchronous waves: level L holds every ray of path-tree depth L of
+// the camera samples in the current batch.  A shaded hit appends up to two
+// children (reflection, transmission/refraction) to the next level's queue and
+// one shadow ray per light sample to the shadow queue; both appends are
+// compacted with a warp ballot + prefix popcount and one atomicAdd per warp.
+//
+// Queues are SoA of float4 (128-bit coalesced loads/stores):
+//   ray:    o.xyz | pixel      d.xyz | node id      throughput.rgb | pass<<8 | depth_remaining
+//   hit:    t | placed prim | top-level object | -
+//   shadow: o.xyz | pixel      d.xyz (unnormalised, light at t=1) | -      contribution.rgb | -
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "render.h"
+#include "shade.cuh"
+
+namespace jsrt {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+struct RayQueue { float4* o; float4* d; float4* w; };
+struct ShadowQueue { float4* o; float4* d; float4* c; };
+
+// counters[0], [1]: ray queue counts (ping-pong); [2]: shadow queue count
+struct Counters { int ray[2]; int shadow; int pad; unsigned long long stats[8]; };
+enum { ST_PRIMARY = 0, ST_SECONDARY = 1, ST_SHADOW = 2, ST_SHADED = 3, ST_SAMPLES = 4 };
+
+struct GenParams {
+    Camera cam;
+    int width, height, x_offset, x_delt, ncols, npix_active;
+    int first_pass, jitter, max_depth;
+    unsigned long long seed;
+    long long first_sample;      // index of the batch's first sample within the call
+    int n_samples;               // samples in this batch
+};
+
+// ---------------------------------------------------------------------------------
+// generate: camera.getRayForPixel for sample s of the batch (src/cameras.js:29-34,46-52)
+// with the pixel / jitter arithmetic of src/renderers.js:89-96, all in f64 so the
+// primary ray is the reference's bit for bit.
+__device__ void camera_ray(const GenParams& g, int px, int py, uint32_t sample_key, bool jitter, bool use_lens, float3& o, float3& d) {
+    const uint32_t nk = rng_node_key(sample_key, 1);
+    double x = 2.0 * ((double)px / (double)g.width) - 1.0;
+    double y = -2.0 * ((double)py / (double)g.height) + 1.0;
+    if (jitter) {
+        x = x + (2.0 / (double)g.width) * ((double)rng_u01(nk, DIM_JITTER_X) - 0.5);
+        y = y + (2.0 / (double)g.height) * ((double)rng_u01(nk, DIM_JITTER_Y) - 0.5);
+    }
+    const Camera& c = g.cam;
+    const float dx = (float)(x * c.tan_fov * c.aspect), dy = (float)(y * c.tan_fov), dz = -1.f;   // Vec.of(...) stores f32
+    const double* t = c.t;
+    // transform.times(direction): f64 dot of the f32 vector with each row, stored f32 (w = 0)
+    float3 dir = f3((float)((double)dx * t[0] + (double)dy * t[1] + (double)dz * t[2] + 0.0 * t[3]),
+                    (float)((double)dx * t[4] + (double)dy * t[5] + (double)dz * t[6] + 0.0 * t[7]),
+                    (float)((double)dx * t[8] + (double)dy * t[9] + (double)dz * t[10] + 0.0 * t[11]));
+    float3 org = f3((float)t[3], (float)t[7], (float)t[11]);       // transform.column(3)
+    if (c.dof && use_lens) {
+        // Vec.circlePick src/math.js:175-179, then DepthOfFieldPerspectiveCamera.getRayForPixel
+        const double a = (double)rng_u01(nk, DIM_LENS_A) * 2.0 * 3.141592653589793, r = sqrt((double)rng_u01(nk, DIM_LENS_R));
+        const float cx = (float)(r * cos(a)), cy = (float)(r * sin(a));
+        const float sx = (float)((double)cx * c.sensor_size), sy = (float)((double)cy * c.sensor_size);
+        const float3 off = f3((float)((double)sx * t[0] + (double)sy * t[1] + 0.0 * t[2] + 0.0 * t[3]),
+                              (float)((double)sx * t[4] + (double)sy * t[5] + 0.0 * t[6] + 0.0 * t[7]),
+                              (float)((double)sx * t[8] + (double)sy * t[9] + 0.0 * t[10] + 0.0 * t[11]));
+        org = f3((float)((double)org.x + (double)off.x), (float)((double)org.y + (double)off.y), (float)((double)org.z + (double)off.z));
+        const float fx = (float)((double)dir.x * c.focus_distance), fy = (float)((double)dir.y * c.focus_distance), fz = (float)((double)dir.z * c.focus_distance);
+        const float mx = (float)((double)fx - (double)off.x), my = (float)((double)fy - (double)off.y), mz = (float)((double)fz - (double)off.z);
+        const double nn = sqrt((double)mx * mx + (double)my * my + (double)mz * mz);
+        if (nn > 0.00001) { const double inv = 1.0 / nn; dir = f3((float)((double)mx * inv), (float)((double)my * inv), (float)((double)mz * inv)); }
+        else dir = f3(mx, my, mz);
+    }
+    o = org; d = dir;
+}
+
+__global__ void __launch_bounds__(kBlock) generate_kernel(const __grid_constant__ GenParams g, RayQueue q, float4* __restrict__ accum) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < g.n_samples; s += stride) {
+        const long long gs = g.first_sample + s;
+        const int pass = g.first_pass + (int)(gs / g.npix_active);
+        const int idx = (int)(gs % g.npix_active);
+        const int py = idx / g.ncols, px = g.x_offset + (idx % g.ncols) * g.x_delt;
+        const uint32_t pixel = (uint32_t)(py * g.width + px);
+        const uint32_t key = rng_sample_key(g.seed, pixel, (uint32_t)pass);
+        float3 o, d;
+        camera_ray(g, px, py, key, g.jitter != 0, true, o, d);
+        q.o[s] = make_float4(o.x, o.y, o.z, __int_as_float((int)pixel));
+        q.d[s] = make_float4(d.x, d.y, d.z, __int_as_float(1));
+        q.w[s] = make_float4(1.f, 1.f, 1.f, __int_as_float((pass << 8) | g.max_depth));
+        atomicAdd(&accum[pixel].w, 1.0f);      // samples taken for this pixel
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// extend: closest hit for every ray of the level (World.cast, src/world.js:28-30).
+// primary rays use minDistance 0, every other ray 0.0001 (src/materials.js:279,286,319,328).
+__global__ void __launch_bounds__(kBlock) extend_kernel(const __grid_constant__ DeviceScene sc, RayQueue q, const int* __restrict__ count,
+                                                         float4* __restrict__ hits) {
+    const int n = *count;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 o4 = q.o[i], d4 = q.d[i];
+        const float minD = (__float_as_int(d4.w) == 1) ? 0.f : 0.0001f;
+        const Hit h = trace_ray<false>(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), minD, CUDART_INF_F);
+        hits[i] = make_float4(h.t, __int_as_float(h.prim), __int_as_float(h.top), 0.f);
+    }
+}
+
+// warp-aggregated append: returns this lane's slot (valid only where `want`)
+__device__ __forceinline__ int warp_append(int* counter, bool want) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0) return -1;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float3 c) {
+    float* a = reinterpret_cast<float*>(accum + pixel);
+    if (c.x != 0.f) atomicAdd(a + 0, c.x);
+    if (c.y != 0.f) atomicAdd(a + 1, c.y);
+    if (c.z != 0.f) atomicAdd(a + 2, c.z);
+}
+
+// ---------------------------------------------------------------------------------
+// shade: World.color's miss / hit handling (src/world.js:31-41), Primitive.color
+// (:125-137), Material.color (src/materials.js).  Emits ambient, pushes shadow rays
+// and children.
+__global__ void __launch_bounds__(kBlock) shade_kernel(const __grid_constant__ DeviceScene sc, RayQueue q, const int* __restrict__ count,
+                                                        const float4* __restrict__ hits, RayQueue next, int* next_count, int next_cap,
+                                                        ShadowQueue sq, int* shadow_count, int shadow_cap, float4* __restrict__ accum,
+                                                        unsigned long long seed, unsigned long long* stats, int* overflow) {
+    const int n = *count;
+    const int stride = gridDim.x * blockDim.x;
+    const int n_round = (n + 31) & ~31;      // warp-uniform trip count: every lane reaches the ballots
+    unsigned long long my_shaded = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool active = i < n;
+        bool hit = false;
+        uint32_t pixel = 0, node = 0; int depth_rem = 0, pass = 0;
+        float3 o = f3(0, 0, 0), d = f3(0, 0, 1), thr = f3(0, 0, 0);
+        SurfaceData s; s.position = f3(0, 0, 0); s.normal = f3(0, 0, 1); s.uv = make_float2(0, 0); s.has_uv = false; s.basecolor = f3(1, 1, 1);
+        PhongFactors f;
+        const Material* mat = sc.materials;
+        uint32_t node_key = 0;
+        if (active) {
+            const float4 o4 = q.o[i], d4 = q.d[i], w4 = q.w[i], h4 = hits[i];
+            o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z); thr = f3(w4.x, w4.y, w4.z);
+            pixel = (uint32_t)__float_as_int(o4.w); node = (uint32_t)__float_as_int(d4.w);
+            const int packed = __float_as_int(w4.w); depth_rem = packed & 0xff; pass = packed >> 8;
+            const int prim = __float_as_int(h4.y), top = __float_as_int(h4.z);
+            const float t = h4.x;
+            if (prim < 0) {
+                accum_add(accum, pixel, thr * f3(sc.bg[0], sc.bg[1], sc.bg[2]));      // `return this.bg_color`
+            } else {
+                hit = true; ++my_shaded;
+                const int4* pp = reinterpret_cast<const int4*>(sc.prims + prim);
+                const int4 pa = __ldg(pp); const int flags = __ldg(reinterpret_cast<const int*>(pp + 1));
+                // inv_transform = prim.inv * ancestorInvTransform (src/world.js:126)
+                XformReg inv = load_xform(sc.xforms, pa.w);
+                const int4 ta = __ldg(reinterpret_cast<const int4*>(sc.tops + top));
+                if (ta.x != T_PRIM) {
+                    const XformReg anc = load_xform(sc.xforms, ta.y);
+                    inv = (flags & PF_IDENTITY_XFORM) ? anc : xf_compose(inv, anc);
+                }
+                const float3 lp = ray_point(xf_point(inv, o), xf_dir(inv, d), t);
+                float3 ln; material_data(sc, pa.x, pa.y, flags, lp, ln, s.uv, s.has_uv, s.basecolor);
+                s.normal = normalized3(xf_normal(inv, ln));
+                s.position = ray_point(o, d, t);
+                mat = sc.materials + pa.z;
+                node_key = rng_node_key(rng_sample_key(seed, pixel, (uint32_t)pass), node);
+                if (mat->kind == M_SOLID) {
+                    accum_add(accum, pixel, thr * color_eval(mat->ambient, s));
+                    hit = false;                 // no lights, no children (src/materials.js:153-155)
+                } else if (mat->kind == M_TRANSPARENT) {
+                    accum_add(accum, pixel, thr * (color_eval(mat->ambient, s) * mat->smoothness));
+                } else {
+                    base_factors(*mat, s, d, f);
+                    accum_add(accum, pixel, thr * f.ambient);      // `let ret = data.ambient`
+                }
+            }
+        }
+        const bool lit = hit && mat->kind != M_TRANSPARENT;
+        // ---- shadow rays: one per light sample (src/materials.js:244-257) -----------
+        uint32_t dim = DIM_LIGHTS;
+        for (int li = 0; li < sc.n_lights; ++li) {
+            const Light& L = sc.lights[li];
+            const int ns = L.samples;
+            for (int k = 0; k < ns; ++k, dim += 2) {
+                LightSample ls; float3 contrib = f3(0, 0, 0);
+                if (lit) {
+                    ls = light_sample(L, s.position, rng_u01(node_key, dim), rng_u01(node_key, dim + 1));
+                    contrib = thr * (color_from_light_sample(*mat, f, ls) * (1.0f / (float)ns));
+                }
+                const int slot = warp_append(shadow_count, lit);
+                if (lit) {
+                    if (slot < shadow_cap) {
+                        sq.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
+                        sq.d[slot] = make_float4(ls.direction.x, ls.direction.y, ls.direction.z, 0.f);
+                        sq.c[slot] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                    } else *overflow = 1;
+                }
+            }
+        }
+        // ---- children (src/materials.js:277-288, 315-330, 169-172).  world.color with
+        // recursionDepth - 1 == 0 returns black without casting (src/world.js:32-33).
+        bool want0 = false, want1 = false; float3 dir0 = f3(0, 0, 1), dir1 = f3(0, 0, 1), w0 = f3(0, 0, 0), w1 = f3(0, 0, 0);
+        if (hit && depth_rem - 1 > 0) {
+            if (mat->kind == M_PHONG) {
+                if (dot3(f.reflectivity, f.reflectivity) > 0.f) { want0 = true; dir0 = f.R; w0 = thr * f.reflectivity; }
+                if (dot3(f.transmissivity, f.transmissivity) > 0.f) { want1 = true; dir1 = normalized3(d); w1 = thr * f.transmissivity; }
+            } else if (mat->kind == M_TRANSPARENT) {
+                want0 = true; dir0 = d; w0 = thr * (1.f - mat->smoothness);
+            } else {
+                const uint32_t sb = DIM_LIGHTS + 2u * (uint32_t)sc.light_samples;
+                float3 col;
+                if (f.kr > 0.f && scatter(*mat, f, true, f.R, f.N, node_key, sb, dir0, col)) { want0 = true; w0 = thr * (col * f.reflectivity * f.kr); }
+                if (f.kr < 1.f && scatter(*mat, f, f.has_refr, f.refr, f.N * -1.f, node_key, sb + 4, dir1, col)) { want1 = true; w1 = thr * (col * f.transmissivity * (1.f - f.kr)); }
+            }
+        }
+        const int packed_next = (pass << 8) | (depth_rem - 1);
+        int slot = warp_append(next_count, want0);
+        if (want0) {
+            if (slot < next_cap) {
+                next.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
+                next.d[slot] = make_float4(dir0.x, dir0.y, dir0.z, __int_as_float((int)(2u * node)));
+                next.w[slot] = make_float4(w0.x, w0.y, w0.z, __int_as_float(packed_next));
+            } else *overflow = 1;
+        }
+        slot = warp_append(next_count, want1);
+        if (want1) {
+            if (slot < next_cap) {
+                next.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
+                next.d[slot] = make_float4(dir1.x, dir1.y, dir1.z, __int_as_float((int)(2u * node + 1u)));
+                next.w[slot] = make_float4(w1.x, w1.y, w1.z, __int_as_float(packed_next));
+            } else *overflow = 1;
+        }
+    }
+    // per-warp reduction of the shaded-hit count, one atomic per warp
+    for (int off = 16; off; off >>= 1) my_shaded += __shfl_down_sync(0xffffffffu, my_shaded, off);
+    if ((threadIdx.x & 31) == 0 && my_shaded) atomicAdd(stats + ST_SHADED, my_shaded);
+}
+
+// ---------------------------------------------------------------------------------
+// shadow: `world.cast(new Ray(position, direction), 0.0001, 1, false)`; the sample is
+// dropped iff 0 < t < 1 (src/materials.js:250-252).
+__global__ void __launch_bounds__(kBlock) shadow_kernel(const __grid_constant__ DeviceScene sc, ShadowQueue sq, const int* __restrict__ count, int cap,
+                                                         float4* __restrict__ accum) {
+    const int n = min(*count, cap);
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 o4 = sq.o[i], d4 = sq.d[i];
+        const Hit h = trace_ray<true>(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), 0.0001f, 1.0f);
+        if (h.prim < 0) {
+            const float4 c4 = sq.c[i];
+            accum_add(accum, (uint32_t)__float_as_int(o4.w), f3(c4.x, c4.y, c4.z));
+        }
+    }
+}
+
+// bookkeeping between levels: fold queue sizes into the ray statistics and recycle the counters
+__global__ void level_end_kernel(Counters* c, int cur, int level, int next_cap, int shadow_cap) {
+    c->stats[level == 0 ? ST_PRIMARY : ST_SECONDARY] += (unsigned long long)c->ray[cur];
+    c->stats[ST_SHADOW] += (unsigned long long)min(c->shadow, shadow_cap);
+    c->ray[cur] = 0;
+    c->shadow = 0;
+    if (c->ray[cur ^ 1] > next_cap) c->ray[cur ^ 1] = next_cap;
+}
+__global__ void set_count_kernel(Counters* c, int which, int n) { c->ray[which] = n; c->ray[which ^ 1] = 0; c->shadow = 0; c->stats[ST_SAMPLES] += (unsigned long long)n; }
+
+// PixelBuffer.setColor on buffer.times(1/(iter+1)) (src/renderers.js:98, src/pixelbuffer.js:39-49)
+__global__ void resolve_kernel(const float4* __restrict__ accum, uchar4* __restrict__ out, int npix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const float4 a = accum[i];
+    if (!(a.w > 0.f)) { out[i] = make_uchar4(0, 0, 0, 0); return; }
+    const double inv = 1.0 / (double)a.w;
+    float c[3] = {(float)((double)a.x * inv), (float)((double)a.y * inv), (float)((double)a.z * inv)};
+    unsigned char r[3];
+    for (int k = 0; k < 3; ++k) {
+        double comp = fmin(fmax((double)c[k], 0.0), 1.0);     // Math.min(Math.max(c, 0), 1): NaN stays NaN -> 0 in a Uint8ClampedArray
+        if (c[k] != c[k]) comp = 0.0;
+        r[k] = (unsigned char)floor(255.0 * comp + 0.5);      // Math.round
+    }
+    out[i] = make_uchar4(r[0], r[1], r[2], 255);
+}
+
+// parity probe: un-jittered pinhole primary rays -> (prim_id, t)
+__global__ void primary_hits_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ GenParams g, int* __restrict__ prim_id, float* __restrict__ tout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.width * g.height) return;
+    const int px = i % g.width, py = i / g.width;
+    float3 o, d;
+    camera_ray(g, px, py, 0u, false, false, o, d);
+    const Hit h = trace_ray<false>(sc, o, d, 0.f, CUDART_INF_F);
+    prim_id[i] = h.prim >= 0 ? sc.prims[h.prim].ext_id : -1;
+    tout[i] = h.t;
+}
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) throw std::runtime_error(std::string("jsrt: CUDA error: ") + cudaGetErrorString(e__) + " at " #call); } while (0)
+
+template <class T> T* toDevice(const std::vector<T>& v, cudaStream_t st) {
+    T* p = nullptr;
+    const size_t bytes = (v.empty() ? 1 : v.size()) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return p;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------
+struct Renderer::Impl {
+    const HostScene& hs;
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    DeviceScene ds{};
+    std::vector<void*> allocs;
+    float4* accum = nullptr;
+    RayQueue rq[2]{}; float4* hits = nullptr; ShadowQueue sq{};
+    Counters* counters = nullptr;
+    int* overflow = nullptr;
+    int ray_cap = 0, shadow_cap = 0, batch = 0;
+    int passes = 0;
+    size_t scene_bytes = 0, queue_bytes = 0;
+    int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0;
+    unsigned long long launches = 0;
+    bool profiling = false;
+    double ms[4] = {0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uchar4* rgba = nullptr; int* hit_ids = nullptr; float* hit_t = nullptr;
+
+    explicit Impl(const HostScene& h) : hs(h) {}
+
+    template <class T> T* dalloc(size_t n) { T* p = nullptr; CK(cudaMalloc(&p, (n ? n : 1) * sizeof(T))); allocs.push_back(p); return p; }
+
+    void uploadScene() {
+        for (void* p : scene_allocs) cudaFree(p);
+        scene_allocs.clear(); scene_bytes = 0;
+        ds.tops = up(hs.tops); ds.prims = up(hs.prims); ds.xforms = up(hs.xforms); ds.nodes = up(hs.nodes);
+        ds.tris = up(hs.tris); ds.tri_shade = up(hs.tri_shade); ds.boxes = up(hs.boxes); ds.materials = up(hs.materials);
+        ds.lights = up(hs.lights); ds.sdfs = up(hs.sdfs); ds.sdf_code = up(hs.sdf_code);
+        ds.n_top = (int)hs.tops.size(); ds.n_lights = (int)hs.lights.size(); ds.light_samples = hs.light_samples; ds.max_depth = hs.max_depth;
+        for (int i = 0; i < 3; ++i) ds.bg[i] = hs.bg[i];
+    }
+    std::vector<void*> scene_allocs;
+    template <class T> T* up(const std::vector<T>& vec) {
+        T* p = toDevice(vec, stream); scene_allocs.push_back((void*)p); scene_bytes += vec.size() * sizeof(T); return p;
+    }
+
+    void init(int dev, size_t queue_budget) {
+        device = dev;
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+        stream = own_stream;
+        uploadScene();
+        const size_t npix = (size_t)hs.width * hs.height;
+        accum = dalloc<float4>(npix);
+        CK(cudaMemsetAsync(accum, 0, npix * sizeof(float4), stream));
+        rgba = dalloc<uchar4>(npix); hit_ids = dalloc<int>(npix); hit_t = dalloc<float>(npix);
+        counters = dalloc<Counters>(1); overflow = dalloc<int>(1);
+        CK(cudaMemsetAsync(counters, 0, sizeof(Counters), stream));
+        CK(cudaMemsetAsync(overflow, 0, sizeof(int), stream));
+
+        // Queue sizing: a camera sample owns at most fanout^L rays at level L and
+        // light_samples shadow rays per ray, so the worst case over the levels is at
+        // the deepest one.  The batch (camera samples in flight) is the largest that
+        // fits the budget; whole frames fit for every BASELINE config but the
+        // depth-8 Cornell box, which runs in sub-frame batches.
+        double worst = 1; for (int l = 1; l < hs.max_depth; ++l) worst *= hs.fanout;
+        if (worst > 1e6) worst = 1e6;
+        const double per_sample = worst * (2.0 * 48 + 16 + 48.0 * std::max(1, hs.light_samples));
+        double b = (double)queue_budget / per_sample;
+        const double want = (double)npix * 4;            // up to 4 passes per wave
+        if (b > want) b = want;
+        if (b < 65536) b = 65536;
+        batch = (int)b;
+        ray_cap = (int)std::min<double>((double)batch * worst, 2.0e9);
+        shadow_cap = (int)std::min<double>((double)ray_cap * std::max(1, hs.light_samples), 2.0e9);
+        for (int k = 0; k < 2; ++k) { rq[k].o = dalloc<float4>(ray_cap); rq[k].d = dalloc<float4>(ray_cap); rq[k].w = dalloc<float4>(ray_cap); }
+        hits = dalloc<float4>(ray_cap);
+        sq.o = dalloc<float4>(shadow_cap); sq.d = dalloc<float4>(shadow_cap); sq.c = dalloc<float4>(shadow_cap);
+        queue_bytes = (size_t)ray_cap * (2 * 48 + 16) + (size_t)shadow_cap * 48;
+
+        cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+        auto grid_for = [&](const void* fn) { int per = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, kBlock, 0)); return prop.multiProcessorCount * std::max(1, per); };
+        grid_extend = grid_for((const void*)extend_kernel);
+        grid_shade = grid_for((const void*)shade_kernel);
+        grid_shadow = grid_for((const void*)shadow_kernel);
+        grid_gen = grid_for((const void*)generate_kernel);
+        CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+        CK(cudaStreamSynchronize(stream));
+    }
+
+    ~Impl() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        for (void* p : allocs) cudaFree(p);
+        for (void* p : scene_allocs) cudaFree(p);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+
+    template <class F> void timed(int which, F&& launch) {
+        if (profiling) CK(cudaEventRecord(ev0, stream));
+        launch();
+        ++launches;
+        CK(cudaGetLastError());
+        if (profiling) { CK(cudaEventRecord(ev1, stream)); CK(cudaEventSynchronize(ev1)); float t = 0; CK(cudaEventElapsedTime(&t, ev0, ev1)); ms[which] += t; }
+    }
+
+    GenParams genParams(int first_pass, uint64_t seed, int x_offset, int x_delt, int flags) const {
+        GenParams g{};
+        g.cam = hs.camera; g.width = hs.width; g.height = hs.height;
+        g.x_offset = x_offset; g.x_delt = x_delt < 1 ? 1 : x_delt;
+        g.ncols = x_offset < hs.width ? (hs.width - x_offset + g.x_delt - 1) / g.x_delt : 0;
+        g.npix_active = g.ncols * hs.height;
+        g.first_pass = first_pass; g.jitter = (flags & 1) ? 0 : 1; g.max_depth = hs.max_depth; g.seed = seed;
+        return g;
+    }
+
+    void render(int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags) {
+        CK(cudaSetDevice(device));
+        if (hs.max_depth <= 0 || hs.max_depth > 255) throw std::runtime_error("jsrt: maxRecursionDepth must be in 1..255");
+        if (x_offset < 0) throw std::runtime_error("jsrt: x_offset must be >= 0");
+        GenParams g = genParams(first_pass, seed, x_offset, x_delt, flags);
+        const long long total = (long long)g.npix_active * n_passes;
+        for (long long done = 0; done < total; done += batch) {
+            g.first_sample = done;
+            g.n_samples = (int)std::min<long long>(batch, total - done);
+            set_count_kernel<<<1, 1, 0, stream>>>(counters, 0, g.n_samples); ++launches;
+            timed(0, [&] { generate_kernel<<<grid_gen, kBlock, 0, stream>>>(g, rq[0], accum); });
+            int cur = 0;
+            for (int level = 0; level < hs.max_depth; ++level) {
+                timed(1, [&] { extend_kernel<<<grid_extend, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits); });
+                timed(2, [&] { shade_kernel<<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap,
+                                                                            sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow); });
+                if (hs.light_samples > 0)
+                    timed(3, [&] { shadow_kernel<<<grid_shadow, kBlock, 0, stream>>>(ds, sq, &counters->shadow, shadow_cap, accum); });
+                level_end_kernel<<<1, 1, 0, stream>>>(counters, cur, level, ray_cap, shadow_cap); ++launches;
+                cur ^= 1;
+            }
+        }
+        CK(cudaGetLastError());
+        if (x_offset == 0 && g.x_delt == 1) passes += n_passes; else passes = std::max(passes, first_pass + n_passes);
+    }
+};
+
+Renderer::Renderer(const HostScene& hs, int device, size_t queue_budget) : impl_(new Impl(hs)) { impl_->init(device, queue_budget); }
+Renderer::~Renderer() { delete impl_; }
+void Renderer::render(int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags) { impl_->render(first_pass, n_passes, seed, x_offset, x_delt, flags); }
+void Renderer::upload() { CK(cudaSetDevice(impl_->device)); impl_->uploadScene(); CK(cudaStreamSynchronize(impl_->stream)); }
+void Renderer::setStream(void* s) { impl_->stream = s ? (cudaStream_t)s : impl_->own_stream; }
+void Renderer::synchronize() {
+    CK(cudaSetDevice(impl_->device)); CK(cudaStreamSynchronize(impl_->stream));
+    int ov = 0; CK(cudaMemcpy(&ov, impl_->overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    if (ov) throw std::runtime_error("jsrt: wavefront queue overflow (internal sizing error)");
+}
+void Renderer::resetAccum() {
+    CK(cudaSetDevice(impl_->device));
+    CK(cudaMemsetAsync(impl_->accum, 0, (size_t)impl_->hs.width * impl_->hs.height * sizeof(float4), impl_->stream));
+    impl_->passes = 0;
+}
+void Renderer::resolve(uint8_t* out) {
+    CK(cudaSetDevice(impl_->device));
+    const int npix = impl_->hs.width * impl_->hs.height;
+    resolve_kernel<<<(npix + 255) / 256, 256, 0, impl_->stream>>>(impl_->accum, impl_->rgba, npix); ++impl_->launches;
+    CK(cudaMemcpyAsync(out, impl_->rgba, (size_t)npix * 4, cudaMemcpyDeviceToHost, impl_->stream));
+    synchronize();
+}
+void Renderer::readAccum(float* out, int* passes) {
+    CK(cudaSetDevice(impl_->device));
+    CK(cudaMemcpyAsync(out, impl_->accum, (size_t)impl_->hs.width * impl_->hs.height * sizeof(float4), cudaMemcpyDeviceToHost, impl_->stream));
+    synchronize();
+    if (passes) *passes = impl_->passes;
+}
+void* Renderer::accumPtr() { return impl_->accum; }
+void Renderer::addPasses(int n) { impl_->passes += n; }
+void Renderer::primaryHits(int32_t* prim_id, float* t) {
+    CK(cudaSetDevice(impl_->device));
+    GenParams g = impl_->genParams(0, 0, 0, 1, 1);
+    const int npix = impl_->hs.width * impl_->hs.height;
+    primary_hits_kernel<<<(npix + 127) / 128, 128, 0, impl_->stream>>>(impl_->ds, g, impl_->hit_ids, impl_->hit_t); ++impl_->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(prim_id, impl_->hit_ids, (size_t)npix * 4, cudaMemcpyDeviceToHost, impl_->stream));
+    CK(cudaMemcpyAsync(t, impl_->hit_t, (size_t)npix * 4, cudaMemcpyDeviceToHost, impl_->stream));
+    synchronize();
+}
+void Renderer::getStats(RenderStats& s) {
+    synchronize();
+    Counters c; CK(cudaMemcpy(&c, impl_->counters, sizeof(Counters), cudaMemcpyDeviceToHost));
+    s.rays_primary = c.stats[ST_PRIMARY]; s.rays_secondary = c.stats[ST_SECONDARY]; s.rays_shadow = c.stats[ST_SHADOW];
+    s.shaded_hits = c.stats[ST_SHADED]; s.camera_samples = c.stats[ST_SAMPLES]; s.launches = impl_->launches;
+    for (int i = 0; i < 4; ++i) s.ms[i] = impl_->ms[i];
+}
+void Renderer::resetStats() {
+    synchronize();
+    CK(cudaMemsetAsync(impl_->counters, 0, sizeof(Counters), impl_->stream));
+    impl_->launches = 0; for (double& m : impl_->ms) m = 0;
+}
+void Renderer::setProfiling(bool on) { impl_->profiling = on; }
+int Renderer::passes() const { return impl_->passes; }
+int Renderer::batchSamples() const { return impl_->batch; }
+size_t Renderer::sceneBytes() const { return impl_->scene_bytes; }
+size_t Renderer::queueBytes() const { return impl_->queue_bytes; }
+
+int deviceCount() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+}  // namespace jsrt

@@ -1,0 +1,45 @@
+// Host interface of the wavefront renderer (render.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+
+#include "host_scene.h"
+
+namespace jsrt {
+
+struct RenderStats {
+    uint64_t rays_primary = 0, rays_secondary = 0, rays_shadow = 0, shaded_hits = 0, camera_samples = 0, launches = 0;
+    double ms[4] = {0, 0, 0, 0};   // generate, extend, shade, shadow (profiling mode only)
+};
+
+class Renderer {
+public:
+    Renderer(const HostScene& hs, int device, size_t queue_budget_bytes);
+    ~Renderer();
+    void render(int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags);
+    void upload();
+    void setStream(void* cuda_stream);
+    void synchronize();
+    void resetAccum();
+    void resolve(uint8_t* out_rgba);
+    void readAccum(float* out, int* passes);
+    void* accumPtr();
+    void addPasses(int n);
+    void primaryHits(int32_t* prim_id, float* t);
+    void getStats(RenderStats& s);
+    void resetStats();
+    void setProfiling(bool on);
+    int passes() const;
+    int batchSamples() const;
+    size_t sceneBytes() const;
+    size_t queueBytes() const;
+
+private:
+    struct Impl;
+    Impl* impl_;
+};
+
+int deviceCount();
+
+}  // namespace jsrt

@@ -1,0 +1,363 @@
+// Serializer object graph -> flattened scene (scene_types.h).
+//
+// Walks `{renderer:{world,camera,maxRecursionDepth[,samplesPerPixel]},width,height}`
+// exactly as the reference's classes lay it out on the wire (key sets in
+// SURVEY.md §8b; src/world.js, src/aggregates.js, src/materials.js,
+// src/lights.js, src/cameras.js, src/geometry.js constructors).  Setup code:
+// runs once per scene on the host, never per ray.
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <unordered_map>
+
+#include "host_scene.h"
+
+namespace jsrt {
+
+static const double kInf = std::numeric_limits<double>::infinity();
+
+namespace {
+
+struct Folded { float c1[3]; float c2[3]; bool checker; };
+
+struct Flattener {
+    const WireDoc& doc;
+    HostScene& out;
+    std::unordered_map<const Val*, int> ext_id;        // Primitive -> prim_id
+    std::unordered_map<const Val*, int> material_of;   // Material -> index
+    std::unordered_map<const Val*, int> tri_of;        // Triangle geometry -> index
+    std::unordered_map<const Val*, int> sdf_of;        // SDFGeometry -> program index
+    struct TreeRef { int first_node, node_count, first_prim, prim_count; };
+    std::unordered_map<const Val*, TreeRef> tree_of;   // kdtree root -> laid-out tree (shared-tree instancing)
+    bool any_tri_data = false;
+
+    Flattener(const WireDoc& d, HostScene& o) : doc(d), out(o) {}
+
+    // ---- transforms -----------------------------------------------------------
+    static void mul44(const double a[16], const double b[16], double r[16]) {
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j]; r[i * 4 + j] = s; }
+    }
+    int addXform(const double m[16], bool* is_identity = nullptr) {
+        if (std::fabs(m[12]) > 1e-9 || std::fabs(m[13]) > 1e-9 || std::fabs(m[14]) > 1e-9 || std::fabs(m[15] - 1) > 1e-9)
+            fail("jsrt: non-affine transform (fourth row is not 0 0 0 1) is not supported");
+        bool ident = true;
+        for (int i = 0; i < 12; ++i) if (m[i] != ((i % 5 == 0) ? 1.0 : 0.0)) ident = false;
+        if (is_identity) *is_identity = ident;
+        if (ident) return 0;
+        Xform x; for (int i = 0; i < 12; ++i) x.m[i] = (float)m[i];
+        out.xforms.push_back(x);
+        return (int)out.xforms.size() - 1;
+    }
+
+    // ---- material colours (src/materials.js:2-76) ------------------------------
+    Folded fold(const Val* mc) {
+        mc = doc.resolve(mc);
+        const std::string& t = doc.typeName(mc);
+        Folded f{}; f.checker = false;
+        if (t == "SolidMaterialColor") {
+            double c[4]; doc.vec(doc.field(mc, "_color"), c);
+            for (int i = 0; i < 3; ++i) f.c1[i] = f.c2[i] = (float)c[i];
+        } else if (t == "ScaledMaterialColor") {
+            f = fold(doc.field(mc, "_mc"));
+            const Val* s = doc.field(mc, "_scale");
+            double sv[4] = {1, 1, 1, 1};
+            if (s && (s->type == Val::NUM || s->type == Val::NIL)) { double x = doc.number(s, kInf); sv[0] = sv[1] = sv[2] = x; }
+            else if (s) doc.vec(s, sv, kInf);
+            // `_mc.color(data).times(_scale)`: f64 product of the f32 colour, stored f32
+            for (int i = 0; i < 3; ++i) { f.c1[i] = (float)((double)f.c1[i] * sv[i]); f.c2[i] = (float)((double)f.c2[i] * sv[i]); }
+        } else if (t == "CheckerboardMaterialColor") {
+            // Nested checkerboards see the same UV, so the outer predicate selects
+            // the same side of the inner one.
+            Folded a = fold(doc.field(mc, "color1")), b = fold(doc.field(mc, "color2"));
+            for (int i = 0; i < 3; ++i) { f.c1[i] = a.c1[i]; f.c2[i] = b.checker ? b.c2[i] : b.c1[i]; }
+            f.checker = true;
+        } else if (t == "TextureMaterialColor") {
+            fail("jsrt: TextureMaterialColor (src/materials.js:77-131) is not supported yet (SURVEY.md §8f item 2)");
+        } else fail("jsrt: unknown MaterialColor type '" + t + "'");
+        return f;
+    }
+    static Color toColor(const Folded& f) {
+        Color c{}; for (int i = 0; i < 3; ++i) { c.c1[i] = f.c1[i]; c.c2[i] = f.checker ? f.c2[i] : f.c1[i]; }
+        c.checker = f.checker ? 1 : 0; return c;
+    }
+    static bool nonzero(const Color& c) { for (int i = 0; i < 3; ++i) if (c.c1[i] != 0 || c.c2[i] != 0) return true; return false; }
+
+    int material(const Val* m) {
+        m = doc.resolve(m);
+        auto it = material_of.find(m);
+        if (it != material_of.end()) return it->second;
+        const std::string& t = doc.typeName(m);
+        Material d{};
+        if (t == "PhongMaterial" || t == "FresnelPhongMaterial" || t == "PhongPathTracingMaterial") {
+            d.kind = (t == "PhongMaterial") ? M_PHONG : (t == "FresnelPhongMaterial" ? M_FRESNEL : M_PATH);
+            d.ambient = toColor(fold(doc.field(m, "ambient")));
+            d.diffusivity = toColor(fold(doc.field(m, "diffusivity")));
+            d.specularity = toColor(fold(doc.field(m, "specularity")));
+            d.reflectivity = toColor(fold(doc.field(m, "reflectivity")));
+            d.transmissivity = toColor(fold(doc.field(m, "transmissivity")));
+            d.smoothness = (float)doc.number(doc.field(m, "smoothness"), kInf);
+            d.ior = (float)(d.kind == M_PHONG ? kInf : doc.number(doc.field(m, "refractiveIndexRatio"), kInf));
+            d.mirror_prob = (float)(d.kind == M_PATH ? doc.number(doc.field(m, "mirrorProbability"), 0) : 0);
+            if (d.kind == M_PATH && !std::isfinite(d.smoothness))
+                fail("jsrt: PhongPathTracingMaterial with infinite smoothness is not executable in the reference (src/materials.js:447-474)");
+            if (d.kind == M_PHONG) { if (nonzero(d.reflectivity) && nonzero(d.transmissivity)) out.fanout = 2; }
+            else if (std::isfinite(d.ior)) out.fanout = 2;
+        } else if (t == "SolidColorMaterial") {
+            d.kind = M_SOLID; d.ambient = toColor(fold(doc.field(m, "_color")));
+        } else if (t == "TransparentMaterial") {
+            d.kind = M_TRANSPARENT; d.ambient = toColor(fold(doc.field(m, "_color")));
+            d.smoothness = (float)doc.number(doc.field(m, "_opacity"), 1);
+        } else fail("jsrt: unsupported material type '" + t + "'");
+        out.materials.push_back(d);
+        return material_of[m] = (int)out.materials.size() - 1;
+    }
+
+    // ---- geometry -----------------------------------------------------------------
+    int triangle(const Val* g, int* flags) {
+        auto it = tri_of.find(g);
+        int idx;
+        if (it != tri_of.end()) idx = it->second;
+        else {
+            const Val* ps = doc.field(g, "ps");
+            if (doc.length(ps) != 3) fail("jsrt: Triangle.ps must hold 3 points");
+            float p[3][4];
+            for (int i = 0; i < 3; ++i) { double v[4]; doc.vec(doc.at(ps, i), v); for (int k = 0; k < 4; ++k) p[i][k] = (float)v[k]; }
+            // Triangle constructor, src/geometry.js:341-353 (f64 ops, f32 stores)
+            float v0[3], v1[3], h[3], n[3];
+            for (int k = 0; k < 3; ++k) { v0[k] = (float)((double)p[1][k] - (double)p[0][k]); v1[k] = (float)((double)p[2][k] - (double)p[0][k]); }
+            h[0] = (float)((double)v0[1] * v1[2] - (double)v0[2] * v1[1]);
+            h[1] = (float)((double)v0[2] * v1[0] - (double)v0[0] * v1[2]);
+            h[2] = (float)((double)v0[0] * v1[1] - (double)v0[1] * v1[0]);
+            const double nn = std::sqrt((double)h[0] * h[0] + (double)h[1] * h[1] + (double)h[2] * h[2]);
+            for (int k = 0; k < 3; ++k) n[k] = (nn > 0.00001) ? (float)((double)h[k] * (1 / nn)) : h[k];
+            Tri t{};
+            t.nx = n[0]; t.ny = n[1]; t.nz = n[2];
+            t.delta = (float)((double)n[0] * p[0][0] + (double)n[1] * p[0][1] + (double)n[2] * p[0][2] + 0.0 * p[0][3]);
+            t.p0x = p[0][0]; t.p0y = p[0][1]; t.p0z = p[0][2];
+            t.v0x = v0[0]; t.v0y = v0[1]; t.v0z = v0[2];
+            t.v1x = v1[0]; t.v1y = v1[1]; t.v1z = v1[2];
+            t.d00 = (float)((double)v0[0] * v0[0] + (double)v0[1] * v0[1] + (double)v0[2] * v0[2]);
+            t.d11 = (float)((double)v1[0] * v1[0] + (double)v1[1] * v1[1] + (double)v1[2] * v1[2]);
+            t.d01 = (float)((double)v0[0] * v1[0] + (double)v0[1] * v1[1] + (double)v0[2] * v1[2]);
+            TriShade s{};
+            // psdata: {UV:[..], normal:[..]} — an Array here means the reference's
+            // lossy Triangle.serialize (src/geometry.js:355-357) wrote `ps` twice.
+            const Val* pd = doc.field(g, "psdata");
+            int fl = 0;
+            if (pd && doc.payload(pd) && doc.payload(pd)->type == Val::MAP) {
+                if (const Val* nv = doc.field(pd, "normal")) {
+                    if (doc.length(nv) == 3) { fl |= PF_HAS_VNORMALS; for (int i = 0; i < 3; ++i) { double v[4]; doc.vec(doc.at(nv, i), v); for (int k = 0; k < 4; ++k) s.n[i][k] = (float)v[k]; } }
+                }
+                if (const Val* uv = doc.field(pd, "UV")) {
+                    if (doc.length(uv) == 3) { fl |= PF_HAS_UVS; for (int i = 0; i < 3; ++i) { double v[4]; doc.vec(doc.at(uv, i), v); s.uv[i][0] = (float)v[0]; s.uv[i][1] = (float)v[1]; } }
+                }
+            }
+            s.pad[0] = (float)fl;
+            if (fl) any_tri_data = true;
+            out.tris.push_back(t);
+            out.tri_shade.push_back(s);
+            idx = tri_of[g] = (int)out.tris.size() - 1;
+        }
+        *flags |= (int)out.tri_shade[idx].pad[0];
+        return idx;
+    }
+
+    // Appends one placed primitive.  `outer` (may be null) is an extra inverse
+    // transform applied before the primitive's own (flattened nested Aggregates).
+    void placePrim(const Val* p, const double* outer) {
+        p = doc.resolve(p);
+        if (doc.typeName(p) != "Primitive")
+            fail("jsrt: '" + doc.typeName(p) + "' inside an aggregate is not supported (only Primitive members)");
+        Prim d{};
+        const Val* g = doc.field(p, "geometry");
+        const std::string& gt = doc.typeName(g);
+        d.geom_index = -1;
+        if (gt == "Plane" || gt == "SimplePlane") d.geom_kind = G_PLANE;
+        else if (gt == "Square") d.geom_kind = G_SQUARE;
+        else if (gt == "Circle") d.geom_kind = G_CIRCLE;
+        else if (gt == "UnitBox") d.geom_kind = G_BOX;
+        else if (gt == "AABB") {
+            d.geom_kind = G_BOX; double c[4], h[4];
+            doc.vec(doc.field(g, "center"), c); doc.vec(doc.field(g, "half_size"), h, kInf);
+            d.geom_index = (int)out.boxes.size() / 8;
+            for (int i = 0; i < 4; ++i) out.boxes.push_back((float)c[i]);
+            for (int i = 0; i < 4; ++i) out.boxes.push_back((float)h[i]);
+        }
+        else if (gt == "Sphere") d.geom_kind = G_SPHERE;
+        else if (gt == "Cylinder") d.geom_kind = G_CYLINDER;
+        else if (gt == "Triangle") { d.geom_kind = G_TRIANGLE; d.geom_index = triangle(g, &d.flags); }
+        else if (gt == "SDFGeometry") {
+            d.geom_kind = G_SDF;
+            auto it = sdf_of.find(g);
+            d.geom_index = (it != sdf_of.end()) ? it->second : (sdf_of[g] = compileSdf(doc, g, out));
+        }
+        else if (gt == "OriginPoint" || gt == "UnitLine") d.geom_kind = G_NEVER;   // intersect() returns -Infinity (src/geometry.js:34-36,59-61)
+        else fail("jsrt: unsupported geometry type '" + gt + "'");
+        d.material = material(doc.field(p, "material"));
+        double inv[16]; doc.mat4(doc.field(p, "inv_transform"), inv);
+        bool ident = false;
+        if (outer) { double c[16]; mul44(inv, outer, c); d.xform = addXform(c, &ident); }
+        else d.xform = addXform(inv, &ident);
+        if (ident) d.flags |= PF_IDENTITY_XFORM;
+        const Val* cs = doc.field(p, "does_cast_shadow");
+        if (!cs || doc.truthy(cs)) d.flags |= PF_CASTS_SHADOW;
+        auto e = ext_id.find(p);
+        if (e == ext_id.end()) fail("jsrt: primitive reachable from the BVH but not from the aggregate's objects array");
+        d.ext_id = e->second;
+        out.prims.push_back(d);
+    }
+
+    // prim_id assignment: DFS of world.objects descending into Aggregate.objects
+    void assignIds(const Val* objects) {
+        for (uint32_t i = 0; i < doc.length(objects); ++i) {
+            const Val* o = doc.at(objects, i);
+            const std::string& t = doc.typeName(o);
+            if (t == "Primitive") { if (!ext_id.count(o)) { int id = (int)ext_id.size(); ext_id[o] = id; } }
+            else if (t == "Aggregate" || t == "BVHAggregate") assignIds(doc.field(o, "objects"));
+        }
+    }
+
+    // ---- BVH layout in reference visit order (src/aggregates.js:207-225) ------------
+    void layoutNode(const Val* n, int first_node, int first_prim, int depth) {
+        n = doc.resolve(n);
+        if (depth > out.max_bvh_depth) out.max_bvh_depth = depth;
+        const int me = (int)out.nodes.size();
+        BvhNode b{};
+        const Val* box = doc.field(n, "aabb");
+        double c[4], h[4];
+        doc.vec(doc.field(box, "center"), c); doc.vec(doc.field(box, "half_size"), h, kInf);
+        b.cx = (float)c[0]; b.cy = (float)c[1]; b.cz = (float)c[2]; b.hx = (float)h[0]; b.hy = (float)h[1]; b.hz = (float)h[2];
+        b.leaf = -1;
+        out.nodes.push_back(b);
+        if (doc.truthy(doc.field(n, "isLeaf"))) {
+            const Val* objs = doc.field(n, "objects");
+            const uint32_t cnt = objs ? doc.length(objs) : 0;
+            if (cnt > 255) fail("jsrt: BVH leaf with more than 255 objects");
+            const int first = (int)out.prims.size() - first_prim;
+            if (first >= (1 << 24)) fail("jsrt: more than 16M primitives in one BVH");
+            for (uint32_t i = 0; i < cnt; ++i) placePrim(doc.at(objs, i), nullptr);
+            out.nodes[me].leaf = (int)((cnt << 24) | (uint32_t)first);
+        } else {
+            layoutNode(doc.field(n, "greater_node"), first_node, first_prim, depth + 1);
+            layoutNode(doc.field(n, "lesser_node"), first_node, first_prim, depth + 1);
+        }
+        out.nodes[me].skip = (int)out.nodes.size() - first_node;
+    }
+
+    void listMembers(const Val* objects, const double* outer) {
+        for (uint32_t i = 0; i < doc.length(objects); ++i) {
+            const Val* o = doc.at(objects, i);
+            const std::string& t = doc.typeName(o);
+            if (t == "Primitive") placePrim(o, outer);
+            else if (t == "Aggregate") {
+                // nested list: the ray is mapped by outer^-1 then inner^-1; fold into one matrix
+                double inner[16]; doc.mat4(doc.field(o, "inv_transform"), inner);
+                if (outer) { double c[16]; mul44(inner, outer, c); listMembers(doc.field(o, "objects"), c); }
+                else listMembers(doc.field(o, "objects"), inner);
+            } else fail("jsrt: '" + t + "' nested inside a plain Aggregate is not supported");
+        }
+    }
+
+    void run() {
+        const Val* root = doc.resolve(doc.root());
+        const Val* rend = doc.field(root, "renderer");
+        if (!rend) fail("jsrt: scene blob has no 'renderer' (expected Serializer({renderer,width,height}))");
+        out.renderer_type = doc.typeName(rend);
+        out.jitter = out.renderer_type != "SimpleRenderer";
+        out.width = (int)doc.number(doc.field(root, "width"), 0);
+        out.height = (int)doc.number(doc.field(root, "height"), 0);
+        if (out.width <= 0 || out.height <= 0) fail("jsrt: scene blob has no positive width/height");
+        out.max_depth = (int)doc.number(doc.field(rend, "maxRecursionDepth"), 3);
+        out.samples_per_pixel = doc.field(rend, "samplesPerPixel") ? (int)doc.number(doc.field(rend, "samplesPerPixel"), 1) : 1;
+
+        const Val* cam = doc.field(rend, "camera");
+        if (!cam) fail("jsrt: renderer has no camera");
+        double t[16]; doc.mat4(doc.field(cam, "transform"), t);
+        for (int i = 0; i < 12; ++i) out.camera.t[i] = t[i];
+        out.camera.tan_fov = doc.number(doc.field(cam, "tan_fov"), 0);
+        out.camera.aspect = doc.number(doc.field(cam, "aspect"), 1);
+        out.camera.dof = doc.typeName(cam) == "DepthOfFieldPerspectiveCamera";
+        if (out.camera.dof) {
+            out.camera.focus_distance = doc.number(doc.field(cam, "focus_distance"), 0);
+            out.camera.sensor_size = doc.number(doc.field(cam, "sensor_size"), 0);
+        }
+
+        const Val* world = doc.field(rend, "world");
+        if (!world) fail("jsrt: renderer has no world");
+        double bg[4]; doc.vec(doc.field(world, "bg_color"), bg);
+        for (int i = 0; i < 3; ++i) out.bg[i] = (float)bg[i];
+
+        Xform id{}; id.m[0] = id.m[5] = id.m[10] = 1; out.xforms.push_back(id);
+
+        const Val* objects = doc.field(world, "objects");
+        assignIds(objects);
+        out.ext_prim_count = (int)ext_id.size();
+        for (uint32_t i = 0; i < doc.length(objects); ++i) {
+            const Val* o = doc.at(objects, i);
+            const std::string& ty = doc.typeName(o);
+            Top top{};
+            if (ty == "Primitive") {
+                top.kind = T_PRIM; top.first_prim = (int)out.prims.size(); top.prim_count = 1;
+                placePrim(o, nullptr);
+            } else if (ty == "BVHAggregate") {
+                top.kind = T_BVH;
+                double inv[16]; doc.mat4(doc.field(o, "inv_transform"), inv);
+                top.xform = addXform(inv);
+                const Val* tree = doc.field(o, "kdtree");
+                auto it = tree_of.find(tree);
+                if (it == tree_of.end()) {
+                    TreeRef r{(int)out.nodes.size(), 0, (int)out.prims.size(), 0};
+                    layoutNode(tree, r.first_node, r.first_prim, 0);
+                    r.node_count = (int)out.nodes.size() - r.first_node;
+                    r.prim_count = (int)out.prims.size() - r.first_prim;
+                    it = tree_of.emplace(tree, r).first;
+                }
+                top.first_node = it->second.first_node; top.node_count = it->second.node_count;
+                top.first_prim = it->second.first_prim; top.prim_count = it->second.prim_count;
+            } else if (ty == "Aggregate") {
+                top.kind = T_LIST;
+                double inv[16]; doc.mat4(doc.field(o, "inv_transform"), inv);
+                top.xform = addXform(inv);
+                top.first_prim = (int)out.prims.size();
+                listMembers(doc.field(o, "objects"), nullptr);
+                top.prim_count = (int)out.prims.size() - top.first_prim;
+            } else fail("jsrt: unsupported world object type '" + ty + "'");
+            out.tops.push_back(top);
+        }
+        if (!any_tri_data) out.tri_shade.clear();
+
+        const Val* lights = doc.field(world, "lights");
+        for (uint32_t i = 0; lights && i < doc.length(lights); ++i) {
+            const Val* l = doc.at(lights, i);
+            const std::string& ty = doc.typeName(l);
+            Light d{};
+            Folded col = fold(doc.field(l, "color_mc"));
+            if (col.checker) fail("jsrt: checkerboard light colours are not supported");
+            for (int k = 0; k < 3; ++k) d.color[k] = col.c1[k];
+            if (ty == "SimplePointLight") {
+                d.kind = L_POINT; d.samples = 1;
+                double p[4]; doc.vec(doc.field(l, "position"), p);
+                for (int k = 0; k < 4; ++k) d.pos[k] = (float)p[k];
+            } else if (ty == "RandomSampleAreaLight") {
+                d.kind = L_AREA; d.samples = (int)doc.number(doc.field(l, "samples"), 1);
+                const std::string& gt = doc.typeName(doc.field(l, "surface_geometry"));
+                if (gt == "Square") d.geom = G_SQUARE; else if (gt == "Circle") d.geom = G_CIRCLE; else if (gt == "Sphere") d.geom = G_SPHERE;
+                else fail("jsrt: area light surface '" + gt + "' has no sampleSurface in the reference");
+                double m[16];
+                doc.mat4(doc.field(l, "transform"), m); for (int k = 0; k < 12; ++k) d.xf.m[k] = (float)m[k];
+                doc.mat4(doc.field(l, "inv_transform"), m); for (int k = 0; k < 12; ++k) d.inv.m[k] = (float)m[k];
+            } else fail("jsrt: unsupported light type '" + ty + "'");
+            out.light_samples += d.samples;
+            out.lights.push_back(d);
+        }
+    }
+};
+
+}  // namespace
+
+void flattenScene(const WireDoc& doc, HostScene& out) {
+    Flattener f(doc, out);
+    f.run();
+}
+
+}  // namespace jsrt

@@ -1,0 +1,132 @@
+// Flattened scene: the layout the CUDA kernels read from HBM/L2.  Built on the
+// host by scene_flatten.cpp from the serializer object graph and uploaded once
+// per scene.  All hot arrays are 16-byte records read with 128-bit loads.
+#pragma once
+#include <cstdint>
+
+namespace jsrt {
+
+// geometry kinds (reference src/geometry.js, src/sdf.js)
+enum GeomKind : int { G_PLANE = 0, G_SQUARE = 1, G_CIRCLE = 2, G_BOX = 3, G_SPHERE = 4, G_CYLINDER = 5, G_TRIANGLE = 6, G_SDF = 7, G_NEVER = 8 };
+// material kinds (reference src/materials.js)
+enum MatKind : int { M_PHONG = 0, M_FRESNEL = 1, M_PATH = 2, M_SOLID = 3, M_TRANSPARENT = 4 };
+// top-level object kinds (reference src/world.js Primitive, src/aggregates.js Aggregate / BVHAggregate)
+enum TopKind : int { T_PRIM = 0, T_BVH = 1, T_LIST = 2 };
+enum LightKind : int { L_POINT = 0, L_AREA = 1 };
+
+enum PrimFlags : int { PF_CASTS_SHADOW = 1, PF_IDENTITY_XFORM = 2, PF_HAS_VNORMALS = 4, PF_HAS_UVS = 8 };
+
+// 3x4 affine map, row-major: the upper three rows of a reference `inv_transform`
+// (the fourth row of every transform the scene API can build is 0 0 0 1).
+struct Xform { float m[12]; };
+
+// One placed Primitive (src/world.js:104-141).  32 bytes = two 128-bit loads.
+struct Prim {
+    int geom_kind;     // GeomKind
+    int geom_index;    // G_TRIANGLE: index into tris; G_SDF: index into sdfs; G_BOX with a non-unit AABB: index into boxes, else -1
+    int material;      // index into materials
+    int xform;         // index into xforms: the primitive's own inv_transform
+    int flags;         // PrimFlags
+    int ext_id;        // prim_id of the drop-in contract: first appearance in a DFS of world.objects
+    int pad0, pad1;
+};
+
+// Triangle constants, computed like the reference constructor
+// (src/geometry.js:335-354) in f64 from the f32 vertices, then stored f32.
+// 64 bytes = four 128-bit loads; the plane test needs only the first.
+struct Tri {
+    float nx, ny, nz, delta;      // normal (normalised v0 x v1), delta = normal . p0
+    float p0x, p0y, p0z, d01;
+    float v0x, v0y, v0z, d00;
+    float v1x, v1y, v1z, d11;
+};
+struct TriShade {                 // per-vertex shading data (only read for shaded hits)
+    float n[3][4];                // psdata.normal (w = 0)
+    float uv[3][2];               // psdata.UV
+    float pad[2];
+};
+
+// BVH node, 32 bytes = two 128-bit loads.  Nodes are laid out in the
+// reference's visit order (greater child first, src/aggregates.js:221-222) so
+// a stackless walk `i -> i+1` on hit / `i -> skip` on miss reproduces the
+// reference traversal, including its tie rule, exactly.
+struct BvhNode {
+    float cx, cy, cz, hx;         // AABB centre, half-size x   (centre/half form: src/geometry.js:189-209)
+    float hy, hz;
+    int skip;                     // next node when this subtree is done (relative to the tree's first node)
+    int leaf;                     // inner: -1; leaf: (count << 24) | first placed-primitive index (relative to the aggregate's first primitive)
+};
+
+struct Top {                      // one entry of world.objects (src/world.js:7-15 walks them in order)
+    int kind;                     // TopKind
+    int xform;                    // T_BVH / T_LIST: the aggregate's inv_transform
+    int first_prim;               // first placed primitive
+    int prim_count;               // T_PRIM: 1
+    int first_node;               // T_BVH: first BvhNode
+    int node_count;
+    int pad0, pad1;
+};
+
+struct Color {                    // a MaterialColor folded to Solid or Checkerboard (src/materials.js:27-76)
+    float c1[3];
+    int checker;
+    float c2[3];
+    int pad;
+};
+
+struct Material {                 // src/materials.js:145-476
+    int kind;                     // MatKind
+    float smoothness;
+    float ior;                    // refractiveIndexRatio (may be +Inf)
+    float mirror_prob;
+    Color ambient, diffusivity, specularity, reflectivity, transmissivity;   // M_SOLID/M_TRANSPARENT: colour in `ambient`, opacity in `smoothness`
+};
+
+struct Light {                    // src/lights.js
+    int kind;                     // LightKind
+    int samples;
+    int geom;                     // L_AREA: GeomKind of surface_geometry (G_SQUARE, G_CIRCLE, G_SPHERE)
+    int pad;
+    float pos[4];                 // L_POINT
+    float color[4];               // folded solid colour (colour * intensity)
+    Xform xf;                     // L_AREA transform
+    Xform inv;                    // L_AREA inv_transform
+};
+
+// SDF programs: see sdf_compile.cpp / kernels.cu for the bytecode.
+enum SdfOp : int {
+    S_END = 0,
+    S_SPHERE,      // a0 = radius                        push |p| - r
+    S_BOX,         // a0..a2 = size                      push box distance
+    S_TETRA,       //                                     push tetrahedron distance
+    S_MIN, S_MAX,  //                                     pop 2, push
+    S_NEG,         //                                     negate top
+    S_ADDC,        // a0                                  top += a0
+    S_SMIN,        // a0 = k                              pop b, a; push smoothMin(a, b, k)
+    S_SMIN_NEGA,   // a0 = k                              pop b, a; push -smoothMin(-a, b, k)   (SmoothDifference)
+    S_SMIN_NEGAB,  // a0 = k                              pop b, a; push -smoothMin(-a, -b, k)  (SmoothIntersection)
+    S_PUSHP,       //                                     duplicate the point, push scale 1
+    S_POPP,        //                                     drop the point and scale
+    S_MULS,        //                                     top distance *= current scale
+    S_XFORM,       // a0 = xform index (bits), a1 = scale  p = M p; scale *= a1
+    S_REFL,        // a0..a2 = normal, a3 = delta
+    S_REP,         // a0..a2 = sizes
+};
+struct SdfInstr { int op; float a0, a1, a2, a3; int pad[3]; };   // 32 bytes
+struct SdfProgram {
+    int first_instr, instr_count;
+    int max_samples;
+    int uniform_base;             // 1: every leaf has the same basecolor (in `base`)
+    float distance_epsilon, max_trace_distance, normal_step_size, pad0;
+    float cx, cy, cz, hx, hy, hz; // SDFGeometry.aabb
+    float base[3];
+    float pad1[3];
+};
+
+struct Camera {                   // src/cameras.js; f64 so primary rays match the reference bit for bit
+    double t[12];                 // transform rows 0..2
+    double tan_fov, aspect, focus_distance, sensor_size;
+    int dof, pad;
+};
+
+}  // namespace jsrt

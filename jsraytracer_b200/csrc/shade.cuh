@@ -1,0 +1,213 @@
+// Shading on the device: Primitive.color (src/world.js:125-137), geometry
+// materialData (src/geometry.js, src/sdf.js:41-47), MaterialColor evaluation
+// (src/materials.js:27-76), PhongMaterial / FresnelPhongMaterial /
+// PhongPathTracingMaterial (src/materials.js:195-476) and the light samplers
+// (src/lights.js:45-53,80-93).
+//
+// The reference evaluates the bounce tree depth-first and multiplies child
+// colours on the way back up; a wavefront instead carries the product of the
+// weights on the way down (`throughput`) and adds every term straight into the
+// pixel: ambient immediately, each light sample when its shadow ray comes back
+// unoccluded, children as new rays.  Same sum, different association.
+#pragma once
+#include "rng.h"
+#include "trace.cuh"
+
+namespace jsrt {
+
+struct SurfaceData {           // the `data` object of materials.js
+    float3 position;           // world
+    float3 normal;             // world, normalised (src/world.js:134)
+    float2 uv; bool has_uv;
+    float3 basecolor;          // SDF only; (1,1,1) otherwise
+};
+
+JSRT_DEV float3 color_eval(const Color& c, const SurfaceData& s) {
+    if (!c.checker) return f3(c.c1[0], c.c1[1], c.c1[2]);
+    // CheckerboardMaterialColor.color src/materials.js:72-75 (f64: UV can be huge towards the horizon)
+    const double u = s.has_uv ? (double)s.uv.x : 0.0, v = s.has_uv ? (double)s.uv.y : 0.0;
+    const double a = floor(u) + floor(v);
+    const double m = a - floor(a * 0.5) * 2.0;
+    return (fmod(m, 2.0) < 1.0) ? f3(c.c1[0], c.c1[1], c.c1[2]) : f3(c.c2[0], c.c2[1], c.c2[2]);
+}
+
+// Vec.cartesianToSpherical src/math.js:189-193
+JSRT_DEV float2 cartesian_to_spherical(float3 n) {
+    return make_float2(0.5f + atan2f(n.z, n.x) / (2.f * CUDART_PI_F), 0.5f - asinf(n.y) / CUDART_PI_F);
+}
+// Vec.spherePick src/math.js:180-188
+JSRT_DEV float3 sphere_pick(float u0, float u1) {
+    const float theta = 2.0f * CUDART_PI_F * u0, phi = acosf(2.0f * u1 - 1.0f);
+    float st, ct; sincosf(theta, &st, &ct);
+    const float sin_phi = sinf(phi);
+    return f3(ct * sin_phi, cosf(phi), st * sin_phi);
+}
+
+// geometry.materialData in the primitive's local space -> local normal, UV, basecolor.
+JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index, int flags, float3 lp,
+                            float3& n, float2& uv, bool& has_uv, float3& base) {
+    has_uv = false; uv = make_float2(0.f, 0.f); base = f3(1.f, 1.f, 1.f); n = f3(0.f, 0.f, 1.f);
+    switch (geom_kind) {
+        case G_PLANE: case G_SQUARE: case G_CIRCLE:       // src/geometry.js:249-254
+            n = f3(0.f, 0.f, 1.f); uv = make_float2(lp.x, lp.y); has_uv = true; break;
+        case G_BOX: {                                     // AABB.materialData src/geometry.js:210-224
+            float3 c = f3(0.f, 0.f, 0.f), h = f3(0.5f, 0.5f, 0.5f);
+            if (geom_index >= 0) { const float* b = sc.boxes + 8 * geom_index; c = f3(b[0], b[1], b[2]); h = f3(b[4], b[5], b[6]); }
+            float norm_dist = 0.f; n = f3(0.f, 0.f, 0.f);
+            const float cx = (lp.x - c.x) / h.x, cy = (lp.y - c.y) / h.y, cz = (lp.z - c.z) / h.z;
+            if (fabsf(cx) > norm_dist) { norm_dist = fabsf(cx); n = f3(js_sign(cx), 0.f, 0.f); }
+            if (fabsf(cy) > norm_dist) { norm_dist = fabsf(cy); n = f3(0.f, js_sign(cy), 0.f); }
+            if (fabsf(cz) > norm_dist) { norm_dist = fabsf(cz); n = f3(0.f, 0.f, js_sign(cz)); }
+            break;
+        }
+        case G_SPHERE: {                                  // src/geometry.js:449-455: position is a 4-vector with w = 1 (sic)
+            const float nn = sqrtf(lp.x * lp.x + lp.y * lp.y + lp.z * lp.z + 1.f);
+            n = (nn > 0.00001f) ? lp * (1.f / nn) : lp;
+            uv = cartesian_to_spherical(n); has_uv = true; break;
+        }
+        case G_CYLINDER:                                  // src/geometry.js:479-487
+            n = normalized3(f3(lp.x, lp.y, 0.f));
+            uv = make_float2(0.5f + atan2f(lp.y, lp.x) / (2.f * CUDART_PI_F), 0.5f + lp.z); has_uv = true; break;
+        case G_TRIANGLE: {                                // src/geometry.js:376-385,397-409
+            const float4 a = __ldg(reinterpret_cast<const float4*>(sc.tris + geom_index));
+            n = f3(a.x, a.y, a.z);
+            if (flags & (PF_HAS_VNORMALS | PF_HAS_UVS)) {
+                const float3 bary = triangle_bary(sc.tris, geom_index, lp);
+                const TriShade* ts = sc.tri_shade + geom_index;
+                if (flags & PF_HAS_UVS) {
+                    uv = make_float2(ts->uv[0][0] * bary.x + ts->uv[1][0] * bary.y + ts->uv[2][0] * bary.z,
+                                     ts->uv[0][1] * bary.x + ts->uv[1][1] * bary.y + ts->uv[2][1] * bary.z);
+                    has_uv = true;
+                }
+                if (flags & PF_HAS_VNORMALS)
+                    n = f3(ts->n[0][0] * bary.x + ts->n[1][0] * bary.y + ts->n[2][0] * bary.z,
+                           ts->n[0][1] * bary.x + ts->n[1][1] * bary.y + ts->n[2][1] * bary.z,
+                           ts->n[0][2] * bary.x + ts->n[1][2] * bary.y + ts->n[2][2] * bary.z);
+            }
+            break;
+        }
+        case G_SDF: {                                     // src/sdf.js:41-47: forward differences
+            const SdfProgram& pr = sc.sdfs[geom_index];
+            const SdfInstr* prog = sc.sdf_code + pr.first_instr;
+            const float s = pr.normal_step_size;
+            const float d0 = sdf_eval(prog, sc.xforms, lp);
+            const float dx = sdf_eval(prog, sc.xforms, f3(lp.x + s, lp.y, lp.z));
+            const float dy = sdf_eval(prog, sc.xforms, f3(lp.x, lp.y + s, lp.z));
+            const float dz = sdf_eval(prog, sc.xforms, f3(lp.x, lp.y, lp.z + s));
+            n = normalized3(f3((dx - d0) / s, (dy - d0) / s, (dz - d0) / s));
+            base = f3(pr.base[0], pr.base[1], pr.base[2]);
+            break;
+        }
+        default: break;
+    }
+}
+
+struct LightSample { float3 direction; float3 color; };
+
+// Light.sampleIterator for sample `u0,u1` (src/lights.js:45-53,80-93)
+JSRT_DEV LightSample light_sample(const Light& l, float3 P, float u0, float u1) {
+    LightSample s;
+    const float3 lc = f3(l.color[0], l.color[1], l.color[2]);
+    if (l.kind == L_POINT) {
+        s.direction = f3(l.pos[0], l.pos[1], l.pos[2]) - P;
+        s.color = lc * (1.f / (4.f * CUDART_PI_F * dot3(s.direction, s.direction)));     // Light.falloff :21-23
+        return s;
+    }
+    float3 lp, ln;
+    if (l.geom == G_SPHERE) {                              // Sphere.sampleSurface + Sphere.materialData (w = 1 quirk)
+        lp = sphere_pick(u0, u1);
+        const float nn = sqrtf(dot3(lp, lp) + 1.f);
+        ln = lp * (1.f / nn);
+    } else {                                               // Square / Circle.sampleSurface src/geometry.js:295-300,326-331
+        lp = f3(u0 - 0.5f, u1 - 0.5f, 0.f); ln = f3(0.f, 0.f, 1.f);
+    }
+    const XformReg xf = load_xform(&l.xf, 0), inv = load_xform(&l.inv, 0);
+    const float3 wp = xf_point(xf, lp);
+    s.direction = wp - P;
+    const float3 nl = normalized3(xf_normal(inv, ln));
+    const float fall = 1.f / (4.f * CUDART_PI_F * dot3(s.direction, s.direction));
+    s.color = lc * (fall * fabsf(dot3(normalized3(s.direction), nl)));
+    return s;
+}
+
+struct PhongFactors {          // PhongMaterial.getBaseFactors src/materials.js:210-238 (+ Fresnel :302-308)
+    float3 V, N, R;
+    bool backside; float vdotn;
+    float3 ambient, diffusivity, specularity, reflectivity, transmissivity;
+    float smoothness;
+    float kr; bool has_refr; float3 refr;
+};
+
+JSRT_DEV void base_factors(const Material& m, const SurfaceData& s, float3 ray_dir, PhongFactors& f) {
+    f.V = normalized3(ray_dir) * -1.f;
+    f.N = normalized3(s.normal); f.backside = false; f.vdotn = dot3(f.V, f.N);
+    if (f.vdotn < 0.f) { f.N = f.N * -1.f; f.backside = true; f.vdotn = -f.vdotn; }
+    f.R = normalized3(f.N * (2.f * f.vdotn) - f.V);
+    f.ambient = s.basecolor * color_eval(m.ambient, s);
+    f.diffusivity = s.basecolor * color_eval(m.diffusivity, s);
+    f.specularity = color_eval(m.specularity, s);
+    f.reflectivity = color_eval(m.reflectivity, s);
+    f.transmissivity = color_eval(m.transmissivity, s);
+    f.smoothness = m.smoothness;
+    f.kr = 1.f; f.has_refr = false; f.refr = f3(0.f, 0.f, 0.f);
+    if (m.kind == M_FRESNEL || m.kind == M_PATH) {
+        const float ior = m.ior;
+        // fresnelReflectionFactor src/materials.js:366-386
+        if (isfinite(ior)) {
+            const float ni = f.backside ? ior : 1.f, nt = f.backside ? 1.f : ior;
+            const float cosi = f.vdotn, sint = ni / nt * sqrtf(fmaxf(0.f, 1.f - cosi * cosi));
+            if (sint >= 1.f) f.kr = 1.f;
+            else {
+                const float cost = sqrtf(fmaxf(0.f, 1.f - sint * sint));
+                const float Rs = ((nt * cosi) - (ni * cost)) / ((nt * cosi) + (ni * cost));
+                const float Rp = ((ni * cosi) - (nt * cost)) / ((ni * cosi) + (nt * cost));
+                f.kr = (Rs * Rs + Rp * Rp) / 2.f;
+            }
+        }
+        // getRefractionDirection src/materials.js:358-364
+        const float r = f.backside ? ior : 1.f / ior, k = 1.f - r * r * (1.f - f.vdotn * f.vdotn);
+        if (!(k < 0.f)) { f.has_refr = true; f.refr = (f.V * -1.f) * r + f.N * (r * f.vdotn - sqrtf(k)); }
+    }
+}
+
+// colorFromLightSample: PhongMaterial src/materials.js:261-269, FresnelPhongMaterial :340-356
+JSRT_DEV float3 color_from_light_sample(const Material& m, const PhongFactors& f, const LightSample& ls) {
+    const float3 L = normalized3(ls.direction);
+    float diffuse, specular;
+    if (m.kind == M_PHONG) {
+        diffuse = fmaxf(dot3(L, f.N), 0.f);
+        specular = powf(fmaxf(dot3(L, f.R), 0.f), f.smoothness);
+    } else {
+        const float ldotn = dot3(L, f.N);
+        diffuse = 0.f; specular = 0.f;
+        if (f.kr > 0.f && ldotn >= 0.f) { diffuse += f.kr * ldotn; specular += f.kr * powf(fmaxf(dot3(L, f.R), 0.f), f.smoothness); }
+        if (f.kr < 1.f && ldotn <= 0.f) {
+            diffuse += (1.f - f.kr) * -ldotn;
+            specular += (1.f - f.kr) * powf(fmaxf(f.has_refr ? dot3(L, f.refr) : 0.f, 0.f), f.smoothness);
+        }
+    }
+    return ls.color * (f.diffusivity * diffuse) + ls.color * (f.specularity * specular);
+}
+
+// scatter(): FresnelPhongMaterial src/materials.js:335-337, PhongPathTracingMaterial :398-412.
+// Returns false for a null direction.  dims: +0 mirror test, +1 lobe choice, +2,+3 spherePick.
+JSRT_DEV bool scatter(const Material& m, const PhongFactors& f, bool has_R, float3 R, float3 N, uint32_t node_key, uint32_t dim_base,
+                      float3& dir, float3& col) {
+    col = f3(1.f, 1.f, 1.f);
+    if (m.kind != M_PATH) { dir = R; return has_R; }
+    if (rng_u01(node_key, dim_base + 0) < m.mirror_prob) { dir = R; return has_R; }
+    const float diffuseProb = (f.diffusivity.x + f.diffusivity.y + f.diffusivity.z) / 3.f,
+                specularProb = (f.specularity.x + f.specularity.y + f.specularity.z) / 3.f;
+    const float probSum = diffuseProb + specularProb;
+    if (probSum == 0.f) return false;
+    if (rng_u01(node_key, dim_base + 1) < (diffuseProb / probSum)) {
+        dir = normalized3(N + sphere_pick(rng_u01(node_key, dim_base + 2), rng_u01(node_key, dim_base + 3)));   // scatterDiffuse :438-440
+        col = f.diffusivity * (1.f / CUDART_PI_F);
+        return true;
+    }
+    col = f.specularity;       // scatterSpecular :441-445 returns R for finite smoothness
+    dir = R;
+    return has_R;
+}
+
+}  // namespace jsrt

@@ -1,0 +1,285 @@
+// See wire.h.  JSON reader accepts, besides RFC 8259, the tokens Infinity /
+// -Infinity / NaN (Python's json module writes them; JSON.stringify writes
+// null, handled by WireDoc::number's nil_value).
+#include "wire.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+namespace jsrt {
+
+static const int kMaxDepth = 4096;
+
+uint64_t WireDoc::commit(const std::vector<Val>& kids) {
+    uint64_t first = arena_.size();
+    arena_.insert(arena_.end(), kids.begin(), kids.end());
+    return first;
+}
+
+static inline void skipWs(const char*& p, const char* e) {
+    while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
+}
+static inline bool lit(const char*& p, const char* e, const char* s) {
+    size_t n = strlen(s);
+    if ((size_t)(e - p) >= n && !memcmp(p, s, n)) { p += n; return true; }
+    return false;
+}
+
+Val WireDoc::parseJson(const char*& p, const char* e, int depth) {
+    if (depth > kMaxDepth) fail("jsrt: JSON nesting too deep");
+    skipWs(p, e);
+    if (p >= e) fail("jsrt: unexpected end of JSON");
+    Val v;
+    char c = *p;
+    if (c == '{') {
+        ++p; v.type = Val::MAP;
+        std::vector<Val> kids;
+        skipWs(p, e);
+        if (p < e && *p == '}') { ++p; v.first = arena_.size(); return v; }
+        for (;;) {
+            skipWs(p, e);
+            if (p >= e || *p != '"') fail("jsrt: JSON object key expected");
+            kids.push_back(parseJson(p, e, depth + 1));
+            skipWs(p, e);
+            if (p >= e || *p != ':') fail("jsrt: JSON ':' expected");
+            ++p;
+            kids.push_back(parseJson(p, e, depth + 1));
+            skipWs(p, e);
+            if (p < e && *p == ',') { ++p; continue; }
+            if (p < e && *p == '}') { ++p; break; }
+            fail("jsrt: JSON object malformed");
+        }
+        v.count = (uint32_t)(kids.size() / 2);
+        v.first = commit(kids);
+        return v;
+    }
+    if (c == '[') {
+        ++p; v.type = Val::ARR;
+        std::vector<Val> kids;
+        skipWs(p, e);
+        if (p < e && *p == ']') { ++p; v.first = arena_.size(); return v; }
+        for (;;) {
+            kids.push_back(parseJson(p, e, depth + 1));
+            skipWs(p, e);
+            if (p < e && *p == ',') { ++p; continue; }
+            if (p < e && *p == ']') { ++p; break; }
+            fail("jsrt: JSON array malformed");
+        }
+        v.count = (uint32_t)kids.size();
+        v.first = commit(kids);
+        return v;
+    }
+    if (c == '"') {
+        ++p; v.type = Val::STR; v.str = p;
+        while (p < e && *p != '"') { if (*p == '\\') ++p; ++p; }   // escapes are kept raw; type names and keys have none
+        if (p >= e) fail("jsrt: unterminated JSON string");
+        v.count = (uint32_t)(p - v.str);
+        ++p;
+        return v;
+    }
+    if (lit(p, e, "true")) { v.type = Val::BOOL; v.b = true; return v; }
+    if (lit(p, e, "false")) { v.type = Val::BOOL; v.b = false; return v; }
+    if (lit(p, e, "null")) { v.type = Val::NIL; return v; }
+    v.type = Val::NUM;
+    if (lit(p, e, "NaN")) { v.num = std::nan(""); return v; }
+    if (lit(p, e, "Infinity")) { v.num = std::numeric_limits<double>::infinity(); return v; }
+    if (lit(p, e, "-Infinity")) { v.num = -std::numeric_limits<double>::infinity(); return v; }
+    char* end = nullptr;
+    v.num = strtod(p, &end);
+    if (end == p) fail("jsrt: JSON value expected");
+    p = end;
+    return v;
+}
+
+// ---- msgpack ------------------------------------------------------------------
+static inline uint64_t be(const uint8_t*& p, const uint8_t* e, int n) {
+    if (e - p < n) fail("jsrt: truncated msgpack");
+    uint64_t x = 0;
+    for (int i = 0; i < n; ++i) x = (x << 8) | *p++;
+    return x;
+}
+
+Val WireDoc::parseMsgpack(const uint8_t*& p, const uint8_t* e, int depth) {
+    if (depth > kMaxDepth) fail("jsrt: msgpack nesting too deep");
+    if (p >= e) fail("jsrt: truncated msgpack");
+    Val v;
+    uint8_t t = *p++;
+    auto str = [&](uint64_t n) { if ((uint64_t)(e - p) < n) fail("jsrt: truncated msgpack string"); v.type = Val::STR; v.str = (const char*)p; v.count = (uint32_t)n; p += n; };
+    auto arr = [&](uint64_t n) {
+        v.type = Val::ARR; std::vector<Val> kids; kids.reserve(n);
+        for (uint64_t i = 0; i < n; ++i) kids.push_back(parseMsgpack(p, e, depth + 1));
+        v.count = (uint32_t)n; v.first = commit(kids);
+    };
+    auto map = [&](uint64_t n) {
+        v.type = Val::MAP; std::vector<Val> kids; kids.reserve(2 * n);
+        for (uint64_t i = 0; i < 2 * n; ++i) kids.push_back(parseMsgpack(p, e, depth + 1));
+        v.count = (uint32_t)n; v.first = commit(kids);
+    };
+    if (t <= 0x7f) { v.type = Val::NUM; v.num = t; }
+    else if (t >= 0xe0) { v.type = Val::NUM; v.num = (int8_t)t; }
+    else if (t >= 0xa0 && t <= 0xbf) str(t & 0x1f);
+    else if (t >= 0x90 && t <= 0x9f) arr(t & 0x0f);
+    else if (t >= 0x80 && t <= 0x8f) map(t & 0x0f);
+    else switch (t) {
+        case 0xc0: v.type = Val::NIL; break;
+        case 0xc2: v.type = Val::BOOL; v.b = false; break;
+        case 0xc3: v.type = Val::BOOL; v.b = true; break;
+        case 0xca: { uint32_t x = (uint32_t)be(p, e, 4); float f; memcpy(&f, &x, 4); v.type = Val::NUM; v.num = f; break; }
+        case 0xcb: { uint64_t x = be(p, e, 8); double d; memcpy(&d, &x, 8); v.type = Val::NUM; v.num = d; break; }
+        case 0xcc: v.type = Val::NUM; v.num = (double)be(p, e, 1); break;
+        case 0xcd: v.type = Val::NUM; v.num = (double)be(p, e, 2); break;
+        case 0xce: v.type = Val::NUM; v.num = (double)be(p, e, 4); break;
+        case 0xcf: v.type = Val::NUM; v.num = (double)be(p, e, 8); break;
+        case 0xd0: v.type = Val::NUM; v.num = (double)(int8_t)be(p, e, 1); break;
+        case 0xd1: v.type = Val::NUM; v.num = (double)(int16_t)be(p, e, 2); break;
+        case 0xd2: v.type = Val::NUM; v.num = (double)(int32_t)be(p, e, 4); break;
+        case 0xd3: v.type = Val::NUM; v.num = (double)(int64_t)be(p, e, 8); break;
+        case 0xd9: str(be(p, e, 1)); break;
+        case 0xda: str(be(p, e, 2)); break;
+        case 0xdb: str(be(p, e, 4)); break;
+        case 0xc4: str(be(p, e, 1)); break;   // bin8/16/32 treated as strings
+        case 0xc5: str(be(p, e, 2)); break;
+        case 0xc6: str(be(p, e, 4)); break;
+        case 0xdc: arr(be(p, e, 2)); break;
+        case 0xdd: arr(be(p, e, 4)); break;
+        case 0xde: map(be(p, e, 2)); break;
+        case 0xdf: map(be(p, e, 4)); break;
+        default: fail("jsrt: unsupported msgpack type byte");
+    }
+    return v;
+}
+
+WireDoc::WireDoc(const uint8_t* blob, size_t len, int format) {
+    if (!blob || !len) fail("jsrt: empty scene blob");
+    if (format == 0) {
+        const char* p = (const char*)blob; const char* e = p + len;
+        root_ = parseJson(p, e, 0);
+        skipWs(p, e);
+        if (p != e) fail("jsrt: trailing bytes after JSON document");
+    } else if (format == 1) {
+        const uint8_t* p = blob; const uint8_t* e = blob + len;
+        root_ = parseMsgpack(p, e, 0);
+        if (p != e) fail("jsrt: trailing bytes after msgpack document");
+    } else fail("jsrt: unknown scene format (0 = JSON, 1 = msgpack)");
+    indexGraph();
+}
+
+bool WireDoc::keyEq(const Val* k, const char* s) {
+    size_t n = strlen(s);
+    return k->type == Val::STR && k->count == n && !memcmp(k->str, s, n);
+}
+
+const Val* WireDoc::mapGet(const Val* map, const char* key) const {
+    if (!map || map->type != Val::MAP) return nullptr;
+    for (uint32_t i = 0; i < map->count; ++i)
+        if (keyEq(&arena_[map->first + 2 * i], key)) return &arena_[map->first + 2 * i + 1];
+    return nullptr;
+}
+
+// One pass in document order: register type names (`_t` = [name, idx] on first
+// appearance, src/serializer.js:38-41) and referenced objects (`_r` next to `_t`).
+void WireDoc::indexGraph() {
+    std::vector<const Val*> stack{&root_};
+    // document order matters only for type names; a DFS that pushes children in
+    // reverse keeps it.
+    while (!stack.empty()) {
+        const Val* v = stack.back(); stack.pop_back();
+        if (v->type == Val::MAP) {
+            const Val* t = mapGet(v, "_t");
+            if (t) {
+                if (t->type == Val::ARR && t->count == 2) {
+                    const Val* nm = child(t, 0); const Val* ix = child(t, 1);
+                    size_t idx = (size_t)ix->num;
+                    if (typenames_.size() <= idx) typenames_.resize(idx + 1);
+                    typenames_[idx] = std::string(nm->str, nm->count);
+                }
+                const Val* r = mapGet(v, "_r");
+                if (r && r->type == Val::NUM) refs_[(long long)r->num] = v;
+            }
+            for (uint32_t i = v->count; i-- > 0;) stack.push_back(&arena_[v->first + 2 * i + 1]);
+        } else if (v->type == Val::ARR) {
+            for (uint32_t i = v->count; i-- > 0;) stack.push_back(&arena_[v->first + i]);
+        }
+    }
+}
+
+const Val* WireDoc::resolve(const Val* v) const {
+    if (!v || v->type != Val::MAP) return v;
+    if (mapGet(v, "_t")) return v;
+    const Val* r = mapGet(v, "_r");
+    if (!r) return v;
+    auto it = refs_.find((long long)r->num);
+    if (it == refs_.end()) fail("jsrt: dangling reference _r in scene blob");
+    return it->second;
+}
+
+bool WireDoc::isObject(const Val* v) const { return v && v->type == Val::MAP && mapGet(v, "_t"); }
+
+const std::string& WireDoc::typeName(const Val* v) const {
+    if (!isObject(v)) return empty_;
+    const Val* t = mapGet(v, "_t");
+    size_t idx = (t->type == Val::ARR) ? (size_t)child(t, 1)->num : (size_t)t->num;
+    if (idx >= typenames_.size()) fail("jsrt: type index without a name in scene blob");
+    return typenames_[idx];
+}
+
+const Val* WireDoc::payload(const Val* v) const { return isObject(v) ? mapGet(v, "_v") : v; }
+
+const Val* WireDoc::field(const Val* obj, const char* key) const {
+    obj = resolve(obj);
+    const Val* pv = payload(obj);
+    const Val* f = mapGet(pv, key);
+    return f ? resolve(f) : nullptr;
+}
+
+uint32_t WireDoc::length(const Val* obj) const {
+    const Val* pv = payload(resolve(obj));
+    return (pv && pv->type == Val::ARR) ? pv->count : 0;
+}
+
+const Val* WireDoc::at(const Val* obj, uint32_t i) const {
+    const Val* pv = payload(resolve(obj));
+    if (!pv || pv->type != Val::ARR || i >= pv->count) fail("jsrt: array index out of range in scene blob");
+    return resolve(child(pv, i));
+}
+
+double WireDoc::number(const Val* v, double nil_value) const {
+    if (!v || v->type == Val::NIL) return nil_value;
+    if (v->type == Val::NUM) return v->num;
+    if (v->type == Val::BOOL) return v->b ? 1 : 0;
+    fail("jsrt: number expected in scene blob");
+}
+
+bool WireDoc::truthy(const Val* v) const {
+    if (!v) return false;
+    switch (v->type) {
+        case Val::NIL: return false;
+        case Val::BOOL: return v->b;
+        case Val::NUM: return v->num != 0 && v->num == v->num;
+        case Val::STR: return v->count != 0;
+        default: return true;
+    }
+}
+
+int WireDoc::vec(const Val* v, double out[4], double nil_value) const {
+    const Val* pv = payload(resolve(v));
+    if (!pv || pv->type != Val::ARR) fail("jsrt: Vec expected in scene blob");
+    int n = (int)pv->count;
+    for (int i = 0; i < 4; ++i) out[i] = 0;
+    for (int i = 0; i < n && i < 4; ++i) out[i] = number(child(pv, i), nil_value);
+    return n;
+}
+
+void WireDoc::mat4(const Val* v, double out[16]) const {
+    const Val* pv = payload(resolve(v));
+    if (!pv || pv->type != Val::ARR || pv->count != 4) fail("jsrt: 4x4 Mat expected in scene blob");
+    for (int r = 0; r < 4; ++r) {
+        const Val* row = payload(resolve(child(pv, r)));
+        if (!row || row->type != Val::ARR || row->count != 4) fail("jsrt: 4x4 Mat row expected in scene blob");
+        for (int c = 0; c < 4; ++c) out[r * 4 + c] = number(child(row, c), std::numeric_limits<double>::infinity());
+    }
+}
+
+}  // namespace jsrt

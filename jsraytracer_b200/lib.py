@@ -1,0 +1,209 @@
+"""ctypes binding of the C-ABI library (include/jsrt.h).  This is the Python
+stand-in for the N-API addon a Node host would load: same
+entry points, plain pointers and sizes.
+
+The library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a) as
+`jsraytracer_b200/libjsrt.so`.  There is no fallback: a missing library or a
+missing CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjsrt.so")
+
+FORMAT_JSON = 0
+FORMAT_MSGPACK = 1
+FLAG_NO_JITTER = 1
+
+_LIB = None
+
+
+class JsrtError(RuntimeError):
+    pass
+
+
+class Info(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "width", "height", "samples_per_pixel", "max_depth", "jitter", "n_top", "n_prims", "n_ext_prims", "n_nodes",
+        "n_tris", "n_materials", "n_lights", "n_sdfs", "n_sdf_instrs", "light_samples", "fanout", "max_bvh_depth",
+        "batch_samples")] + [("scene_bytes", C.c_uint64), ("queue_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays_primary", "rays_secondary", "rays_shadow", "shaded_hits", "launches",
+                                          "camera_samples")] + \
+               [(n, C.c_double) for n in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow")]
+
+    def as_dict(self):
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d["rays"] = d["rays_primary"] + d["rays_secondary"] + d["rays_shadow"]
+        return d
+
+
+class BvhNode(C.Structure):
+    _fields_ = [("depth", C.c_int32), ("is_leaf", C.c_int32), ("obj_first", C.c_int32), ("obj_count", C.c_int32),
+                ("lesser", C.c_int32), ("greater", C.c_int32),
+                ("center", C.c_float * 4), ("half_size", C.c_float * 4), ("min", C.c_float * 4), ("max", C.c_float * 4)]
+
+
+EXPORTS = [
+    "jsrt_device_count", "jsrt_scene_create", "jsrt_scene_create_host", "jsrt_scene_destroy", "jsrt_scene_upload",
+    "jsrt_scene_set_stream", "jsrt_render", "jsrt_reset_accum", "jsrt_synchronize", "jsrt_resolve_rgba8",
+    "jsrt_read_accum", "jsrt_accum_device_ptr", "jsrt_add_passes", "jsrt_primary_hits", "jsrt_scene_info",
+    "jsrt_stats_get", "jsrt_stats_reset", "jsrt_set_profiling", "jsrt_last_error", "jsrt_bvh_build",
+    "jsrt_bvh_node_count", "jsrt_bvh_leaf_object_count", "jsrt_bvh_copy", "jsrt_bvh_free",
+]
+
+
+def load():
+    """Loads libjsrt.so; raises if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise JsrtError("libjsrt.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u64, sz = C.c_void_p, C.c_int, C.c_uint64, C.c_size_t
+    L.jsrt_device_count.restype = i32
+    L.jsrt_scene_create.restype = vp
+    L.jsrt_scene_create.argtypes = [vp, sz, i32, vp, i32]
+    L.jsrt_scene_create_host.restype = vp
+    L.jsrt_scene_create_host.argtypes = [vp, sz, i32]
+    L.jsrt_scene_destroy.argtypes = [vp]
+    L.jsrt_scene_destroy.restype = None
+    L.jsrt_scene_upload.argtypes = [vp]
+    L.jsrt_scene_set_stream.argtypes = [vp, vp]
+    L.jsrt_render.argtypes = [vp, i32, i32, u64, i32, i32, i32]
+    L.jsrt_reset_accum.argtypes = [vp]
+    L.jsrt_synchronize.argtypes = [vp]
+    L.jsrt_resolve_rgba8.argtypes = [vp, vp]
+    L.jsrt_read_accum.argtypes = [vp, vp, vp]
+    L.jsrt_accum_device_ptr.restype = vp
+    L.jsrt_accum_device_ptr.argtypes = [vp]
+    L.jsrt_add_passes.argtypes = [vp, i32]
+    L.jsrt_primary_hits.argtypes = [vp, vp, vp]
+    L.jsrt_scene_info.argtypes = [vp, vp]
+    L.jsrt_stats_get.argtypes = [vp, vp]
+    L.jsrt_stats_reset.argtypes = [vp]
+    L.jsrt_set_profiling.argtypes = [vp, i32]
+    L.jsrt_last_error.restype = C.c_char_p
+    L.jsrt_bvh_build.restype = vp
+    L.jsrt_bvh_build.argtypes = [i32, vp, vp, vp, vp, C.c_double, i32]
+    L.jsrt_bvh_node_count.argtypes = [vp]
+    L.jsrt_bvh_leaf_object_count.argtypes = [vp]
+    L.jsrt_bvh_copy.argtypes = [vp, vp, vp]
+    L.jsrt_bvh_free.argtypes = [vp]
+    L.jsrt_bvh_free.restype = None
+    _LIB = L
+    return L
+
+
+def last_error():
+    return load().jsrt_last_error().decode("utf8", "replace")
+
+
+def device_count():
+    return load().jsrt_device_count()
+
+
+class Scene:
+    """Owns one `jsrt_scene*`."""
+
+    def __init__(self, blob: bytes, fmt: int = FORMAT_MSGPACK, device: int | None = 0):
+        """device=None: parse + flatten only (no CUDA); rendering then fails."""
+        self._L = load()
+        if isinstance(blob, str):
+            blob = blob.encode("utf8")
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        if device is None:
+            self._h = self._L.jsrt_scene_create_host(buf, len(blob), fmt)
+        else:
+            dev = (C.c_int * 1)(device)
+            self._h = self._L.jsrt_scene_create(buf, len(blob), fmt, dev, 1)
+        if not self._h:
+            raise JsrtError(last_error())
+        self.info = self.get_info()
+        self.size = (self.info["width"], self.info["height"])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.jsrt_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise JsrtError(last_error())
+
+    def get_info(self):
+        i = Info()
+        self._ck(self._L.jsrt_scene_info(self._h, C.byref(i)))
+        return i.as_dict()
+
+    def upload(self):
+        self._ck(self._L.jsrt_scene_upload(self._h))
+
+    def set_stream(self, cuda_stream: int | None):
+        self._ck(self._L.jsrt_scene_set_stream(self._h, cuda_stream))
+
+    def render(self, first_pass, n_passes, seed=1, x_offset=0, x_delt=1, flags=0):
+        self._ck(self._L.jsrt_render(self._h, first_pass, n_passes, seed, x_offset, x_delt, flags))
+
+    def reset_accum(self):
+        self._ck(self._L.jsrt_reset_accum(self._h))
+
+    def synchronize(self):
+        self._ck(self._L.jsrt_synchronize(self._h))
+
+    def resolve_rgba8(self, out=None):
+        W, H = self.size
+        if out is None:
+            out = np.empty(W * H * 4, dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.size == W * H * 4 and out.flags["C_CONTIGUOUS"]
+        self._ck(self._L.jsrt_resolve_rgba8(self._h, out.ctypes.data))
+        return out.reshape(H, W, 4)
+
+    def read_accum(self):
+        W, H = self.size
+        out = np.empty((H, W, 4), dtype=np.float32)
+        passes = C.c_int()
+        self._ck(self._L.jsrt_read_accum(self._h, out.ctypes.data, C.byref(passes)))
+        return out, passes.value
+
+    def accum_device_ptr(self):
+        return self._L.jsrt_accum_device_ptr(self._h)
+
+    def add_passes(self, n):
+        self._ck(self._L.jsrt_add_passes(self._h, n))
+
+    def primary_hits(self):
+        W, H = self.size
+        ids = np.empty((H, W), dtype=np.int32)
+        t = np.empty((H, W), dtype=np.float32)
+        self._ck(self._L.jsrt_primary_hits(self._h, ids.ctypes.data, t.ctypes.data))
+        return ids, t
+
+    def stats(self):
+        s = Stats()
+        self._ck(self._L.jsrt_stats_get(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def stats_reset(self):
+        self._ck(self._L.jsrt_stats_reset(self._h))
+
+    def set_profiling(self, on):
+        self._ck(self._L.jsrt_set_profiling(self._h, int(bool(on))))

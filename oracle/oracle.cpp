@@ -990,13 +990,14 @@ int orc_primary_hits(void* h, int W, int H, int32_t* prim_id, double* tout, int 
     Scene* s = (Scene*)h;
     try {
         std::vector<Counters> cs(std::max(1, nthreads));
+        Camera pinhole = s->camera; pinhole.dof = false;   // the probe ignores the lens (PerspectiveCamera.getRayForPixel)
         parallelFor(nthreads, (long)W * H, [&](long b, long e, int tid) {
             Ctx ctx; ctx.c = &cs[tid];
             for (long i = b; i < e; ++i) {
                 const int px = (int)(i % W), py = (int)(i / W);
                 const double x = 2 * ((double)px / W) - 1, y = -2 * ((double)py / H) + 1;
                 ctx.rc = RC_PRIMARY;
-                Intersection in = s->world.cast(s->camera.getRayForPixel(x, y, ctx), 0, INF, true, ctx);
+                Intersection in = s->world.cast(pinhole.getRayForPixel(x, y, ctx), 0, INF, true, ctx);
                 prim_id[i] = in.object ? in.object->prim_id : -1;
                 tout[i] = in.distance;
             }
