@@ -31,6 +31,8 @@ extern "C" {
 
 /* jsrt_render flags */
 #define JSRT_FLAG_NO_JITTER 1   /* SimpleRenderer sampling: pixel corner, no jitter (src/renderers.js:21-25) */
+#define JSRT_FLAG_COUNT_WORK 2  /* instrumented kernels: count BVH nodes visited / primitives tested / SDF evaluations
+                                   per ray class (slower; defines the roofline's algorithmic bytes, never timed) */
 
 typedef struct jsrt_scene jsrt_scene;
 
@@ -116,12 +118,19 @@ typedef struct jsrt_stats {
     uint64_t shaded_hits;
     uint64_t launches;                                    /* kernel launches issued */
     uint64_t camera_samples;
-    double ms_generate, ms_extend, ms_shade, ms_shadow;   /* filled only when profiling is on */
+    double ms_generate, ms_extend, ms_shade, ms_shadow;   /* device time per kernel class; filled only when profiling is on */
+    uint64_t n_generate, n_extend, n_shade, n_shadow;     /* launches per kernel class */
+    /* JSRT_FLAG_COUNT_WORK renders only; index = ray class (0 primary, 1 secondary, 2 shadow) */
+    uint64_t bvh_nodes[3];      /* BVHAggregateNode.intersect calls = AABB slab tests, src/aggregates.js:207-209 */
+    uint64_t bvh_prims[3];      /* leaf object intersect calls, src/aggregates.js:211-212 */
+    uint64_t top_prims[3];      /* top-level / list primitive intersect calls, src/world.js:9-10 */
+    uint64_t sdf_evals[3];      /* root_sdf.distance() calls while marching, src/sdf.js:24 */
 } jsrt_stats;
 /* Counters accumulated since the last jsrt_stats_reset; synchronises the scene's stream. */
 int jsrt_stats_get(jsrt_scene*, jsrt_stats*);
 int jsrt_stats_reset(jsrt_scene*);
-/* Per-kernel CUDA-event timing (adds event records around every launch). */
+/* Per-kernel CUDA-event timing: records an event pair around every launch on the
+ * launching stream (no host sync until jsrt_stats_get). */
 int jsrt_set_profiling(jsrt_scene*, int on);
 
 const char* jsrt_last_error(void);

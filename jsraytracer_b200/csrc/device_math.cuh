@@ -137,80 +137,159 @@ JSRT_DEV float3 triangle_bary(const Tri* __restrict__ tris, int idx, float3 P) {
 // SDF bytecode interpreter: register stacks of points / scales / distances.
 // The program is straight-line (sdf_compile.cpp unrolls every loop), so all lanes
 // of a warp run the same instruction stream; only the REFL fold is predicated.
-JSRT_DEV float sdf_smooth_min(float a, float b, float k) {   // src/sdf.js:128-131
-    const float h = js_max(k - fabsf(a - b), 0.0f) / k;
-    return js_min(a, b) - h * h * h * k * (1.0f / 6.0f);
+//
+// Arithmetic is the reference's, operation for operation: points are f32 vectors,
+// every scalar (distance, scale, dot product, matrix entry) is f64, and each
+// Vec-returning step rounds to f32.  Sphere tracing stops on `distance <= epsilon`
+// (src/sdf.js:32) and the normal is a forward difference over a 1e-3 step
+// (src/sdf.js:42-46); both turn a one-ulp difference into a visibly different pixel on
+// fractal SDFs, so FP32 evaluation cannot meet the parity bar here.  B200's FP64 pipe
+// runs at half the FP32 rate, which this path pays knowingly.
+// Un-contracted f64 helpers: the compiler must not fuse a*b+c here (JS has no FMA).
+JSRT_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
+JSRT_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
+JSRT_DEV double dsub(double a, double b) { return __dsub_rn(a, b); }
+// Vec.dot for 3 / 4 components: products summed left to right (src/math.js:252-254)
+JSRT_DEV double ddot3(double ax, double ay, double az, double bx, double by, double bz) { return dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz)); }
+JSRT_DEV double ddot4(double ax, double ay, double az, double aw, double bx, double by, double bz, double bw) {
+    return dadd(dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz)), dmul(aw, bw));
 }
-JSRT_DEV float sdf_eval(const SdfInstr* __restrict__ code, const Xform* __restrict__ xforms, float3 p0) {
-    float3 P[8]; float S[8]; float D[8];
-    int sp = 0, dp = 0;
-    P[0] = p0; S[0] = 1.f;
+// Mat.times(Vec) with an f64 3x4 matrix: result[r] = b.dot(row r) stored f32 (src/math.js:392-397)
+JSRT_DEV float3 xf64_apply(const double* __restrict__ m, float3 p, double w) {
+    return f3((float)ddot4(p.x, p.y, p.z, w, __ldg(m + 0), __ldg(m + 1), __ldg(m + 2), __ldg(m + 3)),
+              (float)ddot4(p.x, p.y, p.z, w, __ldg(m + 4), __ldg(m + 5), __ldg(m + 6), __ldg(m + 7)),
+              (float)ddot4(p.x, p.y, p.z, w, __ldg(m + 8), __ldg(m + 9), __ldg(m + 10), __ldg(m + 11)));
+}
+JSRT_DEV double jsd_min(double a, double b) { return (a != a || b != b) ? CUDART_NAN : fmin(a, b); }
+JSRT_DEV double jsd_max(double a, double b) { return (a != a || b != b) ? CUDART_NAN : fmax(a, b); }
+JSRT_DEV double sdf_smooth_min(double a, double b, double k) {   // src/sdf.js:128-131
+    const double h = jsd_max(dsub(k, fabs(dsub(a, b))), 0.0) / k;
+    return dsub(jsd_min(a, b), dmul(dmul(dmul(dmul(h, h), h), k), (1.0 / 6.0)));
+}
+// Number(x.toPrecision(8)) (Math.fmod, src/math.js:27): round to 8 significant decimal digits
+JSRT_DEV double js_to_precision8(double x) {
+    if (x == 0.0 || !isfinite(x)) return x;
+    const double ax = fabs(x);
+    int e = (int)floor(log10(ax));
+    if (ax >= exp10((double)(e + 1))) ++e; else if (ax < exp10((double)e)) --e;
+    const int k = 7 - e;
+    // scale by a power of ten that is exact in f64 where possible
+    const double r = (k >= 0) ? rint(dmul(ax, exp10((double)k))) / exp10((double)k) : dmul(rint(ax / exp10((double)-k)), exp10((double)-k));
+    return copysign(r, x);
+}
+JSRT_DEV double js_fmod(double a, double b) { return js_to_precision8(dsub(a, dmul(floor(a / b), b))); }
+
+JSRT_DEV double sdf_eval(const SdfInstr* __restrict__ code, const Xform64* __restrict__ xforms64, float3 p0) {
+    float3 P[8]; double S[12]; double D[8];
+    int sp = 0, ss = 0, dp = 0;
+    P[0] = p0; S[0] = 1.0;
     for (int pc = 0;; ++pc) {
-        const float4* ip = reinterpret_cast<const float4*>(code + pc);
-        const float4 i0 = __ldg(ip);
-        const int op = __float_as_int(i0.x);
-        const float a0 = i0.y, a1 = i0.z, a2 = i0.w;
+        const int4 i0 = __ldg(reinterpret_cast<const int4*>(code + pc));
+        const float4 fv = __ldg(reinterpret_cast<const float4*>(code + pc) + 1);
+        const int op = i0.x;
+        const double a0 = __hiloint2double(i0.w, i0.z);
         switch (op) {
             case S_END: return D[0];
-            case S_SPHERE: { const float3 p = P[sp]; D[dp++] = sqrtf(dot3(p, p)) - a0; break; }          // src/sdf.js:232-234
+            case S_SPHERE: {                                                                              // src/sdf.js:232-234: p.to4(0).norm() - radius
+                const float3 p = P[sp];
+                D[dp++] = dsub(sqrt(ddot4(p.x, p.y, p.z, 0.0, p.x, p.y, p.z, 0.0)), a0); break;
+            }
             case S_BOX: {                                                                                 // src/sdf.js:276-279
                 const float3 p = P[sp];
-                const float qx = fabsf(p.x) - a0, qy = fabsf(p.y) - a1, qz = fabsf(p.z) - a2;
-                const float mx = fmaxf(qx, 0.f), my = fmaxf(qy, 0.f), mz = fmaxf(qz, 0.f);
-                D[dp++] = sqrtf(mx * mx + my * my + mz * mz) + fminf(fmaxf(fmaxf(qx, qy), qz), 0.f);
+                const float qx = (float)dsub(fabsf(p.x), fv.x), qy = (float)dsub(fabsf(p.y), fv.y), qz = (float)dsub(fabsf(p.z), fv.z);
+                const double mx = fmax((double)qx, 0.0), my = fmax((double)qy, 0.0), mz = fmax((double)qz, 0.0);   // Vec.max(q, 0): q.w = 0
+                D[dp++] = dadd(sqrt(ddot4(mx, my, mz, 0.0, mx, my, mz, 0.0)), fmin(fmax(fmax((double)qx, (double)qy), (double)qz), 0.0));
                 break;
             }
-            case S_TETRA: { const float3 p = P[sp]; D[dp++] = (fmaxf(fabsf(p.x + p.y) - p.z, fabsf(p.x - p.y) + p.z) - 1.f) / 1.7320508075688772f; break; }   // src/sdf.js:305-308
-            case S_MIN: { --dp; D[dp - 1] = js_min(D[dp - 1], D[dp]); break; }
-            case S_MAX: { --dp; D[dp - 1] = js_max(D[dp - 1], D[dp]); break; }
+            case S_TETRA: {                                                                               // src/sdf.js:305-308
+                const float3 p = P[sp];
+                const double a = dsub(fabs(dadd(p.x, p.y)), p.z), b = dadd(fabs(dsub(p.x, p.y)), p.z);
+                D[dp++] = dsub(fmax(a, b), 1.0) / sqrt(3.0);
+                break;
+            }
+            case S_MIN: { --dp; D[dp - 1] = jsd_min(D[dp - 1], D[dp]); break; }
+            case S_MAX: { --dp; D[dp - 1] = jsd_max(D[dp - 1], D[dp]); break; }
             case S_NEG: D[dp - 1] = -D[dp - 1]; break;
-            case S_ADDC: D[dp - 1] += a0; break;
+            case S_ADDC: D[dp - 1] = dadd(D[dp - 1], a0); break;
             case S_SMIN: { --dp; D[dp - 1] = sdf_smooth_min(D[dp - 1], D[dp], a0); break; }
             case S_SMIN_NEGA: { --dp; D[dp - 1] = -sdf_smooth_min(-D[dp - 1], D[dp], a0); break; }
             case S_SMIN_NEGAB: { --dp; D[dp - 1] = -sdf_smooth_min(-D[dp - 1], -D[dp], a0); break; }
-            case S_PUSHP: { P[sp + 1] = P[sp]; S[sp + 1] = 1.f; ++sp; break; }
-            case S_POPP: --sp; break;
-            case S_MULS: D[dp - 1] *= S[sp]; break;
-            case S_XFORM: { const XformReg m = load_xform(xforms, __float_as_int(a0)); P[sp] = xf_point(m, P[sp]); S[sp] *= a1; break; }   // src/sdf.js:433-435
+            case S_PUSHP: { P[sp + 1] = P[sp]; ++sp; S[++ss] = 1.0; break; }
+            case S_POPP: --sp; --ss; break;
+            case S_SBEGIN: S[++ss] = 1.0; break;
+            case S_SEND: { --ss; S[ss] = dmul(S[ss], S[ss + 1]); break; }
+            case S_MULS: D[dp - 1] = dmul(D[dp - 1], S[ss]); break;
+            case S_XFORM: {                                                                               // src/sdf.js:433-435
+                P[sp] = xf64_apply(xforms64[i0.y].m, P[sp], 1.0);
+                S[ss] = dmul(S[ss], a0);
+                break;
+            }
             case S_REFL: {                                                                                // src/sdf.js:450-455
-                const float a3 = __ldg(reinterpret_cast<const float*>(ip + 1));
                 const float3 p = P[sp];
-                const float dt = a0 * p.x + a1 * p.y + a2 * p.z - a3;
-                if (dt < 0.f) { const float k = 2.f * dt; P[sp] = f3(p.x - a0 * k, p.y - a1 * k, p.z - a2 * k); }
+                const double dt = dsub(ddot4(fv.x, fv.y, fv.z, 0.0, p.x, p.y, p.z, 1.0), a0);
+                if (dt < 0.0) {
+                    const double k = dmul(2.0, dt);
+                    const float nx = (float)dmul(fv.x, k), ny = (float)dmul(fv.y, k), nz = (float)dmul(fv.z, k);
+                    P[sp] = f3((float)dsub(p.x, nx), (float)dsub(p.y, ny), (float)dsub(p.z, nz));
+                }
                 break;
             }
-            case S_REP: {                                                                                 // src/sdf.js:471-473, Math.fmod src/math.js:27
+            case S_REP: {                                                                                 // src/sdf.js:471-473
                 const float3 p = P[sp];
-                const float ax = p.x + a0 * 0.5f, ay = p.y + a1 * 0.5f, az = p.z + a2 * 0.5f;
-                P[sp] = f3(ax - floorf(ax / a0) * a0 - a0 * 0.5f, ay - floorf(ay / a1) * a1 - a1 * 0.5f, az - floorf(az / a2) * a2 - a2 * 0.5f);
+                const double sx = fv.x, sy = fv.y, sz = fv.z;
+                P[sp] = f3((float)dsub(js_fmod(dadd(p.x, sx / 2), sx), sx / 2), (float)dsub(js_fmod(dadd(p.y, sy / 2), sy), sy / 2),
+                           (float)dsub(js_fmod(dadd(p.z, sz / 2), sz), sz / 2));
                 break;
             }
-            default: return CUDART_NAN_F;
+            default: return CUDART_NAN;
         }
     }
 }
 
-// SDFGeometry.intersect src/sdf.js:12-40.  t advances in f64 like the reference's
-// scalar, the marched point is f32 like its Vec.
-JSRT_DEV float sdf_intersect(const SdfProgram& pr, const SdfInstr* __restrict__ code, const Xform* __restrict__ xforms,
-                             float3 o, float3 d, float minD, float maxD, unsigned long long* evals) {
-    float bt0, bt1;
-    if (!aabb_intersects(f3(pr.cx, pr.cy, pr.cz), f3(pr.hx, pr.hy, pr.hz), o, d, minD, maxD, bt0, bt1)) return -CUDART_INF_F;
-    const double lo = fmax((double)minD, (double)bt0), hi = fmin((double)maxD, (double)bt1);
+// AABB.get_intersects in the reference's arithmetic (f32 vectors, f64 scalars); the SDF
+// march starts exactly at its t_min (src/sdf.js:13-20).
+JSRT_DEV bool aabb_intersects_f64(float3 c, float3 h, float3 o, float3 d, double minD, double maxD, double& t_min, double& t_max) {
+    t_min = -CUDART_INF; t_max = CUDART_INF;
+    const float3 p = f3((float)dsub(c.x, o.x), (float)dsub(c.y, o.y), (float)dsub(c.z, o.z));
+    const double eps = 0.0000001;
+#define JSRT_SLAB64(PI, HI, DI)                                                 \
+    if (fabs((double)DI) > eps) {                                               \
+        double t1 = dadd(PI, HI) / (double)DI, t2 = dsub(PI, HI) / (double)DI;  \
+        if (t1 > t2) { const double tmp = t1; t1 = t2; t2 = tmp; }              \
+        if (t1 > t_min) t_min = t1;                                             \
+        if (t2 < t_max) t_max = t2;                                             \
+        if (t_min > t_max || t_max < minD || t_min > maxD) return false;        \
+    } else if (fabs((double)PI) > (double)HI) return false;
+    JSRT_SLAB64(p.x, h.x, d.x)
+    JSRT_SLAB64(p.y, h.y, d.y)
+    JSRT_SLAB64(p.z, h.z, d.z)
+#undef JSRT_SLAB64
+    return true;
+}
+
+JSRT_DEV float3 ray_point_f64(float3 o, float3 d, double t) {   // origin.plus(direction.times(t)) with an f64 t
+    return f3((float)dadd(o.x, (float)dmul(d.x, t)), (float)dadd(o.y, (float)dmul(d.y, t)), (float)dadd(o.z, (float)dmul(d.z, t)));
+}
+
+// SDFGeometry.intersect src/sdf.js:12-40.  Returns the hit distance as f64 (NaN-free:
+// -inf for a miss).
+JSRT_DEV double sdf_intersect(const SdfProgram& pr, const SdfInstr* __restrict__ code, const Xform64* __restrict__ xforms64,
+                              float3 o, float3 d, double minD, double maxD, unsigned long long* evals) {
+    double bt0, bt1;
+    if (!aabb_intersects_f64(f3(pr.cx, pr.cy, pr.cz), f3(pr.hx, pr.hy, pr.hz), o, d, minD, maxD, bt0, bt1)) return -CUDART_INF;
+    const double lo = jsd_max(minD, bt0), hi = jsd_min(maxD, bt1);
     double t = lo;
-    const double rd_norm = sqrt((double)d.x * d.x + (double)d.y * d.y + (double)d.z * d.z);
+    const double rd_norm = sqrt(ddot4(d.x, d.y, d.z, 0.0, d.x, d.y, d.z, 0.0));
     const SdfInstr* prog = code + pr.first_instr;
     for (int i = 0; i < pr.max_samples; ++i) {
-        const float3 p = f3((float)((double)o.x + (double)(float)((double)d.x * t)), (float)((double)o.y + (double)(float)((double)d.y * t)),
-                            (float)((double)o.z + (double)(float)((double)d.z * t)));
-        const float dist = sdf_eval(prog, xforms, p);
+        const double dist = sdf_eval(prog, xforms64, ray_point_f64(o, d, t));
         if (evals) ++*evals;
         if (!isfinite(dist)) break;
-        if (dist <= pr.distance_epsilon) return (float)t;
-        t += (double)dist / rd_norm;
-        if (t < lo || t > hi || (t - lo) * rd_norm > (double)pr.max_trace_distance) break;
+        if (dist <= pr.distance_epsilon) return t;
+        t = dadd(t, dist / rd_norm);
+        if (t < lo || t > hi || dmul(dsub(t, lo), rd_norm) > pr.max_trace_distance) break;
     }
-    return -CUDART_INF_F;
+    return -CUDART_INF;
 }
 
 }  // namespace jsrt

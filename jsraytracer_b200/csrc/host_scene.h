@@ -18,6 +18,7 @@ struct HostScene {
     std::vector<Top> tops;
     std::vector<Prim> prims;
     std::vector<Xform> xforms;          // xforms[0] is the identity
+    std::vector<Xform64> xforms64;      // parallel to xforms
     std::vector<BvhNode> nodes;
     std::vector<Tri> tris;
     std::vector<TriShade> tri_shade;    // parallel to tris when any triangle has vertex data, else empty

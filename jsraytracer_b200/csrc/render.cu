@@ -35,8 +35,19 @@ struct RayQueue { float4* o; float4* d; float4* w; };
 struct ShadowQueue { float4* o; float4* d; float4* c; };
 
 // counters[0], [1]: ray queue counts (ping-pong); [2]: shadow queue count
-struct Counters { int ray[2]; int shadow; int pad; unsigned long long stats[8]; };
-enum { ST_PRIMARY = 0, ST_SECONDARY = 1, ST_SHADOW = 2, ST_SHADED = 3, ST_SAMPLES = 4 };
+struct Counters { int ray[2]; int shadow; int pad; unsigned long long stats[24]; };
+enum { ST_PRIMARY = 0, ST_SECONDARY = 1, ST_SHADOW = 2, ST_SHADED = 3, ST_SAMPLES = 4,
+       ST_NODES = 8, ST_LEAF_PRIMS = 11, ST_TOP_PRIMS = 14, ST_SDF_EVALS = 17 };   // + ray class (0 primary, 1 secondary, 2 shadow)
+
+__device__ __forceinline__ void flush_work(unsigned long long* stats, int cls, const Work& w) {
+    unsigned long long v[4] = {w.nodes, w.leaf_prims, w.top_prims, w.sdf_evals};
+    const int slot[4] = {ST_NODES, ST_LEAF_PRIMS, ST_TOP_PRIMS, ST_SDF_EVALS};
+    for (int k = 0; k < 4; ++k) {
+        unsigned long long x = v[k];
+        for (int off = 16; off; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(stats + slot[k] + cls, x);
+    }
+}
 
 struct GenParams {
     Camera cam;
@@ -53,33 +64,31 @@ struct GenParams {
 // primary ray is the reference's bit for bit.
 __device__ void camera_ray(const GenParams& g, int px, int py, uint32_t sample_key, bool jitter, bool use_lens, float3& o, float3& d) {
     const uint32_t nk = rng_node_key(sample_key, 1);
-    double x = 2.0 * ((double)px / (double)g.width) - 1.0;
-    double y = -2.0 * ((double)py / (double)g.height) + 1.0;
+    double x = dsub(dmul(2.0, (double)px / (double)g.width), 1.0);
+    double y = dadd(dmul(-2.0, (double)py / (double)g.height), 1.0);
     if (jitter) {
-        x = x + (2.0 / (double)g.width) * ((double)rng_u01(nk, DIM_JITTER_X) - 0.5);
-        y = y + (2.0 / (double)g.height) * ((double)rng_u01(nk, DIM_JITTER_Y) - 0.5);
+        x = dadd(x, dmul(2.0 / (double)g.width, dsub((double)rng_u01(nk, DIM_JITTER_X), 0.5)));
+        y = dadd(y, dmul(2.0 / (double)g.height, dsub((double)rng_u01(nk, DIM_JITTER_Y), 0.5)));
     }
     const Camera& c = g.cam;
-    const float dx = (float)(x * c.tan_fov * c.aspect), dy = (float)(y * c.tan_fov), dz = -1.f;   // Vec.of(...) stores f32
+    const float dx = (float)dmul(dmul(x, c.tan_fov), c.aspect), dy = (float)dmul(y, c.tan_fov), dz = -1.f;   // Vec.of(...) stores f32
     const double* t = c.t;
     // transform.times(direction): f64 dot of the f32 vector with each row, stored f32 (w = 0)
-    float3 dir = f3((float)((double)dx * t[0] + (double)dy * t[1] + (double)dz * t[2] + 0.0 * t[3]),
-                    (float)((double)dx * t[4] + (double)dy * t[5] + (double)dz * t[6] + 0.0 * t[7]),
-                    (float)((double)dx * t[8] + (double)dy * t[9] + (double)dz * t[10] + 0.0 * t[11]));
+    float3 dir = f3((float)ddot4(dx, dy, dz, 0.0, t[0], t[1], t[2], t[3]), (float)ddot4(dx, dy, dz, 0.0, t[4], t[5], t[6], t[7]),
+                    (float)ddot4(dx, dy, dz, 0.0, t[8], t[9], t[10], t[11]));
     float3 org = f3((float)t[3], (float)t[7], (float)t[11]);       // transform.column(3)
     if (c.dof && use_lens) {
-        // Vec.circlePick src/math.js:175-179, then DepthOfFieldPerspectiveCamera.getRayForPixel
-        const double a = (double)rng_u01(nk, DIM_LENS_A) * 2.0 * 3.141592653589793, r = sqrt((double)rng_u01(nk, DIM_LENS_R));
-        const float cx = (float)(r * cos(a)), cy = (float)(r * sin(a));
-        const float sx = (float)((double)cx * c.sensor_size), sy = (float)((double)cy * c.sensor_size);
-        const float3 off = f3((float)((double)sx * t[0] + (double)sy * t[1] + 0.0 * t[2] + 0.0 * t[3]),
-                              (float)((double)sx * t[4] + (double)sy * t[5] + 0.0 * t[6] + 0.0 * t[7]),
-                              (float)((double)sx * t[8] + (double)sy * t[9] + 0.0 * t[10] + 0.0 * t[11]));
-        org = f3((float)((double)org.x + (double)off.x), (float)((double)org.y + (double)off.y), (float)((double)org.z + (double)off.z));
-        const float fx = (float)((double)dir.x * c.focus_distance), fy = (float)((double)dir.y * c.focus_distance), fz = (float)((double)dir.z * c.focus_distance);
-        const float mx = (float)((double)fx - (double)off.x), my = (float)((double)fy - (double)off.y), mz = (float)((double)fz - (double)off.z);
-        const double nn = sqrt((double)mx * mx + (double)my * my + (double)mz * mz);
-        if (nn > 0.00001) { const double inv = 1.0 / nn; dir = f3((float)((double)mx * inv), (float)((double)my * inv), (float)((double)mz * inv)); }
+        // Vec.circlePick src/math.js:175-179, then DepthOfFieldPerspectiveCamera.getRayForPixel (src/cameras.js:46-52)
+        const double a = dmul(dmul((double)rng_u01(nk, DIM_LENS_A), 2.0), 3.141592653589793), r = sqrt((double)rng_u01(nk, DIM_LENS_R));
+        const float cx = (float)dmul(r, cos(a)), cy = (float)dmul(r, sin(a));
+        const float sx = (float)dmul(cx, c.sensor_size), sy = (float)dmul(cy, c.sensor_size);
+        const float3 off = f3((float)ddot4(sx, sy, 0.0, 0.0, t[0], t[1], t[2], t[3]), (float)ddot4(sx, sy, 0.0, 0.0, t[4], t[5], t[6], t[7]),
+                              (float)ddot4(sx, sy, 0.0, 0.0, t[8], t[9], t[10], t[11]));
+        org = f3((float)dadd(org.x, off.x), (float)dadd(org.y, off.y), (float)dadd(org.z, off.z));
+        const float fx = (float)dmul(dir.x, c.focus_distance), fy = (float)dmul(dir.y, c.focus_distance), fz = (float)dmul(dir.z, c.focus_distance);
+        const float mx = (float)dsub(fx, off.x), my = (float)dsub(fy, off.y), mz = (float)dsub(fz, off.z);
+        const double nn = sqrt(ddot4(mx, my, mz, 0.0, mx, my, mz, 0.0));
+        if (nn > 0.00001) { const double inv = 1.0 / nn; dir = f3((float)dmul(mx, inv), (float)dmul(my, inv), (float)dmul(mz, inv)); }
         else dir = f3(mx, my, mz);
     }
     o = org; d = dir;
@@ -106,16 +115,20 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(const __grid_constant_
 // ---------------------------------------------------------------------------------
 // extend: closest hit for every ray of the level (World.cast, src/world.js:28-30).
 // primary rays use minDistance 0, every other ray 0.0001 (src/materials.js:279,286,319,328).
+template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) extend_kernel(const __grid_constant__ DeviceScene sc, RayQueue q, const int* __restrict__ count,
-                                                         float4* __restrict__ hits) {
+                                                         float4* __restrict__ hits, unsigned long long* stats) {
     const int n = *count;
     const int stride = gridDim.x * blockDim.x;
+    Work wp, ws;      // primary / secondary rays of this thread (COUNT only)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float4 o4 = q.o[i], d4 = q.d[i];
-        const float minD = (__float_as_int(d4.w) == 1) ? 0.f : 0.0001f;
-        const Hit h = trace_ray<false>(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), minD, CUDART_INF_F);
-        hits[i] = make_float4(h.t, __int_as_float(h.prim), __int_as_float(h.top), 0.f);
+        const bool primary = __float_as_int(d4.w) == 1;
+        const float minD = primary ? 0.f : 0.0001f;
+        const Hit h = trace_ray<false, COUNT>(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), minD, CUDART_INF_F, primary ? &wp : &ws);
+        hits[i] = make_float4(h.t, __int_as_float(h.prim), __int_as_float(h.top), h.t_lo);
     }
+    if (COUNT) { flush_work(stats, 0, wp); flush_work(stats, 1, ws); }
 }
 
 // warp-aggregated append: returns this lane's slot (valid only where `want`)
@@ -178,7 +191,13 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(const __grid_constant__ D
                     const XformReg anc = load_xform(sc.xforms, ta.y);
                     inv = (flags & PF_IDENTITY_XFORM) ? anc : xf_compose(inv, anc);
                 }
-                const float3 lp = ray_point(xf_point(inv, o), xf_dir(inv, d), t);
+                float3 lp;
+                if (pa.x == G_SDF && ta.x == T_PRIM) {
+                    // the SDF normal is a forward difference: recompute the reference's local hit point exactly
+                    // (f64 matrix, f64 distance carried as t + t_lo)
+                    const double* m64 = sc.xforms64[pa.w].m;
+                    lp = ray_point_f64(xf64_apply(m64, o, 1.0), xf64_apply(m64, d, 0.0), (double)t + (double)h4.w);
+                } else lp = ray_point(xf_point(inv, o), xf_dir(inv, d), t);
                 float3 ln; material_data(sc, pa.x, pa.y, flags, lp, ln, s.uv, s.has_uv, s.basecolor);
                 s.normal = normalized3(xf_normal(inv, ln));
                 s.position = ray_point(o, d, t);
@@ -259,18 +278,21 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(const __grid_constant__ D
 // ---------------------------------------------------------------------------------
 // shadow: `world.cast(new Ray(position, direction), 0.0001, 1, false)`; the sample is
 // dropped iff 0 < t < 1 (src/materials.js:250-252).
+template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) shadow_kernel(const __grid_constant__ DeviceScene sc, ShadowQueue sq, const int* __restrict__ count, int cap,
-                                                         float4* __restrict__ accum) {
+                                                         float4* __restrict__ accum, unsigned long long* stats) {
     const int n = min(*count, cap);
     const int stride = gridDim.x * blockDim.x;
+    Work w;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float4 o4 = sq.o[i], d4 = sq.d[i];
-        const Hit h = trace_ray<true>(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), 0.0001f, 1.0f);
+        const Hit h = trace_ray<true, COUNT>(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), 0.0001f, 1.0f, &w);
         if (h.prim < 0) {
             const float4 c4 = sq.c[i];
             accum_add(accum, (uint32_t)__float_as_int(o4.w), f3(c4.x, c4.y, c4.z));
         }
     }
+    if (COUNT) flush_work(stats, 2, w);
 }
 
 // bookkeeping between levels: fold queue sizes into the ray statistics and recycle the counters
@@ -352,7 +374,7 @@ struct Renderer::Impl {
     void uploadScene() {
         for (void* p : scene_allocs) cudaFree(p);
         scene_allocs.clear(); scene_bytes = 0;
-        ds.tops = up(hs.tops); ds.prims = up(hs.prims); ds.xforms = up(hs.xforms); ds.nodes = up(hs.nodes);
+        ds.tops = up(hs.tops); ds.prims = up(hs.prims); ds.xforms = up(hs.xforms); ds.xforms64 = up(hs.xforms64); ds.nodes = up(hs.nodes);
         ds.tris = up(hs.tris); ds.tri_shade = up(hs.tri_shade); ds.boxes = up(hs.boxes); ds.materials = up(hs.materials);
         ds.lights = up(hs.lights); ds.sdfs = up(hs.sdfs); ds.sdf_code = up(hs.sdf_code);
         ds.n_top = (int)hs.tops.size(); ds.n_lights = (int)hs.lights.size(); ds.light_samples = hs.light_samples; ds.max_depth = hs.max_depth;
@@ -399,9 +421,9 @@ struct Renderer::Impl {
 
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
         auto grid_for = [&](const void* fn) { int per = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, kBlock, 0)); return prop.multiProcessorCount * std::max(1, per); };
-        grid_extend = grid_for((const void*)extend_kernel);
+        grid_extend = grid_for((const void*)extend_kernel<false>);
         grid_shade = grid_for((const void*)shade_kernel);
-        grid_shadow = grid_for((const void*)shadow_kernel);
+        grid_shadow = grid_for((const void*)shadow_kernel<false>);
         grid_gen = grid_for((const void*)generate_kernel);
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
         CK(cudaStreamSynchronize(stream));
@@ -412,17 +434,37 @@ struct Renderer::Impl {
         if (stream) cudaStreamSynchronize(stream);
         for (void* p : allocs) cudaFree(p);
         for (void* p : scene_allocs) cudaFree(p);
+        for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+        for (auto e : free_events) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 
+    // Per-kernel device time without perturbing the pipeline: event pairs are recorded
+    // around each launch on the launching stream and only read back (after a stream
+    // sync) when the statistics are fetched.
+    struct EvPair { cudaEvent_t a, b; int which; };
+    std::vector<EvPair> pending;
+    std::vector<cudaEvent_t> free_events;
+    unsigned long long kernel_launches[4] = {0, 0, 0, 0};
+    cudaEvent_t getEvent() {
+        if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
+        cudaEvent_t e; CK(cudaEventCreate(&e)); return e;
+    }
+    void flushEvents() {
+        if (pending.empty()) return;
+        CK(cudaStreamSynchronize(stream));
+        for (auto& p : pending) { float t = 0; CK(cudaEventElapsedTime(&t, p.a, p.b)); ms[p.which] += t; free_events.push_back(p.a); free_events.push_back(p.b); }
+        pending.clear();
+    }
     template <class F> void timed(int which, F&& launch) {
-        if (profiling) CK(cudaEventRecord(ev0, stream));
+        EvPair p{nullptr, nullptr, which};
+        if (profiling) { p.a = getEvent(); p.b = getEvent(); CK(cudaEventRecord(p.a, stream)); }
         launch();
-        ++launches;
+        ++launches; ++kernel_launches[which];
         CK(cudaGetLastError());
-        if (profiling) { CK(cudaEventRecord(ev1, stream)); CK(cudaEventSynchronize(ev1)); float t = 0; CK(cudaEventElapsedTime(&t, ev0, ev1)); ms[which] += t; }
+        if (profiling) { CK(cudaEventRecord(p.b, stream)); pending.push_back(p); if (pending.size() >= 8192) flushEvents(); }
     }
 
     GenParams genParams(int first_pass, uint64_t seed, int x_offset, int x_delt, int flags) const {
@@ -440,6 +482,7 @@ struct Renderer::Impl {
         if (hs.max_depth <= 0 || hs.max_depth > 255) throw std::runtime_error("jsrt: maxRecursionDepth must be in 1..255");
         if (x_offset < 0) throw std::runtime_error("jsrt: x_offset must be >= 0");
         GenParams g = genParams(first_pass, seed, x_offset, x_delt, flags);
+        const bool count_work = (flags & 2) != 0;
         const long long total = (long long)g.npix_active * n_passes;
         for (long long done = 0; done < total; done += batch) {
             g.first_sample = done;
@@ -448,11 +491,17 @@ struct Renderer::Impl {
             timed(0, [&] { generate_kernel<<<grid_gen, kBlock, 0, stream>>>(g, rq[0], accum); });
             int cur = 0;
             for (int level = 0; level < hs.max_depth; ++level) {
-                timed(1, [&] { extend_kernel<<<grid_extend, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits); });
+                timed(1, [&] {
+                    if (count_work) extend_kernel<true><<<grid_extend, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, counters->stats);
+                    else extend_kernel<false><<<grid_extend, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, counters->stats);
+                });
                 timed(2, [&] { shade_kernel<<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap,
                                                                             sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow); });
                 if (hs.light_samples > 0)
-                    timed(3, [&] { shadow_kernel<<<grid_shadow, kBlock, 0, stream>>>(ds, sq, &counters->shadow, shadow_cap, accum); });
+                    timed(3, [&] {
+                        if (count_work) shadow_kernel<true><<<grid_shadow, kBlock, 0, stream>>>(ds, sq, &counters->shadow, shadow_cap, accum, counters->stats);
+                        else shadow_kernel<false><<<grid_shadow, kBlock, 0, stream>>>(ds, sq, &counters->shadow, shadow_cap, accum, counters->stats);
+                    });
                 level_end_kernel<<<1, 1, 0, stream>>>(counters, cur, level, ray_cap, shadow_cap); ++launches;
                 cur ^= 1;
             }
@@ -504,15 +553,18 @@ void Renderer::primaryHits(int32_t* prim_id, float* t) {
 }
 void Renderer::getStats(RenderStats& s) {
     synchronize();
+    impl_->flushEvents();
     Counters c; CK(cudaMemcpy(&c, impl_->counters, sizeof(Counters), cudaMemcpyDeviceToHost));
     s.rays_primary = c.stats[ST_PRIMARY]; s.rays_secondary = c.stats[ST_SECONDARY]; s.rays_shadow = c.stats[ST_SHADOW];
     s.shaded_hits = c.stats[ST_SHADED]; s.camera_samples = c.stats[ST_SAMPLES]; s.launches = impl_->launches;
-    for (int i = 0; i < 4; ++i) s.ms[i] = impl_->ms[i];
+    for (int k = 0; k < 3; ++k) { s.nodes[k] = c.stats[ST_NODES + k]; s.leaf_prims[k] = c.stats[ST_LEAF_PRIMS + k]; s.top_prims[k] = c.stats[ST_TOP_PRIMS + k]; s.sdf_evals[k] = c.stats[ST_SDF_EVALS + k]; }
+    for (int i = 0; i < 4; ++i) { s.ms[i] = impl_->ms[i]; s.kernel_launches[i] = impl_->kernel_launches[i]; }
 }
 void Renderer::resetStats() {
     synchronize();
     CK(cudaMemsetAsync(impl_->counters, 0, sizeof(Counters), impl_->stream));
-    impl_->launches = 0; for (double& m : impl_->ms) m = 0;
+    impl_->flushEvents();
+    impl_->launches = 0; for (double& m : impl_->ms) m = 0; for (auto& k : impl_->kernel_launches) k = 0;
 }
 void Renderer::setProfiling(bool on) { impl_->profiling = on; }
 int Renderer::passes() const { return impl_->passes; }

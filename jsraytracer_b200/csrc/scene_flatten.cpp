@@ -44,8 +44,8 @@ struct Flattener {
         for (int i = 0; i < 12; ++i) if (m[i] != ((i % 5 == 0) ? 1.0 : 0.0)) ident = false;
         if (is_identity) *is_identity = ident;
         if (ident) return 0;
-        Xform x; for (int i = 0; i < 12; ++i) x.m[i] = (float)m[i];
-        out.xforms.push_back(x);
+        Xform x; Xform64 y; for (int i = 0; i < 12; ++i) { x.m[i] = (float)m[i]; y.m[i] = m[i]; }
+        out.xforms.push_back(x); out.xforms64.push_back(y);
         return (int)out.xforms.size() - 1;
     }
 
@@ -288,6 +288,7 @@ struct Flattener {
         for (int i = 0; i < 3; ++i) out.bg[i] = (float)bg[i];
 
         Xform id{}; id.m[0] = id.m[5] = id.m[10] = 1; out.xforms.push_back(id);
+        Xform64 id64{}; id64.m[0] = id64.m[5] = id64.m[10] = 1; out.xforms64.push_back(id64);
 
         const Val* objects = doc.field(world, "objects");
         assignIds(objects);

@@ -19,6 +19,10 @@ enum PrimFlags : int { PF_CASTS_SHADOW = 1, PF_IDENTITY_XFORM = 2, PF_HAS_VNORMA
 // 3x4 affine map, row-major: the upper three rows of a reference `inv_transform`
 // (the fourth row of every transform the scene API can build is 0 0 0 1).
 struct Xform { float m[12]; };
+// The same map in f64 (the reference keeps matrices as f64, src/math.js:303).  Only the
+// SDF path reads these: sphere tracing stops on a hard `distance <= epsilon` test
+// (src/sdf.js:32), so its inputs must be rounded exactly like the reference's.
+struct Xform64 { double m[12]; };
 
 // One placed Primitive (src/world.js:104-141).  32 bytes = two 128-bit loads.
 struct Prim {
@@ -93,11 +97,14 @@ struct Light {                    // src/lights.js
     Xform inv;                    // L_AREA inv_transform
 };
 
-// SDF programs: see sdf_compile.cpp / kernels.cu for the bytecode.
+// SDF programs: see sdf_compile.cpp / device_math.cuh for the bytecode.  The
+// interpreter mirrors the reference's arithmetic exactly — points are f32 (`Vec`),
+// distances / scales / matrix entries are f64 — because sphere tracing's stop test is
+// a hard threshold and forward-difference normals amplify one-ulp differences.
 enum SdfOp : int {
     S_END = 0,
     S_SPHERE,      // a0 = radius                        push |p| - r
-    S_BOX,         // a0..a2 = size                      push box distance
+    S_BOX,         // f32 size in (a1,a2) as 4 packed floats   push box distance
     S_TETRA,       //                                     push tetrahedron distance
     S_MIN, S_MAX,  //                                     pop 2, push
     S_NEG,         //                                     negate top
@@ -108,16 +115,19 @@ enum SdfOp : int {
     S_PUSHP,       //                                     duplicate the point, push scale 1
     S_POPP,        //                                     drop the point and scale
     S_MULS,        //                                     top distance *= current scale
-    S_XFORM,       // a0 = xform index (bits), a1 = scale  p = M p; scale *= a1
-    S_REFL,        // a0..a2 = normal, a3 = delta
-    S_REP,         // a0..a2 = sizes
+    S_XFORM,       // idx = Xform64 index, a0 = scale     p = M p; scale *= a0
+    S_REFL,        // f32 normal in (a1,a2), a0 = delta
+    S_REP,         // f32 sizes in (a1,a2)
+    S_SBEGIN,      //                                     push a local scale accumulator (= 1)
+    S_SEND,        //                                     pop it; enclosing scale *= popped   (Sequence / Recursive transformers
+                   //                                     return their own product, src/sdf.js:387-394,408-415)
 };
-struct SdfInstr { int op; float a0, a1, a2, a3; int pad[3]; };   // 32 bytes
+struct SdfInstr { int op; int idx; double a0; float f[4]; };   // 32 bytes: two 128-bit loads
 struct SdfProgram {
     int first_instr, instr_count;
     int max_samples;
     int uniform_base;             // 1: every leaf has the same basecolor (in `base`)
-    float distance_epsilon, max_trace_distance, normal_step_size, pad0;
+    double distance_epsilon, max_trace_distance, normal_step_size;
     float cx, cy, cz, hx, hy, hz; // SDFGeometry.aabb
     float base[3];
     float pad1[3];

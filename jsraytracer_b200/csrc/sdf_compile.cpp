@@ -25,20 +25,22 @@ namespace {
 struct SdfCompiler {
     const WireDoc& doc;
     HostScene& out;
-    int depth_points = 1, max_points = 1, depth_dist = 0, max_dist = 0;
+    int depth_points = 1, max_points = 1, depth_dist = 0, max_dist = 0, depth_scale = 1, max_scale = 1;
     bool base_set = false, base_uniform = true;
     float base[3] = {1, 1, 1};
 
     SdfCompiler(const WireDoc& d, HostScene& o) : doc(d), out(o) {}
 
-    void emit(int op, float a0 = 0, float a1 = 0, float a2 = 0, float a3 = 0) {
-        SdfInstr i{}; i.op = op; i.a0 = a0; i.a1 = a1; i.a2 = a2; i.a3 = a3;
+    void emit(int op, double a0 = 0, float f0 = 0, float f1 = 0, float f2 = 0, int idx = 0) {
+        SdfInstr i{}; i.op = op; i.idx = idx; i.a0 = a0; i.f[0] = f0; i.f[1] = f1; i.f[2] = f2; i.f[3] = 0;
         out.sdf_code.push_back(i);
         switch (op) {
             case S_SPHERE: case S_BOX: case S_TETRA: if (++depth_dist > max_dist) max_dist = depth_dist; break;
             case S_MIN: case S_MAX: case S_SMIN: case S_SMIN_NEGA: case S_SMIN_NEGAB: --depth_dist; break;
-            case S_PUSHP: if (++depth_points > max_points) max_points = depth_points; break;
-            case S_POPP: --depth_points; break;
+            case S_PUSHP: if (++depth_points > max_points) max_points = depth_points; if (++depth_scale > max_scale) max_scale = depth_scale; break;
+            case S_POPP: --depth_points; --depth_scale; break;
+            case S_SBEGIN: if (++depth_scale > max_scale) max_scale = depth_scale; break;
+            case S_SEND: --depth_scale; break;
             default: break;
         }
         if (out.sdf_code.size() > 65536) fail("jsrt: SDF program longer than 65536 instructions after unrolling");
@@ -55,31 +57,33 @@ struct SdfCompiler {
         const std::string& ty = doc.typeName(t);
         if (ty == "SDFTransformerSequence") {
             const Val* ts = doc.field(t, "transformers");
+            emit(S_SBEGIN);
             for (uint32_t i = 0; i < doc.length(ts); ++i) transformer(doc.at(ts, i));
+            emit(S_SEND);
         } else if (ty == "SDFRecursiveTransformer") {
             const int n = (int)doc.number(doc.field(t, "iterations"), 0);
+            emit(S_SBEGIN);
             for (int i = 0; i < n; ++i) transformer(doc.field(t, "transformer"));
+            emit(S_SEND);
         } else if (ty == "SDFMatrixTransformer") {
             double m[16]; doc.mat4(doc.field(t, "_inv_transform"), m);
-            Xform x; for (int i = 0; i < 12; ++i) x.m[i] = (float)m[i];
-            out.xforms.push_back(x);
-            const int idx = (int)out.xforms.size() - 1;
-            float fi; memcpy(&fi, &idx, 4);
-            emit(S_XFORM, fi, (float)doc.number(doc.field(t, "_scale"), 1));
+            Xform x; Xform64 y; for (int i = 0; i < 12; ++i) { x.m[i] = (float)m[i]; y.m[i] = m[i]; }
+            out.xforms.push_back(x); out.xforms64.push_back(y);
+            emit(S_XFORM, doc.number(doc.field(t, "_scale"), 1), 0, 0, 0, (int)out.xforms.size() - 1);
         } else if (ty == "SDFReflectionTransformer") {
             double n[4]; doc.vec(doc.field(t, "normal"), n);
-            emit(S_REFL, (float)n[0], (float)n[1], (float)n[2], (float)doc.number(doc.field(t, "delta"), 0));
+            emit(S_REFL, doc.number(doc.field(t, "delta"), 0), (float)n[0], (float)n[1], (float)n[2]);
         } else if (ty == "SDFInfiniteRepetitionTransformer") {
             double s[4]; doc.vec(doc.field(t, "sizes"), s, kInf);
-            emit(S_REP, (float)s[0], (float)s[1], (float)s[2]);
+            emit(S_REP, 0, (float)s[0], (float)s[1], (float)s[2]);
         } else fail("jsrt: unsupported SDF transformer '" + ty + "'");
     }
 
     void node(const Val* n) {
         n = doc.resolve(n);
         const std::string& ty = doc.typeName(n);
-        if (ty == "SphereSDF") { noteBase(n); emit(S_SPHERE, (float)doc.number(doc.field(n, "radius"), kInf)); }
-        else if (ty == "BoxSDF") { noteBase(n); double s[4]; doc.vec(doc.field(n, "size"), s, kInf); emit(S_BOX, (float)s[0], (float)s[1], (float)s[2]); }
+        if (ty == "SphereSDF") { noteBase(n); emit(S_SPHERE, doc.number(doc.field(n, "radius"), kInf)); }
+        else if (ty == "BoxSDF") { noteBase(n); double s[4]; doc.vec(doc.field(n, "size"), s, kInf); emit(S_BOX, 0, (float)s[0], (float)s[1], (float)s[2]); }
         else if (ty == "TetrahedronSDF") { noteBase(n); emit(S_TETRA); }
         else if (ty == "UnionSDF" || ty == "IntersectionSDF") {
             const Val* cs = doc.field(n, "children");
@@ -88,10 +92,10 @@ struct SdfCompiler {
             for (uint32_t i = 0; i < cnt; ++i) { node(doc.at(cs, i)); if (i) emit(ty == "UnionSDF" ? S_MIN : S_MAX); }
         }
         else if (ty == "DifferenceSDF") { node(doc.field(n, "positive")); node(doc.field(n, "negative")); emit(S_NEG); emit(S_MAX); }
-        else if (ty == "SmoothUnionSDF") { node(doc.field(n, "childA")); node(doc.field(n, "childB")); emit(S_SMIN, (float)doc.number(doc.field(n, "k"), 1)); }
-        else if (ty == "SmoothIntersectionSDF") { node(doc.field(n, "childA")); node(doc.field(n, "childB")); emit(S_SMIN_NEGAB, (float)doc.number(doc.field(n, "k"), 1)); }
-        else if (ty == "SmoothDifferenceSDF") { node(doc.field(n, "positive")); node(doc.field(n, "negative")); emit(S_SMIN_NEGA, (float)doc.number(doc.field(n, "k"), 1)); }
-        else if (ty == "RoundSDF") { node(doc.field(n, "child_sdf")); emit(S_ADDC, -(float)doc.number(doc.field(n, "rounding"), 0)); }
+        else if (ty == "SmoothUnionSDF") { node(doc.field(n, "childA")); node(doc.field(n, "childB")); emit(S_SMIN, doc.number(doc.field(n, "k"), 1)); }
+        else if (ty == "SmoothIntersectionSDF") { node(doc.field(n, "childA")); node(doc.field(n, "childB")); emit(S_SMIN_NEGAB, doc.number(doc.field(n, "k"), 1)); }
+        else if (ty == "SmoothDifferenceSDF") { node(doc.field(n, "positive")); node(doc.field(n, "negative")); emit(S_SMIN_NEGA, doc.number(doc.field(n, "k"), 1)); }
+        else if (ty == "RoundSDF") { node(doc.field(n, "child_sdf")); emit(S_ADDC, -doc.number(doc.field(n, "rounding"), 0)); }
         else if (ty == "TransformSDF") {
             emit(S_PUSHP); transformer(doc.field(n, "transformer")); node(doc.field(n, "child_sdf")); emit(S_MULS); emit(S_POPP);
         }
@@ -115,12 +119,12 @@ int compileSdf(const WireDoc& doc, const Val* g, HostScene& out) {
     c.node(doc.field(g, "root_sdf"));
     c.emit(S_END);
     p.instr_count = (int)out.sdf_code.size() - p.first_instr;
-    if (c.max_points > 8 || c.max_dist > 8) fail("jsrt: SDF tree needs more than 8 interpreter stack slots");
+    if (c.max_points > 8 || c.max_dist > 8 || c.max_scale > 12) fail("jsrt: SDF tree needs more interpreter stack slots than the 8 / 8 / 12 available");
     const double ms = doc.number(doc.field(g, "max_samples"), 1000);
     p.max_samples = ms > 2147483647.0 ? 2147483647 : (int)ms;
-    p.distance_epsilon = (float)doc.number(doc.field(g, "distance_epsilon"), 0.0001);
-    p.max_trace_distance = (float)doc.number(doc.field(g, "max_trace_distance"), 1000);
-    p.normal_step_size = (float)doc.number(doc.field(g, "normal_step_size"), 0.001);
+    p.distance_epsilon = doc.number(doc.field(g, "distance_epsilon"), 0.0001);
+    p.max_trace_distance = doc.number(doc.field(g, "max_trace_distance"), 1000);
+    p.normal_step_size = doc.number(doc.field(g, "normal_step_size"), 0.001);
     const Val* box = doc.field(g, "aabb");
     double ce[4], h[4];
     doc.vec(doc.field(box, "center"), ce); doc.vec(doc.field(box, "half_size"), h, kInf);

@@ -86,15 +86,18 @@ JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index
             }
             break;
         }
-        case G_SDF: {                                     // src/sdf.js:41-47: forward differences
+        case G_SDF: {                                     // src/sdf.js:41-47: forward differences, reference arithmetic
             const SdfProgram& pr = sc.sdfs[geom_index];
             const SdfInstr* prog = sc.sdf_code + pr.first_instr;
-            const float s = pr.normal_step_size;
-            const float d0 = sdf_eval(prog, sc.xforms, lp);
-            const float dx = sdf_eval(prog, sc.xforms, f3(lp.x + s, lp.y, lp.z));
-            const float dy = sdf_eval(prog, sc.xforms, f3(lp.x, lp.y + s, lp.z));
-            const float dz = sdf_eval(prog, sc.xforms, f3(lp.x, lp.y, lp.z + s));
-            n = normalized3(f3((dx - d0) / s, (dy - d0) / s, (dz - d0) / s));
+            const double step = pr.normal_step_size;
+            const float fs = (float)step;                 // Vec.axis(i, 4, step) stores the step as f32
+            const double d0 = sdf_eval(prog, sc.xforms64, lp);
+            const double dx = sdf_eval(prog, sc.xforms64, f3((float)dadd(lp.x, fs), lp.y, lp.z));
+            const double dy = sdf_eval(prog, sc.xforms64, f3(lp.x, (float)dadd(lp.y, fs), lp.z));
+            const double dz = sdf_eval(prog, sc.xforms64, f3(lp.x, lp.y, (float)dadd(lp.z, fs)));
+            const float nx = (float)(dsub(dx, d0) / step), ny = (float)(dsub(dy, d0) / step), nz = (float)(dsub(dz, d0) / step);
+            const double nn = sqrt(ddot4(nx, ny, nz, 0.0, nx, ny, nz, 0.0));
+            n = (nn > 0.00001) ? f3((float)dmul(nx, 1.0 / nn), (float)dmul(ny, 1.0 / nn), (float)dmul(nz, 1.0 / nn)) : f3(nx, ny, nz);
             base = f3(pr.base[0], pr.base[1], pr.base[2]);
             break;
         }

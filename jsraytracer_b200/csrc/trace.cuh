@@ -11,6 +11,7 @@ struct DeviceScene {
     const Top* tops;
     const Prim* prims;
     const Xform* xforms;
+    const Xform64* xforms64;
     const BvhNode* nodes;
     const Tri* tris;
     const TriShade* tri_shade;
@@ -24,12 +25,16 @@ struct DeviceScene {
     int pad;
 };
 
-struct Hit { float t; int prim; int top; };
+struct Hit { float t; int prim; int top; float t_lo; };   // t_lo: low-order part of an f64 hit distance (SDF hits)
+
+// Work counters of one ray (only maintained by the COUNT instantiations, which back
+// the roofline's algorithmic bytes: SURVEY.md §8d).
+struct Work { unsigned nodes = 0, leaf_prims = 0, top_prims = 0; unsigned long long sdf_evals = 0; };
 
 // geometry.intersect(localRay, minDistance, maxDistance) for one placed primitive.
 // `best` is the caller's current closest distance (only used to skip work that the
 // caller's acceptance test would reject anyway).
-JSRT_DEV float prim_intersect(const DeviceScene& sc, const int4 pa, float3 o, float3 d, float minD, float maxD, float best) {
+JSRT_DEV float prim_intersect(const DeviceScene& sc, const int4 pa, float3 o, float3 d, float minD, float maxD, float best, unsigned long long* sdf_evals = nullptr) {
     switch (pa.x) {   // geom_kind
         case G_TRIANGLE: return triangle_intersect(sc.tris, pa.y, o, d, minD, fminf(maxD, best));
         case G_PLANE: return plane_t(o, d);
@@ -58,46 +63,62 @@ JSRT_DEV float prim_intersect(const DeviceScene& sc, const int4 pa, float3 o, fl
             const float t = sphere_intersect(f3(o.x, o.y, 0.f), f3(d.x, d.y, 0.f), md);
             return (fabsf(o.z + t * d.z) <= 1.f) ? t : -CUDART_INF_F;
         }
-        case G_SDF: return sdf_intersect(sc.sdfs[pa.y], sc.sdf_code, sc.xforms, o, d, minD, maxD, nullptr);
         default: return -CUDART_INF_F;
     }
 }
 
 // One placed primitive against a ray given in its parent's space.
-JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, float3 o, float3 d, float minD, float maxD, float best, bool shadow_ray) {
+// `t_lo` receives the low-order part of the distance for SDF hits (their f64 distance
+// is carried as t + t_lo so that shading recomputes the reference's hit point exactly).
+JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, float3 o, float3 d, float minD, float maxD, float best, bool shadow_ray,
+                                     unsigned long long* sdf_evals = nullptr, float* t_lo = nullptr) {
     const int4* pp = reinterpret_cast<const int4*>(sc.prims + prim_index);
     const int4 pa = __ldg(pp);          // geom_kind, geom_index, material, xform
     const int flags = __ldg(reinterpret_cast<const int*>(pp + 1));
     if (shadow_ray && !(flags & PF_CASTS_SHADOW)) return CUDART_INF_F;     // src/world.js:117-118
+    if (pa.x == G_SDF) {
+        // ray.getTransformed(inv_transform) with the f64 matrix (src/math.js:392-397), then SDFGeometry.intersect
+        const double* m = sc.xforms64[pa.w].m;
+        const float3 lo = xf64_apply(m, o, 1.0), ld = xf64_apply(m, d, 0.0);
+        const double t = sdf_intersect(sc.sdfs[pa.y], sc.sdf_code, sc.xforms64, lo, ld, (double)minD, (double)maxD, sdf_evals);
+        const float tf = (float)t;
+        if (t_lo) *t_lo = isfinite(t) ? (float)(t - (double)tf) : 0.f;
+        return tf;
+    }
     if (!(flags & PF_IDENTITY_XFORM)) {                                    // ray.getTransformed(inv_transform), src/world.js:120
         const XformReg m = load_xform(sc.xforms, pa.w);
         const float3 lo = xf_point(m, o), ld = xf_dir(m, d);
-        return prim_intersect(sc, pa, lo, ld, minD, maxD, best);
+        return prim_intersect(sc, pa, lo, ld, minD, maxD, best, sdf_evals);
     }
-    return prim_intersect(sc, pa, o, d, minD, maxD, best);
+    return prim_intersect(sc, pa, o, d, minD, maxD, best, sdf_evals);
 }
 
 // World.cast: closest hit over the top-level list in order, strict `<` so the
 // earliest object wins exact ties (src/world.js:9-13).  ANY_HIT: shadow-ray
 // semantics of materials.js:250-252 — only "is there a hit with minD < t < maxD"
 // matters, so the walk stops at the first accepted hit (result-identical).
-template <bool ANY_HIT>
-JSRT_DEV Hit trace_ray(const DeviceScene& sc, float3 o, float3 d, float minD, float maxD) {
-    Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1;
+template <bool ANY_HIT, bool COUNT = false>
+JSRT_DEV Hit trace_ray(const DeviceScene& sc, float3 o, float3 d, float minD, float maxD, Work* work = nullptr) {
+    unsigned long long* const se = COUNT ? &work->sdf_evals : nullptr;
+    Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
     for (int ti = 0; ti < sc.n_top; ++ti) {
         const int4* tp = reinterpret_cast<const int4*>(sc.tops + ti);
         const int4 ta = __ldg(tp);          // kind, xform, first_prim, prim_count
         if (ta.x == T_PRIM) {
-            const float t = placed_prim_intersect(sc, ta.z, o, d, minD, maxD, best.t, ANY_HIT);
-            if (t > minD && t < best.t && t < maxD) { best.t = t; best.prim = ta.z; best.top = ti; if (ANY_HIT) return best; }
+            if (COUNT) ++work->top_prims;
+            float tl = 0.f;
+            const float t = placed_prim_intersect(sc, ta.z, o, d, minD, maxD, best.t, ANY_HIT, se, &tl);
+            if (t > minD && t < best.t && t < maxD) { best.t = t; best.prim = ta.z; best.top = ti; best.t_lo = tl; if (ANY_HIT) return best; }
             continue;
         }
         const XformReg m = load_xform(sc.xforms, ta.y);
         const float3 lo = xf_point(m, o), ld = xf_dir(m, d);     // ray.getTransformed(this.getInvTransform())
         if (ta.x == T_LIST) {
             for (int k = 0; k < ta.w; ++k) {
-                const float t = placed_prim_intersect(sc, ta.z + k, lo, ld, minD, maxD, best.t, ANY_HIT);
-                if (t > minD && t < best.t && t < maxD) { best.t = t; best.prim = ta.z + k; best.top = ti; if (ANY_HIT) return best; }
+                if (COUNT) ++work->top_prims;
+                float tl = 0.f;
+                const float t = placed_prim_intersect(sc, ta.z + k, lo, ld, minD, maxD, best.t, ANY_HIT, se, &tl);
+                if (t > minD && t < best.t && t < maxD) { best.t = t; best.prim = ta.z + k; best.top = ti; best.t_lo = tl; if (ANY_HIT) return best; }
             }
             continue;
         }
@@ -108,26 +129,29 @@ JSRT_DEV Hit trace_ray(const DeviceScene& sc, float3 o, float3 d, float minD, fl
         // answer because a later-equal hit never replaces an earlier one.
         const int4 tb = __ldg(tp + 1);      // first_node, node_count, pad, pad
         const float4* nodes = reinterpret_cast<const float4*>(sc.nodes + tb.x);
-        float local_best = CUDART_INF_F; int local_prim = -1;
+        float local_best = CUDART_INF_F, local_lo = 0.f; int local_prim = -1;
         int i = 0;
         while (i < tb.y) {
             const float4 n0 = __ldg(nodes + 2 * i), n1 = __ldg(nodes + 2 * i + 1);
             const int skip = __float_as_int(n1.z), leaf = __float_as_int(n1.w);
             float b0, b1;
+            if (COUNT) ++work->nodes;
             // src/aggregates.js:208-209
             if (aabb_intersects(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), lo, ld, minD, maxD, b0, b1) && b0 <= maxD && b1 >= minD && b0 <= local_best) {
                 if (leaf != -1) {
                     const int cnt = (int)((unsigned)leaf >> 24), first = ta.z + (leaf & 0xffffff);
                     for (int k = 0; k < cnt; ++k) {
-                        const float t = placed_prim_intersect(sc, first + k, lo, ld, minD, maxD, fminf(local_best, best.t), ANY_HIT);
-                        if (t > minD && t < maxD && t < local_best) { local_best = t; local_prim = first + k; }   // :213
+                        if (COUNT) ++work->leaf_prims;
+                        float tl = 0.f;
+                        const float t = placed_prim_intersect(sc, first + k, lo, ld, minD, maxD, fminf(local_best, best.t), ANY_HIT, se, &tl);
+                        if (t > minD && t < maxD && t < local_best) { local_best = t; local_prim = first + k; local_lo = tl; }   // :213
                     }
                     if (ANY_HIT && local_prim >= 0) break;
                     i = skip;
                 } else ++i;
             } else i = skip;
         }
-        if (local_best > minD && local_best < best.t && local_best < maxD) { best.t = local_best; best.prim = local_prim; best.top = ti; if (ANY_HIT) return best; }
+        if (local_best > minD && local_best < best.t && local_best < maxD) { best.t = local_best; best.prim = local_prim; best.top = ti; best.t_lo = local_lo; if (ANY_HIT) return best; }
     }
     return best;
 }

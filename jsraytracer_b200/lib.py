@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libjsrt.so")
 FORMAT_JSON = 0
 FORMAT_MSGPACK = 1
 FLAG_NO_JITTER = 1
+FLAG_COUNT_WORK = 2
 
 _LIB = None
 
@@ -40,10 +41,13 @@ class Info(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays_primary", "rays_secondary", "rays_shadow", "shaded_hits", "launches",
                                           "camera_samples")] + \
-               [(n, C.c_double) for n in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow")]
+               [(n, C.c_double) for n in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow")] + \
+               [(n, C.c_uint64) for n in ("n_generate", "n_extend", "n_shade", "n_shadow")] + \
+               [(n, C.c_uint64 * 3) for n in ("bvh_nodes", "bvh_prims", "top_prims", "sdf_evals")]
 
     def as_dict(self):
-        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: (list(getattr(self, n)) if hasattr(getattr(self, n), "__len__") else getattr(self, n))
+             for n, _ in self._fields_}
         d["rays"] = d["rays_primary"] + d["rays_secondary"] + d["rays_shadow"]
         return d
 

@@ -1,0 +1,73 @@
+"""Wire format of the drop-in boundary (src/serializer.js:12-60)."""
+import json
+import math
+
+import numpy as np
+import pytest
+
+from jsraytracer_b200 import lib, scenes
+from jsraytracer_b200.jsmath import Vec, Mat4
+from jsraytracer_b200.geometry import Triangle
+from jsraytracer_b200.serializer import Serializer
+from jsraytracer_b200.world import Primitive
+from jsraytracer_b200.materials import PhongMaterial, SolidMaterialColor
+
+
+def test_type_table_and_refs():
+    v = Vec.of(1, 2, 3)
+    plain = Serializer({"a": v, "b": v, "c": Vec.of(4, 5, 6)}).plain()
+    assert plain["_t"] == ["Object", 0]
+    a, b, c = plain["_v"]["a"], plain["_v"]["b"], plain["_v"]["c"]
+    assert a["_t"] == ["Vec", 1] and a["_v"] == [1, 2, 3]
+    assert "_r" in a and b == {"_r": a["_r"]}            # _r added retroactively on the second visit
+    assert c["_t"] == 1 and "_r" not in c                # bare type index afterwards, no id when unshared
+
+
+def test_key_order_follows_constructors():
+    test = scenes.configure("BoxBall")
+    plain = Serializer(test).plain()
+    assert list(plain["_v"].keys()) == ["renderer", "width", "height"]
+    r = plain["_v"]["renderer"]
+    assert r["_t"][0] == "IncrementalMultisamplingRenderer"
+    assert list(r["_v"].keys()) == ["world", "camera", "maxRecursionDepth", "samplesPerPixel"]
+    w = r["_v"]["world"]["_v"]
+    assert list(w.keys()) == ["bg_color", "objects", "lights"]
+    p0 = w["objects"]["_v"][0]["_v"]
+    assert list(p0.keys()) == ["transform", "inv_transform", "geometry", "material", "does_cast_shadow"]
+    m = p0["material"]["_v"]
+    assert list(m.keys()) == ["baseColor", "ambient", "diffusivity", "specularity", "reflectivity", "transmissivity", "smoothness"]
+    cam = r["_v"]["camera"]["_v"]
+    assert list(cam.keys()) == ["transform", "inv_transform", "FOV", "tan_fov", "aspect"]
+
+
+def test_white_is_shared_between_materials():
+    # SolidMaterialColor.White is one static object (src/materials.js:28): it must travel as a reference
+    a = PhongMaterial(Vec.of(1, 0, 0), 0.1, 0.4, 0.6, 100, 0.5)
+    s = Serializer([a]).to_json()
+    assert s.count('"_color":{"_t"') >= 1 and '"_r"' in s
+
+
+def test_triangle_psdata_fixed_and_bug_compat():
+    ps = [Vec.of(0, 0, 0, 1), Vec.of(1, 0, 0, 1), Vec.of(0, 1, 0, 1)]
+    tri = Triangle(ps, {"normal": [Vec.of(0, 0, 1, 0)] * 3})
+    good = Serializer(tri).plain()["_v"]
+    assert good["psdata"]["_t"][0] == "Object" and "normal" in good["psdata"]["_v"]
+    lossy = Serializer(tri, reference_bug_compat=True).plain()["_v"]     # src/geometry.js:355-357 writes ps twice
+    assert lossy["psdata"] == {"_r": lossy["ps"]["_r"]}
+
+
+def test_infinity_json_variants_and_msgpack_agree(blobs):
+    js, mp = blobs("cornell_box_path", width=32, height=32)
+    assert "Infinity" in js
+    a = lib.Scene(js, lib.FORMAT_JSON, device=None).info
+    b = lib.Scene(mp, lib.FORMAT_MSGPACK, device=None).info
+    assert a == b
+    # JSON.stringify writes null for the infinite IOR; the reader maps it back
+    ser = Serializer(scenes.configure("cornell_box_path", width=32, height=32))
+    c = lib.Scene(ser.to_json(js_compatible=True), lib.FORMAT_JSON, device=None).info
+    assert c == a and "Infinity" not in ser.to_json(js_compatible=True)
+
+
+def test_integer_valued_numbers_print_like_js():
+    s = Serializer({"v": Vec.of(1, 0.5, -0.0)}).to_json()
+    assert '"_v":[1,0.5,0]' in s
