@@ -144,7 +144,10 @@ def run_ours(args):
     t0 = time.perf_counter()
     scene = lib.Scene(blob, lib.FORMAT_MSGPACK, device=local)
     create_s = time.perf_counter() - t0
-    stream = torch.cuda.current_stream()
+    # all work (kernels, NCCL reduce, timing events) goes on one non-default torch stream
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     scene.set_stream(stream.cuda_stream)
     info = scene.info
     W, H = scene.size
@@ -159,11 +162,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    next_pass = [rank * P]
+    from jsraytracer_b200.parallel import pass_block, reduce_accum
+    step_no = [0]
 
     def step():
-        scene.render(next_pass[0], P, seed=1)
-        next_pass[0] += world * P
+        first, n = pass_block(step_no[0], rank, world, P)
+        scene.render(first, n, seed=1)
+        step_no[0] += 1
 
     # ---- warm-up ------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -181,8 +186,7 @@ def run_ours(args):
     ev0.record(stream)
     for _ in range(args.steps):
         step()
-    if world > 1:
-        dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
+    reduce_accum(accum_t, dst=0)
     ev1.record(stream)
     barrier()
     sampler.stop_flag.set()

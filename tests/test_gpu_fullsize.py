@@ -32,25 +32,31 @@ def test_bunny_path_1080p_properties():
 
 
 def test_bunny_path_converges_to_oracle_mean():
-    """Path-traced convergence: the GPU's 64-spp mean must lie within 3 sigma (per-pixel, from the
-    oracle's own sample variance) of an independent-seed oracle render, for >= 99 % of pixels."""
+    """Path-traced convergence (north_star: "within a stated per-pixel 3 sigma tolerance of a high-spp
+    reference render").  Reference R = 512-spp oracle render with its per-pixel sample variance;
+    stated tolerance: |mean_64 - R| <= 3 * sqrt(var/64 + var/512) + 2e-3 on every channel.  The GPU's
+    64-spp mean (its own seed) must satisfy it on >= 97 % of pixels and on no fewer pixels (-1 %)
+    than an independent 64-spp *oracle* render does — heavy-tailed pixels (specular paths) miss a
+    Gaussian 3 sigma bound for the reference itself, so the control run sets the achievable rate."""
     from jsraytracer_b200 import lib
     from oracle.oracle import OracleScene
-    kw = dict(width=240, height=135, aspect=16 / 9)
+    W, H = 160, 90
+    kw = dict(width=W, height=H, aspect=16 / 9)
     js, mp = scene_blobs("bunny_path", **kw)
     sc = lib.Scene(mp, lib.FORMAT_MSGPACK, device=0)
     orc = OracleScene(js)
-    n = 64
-    sc.render(0, n, seed=11)
-    g = sc.read_accum()[0][..., :3] / n
-    # oracle: n samples with a different seed, per-pixel mean and variance from per-pass images
-    s1 = np.zeros((135, 240, 3)); s2 = np.zeros((135, 240, 3))
-    for p in range(n):
+    n, nref = 64, 512
+    s1 = np.zeros((H, W, 3)); s2 = np.zeros((H, W, 3))
+    for p in range(nref):
         acc, _ = orc.render(1, first_pass=p, seed=99)
         s1 += acc; s2 += acc.astype(np.float64) ** 2
-    mean = s1 / n
-    var = np.maximum(s2 / n - mean ** 2, 0)
-    sigma = np.sqrt(2 * var / n) + 2e-3                         # difference of two independent n-sample means
-    ok = (np.abs(g - mean) <= 3 * sigma).all(axis=-1)
-    assert float(ok.mean()) >= 0.99, "within 3 sigma: %.4f" % ok.mean()
-    assert abs(float(g.mean()) - float(mean.mean())) < 0.01 * float(mean.mean()) + 1e-3
+    ref = s1 / nref
+    var = np.maximum(s2 / nref - ref ** 2, 0)
+    tol = 3 * np.sqrt(var / n + var / nref) + 2e-3
+    sc.render(0, n, seed=11)
+    g = sc.read_accum()[0][..., :3] / n
+    ctrl = orc.render(n, seed=12345)[0] / n
+    frac_gpu = float((np.abs(g - ref) <= tol).all(axis=-1).mean())
+    frac_ctrl = float((np.abs(ctrl - ref) <= tol).all(axis=-1).mean())
+    assert frac_gpu >= 0.97 and frac_gpu >= frac_ctrl - 0.01, (frac_gpu, frac_ctrl)
+    assert abs(float(g.mean()) - float(ref.mean())) < 0.01 * float(ref.mean()) + 1e-3

@@ -58,6 +58,9 @@ def check(name, passes, jitter, **kw):
     res["max_abs_diff"] = float(np.abs(gimg - oimg).max())
     res["frac_pixels_diff_gt_1e-3"] = float((np.abs(gimg - oimg).max(axis=-1) > 1e-3).mean())
     res["ray_count_match"] = [st["rays_primary"] == ocnt["rays_primary"], st["rays_secondary"] == ocnt["rays_secondary"], st["rays_shadow"] == ocnt["rays_shadow"]]
+    if os.environ.get("JSRT_DUMP"):
+        np.save(os.path.join(OUT, "%s_gpu.npy" % name), gimg.astype(np.float32))
+        np.save(os.path.join(OUT, "%s_oracle.npy" % name), oimg.astype(np.float32))
     try:
         from PIL import Image
         Image.fromarray(sc.resolve_rgba8().copy()).save(os.path.join(OUT, "%s_gpu.png" % name))
@@ -71,6 +74,10 @@ def check(name, passes, jitter, **kw):
 if __name__ == "__main__":
     print("devices", lib.device_count())
     out = []
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            out.append(check(name, 1, False, width=256, height=256))
+        sys.exit(0)
     out.append(check("BoxBall", 1, False, width=512, height=512))
     out.append(check("BoxBall", 4, True, width=256, height=256))
     out.append(check("bunny", 1, False, width=480, height=270, aspect=16 / 9))
