@@ -1,0 +1,96 @@
+// CUDARenderer — the B200 render path as a class that sits next to the reference's
+// SimpleRenderer / IncrementalMultisamplingRenderer (reference: src/renderers.js).
+//
+// Same constructor shape (world, camera, samplesPerPixel, maxRecursionDepth = 3) and the same
+// render(img, timelimit = 0, callback = false, x_offset = 0, x_delt = 1) signature as
+// IncrementalMultisamplingRenderer.render (src/renderers.js:66-70): it fills img.imgdata.data
+// (PixelBuffer.setColor semantics, src/pixelbuffer.js:39-49), calls callback({pass, completion})
+// at most every `timelimit` ms (src/renderers.js:103-112) and returns img.
+//
+// It replaces the worker pool of src/raytrace_launcher.js / src/worker.js for this path: the scene
+// travels once as `new Serializer({renderer, width, height}).plain()` (src/serializer.js) through
+// the N-API addon (js/napi/jsrt_addon.cc -> include/jsrt.h); all passes run on the GPU with the
+// accumulation buffer resident in HBM.
+//
+// NOTE: no JavaScript engine exists in the build image, so this file is exercised only through
+// its Python twin (jsraytracer_b200/renderers.py, same logic over the same C ABI).  It is loaded
+// like the reference's sources (tests/test_to_json.js:7-22 runs them with vm.runInThisContext), so
+// it uses the reference's globals (Serializer, Triangle, IncrementalMultisamplingRenderer).
+"use strict";
+
+// The reference's Triangle.serialize writes `psdata: serializeStep(this.ps)`
+// (src/geometry.js:355-357), which drops vertex normals / UVs that the worker path keeps.
+// Serialise what the constructor actually takes.
+function installTriangleSerializeFix() {
+    Triangle.prototype.serialize = function (serializer) {
+        return { ps: serializer.serializeStep(this.ps), psdata: serializer.serializeStep(this.psdata) };
+    };
+}
+
+class CUDARenderer extends IncrementalMultisamplingRenderer {
+    constructor(world, camera, samplesPerPixel, maxRecursionDepth = 3, options = {}) {
+        super(world, camera, samplesPerPixel, maxRecursionDepth);
+        // non-enumerable: must not travel with the scene (src/serializer.js:54-57 emits own enumerable keys)
+        Object.defineProperty(this, "_opt", { value: Object.assign({ seed: 1, device: 0, addon: null }, options), enumerable: false, writable: true });
+        Object.defineProperty(this, "_scene", { value: null, enumerable: false, writable: true });
+        Object.defineProperty(this, "_size", { value: null, enumerable: false, writable: true });
+    }
+
+    _addon() {
+        if (!this._opt.addon)
+            this._opt.addon = require("./napi/build/Release/jsrt_addon.node");
+        return this._opt.addon;
+    }
+
+    _ensureScene(img) {
+        const w = img.width(), h = img.height();
+        if (this._scene && this._size[0] === w && this._size[1] === h)
+            return this._scene;
+        if (this._scene) this._addon().destroyScene(this._scene);
+        installTriangleSerializeFix();
+        const plain = new Serializer({ renderer: this, width: w, height: h }).plain();
+        // msgpack keeps Infinity (IOR, SDF box sizes); JSON.stringify would write null, which the
+        // reader maps back to +Infinity at those fields, so both work (tests/test_to_json.js:36-38).
+        let blob, format;
+        try {
+            blob = Buffer.from(require("@msgpack/msgpack").encode(plain));
+            format = 1;
+        } catch (e) {
+            blob = Buffer.from(JSON.stringify(plain), "utf8");
+            format = 0;
+        }
+        this._scene = this._addon().createScene(blob, format, this._opt.device);   // throws Error(jsrt_last_error())
+        this._size = [w, h];
+        return this._scene;
+    }
+
+    render(img, timelimit = 0, callback = false, x_offset = 0, x_delt = 1) {
+        const addon = this._addon(), scene = this._ensureScene(img);
+        const spp = this.samplesPerPixel;
+        const step = (timelimit && callback) ? 1 : spp;
+        addon.resetAccum(scene);
+        let last = Date.now();
+        for (let done = 0; done < spp; ) {
+            const n = Math.min(step, spp - done);
+            addon.render(scene, done, n, this._opt.seed, x_offset, x_delt, 0);      // asynchronous on the scene's stream
+            done += n;
+            if (timelimit && callback) {
+                addon.synchronize(scene);
+                const now = Date.now();
+                if (now - last >= timelimit) {
+                    last = now;
+                    addon.resolveRGBA8(scene, img.imgdata.data);
+                    callback({ pass: done - 1, completion: done / spp });
+                }
+            }
+        }
+        addon.resolveRGBA8(scene, img.imgdata.data);        // Uint8ClampedArray of W*H*4, like PixelBuffer.setColor fills
+        return img;
+    }
+
+    close() {
+        if (this._scene) { this._addon().destroyScene(this._scene); this._scene = null; }
+    }
+}
+
+if (typeof module !== "undefined") module.exports = { CUDARenderer, installTriangleSerializeFix };

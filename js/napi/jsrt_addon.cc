@@ -1,0 +1,102 @@
+// N-API shim between Node and libjsrt (include/jsrt.h): the binding a maintainer of the
+// reference would add so that js/cuda_renderer.js can run under Node next to the web-worker
+// renderer.  Pure C N-API (node_api.h is a stable C ABI); one function per C entry point,
+// errors become thrown JS Errors carrying jsrt_last_error() (the reference throws strings,
+// e.g. src/aggregates.js:39).
+//
+// Not compiled in this repository's CI: neither node nor node_api.h exist in the build image
+// (SURVEY.md Appendix A).  Build under Node with:  npx node-gyp configure build   (binding.gyp).
+#include <node_api.h>
+
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/jsrt.h"
+
+#define NAPI_OK(call) do { if ((call) != napi_ok) { napi_throw_error(env, NULL, "N-API call failed: " #call); return NULL; } } while (0)
+
+static napi_value throw_last(napi_env env) { napi_throw_error(env, "JSRT", jsrt_last_error()); return NULL; }
+
+static jsrt_scene* scene_arg(napi_env env, napi_value v) {
+    void* p = NULL;
+    if (napi_get_value_external(env, v, &p) != napi_ok || !p) { napi_throw_type_error(env, NULL, "scene handle expected"); return NULL; }
+    return (jsrt_scene*)p;
+}
+static int32_t int_arg(napi_env env, napi_value v) { int32_t x = 0; napi_get_value_int32(env, v, &x); return x; }
+
+// createScene(blob: Buffer, format: 0|1, device: number) -> external
+static napi_value CreateScene(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value a[3];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    void* data = NULL; size_t len = 0;
+    NAPI_OK(napi_get_buffer_info(env, a[0], &data, &len));
+    int dev = argc > 2 ? int_arg(env, a[2]) : 0;
+    jsrt_scene* s = jsrt_scene_create((const uint8_t*)data, len, int_arg(env, a[1]), &dev, 1);
+    if (!s) return throw_last(env);
+    napi_value ext; NAPI_OK(napi_create_external(env, s, NULL, NULL, &ext));
+    return ext;
+}
+static napi_value DestroyScene(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value a[1]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    jsrt_scene* s = scene_arg(env, a[0]); if (s) jsrt_scene_destroy(s);
+    return NULL;
+}
+// render(scene, firstPass, nPasses, seed, xOffset, xDelt, flags)
+static napi_value Render(napi_env env, napi_callback_info info) {
+    size_t argc = 7; napi_value a[7]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    jsrt_scene* s = scene_arg(env, a[0]); if (!s) return NULL;
+    int64_t seed = 1; napi_get_value_int64(env, a[3], &seed);
+    if (jsrt_render(s, int_arg(env, a[1]), int_arg(env, a[2]), (uint64_t)seed, int_arg(env, a[4]), int_arg(env, a[5]), argc > 6 ? int_arg(env, a[6]) : 0))
+        return throw_last(env);
+    return NULL;
+}
+static napi_value ResetAccum(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value a[1]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    jsrt_scene* s = scene_arg(env, a[0]); if (!s) return NULL;
+    if (jsrt_reset_accum(s)) return throw_last(env);
+    return NULL;
+}
+static napi_value Synchronize(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value a[1]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    jsrt_scene* s = scene_arg(env, a[0]); if (!s) return NULL;
+    if (jsrt_synchronize(s)) return throw_last(env);
+    return NULL;
+}
+// resolveRGBA8(scene, out: Uint8ClampedArray | Buffer of W*H*4)
+static napi_value ResolveRGBA8(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value a[2]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    jsrt_scene* s = scene_arg(env, a[0]); if (!s) return NULL;
+    napi_typedarray_type ty; size_t n = 0; void* data = NULL; napi_value ab; size_t off = 0;
+    NAPI_OK(napi_get_typedarray_info(env, a[1], &ty, &n, &data, &ab, &off));
+    jsrt_info inf; if (jsrt_scene_info(s, &inf)) return throw_last(env);
+    if ((ty != napi_uint8_clamped_array && ty != napi_uint8_array) || n < (size_t)inf.width * inf.height * 4) {
+        napi_throw_range_error(env, NULL, "output must be a Uint8ClampedArray of width*height*4"); return NULL;
+    }
+    if (jsrt_resolve_rgba8(s, (uint8_t*)data)) return throw_last(env);
+    return NULL;
+}
+// primaryHits(scene, primId: Int32Array, t: Float32Array)  — parity probe
+static napi_value PrimaryHits(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value a[3]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    jsrt_scene* s = scene_arg(env, a[0]); if (!s) return NULL;
+    napi_typedarray_type ty; size_t n1 = 0, n2 = 0; void *d1 = NULL, *d2 = NULL; napi_value ab; size_t off;
+    NAPI_OK(napi_get_typedarray_info(env, a[1], &ty, &n1, &d1, &ab, &off));
+    NAPI_OK(napi_get_typedarray_info(env, a[2], &ty, &n2, &d2, &ab, &off));
+    if (jsrt_primary_hits(s, (int32_t*)d1, (float*)d2)) return throw_last(env);
+    return NULL;
+}
+static napi_value DeviceCount(napi_env env, napi_callback_info info) {
+    (void)info; napi_value v; NAPI_OK(napi_create_int32(env, jsrt_device_count(), &v)); return v;
+}
+
+static napi_value Init(napi_env env, napi_value exports) {
+    const struct { const char* name; napi_callback fn; } fns[] = {
+        {"createScene", CreateScene}, {"destroyScene", DestroyScene}, {"render", Render}, {"resetAccum", ResetAccum},
+        {"synchronize", Synchronize}, {"resolveRGBA8", ResolveRGBA8}, {"primaryHits", PrimaryHits}, {"deviceCount", DeviceCount}};
+    for (size_t i = 0; i < sizeof fns / sizeof fns[0]; ++i) {
+        napi_value f; NAPI_OK(napi_create_function(env, fns[i].name, NAPI_AUTO_LENGTH, fns[i].fn, NULL, &f));
+        NAPI_OK(napi_set_named_property(env, exports, fns[i].name, f));
+    }
+    return exports;
+}
+NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)

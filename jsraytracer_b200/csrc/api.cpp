@@ -83,7 +83,7 @@ int jsrt_scene_info(jsrt_scene* s, jsrt_info* o) {
     const HostScene& h = s->host;
     memset(o, 0, sizeof *o);
     o->width = h.width; o->height = h.height; o->samples_per_pixel = h.samples_per_pixel; o->max_depth = h.max_depth; o->jitter = h.jitter;
-    o->n_top = (int)h.tops.size(); o->n_prims = (int)h.prims.size(); o->n_ext_prims = h.ext_prim_count; o->n_nodes = (int)h.nodes.size();
+    o->n_top = (int)h.tops.size(); o->n_prims = (int)h.prims.size(); o->n_ext_prims = h.ext_prim_count; o->n_nodes = h.tree_node_count;
     o->n_tris = (int)h.tris.size(); o->n_materials = (int)h.materials.size(); o->n_lights = (int)h.lights.size();
     o->n_sdfs = (int)h.sdfs.size(); o->n_sdf_instrs = (int)h.sdf_code.size(); o->light_samples = h.light_samples; o->fanout = h.fanout;
     o->max_bvh_depth = h.max_bvh_depth;

@@ -102,7 +102,8 @@ JSRT_DEV float sphere_intersect(float3 o, float3 d, float minD) {
 }
 
 // Triangle.intersect src/geometry.js:368-375 with the constructor constants of :341-353.
-// `accept_lo` / `accept_hi` are the caller's acceptance window (t > lo && t < hi);
+// `accept_lo` / `accept_hi` are the caller's acceptance window (t > lo && t <= hi; the caller applies
+// its own strict tests and the tie rule);
 // the reference evaluates the barycentrics regardless and the caller filters, which
 // gives the same result as skipping them for a t that will be rejected anyway.
 JSRT_DEV float triangle_intersect(const Tri* __restrict__ tris, int idx, float3 o, float3 d, float accept_lo, float accept_hi) {
@@ -110,7 +111,7 @@ JSRT_DEV float triangle_intersect(const Tri* __restrict__ tris, int idx, float3 
     const float4 a = __ldg(tp);
     const float den = a.x * d.x + a.y * d.y + a.z * d.z;
     const float t = (den != 0.f) ? (a.w - (a.x * o.x + a.y * o.y + a.z * o.z)) / den : -CUDART_INF_F;
-    if (!(t > accept_lo && t < accept_hi) || t < 0.f || isinf(t)) return -CUDART_INF_F;
+    if (!(t > accept_lo && t <= accept_hi) || t < 0.f || isinf(t)) return -CUDART_INF_F;
     const float4 b = __ldg(tp + 1), c = __ldg(tp + 2), e = __ldg(tp + 3);
     const float3 P = ray_point(o, d, t);
     const float3 v2 = f3(P.x - b.x, P.y - b.y, P.z - b.z);

@@ -32,6 +32,7 @@ struct HostScene {
     int light_samples = 0;              // sum of samples over lights = shadow rays per shaded hit
     int fanout = 1;                     // 2 if any material can spawn both a reflection and a transmission child
     int max_bvh_depth = 0;
+    int tree_node_count = 0;            // BVH nodes over the distinct trees (one layout each)
 };
 
 void flattenScene(const WireDoc& doc, HostScene& out);

@@ -35,7 +35,7 @@ struct RayQueue { float4* o; float4* d; float4* w; };
 struct ShadowQueue { float4* o; float4* d; float4* c; };
 
 // counters[0], [1]: ray queue counts (ping-pong); [2]: shadow queue count
-struct Counters { int ray[2]; int shadow; int pad; unsigned long long stats[24]; };
+struct Counters { int ray[2]; int shadow; int pad; int cursor_extend; int cursor_shadow; int pad2[2]; unsigned long long stats[24]; };
 enum { ST_PRIMARY = 0, ST_SECONDARY = 1, ST_SHADOW = 2, ST_SHADED = 3, ST_SAMPLES = 4,
        ST_NODES = 8, ST_LEAF_PRIMS = 11, ST_TOP_PRIMS = 14, ST_SDF_EVALS = 17 };   // + ray class (0 primary, 1 secondary, 2 shadow)
 
@@ -52,7 +52,7 @@ __device__ __forceinline__ void flush_work(unsigned long long* stats, int cls, c
 struct GenParams {
     Camera cam;
     int width, height, x_offset, x_delt, ncols, npix_active;
-    int first_pass, jitter, max_depth;
+    int first_pass, jitter, max_depth, use_lens, count_samples;
     unsigned long long seed;
     long long first_sample;      // index of the batch's first sample within the call
     int n_samples;               // samples in this batch
@@ -104,31 +104,29 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(const __grid_constant_
         const uint32_t pixel = (uint32_t)(py * g.width + px);
         const uint32_t key = rng_sample_key(g.seed, pixel, (uint32_t)pass);
         float3 o, d;
-        camera_ray(g, px, py, key, g.jitter != 0, true, o, d);
+        camera_ray(g, px, py, key, g.jitter != 0, g.use_lens != 0, o, d);
         q.o[s] = make_float4(o.x, o.y, o.z, __int_as_float((int)pixel));
         q.d[s] = make_float4(d.x, d.y, d.z, __int_as_float(1));
         q.w[s] = make_float4(1.f, 1.f, 1.f, __int_as_float((pass << 8) | g.max_depth));
-        atomicAdd(&accum[pixel].w, 1.0f);      // samples taken for this pixel
+        if (g.count_samples) atomicAdd(&accum[pixel].w, 1.0f);      // samples taken for this pixel
     }
 }
 
 // ---------------------------------------------------------------------------------
-// extend: closest hit for every ray of the level (World.cast, src/world.js:28-30).
-// primary rays use minDistance 0, every other ray 0.0001 (src/materials.js:279,286,319,328).
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) extend_kernel(const __grid_constant__ DeviceScene sc, RayQueue q, const int* __restrict__ count,
-                                                         float4* __restrict__ hits, unsigned long long* stats) {
-    const int n = *count;
-    const int stride = gridDim.x * blockDim.x;
-    Work wp, ws;      // primary / secondary rays of this thread (COUNT only)
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float4 o4 = q.o[i], d4 = q.d[i];
-        const bool primary = __float_as_int(d4.w) == 1;
-        const float minD = primary ? 0.f : 0.0001f;
-        const Hit h = trace_ray<false, COUNT>(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), minD, CUDART_INF_F, primary ? &wp : &ws);
-        hits[i] = make_float4(h.t, __int_as_float(h.prim), __int_as_float(h.top), h.t_lo);
-    }
-    if (COUNT) { flush_work(stats, 0, wp); flush_work(stats, 1, ws); }
+// extend: closest hit for every ray of the level (World.cast, src/world.js:28-30);
+// shadow: `world.cast(new Ray(position, direction), 0.0001, 1, false)`, the sample is
+// dropped iff 0 < t < 1 (src/materials.js:250-252).  Two kernels each: trace.cuh.
+template <int MODE, bool COUNT, bool HAS_SDF>
+__global__ void __launch_bounds__(kBlock) prims_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
+    Work wp, ws;
+    prims_wave<MODE, COUNT, HAS_SDF>(sc, io, &wp, &ws);
+    if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
+}
+template <int MODE, bool COUNT, bool HAS_SDF>
+__global__ void __launch_bounds__(kBlock, 4) bvh_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
+    Work wp, ws;
+    bvh_wave<MODE, COUNT, HAS_SDF>(sc, io, &wp, &ws);
+    if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
 
 // warp-aggregated append: returns this lane's slot (valid only where `want`)
@@ -275,35 +273,19 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(const __grid_constant__ D
     if ((threadIdx.x & 31) == 0 && my_shaded) atomicAdd(stats + ST_SHADED, my_shaded);
 }
 
-// ---------------------------------------------------------------------------------
-// shadow: `world.cast(new Ray(position, direction), 0.0001, 1, false)`; the sample is
-// dropped iff 0 < t < 1 (src/materials.js:250-252).
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) shadow_kernel(const __grid_constant__ DeviceScene sc, ShadowQueue sq, const int* __restrict__ count, int cap,
-                                                         float4* __restrict__ accum, unsigned long long* stats) {
-    const int n = min(*count, cap);
-    const int stride = gridDim.x * blockDim.x;
-    Work w;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float4 o4 = sq.o[i], d4 = sq.d[i];
-        const Hit h = trace_ray<true, COUNT>(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), 0.0001f, 1.0f, &w);
-        if (h.prim < 0) {
-            const float4 c4 = sq.c[i];
-            accum_add(accum, (uint32_t)__float_as_int(o4.w), f3(c4.x, c4.y, c4.z));
-        }
-    }
-    if (COUNT) flush_work(stats, 2, w);
-}
-
 // bookkeeping between levels: fold queue sizes into the ray statistics and recycle the counters
 __global__ void level_end_kernel(Counters* c, int cur, int level, int next_cap, int shadow_cap) {
     c->stats[level == 0 ? ST_PRIMARY : ST_SECONDARY] += (unsigned long long)c->ray[cur];
     c->stats[ST_SHADOW] += (unsigned long long)min(c->shadow, shadow_cap);
     c->ray[cur] = 0;
     c->shadow = 0;
+    c->cursor_extend = 0; c->cursor_shadow = 0;
     if (c->ray[cur ^ 1] > next_cap) c->ray[cur ^ 1] = next_cap;
 }
-__global__ void set_count_kernel(Counters* c, int which, int n) { c->ray[which] = n; c->ray[which ^ 1] = 0; c->shadow = 0; c->stats[ST_SAMPLES] += (unsigned long long)n; }
+__global__ void set_count_kernel(Counters* c, int which, int n, int count_samples) {
+    c->ray[which] = n; c->ray[which ^ 1] = 0; c->shadow = 0; c->cursor_extend = 0; c->cursor_shadow = 0;
+    if (count_samples) c->stats[ST_SAMPLES] += (unsigned long long)n;
+}
 
 // PixelBuffer.setColor on buffer.times(1/(iter+1)) (src/renderers.js:98, src/pixelbuffer.js:39-49)
 __global__ void resolve_kernel(const float4* __restrict__ accum, uchar4* __restrict__ out, int npix) {
@@ -322,16 +304,15 @@ __global__ void resolve_kernel(const float4* __restrict__ accum, uchar4* __restr
     out[i] = make_uchar4(r[0], r[1], r[2], 255);
 }
 
-// parity probe: un-jittered pinhole primary rays -> (prim_id, t)
-__global__ void primary_hits_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ GenParams g, int* __restrict__ prim_id, float* __restrict__ tout) {
+// parity probe: hits of the un-jittered pinhole primary rays -> (prim_id, t)
+__global__ void hits_to_ids_kernel(const __grid_constant__ DeviceScene sc, const float4* __restrict__ hits, const float4* __restrict__ ro, int n,
+                                   int* __restrict__ prim_id, float* __restrict__ tout) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.width * g.height) return;
-    const int px = i % g.width, py = i / g.width;
-    float3 o, d;
-    camera_ray(g, px, py, 0u, false, false, o, d);
-    const Hit h = trace_ray<false>(sc, o, d, 0.f, CUDART_INF_F);
-    prim_id[i] = h.prim >= 0 ? sc.prims[h.prim].ext_id : -1;
-    tout[i] = h.t;
+    if (i >= n) return;
+    const float4 h = hits[i];
+    const int pixel = __float_as_int(ro[i].w), prim = __float_as_int(h.y);
+    prim_id[pixel] = prim >= 0 ? sc.prims[prim].ext_id : -1;
+    tout[pixel] = h.x;
 }
 
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) throw std::runtime_error(std::string("jsrt: CUDA error: ") + cudaGetErrorString(e__) + " at " #call); } while (0)
@@ -354,15 +335,15 @@ struct Renderer::Impl {
     DeviceScene ds{};
     std::vector<void*> allocs;
     float4* accum = nullptr;
-    RayQueue rq[2]{}; float4* hits = nullptr; ShadowQueue sq{};
+    RayQueue rq[2]{}; float4* hits = nullptr; float4* shadow_hits = nullptr; ShadowQueue sq{};
     Counters* counters = nullptr;
     int* overflow = nullptr;
     int ray_cap = 0, shadow_cap = 0, batch = 0;
     int passes = 0;
     size_t scene_bytes = 0, queue_bytes = 0;
-    int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0;
+    int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0, grid_bvh = 0;
     unsigned long long launches = 0;
-    bool profiling = false;
+    bool profiling = false, has_sdf = false;
     double ms[4] = {0, 0, 0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uchar4* rgba = nullptr; int* hit_ids = nullptr; float* hit_t = nullptr;
@@ -371,18 +352,29 @@ struct Renderer::Impl {
 
     template <class T> T* dalloc(size_t n) { T* p = nullptr; CK(cudaMalloc(&p, (n ? n : 1) * sizeof(T))); allocs.push_back(p); return p; }
 
+    // First call allocates, later calls (jsrt_scene_upload) re-copy into the same buffers.
     void uploadScene() {
-        for (void* p : scene_allocs) cudaFree(p);
-        scene_allocs.clear(); scene_bytes = 0;
+        scene_bytes = 0; up_index = 0;
+        bvh_tops_host.clear();
+        for (size_t i = 0; i < hs.tops.size(); ++i) if (hs.tops[i].kind == T_BVH && hs.tops[i].node_count > 0) bvh_tops_host.push_back((int)i);
         ds.tops = up(hs.tops); ds.prims = up(hs.prims); ds.xforms = up(hs.xforms); ds.xforms64 = up(hs.xforms64); ds.nodes = up(hs.nodes);
         ds.tris = up(hs.tris); ds.tri_shade = up(hs.tri_shade); ds.boxes = up(hs.boxes); ds.materials = up(hs.materials);
         ds.lights = up(hs.lights); ds.sdfs = up(hs.sdfs); ds.sdf_code = up(hs.sdf_code);
+        ds.bvh_tops = up(bvh_tops_host); ds.n_bvh = (int)bvh_tops_host.size();
         ds.n_top = (int)hs.tops.size(); ds.n_lights = (int)hs.lights.size(); ds.light_samples = hs.light_samples; ds.max_depth = hs.max_depth;
         for (int i = 0; i < 3; ++i) ds.bg[i] = hs.bg[i];
     }
     std::vector<void*> scene_allocs;
+    std::vector<int> bvh_tops_host;
+    size_t up_index = 0;
     template <class T> T* up(const std::vector<T>& vec) {
-        T* p = toDevice(vec, stream); scene_allocs.push_back((void*)p); scene_bytes += vec.size() * sizeof(T); return p;
+        T* p;
+        if (up_index < scene_allocs.size()) p = (T*)scene_allocs[up_index];
+        else { CK(cudaMalloc(&p, (vec.empty() ? 1 : vec.size()) * sizeof(T))); scene_allocs.push_back((void*)p); }
+        ++up_index;
+        if (!vec.empty()) CK(cudaMemcpyAsync(p, vec.data(), vec.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+        scene_bytes += vec.size() * sizeof(T);
+        return p;
     }
 
     void init(int dev, size_t queue_budget) {
@@ -406,7 +398,7 @@ struct Renderer::Impl {
         // depth-8 Cornell box, which runs in sub-frame batches.
         double worst = 1; for (int l = 1; l < hs.max_depth; ++l) worst *= hs.fanout;
         if (worst > 1e6) worst = 1e6;
-        const double per_sample = worst * (2.0 * 48 + 16 + 48.0 * std::max(1, hs.light_samples));
+        const double per_sample = worst * (2.0 * 48 + 16 + 64.0 * std::max(1, hs.light_samples));
         double b = (double)queue_budget / per_sample;
         const double want = (double)npix * 4;            // up to 4 passes per wave
         if (b > want) b = want;
@@ -417,13 +409,16 @@ struct Renderer::Impl {
         for (int k = 0; k < 2; ++k) { rq[k].o = dalloc<float4>(ray_cap); rq[k].d = dalloc<float4>(ray_cap); rq[k].w = dalloc<float4>(ray_cap); }
         hits = dalloc<float4>(ray_cap);
         sq.o = dalloc<float4>(shadow_cap); sq.d = dalloc<float4>(shadow_cap); sq.c = dalloc<float4>(shadow_cap);
-        queue_bytes = (size_t)ray_cap * (2 * 48 + 16) + (size_t)shadow_cap * 48;
+        shadow_hits = dalloc<float4>(shadow_cap);
+        queue_bytes = (size_t)ray_cap * (2 * 48 + 16) + (size_t)shadow_cap * (48 + 16);
 
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
         auto grid_for = [&](const void* fn) { int per = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, kBlock, 0)); return prop.multiProcessorCount * std::max(1, per); };
-        grid_extend = grid_for((const void*)extend_kernel<false>);
+        has_sdf = !hs.sdfs.empty();
+        grid_extend = has_sdf ? grid_for((const void*)prims_kernel<TM_EXTEND, false, true>) : grid_for((const void*)prims_kernel<TM_EXTEND, false, false>);
+        grid_bvh = has_sdf ? grid_for((const void*)bvh_kernel<TM_EXTEND, false, true>) : grid_for((const void*)bvh_kernel<TM_EXTEND, false, false>);
         grid_shade = grid_for((const void*)shade_kernel);
-        grid_shadow = grid_for((const void*)shadow_kernel<false>);
+        grid_shadow = has_sdf ? grid_for((const void*)prims_kernel<TM_SHADOW, false, true>) : grid_for((const void*)prims_kernel<TM_SHADOW, false, false>);
         grid_gen = grid_for((const void*)generate_kernel);
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
         CK(cudaStreamSynchronize(stream));
@@ -467,6 +462,31 @@ struct Renderer::Impl {
         if (profiling) { CK(cudaEventRecord(p.b, stream)); pending.push_back(p); if (pending.size() >= 8192) flushEvents(); }
     }
 
+    template <int MODE> void launchTrace(const TraceIO& io0, bool count_work, int grid_prims) {
+        TraceIO io = io0;
+        const bool has_bvh = ds.n_bvh > 0;
+        io.final_pass = has_bvh ? 0 : 1;
+        #define JSRT_LAUNCH(K, G, C, S) K<MODE, C, S><<<G, kBlock, 0, stream>>>(ds, io)
+        if (count_work) { if (has_sdf) JSRT_LAUNCH(prims_kernel, grid_prims, true, true); else JSRT_LAUNCH(prims_kernel, grid_prims, true, false); }
+        else { if (has_sdf) JSRT_LAUNCH(prims_kernel, grid_prims, false, true); else JSRT_LAUNCH(prims_kernel, grid_prims, false, false); }
+        if (has_bvh) {
+            ++launches;
+            if (count_work) { if (has_sdf) JSRT_LAUNCH(bvh_kernel, grid_bvh, true, true); else JSRT_LAUNCH(bvh_kernel, grid_bvh, true, false); }
+            else { if (has_sdf) JSRT_LAUNCH(bvh_kernel, grid_bvh, false, true); else JSRT_LAUNCH(bvh_kernel, grid_bvh, false, false); }
+        }
+        #undef JSRT_LAUNCH
+    }
+    void launchExtend(int cur, bool count_work) {
+        TraceIO io{}; io.o = rq[cur].o; io.d = rq[cur].d; io.hits = hits; io.count = &counters->ray[cur]; io.cap = ray_cap;
+        io.cursor = &counters->cursor_extend; io.stats = counters->stats;
+        timed(1, [&] { launchTrace<TM_EXTEND>(io, count_work, grid_extend); });
+    }
+    void launchShadow(bool count_work) {
+        TraceIO io{}; io.o = sq.o; io.d = sq.d; io.c = sq.c; io.hits = shadow_hits; io.accum = accum; io.count = &counters->shadow; io.cap = shadow_cap;
+        io.cursor = &counters->cursor_shadow; io.stats = counters->stats;
+        timed(3, [&] { launchTrace<TM_SHADOW>(io, count_work, grid_shadow); });
+    }
+
     GenParams genParams(int first_pass, uint64_t seed, int x_offset, int x_delt, int flags) const {
         GenParams g{};
         g.cam = hs.camera; g.width = hs.width; g.height = hs.height;
@@ -474,6 +494,7 @@ struct Renderer::Impl {
         g.ncols = x_offset < hs.width ? (hs.width - x_offset + g.x_delt - 1) / g.x_delt : 0;
         g.npix_active = g.ncols * hs.height;
         g.first_pass = first_pass; g.jitter = (flags & 1) ? 0 : 1; g.max_depth = hs.max_depth; g.seed = seed;
+        g.use_lens = 1; g.count_samples = 1;
         return g;
     }
 
@@ -487,21 +508,14 @@ struct Renderer::Impl {
         for (long long done = 0; done < total; done += batch) {
             g.first_sample = done;
             g.n_samples = (int)std::min<long long>(batch, total - done);
-            set_count_kernel<<<1, 1, 0, stream>>>(counters, 0, g.n_samples); ++launches;
+            set_count_kernel<<<1, 1, 0, stream>>>(counters, 0, g.n_samples, 1); ++launches;
             timed(0, [&] { generate_kernel<<<grid_gen, kBlock, 0, stream>>>(g, rq[0], accum); });
             int cur = 0;
             for (int level = 0; level < hs.max_depth; ++level) {
-                timed(1, [&] {
-                    if (count_work) extend_kernel<true><<<grid_extend, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, counters->stats);
-                    else extend_kernel<false><<<grid_extend, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, counters->stats);
-                });
+                launchExtend(cur, count_work);
                 timed(2, [&] { shade_kernel<<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap,
                                                                             sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow); });
-                if (hs.light_samples > 0)
-                    timed(3, [&] {
-                        if (count_work) shadow_kernel<true><<<grid_shadow, kBlock, 0, stream>>>(ds, sq, &counters->shadow, shadow_cap, accum, counters->stats);
-                        else shadow_kernel<false><<<grid_shadow, kBlock, 0, stream>>>(ds, sq, &counters->shadow, shadow_cap, accum, counters->stats);
-                    });
+                if (hs.light_samples > 0) launchShadow(count_work);
                 level_end_kernel<<<1, 1, 0, stream>>>(counters, cur, level, ray_cap, shadow_cap); ++launches;
                 cur ^= 1;
             }
@@ -543,12 +557,21 @@ void* Renderer::accumPtr() { return impl_->accum; }
 void Renderer::addPasses(int n) { impl_->passes += n; }
 void Renderer::primaryHits(int32_t* prim_id, float* t) {
     CK(cudaSetDevice(impl_->device));
-    GenParams g = impl_->genParams(0, 0, 0, 1, 1);
-    const int npix = impl_->hs.width * impl_->hs.height;
-    primary_hits_kernel<<<(npix + 127) / 128, 128, 0, impl_->stream>>>(impl_->ds, g, impl_->hit_ids, impl_->hit_t); ++impl_->launches;
+    Impl& m = *impl_;
+    GenParams g = m.genParams(0, 0, 0, 1, 1);
+    g.use_lens = 0; g.count_samples = 0;
+    const int npix = m.hs.width * m.hs.height;
+    for (int done = 0; done < npix; done += m.batch) {
+        g.first_sample = done; g.n_samples = std::min(m.batch, npix - done);
+        set_count_kernel<<<1, 1, 0, m.stream>>>(m.counters, 0, g.n_samples, 0); ++m.launches;
+        generate_kernel<<<m.grid_gen, kBlock, 0, m.stream>>>(g, m.rq[0], m.accum); ++m.launches;
+        m.launchExtend(0, false);
+        hits_to_ids_kernel<<<(g.n_samples + 255) / 256, 256, 0, m.stream>>>(m.ds, m.hits, m.rq[0].o, g.n_samples, m.hit_ids, m.hit_t); ++m.launches;
+        set_count_kernel<<<1, 1, 0, m.stream>>>(m.counters, 0, 0, 0); ++m.launches;
+    }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(prim_id, impl_->hit_ids, (size_t)npix * 4, cudaMemcpyDeviceToHost, impl_->stream));
-    CK(cudaMemcpyAsync(t, impl_->hit_t, (size_t)npix * 4, cudaMemcpyDeviceToHost, impl_->stream));
+    CK(cudaMemcpyAsync(prim_id, m.hit_ids, (size_t)npix * 4, cudaMemcpyDeviceToHost, m.stream));
+    CK(cudaMemcpyAsync(t, m.hit_t, (size_t)npix * 4, cudaMemcpyDeviceToHost, m.stream));
     synchronize();
 }
 void Renderer::getStats(RenderStats& s) {

@@ -50,10 +50,12 @@ struct TriShade {                 // per-vertex shading data (only read for shad
     float pad[2];
 };
 
-// BVH node, 32 bytes = two 128-bit loads.  Nodes are laid out in the
-// reference's visit order (greater child first, src/aggregates.js:221-222) so
-// a stackless walk `i -> i+1` on hit / `i -> skip` on miss reproduces the
-// reference traversal, including its tie rule, exactly.
+// BVH node, 32 bytes = two 128-bit loads.  Nodes are laid out in visit order so a
+// stackless walk `i -> i+1` on hit / `i -> skip` on miss needs no stack.  Placed
+// primitives are stored in the reference's visit order (greater child first,
+// src/aggregates.js:221-222), which makes "lower primitive index" the reference's tie
+// rule; the node array exists in eight orders, one per ray-direction octant, each
+// visiting the nearer child first (trace.cuh).
 struct BvhNode {
     float cx, cy, cz, hx;         // AABB centre, half-size x   (centre/half form: src/geometry.js:189-209)
     float hy, hz;
@@ -66,9 +68,11 @@ struct Top {                      // one entry of world.objects (src/world.js:7-
     int xform;                    // T_BVH / T_LIST: the aggregate's inv_transform
     int first_prim;               // first placed primitive
     int prim_count;               // T_PRIM: 1
-    int first_node;               // T_BVH: first BvhNode
+    int first_node;               // T_BVH: first BvhNode of layout 0; layout q starts at first_node + q * node_count
     int node_count;
-    int pad0, pad1;
+    int tri_base;                 // >= 0: every leaf object is an identity-transform, shadow-casting Triangle and
+                                  // triangle index = tri_base + (placed primitive index - first_prim); else -1
+    int n_layouts;                // 8: one node layout per ray-direction octant (near child first); 1: reference order only
 };
 
 struct Color {                    // a MaterialColor folded to Solid or Checkerboard (src/materials.js:27-76)

@@ -20,9 +20,10 @@ struct DeviceScene {
     const Light* lights;
     const SdfProgram* sdfs;
     const SdfInstr* sdf_code;
+    const int* bvh_tops;       // indices of the T_BVH entries of `tops`
     int n_top, n_lights, light_samples, max_depth;
     float bg[3];
-    int pad;
+    int n_bvh;
 };
 
 struct Hit { float t; int prim; int top; float t_lo; };   // t_lo: low-order part of an f64 hit distance (SDF hits)
@@ -70,13 +71,14 @@ JSRT_DEV float prim_intersect(const DeviceScene& sc, const int4 pa, float3 o, fl
 // One placed primitive against a ray given in its parent's space.
 // `t_lo` receives the low-order part of the distance for SDF hits (their f64 distance
 // is carried as t + t_lo so that shading recomputes the reference's hit point exactly).
+template <bool HAS_SDF>
 JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, float3 o, float3 d, float minD, float maxD, float best, bool shadow_ray,
                                      unsigned long long* sdf_evals = nullptr, float* t_lo = nullptr) {
     const int4* pp = reinterpret_cast<const int4*>(sc.prims + prim_index);
     const int4 pa = __ldg(pp);          // geom_kind, geom_index, material, xform
     const int flags = __ldg(reinterpret_cast<const int*>(pp + 1));
     if (shadow_ray && !(flags & PF_CASTS_SHADOW)) return CUDART_INF_F;     // src/world.js:117-118
-    if (pa.x == G_SDF) {
+    if (HAS_SDF && pa.x == G_SDF) {
         // ray.getTransformed(inv_transform) with the f64 matrix (src/math.js:392-397), then SDFGeometry.intersect
         const double* m = sc.xforms64[pa.w].m;
         const float3 lo = xf64_apply(m, o, 1.0), ld = xf64_apply(m, d, 0.0);
@@ -93,67 +95,215 @@ JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, floa
     return prim_intersect(sc, pa, o, d, minD, maxD, best, sdf_evals);
 }
 
-// World.cast: closest hit over the top-level list in order, strict `<` so the
-// earliest object wins exact ties (src/world.js:9-13).  ANY_HIT: shadow-ray
-// semantics of materials.js:250-252 — only "is there a hit with minD < t < maxD"
-// matters, so the walk stops at the first accepted hit (result-identical).
-template <bool ANY_HIT, bool COUNT = false>
-JSRT_DEV Hit trace_ray(const DeviceScene& sc, float3 o, float3 d, float minD, float maxD, Work* work = nullptr) {
-    unsigned long long* const se = COUNT ? &work->sdf_evals : nullptr;
-    Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
-    for (int ti = 0; ti < sc.n_top; ++ti) {
-        const int4* tp = reinterpret_cast<const int4*>(sc.tops + ti);
-        const int4 ta = __ldg(tp);          // kind, xform, first_prim, prim_count
-        if (ta.x == T_PRIM) {
-            if (COUNT) ++work->top_prims;
-            float tl = 0.f;
-            const float t = placed_prim_intersect(sc, ta.z, o, d, minD, maxD, best.t, ANY_HIT, se, &tl);
-            if (t > minD && t < best.t && t < maxD) { best.t = t; best.prim = ta.z; best.top = ti; best.t_lo = tl; if (ANY_HIT) return best; }
-            continue;
-        }
-        const XformReg m = load_xform(sc.xforms, ta.y);
-        const float3 lo = xf_point(m, o), ld = xf_dir(m, d);     // ray.getTransformed(this.getInvTransform())
-        if (ta.x == T_LIST) {
+// ---------------------------------------------------------------------------------
+// World.cast for a whole queue of rays, in two kernels per wave:
+//
+//   prims_wave  every top-level Primitive / plain Aggregate of world.objects, one ray per
+//               thread: all lanes run the same short loop, no divergence to speak of.
+//   bvh_wave    the BVHAggregates, persistent threads, one ray per lane, lanes refilled
+//               individually from a warp-local pool (one atomicAdd per 128 rays): a
+//               lane whose walk ends takes the next ray instead of idling while its
+//               neighbours finish (walk lengths differ by two orders of magnitude: most
+//               rays miss the mesh's root box after one node).
+//
+// Reference semantics being reproduced (src/world.js:7-15, src/aggregates.js:43-49,207-225):
+// the closest hit over world.objects with strict `<`, so the earliest object wins exact
+// ties; inside a BVHAggregate the reference walks greater-child-first and also keeps the
+// first of equal hits.  Both orders are ray-independent, so "first visited" is a static
+// rank: (top-level index, leaf rank).  Placed primitives are stored in leaf-rank order,
+// hence any evaluation order gives the reference's answer as long as ties go to the lower
+// (top index, primitive index) — which is what lets the analytic primitives run before
+// the BVHs and lets the walk pick, per ray-direction octant, one of eight stackless
+// (hit/miss-link) layouts of the same tree that visit the nearer child first.
+enum TraceMode { TM_EXTEND = 0, TM_SHADOW = 1 };
+
+struct TraceIO {
+    const float4* __restrict__ o;       // origin.xyz | pixel
+    const float4* __restrict__ d;       // direction.xyz | node id (extend)
+    const float4* __restrict__ c;       // shadow: contribution
+    float4* __restrict__ hits;          // t | prim | top | t_lo   (partial result between the two kernels)
+    float4* __restrict__ accum;         // shadow: pixel sums
+    const int* __restrict__ count;
+    int cap;
+    int* cursor;
+    unsigned long long* stats;
+    int final_pass;                     // prims_wave: 1 if no BVH pass follows
+};
+
+JSRT_DEV void accum_add3(float4* accum, uint32_t pixel, float3 c) {
+    float* a = reinterpret_cast<float*>(accum + pixel);
+    if (c.x != 0.f) atomicAdd(a + 0, c.x);
+    if (c.y != 0.f) atomicAdd(a + 1, c.y);
+    if (c.z != 0.f) atomicAdd(a + 2, c.z);
+}
+
+JSRT_DEV bool better_hit(float t, int top, const Hit& best) { return t < best.t || (t == best.t && top < best.top); }
+
+template <int MODE>
+JSRT_DEV void ray_window(const float4 d4, float& minD, float& maxD, bool& primary) {
+    if (MODE == TM_EXTEND) {
+        primary = __float_as_int(d4.w) == 1;
+        minD = primary ? 0.f : 0.0001f; maxD = CUDART_INF_F;       // src/world.js:31-34, src/materials.js:279,286,319,328
+    } else { primary = false; minD = 0.0001f; maxD = 1.0f; }        // src/materials.js:250
+}
+
+template <int MODE>
+JSRT_DEV void finish_ray(const TraceIO& io, int i, const Hit& best, const float4 o4) {
+    if (MODE == TM_EXTEND) io.hits[i] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
+    else if (best.prim < 0) {            // unoccluded: the light sample counts (src/materials.js:251-253)
+        const float4 c4 = io.c[i];
+        accum_add3(io.accum, (uint32_t)__float_as_int(o4.w), f3(c4.x, c4.y, c4.z));
+    }
+}
+
+template <int MODE, bool COUNT, bool HAS_SDF>
+JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other) {
+    constexpr bool ANY_HIT = (MODE == TM_SHADOW);
+    const int n = min(*io.count, io.cap);
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 o4 = io.o[i], d4 = io.d[i];
+        const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
+        float minD, maxD; bool primary;
+        ray_window<MODE>(d4, minD, maxD, primary);
+        Work* work = (COUNT && primary) ? work_primary : work_other;
+        Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
+        for (int ti = 0; ti < sc.n_top; ++ti) {
+            const int4 ta = __ldg(reinterpret_cast<const int4*>(sc.tops + ti));          // kind, xform, first_prim, prim_count
+            if (ta.x == T_BVH) continue;
+            float3 lo = o, ld = d;
+            if (ta.x == T_LIST) { const XformReg m = load_xform(sc.xforms, ta.y); lo = xf_point(m, o); ld = xf_dir(m, d); }   // src/aggregates.js:15
             for (int k = 0; k < ta.w; ++k) {
                 if (COUNT) ++work->top_prims;
                 float tl = 0.f;
-                const float t = placed_prim_intersect(sc, ta.z + k, lo, ld, minD, maxD, best.t, ANY_HIT, se, &tl);
-                if (t > minD && t < best.t && t < maxD) { best.t = t; best.prim = ta.z + k; best.top = ti; best.t_lo = tl; if (ANY_HIT) return best; }
+                const float t = placed_prim_intersect<HAS_SDF>(sc, ta.z + k, lo, ld, minD, maxD, best.t, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
+                if (t > minD && t < maxD && t < best.t) { best.t = t; best.prim = ta.z + k; best.top = ti; best.t_lo = tl; if (ANY_HIT) break; }
             }
-            continue;
+            if (ANY_HIT && best.prim >= 0) break;
         }
-        // T_BVH: stackless walk of the tree laid out in the reference's visit order.
-        // The aggregate starts from its own `ret` (distance = Infinity,
-        // src/aggregates.js:45) and the caller keeps it only if it beats the running
-        // best with strict `<`; pruning with min(local, running) best gives the same
-        // answer because a later-equal hit never replaces an earlier one.
-        const int4 tb = __ldg(tp + 1);      // first_node, node_count, pad, pad
-        const float4* nodes = reinterpret_cast<const float4*>(sc.nodes + tb.x);
-        float local_best = CUDART_INF_F, local_lo = 0.f; int local_prim = -1;
-        int i = 0;
-        while (i < tb.y) {
-            const float4 n0 = __ldg(nodes + 2 * i), n1 = __ldg(nodes + 2 * i + 1);
+        if (io.final_pass) finish_ray<MODE>(io, i, best, o4);
+        else io.hits[i] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
+    }
+}
+
+template <int MODE, bool COUNT, bool HAS_SDF>
+JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other) {
+    constexpr bool ANY_HIT = (MODE == TM_SHADOW);
+    constexpr int BATCH = 128;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int n = min(*io.count, io.cap);
+    int pool_next = 0, pool_end = 0;      // warp-uniform
+    bool exhausted = false;               // warp-uniform
+
+    // per-lane ray state
+    int cur = -1;
+    float4 o4 = make_float4(0, 0, 0, 0);
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), lo = o, inv = d;
+    bool parx = false, pary = false, parz = false;
+    float minD = 0.f, maxD = CUDART_INF_F;
+    Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
+    int bi = 0, top_i = 0;
+    float3 ld = d;
+    int node_i = 0, node_end = 0, first_prim = 0, tri_base = -1;
+    const float4* nodes = nullptr;
+    float local_best = CUDART_INF_F, local_lo = 0.f; int local_prim = -1;
+    Work* work = work_other;
+
+    // enter BVH number `bi` of the scene (Aggregate.intersect / BVHAggregate.intersect, src/aggregates.js:43-46)
+    auto enter = [&]() {
+        top_i = __ldg(sc.bvh_tops + bi);
+        const int4* tp = reinterpret_cast<const int4*>(sc.tops + top_i);
+        const int4 ta = __ldg(tp), tb = __ldg(tp + 1);      // kind, xform, first_prim, prim_count | first_node, node_count, tri_base, n_layouts
+        const XformReg m = load_xform(sc.xforms, ta.y);
+        lo = xf_point(m, o); ld = xf_dir(m, d);              // ray.getTransformed(this.getInvTransform())
+        // AABB.get_intersects treats |d_i| <= 1e-7 as parallel (src/geometry.js:194,205); otherwise the slab
+        // distances are (p_i +- h_i) / d_i, evaluated here as a product with the reciprocal
+        parx = !(fabsf(ld.x) > 0.0000001f); pary = !(fabsf(ld.y) > 0.0000001f); parz = !(fabsf(ld.z) > 0.0000001f);
+        inv = f3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
+        const int octant = (tb.w == 8) ? ((ld.x < 0.f ? 1 : 0) | (ld.y < 0.f ? 2 : 0) | (ld.z < 0.f ? 4 : 0)) : 0;
+        nodes = reinterpret_cast<const float4*>(sc.nodes + tb.x + octant * tb.y);
+        node_i = 0; node_end = tb.y; first_prim = ta.z; tri_base = tb.z;
+        local_best = CUDART_INF_F; local_prim = -1; local_lo = 0.f;
+    };
+
+    for (;;) {
+        // ---- refill idle lanes ---------------------------------------------------------
+        const unsigned idle_mask = __ballot_sync(FULL, cur < 0);
+        if (idle_mask) {
+            if (pool_next >= pool_end && !exhausted) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(io.cursor, BATCH);
+                base = __shfl_sync(FULL, base, 0);
+                pool_next = base; pool_end = min(base + BATCH, n);
+                if (base >= n) { exhausted = true; pool_next = pool_end = 0; }
+            }
+            const int avail = pool_end - pool_next;
+            if (avail > 0) {
+                const int rank = __popc(idle_mask & ((1u << lane) - 1u));
+                if (cur < 0 && rank < avail) {
+                    cur = pool_next + rank;
+                    o4 = io.o[cur];
+                    const float4 d4 = io.d[cur], h4 = io.hits[cur];
+                    o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
+                    bool primary;
+                    ray_window<MODE>(d4, minD, maxD, primary);
+                    if (COUNT) work = primary ? work_primary : work_other;
+                    best.t = h4.x; best.prim = __float_as_int(h4.y); best.top = __float_as_int(h4.z); best.t_lo = h4.w;
+                    bi = 0;
+                    if (ANY_HIT && best.prim >= 0) cur = -1;        // already occluded by a top-level primitive
+                    else enter();
+                }
+                pool_next += min(avail, __popc(idle_mask));
+            } else if (exhausted && idle_mask == FULL) break;
+        }
+        if (cur < 0) continue;
+
+        // ---- one node of BVHAggregateNode.intersect (src/aggregates.js:207-225) ----------
+        bool done_tree = node_i >= node_end;
+        if (!done_tree) {
+            const float4 n0 = __ldg(nodes + 2 * node_i), n1 = __ldg(nodes + 2 * node_i + 1);
             const int skip = __float_as_int(n1.z), leaf = __float_as_int(n1.w);
-            float b0, b1;
             if (COUNT) ++work->nodes;
-            // src/aggregates.js:208-209
-            if (aabb_intersects(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), lo, ld, minD, maxD, b0, b1) && b0 <= maxD && b1 >= minD && b0 <= local_best) {
+            const float bound = fminf(local_best, best.t);
+            // AABB.get_intersects (src/geometry.js:189-209); the per-axis early returns are equivalent to one
+            // final test because t_min only grows and t_max only shrinks
+            const float px = n0.x - lo.x, py = n0.y - lo.y, pz = n0.z - lo.z;
+            const float ax = (px + n0.w) * inv.x, bx = (px - n0.w) * inv.x;
+            const float ay = (py + n1.x) * inv.y, by = (py - n1.x) * inv.y;
+            const float az = (pz + n1.y) * inv.z, bz = (pz - n1.y) * inv.z;
+            float b0 = -CUDART_INF_F, b1 = CUDART_INF_F;
+            bool miss = false;
+            if (parx) miss = fabsf(px) > n0.w; else { b0 = fminf(ax, bx); b1 = fmaxf(ax, bx); }
+            if (pary) miss = miss || fabsf(py) > n1.x; else { b0 = fmaxf(b0, fminf(ay, by)); b1 = fminf(b1, fmaxf(ay, by)); }
+            if (parz) miss = miss || fabsf(pz) > n1.y; else { b0 = fmaxf(b0, fminf(az, bz)); b1 = fminf(b1, fmaxf(az, bz)); }
+            const bool hit_box = !miss && !(b0 > b1) && !(b1 < minD) && !(b0 > maxD) && b0 <= bound;    // + :209
+            if (hit_box) {
                 if (leaf != -1) {
-                    const int cnt = (int)((unsigned)leaf >> 24), first = ta.z + (leaf & 0xffffff);
+                    const int cnt = (int)((unsigned)leaf >> 24), rel = leaf & 0xffffff;
                     for (int k = 0; k < cnt; ++k) {
                         if (COUNT) ++work->leaf_prims;
-                        float tl = 0.f;
-                        const float t = placed_prim_intersect(sc, first + k, lo, ld, minD, maxD, fminf(local_best, best.t), ANY_HIT, se, &tl);
-                        if (t > minD && t < maxD && t < local_best) { local_best = t; local_prim = first + k; local_lo = tl; }   // :213
+                        const int pi = first_prim + rel + k;
+                        float tl = 0.f, t;
+                        if (tri_base >= 0) t = triangle_intersect(sc.tris, tri_base + rel + k, lo, ld, minD, fminf(maxD, bound));
+                        else t = placed_prim_intersect<HAS_SDF>(sc, pi, lo, ld, minD, maxD, bound, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
+                        // :213 with the rank tie rule (see the header comment)
+                        if (t > minD && t < maxD && (t < local_best || (t == local_best && pi < local_prim))) { local_best = t; local_prim = pi; local_lo = tl; }
                     }
-                    if (ANY_HIT && local_prim >= 0) break;
-                    i = skip;
-                } else ++i;
-            } else i = skip;
+                    node_i = (ANY_HIT && local_prim >= 0) ? node_end : skip;
+                } else ++node_i;
+            } else node_i = skip;
+            done_tree = node_i >= node_end;
         }
-        if (local_best > minD && local_best < best.t && local_best < maxD) { best.t = local_best; best.prim = local_prim; best.top = ti; best.t_lo = local_lo; if (ANY_HIT) return best; }
+        if (done_tree) {
+            if (local_best > minD && local_best < maxD && better_hit(local_best, top_i, best)) {
+                best.t = local_best; best.prim = local_prim; best.top = top_i; best.t_lo = local_lo;
+            }
+            ++bi;
+            if (bi >= sc.n_bvh || (ANY_HIT && best.prim >= 0)) { finish_ray<MODE>(io, cur, best, o4); cur = -1; }
+            else enter();
+        }
     }
-    return best;
 }
 
 }  // namespace jsrt
