@@ -152,7 +152,8 @@ __device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float3 
 // shade: World.color's miss / hit handling (src/world.js:31-41), Primitive.color
 // (:125-137), Material.color (src/materials.js).  Emits ambient, pushes shadow rays
 // and children.
-__global__ void __launch_bounds__(kBlock) shade_kernel(const __grid_constant__ DeviceScene sc, RayQueue q, const int* __restrict__ count,
+template <bool HAS_SDF>
+__global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : 3) shade_kernel(const __grid_constant__ DeviceScene sc, RayQueue q, const int* __restrict__ count,
                                                         const float4* __restrict__ hits, RayQueue next, int* next_count, int next_cap,
                                                         ShadowQueue sq, int* shadow_count, int shadow_cap, float4* __restrict__ accum,
                                                         unsigned long long seed, unsigned long long* stats, int* overflow) {
@@ -190,13 +191,13 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(const __grid_constant__ D
                     inv = (flags & PF_IDENTITY_XFORM) ? anc : xf_compose(inv, anc);
                 }
                 float3 lp;
-                if (pa.x == G_SDF && ta.x == T_PRIM) {
+                if (HAS_SDF && pa.x == G_SDF && ta.x == T_PRIM) {
                     // the SDF normal is a forward difference: recompute the reference's local hit point exactly
                     // (f64 matrix, f64 distance carried as t + t_lo)
                     const double* m64 = sc.xforms64[pa.w].m;
                     lp = ray_point_f64(xf64_apply(m64, o, 1.0), xf64_apply(m64, d, 0.0), (double)t + (double)h4.w);
                 } else lp = ray_point(xf_point(inv, o), xf_dir(inv, d), t);
-                float3 ln; material_data(sc, pa.x, pa.y, flags, lp, ln, s.uv, s.has_uv, s.basecolor);
+                float3 ln; material_data<HAS_SDF>(sc, pa.x, pa.y, flags, lp, ln, s.uv, s.has_uv, s.basecolor);
                 s.normal = normalized3(xf_normal(inv, ln));
                 s.position = ray_point(o, d, t);
                 mat = sc.materials + pa.z;
@@ -417,7 +418,7 @@ struct Renderer::Impl {
         has_sdf = !hs.sdfs.empty();
         grid_extend = has_sdf ? grid_for((const void*)prims_kernel<TM_EXTEND, false, true>) : grid_for((const void*)prims_kernel<TM_EXTEND, false, false>);
         grid_bvh = has_sdf ? grid_for((const void*)bvh_kernel<TM_EXTEND, false, true>) : grid_for((const void*)bvh_kernel<TM_EXTEND, false, false>);
-        grid_shade = grid_for((const void*)shade_kernel);
+        grid_shade = has_sdf ? grid_for((const void*)shade_kernel<true>) : grid_for((const void*)shade_kernel<false>);
         grid_shadow = has_sdf ? grid_for((const void*)prims_kernel<TM_SHADOW, false, true>) : grid_for((const void*)prims_kernel<TM_SHADOW, false, false>);
         grid_gen = grid_for((const void*)generate_kernel);
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
@@ -513,8 +514,12 @@ struct Renderer::Impl {
             int cur = 0;
             for (int level = 0; level < hs.max_depth; ++level) {
                 launchExtend(cur, count_work);
-                timed(2, [&] { shade_kernel<<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap,
-                                                                            sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow); });
+                timed(2, [&] {
+                    if (has_sdf) shade_kernel<true><<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap,
+                                                                                       sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow);
+                    else shade_kernel<false><<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap,
+                                                                                sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow);
+                });
                 if (hs.light_samples > 0) launchShadow(count_work);
                 level_end_kernel<<<1, 1, 0, stream>>>(counters, cur, level, ray_cap, shadow_cap); ++launches;
                 cur ^= 1;

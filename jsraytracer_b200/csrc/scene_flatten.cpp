@@ -233,7 +233,7 @@ struct Flattener {
         if (doc.truthy(doc.field(n, "isLeaf"))) {
             const Val* objs = doc.field(n, "objects");
             const uint32_t cnt = objs ? doc.length(objs) : 0;
-            if (cnt > 255) fail("jsrt: BVH leaf with more than 255 objects");
+            if (cnt > 127) fail("jsrt: BVH leaf with more than 127 objects");
             const int first = (int)out.prims.size() - first_prim;
             if (first >= (1 << 24)) fail("jsrt: more than 16M primitives in one BVH");
             for (uint32_t i = 0; i < cnt; ++i) placePrim(doc.at(objs, i), nullptr);

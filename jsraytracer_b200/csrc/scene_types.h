@@ -125,6 +125,17 @@ enum SdfOp : int {
     S_SBEGIN,      //                                     push a local scale accumulator (= 1)
     S_SEND,        //                                     pop it; enclosing scale *= popped   (Sequence / Recursive transformers
                    //                                     return their own product, src/sdf.js:387-394,408-415)
+    // ---- material program (getMaterialData, src/sdf.js:86-88,102-104,119-121,149-154,...): straight-line code over a
+    // stack of {distance, basecolor, UV}; every leaf is evaluated, selections / blends fold them bottom-up.
+    MP_END = 32,
+    MP_LEAF,       // f[0..2] = basecolor, idx = 1: UV = cartesianToSpherical(normalize(p)) (SphereSDF), 0: no UV
+    MP_ATTACH,     // idx = first instruction of the node's own distance program: top.d = distance(p)
+    MP_SELMIN,     // pop b, a: keep a unless b.d < a.d          (UnionSDF: Math.indexOfMin, first minimum wins)
+    MP_SELMAX,     // pop b, a: keep a unless b.d > a.d          (IntersectionSDF)
+    MP_DIFF,       // pop neg, pos: pos.d > -neg.d ? pos : neg   (DifferenceSDF)
+    MP_BLEND_U,    // a0 = k: SmoothUnion        mix = smoothMinBlend(a.d, b.d, k)
+    MP_BLEND_I,    // a0 = k: SmoothIntersection mix = 1 - smoothMinBlend(-a.d, -b.d, k)
+    MP_BLEND_D,    // a0 = k: SmoothDifference   mix = smoothMinBlend(-pos.d, neg.d, k)
 };
 struct SdfInstr { int op; int idx; double a0; float f[4]; };   // 32 bytes: two 128-bit loads
 struct SdfProgram {
@@ -134,7 +145,8 @@ struct SdfProgram {
     double distance_epsilon, max_trace_distance, normal_step_size;
     float cx, cy, cz, hx, hy, hz; // SDFGeometry.aabb
     float base[3];
-    float pad1[3];
+    int mat_first;                // first instruction of the material program, -1 if uniform_base
+    float pad1[2];
 };
 
 struct Camera {                   // src/cameras.js; f64 so primary rays match the reference bit for bit

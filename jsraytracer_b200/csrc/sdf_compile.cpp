@@ -13,6 +13,8 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <unordered_map>
+#include <vector>
 
 #include "host_scene.h"
 
@@ -26,7 +28,7 @@ struct SdfCompiler {
     const WireDoc& doc;
     HostScene& out;
     int depth_points = 1, max_points = 1, depth_dist = 0, max_dist = 0, depth_scale = 1, max_scale = 1;
-    bool base_set = false, base_uniform = true;
+    bool base_set = false, base_uniform = true, any_sphere_leaf = false;
     float base[3] = {1, 1, 1};
 
     SdfCompiler(const WireDoc& d, HostScene& o) : doc(d), out(o) {}
@@ -50,6 +52,51 @@ struct SdfCompiler {
         if (const Val* b = doc.field(n, "basecolor")) doc.vec(b, c);
         if (!base_set) { base_set = true; for (int i = 0; i < 3; ++i) base[i] = (float)c[i]; }
         else for (int i = 0; i < 3; ++i) if (base[i] != (float)c[i]) base_uniform = false;
+    }
+
+    // ---- material program -------------------------------------------------------------
+    std::vector<SdfInstr> mat;                          // built aside, appended after the distance programs
+    std::unordered_map<const Val*, int> dist_prog;      // node -> first instruction of its standalone distance program
+    int mat_depth = 0, mat_max = 0;
+    void memit(int op, int idx = 0, double a0 = 0, float f0 = 0, float f1 = 0, float f2 = 0) {
+        SdfInstr i{}; i.op = op; i.idx = idx; i.a0 = a0; i.f[0] = f0; i.f[1] = f1; i.f[2] = f2;
+        mat.push_back(i);
+        if (op == MP_LEAF) { if (++mat_depth > mat_max) mat_max = mat_depth; }
+        else if (op >= MP_SELMIN && op <= MP_BLEND_D) --mat_depth;
+    }
+    int distanceProgram(const Val* n) {
+        n = doc.resolve(n);
+        auto it = dist_prog.find(n);
+        if (it != dist_prog.end()) return it->second;
+        const int first = (int)out.sdf_code.size();
+        depth_points = 1; depth_dist = 0; depth_scale = 1;
+        node(n); emit(S_END);
+        return dist_prog[n] = first;
+    }
+    void attach(const Val* n) { memit(MP_ATTACH, distanceProgram(n)); }
+    // pushes node.getMaterialData(p) (the point is NOT transformed on the way down: src/sdf.js:334-336,358-361)
+    void material(const Val* n) {
+        n = doc.resolve(n);
+        const std::string& ty = doc.typeName(n);
+        auto base = [&](float c[3]) { double v[4] = {1, 1, 1, 0}; if (const Val* b = doc.field(n, "basecolor")) doc.vec(b, v); for (int i = 0; i < 3; ++i) c[i] = (float)v[i]; };
+        if (ty == "SphereSDF") { float c[3]; base(c); memit(MP_LEAF, 1, 0, c[0], c[1], c[2]); }
+        else if (ty == "BoxSDF" || ty == "TetrahedronSDF") { float c[3]; base(c); memit(MP_LEAF, 0, 0, c[0], c[1], c[2]); }
+        else if (ty == "UnionSDF" || ty == "IntersectionSDF") {
+            const Val* cs = doc.field(n, "children");
+            for (uint32_t i = 0; i < doc.length(cs); ++i) { material(doc.at(cs, i)); attach(doc.at(cs, i)); if (i) memit(ty == "UnionSDF" ? MP_SELMIN : MP_SELMAX); }
+        }
+        else if (ty == "DifferenceSDF") { material(doc.field(n, "positive")); attach(doc.field(n, "positive")); material(doc.field(n, "negative")); attach(doc.field(n, "negative")); memit(MP_DIFF); }
+        else if (ty == "SmoothUnionSDF" || ty == "SmoothIntersectionSDF") {
+            material(doc.field(n, "childA")); attach(doc.field(n, "childA")); material(doc.field(n, "childB")); attach(doc.field(n, "childB"));
+            memit(ty == "SmoothUnionSDF" ? MP_BLEND_U : MP_BLEND_I, 0, doc.number(doc.field(n, "k"), 1));
+        }
+        else if (ty == "SmoothDifferenceSDF") {
+            material(doc.field(n, "positive")); attach(doc.field(n, "positive")); material(doc.field(n, "negative")); attach(doc.field(n, "negative"));
+            memit(MP_BLEND_D, 0, doc.number(doc.field(n, "k"), 1));
+        }
+        else if (ty == "RoundSDF" || ty == "TransformSDF") material(doc.field(n, "child_sdf"));
+        else if (ty == "RecursiveTransformUnionSDF") material(doc.field(n, "sdf"));
+        else fail("jsrt: unsupported SDF node '" + ty + "'");
     }
 
     void transformer(const Val* t) {
@@ -82,7 +129,7 @@ struct SdfCompiler {
     void node(const Val* n) {
         n = doc.resolve(n);
         const std::string& ty = doc.typeName(n);
-        if (ty == "SphereSDF") { noteBase(n); emit(S_SPHERE, doc.number(doc.field(n, "radius"), kInf)); }
+        if (ty == "SphereSDF") { noteBase(n); any_sphere_leaf = true; emit(S_SPHERE, doc.number(doc.field(n, "radius"), kInf)); }
         else if (ty == "BoxSDF") { noteBase(n); double s[4]; doc.vec(doc.field(n, "size"), s, kInf); emit(S_BOX, 0, (float)s[0], (float)s[1], (float)s[2]); }
         else if (ty == "TetrahedronSDF") { noteBase(n); emit(S_TETRA); }
         else if (ty == "UnionSDF" || ty == "IntersectionSDF") {
@@ -131,6 +178,16 @@ int compileSdf(const WireDoc& doc, const Val* g, HostScene& out) {
     p.cx = (float)ce[0]; p.cy = (float)ce[1]; p.cz = (float)ce[2]; p.hx = (float)h[0]; p.hy = (float)h[1]; p.hz = (float)h[2];
     p.uniform_base = c.base_uniform ? 1 : 0;
     for (int i = 0; i < 3; ++i) p.base[i] = c.base[i];
+    p.mat_first = -1;
+    if (!c.base_uniform || c.any_sphere_leaf) {
+        // leaves disagree on basecolor, or a SphereSDF leaf supplies UVs: compile getMaterialData
+        c.material(doc.field(g, "root_sdf"));
+        c.memit(MP_END);
+        if (c.mat_max > 8) fail("jsrt: SDF material program needs more than 8 stack slots");
+        p.mat_first = (int)out.sdf_code.size();
+        out.sdf_code.insert(out.sdf_code.end(), c.mat.begin(), c.mat.end());
+        p.uniform_base = 0;
+    }
     out.sdfs.push_back(p);
     return (int)out.sdfs.size() - 1;
 }

@@ -43,7 +43,56 @@ JSRT_DEV float3 sphere_pick(float u0, float u1) {
     return f3(ct * sin_phi, cosf(phi), st * sin_phi);
 }
 
+// SDF material program (sdf_compile.cpp): root_sdf.getMaterialData(p) -> basecolor, UV.
+struct SdfMat { double d; float3 base; float2 uv; bool has_uv; };
+JSRT_DEV double smooth_min_blend(double a, double b, double k) {     // src/sdf.js:133-137
+    const double h = jsd_max(dsub(k, fabs(dsub(a, b))), 0.0) / k;
+    const double m = dmul(dmul(dmul(h, h), h), 0.5);
+    return (a < b) ? m : dsub(1.0, m);
+}
+JSRT_DEV SdfMat sdf_blend(double mix, const SdfMat& a, const SdfMat& b) {   // SDF.blendMaterialData src/sdf.js:66-73
+    if (mix <= 0.0) return a;
+    if (mix >= 1.0) return b;
+    SdfMat r; r.d = 0; r.has_uv = true;
+    const float2 ua = a.has_uv ? a.uv : make_float2(0.f, 0.f), ub = b.has_uv ? b.uv : make_float2(0.f, 0.f);
+    const double w = dsub(1.0, mix);
+    r.base = f3((float)dadd(dmul(w, a.base.x), dmul(mix, b.base.x)), (float)dadd(dmul(w, a.base.y), dmul(mix, b.base.y)), (float)dadd(dmul(w, a.base.z), dmul(mix, b.base.z)));
+    r.uv = make_float2((float)dadd(dmul(w, ua.x), dmul(mix, ub.x)), (float)dadd(dmul(w, ua.y), dmul(mix, ub.y)));
+    return r;
+}
+JSRT_DEV void sdf_material(const DeviceScene& sc, int first, float3 p, float3& base, float2& uv, bool& has_uv) {
+    SdfMat M[8]; int sp = 0;
+    for (int pc = first;; ++pc) {
+        const int4 i0 = __ldg(reinterpret_cast<const int4*>(sc.sdf_code + pc));
+        const float4 fv = __ldg(reinterpret_cast<const float4*>(sc.sdf_code + pc) + 1);
+        const double a0 = __hiloint2double(i0.w, i0.z);
+        switch (i0.x) {
+            case MP_LEAF: {
+                SdfMat m; m.d = 0; m.base = f3(fv.x, fv.y, fv.z); m.has_uv = false; m.uv = make_float2(0.f, 0.f);
+                if (i0.y == 1) {          // SphereSDF.getMaterialData src/sdf.js:235-240
+                    const double nn = sqrt(ddot4(p.x, p.y, p.z, 0.0, p.x, p.y, p.z, 0.0));
+                    float3 n = p;
+                    if (nn > 0.00001) n = f3((float)dmul(p.x, 1.0 / nn), (float)dmul(p.y, 1.0 / nn), (float)dmul(p.z, 1.0 / nn));
+                    m.uv = make_float2((float)dadd(0.5, atan2((double)n.z, (double)n.x) / dmul(2.0, 3.141592653589793)),
+                                       (float)dsub(0.5, asin((double)n.y) / 3.141592653589793));
+                    m.has_uv = true;
+                }
+                M[sp++] = m; break;
+            }
+            case MP_ATTACH: M[sp - 1].d = sdf_eval(sc.sdf_code + i0.y, sc.xforms64, p); break;
+            case MP_SELMIN: { --sp; if (M[sp].d < M[sp - 1].d) M[sp - 1] = M[sp]; break; }
+            case MP_SELMAX: { --sp; if (M[sp].d > M[sp - 1].d) M[sp - 1] = M[sp]; break; }
+            case MP_DIFF: { --sp; if (!(M[sp - 1].d > -M[sp].d)) M[sp - 1] = M[sp]; break; }
+            case MP_BLEND_U: { --sp; M[sp - 1] = sdf_blend(smooth_min_blend(M[sp - 1].d, M[sp].d, a0), M[sp - 1], M[sp]); break; }
+            case MP_BLEND_I: { --sp; M[sp - 1] = sdf_blend(dsub(1.0, smooth_min_blend(-M[sp - 1].d, -M[sp].d, a0)), M[sp - 1], M[sp]); break; }
+            case MP_BLEND_D: { --sp; M[sp - 1] = sdf_blend(smooth_min_blend(-M[sp - 1].d, M[sp].d, a0), M[sp - 1], M[sp]); break; }
+            default: base = M[0].base; uv = M[0].uv; has_uv = M[0].has_uv; return;    // MP_END
+        }
+    }
+}
+
 // geometry.materialData in the primitive's local space -> local normal, UV, basecolor.
+template <bool HAS_SDF>
 JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index, int flags, float3 lp,
                             float3& n, float2& uv, bool& has_uv, float3& base) {
     has_uv = false; uv = make_float2(0.f, 0.f); base = f3(1.f, 1.f, 1.f); n = f3(0.f, 0.f, 1.f);
@@ -86,7 +135,7 @@ JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index
             }
             break;
         }
-        case G_SDF: {                                     // src/sdf.js:41-47: forward differences, reference arithmetic
+        case G_SDF: if (HAS_SDF) {                        // src/sdf.js:41-47: forward differences, reference arithmetic
             const SdfProgram& pr = sc.sdfs[geom_index];
             const SdfInstr* prog = sc.sdf_code + pr.first_instr;
             const double step = pr.normal_step_size;
@@ -99,6 +148,7 @@ JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index
             const double nn = sqrt(ddot4(nx, ny, nz, 0.0, nx, ny, nz, 0.0));
             n = (nn > 0.00001) ? f3((float)dmul(nx, 1.0 / nn), (float)dmul(ny, 1.0 / nn), (float)dmul(nz, 1.0 / nn)) : f3(nx, ny, nz);
             base = f3(pr.base[0], pr.base[1], pr.base[2]);
+            if (pr.mat_first >= 0) sdf_material(sc, pr.mat_first, lp, base, uv, has_uv);
             break;
         }
         default: break;

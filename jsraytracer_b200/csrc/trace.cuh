@@ -190,6 +190,10 @@ template <int MODE, bool COUNT, bool HAS_SDF>
 JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other) {
     constexpr bool ANY_HIT = (MODE == TM_SHADOW);
     constexpr int BATCH = 128;
+    // A warp runs three phases per iteration, each only when enough lanes need it, so that the
+    // rarely-needed code (ray hand-over, leaf tests) executes with many lanes instead of one or two:
+    constexpr int REFILL_T = 8;           // finish + refill when >= 8 lanes are idle (or nothing else is left)
+    constexpr int LEAF_T = 8;             // test postponed leaves when >= 8 lanes hold one (or one must be flushed)
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int n = min(*io.count, io.cap);
@@ -197,14 +201,15 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     bool exhausted = false;               // warp-uniform
 
     // per-lane ray state
-    int cur = -1;
+    int cur = -1;                         // ray index, -1: none
+    bool done = false;                    // walk finished, result not yet written
+    int pending = -1;                     // postponed leaf word
     float4 o4 = make_float4(0, 0, 0, 0);
-    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), lo = o, inv = d;
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), lo = o, inv = d, ld = d;
     bool parx = false, pary = false, parz = false;
     float minD = 0.f, maxD = CUDART_INF_F;
     Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
     int bi = 0, top_i = 0;
-    float3 ld = d;
     int node_i = 0, node_end = 0, first_prim = 0, tri_base = -1;
     const float4* nodes = nullptr;
     float local_best = CUDART_INF_F, local_lo = 0.f; int local_prim = -1;
@@ -224,13 +229,15 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
         const int octant = (tb.w == 8) ? ((ld.x < 0.f ? 1 : 0) | (ld.y < 0.f ? 2 : 0) | (ld.z < 0.f ? 4 : 0)) : 0;
         nodes = reinterpret_cast<const float4*>(sc.nodes + tb.x + octant * tb.y);
         node_i = 0; node_end = tb.y; first_prim = ta.z; tri_base = tb.z;
-        local_best = CUDART_INF_F; local_prim = -1; local_lo = 0.f;
+        local_best = CUDART_INF_F; local_prim = -1; local_lo = 0.f; pending = -1;
     };
 
     for (;;) {
-        // ---- refill idle lanes ---------------------------------------------------------
-        const unsigned idle_mask = __ballot_sync(FULL, cur < 0);
-        if (idle_mask) {
+        // ---- phase 1: write finished rays, hand out new ones ------------------------------
+        const unsigned idle_mask = __ballot_sync(FULL, cur < 0 || done);
+        const int n_idle = __popc(idle_mask);
+        if (n_idle >= REFILL_T || idle_mask == FULL) {
+            if (cur >= 0 && done) { finish_ray<MODE>(io, cur, best, o4); cur = -1; done = false; }
             if (pool_next >= pool_end && !exhausted) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(io.cursor, BATCH);
@@ -251,57 +258,74 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                     if (COUNT) work = primary ? work_primary : work_other;
                     best.t = h4.x; best.prim = __float_as_int(h4.y); best.top = __float_as_int(h4.z); best.t_lo = h4.w;
                     bi = 0;
-                    if (ANY_HIT && best.prim >= 0) cur = -1;        // already occluded by a top-level primitive
+                    if (ANY_HIT && best.prim >= 0) cur = -1;        // already occluded by a top-level primitive: nothing to do or write
                     else enter();
                 }
-                pool_next += min(avail, __popc(idle_mask));
-            } else if (exhausted && idle_mask == FULL) break;
+                pool_next += min(avail, n_idle);
+            } else if (exhausted && __all_sync(FULL, cur < 0)) break;
         }
-        if (cur < 0) continue;
+        const bool active = cur >= 0 && !done;
 
-        // ---- one node of BVHAggregateNode.intersect (src/aggregates.js:207-225) ----------
-        bool done_tree = node_i >= node_end;
-        if (!done_tree) {
-            const float4 n0 = __ldg(nodes + 2 * node_i), n1 = __ldg(nodes + 2 * node_i + 1);
-            const int skip = __float_as_int(n1.z), leaf = __float_as_int(n1.w);
-            if (COUNT) ++work->nodes;
-            const float bound = fminf(local_best, best.t);
-            // AABB.get_intersects (src/geometry.js:189-209); the per-axis early returns are equivalent to one
-            // final test because t_min only grows and t_max only shrinks
-            const float px = n0.x - lo.x, py = n0.y - lo.y, pz = n0.z - lo.z;
-            const float ax = (px + n0.w) * inv.x, bx = (px - n0.w) * inv.x;
-            const float ay = (py + n1.x) * inv.y, by = (py - n1.x) * inv.y;
-            const float az = (pz + n1.y) * inv.z, bz = (pz - n1.y) * inv.z;
-            float b0 = -CUDART_INF_F, b1 = CUDART_INF_F;
-            bool miss = false;
-            if (parx) miss = fabsf(px) > n0.w; else { b0 = fminf(ax, bx); b1 = fmaxf(ax, bx); }
-            if (pary) miss = miss || fabsf(py) > n1.x; else { b0 = fmaxf(b0, fminf(ay, by)); b1 = fminf(b1, fmaxf(ay, by)); }
-            if (parz) miss = miss || fabsf(pz) > n1.y; else { b0 = fmaxf(b0, fminf(az, bz)); b1 = fminf(b1, fmaxf(az, bz)); }
-            const bool hit_box = !miss && !(b0 > b1) && !(b1 < minD) && !(b0 > maxD) && b0 <= bound;    // + :209
-            if (hit_box) {
-                if (leaf != -1) {
-                    const int cnt = (int)((unsigned)leaf >> 24), rel = leaf & 0xffffff;
-                    for (int k = 0; k < cnt; ++k) {
-                        if (COUNT) ++work->leaf_prims;
-                        const int pi = first_prim + rel + k;
-                        float tl = 0.f, t;
-                        if (tri_base >= 0) t = triangle_intersect(sc.tris, tri_base + rel + k, lo, ld, minD, fminf(maxD, bound));
-                        else t = placed_prim_intersect<HAS_SDF>(sc, pi, lo, ld, minD, maxD, bound, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
-                        // :213 with the rank tie rule (see the header comment)
-                        if (t > minD && t < maxD && (t < local_best || (t == local_best && pi < local_prim))) { local_best = t; local_prim = pi; local_lo = tl; }
-                    }
-                    node_i = (ANY_HIT && local_prim >= 0) ? node_end : skip;
-                } else ++node_i;
-            } else node_i = skip;
-            done_tree = node_i >= node_end;
-        }
-        if (done_tree) {
-            if (local_best > minD && local_best < maxD && better_hit(local_best, top_i, best)) {
-                best.t = local_best; best.prim = local_prim; best.top = top_i; best.t_lo = local_lo;
+        // ---- phase 2: postponed leaf tests (src/aggregates.js:211-218) -------------------------
+        // A lane that reaches a leaf parks it and keeps walking; the leaf is tested when enough
+        // lanes hold one, when the lane reaches its next leaf, or when its walk ends.  Testing later
+        // only delays the `ret.distance` update that prunes the walk; the result is the same.
+        const bool walk_over = node_i >= node_end;
+        const unsigned pend_mask = __ballot_sync(FULL, active && pending != -1);
+        const bool must = active && pending != -1 && (walk_over || pending < -1);
+        if (pend_mask && (__popc(pend_mask) >= LEAF_T || __any_sync(FULL, must))) {
+            if (active && pending != -1) {
+                const int leaf = (pending < -1) ? -(pending + 2) : pending;      // a blocked lane stores -(leaf + 2)
+                const int cnt = (int)((unsigned)leaf >> 24), rel = leaf & 0xffffff;
+                const float bound = fminf(local_best, best.t);
+                for (int k = 0; k < cnt; ++k) {
+                    if (COUNT) ++work->leaf_prims;
+                    const int pi = first_prim + rel + k;
+                    float tl = 0.f, t;
+                    if (tri_base >= 0) t = triangle_intersect(sc.tris, tri_base + rel + k, lo, ld, minD, fminf(maxD, bound));
+                    else t = placed_prim_intersect<HAS_SDF>(sc, pi, lo, ld, minD, maxD, bound, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
+                    // :213 with the rank tie rule (see the header comment)
+                    if (t > minD && t < maxD && (t < local_best || (t == local_best && pi < local_prim))) { local_best = t; local_prim = pi; local_lo = tl; }
+                }
+                pending = -1;
+                if (ANY_HIT && local_prim >= 0) node_i = node_end;
             }
-            ++bi;
-            if (bi >= sc.n_bvh || (ANY_HIT && best.prim >= 0)) { finish_ray<MODE>(io, cur, best, o4); cur = -1; }
-            else enter();
+        }
+
+        if (active) {
+            if (node_i >= node_end && pending == -1) {
+                // ---- tree finished: merge into the running closest hit, next BVH or done -------
+                if (local_best > minD && local_best < maxD && better_hit(local_best, top_i, best)) {
+                    best.t = local_best; best.prim = local_prim; best.top = top_i; best.t_lo = local_lo;
+                }
+                ++bi;
+                if (bi >= sc.n_bvh || (ANY_HIT && best.prim >= 0)) done = true;
+                else enter();
+            } else if (node_i < node_end && pending >= -1) {
+                // ---- phase 3: one node of BVHAggregateNode.intersect (src/aggregates.js:207-225) --
+                const float4 n0 = __ldg(nodes + 2 * node_i), n1 = __ldg(nodes + 2 * node_i + 1);
+                const int skip = __float_as_int(n1.z), leaf = __float_as_int(n1.w);
+                if (COUNT) ++work->nodes;
+                const float bound = fminf(local_best, best.t);
+                // AABB.get_intersects (src/geometry.js:189-209); the per-axis early returns are equivalent to one
+                // final test because t_min only grows and t_max only shrinks
+                const float px = n0.x - lo.x, py = n0.y - lo.y, pz = n0.z - lo.z;
+                const float ax = (px + n0.w) * inv.x, bx = (px - n0.w) * inv.x;
+                const float ay = (py + n1.x) * inv.y, by = (py - n1.x) * inv.y;
+                const float az = (pz + n1.y) * inv.z, bz = (pz - n1.y) * inv.z;
+                float b0 = -CUDART_INF_F, b1 = CUDART_INF_F;
+                bool miss = false;
+                if (parx) miss = fabsf(px) > n0.w; else { b0 = fminf(ax, bx); b1 = fmaxf(ax, bx); }
+                if (pary) miss = miss || fabsf(py) > n1.x; else { b0 = fmaxf(b0, fminf(ay, by)); b1 = fminf(b1, fmaxf(ay, by)); }
+                if (parz) miss = miss || fabsf(pz) > n1.y; else { b0 = fmaxf(b0, fminf(az, bz)); b1 = fminf(b1, fmaxf(az, bz)); }
+                const bool hit_box = !miss && !(b0 > b1) && !(b1 < minD) && !(b0 > maxD) && b0 <= bound;    // + :209
+                if (hit_box) {
+                    if (leaf != -1) {
+                        if (pending == -1) { pending = leaf; node_i = skip; }
+                        else pending = -(pending + 2);      // one leaf already parked: block here until it is tested
+                    } else ++node_i;
+                } else node_i = skip;
+            }
         }
     }
 }

@@ -71,6 +71,9 @@ WHITTED = [
     ("refraction", dict(width=768, height=768), 1),
     ("SDF_Sierpinski", dict(width=160, height=160), 1),
     ("SDF_Menger", dict(width=160, height=160), 1),
+    ("SDF_BoxBall", dict(width=160, height=160), 1),            # per-leaf basecolor through UnionSDF.getMaterialData
+    ("SDF_Combinations", dict(width=192, height=192), 1),       # all six combinators incl. the smooth blends
+    ("SDF_Simple", dict(width=128, height=128), 1),
 ]
 
 
