@@ -33,6 +33,18 @@ JSRT_DEV float js_sign(float x) { return (x > 0.f) ? 1.f : (x < 0.f ? -1.f : x);
 JSRT_DEV float js_min(float a, float b) { return (a != a || b != b) ? CUDART_NAN_F : fminf(a, b); }
 JSRT_DEV float js_max(float a, float b) { return (a != a || b != b) ? CUDART_NAN_F : fmaxf(a, b); }
 
+// Un-contracted f64 helpers: the compiler must not fuse a*b+c here (JS has no FMA).
+JSRT_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
+JSRT_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
+JSRT_DEV double dsub(double a, double b) { return __dsub_rn(a, b); }
+// Vec.dot for 3 / 4 components: products summed left to right (src/math.js:252-254)
+JSRT_DEV double ddot3(double ax, double ay, double az, double bx, double by, double bz) { return dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz)); }
+JSRT_DEV double ddot4(double ax, double ay, double az, double aw, double bx, double by, double bz, double bw) {
+    return dadd(dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz)), dmul(aw, bw));
+}
+JSRT_DEV double jsd_min(double a, double b) { return (a != a || b != b) ? CUDART_NAN : fmin(a, b); }
+JSRT_DEV double jsd_max(double a, double b) { return (a != a || b != b) ? CUDART_NAN : fmax(a, b); }
+
 struct XformReg { float4 r0, r1, r2; };
 JSRT_DEV XformReg load_xform(const Xform* __restrict__ xs, int i) {
     const float4* p = reinterpret_cast<const float4*>(xs + i);
@@ -90,15 +102,49 @@ JSRT_DEV bool aabb_intersects(float3 c, float3 h, float3 o, float3 d, float minD
 // SimplePlane.intersect src/geometry.js:246-248
 JSRT_DEV float plane_t(float3 o, float3 d) { return (d.z != 0.f) ? -o.z / d.z : -CUDART_INF_F; }
 
-// Sphere.staticIntersect src/geometry.js:429-442
+// Sphere.staticIntersect src/geometry.js:429-442.  The reference solves the quadratic in f64, where
+// its textbook root formula is harmless; in FP32 it is not, and the place it breaks is systematic: a ray
+// that starts on the sphere (every reflection / refraction / shadow ray leaving one) has c = |o|^2 - 1
+// equal to the rounding residue of its f32 origin (~3e-7), an FP32 dot product adds an error of the same
+// size, and at grazing angles the near root c / 2b then crosses the 1e-4 self-hit threshold more often than
+// in the reference (measured: silhouette pixels of tests/refraction systematically darker, 47 dB).
+// So: c is accumulated in f64 (three DFMAs — it is exact for f32 inputs up to the final rounding), and
+// the roots come from the cancellation-free form q = -(b + sign(b) sqrt(disc)), {q / a, c / q}, which
+// returns the same two numbers as (-b +- sqrt(disc)) / a would in exact arithmetic.
 JSRT_DEV float sphere_intersect(float3 o, float3 d, float minD) {
-    const float a = dot3(d, d), b = dot3(d, o), c = dot3(o, o) - 1.f;
-    float big = b * b - a * c;
-    if (big < 0.f || a == 0.f) return -CUDART_INF_F;
-    big = sqrtf(big);
-    const float t1 = (-b + big) / a, t2 = (-b - big) / a;
+    const float a = dot3(d, d), b = dot3(d, o);
+    const float c = (float)fma((double)o.x, (double)o.x, fma((double)o.y, (double)o.y, fma((double)o.z, (double)o.z, -1.0)));
+    const float disc = fmaf(b, b, -a * c);
+    if (disc < 0.f || a == 0.f) return -CUDART_INF_F;
+    const float big = sqrtf(disc);
+    const float q = -(b + copysignf(big, b));
+    const float ra = q / a, rb = (q != 0.f) ? c / q : 0.f;
+    // t1 = (-b + big) / a, t2 = (-b - big) / a
+    const float t1 = (b < 0.f) ? ra : rb, t2 = (b < 0.f) ? rb : ra;
     if (t1 >= minD && t2 >= minD) return js_min(t1, t2);
     return (t2 < minD) ? t1 : t2;
+}
+
+// The same quadratic solved like the reference does, in f64 (src/geometry.js:429-442).  Used once per *shaded*
+// sphere / cylinder hit to recover the reference's hit distance to f64 accuracy before the hit point is formed:
+// the point's distance from the surface (the `c` of the next ray's quadratic) is what decides self-hits at
+// grazing angles, and a point built from an f32 distance sits up to 1e-6 further off the surface.
+JSRT_DEV double sphere_intersect64(float3 o, float3 d, double md) {
+    const double a = ddot3(d.x, d.y, d.z, d.x, d.y, d.z), b = ddot3(d.x, d.y, d.z, o.x, o.y, o.z), c = dsub(ddot3(o.x, o.y, o.z, o.x, o.y, o.z), 1.0);
+    double big = dsub(dmul(b, b), dmul(a, c));
+    if (big < 0.0 || a == 0.0) return -CUDART_INF;
+    big = sqrt(big);
+    const double t1 = dsub(-b, -big) / a, t2 = dsub(-b, big) / a;      // (-b + big) / a, (-b - big) / a
+    if (t1 >= md && t2 >= md) return jsd_min(t1, t2);
+    return (t2 < md) ? t1 : t2;
+}
+
+// f64 distance -> (f32 value, f32 remainder): hit records carry t + t_lo so that shading recomputes the
+// reference's hit point (origin.plus(direction.times(t)) with an f64 t) instead of one rounded through f32
+JSRT_DEV float split_t(double t, float* t_lo) {
+    const float tf = (float)t;
+    if (t_lo) *t_lo = isfinite(t) ? (float)(t - (double)tf) : 0.f;
+    return tf;
 }
 
 // Triangle.intersect src/geometry.js:368-375 with the constructor constants of :341-353.
@@ -146,36 +192,38 @@ JSRT_DEV float3 triangle_bary(const Tri* __restrict__ tris, int idx, float3 P) {
 // (src/sdf.js:42-46); both turn a one-ulp difference into a visibly different pixel on
 // fractal SDFs, so FP32 evaluation cannot meet the parity bar here.  B200's FP64 pipe
 // runs at half the FP32 rate, which this path pays knowingly.
-// Un-contracted f64 helpers: the compiler must not fuse a*b+c here (JS has no FMA).
-JSRT_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
-JSRT_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
-JSRT_DEV double dsub(double a, double b) { return __dsub_rn(a, b); }
-// Vec.dot for 3 / 4 components: products summed left to right (src/math.js:252-254)
-JSRT_DEV double ddot3(double ax, double ay, double az, double bx, double by, double bz) { return dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz)); }
-JSRT_DEV double ddot4(double ax, double ay, double az, double aw, double bx, double by, double bz, double bw) {
-    return dadd(dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz)), dmul(aw, bw));
-}
 // Mat.times(Vec) with an f64 3x4 matrix: result[r] = b.dot(row r) stored f32 (src/math.js:392-397)
 JSRT_DEV float3 xf64_apply(const double* __restrict__ m, float3 p, double w) {
     return f3((float)ddot4(p.x, p.y, p.z, w, __ldg(m + 0), __ldg(m + 1), __ldg(m + 2), __ldg(m + 3)),
               (float)ddot4(p.x, p.y, p.z, w, __ldg(m + 4), __ldg(m + 5), __ldg(m + 6), __ldg(m + 7)),
               (float)ddot4(p.x, p.y, p.z, w, __ldg(m + 8), __ldg(m + 9), __ldg(m + 10), __ldg(m + 11)));
 }
-JSRT_DEV double jsd_min(double a, double b) { return (a != a || b != b) ? CUDART_NAN : fmin(a, b); }
-JSRT_DEV double jsd_max(double a, double b) { return (a != a || b != b) ? CUDART_NAN : fmax(a, b); }
 JSRT_DEV double sdf_smooth_min(double a, double b, double k) {   // src/sdf.js:128-131
     const double h = jsd_max(dsub(k, fabs(dsub(a, b))), 0.0) / k;
     return dsub(jsd_min(a, b), dmul(dmul(dmul(dmul(h, h), h), k), (1.0 / 6.0)));
 }
-// Number(x.toPrecision(8)) (Math.fmod, src/math.js:27): round to 8 significant decimal digits
+// Number(x.toPrecision(8)) (Math.fmod, src/math.js:27): round to 8 significant decimal digits.
+// N = round(|x| * 10^k) with k chosen so that N has 8 digits, result = N / 10^k (or N * 10^-k for
+// |x| >= 1e8); 10^|k| is exact in f64 for |k| <= 22 and the final division is correctly rounded, so this
+// equals the decimal round trip except when |x| * 10^k lands within an ulp of a half-way point.
+__device__ const double kPow10[32] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                      1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22, 1e23, 1e24, 1e25, 1e26, 1e27, 1e28, 1e29, 1e30, 1e31};
 JSRT_DEV double js_to_precision8(double x) {
     if (x == 0.0 || !isfinite(x)) return x;
     const double ax = fabs(x);
-    int e = (int)floor(log10(ax));
-    if (ax >= exp10((double)(e + 1))) ++e; else if (ax < exp10((double)e)) --e;
-    const int k = 7 - e;
-    // scale by a power of ten that is exact in f64 where possible
-    const double r = (k >= 0) ? rint(dmul(ax, exp10((double)k))) / exp10((double)k) : dmul(rint(ax / exp10((double)-k)), exp10((double)-k));
+    int e = (int)floor((double)(ilogb(ax)) * 0.30102999566398120);      // floor(log10(ax)) or one less
+    int k = 7 - e;
+    if (k > 30 || k < -30) {                                             // far outside the table: generic path
+        e = (int)floor(log10(ax));
+        if (ax >= exp10((double)(e + 1))) ++e; else if (ax < exp10((double)e)) --e;
+        k = 7 - e;
+        const double r = (k >= 0) ? rint(dmul(ax, exp10((double)k))) / exp10((double)k) : dmul(rint(ax / exp10((double)-k)), exp10((double)-k));
+        return copysign(r, x);
+    }
+    double y = (k >= 0) ? dmul(ax, kPow10[k]) : ax / kPow10[-k];
+    if (y >= 1e8) { --k; y = (k >= 0) ? dmul(ax, kPow10[k]) : ax / kPow10[-k]; }
+    const double nn = rint(y);
+    const double r = (k >= 0) ? nn / kPow10[k] : dmul(nn, kPow10[-k]);
     return copysign(r, x);
 }
 JSRT_DEV double js_fmod(double a, double b) { return js_to_precision8(dsub(a, dmul(floor(a / b), b))); }

@@ -35,7 +35,7 @@ struct RayQueue { float4* o; float4* d; float4* w; };
 struct ShadowQueue { float4* o; float4* d; float4* c; };
 
 // counters[0], [1]: ray queue counts (ping-pong); [2]: shadow queue count
-struct Counters { int ray[2]; int shadow; int pad; int cursor_extend; int cursor_shadow; int pad2[2]; unsigned long long stats[24]; };
+struct Counters { int ray[2]; int shadow; int pad; int cursor_extend; int cursor_shadow; int cursor_extend_sdf; int cursor_shadow_sdf; unsigned long long stats[24]; };
 enum { ST_PRIMARY = 0, ST_SECONDARY = 1, ST_SHADOW = 2, ST_SHADED = 3, ST_SAMPLES = 4,
        ST_NODES = 8, ST_LEAF_PRIMS = 11, ST_TOP_PRIMS = 14, ST_SDF_EVALS = 17 };   // + ray class (0 primary, 1 secondary, 2 shadow)
 
@@ -122,6 +122,12 @@ __global__ void __launch_bounds__(kBlock) prims_kernel(const __grid_constant__ D
     prims_wave<MODE, COUNT, HAS_SDF>(sc, io, &wp, &ws);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(kBlock) sdf_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
+    Work wp, ws;
+    sdf_wave<MODE, COUNT>(sc, io, &wp, &ws);
+    if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
+}
 template <int MODE, bool COUNT, bool HAS_SDF>
 __global__ void __launch_bounds__(kBlock, 4) bvh_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
     Work wp, ws;
@@ -186,20 +192,31 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : 3) shade_kernel(const __
                 // inv_transform = prim.inv * ancestorInvTransform (src/world.js:126)
                 XformReg inv = load_xform(sc.xforms, pa.w);
                 const int4 ta = __ldg(reinterpret_cast<const int4*>(sc.tops + top));
-                if (ta.x != T_PRIM) {
+                if (ta.x == T_BVH || ta.x == T_LIST) {
                     const XformReg anc = load_xform(sc.xforms, ta.y);
                     inv = (flags & PF_IDENTITY_XFORM) ? anc : xf_compose(inv, anc);
                 }
                 float3 lp;
-                if (HAS_SDF && pa.x == G_SDF && ta.x == T_PRIM) {
+                double td = (double)t + (double)h4.w;
+                if (HAS_SDF && pa.x == G_SDF && ta.x == T_SDF) {
                     // the SDF normal is a forward difference: recompute the reference's local hit point exactly
                     // (f64 matrix, f64 distance carried as t + t_lo)
                     const double* m64 = sc.xforms64[pa.w].m;
                     lp = ray_point_f64(xf64_apply(m64, o, 1.0), xf64_apply(m64, d, 0.0), (double)t + (double)h4.w);
-                } else lp = ray_point(xf_point(inv, o), xf_dir(inv, d), t);
+                } else {
+                    const float3 lo = xf_point(inv, o), ld = xf_dir(inv, d);
+                    if (pa.x == G_SPHERE || pa.x == G_CYLINDER) {
+                        // re-solve the accepted hit in f64 (see sphere_intersect64); keep the f32 value if the
+                        // two disagree about which root it was
+                        const double md = (node == 1u) ? 0.0 : 0.0001;
+                        const double t64 = (pa.x == G_SPHERE) ? sphere_intersect64(lo, ld, md) : sphere_intersect64(f3(lo.x, lo.y, 0.f), f3(ld.x, ld.y, 0.f), md);
+                        if (fabs(t64 - (double)t) <= 1e-4 * fabs((double)t)) td = t64;
+                    }
+                    lp = ray_point_f64(lo, ld, td);
+                }
                 float3 ln; material_data<HAS_SDF>(sc, pa.x, pa.y, flags, lp, ln, s.uv, s.has_uv, s.basecolor);
                 s.normal = normalized3(xf_normal(inv, ln));
-                s.position = ray_point(o, d, t);
+                s.position = ray_point_f64(o, d, td);
                 mat = sc.materials + pa.z;
                 node_key = rng_node_key(rng_sample_key(seed, pixel, (uint32_t)pass), node);
                 if (mat->kind == M_SOLID) {
@@ -280,11 +297,11 @@ __global__ void level_end_kernel(Counters* c, int cur, int level, int next_cap, 
     c->stats[ST_SHADOW] += (unsigned long long)min(c->shadow, shadow_cap);
     c->ray[cur] = 0;
     c->shadow = 0;
-    c->cursor_extend = 0; c->cursor_shadow = 0;
+    c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0;
     if (c->ray[cur ^ 1] > next_cap) c->ray[cur ^ 1] = next_cap;
 }
 __global__ void set_count_kernel(Counters* c, int which, int n, int count_samples) {
-    c->ray[which] = n; c->ray[which ^ 1] = 0; c->shadow = 0; c->cursor_extend = 0; c->cursor_shadow = 0;
+    c->ray[which] = n; c->ray[which ^ 1] = 0; c->shadow = 0; c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0;
     if (count_samples) c->stats[ST_SAMPLES] += (unsigned long long)n;
 }
 
@@ -342,7 +359,7 @@ struct Renderer::Impl {
     int ray_cap = 0, shadow_cap = 0, batch = 0;
     int passes = 0;
     size_t scene_bytes = 0, queue_bytes = 0;
-    int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0, grid_bvh = 0;
+    int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0, grid_bvh = 0, grid_sdf = 0;
     unsigned long long launches = 0;
     bool profiling = false, has_sdf = false;
     double ms[4] = {0, 0, 0, 0};
@@ -362,11 +379,14 @@ struct Renderer::Impl {
         ds.tris = up(hs.tris); ds.tri_shade = up(hs.tri_shade); ds.boxes = up(hs.boxes); ds.materials = up(hs.materials);
         ds.lights = up(hs.lights); ds.sdfs = up(hs.sdfs); ds.sdf_code = up(hs.sdf_code);
         ds.bvh_tops = up(bvh_tops_host); ds.n_bvh = (int)bvh_tops_host.size();
+        sdf_tops_host.clear();
+        for (size_t i = 0; i < hs.tops.size(); ++i) if (hs.tops[i].kind == T_SDF) sdf_tops_host.push_back((int)i);
+        ds.sdf_tops = up(sdf_tops_host); ds.n_sdf_tops = (int)sdf_tops_host.size();
         ds.n_top = (int)hs.tops.size(); ds.n_lights = (int)hs.lights.size(); ds.light_samples = hs.light_samples; ds.max_depth = hs.max_depth;
         for (int i = 0; i < 3; ++i) ds.bg[i] = hs.bg[i];
     }
     std::vector<void*> scene_allocs;
-    std::vector<int> bvh_tops_host;
+    std::vector<int> bvh_tops_host, sdf_tops_host;
     size_t up_index = 0;
     template <class T> T* up(const std::vector<T>& vec) {
         T* p;
@@ -421,6 +441,7 @@ struct Renderer::Impl {
         grid_shade = has_sdf ? grid_for((const void*)shade_kernel<true>) : grid_for((const void*)shade_kernel<false>);
         grid_shadow = has_sdf ? grid_for((const void*)prims_kernel<TM_SHADOW, false, true>) : grid_for((const void*)prims_kernel<TM_SHADOW, false, false>);
         grid_gen = grid_for((const void*)generate_kernel);
+        grid_sdf = grid_for((const void*)sdf_kernel<TM_EXTEND, false>);
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
         CK(cudaStreamSynchronize(stream));
     }
@@ -465,15 +486,23 @@ struct Renderer::Impl {
 
     template <int MODE> void launchTrace(const TraceIO& io0, bool count_work, int grid_prims) {
         TraceIO io = io0;
-        const bool has_bvh = ds.n_bvh > 0;
-        io.final_pass = has_bvh ? 0 : 1;
+        const bool has_bvh = ds.n_bvh > 0, has_sdf_tops = ds.n_sdf_tops > 0;
+        io.final_pass = (has_bvh || has_sdf_tops) ? 0 : 1;
         #define JSRT_LAUNCH(K, G, C, S) K<MODE, C, S><<<G, kBlock, 0, stream>>>(ds, io)
         if (count_work) { if (has_sdf) JSRT_LAUNCH(prims_kernel, grid_prims, true, true); else JSRT_LAUNCH(prims_kernel, grid_prims, true, false); }
         else { if (has_sdf) JSRT_LAUNCH(prims_kernel, grid_prims, false, true); else JSRT_LAUNCH(prims_kernel, grid_prims, false, false); }
         if (has_bvh) {
             ++launches;
+            io.final_pass = has_sdf_tops ? 0 : 1;
             if (count_work) { if (has_sdf) JSRT_LAUNCH(bvh_kernel, grid_bvh, true, true); else JSRT_LAUNCH(bvh_kernel, grid_bvh, true, false); }
             else { if (has_sdf) JSRT_LAUNCH(bvh_kernel, grid_bvh, false, true); else JSRT_LAUNCH(bvh_kernel, grid_bvh, false, false); }
+        }
+        if (has_sdf_tops) {
+            ++launches;
+            io.final_pass = 1;
+            io.cursor = io0.cursor + 2;          // cursor_extend_sdf / cursor_shadow_sdf
+            if (count_work) sdf_kernel<MODE, true><<<grid_sdf, kBlock, 0, stream>>>(ds, io);
+            else sdf_kernel<MODE, false><<<grid_sdf, kBlock, 0, stream>>>(ds, io);
         }
         #undef JSRT_LAUNCH
     }

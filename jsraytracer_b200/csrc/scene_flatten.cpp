@@ -321,6 +321,7 @@ struct Flattener {
             if (ty == "Primitive") {
                 top.kind = T_PRIM; top.first_prim = (int)out.prims.size(); top.prim_count = 1;
                 placePrim(o, nullptr);
+                if (out.prims.back().geom_kind == G_SDF) top.kind = T_SDF;
             } else if (ty == "BVHAggregate") {
                 top.kind = T_BVH;
                 double inv[16]; doc.mat4(doc.field(o, "inv_transform"), inv);

@@ -11,7 +11,7 @@ enum GeomKind : int { G_PLANE = 0, G_SQUARE = 1, G_CIRCLE = 2, G_BOX = 3, G_SPHE
 // material kinds (reference src/materials.js)
 enum MatKind : int { M_PHONG = 0, M_FRESNEL = 1, M_PATH = 2, M_SOLID = 3, M_TRANSPARENT = 4 };
 // top-level object kinds (reference src/world.js Primitive, src/aggregates.js Aggregate / BVHAggregate)
-enum TopKind : int { T_PRIM = 0, T_BVH = 1, T_LIST = 2 };
+enum TopKind : int { T_PRIM = 0, T_BVH = 1, T_LIST = 2, T_SDF = 3 };   // T_SDF: a top-level Primitive whose geometry is an SDFGeometry (marched by its own kernel)
 enum LightKind : int { L_POINT = 0, L_AREA = 1 };
 
 enum PrimFlags : int { PF_CASTS_SHADOW = 1, PF_IDENTITY_XFORM = 2, PF_HAS_VNORMALS = 4, PF_HAS_UVS = 8 };

@@ -21,6 +21,8 @@ struct DeviceScene {
     const SdfProgram* sdfs;
     const SdfInstr* sdf_code;
     const int* bvh_tops;       // indices of the T_BVH entries of `tops`
+    const int* sdf_tops;       // indices of the T_SDF entries of `tops`
+    int n_sdf_tops, pad0, pad1, pad2;
     int n_top, n_lights, light_samples, max_depth;
     float bg[3];
     int n_bvh;
@@ -35,7 +37,7 @@ struct Work { unsigned nodes = 0, leaf_prims = 0, top_prims = 0; unsigned long l
 // geometry.intersect(localRay, minDistance, maxDistance) for one placed primitive.
 // `best` is the caller's current closest distance (only used to skip work that the
 // caller's acceptance test would reject anyway).
-JSRT_DEV float prim_intersect(const DeviceScene& sc, const int4 pa, float3 o, float3 d, float minD, float maxD, float best, unsigned long long* sdf_evals = nullptr) {
+JSRT_DEV float prim_intersect(const DeviceScene& sc, const int4 pa, float3 o, float3 d, float minD, float maxD, float best, float* t_lo = nullptr) {
     switch (pa.x) {   // geom_kind
         case G_TRIANGLE: return triangle_intersect(sc.tris, pa.y, o, d, minD, fminf(maxD, best));
         case G_PLANE: return plane_t(o, d);
@@ -82,17 +84,14 @@ JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, floa
         // ray.getTransformed(inv_transform) with the f64 matrix (src/math.js:392-397), then SDFGeometry.intersect
         const double* m = sc.xforms64[pa.w].m;
         const float3 lo = xf64_apply(m, o, 1.0), ld = xf64_apply(m, d, 0.0);
-        const double t = sdf_intersect(sc.sdfs[pa.y], sc.sdf_code, sc.xforms64, lo, ld, (double)minD, (double)maxD, sdf_evals);
-        const float tf = (float)t;
-        if (t_lo) *t_lo = isfinite(t) ? (float)(t - (double)tf) : 0.f;
-        return tf;
+        return split_t(sdf_intersect(sc.sdfs[pa.y], sc.sdf_code, sc.xforms64, lo, ld, (double)minD, (double)maxD, sdf_evals), t_lo);
     }
     if (!(flags & PF_IDENTITY_XFORM)) {                                    // ray.getTransformed(inv_transform), src/world.js:120
         const XformReg m = load_xform(sc.xforms, pa.w);
         const float3 lo = xf_point(m, o), ld = xf_dir(m, d);
-        return prim_intersect(sc, pa, lo, ld, minD, maxD, best, sdf_evals);
+        return prim_intersect(sc, pa, lo, ld, minD, maxD, best, t_lo);
     }
-    return prim_intersect(sc, pa, o, d, minD, maxD, best, sdf_evals);
+    return prim_intersect(sc, pa, o, d, minD, maxD, best, t_lo);
 }
 
 // ---------------------------------------------------------------------------------
@@ -127,7 +126,7 @@ struct TraceIO {
     int cap;
     int* cursor;
     unsigned long long* stats;
-    int final_pass;                     // prims_wave: 1 if no BVH pass follows
+    int final_pass;                     // 1 if no further tracing kernel follows for this wave (the last one writes results)
 };
 
 JSRT_DEV void accum_add3(float4* accum, uint32_t pixel, float3 c) {
@@ -170,7 +169,7 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_pr
         Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
         for (int ti = 0; ti < sc.n_top; ++ti) {
             const int4 ta = __ldg(reinterpret_cast<const int4*>(sc.tops + ti));          // kind, xform, first_prim, prim_count
-            if (ta.x == T_BVH) continue;
+            if (ta.x == T_BVH || ta.x == T_SDF) continue;
             float3 lo = o, ld = d;
             if (ta.x == T_LIST) { const XformReg m = load_xform(sc.xforms, ta.y); lo = xf_point(m, o); ld = xf_dir(m, d); }   // src/aggregates.js:15
             for (int k = 0; k < ta.w; ++k) {
@@ -237,7 +236,11 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
         const unsigned idle_mask = __ballot_sync(FULL, cur < 0 || done);
         const int n_idle = __popc(idle_mask);
         if (n_idle >= REFILL_T || idle_mask == FULL) {
-            if (cur >= 0 && done) { finish_ray<MODE>(io, cur, best, o4); cur = -1; done = false; }
+            if (cur >= 0 && done) {
+                if (io.final_pass) finish_ray<MODE>(io, cur, best, o4);
+                else io.hits[cur] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
+                cur = -1; done = false;
+            }
             if (pool_next >= pool_end && !exhausted) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(io.cursor, BATCH);
@@ -325,6 +328,117 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                         else pending = -(pending + 2);      // one leaf already parked: block here until it is tested
                     } else ++node_i;
                 } else node_i = skip;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// SDFGeometry.intersect (src/sdf.js:12-40) for the top-level SDF primitives of a whole
+// queue: persistent threads, one ray per lane, one sphere-tracing step (one
+// root_sdf.distance evaluation) per iteration, lanes refilled in batches.  Step counts
+// range from 0 (ray misses the SDF's box) to max_samples, and the bytecode itself is
+// branch-free, so with per-lane refill every lane of a warp executes the interpreter
+// in lockstep.  Arithmetic: the reference's (device_math.cuh).
+template <int MODE, bool COUNT>
+JSRT_DEV void sdf_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other) {
+    constexpr bool ANY_HIT = (MODE == TM_SHADOW);
+    constexpr int BATCH = 64, REFILL_T = 8;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int n = min(*io.count, io.cap);
+    int pool_next = 0, pool_end = 0; bool exhausted = false;       // warp-uniform
+
+    int cur = -1; bool done = false;
+    float4 o4 = make_float4(0, 0, 0, 0);
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), lo = o, ld = d;
+    float minD = 0.f, maxD = CUDART_INF_F;
+    Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
+    int si = 0, top_i = 0, prim_i = 0, step = 0, max_steps = 0;
+    bool marching = false;
+    double t = 0, t_lo = 0, t_hi = 0, rd_norm = 1, eps = 0, max_trace = 0;
+    const SdfInstr* prog = nullptr;
+    Work* work = work_other;
+
+    // set up the march through SDF primitive number `si` (Primitive.intersect + the head of SDFGeometry.intersect)
+    auto enter = [&]() {
+        marching = false;
+        while (si < sc.n_sdf_tops && !marching) {
+            top_i = __ldg(sc.sdf_tops + si);
+            prim_i = __ldg(&sc.tops[top_i].first_prim);
+            const int4* pp = reinterpret_cast<const int4*>(sc.prims + prim_i);
+            const int4 pa = __ldg(pp); const int flags = __ldg(reinterpret_cast<const int*>(pp + 1));
+            if (!(ANY_HIT && !(flags & PF_CASTS_SHADOW))) {                   // src/world.js:117-118
+                const double* m = sc.xforms64[pa.w].m;
+                lo = xf64_apply(m, o, 1.0); ld = xf64_apply(m, d, 0.0);        // ray.getTransformed(inv_transform)
+                const SdfProgram& pr = sc.sdfs[pa.y];
+                double b0, b1;
+                // a hit beyond the running closest hit cannot win, so the march may stop there
+                const double cap = fmin((double)maxD, (double)best.t);
+                if (aabb_intersects_f64(f3(pr.cx, pr.cy, pr.cz), f3(pr.hx, pr.hy, pr.hz), lo, ld, (double)minD, (double)maxD, b0, b1)) {
+                    t_lo = jsd_max((double)minD, b0); t_hi = jsd_min((double)maxD, b1);
+                    if (t_lo <= cap) {
+                        t = t_lo; step = 0; max_steps = pr.max_samples; eps = pr.distance_epsilon; max_trace = pr.max_trace_distance;
+                        if (cap < t_hi) t_hi = cap;
+                        rd_norm = sqrt(ddot4(ld.x, ld.y, ld.z, 0.0, ld.x, ld.y, ld.z, 0.0));
+                        prog = sc.sdf_code + pr.first_instr;
+                        marching = max_steps > 0;
+                    }
+                }
+            }
+            if (!marching) ++si;
+        }
+        if (!marching) done = true;
+    };
+
+    for (;;) {
+        const unsigned idle_mask = __ballot_sync(FULL, cur < 0 || done);
+        const int n_idle = __popc(idle_mask);
+        if (n_idle >= REFILL_T || idle_mask == FULL) {
+            if (cur >= 0 && done) { finish_ray<MODE>(io, cur, best, o4); cur = -1; done = false; }
+            if (pool_next >= pool_end && !exhausted) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(io.cursor, BATCH);
+                base = __shfl_sync(FULL, base, 0);
+                pool_next = base; pool_end = min(base + BATCH, n);
+                if (base >= n) { exhausted = true; pool_next = pool_end = 0; }
+            }
+            const int avail = pool_end - pool_next;
+            if (avail > 0) {
+                const int rank = __popc(idle_mask & ((1u << lane) - 1u));
+                if (cur < 0 && rank < avail) {
+                    cur = pool_next + rank;
+                    o4 = io.o[cur];
+                    const float4 d4 = io.d[cur], h4 = io.hits[cur];
+                    o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
+                    bool primary;
+                    ray_window<MODE>(d4, minD, maxD, primary);
+                    if (COUNT) work = primary ? work_primary : work_other;
+                    best.t = h4.x; best.prim = __float_as_int(h4.y); best.top = __float_as_int(h4.z); best.t_lo = h4.w;
+                    si = 0; done = false;
+                    if (ANY_HIT && best.prim >= 0) cur = -1;
+                    else enter();
+                }
+                pool_next += min(avail, n_idle);
+            } else if (exhausted && __all_sync(FULL, cur < 0)) break;
+        }
+        if (cur >= 0 && !done) {
+            // ---- one iteration of the sphere-tracing loop (src/sdf.js:22-38) -------------------
+            const double dist = sdf_eval(prog, sc.xforms64, ray_point_f64(lo, ld, t));
+            if (COUNT) ++work->sdf_evals;
+            bool over = false;
+            if (!isfinite(dist)) over = true;
+            else if (dist <= eps) {
+                const float tf = (float)t;
+                if (tf > minD && tf < maxD && better_hit(tf, top_i, best)) { best.t = tf; best.prim = prim_i; best.top = top_i; best.t_lo = (float)(t - (double)tf); }
+                over = true;
+            } else {
+                t = dadd(t, dist / rd_norm);
+                if (t < t_lo || t > t_hi || dmul(dsub(t, t_lo), rd_norm) > max_trace || ++step >= max_steps) over = true;
+            }
+            if (over) {
+                ++si;
+                if (ANY_HIT && best.prim >= 0) done = true; else enter();
             }
         }
     }

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjsrt.so")
+LIB_PATH = os.environ.get("JSRT_LIB") or os.path.join(_HERE, "libjsrt.so")   # JSRT_LIB: A/B-test another build of the same ABI
 
 FORMAT_JSON = 0
 FORMAT_MSGPACK = 1
