@@ -258,8 +258,16 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    roofline = {"bound": "hbm", "kernel": dominant + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+    kernel_name = {"extend": "bvh_kernel<extend> (+ prims_kernel<extend>)", "shadow": "bvh_kernel<shadow> (+ prims_kernel<shadow>)"}[dominant]
+    traffic = None
+    try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.scene == tj.get("scene") and args.width == tj.get("width"):
+            traffic = tj["traffic_bytes_per_launch"].get(dominant)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_t / max(1, kern_n[dominant]), "avg_launch_ms": avg_ms,
                 "kernel_ms": kern_ms, "kernel_launches": kern_n,
                 "note": "scene (%.1f MB) is L2-resident: the kernel is latency/issue bound, not HBM bound; see DESIGN.md" % (info["scene_bytes"] / 1e6)}
