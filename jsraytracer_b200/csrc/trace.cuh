@@ -114,6 +114,16 @@ JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, floa
 // (top index, primitive index) — which is what lets the analytic primitives run before
 // the BVHs and lets the walk pick, per ray-direction octant, one of eight stackless
 // (hit/miss-link) layouts of the same tree that visit the nearer child first.
+// tuning constants of bvh_wave (measured on bunny_path / dragon 1080p, profiles/r1_ncu_summary.md)
+#ifndef JSRT_REFILL_T
+#define JSRT_REFILL_T 8
+#endif
+#ifndef JSRT_LEAF_T
+#define JSRT_LEAF_T 16
+#endif
+#ifndef JSRT_NODE_STEPS
+#define JSRT_NODE_STEPS 8
+#endif
 enum TraceMode { TM_EXTEND = 0, TM_SHADOW = 1 };
 
 struct TraceIO {
@@ -191,8 +201,9 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     constexpr int BATCH = 128;
     // A warp runs three phases per iteration, each only when enough lanes need it, so that the
     // rarely-needed code (ray hand-over, leaf tests) executes with many lanes instead of one or two:
-    constexpr int REFILL_T = 8;           // finish + refill when >= 8 lanes are idle (or nothing else is left)
-    constexpr int LEAF_T = 8;             // test postponed leaves when >= 8 lanes hold one (or one must be flushed)
+    constexpr int REFILL_T = JSRT_REFILL_T;     // finish + refill when this many lanes are idle (or nothing else is left)
+    constexpr int LEAF_T = JSRT_LEAF_T;         // test postponed leaves when this many lanes hold one (or one must be flushed)
+    constexpr int NODE_STEPS = JSRT_NODE_STEPS; // nodes walked per iteration between the warp votes
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int n = min(*io.count, io.cap);
@@ -304,30 +315,34 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 ++bi;
                 if (bi >= sc.n_bvh || (ANY_HIT && best.prim >= 0)) done = true;
                 else enter();
-            } else if (node_i < node_end && pending >= -1) {
-                // ---- phase 3: one node of BVHAggregateNode.intersect (src/aggregates.js:207-225) --
-                const float4 n0 = __ldg(nodes + 2 * node_i), n1 = __ldg(nodes + 2 * node_i + 1);
-                const int skip = __float_as_int(n1.z), leaf = __float_as_int(n1.w);
-                if (COUNT) ++work->nodes;
-                const float bound = fminf(local_best, best.t);
-                // AABB.get_intersects (src/geometry.js:189-209); the per-axis early returns are equivalent to one
-                // final test because t_min only grows and t_max only shrinks
-                const float px = n0.x - lo.x, py = n0.y - lo.y, pz = n0.z - lo.z;
-                const float ax = (px + n0.w) * inv.x, bx = (px - n0.w) * inv.x;
-                const float ay = (py + n1.x) * inv.y, by = (py - n1.x) * inv.y;
-                const float az = (pz + n1.y) * inv.z, bz = (pz - n1.y) * inv.z;
-                float b0 = -CUDART_INF_F, b1 = CUDART_INF_F;
-                bool miss = false;
-                if (parx) miss = fabsf(px) > n0.w; else { b0 = fminf(ax, bx); b1 = fmaxf(ax, bx); }
-                if (pary) miss = miss || fabsf(py) > n1.x; else { b0 = fmaxf(b0, fminf(ay, by)); b1 = fminf(b1, fmaxf(ay, by)); }
-                if (parz) miss = miss || fabsf(pz) > n1.y; else { b0 = fmaxf(b0, fminf(az, bz)); b1 = fminf(b1, fmaxf(az, bz)); }
-                const bool hit_box = !miss && !(b0 > b1) && !(b1 < minD) && !(b0 > maxD) && b0 <= bound;    // + :209
-                if (hit_box) {
-                    if (leaf != -1) {
-                        if (pending == -1) { pending = leaf; node_i = skip; }
-                        else pending = -(pending + 2);      // one leaf already parked: block here until it is tested
-                    } else ++node_i;
-                } else node_i = skip;
+            } else {
+                // ---- phase 3: up to NODE_STEPS nodes of BVHAggregateNode.intersect (src/aggregates.js:207-225)
+                // per iteration, so the warp votes of phases 1-2 are paid once per few nodes
+                #pragma unroll 1
+                for (int rep = 0; rep < NODE_STEPS && node_i < node_end && pending >= -1; ++rep) {
+                    const float4 n0 = __ldg(nodes + 2 * node_i), n1 = __ldg(nodes + 2 * node_i + 1);
+                    const int skip = __float_as_int(n1.z), leaf = __float_as_int(n1.w);
+                    if (COUNT) ++work->nodes;
+                    const float bound = fminf(local_best, best.t);
+                    // AABB.get_intersects (src/geometry.js:189-209); the per-axis early returns are equivalent to one
+                    // final test because t_min only grows and t_max only shrinks
+                    const float px = n0.x - lo.x, py = n0.y - lo.y, pz = n0.z - lo.z;
+                    const float ax = (px + n0.w) * inv.x, bx = (px - n0.w) * inv.x;
+                    const float ay = (py + n1.x) * inv.y, by = (py - n1.x) * inv.y;
+                    const float az = (pz + n1.y) * inv.z, bz = (pz - n1.y) * inv.z;
+                    float b0 = -CUDART_INF_F, b1 = CUDART_INF_F;
+                    bool miss = false;
+                    if (parx) miss = fabsf(px) > n0.w; else { b0 = fminf(ax, bx); b1 = fmaxf(ax, bx); }
+                    if (pary) miss = miss || fabsf(py) > n1.x; else { b0 = fmaxf(b0, fminf(ay, by)); b1 = fminf(b1, fmaxf(ay, by)); }
+                    if (parz) miss = miss || fabsf(pz) > n1.y; else { b0 = fmaxf(b0, fminf(az, bz)); b1 = fminf(b1, fmaxf(az, bz)); }
+                    const bool hit_box = !miss && !(b0 > b1) && !(b1 < minD) && !(b0 > maxD) && b0 <= bound;    // + :209
+                    if (hit_box) {
+                        if (leaf != -1) {
+                            if (pending == -1) { pending = leaf; node_i = skip; }
+                            else pending = -(pending + 2);      // one leaf already parked: block here until it is tested
+                        } else ++node_i;
+                    } else node_i = skip;
+                }
             }
         }
     }

@@ -46,18 +46,20 @@ class ParsedObj:
     face_material: np.ndarray        # (F,) int32 index into material_names; -1 = default
     material_names: list = field(default_factory=list)
     mtllibs: list = field(default_factory=list)
+    mtl_texts: list = field(default_factory=list)   # contents of the mtllibs (fixtures only; parse_obj_text leaves it empty)
 
     def save(self, path):
         np.savez_compressed(path, positions=self.positions, texcoords=self.texcoords, normals=self.normals,
                             faces=self.faces, face_material=self.face_material,
                             material_names=np.array(self.material_names, dtype="U"),
-                            mtllibs=np.array(self.mtllibs, dtype="U"))
+                            mtllibs=np.array(self.mtllibs, dtype="U"), mtl_texts=np.array(self.mtl_texts, dtype="U"))
 
     @staticmethod
     def load(path):
         z = np.load(path, allow_pickle=False)
         return ParsedObj(z["positions"], z["texcoords"], z["normals"], z["faces"], z["face_material"],
-                         [str(s) for s in z["material_names"]], [str(s) for s in z["mtllibs"]])
+                         [str(s) for s in z["material_names"]], [str(s) for s in z["mtllibs"]],
+                         [str(s) for s in z["mtl_texts"]] if "mtl_texts" in z.files else [])
 
 
 def parse_obj_text(data: str) -> ParsedObj:

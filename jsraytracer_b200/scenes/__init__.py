@@ -26,7 +26,7 @@ from ..materials import (CheckerboardMaterialColor, PhongMaterial, FresnelPhongM
 from ..world import World, Primitive, Aggregate, BVHAggregate
 from ..cameras import PerspectiveCamera, DepthOfFieldPerspectiveCamera
 from ..renderers import SimpleRenderer, IncrementalMultisamplingRenderer
-from ..objloader import ParsedObj, triangles_from_parsed
+from ..objloader import ParsedObj, triangles_from_parsed, parse_mtl_text
 
 PI = math.pi
 INF = math.inf
@@ -36,7 +36,10 @@ DATA_DIR = os.path.join(os.path.dirname(__file__), "data")
 def load_mesh(name, defaultMaterial=None, transform=None, minArea=0.00001):
     """`loadObjFile("../assets/<name>.obj", ...)` (src/objloader.js:240-247)."""
     parsed = ParsedObj.load(os.path.join(DATA_DIR, name + ".npz"))
-    return triangles_from_parsed(parsed, defaultMaterial, transform, minArea)
+    materials = {}
+    for text in parsed.mtl_texts:                      # loadMtlFiles, src/objloader.js:124-142
+        materials.update(parse_mtl_text(text))
+    return triangles_from_parsed(parsed, defaultMaterial, transform, minArea, materials)
 
 
 def _boxball_camera_transform():
@@ -271,6 +274,32 @@ def AHollowTetrahedron(aspect=1, width=600, height=600, spp=1, depth=4, renderer
     return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
 
 
+# tests/starwars/test.mjs (four BVH instances, three of them sharing one kdtree; DOF; point + area lights;
+# MTL materials).  Stands in for the missing Toledo scene of BASELINE configs[4].
+def starwars(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    X, Y, Z = Vec.of(1, 0, 0), Vec.of(0, 1, 0), Vec.of(0, 0, 1)
+    camera = DepthOfFieldPerspectiveCamera(PI / 4, aspect, Mat4.translation([-0.73, 2.05, 7.5]).times(Mat4.rotation(-0.2, X))
+                                           .times(Mat4.rotation(-0.3, Y)), 5.35, 0.04)
+    lights = [SimplePointLight(Vec.of(-10, 10, -12, 1), Vec.of(1, 1, 1), 5000)]
+    objs = [Primitive(Plane(), PhongMaterial(Vec.of(0.3, 0.3, 0.3), 0.3, 0.4, 0.6, 100, 0.4),
+                      Mat4.translation([0, 1, 0]).times(Mat4.rotation(PI / 2, X)))]
+    bolttransforms = [Mat4.translation(p).times(Mat4.rotation(0.4, Y)).times(Mat4.scale([0.01, 0.01, 1.5]))
+                      for p in ([-0.15, 1.86, -2.73], [0.1, 2.15, 1.5], [2, 1.7, 2.6])]
+    boltlighttransform = Mat4.scale(2).times(Mat4.rotation(PI / 2, X))
+    for bt in bolttransforms:
+        lights.append(RandomSampleAreaLight(Square(), bt.times(boltlighttransform), Vec.of(0, 1, 0), 10, 4))
+        objs.append(Primitive(Sphere(), FresnelPhongMaterial(Vec.of(0, 1, 0), 0.2, 0.4, 0.5, 100, 1.3), bt, Mat4.inverse(bt), False))
+    tiefighter = load_mesh("Tie_Fighter")
+    xwing = load_mesh("x_wing_fighter")
+    tie1 = BVHAggregate.build(tiefighter, Mat4.translation([-0.75, 2, -4]).times(Mat4.rotation(0.4, Y)).times(Mat4.scale(0.2)))
+    tie2 = BVHAggregate(tiefighter, tie1.kdtree, Mat4.translation([6, 6, -20]).times(Mat4.rotation(0.2, Y)).times(Mat4.scale(0.2)))
+    tie3 = BVHAggregate(tiefighter, tie1.kdtree, Mat4.translation([0.5, 4, -10]).times(Mat4.rotation(0.3, Y)).times(Mat4.scale(0.2)))
+    objs += [tie1, tie2, tie3]
+    objs.append(BVHAggregate.build(xwing, Mat4.translation([0.2, 1.1, 0.43]).times(Mat4.rotation(0.2, Z))
+                                   .times(Mat4.rotation(-1.22, Y)).times(Mat4.scale(0.0075))))
+    return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height)
+
+
 # tests/SDF_*/test.mjs -------------------------------------------------------------
 def _sdf_scene(sdf_prims, aspect, width, height, spp, depth, dof, renderer_cls):
     camera = _make_camera(_boxball_camera_transform(), aspect, dof)
@@ -350,7 +379,7 @@ def SDF_Sierpinski(aspect=1, width=600, height=600, spp=16, depth=4, dof=None,
 
 REGISTRY = {f.__name__: f for f in (
     BoxBall, BoxBall_DOF, BoxBall_path, ASimpleScene, spheres010, refraction, refraction_path, cornell_box_path,
-    bunny, bunny_path, dragon, AHollowTetrahedron, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
+    bunny, bunny_path, dragon, AHollowTetrahedron, starwars, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
     SDF_Sierpinski)}
 
 

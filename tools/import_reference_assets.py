@@ -27,6 +27,9 @@ def main():
     for name in ASSETS:
         with open(os.path.join(src, name + ".obj"), encoding="utf8") as fh:
             parsed = parse_obj_text(fh.read())
+        for lib in parsed.mtllibs:          # MTL files are a few hundred bytes: keep their text with the mesh
+            with open(os.path.join(src, lib), encoding="utf8") as fh:
+                parsed.mtl_texts.append(fh.read())
         path = os.path.join(out, name + ".npz")
         parsed.save(path)
         print("%-20s verts=%d normals=%d uvs=%d tris=%d mats=%s -> %d bytes" % (
