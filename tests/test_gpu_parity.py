@@ -33,6 +33,7 @@ PRIMARY = [
     ("SDF_Sierpinski", dict(width=160, height=160)),
     ("SDF_Menger", dict(width=160, height=160)),
     ("spheres010", dict(width=200, height=200)),
+    ("starwars", dict(width=480, height=270, aspect=16 / 9)),      # 4 BVH instances (3 share a kdtree), MTL materials; stands in for Toledo
 ]
 
 
@@ -96,6 +97,7 @@ STOCHASTIC = [
     ("cornell_box_path", dict(width=256, height=256), 4),
     ("bunny_path", dict(width=480, height=270, aspect=16 / 9), 4),
     ("refraction_path", dict(width=192, height=192), 4),
+    ("starwars", dict(width=320, height=180, aspect=16 / 9), 2),   # DOF + 3 square area lights x 4 samples + point light
 ]
 
 
