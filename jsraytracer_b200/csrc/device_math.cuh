@@ -114,7 +114,14 @@ JSRT_DEV float plane_t(float3 o, float3 d) { return (d.z != 0.f) ? -o.z / d.z : 
 JSRT_DEV float sphere_intersect(float3 o, float3 d, float minD) {
     const float a = dot3(d, d), b = dot3(d, o);
     const float c = (float)fma((double)o.x, (double)o.x, fma((double)o.y, (double)o.y, fma((double)o.z, (double)o.z, -1.0)));
-    const float disc = fmaf(b, b, -a * c);
+    float disc = fmaf(b, b, -a * c);
+    if (fabsf(disc) < 1e-5f * fmaf(b, b, fabsf(a * c))) {
+        // near the silhouette b^2 and a*c cancel; with strongly anisotropic transforms (a bolt scaled 0.01 x 0.01 x 1.5
+        // in tests/starwars) the FP32 residue decides hit or miss for the whole primitive.  Redo the discriminant in f64.
+        const double a64 = ddot3(d.x, d.y, d.z, d.x, d.y, d.z), b64 = ddot3(d.x, d.y, d.z, o.x, o.y, o.z);
+        const double c64 = fma((double)o.x, (double)o.x, fma((double)o.y, (double)o.y, fma((double)o.z, (double)o.z, -1.0)));
+        disc = (float)dsub(dmul(b64, b64), dmul(a64, c64));
+    }
     if (disc < 0.f || a == 0.f) return -CUDART_INF_F;
     const float big = sqrtf(disc);
     const float q = -(b + copysignf(big, b));
@@ -147,37 +154,28 @@ JSRT_DEV float split_t(double t, float* t_lo) {
     return tf;
 }
 
-// Triangle.intersect src/geometry.js:368-375 with the constructor constants of :341-353.
-// `accept_lo` / `accept_hi` are the caller's acceptance window (t > lo && t <= hi; the caller applies
-// its own strict tests and the tie rule);
-// the reference evaluates the barycentrics regardless and the caller filters, which
-// gives the same result as skipping them for a t that will be rejected anyway.
-JSRT_DEV float triangle_intersect(const Tri* __restrict__ tris, int idx, float3 o, float3 d, float accept_lo, float accept_hi) {
-    const float4* tp = reinterpret_cast<const float4*>(tris + idx);
-    const float4 a = __ldg(tp);
-    const float den = a.x * d.x + a.y * d.y + a.z * d.z;
-    const float t = (den != 0.f) ? (a.w - (a.x * o.x + a.y * o.y + a.z * o.z)) / den : -CUDART_INF_F;
-    if (!(t > accept_lo && t <= accept_hi) || t < 0.f || isinf(t)) return -CUDART_INF_F;
-    const float4 b = __ldg(tp + 1), c = __ldg(tp + 2), e = __ldg(tp + 3);
-    const float3 P = ray_point(o, d, t);
-    const float3 v2 = f3(P.x - b.x, P.y - b.y, P.z - b.z);
-    const float d20 = v2.x * c.x + v2.y * c.y + v2.z * c.z, d21 = v2.x * e.x + v2.y * e.y + v2.z * e.z;
-    const float d00 = c.w, d11 = e.w, d01 = b.w;
-    const float denom = d00 * d11 - d01 * d01;
-    const float v = (d11 * d20 - d01 * d21) / denom, w = (d00 * d21 - d01 * d20) / denom;
-    const float u = 1.f - v - w;
-    return (u >= 0.f && u <= 1.f && v >= 0.f && v <= 1.f && w >= 0.f && w <= 1.f) ? t : -CUDART_INF_F;
-}
-// Triangle.toBarycentric src/geometry.js:389-396
+// Triangle.toBarycentric src/geometry.js:389-396, in the reference's arithmetic: v2 is an f32 vector, the
+// dot products and the Cramer solve are f64 (see the note on struct Tri), the result is stored f32.
 JSRT_DEV float3 triangle_bary(const Tri* __restrict__ tris, int idx, float3 P) {
     const float4* tp = reinterpret_cast<const float4*>(tris + idx);
     const float4 b = __ldg(tp + 1), c = __ldg(tp + 2), e = __ldg(tp + 3);
-    const float3 v2 = f3(P.x - b.x, P.y - b.y, P.z - b.z);
-    const float d20 = v2.x * c.x + v2.y * c.y + v2.z * c.z, d21 = v2.x * e.x + v2.y * e.y + v2.z * e.z;
-    const float d00 = c.w, d11 = e.w, d01 = b.w;
-    const float denom = d00 * d11 - d01 * d01;
-    const float v = (d11 * d20 - d01 * d21) / denom, w = (d00 * d21 - d01 * d20) / denom;
-    return f3(1.f - v - w, v, w);
+    const double2 g = __ldg(reinterpret_cast<const double2*>(tp + 4)), h = __ldg(reinterpret_cast<const double2*>(tp + 5));
+    const float v2x = (float)dsub(P.x, b.x), v2y = (float)dsub(P.y, b.y), v2z = (float)dsub(P.z, b.z);
+    const double d20 = ddot3(v2x, v2y, v2z, c.x, c.y, c.z), d21 = ddot3(v2x, v2y, v2z, e.x, e.y, e.z);
+    const double v = dmul(dsub(dmul(g.y, d20), dmul(h.x, d21)), h.y), w = dmul(dsub(dmul(g.x, d21), dmul(h.x, d20)), h.y);
+    return f3((float)dsub(dsub(1.0, v), w), (float)v, (float)w);
+}
+// Triangle.intersect src/geometry.js:368-375 with the constructor constants of :341-353.
+// `accept_lo` / `accept_hi` are the caller's acceptance window (t > lo && t <= hi; the caller applies
+// its own strict tests and the tie rule); the reference evaluates the barycentrics regardless and the
+// caller filters, which gives the same result as skipping them for a t that will be rejected anyway.
+JSRT_DEV float triangle_intersect(const Tri* __restrict__ tris, int idx, float3 o, float3 d, float accept_lo, float accept_hi) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(tris + idx));
+    const float den = a.x * d.x + a.y * d.y + a.z * d.z;
+    const float t = (den != 0.f) ? (a.w - (a.x * o.x + a.y * o.y + a.z * o.z)) / den : -CUDART_INF_F;
+    if (!(t > accept_lo && t <= accept_hi) || t < 0.f || isinf(t)) return -CUDART_INF_F;
+    const float3 bary = triangle_bary(tris, idx, ray_point(o, d, t));
+    return (bary.x >= 0.f && bary.x <= 1.f && bary.y >= 0.f && bary.y <= 1.f && bary.z >= 0.f && bary.z <= 1.f) ? t : -CUDART_INF_F;
 }
 
 // ---------------------------------------------------------------------------------

@@ -231,27 +231,6 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : 3) shade_kernel(const __
             }
         }
         const bool lit = hit && mat->kind != M_TRANSPARENT;
-        // ---- shadow rays: one per light sample (src/materials.js:244-257) -----------
-        uint32_t dim = DIM_LIGHTS;
-        for (int li = 0; li < sc.n_lights; ++li) {
-            const Light& L = sc.lights[li];
-            const int ns = L.samples;
-            for (int k = 0; k < ns; ++k, dim += 2) {
-                LightSample ls; float3 contrib = f3(0, 0, 0);
-                if (lit) {
-                    ls = light_sample(L, s.position, rng_u01(node_key, dim), rng_u01(node_key, dim + 1));
-                    contrib = thr * (color_from_light_sample(*mat, f, ls) * (1.0f / (float)ns));
-                }
-                const int slot = warp_append(shadow_count, lit);
-                if (lit) {
-                    if (slot < shadow_cap) {
-                        sq.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
-                        sq.d[slot] = make_float4(ls.direction.x, ls.direction.y, ls.direction.z, 0.f);
-                        sq.c[slot] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
-                    } else *overflow = 1;
-                }
-            }
-        }
         // ---- children (src/materials.js:277-288, 315-330, 169-172).  world.color with
         // recursionDepth - 1 == 0 returns black without casting (src/world.js:32-33).
         bool want0 = false, want1 = false; float3 dir0 = f3(0, 0, 1), dir1 = f3(0, 0, 1), w0 = f3(0, 0, 0), w1 = f3(0, 0, 0);
@@ -268,17 +247,57 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : 3) shade_kernel(const __
                 if (f.kr < 1.f && scatter(*mat, f, f.has_refr, f.refr, f.N * -1.f, node_key, sb + 4, dir1, col)) { want1 = true; w1 = thr * (col * f.transmissivity * (1.f - f.kr)); }
             }
         }
+        // ---- queue space: ONE atomicAdd per warp per queue per iteration, issued here and consumed
+        // after the light-sample arithmetic below.  (One atomic per appended item made the return
+        // latency of the contended counter 60 % of this kernel's stall samples: profiles/r1_ncu_summary.md.)
+        const int lane = threadIdx.x & 31;
+        const unsigned lit_mask = __ballot_sync(0xffffffffu, lit), m0 = __ballot_sync(0xffffffffu, want0), m1 = __ballot_sync(0xffffffffu, want1);
+        const int n_lit = __popc(lit_mask), n0 = __popc(m0), n1 = __popc(m1);
+        int base_s = 0, base_c = 0;
+        if (lane == 0) {
+            if (n_lit) base_s = atomicAdd(shadow_count, n_lit * sc.light_samples);
+            if (n0 + n1) base_c = atomicAdd(next_count, n0 + n1);
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        const int rank_s = __popc(lit_mask & lt), rank0 = __popc(m0 & lt), rank1 = n0 + __popc(m1 & lt);
+
+        // ---- shadow rays: one per light sample (src/materials.js:244-257); sample j of the warp's lit
+        // lanes occupies slots [base_s + j * n_lit, base_s + (j + 1) * n_lit): coalesced per sample
+        uint32_t dim = DIM_LIGHTS;
+        int j = 0;
+        bool have_base = false;
+        for (int li = 0; li < sc.n_lights; ++li) {
+            const Light& L = sc.lights[li];
+            const int ns = L.samples;
+            for (int k = 0; k < ns; ++k, dim += 2, ++j) {
+                LightSample ls; float3 contrib = f3(0, 0, 0);
+                if (lit) {
+                    ls = light_sample(L, s.position, rng_u01(node_key, dim), rng_u01(node_key, dim + 1));
+                    contrib = thr * (color_from_light_sample(*mat, f, ls) * (1.0f / (float)ns));
+                }
+                if (!have_base) { base_s = __shfl_sync(0xffffffffu, base_s, 0); have_base = true; }
+                if (lit) {
+                    const int slot = base_s + j * n_lit + rank_s;
+                    if (slot < shadow_cap) {
+                        sq.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
+                        sq.d[slot] = make_float4(ls.direction.x, ls.direction.y, ls.direction.z, 0.f);
+                        sq.c[slot] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                    } else *overflow = 1;
+                }
+            }
+        }
+        base_c = __shfl_sync(0xffffffffu, base_c, 0);
         const int packed_next = (pass << 8) | (depth_rem - 1);
-        int slot = warp_append(next_count, want0);
         if (want0) {
+            const int slot = base_c + rank0;
             if (slot < next_cap) {
                 next.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
                 next.d[slot] = make_float4(dir0.x, dir0.y, dir0.z, __int_as_float((int)(2u * node)));
                 next.w[slot] = make_float4(w0.x, w0.y, w0.z, __int_as_float(packed_next));
             } else *overflow = 1;
         }
-        slot = warp_append(next_count, want1);
         if (want1) {
+            const int slot = base_c + rank1;
             if (slot < next_cap) {
                 next.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
                 next.d[slot] = make_float4(dir1.x, dir1.y, dir1.z, __int_as_float((int)(2u * node + 1u)));

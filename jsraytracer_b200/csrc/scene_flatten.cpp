@@ -137,9 +137,10 @@ struct Flattener {
             t.p0x = p[0][0]; t.p0y = p[0][1]; t.p0z = p[0][2];
             t.v0x = v0[0]; t.v0y = v0[1]; t.v0z = v0[2];
             t.v1x = v1[0]; t.v1y = v1[1]; t.v1z = v1[2];
-            t.d00 = (float)((double)v0[0] * v0[0] + (double)v0[1] * v0[1] + (double)v0[2] * v0[2]);
-            t.d11 = (float)((double)v1[0] * v1[0] + (double)v1[1] * v1[1] + (double)v1[2] * v1[2]);
-            t.d01 = (float)((double)v0[0] * v1[0] + (double)v0[1] * v1[1] + (double)v0[2] * v1[2]);
+            t.d00 = (double)v0[0] * v0[0] + (double)v0[1] * v0[1] + (double)v0[2] * v0[2];
+            t.d11 = (double)v1[0] * v1[0] + (double)v1[1] * v1[1] + (double)v1[2] * v1[2];
+            t.d01 = (double)v0[0] * v1[0] + (double)v0[1] * v1[1] + (double)v0[2] * v1[2];
+            t.inv_denom = 1.0 / (t.d00 * t.d11 - t.d01 * t.d01);
             TriShade s{};
             // psdata: {UV:[..], normal:[..]} — an Array here means the reference's
             // lossy Triangle.serialize (src/geometry.js:355-357) wrote `ps` twice.

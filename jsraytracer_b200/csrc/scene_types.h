@@ -35,14 +35,17 @@ struct Prim {
     int pad0, pad1;
 };
 
-// Triangle constants, computed like the reference constructor
-// (src/geometry.js:335-354) in f64 from the f32 vertices, then stored f32.
-// 64 bytes = four 128-bit loads; the plane test needs only the first.
+// Triangle constants, computed like the reference constructor (src/geometry.js:335-354) in f64 from
+// the f32 vertices.  96 bytes = six 128-bit loads; the plane test needs only the first.  The
+// barycentric constants stay f64: for sliver triangles (d00 d11 - d01^2 -> 0) their f32 roundings alone
+// are larger than the determinant, and real meshes are full of slivers (x_wing_fighter.obj).
 struct Tri {
     float nx, ny, nz, delta;      // normal (normalised v0 x v1), delta = normal . p0
-    float p0x, p0y, p0z, d01;
-    float v0x, v0y, v0z, d00;
-    float v1x, v1y, v1z, d11;
+    float p0x, p0y, p0z, pad0;
+    float v0x, v0y, v0z, pad1;
+    float v1x, v1y, v1z, pad2;
+    double d00, d11;
+    double d01, inv_denom;        // 1 / (d00 d11 - d01^2)
 };
 struct TriShade {                 // per-vertex shading data (only read for shaded hits)
     float n[3][4];                // psdata.normal (w = 0)
