@@ -300,6 +300,45 @@ def starwars(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=Incr
     return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height)
 
 
+# tests/Aggregates/test.mjs: plain Aggregates, one nested in another, a primitive shared between them
+def Aggregates(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([-7, 0.5, 4]))
+    lights = [SimplePointLight(Vec.of(10, 7, 10, 1), Vec.of(1, 1, 1), 10000)]
+    objects = [Primitive(Plane(), PhongMaterial(Vec.of(0.5, 0.5, 0.5), 0.1, 0.4, 0.6, 100, 0.5),
+                         Mat4.translation([0, -1.5, 0]).times(Mat4.rotation(PI / 2, Vec.of(1, 0, 0))))]
+    box = Primitive(UnitBox(), PhongMaterial(Vec.of(1, 0, 0), 0.2, 0.4, 0.6, 100, 0.5),
+                    Mat4.translation([1, 0.3, -9, 1]).times(Mat4.scale(2)))
+    ball = Primitive(Sphere(), PhongMaterial(Vec.of(0, 0, 1), 0.2, 0.4, 0.6, 100, 0.5), Mat4.translation([-2, 0.3, -9]))
+    agg = Aggregate([box, ball], Mat4.translation([-6, 0, 0]))
+    objects.append(agg)
+    objects.append(Aggregate([agg, ball], Mat4.translation([-9, 3, -9]).times(Mat4.eulerRotation([0, PI, 0]))
+                             .times(Mat4.translation([3, 0, 9]))))
+    return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+# Stand-in for the scale of BASELINE configs[4] (tests/toledo: asset missing): a 3 x 3 x 3 grid of
+# dragon instances sharing one kdtree (27 x 99 968 = 2.7 M triangle instances), built with the reference's own
+# instancing idiom `new BVHAggregate(triangles, bvh.kdtree, transform)` (tests/starwars/test.mjs:57-62).
+def dragon_grid(aspect=1, width=600, height=600, spp=16, depth=4, n=3, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([0, 3.2, 5.5]).times(Mat4.rotation(-0.3, Vec.of(1, 0, 0))))
+    lights = [SimplePointLight(Vec.of(-15, 12, 12, 1), Vec.of(1, 1, 1), 8000)]
+    objs = [_checker_floor(PhongMaterial, (CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0, 0, 0)),
+                                           0.3, 0.4, 0.6, 100, 0.5), y=0)]
+    triangles = load_mesh("dragon", PhongMaterial(Vec.of(0.3884335160255432, 1, 0.8839936256408691), 0.01, 0.8, 0.2, 32, 0.5))
+    first = None
+    for i in range(n):
+        for j in range(n):
+            for k in range(n):
+                t = (Mat4.translation([(i - (n - 1) / 2) * 2.2, 0.05 + j * 1.6, -4 - k * 2.4])
+                     .times(Mat4.rotation(0.3 + 0.4 * (i + 2 * j + 3 * k), Vec.of(0, 1, 0))).times(Mat4.scale(0.12)))
+                if first is None:
+                    first = BVHAggregate.build(triangles, t)
+                    objs.append(first)
+                else:
+                    objs.append(BVHAggregate(triangles, first.kdtree, t))
+    return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height, bg=Vec.of(0.05, 0.06, 0.1))
+
+
 # tests/SDF_*/test.mjs -------------------------------------------------------------
 def _sdf_scene(sdf_prims, aspect, width, height, spp, depth, dof, renderer_cls):
     camera = _make_camera(_boxball_camera_transform(), aspect, dof)
@@ -379,7 +418,7 @@ def SDF_Sierpinski(aspect=1, width=600, height=600, spp=16, depth=4, dof=None,
 
 REGISTRY = {f.__name__: f for f in (
     BoxBall, BoxBall_DOF, BoxBall_path, ASimpleScene, spheres010, refraction, refraction_path, cornell_box_path,
-    bunny, bunny_path, dragon, AHollowTetrahedron, starwars, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
+    bunny, bunny_path, dragon, AHollowTetrahedron, starwars, Aggregates, dragon_grid, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
     SDF_Sierpinski)}
 
 

@@ -33,6 +33,8 @@ PRIMARY = [
     ("SDF_Sierpinski", dict(width=160, height=160)),
     ("SDF_Menger", dict(width=160, height=160)),
     ("spheres010", dict(width=200, height=200)),
+    ("Aggregates", dict(width=256, height=256)),                   # plain Aggregates, nested, with a shared primitive
+    ("dragon_grid", dict(width=320, height=180, aspect=16 / 9, n=2)),   # 8 instances of one kdtree (Toledo-scale stand-in)
     ("starwars", dict(width=480, height=270, aspect=16 / 9)),      # 4 BVH instances (3 share a kdtree), MTL materials; stands in for Toledo
 ]
 
@@ -70,6 +72,7 @@ WHITTED = [
     # ill-conditioned in the reference itself (a 1e-7 rad camera roll flips ~50 of them at 256^2), so this
     # scene is compared at the resolution where such rows are a small share of the frame.
     ("refraction", dict(width=768, height=768), 1),
+    ("Aggregates", dict(width=256, height=256), 1),
     ("SDF_Sierpinski", dict(width=160, height=160), 1),
     ("SDF_Menger", dict(width=160, height=160), 1),
     ("SDF_BoxBall", dict(width=160, height=160), 1),            # per-leaf basecolor through UnionSDF.getMaterialData

@@ -15,7 +15,11 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "bunny_path"
     W, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1920, 1080)
     passes = int(sys.argv[4]) if len(sys.argv) > 4 else 8
-    ser = Serializer(scenes.configure(name, width=W, height=H, aspect=W / H))
+    kw = {}
+    for a in sys.argv[5:]:                      # extra scene keywords, e.g. n=3
+        k, v = a.split("=")
+        kw[k] = int(v)
+    ser = Serializer(scenes.configure(name, width=W, height=H, aspect=W / H, **kw))
     sc = lib.Scene(ser.to_msgpack(), lib.FORMAT_MSGPACK, device=0)
     sc.render(0, passes, seed=1)
     sc.synchronize()
