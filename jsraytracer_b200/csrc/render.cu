@@ -30,6 +30,9 @@ namespace jsrt {
 namespace {
 
 constexpr int kBlock = 256;
+#ifndef JSRT_BVH_MIN_BLOCKS
+#define JSRT_BVH_MIN_BLOCKS 4      // 64 registers: 4 CTAs / SM (measured against 3 and 5: profiles/r1_ncu_summary.md)
+#endif
 
 struct RayQueue { float4* o; float4* d; float4* w; };
 struct ShadowQueue { float4* o; float4* d; float4* c; };
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(kBlock) sdf_kernel(const __grid_constant__ Dev
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
 template <int MODE, bool COUNT, bool HAS_SDF>
-__global__ void __launch_bounds__(kBlock, 4) bvh_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
+__global__ void __launch_bounds__(kBlock, JSRT_BVH_MIN_BLOCKS) bvh_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
     Work wp, ws;
     bvh_wave<MODE, COUNT, HAS_SDF>(sc, io, &wp, &ws);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }

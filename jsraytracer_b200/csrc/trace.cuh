@@ -148,6 +148,23 @@ JSRT_DEV void accum_add3(float4* accum, uint32_t pixel, float3 c) {
 
 JSRT_DEV bool better_hit(float t, int top, const Hit& best) { return t < best.t || (t == best.t && top < best.top); }
 
+// AABB.get_intersects (src/geometry.js:189-209) for a node stored as (centre, half) with the ray's reciprocal
+// direction: (p_i +- h_i) * (1 / d_i); axes with |d_i| <= 1e-7 follow the reference's parallel rule (:194,205).
+// The per-axis early returns of the reference are equivalent to one final test because t_min only grows and
+// t_max only shrinks.  Returns the entry distance in b0.
+JSRT_DEV bool slab_test(const float4 n0, const float4 n1, float3 lo, float3 inv, bool parx, bool pary, bool parz, float minD, float maxD, float& b0) {
+    const float px = n0.x - lo.x, py = n0.y - lo.y, pz = n0.z - lo.z;
+    const float ax = (px + n0.w) * inv.x, bx = (px - n0.w) * inv.x;
+    const float ay = (py + n1.x) * inv.y, by = (py - n1.x) * inv.y;
+    const float az = (pz + n1.y) * inv.z, bz = (pz - n1.y) * inv.z;
+    float b1 = CUDART_INF_F; b0 = -CUDART_INF_F;
+    bool miss = false;
+    if (parx) miss = fabsf(px) > n0.w; else { b0 = fminf(ax, bx); b1 = fmaxf(ax, bx); }
+    if (pary) miss = miss || fabsf(py) > n1.x; else { b0 = fmaxf(b0, fminf(ay, by)); b1 = fminf(b1, fmaxf(ay, by)); }
+    if (parz) miss = miss || fabsf(pz) > n1.y; else { b0 = fmaxf(b0, fminf(az, bz)); b1 = fminf(b1, fmaxf(az, bz)); }
+    return !miss && !(b0 > b1) && !(b1 < minD) && !(b0 > maxD);
+}
+
 template <int MODE>
 JSRT_DEV void ray_window(const float4 d4, float& minD, float& maxD, bool& primary) {
     if (MODE == TM_EXTEND) {
@@ -204,6 +221,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     constexpr int REFILL_T = JSRT_REFILL_T;     // finish + refill when this many lanes are idle (or nothing else is left)
     constexpr int LEAF_T = JSRT_LEAF_T;         // test postponed leaves when this many lanes hold one (or one must be flushed)
     constexpr int NODE_STEPS = JSRT_NODE_STEPS; // nodes walked per iteration between the warp votes
+    constexpr int REFILL_ROUNDS = 8;            // hand-over rounds per iteration (rays that miss every root box are replaced at once)
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int n = min(*io.count, io.cap);
@@ -244,9 +262,15 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
 
     for (;;) {
         // ---- phase 1: write finished rays, hand out new ones ------------------------------
-        const unsigned idle_mask = __ballot_sync(FULL, cur < 0 || done);
-        const int n_idle = __popc(idle_mask);
-        if (n_idle >= REFILL_T || idle_mask == FULL) {
+        // A new ray is tested against its tree's root box right here, and a ray that misses every root is
+        // finished and replaced in the next round of this loop: most rays miss the mesh altogether (92 % of
+        // bunny_path's camera rays), and they should not occupy a lane of the node loop for one step each.
+        bool all_out = false;
+        #pragma unroll 1
+        for (int round = 0; round < REFILL_ROUNDS; ++round) {
+            const unsigned idle_mask = __ballot_sync(FULL, cur < 0 || done);
+            const int n_idle = __popc(idle_mask);
+            if (!(n_idle >= REFILL_T || idle_mask == FULL)) break;
             if (cur >= 0 && done) {
                 if (io.final_pass) finish_ray<MODE>(io, cur, best, o4);
                 else io.hits[cur] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
@@ -260,24 +284,37 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 if (base >= n) { exhausted = true; pool_next = pool_end = 0; }
             }
             const int avail = pool_end - pool_next;
-            if (avail > 0) {
-                const int rank = __popc(idle_mask & ((1u << lane) - 1u));
-                if (cur < 0 && rank < avail) {
-                    cur = pool_next + rank;
-                    o4 = io.o[cur];
-                    const float4 d4 = io.d[cur], h4 = io.hits[cur];
-                    o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
-                    bool primary;
-                    ray_window<MODE>(d4, minD, maxD, primary);
-                    if (COUNT) work = primary ? work_primary : work_other;
-                    best.t = h4.x; best.prim = __float_as_int(h4.y); best.top = __float_as_int(h4.z); best.t_lo = h4.w;
-                    bi = 0;
-                    if (ANY_HIT && best.prim >= 0) cur = -1;        // already occluded by a top-level primitive: nothing to do or write
-                    else enter();
+            if (avail <= 0) { all_out = exhausted && __all_sync(FULL, cur < 0); break; }
+            const int rank = __popc(idle_mask & ((1u << lane) - 1u));
+            if (cur < 0 && rank < avail) {
+                cur = pool_next + rank;
+                o4 = io.o[cur];
+                const float4 d4 = io.d[cur], h4 = io.hits[cur];
+                o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
+                bool primary;
+                ray_window<MODE>(d4, minD, maxD, primary);
+                if (COUNT) work = primary ? work_primary : work_other;
+                best.t = h4.x; best.prim = __float_as_int(h4.y); best.top = __float_as_int(h4.z); best.t_lo = h4.w;
+                bi = 0;
+                if (ANY_HIT && best.prim >= 0) cur = -1;        // already occluded by a top-level primitive: nothing to do or write
+                else {
+                    // skip the trees whose root box the ray misses (the first test of BVHAggregateNode.intersect, :208-209)
+                    for (;;) {
+                        enter();
+                        const float4 n0 = __ldg(nodes), n1 = __ldg(nodes + 1);
+                        float b0;
+                        if (COUNT) ++work->nodes;
+                        if (slab_test(n0, n1, lo, inv, parx, pary, parz, minD, maxD, b0) && b0 <= best.t) {
+                            if (__float_as_int(n1.w) == -1) node_i = 1;      // inner root: its test is done
+                            break;
+                        }
+                        if (++bi >= sc.n_bvh) { done = true; break; }
+                    }
                 }
-                pool_next += min(avail, n_idle);
-            } else if (exhausted && __all_sync(FULL, cur < 0)) break;
+            }
+            pool_next += min(avail, n_idle);
         }
+        if (all_out) break;
         const bool active = cur >= 0 && !done;
 
         // ---- phase 2: postponed leaf tests (src/aggregates.js:211-218) -------------------------
