@@ -174,7 +174,23 @@ JSRT_DEV float triangle_intersect(const Tri* __restrict__ tris, int idx, float3 
     const float den = a.x * d.x + a.y * d.y + a.z * d.z;
     const float t = (den != 0.f) ? (a.w - (a.x * o.x + a.y * o.y + a.z * o.z)) / den : -CUDART_INF_F;
     if (!(t > accept_lo && t <= accept_hi) || t < 0.f || isinf(t)) return -CUDART_INF_F;
-    const float3 bary = triangle_bary(tris, idx, ray_point(o, d, t));
+    const float3 P = ray_point(o, d, t);
+    {
+        // FP32 fast path: the reference tests the f32-rounded barycentrics against [0, 1]; for a well-conditioned
+        // triangle the FP32 Cramer solve is within ~1e-6 of them, so any point whose barycentrics clear 0 and 1
+        // by 1e-4 is decided here (hit or miss); everything else (edges, slivers via the NaN in d00f) falls
+        // through to the reference's arithmetic below.
+        const float4* tp = reinterpret_cast<const float4*>(tris + idx);
+        const float4 b = __ldg(tp + 1), c = __ldg(tp + 2), e = __ldg(tp + 3);
+        const float v2x = P.x - b.x, v2y = P.y - b.y, v2z = P.z - b.z;
+        const float d20 = v2x * c.x + v2y * c.y + v2z * c.z, d21 = v2x * e.x + v2y * e.y + v2z * e.z;
+        const float inv = 1.0f / (c.w * e.w - b.w * b.w);
+        const float v = (e.w * d20 - b.w * d21) * inv, w = (c.w * d21 - b.w * d20) * inv, u = 1.f - v - w;
+        const float m = 1e-4f;
+        if (u > m && v > m && w > m && u < 1.f - m && v < 1.f - m && w < 1.f - m) return t;
+        if (u < -m || v < -m || w < -m || u > 1.f + m || v > 1.f + m || w > 1.f + m) return -CUDART_INF_F;
+    }
+    const float3 bary = triangle_bary(tris, idx, P);
     return (bary.x >= 0.f && bary.x <= 1.f && bary.y >= 0.f && bary.y <= 1.f && bary.z >= 0.f && bary.z <= 1.f) ? t : -CUDART_INF_F;
 }
 
@@ -224,7 +240,12 @@ JSRT_DEV double js_to_precision8(double x) {
     const double r = (k >= 0) ? nn / kPow10[k] : dmul(nn, kPow10[-k]);
     return copysign(r, x);
 }
-JSRT_DEV double js_fmod(double a, double b) { return js_to_precision8(dsub(a, dmul(floor(a / b), b))); }
+JSRT_DEV double js_fmod(double a, double b) {
+    // a / b: for a power-of-two period the product with the (exact) reciprocal is the same number
+    int e; const bool pow2 = frexp(b, &e) == 0.5;
+    const double q = pow2 ? dmul(a, 1.0 / b) : a / b;
+    return js_to_precision8(dsub(a, dmul(floor(q), b)));
+}
 
 JSRT_DEV double sdf_eval(const SdfInstr* __restrict__ code, const Xform64* __restrict__ xforms64, float3 p0) {
     float3 P[8]; double S[12]; double D[8];
@@ -245,7 +266,14 @@ JSRT_DEV double sdf_eval(const SdfInstr* __restrict__ code, const Xform64* __res
                 const float3 p = P[sp];
                 const float qx = (float)dsub(fabsf(p.x), fv.x), qy = (float)dsub(fabsf(p.y), fv.y), qz = (float)dsub(fabsf(p.z), fv.z);
                 const double mx = fmax((double)qx, 0.0), my = fmax((double)qy, 0.0), mz = fmax((double)qz, 0.0);   // Vec.max(q, 0): q.w = 0
-                D[dp++] = dadd(sqrt(ddot4(mx, my, mz, 0.0, mx, my, mz, 0.0)), fmin(fmax(fmax((double)qx, (double)qy), (double)qz), 0.0));
+                // |max(q, 0)|: with at most one positive component the f64 square of an f32 value is exact and
+                // its correctly rounded root is that value again, so the sqrt can be skipped without changing a bit
+                double len;
+                if (my == 0.0 && mz == 0.0) len = mx;
+                else if (mx == 0.0 && mz == 0.0) len = my;
+                else if (mx == 0.0 && my == 0.0) len = mz;
+                else len = sqrt(ddot4(mx, my, mz, 0.0, mx, my, mz, 0.0));
+                D[dp++] = dadd(len, fmin(fmax(fmax((double)qx, (double)qy), (double)qz), 0.0));
                 break;
             }
             case S_TETRA: {                                                                               // src/sdf.js:305-308

@@ -138,18 +138,6 @@ __global__ void __launch_bounds__(kBlock, JSRT_BVH_MIN_BLOCKS) bvh_kernel(const 
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
 
-// warp-aggregated append: returns this lane's slot (valid only where `want`)
-__device__ __forceinline__ int warp_append(int* counter, bool want) {
-    const unsigned mask = __ballot_sync(0xffffffffu, want);
-    if (mask == 0) return -1;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return base + __popc(mask & ((1u << lane) - 1u));
-}
-
 __device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float3 c) {
     float* a = reinterpret_cast<float*>(accum + pixel);
     if (c.x != 0.f) atomicAdd(a + 0, c.x);
@@ -165,7 +153,7 @@ template <bool HAS_SDF>
 __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : 3) shade_kernel(const __grid_constant__ DeviceScene sc, RayQueue q, const int* __restrict__ count,
                                                         const float4* __restrict__ hits, RayQueue next, int* next_count, int next_cap,
                                                         ShadowQueue sq, int* shadow_count, int shadow_cap, float4* __restrict__ accum,
-                                                        unsigned long long seed, unsigned long long* stats, int* overflow) {
+                                                        unsigned long long seed, unsigned long long* stats, int* overflow, const float4* __restrict__ sdf_normals) {
     const int n = *count;
     const int stride = gridDim.x * blockDim.x;
     const int n_round = (n + 31) & ~31;      // warp-uniform trip count: every lane reaches the ballots
@@ -217,7 +205,9 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : 3) shade_kernel(const __
                     }
                     lp = ray_point_f64(lo, ld, td);
                 }
-                float3 ln; material_data<HAS_SDF>(sc, pa.x, pa.y, flags, lp, ln, s.uv, s.has_uv, s.basecolor);
+                float3 ln; float4 sn = make_float4(0, 0, 0, 0);
+                if (HAS_SDF && sdf_normals && ta.x == T_SDF) sn = sdf_normals[i];
+                material_data<HAS_SDF>(sc, pa.x, pa.y, flags, lp, ln, s.uv, s.has_uv, s.basecolor, &sn);
                 s.normal = normalized3(xf_normal(inv, ln));
                 s.position = ray_point_f64(o, d, td);
                 mat = sc.materials + pa.z;
@@ -357,13 +347,6 @@ __global__ void hits_to_ids_kernel(const __grid_constant__ DeviceScene sc, const
 
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) throw std::runtime_error(std::string("jsrt: CUDA error: ") + cudaGetErrorString(e__) + " at " #call); } while (0)
 
-template <class T> T* toDevice(const std::vector<T>& v, cudaStream_t st) {
-    T* p = nullptr;
-    const size_t bytes = (v.empty() ? 1 : v.size()) * sizeof(T);
-    CK(cudaMalloc(&p, bytes));
-    if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
-    return p;
-}
 
 }  // namespace
 
@@ -376,6 +359,7 @@ struct Renderer::Impl {
     std::vector<void*> allocs;
     float4* accum = nullptr;
     RayQueue rq[2]{}; float4* hits = nullptr; float4* shadow_hits = nullptr; ShadowQueue sq{};
+    float4* sdf_normals = nullptr;
     Counters* counters = nullptr;
     int* overflow = nullptr;
     int ray_cap = 0, shadow_cap = 0, batch = 0;
@@ -441,7 +425,7 @@ struct Renderer::Impl {
         // depth-8 Cornell box, which runs in sub-frame batches.
         double worst = 1; for (int l = 1; l < hs.max_depth; ++l) worst *= hs.fanout;
         if (worst > 1e6) worst = 1e6;
-        const double per_sample = worst * (2.0 * 48 + 16 + 64.0 * std::max(1, hs.light_samples));
+        const double per_sample = worst * (2.0 * 48 + 16 + (hs.sdfs.empty() ? 0 : 16) + 64.0 * std::max(1, hs.light_samples));
         double b = (double)queue_budget / per_sample;
         const double want = (double)npix * 4;            // up to 4 passes per wave
         if (b > want) b = want;
@@ -453,6 +437,7 @@ struct Renderer::Impl {
         hits = dalloc<float4>(ray_cap);
         sq.o = dalloc<float4>(shadow_cap); sq.d = dalloc<float4>(shadow_cap); sq.c = dalloc<float4>(shadow_cap);
         shadow_hits = dalloc<float4>(shadow_cap);
+        if (!hs.sdfs.empty()) { sdf_normals = dalloc<float4>(ray_cap); CK(cudaMemsetAsync(sdf_normals, 0, (size_t)ray_cap * sizeof(float4), stream)); }
         queue_bytes = (size_t)ray_cap * (2 * 48 + 16) + (size_t)shadow_cap * (48 + 16);
 
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
@@ -530,7 +515,7 @@ struct Renderer::Impl {
     }
     void launchExtend(int cur, bool count_work) {
         TraceIO io{}; io.o = rq[cur].o; io.d = rq[cur].d; io.hits = hits; io.count = &counters->ray[cur]; io.cap = ray_cap;
-        io.cursor = &counters->cursor_extend; io.stats = counters->stats;
+        io.cursor = &counters->cursor_extend; io.stats = counters->stats; io.aux = sdf_normals;
         timed(1, [&] { launchTrace<TM_EXTEND>(io, count_work, grid_extend); });
     }
     void launchShadow(bool count_work) {
@@ -567,9 +552,9 @@ struct Renderer::Impl {
                 launchExtend(cur, count_work);
                 timed(2, [&] {
                     if (has_sdf) shade_kernel<true><<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap,
-                                                                                       sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow);
+                                                                                       sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow, sdf_normals);
                     else shade_kernel<false><<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap,
-                                                                                sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow);
+                                                                                sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow, nullptr);
                 });
                 if (hs.light_samples > 0) launchShadow(count_work);
                 level_end_kernel<<<1, 1, 0, stream>>>(counters, cur, level, ray_cap, shadow_cap); ++launches;

@@ -141,6 +141,10 @@ struct Flattener {
             t.d11 = (double)v1[0] * v1[0] + (double)v1[1] * v1[1] + (double)v1[2] * v1[2];
             t.d01 = (double)v0[0] * v1[0] + (double)v0[1] * v1[1] + (double)v0[2] * v1[2];
             t.inv_denom = 1.0 / (t.d00 * t.d11 - t.d01 * t.d01);
+            // f32 fast path only for well-conditioned triangles: sin^2 of the corner angle = denom / (d00 d11)
+            const double cond = (t.d00 * t.d11 - t.d01 * t.d01) / (t.d00 * t.d11);
+            t.d00f = (cond > 1e-2) ? (float)t.d00 : std::numeric_limits<float>::quiet_NaN();
+            t.d11f = (float)t.d11; t.d01f = (float)t.d01;
             TriShade s{};
             // psdata: {UV:[..], normal:[..]} — an Array here means the reference's
             // lossy Triangle.serialize (src/geometry.js:355-357) wrote `ps` twice.

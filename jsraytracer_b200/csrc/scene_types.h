@@ -41,9 +41,9 @@ struct Prim {
 // are larger than the determinant, and real meshes are full of slivers (x_wing_fighter.obj).
 struct Tri {
     float nx, ny, nz, delta;      // normal (normalised v0 x v1), delta = normal . p0
-    float p0x, p0y, p0z, pad0;
-    float v0x, v0y, v0z, pad1;
-    float v1x, v1y, v1z, pad2;
+    float p0x, p0y, p0z, d01f;    // f32 copies of the barycentric constants for the fast path;
+    float v0x, v0y, v0z, d00f;    // d00f is NaN for ill-conditioned (sliver) triangles, which sends every
+    float v1x, v1y, v1z, d11f;    // test of such a triangle down the f64 path
     double d00, d11;
     double d01, inv_denom;        // 1 / (d00 d11 - d01^2)
 };

@@ -94,7 +94,7 @@ JSRT_DEV void sdf_material(const DeviceScene& sc, int first, float3 p, float3& b
 // geometry.materialData in the primitive's local space -> local normal, UV, basecolor.
 template <bool HAS_SDF>
 JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index, int flags, float3 lp,
-                            float3& n, float2& uv, bool& has_uv, float3& base) {
+                            float3& n, float2& uv, bool& has_uv, float3& base, const float4* sdf_normal = nullptr) {
     has_uv = false; uv = make_float2(0.f, 0.f); base = f3(1.f, 1.f, 1.f); n = f3(0.f, 0.f, 1.f);
     switch (geom_kind) {
         case G_PLANE: case G_SQUARE: case G_CIRCLE:       // src/geometry.js:249-254
@@ -137,6 +137,9 @@ JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index
         }
         case G_SDF: if (HAS_SDF) {                        // src/sdf.js:41-47: forward differences, reference arithmetic
             const SdfProgram& pr = sc.sdfs[geom_index];
+            base = f3(pr.base[0], pr.base[1], pr.base[2]);
+            if (pr.mat_first >= 0) sdf_material(sc, pr.mat_first, lp, base, uv, has_uv);
+            if (sdf_normal && sdf_normal->w != 0.f) { n = f3(sdf_normal->x, sdf_normal->y, sdf_normal->z); break; }   // computed by sdf_kernel
             const SdfInstr* prog = sc.sdf_code + pr.first_instr;
             const double step = pr.normal_step_size;
             const float fs = (float)step;                 // Vec.axis(i, 4, step) stores the step as f32
@@ -147,8 +150,6 @@ JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index
             const float nx = (float)(dsub(dx, d0) / step), ny = (float)(dsub(dy, d0) / step), nz = (float)(dsub(dz, d0) / step);
             const double nn = sqrt(ddot4(nx, ny, nz, 0.0, nx, ny, nz, 0.0));
             n = (nn > 0.00001) ? f3((float)dmul(nx, 1.0 / nn), (float)dmul(ny, 1.0 / nn), (float)dmul(nz, 1.0 / nn)) : f3(nx, ny, nz);
-            base = f3(pr.base[0], pr.base[1], pr.base[2]);
-            if (pr.mat_first >= 0) sdf_material(sc, pr.mat_first, lp, base, uv, has_uv);
             break;
         }
         default: break;
