@@ -3,10 +3,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A step = `--passes-per-step` (default 8) full-frame sample passes of the
+A step = `--passes-per-step` (default 16) full-frame sample passes of the
 reference's `IncrementalMultisamplingRenderer.render` loop (src/renderers.js:87-98)
 on the BASELINE workload `tests/bunny_path` at 1920x1080, camera aspect 16/9,
-depth 4 (BASELINE.json configs[2]; 32 steps = the config's 256 spp).  Rays are
+depth 4 (BASELINE.json configs[2]; 16 steps = the config's 256 spp).  Rays are
 counted as the reference would: one per `World.cast` call (primary, secondary
 and shadow rays; src/world.js:28-30).
 
@@ -32,7 +32,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "tests/bunny_path 1920x1080 aspect 16/9 depth 4 (BASELINE configs[2]; 256 spp = 32 steps x 8 passes)"
+WORKLOAD = "tests/bunny_path 1920x1080 aspect 16/9 depth 4 (BASELINE configs[2]; 256 spp = 16 steps x 16 passes)"
 METRIC = "Mrays/s at 1080p on bunny_path"
 
 
@@ -305,13 +305,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="bunny_path")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--passes-per-step", type=int, default=8)
+    ap.add_argument("--passes-per-step", type=int, default=16)
     ap.add_argument("--cpu-passes", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

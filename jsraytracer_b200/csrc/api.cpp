@@ -28,7 +28,7 @@ static int needDevice(jsrt_scene* s) {
 
 static size_t queueBudget() {
     if (const char* e = getenv("JSRT_QUEUE_BYTES")) { const double v = atof(e); if (v >= 1e6) return (size_t)v; }
-    return (size_t)12 << 30;
+    return (size_t)64 << 30;      // of the 180 GB of HBM3e; see render.cu for why big waves pay
 }
 
 extern "C" {

@@ -121,6 +121,9 @@ JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, floa
 #ifndef JSRT_LEAF_T
 #define JSRT_LEAF_T 16
 #endif
+#ifndef JSRT_POOL_BATCH
+#define JSRT_POOL_BATCH 64
+#endif
 #ifndef JSRT_NODE_STEPS
 #define JSRT_NODE_STEPS 8
 #endif
@@ -216,7 +219,7 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_pr
 template <int MODE, bool COUNT, bool HAS_SDF>
 JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other) {
     constexpr bool ANY_HIT = (MODE == TM_SHADOW);
-    constexpr int BATCH = 128;
+    constexpr int BATCH = JSRT_POOL_BATCH;      // ray indices fetched per atomicAdd
     // A warp runs three phases per iteration, each only when enough lanes need it, so that the
     // rarely-needed code (ray hand-over, leaf tests) executes with many lanes instead of one or two:
     constexpr int REFILL_T = JSRT_REFILL_T;     // finish + refill when this many lanes are idle (or nothing else is left)
