@@ -300,6 +300,24 @@ def starwars(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=Incr
     return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height)
 
 
+# tests/tie_fighter/test.mjs — the one scene whose committed screenshots (tests/tie_fighter/download (10|11).png)
+# can be compared with a render (tests/test_reference_screenshots.py)
+def tie_fighter(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    X, Y = Vec.of(1, 0, 0), Vec.of(0, 1, 0)
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([0, 2, 0]).times(Mat4.rotation(-0.2, X)))
+    lights = [SimplePointLight(Vec.of(-10, 10, -12, 1), Vec.of(1, 1, 1), 5000),
+              RandomSampleAreaLight(Square(), Mat4.translation([-0.15, 1.86, -2.73]).times(Mat4.rotation(0.4, Y))
+                                    .times(Mat4.scale([0.01, 0.01, 3])).times(Mat4.rotation(PI / 2, X)),
+                                    Vec.of(0, 1, 0), 10, 4)]
+    objs = [Primitive(Plane(), PhongMaterial(Vec.of(0.3, 0.3, 0.3), 0.3, 0.4, 0.6, 100, 0.4),
+                      Mat4.translation([0, 1, 0]).times(Mat4.rotation(PI / 2, X)))]
+    st = Mat4.translation([-0.15, 1.86, -2.73]).times(Mat4.rotation(0.4, Y)).times(Mat4.scale([0.01, 0.01, 1.5]))
+    objs.append(Primitive(Sphere(), FresnelPhongMaterial(Vec.of(0, 1, 0), 0.2, 0.4, 0.5, 100, 1.3), st, Mat4.inverse(st), False))
+    tris = load_mesh("Tie_Fighter", PhongMaterial(Vec.of(1, 0, 0), 0.1, 0.4, 0.6, 100, 0.5))
+    objs.append(BVHAggregate.build(tris, Mat4.translation([-0.75, 2, -4]).times(Mat4.rotation(0.4, Y)).times(Mat4.scale(0.2))))
+    return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height)
+
+
 # tests/Aggregates/test.mjs: plain Aggregates, one nested in another, a primitive shared between them
 def Aggregates(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
     camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([-7, 0.5, 4]))
@@ -418,7 +436,7 @@ def SDF_Sierpinski(aspect=1, width=600, height=600, spp=16, depth=4, dof=None,
 
 REGISTRY = {f.__name__: f for f in (
     BoxBall, BoxBall_DOF, BoxBall_path, ASimpleScene, spheres010, refraction, refraction_path, cornell_box_path,
-    bunny, bunny_path, dragon, AHollowTetrahedron, starwars, Aggregates, dragon_grid, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
+    bunny, bunny_path, dragon, AHollowTetrahedron, starwars, tie_fighter, Aggregates, dragon_grid, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
     SDF_Sierpinski)}
 
 

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — ctypes wrapper of the CPU restatement oracle
 (oracle/oracle.cpp).  Import only from tests/, __graft_entry__.smoke() and
-bench.py's cpu_baseline / --impl reference legs.  PARITY UNPINNED (see
+bench.py's cpu_baseline / --impl reference legs.  PARITY PARTLY PINNED (see
 oracle_math.h)."""
 from __future__ import annotations
 

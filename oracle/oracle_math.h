@@ -1,10 +1,15 @@
 // TEST INFRASTRUCTURE — CPU restatement oracle of alitteneker/jsraytracer's
 // render path.  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may use anything under oracle/.
-// PARITY UNPINNED: the reference ships no golden vectors or assertions for
+// PARITY PARTLY PINNED: the reference ships no golden vectors or assertions for
 // this path and no JavaScript engine exists in this image,
-// so this restatement cannot be checked against the reference running; it is
-// pinned only by formula-level known-answer tests (tests/test_oracle_kat.py).
+// so this restatement cannot be checked against the reference running.  It is
+// pinned by (i) the reference's own committed screenshots of tests/tie_fighter
+// (camera, Plane, point-light Phong, BVH shadow rays, resolve: bit-identical on
+// 95 % and within 2 levels on 100 % of the 304 000 comparable pixels —
+// tests/test_reference_screenshot.py) and (ii) formula-level known-answer tests
+// (tests/test_oracle_kat.py).  SDF, path-tracing scatter, Fresnel, DOF and
+// area-light sampling have no reference output to compare with: UNPINNED.
 //
 // Numeric model (reference src/math.js:160 `class Vec extends Float32Array`,
 // :303 `class Mat extends Array`): vectors are f32 storage, every scalar and
