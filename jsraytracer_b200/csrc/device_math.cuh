@@ -187,8 +187,10 @@ JSRT_DEV float triangle_intersect(const Tri* __restrict__ tris, int idx, float3 
         const float inv = 1.0f / (c.w * e.w - b.w * b.w);
         const float v = (e.w * d20 - b.w * d21) * inv, w = (c.w * d21 - b.w * d20) * inv, u = 1.f - v - w;
         const float m = 1e-4f;
-        if (u > m && v > m && w > m && u < 1.f - m && v < 1.f - m && w < 1.f - m) return t;
-        if (u < -m || v < -m || w < -m || u > 1.f + m || v > 1.f + m || w > 1.f + m) return -CUDART_INF_F;
+        // (all three NaN for a sliver: both tests fail and the f64 path decides)
+        const float lo3 = fminf(fminf(u, v), w), hi3 = fmaxf(fmaxf(u, v), w);
+        if (lo3 > m && hi3 < 1.f - m) return t;
+        if (lo3 < -m || hi3 > 1.f + m) return -CUDART_INF_F;
     }
     const float3 bary = triangle_bary(tris, idx, P);
     return (bary.x >= 0.f && bary.x <= 1.f && bary.y >= 0.f && bary.y <= 1.f && bary.z >= 0.f && bary.z <= 1.f) ? t : -CUDART_INF_F;

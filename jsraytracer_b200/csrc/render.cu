@@ -39,7 +39,7 @@ struct RayQueue { float4* o; float4* d; float4* w; };
 struct ShadowQueue { float4* o; float4* d; float4* c; };
 
 // counters[0], [1]: ray queue counts (ping-pong); [2]: shadow queue count
-struct Counters { int ray[2]; int shadow; int pad; int cursor_extend; int cursor_shadow; int cursor_extend_sdf; int cursor_shadow_sdf; unsigned long long stats[24]; };
+struct Counters { int ray[2]; int shadow; int pad; int cursor_extend; int cursor_shadow; int cursor_extend_sdf; int cursor_shadow_sdf; int list_extend; int list_shadow; unsigned long long stats[24]; };
 enum { ST_PRIMARY = 0, ST_SECONDARY = 1, ST_SHADOW = 2, ST_SHADED = 3, ST_SAMPLES = 4,
        ST_NODES = 8, ST_LEAF_PRIMS = 11, ST_TOP_PRIMS = 14, ST_SDF_EVALS = 17 };   // + ray class (0 primary, 1 secondary, 2 shadow)
 
@@ -310,11 +310,11 @@ __global__ void level_end_kernel(Counters* c, int cur, int level, int next_cap, 
     c->stats[ST_SHADOW] += (unsigned long long)min(c->shadow, shadow_cap);
     c->ray[cur] = 0;
     c->shadow = 0;
-    c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0;
+    c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0; c->list_extend = 0; c->list_shadow = 0;
     if (c->ray[cur ^ 1] > next_cap) c->ray[cur ^ 1] = next_cap;
 }
 __global__ void set_count_kernel(Counters* c, int which, int n, int count_samples) {
-    c->ray[which] = n; c->ray[which ^ 1] = 0; c->shadow = 0; c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0;
+    c->ray[which] = n; c->ray[which ^ 1] = 0; c->shadow = 0; c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0; c->list_extend = 0; c->list_shadow = 0;
     if (count_samples) c->stats[ST_SAMPLES] += (unsigned long long)n;
 }
 
@@ -361,6 +361,7 @@ struct Renderer::Impl {
     float4* accum = nullptr;
     RayQueue rq[2]{}; float4* hits = nullptr; float4* shadow_hits = nullptr; ShadowQueue sq{};
     float4* sdf_normals = nullptr;
+    int2* work_list = nullptr;          // BVH work list (trace.cuh), shared by the extend and the shadow wave of a level
     Counters* counters = nullptr;
     int* overflow = nullptr;
     int ray_cap = 0, shadow_cap = 0, batch = 0;
@@ -426,7 +427,7 @@ struct Renderer::Impl {
         // depth-8 Cornell box, which runs in sub-frame batches.
         double worst = 1; for (int l = 1; l < hs.max_depth; ++l) worst *= hs.fanout;
         if (worst > 1e6) worst = 1e6;
-        const double per_sample = worst * (2.0 * 48 + 16 + (hs.sdfs.empty() ? 0 : 16) + 64.0 * std::max(1, hs.light_samples));
+        const double per_sample = worst * (2.0 * 48 + 16 + (hs.sdfs.empty() ? 0 : 16) + 72.0 * std::max(1, hs.light_samples));
         double b = (double)queue_budget / per_sample;
         // up to 16 passes per wave (JSRT_BATCH_PASSES overrides): the persistent trace kernels end with a tail of
         // long walks, so bigger waves are faster (bunny_path 1080p: 2.75 / 3.47 / 3.78 / 3.90 Grays/s at 1 / 3.2 / 8 / 16 passes)
@@ -442,8 +443,9 @@ struct Renderer::Impl {
         hits = dalloc<float4>(ray_cap);
         sq.o = dalloc<float4>(shadow_cap); sq.d = dalloc<float4>(shadow_cap); sq.c = dalloc<float4>(shadow_cap);
         shadow_hits = dalloc<float4>(shadow_cap);
+        work_list = dalloc<int2>(std::max(ray_cap, shadow_cap));
         if (!hs.sdfs.empty()) { sdf_normals = dalloc<float4>(ray_cap); CK(cudaMemsetAsync(sdf_normals, 0, (size_t)ray_cap * sizeof(float4), stream)); }
-        queue_bytes = (size_t)ray_cap * (2 * 48 + 16) + (size_t)shadow_cap * (48 + 16);
+        queue_bytes = (size_t)ray_cap * (2 * 48 + 16) + (size_t)shadow_cap * (48 + 16) + (size_t)std::max(ray_cap, shadow_cap) * 8;
 
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
         auto grid_for = [&](const void* fn) { int per = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, kBlock, 0)); return prop.multiProcessorCount * std::max(1, per); };
@@ -499,7 +501,7 @@ struct Renderer::Impl {
     template <int MODE> void launchTrace(const TraceIO& io0, bool count_work, int grid_prims) {
         TraceIO io = io0;
         const bool has_bvh = ds.n_bvh > 0, has_sdf_tops = ds.n_sdf_tops > 0;
-        io.final_pass = (has_bvh || has_sdf_tops) ? 0 : 1;
+        io.final_pass = has_sdf_tops ? 0 : 1;        // prims_wave finishes the rays that need no BVH walk unless an SDF march follows
         #define JSRT_LAUNCH(K, G, C, S) K<MODE, C, S><<<G, kBlock, 0, stream>>>(ds, io)
         if (count_work) { if (has_sdf) JSRT_LAUNCH(prims_kernel, grid_prims, true, true); else JSRT_LAUNCH(prims_kernel, grid_prims, true, false); }
         else { if (has_sdf) JSRT_LAUNCH(prims_kernel, grid_prims, false, true); else JSRT_LAUNCH(prims_kernel, grid_prims, false, false); }
@@ -521,11 +523,13 @@ struct Renderer::Impl {
     void launchExtend(int cur, bool count_work) {
         TraceIO io{}; io.o = rq[cur].o; io.d = rq[cur].d; io.hits = hits; io.count = &counters->ray[cur]; io.cap = ray_cap;
         io.cursor = &counters->cursor_extend; io.stats = counters->stats; io.aux = sdf_normals;
+        io.list = work_list; io.list_count = &counters->list_extend;
         timed(1, [&] { launchTrace<TM_EXTEND>(io, count_work, grid_extend); });
     }
     void launchShadow(bool count_work) {
         TraceIO io{}; io.o = sq.o; io.d = sq.d; io.c = sq.c; io.hits = shadow_hits; io.accum = accum; io.count = &counters->shadow; io.cap = shadow_cap;
         io.cursor = &counters->cursor_shadow; io.stats = counters->stats;
+        io.list = work_list; io.list_count = &counters->list_shadow;
         timed(3, [&] { launchTrace<TM_SHADOW>(io, count_work, grid_shadow); });
     }
 

@@ -360,6 +360,9 @@ struct Flattener {
                         }
                         r.n_layouts = 8;
                     }
+                    // the device walk uses absolute node indices (no per-tree base pointer in registers)
+                    for (int q = 0; q < r.n_layouts; ++q)
+                        for (int k = 0; k < r.node_count; ++k) out.nodes[r.first_node + q * r.node_count + k].skip += r.first_node + q * r.node_count;
                     it = tree_of.emplace(tree, r).first;
                 }
                 top.first_node = it->second.first_node; top.node_count = it->second.node_count;

@@ -62,7 +62,7 @@ struct TriShade {                 // per-vertex shading data (only read for shad
 struct BvhNode {
     float cx, cy, cz, hx;         // AABB centre, half-size x   (centre/half form: src/geometry.js:189-209)
     float hy, hz;
-    int skip;                     // next node when this subtree is done (relative to the tree's first node)
+    int skip;                     // next node when this subtree is done (absolute index into the scene's node array)
     int leaf;                     // inner: -1; leaf: (count << 24) | first placed-primitive index (relative to the aggregate's first primitive)
 };
 

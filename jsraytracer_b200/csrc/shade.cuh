@@ -27,8 +27,10 @@ JSRT_DEV float3 color_eval(const Color& c, const SurfaceData& s) {
     // CheckerboardMaterialColor.color src/materials.js:72-75 (f64: UV can be huge towards the horizon)
     const double u = s.has_uv ? (double)s.uv.x : 0.0, v = s.has_uv ? (double)s.uv.y : 0.0;
     const double a = floor(u) + floor(v);
+    // Math.fmod(a, 2) % 2 for an integer-valued a: a - floor(a / 2) * 2 is exactly 0 or 1 (NaN for an infinite a), which
+    // neither toPrecision(8) nor the second `% 2` changes
     const double m = a - floor(a * 0.5) * 2.0;
-    return (fmod(m, 2.0) < 1.0) ? f3(c.c1[0], c.c1[1], c.c1[2]) : f3(c.c2[0], c.c2[1], c.c2[2]);
+    return (m < 1.0) ? f3(c.c1[0], c.c1[1], c.c1[2]) : f3(c.c2[0], c.c2[1], c.c2[2]);
 }
 
 // Vec.cartesianToSpherical src/math.js:189-193

@@ -141,6 +141,8 @@ struct TraceIO {
     unsigned long long* stats;
     float4* __restrict__ aux;           // extend + SDF scenes: local SDF normal of the hit (xyz, w = 1) or w = 0
     int final_pass;                     // 1 if no further tracing kernel follows for this wave (the last one writes results)
+    int2* __restrict__ list;            // BVH work list: (ray index, first BVH whose root box the ray hits), written by
+    int* list_count;                    //   prims_wave with warp-aggregated appends, consumed by bvh_wave
 };
 
 JSRT_DEV void accum_add3(float4* accum, uint32_t pixel, float3 c) {
@@ -186,163 +188,214 @@ JSRT_DEV void finish_ray(const TraceIO& io, int i, const Hit& best, const float4
     }
 }
 
+// Per-ray constants of a walk through one BVHAggregate: the ray in the aggregate's space
+// (Aggregate.intersect, src/aggregates.js:15) and what the slab test needs.
+struct LocalRay {
+    float3 lo, ld, inv, sgn;      // origin, direction, 1 / direction, sign of the direction (+-1)
+    bool par;                     // some |d_i| <= 1e-7: AABB.get_intersects' parallel rule applies (src/geometry.js:194,205)
+};
+JSRT_DEV LocalRay make_local_ray(const XformReg& m, float3 o, float3 d) {
+    LocalRay r;
+    r.lo = xf_point(m, o); r.ld = xf_dir(m, d);              // ray.getTransformed(this.getInvTransform())
+    r.par = !(fabsf(r.ld.x) > 0.0000001f) || !(fabsf(r.ld.y) > 0.0000001f) || !(fabsf(r.ld.z) > 0.0000001f);
+    r.inv = f3(1.0f / r.ld.x, 1.0f / r.ld.y, 1.0f / r.ld.z);
+    r.sgn = f3(r.ld.x < 0.f ? -1.f : 1.f, r.ld.y < 0.f ? -1.f : 1.f, r.ld.z < 0.f ? -1.f : 1.f);
+    return r;
+}
+// AABB.get_intersects (src/geometry.js:189-209) + the visit condition of BVHAggregateNode.intersect (:209) for
+// a ray without parallel axes.  The reference sorts (p+h)/d and (p-h)/d per axis; which of the two is the
+// smaller is known from the sign of d, so the entry distance of an axis is (p - sgn*h) * (1/d) and the exit
+// distance (p + sgn*h) * (1/d): the same two products, no min/max.  `hi` = min(maxDistance, closest hit so far).
+JSRT_DEV bool slab_fast(const float4 n0, const float4 n1, const LocalRay& r, float minD, float hi) {
+    const float px = n0.x - r.lo.x, py = n0.y - r.lo.y, pz = n0.z - r.lo.z;
+    const float nx = fmaf(-r.sgn.x, n0.w, px) * r.inv.x, fx = fmaf(r.sgn.x, n0.w, px) * r.inv.x;
+    const float ny = fmaf(-r.sgn.y, n1.x, py) * r.inv.y, fy = fmaf(r.sgn.y, n1.x, py) * r.inv.y;
+    const float nz = fmaf(-r.sgn.z, n1.y, pz) * r.inv.z, fz = fmaf(r.sgn.z, n1.y, pz) * r.inv.z;
+    const float b0 = fmaxf(fmaxf(nx, ny), nz), b1 = fminf(fminf(fx, fy), fz);
+    return b0 <= b1 && b1 >= minD && b0 <= hi;
+}
+// the general form (parallel axes): as the reference writes it
+JSRT_DEV bool slab_general(const float4 n0, const float4 n1, const LocalRay& r, float minD, float maxD, float bound) {
+    const bool parx = !(fabsf(r.ld.x) > 0.0000001f), pary = !(fabsf(r.ld.y) > 0.0000001f), parz = !(fabsf(r.ld.z) > 0.0000001f);
+    float b0;
+    return slab_test(n0, n1, r.lo, r.inv, parx, pary, parz, minD, maxD, b0) && b0 <= bound;
+}
+JSRT_DEV bool slab_any(const float4 n0, const float4 n1, const LocalRay& r, float minD, float maxD, float bound) {
+    return r.par ? slab_general(n0, n1, r, minD, maxD, bound) : slab_fast(n0, n1, r, minD, fminf(maxD, bound));
+}
+
+// prims_wave: every top-level Primitive / plain Aggregate against every ray of the queue, one ray per thread,
+// then the root box of every BVHAggregate (the first test of BVHAggregateNode.intersect, src/aggregates.js:208-209).
+// Rays that hit no root box are finished here (most rays: 92 % of bunny_path's camera rays miss the mesh's
+// box); the others are appended to the BVH work list, compacted with a warp ballot + prefix popcount and one
+// atomicAdd per warp, so that bvh_wave only ever sees rays that walk.
 template <int MODE, bool COUNT, bool HAS_SDF>
 JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other) {
     constexpr bool ANY_HIT = (MODE == TM_SHADOW);
+    const unsigned FULL = 0xffffffffu;
     const int n = min(*io.count, io.cap);
     const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float4 o4 = io.o[i], d4 = io.d[i];
-        const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
-        float minD, maxD; bool primary;
-        ray_window<MODE>(d4, minD, maxD, primary);
-        Work* work = (COUNT && primary) ? work_primary : work_other;
+    const int n_round = (n + 31) & ~31;                // warp-uniform trip count: every lane reaches the ballot
+    const int lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        int first_bvh = -1;
         Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
-        for (int ti = 0; ti < sc.n_top; ++ti) {
-            const int4 ta = __ldg(reinterpret_cast<const int4*>(sc.tops + ti));          // kind, xform, first_prim, prim_count
-            if (ta.x == T_BVH || ta.x == T_SDF) continue;
-            float3 lo = o, ld = d;
-            if (ta.x == T_LIST) { const XformReg m = load_xform(sc.xforms, ta.y); lo = xf_point(m, o); ld = xf_dir(m, d); }   // src/aggregates.js:15
-            for (int k = 0; k < ta.w; ++k) {
-                if (COUNT) ++work->top_prims;
-                float tl = 0.f;
-                const float t = placed_prim_intersect<HAS_SDF>(sc, ta.z + k, lo, ld, minD, maxD, best.t, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
-                if (t > minD && t < maxD && t < best.t) { best.t = t; best.prim = ta.z + k; best.top = ti; best.t_lo = tl; if (ANY_HIT) break; }
+        float4 o4 = make_float4(0, 0, 0, 0);
+        if (i < n) {
+            o4 = io.o[i];
+            const float4 d4 = io.d[i];
+            const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
+            float minD, maxD; bool primary;
+            ray_window<MODE>(d4, minD, maxD, primary);
+            Work* work = (COUNT && primary) ? work_primary : work_other;
+            for (int ti = 0; ti < sc.n_top; ++ti) {
+                const int4 ta = __ldg(reinterpret_cast<const int4*>(sc.tops + ti));          // kind, xform, first_prim, prim_count
+                if (ta.x == T_BVH || ta.x == T_SDF) continue;
+                float3 lo = o, ld = d;
+                if (ta.x == T_LIST) { const XformReg m = load_xform(sc.xforms, ta.y); lo = xf_point(m, o); ld = xf_dir(m, d); }   // src/aggregates.js:15
+                for (int k = 0; k < ta.w; ++k) {
+                    if (COUNT) ++work->top_prims;
+                    float tl = 0.f;
+                    const float t = placed_prim_intersect<HAS_SDF>(sc, ta.z + k, lo, ld, minD, maxD, best.t, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
+                    if (t > minD && t < maxD && t < best.t) { best.t = t; best.prim = ta.z + k; best.top = ti; best.t_lo = tl; if (ANY_HIT) break; }
+                }
+                if (ANY_HIT && best.prim >= 0) break;
             }
-            if (ANY_HIT && best.prim >= 0) break;
+            if (!(ANY_HIT && best.prim >= 0)) {
+                for (int b = 0; b < sc.n_bvh; ++b) {
+                    const int4* tp = reinterpret_cast<const int4*>(sc.tops + __ldg(sc.bvh_tops + b));
+                    const int4 ta = __ldg(tp); const int first_node = __ldg(reinterpret_cast<const int*>(tp + 1));
+                    const LocalRay r = make_local_ray(load_xform(sc.xforms, ta.y), o, d);
+                    const float4* root = reinterpret_cast<const float4*>(sc.nodes + first_node);
+                    if (COUNT) ++work->nodes;
+                    if (slab_any(__ldg(root), __ldg(root + 1), r, minD, maxD, best.t)) { first_bvh = b; break; }
+                }
+            }
         }
-        if (io.final_pass) finish_ray<MODE>(io, i, best, o4);
-        else io.hits[i] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
+        const unsigned walkers = __ballot_sync(FULL, first_bvh >= 0);
+        if (walkers) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(io.list_count, __popc(walkers));
+            base = __shfl_sync(FULL, base, 0);
+            if (first_bvh >= 0) io.list[base + __popc(walkers & ((1u << lane) - 1u))] = make_int2(i, first_bvh);
+        }
+        if (i < n) {
+            if (io.final_pass && first_bvh < 0) finish_ray<MODE>(io, i, best, o4);
+            else io.hits[i] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
+        }
     }
 }
 
+// bvh_wave: BVHAggregateNode.intersect (src/aggregates.js:207-225) for the rays of the work list.
+// Persistent threads, one ray per lane, lanes refilled individually from a warp-local pool of list
+// entries (one atomicAdd per JSRT_POOL_BATCH rays): a lane whose walk ends takes the next ray instead of
+// idling while its neighbours finish (walk lengths differ by two orders of magnitude).
 template <int MODE, bool COUNT, bool HAS_SDF>
 JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other) {
     constexpr bool ANY_HIT = (MODE == TM_SHADOW);
-    constexpr int BATCH = JSRT_POOL_BATCH;      // ray indices fetched per atomicAdd
+    constexpr int BATCH = JSRT_POOL_BATCH;      // list entries fetched per atomicAdd
     // A warp runs three phases per iteration, each only when enough lanes need it, so that the
     // rarely-needed code (ray hand-over, leaf tests) executes with many lanes instead of one or two:
     constexpr int REFILL_T = JSRT_REFILL_T;     // finish + refill when this many lanes are idle (or nothing else is left)
     constexpr int LEAF_T = JSRT_LEAF_T;         // test postponed leaves when this many lanes hold one (or one must be flushed)
     constexpr int NODE_STEPS = JSRT_NODE_STEPS; // nodes walked per iteration between the warp votes
-    constexpr int REFILL_ROUNDS = 8;            // hand-over rounds per iteration (rays that miss every root box are replaced at once)
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int n = min(*io.count, io.cap);
+    const int n = min(*io.list_count, io.cap);
     int pool_next = 0, pool_end = 0;      // warp-uniform
     bool exhausted = false;               // warp-uniform
-
-    // per-lane ray state
-    int cur = -1;                         // ray index, -1: none
-    bool done = false;                    // walk finished, result not yet written
-    int pending = -1;                     // postponed leaf word
-    float4 o4 = make_float4(0, 0, 0, 0);
-    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), lo = o, inv = d, ld = d;
-    bool parx = false, pary = false, parz = false;
-    float minD = 0.f, maxD = CUDART_INF_F;
+    // per-lane ray state, kept small (64 registers at 4 CTAs / SM): the world-space ray is not kept — it is
+    // re-read from the queue in the rare case that a second BVH has to be entered — and node indices are
+    // absolute (scene_flatten.cpp stores absolute skip links), so no per-tree base pointer is carried.
+    int cur = -1;                         // >= 0: ray index, walking; -1: none; <= -2: ray -2 - cur has finished, result not yet written
+    int pending = -1;                     // postponed leaf word; -(leaf + 2): a second leaf is waiting behind it
+    LocalRay r; r.lo = f3(0, 0, 0); r.ld = f3(0, 0, 1); r.inv = r.ld; r.sgn = r.ld; r.par = false;
+    float minD_v = 0.f;                   // extend only (the shadow window is a constant)
+    #define JSRT_MIND ((MODE == TM_SHADOW) ? 0.0001f : minD_v)
+    #define JSRT_MAXD ((MODE == TM_SHADOW) ? 1.0f : CUDART_INF_F)
+    float hi = CUDART_INF_F;              // min(maxD, local_best, best.t): the pruning bound of :209
     Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
-    int bi = 0, top_i = 0;
+    int bi = 0;
     int node_i = 0, node_end = 0, first_prim = 0, tri_base = -1;
-    const float4* nodes = nullptr;
     float local_best = CUDART_INF_F, local_lo = 0.f; int local_prim = -1;
     Work* work = work_other;
+    const float4* const all_nodes = reinterpret_cast<const float4*>(sc.nodes);
 
     // enter BVH number `bi` of the scene (Aggregate.intersect / BVHAggregate.intersect, src/aggregates.js:43-46)
-    auto enter = [&]() {
-        top_i = __ldg(sc.bvh_tops + bi);
-        const int4* tp = reinterpret_cast<const int4*>(sc.tops + top_i);
+    auto enter = [&](float3 o, float3 d) {
+        const int4* tp = reinterpret_cast<const int4*>(sc.tops + __ldg(sc.bvh_tops + bi));
         const int4 ta = __ldg(tp), tb = __ldg(tp + 1);      // kind, xform, first_prim, prim_count | first_node, node_count, tri_base, n_layouts
-        const XformReg m = load_xform(sc.xforms, ta.y);
-        lo = xf_point(m, o); ld = xf_dir(m, d);              // ray.getTransformed(this.getInvTransform())
-        // AABB.get_intersects treats |d_i| <= 1e-7 as parallel (src/geometry.js:194,205); otherwise the slab
-        // distances are (p_i +- h_i) / d_i, evaluated here as a product with the reciprocal
-        parx = !(fabsf(ld.x) > 0.0000001f); pary = !(fabsf(ld.y) > 0.0000001f); parz = !(fabsf(ld.z) > 0.0000001f);
-        inv = f3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
-        const int octant = (tb.w == 8) ? ((ld.x < 0.f ? 1 : 0) | (ld.y < 0.f ? 2 : 0) | (ld.z < 0.f ? 4 : 0)) : 0;
-        nodes = reinterpret_cast<const float4*>(sc.nodes + tb.x + octant * tb.y);
-        node_i = 0; node_end = tb.y; first_prim = ta.z; tri_base = tb.z;
+        r = make_local_ray(load_xform(sc.xforms, ta.y), o, d);
+        const int octant = (tb.w == 8) ? ((r.ld.x < 0.f ? 1 : 0) | (r.ld.y < 0.f ? 2 : 0) | (r.ld.z < 0.f ? 4 : 0)) : 0;
+        node_i = tb.x + octant * tb.y; node_end = node_i + tb.y; first_prim = ta.z; tri_base = tb.z;
         local_best = CUDART_INF_F; local_prim = -1; local_lo = 0.f; pending = -1;
+        hi = fminf(JSRT_MAXD, best.t);
     };
 
     for (;;) {
         // ---- phase 1: write finished rays, hand out new ones ------------------------------
-        // A new ray is tested against its tree's root box right here, and a ray that misses every root is
-        // finished and replaced in the next round of this loop: most rays miss the mesh altogether (92 % of
-        // bunny_path's camera rays), and they should not occupy a lane of the node loop for one step each.
-        bool all_out = false;
-        #pragma unroll 1
-        for (int round = 0; round < REFILL_ROUNDS; ++round) {
-            const unsigned idle_mask = __ballot_sync(FULL, cur < 0 || done);
+        {
+            const unsigned idle_mask = __ballot_sync(FULL, cur < 0);
             const int n_idle = __popc(idle_mask);
-            if (!(n_idle >= REFILL_T || idle_mask == FULL)) break;
-            if (cur >= 0 && done) {
-                if (io.final_pass) finish_ray<MODE>(io, cur, best, o4);
-                else io.hits[cur] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
-                cur = -1; done = false;
-            }
-            if (pool_next >= pool_end && !exhausted) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(io.cursor, BATCH);
-                base = __shfl_sync(FULL, base, 0);
-                pool_next = base; pool_end = min(base + BATCH, n);
-                if (base >= n) { exhausted = true; pool_next = pool_end = 0; }
-            }
-            const int avail = pool_end - pool_next;
-            if (avail <= 0) { all_out = exhausted && __all_sync(FULL, cur < 0); break; }
-            const int rank = __popc(idle_mask & ((1u << lane) - 1u));
-            if (cur < 0 && rank < avail) {
-                cur = pool_next + rank;
-                o4 = io.o[cur];
-                const float4 d4 = io.d[cur], h4 = io.hits[cur];
-                o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z);
-                bool primary;
-                ray_window<MODE>(d4, minD, maxD, primary);
-                if (COUNT) work = primary ? work_primary : work_other;
-                best.t = h4.x; best.prim = __float_as_int(h4.y); best.top = __float_as_int(h4.z); best.t_lo = h4.w;
-                bi = 0;
-                if (ANY_HIT && best.prim >= 0) cur = -1;        // already occluded by a top-level primitive: nothing to do or write
+            if (n_idle >= REFILL_T || idle_mask == FULL) {
+                if (cur < -1) {
+                    const int ray = -2 - cur;
+                    if (io.final_pass) finish_ray<MODE>(io, ray, best, io.o[ray]);
+                    else io.hits[ray] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
+                    cur = -1;
+                }
+                if (pool_next >= pool_end && !exhausted) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(io.cursor, BATCH);
+                    base = __shfl_sync(FULL, base, 0);
+                    pool_next = base; pool_end = min(base + BATCH, n);
+                    if (base >= n) { exhausted = true; pool_next = pool_end = 0; }
+                }
+                const int avail = pool_end - pool_next;
+                if (avail <= 0) { if (exhausted && __all_sync(FULL, cur < 0)) break; }
                 else {
-                    // skip the trees whose root box the ray misses (the first test of BVHAggregateNode.intersect, :208-209)
-                    for (;;) {
-                        enter();
-                        const float4 n0 = __ldg(nodes), n1 = __ldg(nodes + 1);
-                        float b0;
-                        if (COUNT) ++work->nodes;
-                        if (slab_test(n0, n1, lo, inv, parx, pary, parz, minD, maxD, b0) && b0 <= best.t) {
-                            if (__float_as_int(n1.w) == -1) node_i = 1;      // inner root: its test is done
-                            break;
+                    const int rank = __popc(idle_mask & ((1u << lane) - 1u));
+                    if (rank < avail) {             // only idle lanes have a rank that is meaningful: cur < 0 here for them
+                        if (cur < 0) {
+                            const int2 e = __ldg(reinterpret_cast<const int2*>(io.list) + pool_next + rank);
+                            cur = e.x; bi = e.y;
+                            const float4 o4 = io.o[cur], d4 = io.d[cur], h4 = io.hits[cur];
+                            bool primary; float mx;
+                            ray_window<MODE>(d4, minD_v, mx, primary);
+                            if (COUNT) work = primary ? work_primary : work_other;
+                            best.t = h4.x; best.prim = __float_as_int(h4.y); best.top = __float_as_int(h4.z); best.t_lo = h4.w;
+                            enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
+                            // prims_wave has tested this tree's root box; an inner root needs no second test
+                            if (__float_as_int(__ldg(all_nodes + 2 * node_i + 1).w) == -1) ++node_i;
                         }
-                        if (++bi >= sc.n_bvh) { done = true; break; }
                     }
+                    pool_next += min(avail, n_idle);
                 }
             }
-            pool_next += min(avail, n_idle);
         }
-        if (all_out) break;
-        const bool active = cur >= 0 && !done;
+        const bool active = cur >= 0;
 
         // ---- phase 2: postponed leaf tests (src/aggregates.js:211-218) -------------------------
         // A lane that reaches a leaf parks it and keeps walking; the leaf is tested when enough
         // lanes hold one, when the lane reaches its next leaf, or when its walk ends.  Testing later
         // only delays the `ret.distance` update that prunes the walk; the result is the same.
-        const bool walk_over = node_i >= node_end;
         const unsigned pend_mask = __ballot_sync(FULL, active && pending != -1);
-        const bool must = active && pending != -1 && (walk_over || pending < -1);
+        const bool must = active && pending != -1 && (node_i >= node_end || pending < -1);
         if (pend_mask && (__popc(pend_mask) >= LEAF_T || __any_sync(FULL, must))) {
             if (active && pending != -1) {
                 const int leaf = (pending < -1) ? -(pending + 2) : pending;      // a blocked lane stores -(leaf + 2)
                 const int cnt = (int)((unsigned)leaf >> 24), rel = leaf & 0xffffff;
-                const float bound = fminf(local_best, best.t);
                 for (int k = 0; k < cnt; ++k) {
                     if (COUNT) ++work->leaf_prims;
                     const int pi = first_prim + rel + k;
                     float tl = 0.f, t;
-                    if (tri_base >= 0) t = triangle_intersect(sc.tris, tri_base + rel + k, lo, ld, minD, fminf(maxD, bound));
-                    else t = placed_prim_intersect<HAS_SDF>(sc, pi, lo, ld, minD, maxD, bound, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
+                    if (tri_base >= 0) t = triangle_intersect(sc.tris, tri_base + rel + k, r.lo, r.ld, JSRT_MIND, hi);
+                    else t = placed_prim_intersect<HAS_SDF>(sc, pi, r.lo, r.ld, JSRT_MIND, JSRT_MAXD, hi, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
                     // :213 with the rank tie rule (see the header comment)
-                    if (t > minD && t < maxD && (t < local_best || (t == local_best && pi < local_prim))) { local_best = t; local_prim = pi; local_lo = tl; }
+                    if (t > JSRT_MIND && t < JSRT_MAXD && (t < local_best || (t == local_best && pi < local_prim))) { local_best = t; local_prim = pi; local_lo = tl; }
                 }
                 pending = -1;
+                hi = fminf(hi, local_best);
                 if (ANY_HIT && local_prim >= 0) node_i = node_end;
             }
         }
@@ -350,33 +403,22 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
         if (active) {
             if (node_i >= node_end && pending == -1) {
                 // ---- tree finished: merge into the running closest hit, next BVH or done -------
-                if (local_best > minD && local_best < maxD && better_hit(local_best, top_i, best)) {
+                const int top_i = __ldg(sc.bvh_tops + bi);
+                if (local_best > JSRT_MIND && local_best < JSRT_MAXD && better_hit(local_best, top_i, best)) {
                     best.t = local_best; best.prim = local_prim; best.top = top_i; best.t_lo = local_lo;
                 }
                 ++bi;
-                if (bi >= sc.n_bvh || (ANY_HIT && best.prim >= 0)) done = true;
-                else enter();
+                if (bi >= sc.n_bvh || (ANY_HIT && best.prim >= 0)) cur = -2 - cur;
+                else { const float4 o4 = io.o[cur], d4 = io.d[cur]; enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z)); }
             } else {
                 // ---- phase 3: up to NODE_STEPS nodes of BVHAggregateNode.intersect (src/aggregates.js:207-225)
                 // per iteration, so the warp votes of phases 1-2 are paid once per few nodes
                 #pragma unroll 1
                 for (int rep = 0; rep < NODE_STEPS && node_i < node_end && pending >= -1; ++rep) {
-                    const float4 n0 = __ldg(nodes + 2 * node_i), n1 = __ldg(nodes + 2 * node_i + 1);
+                    const float4 n0 = __ldg(all_nodes + 2 * node_i), n1 = __ldg(all_nodes + 2 * node_i + 1);
                     const int skip = __float_as_int(n1.z), leaf = __float_as_int(n1.w);
                     if (COUNT) ++work->nodes;
-                    const float bound = fminf(local_best, best.t);
-                    // AABB.get_intersects (src/geometry.js:189-209); the per-axis early returns are equivalent to one
-                    // final test because t_min only grows and t_max only shrinks
-                    const float px = n0.x - lo.x, py = n0.y - lo.y, pz = n0.z - lo.z;
-                    const float ax = (px + n0.w) * inv.x, bx = (px - n0.w) * inv.x;
-                    const float ay = (py + n1.x) * inv.y, by = (py - n1.x) * inv.y;
-                    const float az = (pz + n1.y) * inv.z, bz = (pz - n1.y) * inv.z;
-                    float b0 = -CUDART_INF_F, b1 = CUDART_INF_F;
-                    bool miss = false;
-                    if (parx) miss = fabsf(px) > n0.w; else { b0 = fminf(ax, bx); b1 = fmaxf(ax, bx); }
-                    if (pary) miss = miss || fabsf(py) > n1.x; else { b0 = fmaxf(b0, fminf(ay, by)); b1 = fminf(b1, fmaxf(ay, by)); }
-                    if (parz) miss = miss || fabsf(pz) > n1.y; else { b0 = fmaxf(b0, fminf(az, bz)); b1 = fminf(b1, fmaxf(az, bz)); }
-                    const bool hit_box = !miss && !(b0 > b1) && !(b1 < minD) && !(b0 > maxD) && b0 <= bound;    // + :209
+                    const bool hit_box = r.par ? slab_general(n0, n1, r, JSRT_MIND, JSRT_MAXD, hi) : slab_fast(n0, n1, r, JSRT_MIND, hi);
                     if (hit_box) {
                         if (leaf != -1) {
                             if (pending == -1) { pending = leaf; node_i = skip; }
@@ -387,6 +429,8 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
             }
         }
     }
+    #undef JSRT_MIND
+    #undef JSRT_MAXD
 }
 
 // ---------------------------------------------------------------------------------
