@@ -31,6 +31,9 @@ namespace jsrt {
 namespace {
 
 constexpr int kBlock = 256;
+#ifndef JSRT_SHADE_SORT
+#define JSRT_SHADE_SORT 1
+#endif
 #ifndef JSRT_BVH_MIN_BLOCKS
 #define JSRT_BVH_MIN_BLOCKS 4      // 64 registers: 4 CTAs / SM (measured against 3 and 5: profiles/r1_ncu_summary.md)
 #endif
@@ -157,9 +160,52 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : 3) shade_kernel(const __
                                                         unsigned long long seed, unsigned long long* stats, int* overflow, const float4* __restrict__ sdf_normals) {
     const int n = *count;
     const int stride = gridDim.x * blockDim.x;
-    const int n_round = (n + 31) & ~31;      // warp-uniform trip count: every lane reaches the ballots
     unsigned long long my_shaded = 0;
+#if JSRT_SHADE_SORT
+    // Shading sorted by material: the kBlock rays of a tile are permuted inside the CTA by a counting sort on
+    // (miss | material index) before they are shaded, so that a warp runs one material's code path instead of
+    // the union of its 32 rays' paths (profiles/: 18 of 32 threads active per instruction without it at the
+    // deeper levels).  The permutation stays inside a 4 KB window of each queue array, so the loads still hit
+    // whole sectors.  Results do not depend on the order (the RNG is keyed by pixel / pass / path node).
+    __shared__ int s_hist[64], s_off[64];
+    __shared__ unsigned short s_perm[kBlock];
+    if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int tile = blockIdx.x * blockDim.x; tile < n; tile += stride) {
+        int i;
+        {
+            const int j = tile + threadIdx.x, lane_s = threadIdx.x & 31;
+            int key = 63;
+            if (j < n) {
+                const int prim = __float_as_int(hits[j].y);
+                key = prim < 0 ? 0 : min(1 + __ldg(&sc.prims[prim].material), 62);
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane_s == leader) base = atomicAdd(&s_hist[key], __popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader) + __popc(peers & ((1u << lane_s) - 1u));
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                const int v0 = s_hist[lane_s], v1 = s_hist[lane_s + 32];
+                int a = v0, b = v1;
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int ta = __shfl_up_sync(0xffffffffu, a, off), tb = __shfl_up_sync(0xffffffffu, b, off);
+                    if (lane_s >= off) { a += ta; b += tb; }
+                }
+                const int total0 = __shfl_sync(0xffffffffu, a, 31);
+                s_off[lane_s] = a - v0; s_off[lane_s + 32] = total0 + b - v1;
+                s_hist[lane_s] = 0; s_hist[lane_s + 32] = 0;
+            }
+            __syncthreads();
+            s_perm[s_off[key] + base] = (unsigned short)threadIdx.x;
+            __syncthreads();
+            i = tile + s_perm[threadIdx.x];
+        }
+#else
+    const int n_round = (n + 31) & ~31;      // warp-uniform trip count: every lane reaches the ballots
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+#endif
         const bool active = i < n;
         bool hit = false;
         uint32_t pixel = 0, node = 0; int depth_rem = 0, pass = 0;
@@ -458,6 +504,11 @@ struct Renderer::Impl {
         grid_sdf = grid_for((const void*)sdf_kernel<TM_EXTEND, false>);
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
         CK(cudaStreamSynchronize(stream));
+        if (getenv("JSRT_DEBUG_PTRS"))
+            fprintf(stderr, "jsrt ptrs: tops %p prims %p xforms %p nodes %p tris %p tri_shade %p materials %p lights %p bvh_tops %p accum %p counters %p rq0 %p %p %p rq1 %p %p %p hits %p sq %p %p %p shits %p list %p\n",
+                    (void*)ds.tops, (void*)ds.prims, (void*)ds.xforms, (void*)ds.nodes, (void*)ds.tris, (void*)ds.tri_shade, (void*)ds.materials, (void*)ds.lights, (void*)ds.bvh_tops,
+                    (void*)accum, (void*)counters, (void*)rq[0].o, (void*)rq[0].d, (void*)rq[0].w, (void*)rq[1].o, (void*)rq[1].d, (void*)rq[1].w, (void*)hits, (void*)sq.o, (void*)sq.d, (void*)sq.c,
+                    (void*)shadow_hits, (void*)work_list);
     }
 
     ~Impl() {

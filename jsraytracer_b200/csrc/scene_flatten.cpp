@@ -224,6 +224,51 @@ struct Flattener {
     }
 
     // ---- BVH layout in reference visit order (src/aggregates.js:207-225) ------------
+    // Number of objects below node `n` if they are all Triangles and there are at most `cap` of them, else cap + 1.
+    int smallTriSubtree(const Val* n, int cap) {
+        n = doc.resolve(n);
+        if (doc.truthy(doc.field(n, "isLeaf"))) {
+            const Val* objs = doc.field(n, "objects");
+            const uint32_t cnt = objs ? doc.length(objs) : 0;
+            if ((int)cnt > cap) return cap + 1;
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const Val* p = doc.resolve(doc.at(objs, i));
+                if (doc.typeName(p) != "Primitive" || doc.typeName(doc.field(p, "geometry")) != "Triangle") return cap + 1;
+            }
+            return (int)cnt;
+        }
+        const int g = smallTriSubtree(doc.field(n, "greater_node"), cap);
+        if (g > cap) return cap + 1;
+        const int l = smallTriSubtree(doc.field(n, "lesser_node"), cap - g);
+        return (g + l > cap) ? cap + 1 : g + l;
+    }
+    // the objects below `n` in the reference's visit order (greater child first)
+    void placeSubtree(const Val* n) {
+        n = doc.resolve(n);
+        if (doc.truthy(doc.field(n, "isLeaf"))) {
+            const Val* objs = doc.field(n, "objects");
+            const uint32_t cnt = objs ? doc.length(objs) : 0;
+            for (uint32_t i = 0; i < cnt; ++i) placePrim(doc.at(objs, i), nullptr);
+        } else {
+            placeSubtree(doc.field(n, "greater_node"));
+            placeSubtree(doc.field(n, "lesser_node"));
+        }
+    }
+    // The reference's leaves hold one object each (src/aggregates.js:66,87-89), so half of its nodes are boxes
+    // around single triangles.  A subtree with at most `leaf_tris` triangles is emitted as ONE leaf (its root's
+    // box, its triangles in visit order): the walk tests those few triangles directly instead of first walking
+    // 2k-1 more boxes.  Same hits (every triangle the reference would test is still tested, ties still go to the
+    // earlier-visited one); fewer dependent node fetches.  JSRT_LEAF_TRIS=1 keeps the reference topology.
+    int leaf_tris = 2;                 // measured: profiles/r1_ab.md (2 is the best of 1..8 on bunny_path, dragon and starwars)
+    int collapsed_nodes = 0;           // reference nodes folded into multi-triangle leaves
+    void refStats(const Val* n, int depth) {
+        n = doc.resolve(n);
+        if (depth > out.max_bvh_depth) out.max_bvh_depth = depth;
+        if (doc.truthy(doc.field(n, "isLeaf"))) return;
+        collapsed_nodes += 2;
+        refStats(doc.field(n, "greater_node"), depth + 1);
+        refStats(doc.field(n, "lesser_node"), depth + 1);
+    }
     void layoutNode(const Val* n, int first_node, int first_prim, int depth) {
         n = doc.resolve(n);
         if (depth > out.max_bvh_depth) out.max_bvh_depth = depth;
@@ -235,13 +280,14 @@ struct Flattener {
         b.cx = (float)c[0]; b.cy = (float)c[1]; b.cz = (float)c[2]; b.hx = (float)h[0]; b.hy = (float)h[1]; b.hz = (float)h[2];
         b.leaf = -1;
         out.nodes.push_back(b);
-        if (doc.truthy(doc.field(n, "isLeaf"))) {
-            const Val* objs = doc.field(n, "objects");
-            const uint32_t cnt = objs ? doc.length(objs) : 0;
-            if (cnt > 127) fail("jsrt: BVH leaf with more than 127 objects");
+        const bool is_leaf = doc.truthy(doc.field(n, "isLeaf"));
+        if (is_leaf || (leaf_tris > 1 && smallTriSubtree(n, leaf_tris) <= leaf_tris)) {
             const int first = (int)out.prims.size() - first_prim;
             if (first >= (1 << 24)) fail("jsrt: more than 16M primitives in one BVH");
-            for (uint32_t i = 0; i < cnt; ++i) placePrim(doc.at(objs, i), nullptr);
+            placeSubtree(n);
+            if (!is_leaf) refStats(n, depth);          // Info.n_nodes / max_bvh_depth keep describing the reference's tree
+            const uint32_t cnt = (uint32_t)((int)out.prims.size() - first_prim - first);
+            if (cnt > 127) fail("jsrt: BVH leaf with more than 127 objects");
             out.nodes[me].leaf = (int)((cnt << 24) | (uint32_t)first);
         } else {
             layoutNode(doc.field(n, "greater_node"), first_node, first_prim, depth + 1);
@@ -285,6 +331,7 @@ struct Flattener {
     }
 
     void run() {
+        if (const char* e = getenv("JSRT_LEAF_TRIS")) { const int v = atoi(e); if (v >= 1 && v <= 64) leaf_tris = v; }
         const Val* root = doc.resolve(doc.root());
         const Val* rend = doc.field(root, "renderer");
         if (!rend) fail("jsrt: scene blob has no 'renderer' (expected Serializer({renderer,width,height}))");
@@ -336,6 +383,7 @@ struct Flattener {
                 if (it == tree_of.end()) {
                     TreeRef r{(int)out.nodes.size(), 0, (int)out.prims.size(), 0, -1, 1};
                     const int first_tri = (int)out.tris.size();
+                    collapsed_nodes = 0;
                     layoutNode(tree, r.first_node, r.first_prim, 0);
                     r.node_count = (int)out.nodes.size() - r.first_node;
                     r.prim_count = (int)out.prims.size() - r.first_prim;
@@ -346,7 +394,7 @@ struct Flattener {
                         pure = p.geom_kind == G_TRIANGLE && p.geom_index == first_tri + k && (p.flags & PF_IDENTITY_XFORM) && (p.flags & PF_CASTS_SHADOW);
                     }
                     r.tri_base = pure ? first_tri : -1;
-                    out.tree_node_count += r.node_count;
+                    out.tree_node_count += r.node_count + collapsed_nodes; collapsed_nodes = 0;
                     // optional: eight octant layouts replacing the reference-order one (JSRT_OCTANT_LAYOUTS=1).
                     // Measured on bunny_path / dragon at 1080p the reference order is as fast or faster: most rays
                     // miss the mesh, and a miss visits the same nodes in any order, while 8 layouts cost L1 hits.

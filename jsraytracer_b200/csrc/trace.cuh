@@ -121,6 +121,12 @@ JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, floa
 #ifndef JSRT_LEAF_T
 #define JSRT_LEAF_T 16
 #endif
+#ifndef JSRT_PROG_T
+#define JSRT_PROG_T 33     // > 32: parked leaves are tested after every round of node steps (measured best: profiles/r2_ab.md)
+#endif
+#ifndef JSRT_NODE_LDG256
+#define JSRT_NODE_LDG256 0
+#endif
 #ifndef JSRT_POOL_BATCH
 #define JSRT_POOL_BATCH 64
 #endif
@@ -286,6 +292,16 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_pr
     }
 }
 
+// One 32-byte node: two 128-bit loads, or (JSRT_NODE_LDG256) one 256-bit load (sm_100: LDG.E.256).
+JSRT_DEV void load_node(const float4* p, float4& a, float4& b) {
+#if JSRT_NODE_LDG256
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+    a = __ldg(p); b = __ldg(p + 1);
+#endif
+}
+
 // bvh_wave: BVHAggregateNode.intersect (src/aggregates.js:207-225) for the rays of the work list.
 // Persistent threads, one ray per lane, lanes refilled individually from a warp-local pool of list
 // entries (one atomicAdd per JSRT_POOL_BATCH rays): a lane whose walk ends takes the next ray instead of
@@ -299,6 +315,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     constexpr int REFILL_T = JSRT_REFILL_T;     // finish + refill when this many lanes are idle (or nothing else is left)
     constexpr int LEAF_T = JSRT_LEAF_T;         // test postponed leaves when this many lanes hold one (or one must be flushed)
     constexpr int NODE_STEPS = JSRT_NODE_STEPS; // nodes walked per iteration between the warp votes
+    constexpr int PROG_T = JSRT_PROG_T;         // ... or when fewer than this many lanes can still walk
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int n = min(*io.list_count, io.cap);
@@ -379,20 +396,33 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
         // A lane that reaches a leaf parks it and keeps walking; the leaf is tested when enough
         // lanes hold one, when the lane reaches its next leaf, or when its walk ends.  Testing later
         // only delays the `ret.distance` update that prunes the walk; the result is the same.
+        // Policy: run the leaf phase when LEAF_T lanes hold a leaf, or when fewer than PROG_T lanes could still
+        // walk (the others are parked, blocked or idle): a blocked or finished lane waits for company instead of
+        // dragging the whole warp through the triangle code with a handful of lanes.
         const unsigned pend_mask = __ballot_sync(FULL, active && pending != -1);
-        const bool must = active && pending != -1 && (node_i >= node_end || pending < -1);
-        if (pend_mask && (__popc(pend_mask) >= LEAF_T || __any_sync(FULL, must))) {
+        const unsigned prog_mask = __ballot_sync(FULL, active && node_i < node_end && pending >= -1);
+        if (pend_mask && (__popc(pend_mask) >= LEAF_T || __popc(prog_mask) < PROG_T)) {
             if (active && pending != -1) {
                 const int leaf = (pending < -1) ? -(pending + 2) : pending;      // a blocked lane stores -(leaf + 2)
                 const int cnt = (int)((unsigned)leaf >> 24), rel = leaf & 0xffffff;
-                for (int k = 0; k < cnt; ++k) {
-                    if (COUNT) ++work->leaf_prims;
-                    const int pi = first_prim + rel + k;
-                    float tl = 0.f, t;
-                    if (tri_base >= 0) t = triangle_intersect(sc.tris, tri_base + rel + k, r.lo, r.ld, JSRT_MIND, hi);
-                    else t = placed_prim_intersect<HAS_SDF>(sc, pi, r.lo, r.ld, JSRT_MIND, JSRT_MAXD, hi, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
-                    // :213 with the rank tie rule (see the header comment)
-                    if (t > JSRT_MIND && t < JSRT_MAXD && (t < local_best || (t == local_best && pi < local_prim))) { local_best = t; local_prim = pi; local_lo = tl; }
+                // (two loops, so that the compiler cannot hoist the general primitives' ray setup in front of the
+                // triangle path: it did, 140 instructions with 25 FP64 ones per leaf — profiles/r2_ncu_summary.md)
+                if (tri_base >= 0) {
+                    for (int k = 0; k < cnt; ++k) {
+                        if (COUNT) ++work->leaf_prims;
+                        const int pi = first_prim + rel + k;
+                        const float t = triangle_intersect(sc.tris, tri_base + rel + k, r.lo, r.ld, JSRT_MIND, hi);
+                        // :213 with the rank tie rule (see the header comment)
+                        if (t > JSRT_MIND && t < JSRT_MAXD && (t < local_best || (t == local_best && pi < local_prim))) { local_best = t; local_prim = pi; local_lo = 0.f; }
+                    }
+                } else {
+                    for (int k = 0; k < cnt; ++k) {
+                        if (COUNT) ++work->leaf_prims;
+                        const int pi = first_prim + rel + k;
+                        float tl = 0.f;
+                        const float t = placed_prim_intersect<HAS_SDF>(sc, pi, r.lo, r.ld, JSRT_MIND, JSRT_MAXD, hi, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
+                        if (t > JSRT_MIND && t < JSRT_MAXD && (t < local_best || (t == local_best && pi < local_prim))) { local_best = t; local_prim = pi; local_lo = tl; }
+                    }
                 }
                 pending = -1;
                 hi = fminf(hi, local_best);
@@ -415,7 +445,8 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 // per iteration, so the warp votes of phases 1-2 are paid once per few nodes
                 #pragma unroll 1
                 for (int rep = 0; rep < NODE_STEPS && node_i < node_end && pending >= -1; ++rep) {
-                    const float4 n0 = __ldg(all_nodes + 2 * node_i), n1 = __ldg(all_nodes + 2 * node_i + 1);
+                    float4 n0, n1;
+                    load_node(all_nodes + 2 * node_i, n0, n1);
                     const int skip = __float_as_int(n1.z), leaf = __float_as_int(n1.w);
                     if (COUNT) ++work->nodes;
                     const bool hit_box = r.par ? slab_general(n0, n1, r, JSRT_MIND, JSRT_MAXD, hi) : slab_fast(n0, n1, r, JSRT_MIND, hi);
