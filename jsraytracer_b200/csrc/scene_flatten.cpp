@@ -395,10 +395,13 @@ struct Flattener {
                     }
                     r.tri_base = pure ? first_tri : -1;
                     out.tree_node_count += r.node_count + collapsed_nodes; collapsed_nodes = 0;
-                    // optional: eight octant layouts replacing the reference-order one (JSRT_OCTANT_LAYOUTS=1).
-                    // Measured on bunny_path / dragon at 1080p the reference order is as fast or faster: most rays
-                    // miss the mesh, and a miss visits the same nodes in any order, while 8 layouts cost L1 hits.
-                    if (r.node_count > 1 && getenv("JSRT_OCTANT_LAYOUTS")) {
+                    // Eight octant layouts (closest-hit rays use the layout of their direction octant, shadow rays layout 7,
+                    // which is the reference's greater-child-first order).  Pays on big meshes (dragon 1080p: extend 11.9 -> 9.8 ms per 16
+                    // passes); on small ones the reference order is as good and 8 layouts only cost L1 hits (bunny:
+                    // 10.6 -> 10.8 ms).  Default: trees with >= 32768 nodes; JSRT_OCTANT_LAYOUTS=0/1 forces it.
+                    bool octants = r.node_count >= 32768;
+                    if (const char* e = getenv("JSRT_OCTANT_LAYOUTS")) octants = atoi(e) != 0;
+                    if (r.node_count > 1 && octants) {
                         const std::vector<BvhNode> ref(out.nodes.begin() + r.first_node, out.nodes.end());
                         out.nodes.resize(r.first_node);
                         for (int q = 0; q < 8; ++q) {

@@ -124,6 +124,9 @@ JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, floa
 #ifndef JSRT_PROG_T
 #define JSRT_PROG_T 33     // > 32: parked leaves are tested after every round of node steps (measured best: profiles/r2_ab.md)
 #endif
+#ifndef JSRT_NODE_PREFETCH
+#define JSRT_NODE_PREFETCH 0
+#endif
 #ifndef JSRT_NODE_LDG256
 #define JSRT_NODE_LDG256 0
 #endif
@@ -343,7 +346,10 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
         const int4* tp = reinterpret_cast<const int4*>(sc.tops + __ldg(sc.bvh_tops + bi));
         const int4 ta = __ldg(tp), tb = __ldg(tp + 1);      // kind, xform, first_prim, prim_count | first_node, node_count, tri_base, n_layouts
         r = make_local_ray(load_xform(sc.xforms, ta.y), o, d);
-        const int octant = (tb.w == 8) ? ((r.ld.x < 0.f ? 1 : 0) | (r.ld.y < 0.f ? 2 : 0) | (r.ld.z < 0.f ? 4 : 0)) : 0;
+        // closest-hit rays pick the layout that visits the nearer child first; any-hit (shadow) rays gain nothing from
+        // it (measured: +18 % nodes per shadow ray on bunny_path) and keep the reference order
+        // (layout 7 = higher child first on every axis = the reference's greater-child-first order)
+        const int octant = (tb.w != 8) ? 0 : ANY_HIT ? 7 : ((r.ld.x < 0.f ? 1 : 0) | (r.ld.y < 0.f ? 2 : 0) | (r.ld.z < 0.f ? 4 : 0));
         node_i = tb.x + octant * tb.y; node_end = node_i + tb.y; first_prim = ta.z; tri_base = tb.z;
         local_best = CUDART_INF_F; local_prim = -1; local_lo = 0.f; pending = -1;
         hi = fminf(JSRT_MAXD, best.t);
@@ -447,7 +453,13 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 for (int rep = 0; rep < NODE_STEPS && node_i < node_end && pending >= -1; ++rep) {
                     float4 n0, n1;
                     load_node(all_nodes + 2 * node_i, n0, n1);
+#if JSRT_NODE_PREFETCH & 1
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(all_nodes + 2 * node_i + 2));      // the hit successor
+#endif
                     const int skip = __float_as_int(n1.z), leaf = __float_as_int(n1.w);
+#if JSRT_NODE_PREFETCH & 2
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(all_nodes + 2 * skip));            // the miss successor
+#endif
                     if (COUNT) ++work->nodes;
                     const bool hit_box = r.par ? slab_general(n0, n1, r, JSRT_MIND, JSRT_MAXD, hi) : slab_fast(n0, n1, r, JSRT_MIND, hi);
                     if (hit_box) {
