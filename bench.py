@@ -231,9 +231,22 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
+    # ---- CPU baseline beside it (bounded sample, rank 0, N = 1 only) --------------------------
+    # The same oracle run supplies the ALGORITHMIC work per ray for the roofline ("defined by
+    # the reference algorithm on the reference-built BVH, counted by the oracle").
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpasses = args.cpu_passes
+        crays, cdt, threads, ocnt = cpu_reference_run(ser, args, cpasses)
+        cpu = {"value": crays / cdt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+               "sample": "%d full-frame passes of the same workload on the C++ restatement oracle (%.1f s)" % (cpasses, cdt)}
+    else:
+        _, _, _, ocnt = cpu_reference_run(ser, args, 1)       # counts only (one pass, untimed leg)
+
     # ---- roofline of the dominant kernel --------------------------------------------------
-    # Algorithmic bytes: 32 B per BVH node visited + 36 B per triangle
-    # tested, counted by an instrumented (untimed) pass of the same workload.
+    # Algorithmic bytes per ray = 32 B per BVH node the REFERENCE algorithm visits + 36 B per triangle it tests
+    # (oracle counters, per ray class).  The device's own walk (collapsed leaves, octant order) visits fewer nodes
+    # and tests more triangles; its counters (an instrumented, untimed pass) are reported beside it.
     scene.stats_reset()
     scene.render(1 << 20, 1, seed=1, flags=lib.FLAG_COUNT_WORK)
     cw = scene.stats()
@@ -241,23 +254,35 @@ def run_ours(args):
     kern_n = {"generate": st["n_generate"], "extend": st["n_extend"], "shade": st["n_shade"], "shadow": st["n_shadow"]}
     dominant = max(("extend", "shadow"), key=lambda k: kern_ms[k])
     if dominant == "extend":
-        rays_c = cw["rays_primary"] + cw["rays_secondary"]
-        bytes_c = 32 * (cw["bvh_nodes"][0] + cw["bvh_nodes"][1]) + 36 * (cw["bvh_prims"][0] + cw["bvh_prims"][1])
+        o_rays = ocnt["rays_primary"] + ocnt["rays_secondary"]
+        o_nodes = ocnt["bvh_nodes_primary"] + ocnt["bvh_nodes_secondary"]
+        o_prims = ocnt["bvh_prims_primary"] + ocnt["bvh_prims_secondary"]
+        d_rays = cw["rays_primary"] + cw["rays_secondary"]
+        d_nodes, d_prims = cw["bvh_nodes"][0] + cw["bvh_nodes"][1], cw["bvh_prims"][0] + cw["bvh_prims"][1]
         rays_t = st["rays_primary"] + st["rays_secondary"]
     else:
-        rays_c = cw["rays_shadow"]
-        bytes_c = 32 * cw["bvh_nodes"][2] + 36 * cw["bvh_prims"][2]
+        o_rays, o_nodes, o_prims = ocnt["rays_shadow"], ocnt["bvh_nodes_shadow"], ocnt["bvh_prims_shadow"]
+        d_rays, d_nodes, d_prims = cw["rays_shadow"], cw["bvh_nodes"][2], cw["bvh_prims"][2]
         rays_t = st["rays_shadow"]
-    bytes_per_ray = bytes_c / max(1, rays_c)
+    nodes_per_ray, prims_per_ray = o_nodes / max(1, o_rays), o_prims / max(1, o_rays)
+    bytes_per_ray = 32 * nodes_per_ray + 36 * prims_per_ray
+    flops_per_ray = 27 * nodes_per_ray + 40 * prims_per_ray
     avg_ms = kern_ms[dominant] / max(1, kern_n[dominant])
-    bytes_per_launch = bytes_per_ray * rays_t / max(1, kern_n[dominant])
-    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    rays_per_launch = rays_t / max(1, kern_n[dominant])
+    achieved = bytes_per_ray * rays_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12            # SMs x FP32 lanes x 2 (FMA) x max SM clock, TFLOP/s
+    # the scene is L2-resident, so the memory-side ceiling that can bind the walk is L2, measured here on this box
+    # (SURVEY.md §8d): 128-bit reads of a 32 MB buffer from every SM
+    try:
+        l2_gbs = lib.measure_read_bandwidth(local, 32 << 20, 200)
+    except Exception:
+        l2_gbs = None
     kernel_name = {"extend": "bvh_kernel<extend> (+ prims_kernel<extend>)", "shadow": "bvh_kernel<shadow> (+ prims_kernel<shadow>)"}[dominant]
     traffic = None
     try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
@@ -268,17 +293,16 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_t / max(1, kern_n[dominant]), "avg_launch_ms": avg_ms,
+                "bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_ms,
+                "algorithmic_work": {"source": "oracle counters (reference algorithm, reference-built BVH)",
+                                     "nodes_per_ray": nodes_per_ray, "tris_per_ray": prims_per_ray,
+                                     "device_nodes_per_ray": d_nodes / max(1, d_rays), "device_tris_per_ray": d_prims / max(1, d_rays)},
+                "l2": {"measured_read_gbs": l2_gbs, "frac": (achieved / l2_gbs) if l2_gbs else None,
+                       "note": "algorithmic bytes / measured L2 read bandwidth (32 MB buffer, all SMs): the ceiling that applies to an L2-resident scene"},
+                "fp32": {"flops_per_ray": flops_per_ray, "achieved_tflops": flops_per_ray * rays_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0,
+                         "peak_tflops": fp32_peak, "note": "the HBM-side ceiling (peak / bytes_per_ray) is the lower of the two, so bound = hbm"},
                 "kernel_ms": kern_ms, "kernel_launches": kern_n,
-                "note": "scene (%.1f MB) is L2-resident: the kernel is latency/issue bound, not HBM bound; see DESIGN.md" % (info["scene_bytes"] / 1e6)}
-
-    # ---- CPU baseline beside it (bounded sample, rank 0, N = 1 only) --------------------------
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpasses = args.cpu_passes
-        crays, cdt, threads, _ = cpu_reference_run(ser, args, cpasses)
-        cpu = {"value": crays / cdt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-               "sample": "%d full-frame passes of the same workload on the C++ restatement oracle (%.1f s)" % (cpasses, cdt)}
+                "note": "scene (%.1f MB) is L1/L2-resident, so its algorithmic bytes never reach HBM and frac (of the HBM peak) can exceed 1; the l2 fraction is the meaningful one; the kernel is latency/issue bound, see DESIGN.md" % (info["scene_bytes"] / 1e6)}
 
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -135,6 +135,13 @@ int jsrt_set_profiling(jsrt_scene*, int on);
 
 const char* jsrt_last_error(void);
 
+/* Measurement helper for the traversal roofline (the config scenes are L2-resident, so the
+ * memory-side ceiling that binds the trace kernels is L2 bandwidth, "which the builder must measure on the box"):
+ * reads a `bytes`-sized device buffer `iters` times with 128-bit loads from every SM (after one untimed pass)
+ * and stores the achieved read bandwidth in GB/s.  bytes <= ~64 MB stays L2-resident; a multi-GB buffer
+ * measures HBM instead. */
+int jsrt_measure_read_bandwidth(int device, size_t bytes, int iters, double* gb_per_s);
+
 /* ---- scene-build helper (host only) --------------------
  * BVHAggregateNode.build / split_objects (src/aggregates.js:65-185) over n
  * object boxes given as the reference stores them (centre, half_size, min, max;

@@ -107,4 +107,13 @@ int jsrt_stats_get(jsrt_scene* s, jsrt_stats* o) {
 int jsrt_stats_reset(jsrt_scene* s) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->resetStats()) }
 int jsrt_set_profiling(jsrt_scene* s, int on) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->setProfiling(on != 0)) }
 
+int jsrt_measure_read_bandwidth(int device, size_t bytes, int iters, double* gb_per_s) {
+    try {
+        if (jsrt::deviceCount() < 1) throw std::runtime_error("jsrt: no CUDA device");
+        if (!gb_per_s || bytes < 4096 || iters < 1) throw std::runtime_error("jsrt: bad arguments");
+        *gb_per_s = jsrt::measureReadBandwidth(device, bytes, iters);
+        return 0;
+    } catch (const std::exception& e) { return failWith(e); }
+}
+
 }  // extern "C"

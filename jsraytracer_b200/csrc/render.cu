@@ -696,6 +696,34 @@ int Renderer::batchSamples() const { return impl_->batch; }
 size_t Renderer::sceneBytes() const { return impl_->scene_bytes; }
 size_t Renderer::queueBytes() const { return impl_->queue_bytes; }
 
+__global__ void __launch_bounds__(256) read_bw_kernel(const float4* __restrict__ buf, size_t n, int iters, float4* sink) {
+    float4 acc = make_float4(0, 0, 0, 0);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; ++it)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const float4 v = buf[i]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    if (acc.x == 1234567.f) *sink = acc;      // never true: keeps the loads alive
+}
+double measureReadBandwidth(int device, size_t bytes, int iters) {
+    CK(cudaSetDevice(device));
+    const size_t n = bytes / sizeof(float4);
+    float4 *buf = nullptr, *sink = nullptr;
+    CK(cudaMalloc(&buf, n * sizeof(float4))); CK(cudaMalloc(&sink, sizeof(float4)));
+    CK(cudaMemset(buf, 0, n * sizeof(float4)));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 8;
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    read_bw_kernel<<<grid, 256>>>(buf, n, 1, sink);                  // warm: brings the buffer into L2
+    CK(cudaEventRecord(a));
+    read_bw_kernel<<<grid, 256>>>(buf, n, iters, sink);
+    CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(buf); cudaFree(sink);
+    CK(cudaGetLastError());
+    return (double)n * sizeof(float4) * iters / (ms * 1e-3) / 1e9;
+}
+
 int deviceCount() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 
 }  // namespace jsrt

@@ -44,5 +44,6 @@ private:
 };
 
 int deviceCount();
+double measureReadBandwidth(int device, size_t bytes, int iters);
 
 }  // namespace jsrt

@@ -63,7 +63,7 @@ EXPORTS = [
     "jsrt_scene_set_stream", "jsrt_render", "jsrt_reset_accum", "jsrt_synchronize", "jsrt_resolve_rgba8",
     "jsrt_read_accum", "jsrt_accum_device_ptr", "jsrt_add_passes", "jsrt_primary_hits", "jsrt_scene_info",
     "jsrt_stats_get", "jsrt_stats_reset", "jsrt_set_profiling", "jsrt_last_error", "jsrt_bvh_build",
-    "jsrt_bvh_node_count", "jsrt_bvh_leaf_object_count", "jsrt_bvh_copy", "jsrt_bvh_free",
+    "jsrt_bvh_node_count", "jsrt_bvh_leaf_object_count", "jsrt_bvh_copy", "jsrt_bvh_free", "jsrt_measure_read_bandwidth",
 ]
 
 
@@ -107,12 +107,21 @@ def load():
     L.jsrt_bvh_copy.argtypes = [vp, vp, vp]
     L.jsrt_bvh_free.argtypes = [vp]
     L.jsrt_bvh_free.restype = None
+    L.jsrt_measure_read_bandwidth.argtypes = [i32, sz, i32, vp]
     _LIB = L
     return L
 
 
 def last_error():
     return load().jsrt_last_error().decode("utf8", "replace")
+
+
+def measure_read_bandwidth(device=0, nbytes=32 << 20, iters=200):
+    """GB/s of 128-bit reads over an `nbytes` device buffer (L2-resident when small): the measured L2 ceiling."""
+    out = C.c_double()
+    if load().jsrt_measure_read_bandwidth(device, nbytes, iters, C.byref(out)):
+        raise JsrtError(last_error())
+    return out.value
 
 
 def device_count():
