@@ -24,6 +24,8 @@ struct HostScene {
     std::vector<TriShade> tri_shade;    // parallel to tris when any triangle has vertex data, else empty
     std::vector<float> boxes;           // 8 floats per non-unit AABB geometry: centre xyz_, half xyz_
     std::vector<Material> materials;
+    std::vector<Texture> textures;
+    std::vector<unsigned char> texels;  // RGBA8, all textures back to back (16-byte aligned starts)
     std::vector<Light> lights;
     std::vector<SdfProgram> sdfs;
     std::vector<SdfInstr> sdf_code;

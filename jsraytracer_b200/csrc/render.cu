@@ -258,14 +258,19 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : 3) shade_kernel(const __
                 s.normal = normalized3(xf_normal(inv, ln));
                 s.position = ray_point_f64(o, d, td);
                 mat = sc.materials + pa.z;
+                if (mat->uv_from_position) {          // PositionalUVMaterial.color src/materials.js:188-192
+                    const float dx = (float)dsub(mat->uv_origin[0], s.position.x), dy = (float)dsub(mat->uv_origin[1], s.position.y), dz = (float)dsub(mat->uv_origin[2], s.position.z);
+                    s.uv = make_float2((float)ddot3(mat->u_axis[0], mat->u_axis[1], mat->u_axis[2], dx, dy, dz), (float)ddot3(mat->v_axis[0], mat->v_axis[1], mat->v_axis[2], dx, dy, dz));
+                    s.has_uv = true;
+                }
                 node_key = rng_node_key(rng_sample_key(seed, pixel, (uint32_t)pass), node);
                 if (mat->kind == M_SOLID) {
-                    accum_add(accum, pixel, thr * color_eval(mat->ambient, s));
+                    accum_add(accum, pixel, thr * color_eval(sc, mat->ambient, s));
                     hit = false;                 // no lights, no children (src/materials.js:153-155)
                 } else if (mat->kind == M_TRANSPARENT) {
-                    accum_add(accum, pixel, thr * (color_eval(mat->ambient, s) * mat->smoothness));
+                    accum_add(accum, pixel, thr * (color_eval(sc, mat->ambient, s) * mat->smoothness));
                 } else {
-                    base_factors(*mat, s, d, f);
+                    base_factors(sc, *mat, s, d, f);
                     accum_add(accum, pixel, thr * f.ambient);      // `let ret = data.ambient`
                 }
             }
@@ -276,8 +281,8 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : 3) shade_kernel(const __
         bool want0 = false, want1 = false; float3 dir0 = f3(0, 0, 1), dir1 = f3(0, 0, 1), w0 = f3(0, 0, 0), w1 = f3(0, 0, 0);
         if (hit && depth_rem - 1 > 0) {
             if (mat->kind == M_PHONG) {
-                if (dot3(f.reflectivity, f.reflectivity) > 0.f) { want0 = true; dir0 = f.R; w0 = thr * f.reflectivity; }
-                if (dot3(f.transmissivity, f.transmissivity) > 0.f) { want1 = true; dir1 = normalized3(d); w1 = thr * f.transmissivity; }
+                if (dot3(f.reflectivity, f.reflectivity) + f.refl_alpha * f.refl_alpha > 0.f) { want0 = true; dir0 = f.R; w0 = thr * f.reflectivity; }
+                if (dot3(f.transmissivity, f.transmissivity) + f.trans_alpha * f.trans_alpha > 0.f) { want1 = true; dir1 = normalized3(d); w1 = thr * f.transmissivity; }
             } else if (mat->kind == M_TRANSPARENT) {
                 want0 = true; dir0 = d; w0 = thr * (1.f - mat->smoothness);
             } else {
@@ -432,6 +437,7 @@ struct Renderer::Impl {
         ds.tops = up(hs.tops); ds.prims = up(hs.prims); ds.xforms = up(hs.xforms); ds.xforms64 = up(hs.xforms64); ds.nodes = up(hs.nodes);
         ds.tris = up(hs.tris); ds.tri_shade = up(hs.tri_shade); ds.boxes = up(hs.boxes); ds.materials = up(hs.materials);
         ds.lights = up(hs.lights); ds.sdfs = up(hs.sdfs); ds.sdf_code = up(hs.sdf_code);
+        ds.textures = up(hs.textures); ds.texels = up(hs.texels);
         ds.bvh_tops = up(bvh_tops_host); ds.n_bvh = (int)bvh_tops_host.size();
         sdf_tops_host.clear();
         for (size_t i = 0; i < hs.tops.size(); ++i) if (hs.tops[i].kind == T_SDF) sdf_tops_host.push_back((int)i);

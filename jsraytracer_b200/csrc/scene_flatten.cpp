@@ -19,7 +19,7 @@ static const double kInf = std::numeric_limits<double>::infinity();
 
 namespace {
 
-struct Folded { float c1[3]; float c2[3]; bool checker; };
+struct Folded { float c1[3]; float c2[3]; bool checker; int tex = -1; float alpha_scale = 1.f; };
 
 struct Flattener {
     const WireDoc& doc;
@@ -66,22 +66,65 @@ struct Flattener {
             else if (s) doc.vec(s, sv, kInf);
             // `_mc.color(data).times(_scale)`: f64 product of the f32 colour, stored f32
             for (int i = 0; i < 3; ++i) { f.c1[i] = (float)((double)f.c1[i] * sv[i]); f.c2[i] = (float)((double)f.c2[i] * sv[i]); }
+            // a texture colour is RGBA: a number also scales alpha, an array leaves alpha * undefined = NaN
+            if (f.tex >= 0) f.alpha_scale = (s && (s->type == Val::NUM || s->type == Val::NIL)) ? (float)((double)f.alpha_scale * sv[0]) : NAN;
         } else if (t == "CheckerboardMaterialColor") {
             // Nested checkerboards see the same UV, so the outer predicate selects
             // the same side of the inner one.
             Folded a = fold(doc.field(mc, "color1")), b = fold(doc.field(mc, "color2"));
+            if (a.tex >= 0 || b.tex >= 0) fail("jsrt: a TextureMaterialColor inside a CheckerboardMaterialColor is not supported");
             for (int i = 0; i < 3; ++i) { f.c1[i] = a.c1[i]; f.c2[i] = b.checker ? b.c2[i] : b.c1[i]; }
             f.checker = true;
         } else if (t == "TextureMaterialColor") {
-            fail("jsrt: TextureMaterialColor (src/materials.js:77-131) is not supported yet (SURVEY.md §8f item 2)");
+            f.tex = texture(mc);
+            for (int i = 0; i < 3; ++i) f.c1[i] = f.c2[i] = 1.f;
         } else fail("jsrt: unknown MaterialColor type '" + t + "'");
         return f;
     }
     static Color toColor(const Folded& f) {
         Color c{}; for (int i = 0; i < 3; ++i) { c.c1[i] = f.c1[i]; c.c2[i] = f.checker ? f.c2[i] : f.c1[i]; }
-        c.checker = f.checker ? 1 : 0; return c;
+        c.checker = f.checker ? CK_CHECKER : CK_SOLID;
+        if (f.tex >= 0) { c.checker = CK_TEXTURE; c.tex = f.tex; c.c2[0] = f.alpha_scale; }
+        return c;
     }
-    static bool nonzero(const Color& c) { for (int i = 0; i < 3; ++i) if (c.c1[i] != 0 || c.c2[i] != 0) return true; return false; }
+    // may `color(data).squarednorm() > 0` hold?  (a texture's alpha counts: src/materials.js:277,284)
+    static bool nonzero(const Color& c) { if (c.checker == CK_TEXTURE) return true; for (int i = 0; i < 3; ++i) if (c.c1[i] != 0 || c.c2[i] != 0) return true; return false; }
+
+    // TextureMaterialColor -> texture table entry; `_imgdata` = {width, height, data} with data a msgpack bin or an
+    // array of numbers (the wire form of ImageData is defined by this repo's glue, see jsraytracer_b200/materials.py)
+    std::unordered_map<const Val*, int> texture_of;
+    int texture(const Val* mc) {
+        auto it = texture_of.find(mc);
+        if (it != texture_of.end()) return it->second;
+        const Val* img = doc.field(mc, "_imgdata");
+        if (!img) fail("jsrt: TextureMaterialColor without _imgdata");
+        Texture t{};
+        t.width = (int)doc.number(doc.field(img, "width"), 0); t.height = (int)doc.number(doc.field(img, "height"), 0);
+        if (t.width <= 0 || t.height <= 0) fail("jsrt: TextureMaterialColor with an empty image (a browser ImageData serialises empty: SURVEY.md §8b)");
+        const size_t nbytes = (size_t)t.width * t.height * 4;
+        while (out.texels.size() % 16) out.texels.push_back(0);
+        t.offset = out.texels.size();
+        const Val* data = doc.payload(doc.field(img, "data"));
+        if (!data) fail("jsrt: TextureMaterialColor: _imgdata.data is missing");
+        if (data->type == Val::STR) {
+            if (data->count != nbytes) fail("jsrt: TextureMaterialColor: _imgdata.data must hold width*height*4 bytes");
+            out.texels.insert(out.texels.end(), (const unsigned char*)data->str, (const unsigned char*)data->str + nbytes);
+        } else if (data->type == Val::ARR) {
+            if (doc.length(data) != nbytes) fail("jsrt: TextureMaterialColor: _imgdata.data must hold width*height*4 numbers");
+            for (uint32_t i = 0; i < nbytes; ++i) out.texels.push_back((unsigned char)doc.number(doc.at(data, i), 0));
+        } else fail("jsrt: TextureMaterialColor: unsupported _imgdata.data encoding");
+        const Val* mode = doc.payload(doc.field(mc, "mode"));
+        if (mode && mode->type == Val::STR) {
+            const std::string m(mode->str, mode->count);
+            if (m == "nearest") t.flags |= TF_NEAREST;
+            else if (m != "bilinear") fail("jsrt: Unsupported texture mode " + m);       // src/materials.js:119
+        }
+        const Val* cu = doc.field(mc, "clampU"); const Val* cv = doc.field(mc, "clampV");
+        if (!cu || doc.truthy(cu)) t.flags |= TF_CLAMP_U;
+        if (!cv || doc.truthy(cv)) t.flags |= TF_CLAMP_V;
+        out.textures.push_back(t);
+        return texture_of[mc] = (int)out.textures.size() - 1;
+    }
 
     int material(const Val* m) {
         m = doc.resolve(m);
@@ -108,6 +151,15 @@ struct Flattener {
         } else if (t == "TransparentMaterial") {
             d.kind = M_TRANSPARENT; d.ambient = toColor(fold(doc.field(m, "_color")));
             d.smoothness = (float)doc.number(doc.field(m, "_opacity"), 1);
+        } else if (t == "PositionalUVMaterial") {
+            // the innermost PositionalUVMaterial of a chain wins (each overwrites data.UV before calling its base)
+            d = out.materials[material(doc.field(m, "baseMaterial"))];
+            if (!d.uv_from_position) {
+                d.uv_from_position = 1;
+                double o[4] = {0, 0, 0, 0}, u[4] = {1, 0, 0, 0}, v[4] = {0, 0, 1, 0};
+                doc.vec(doc.field(m, "origin"), o); doc.vec(doc.field(m, "u_axis"), u); doc.vec(doc.field(m, "v_axis"), v);
+                for (int i = 0; i < 3; ++i) { d.uv_origin[i] = (float)o[i]; d.u_axis[i] = (float)u[i]; d.v_axis[i] = (float)v[i]; }
+            }
         } else fail("jsrt: unsupported material type '" + t + "'");
         out.materials.push_back(d);
         return material_of[m] = (int)out.materials.size() - 1;

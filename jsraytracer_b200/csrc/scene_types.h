@@ -78,12 +78,22 @@ struct Top {                      // one entry of world.objects (src/world.js:7-
     int n_layouts;                // 8: one node layout per ray-direction octant (near child first); 1: reference order only
 };
 
-struct Color {                    // a MaterialColor folded to Solid or Checkerboard (src/materials.js:27-76)
-    float c1[3];
-    int checker;
-    float c2[3];
-    int pad;
+struct Color {                    // a MaterialColor folded to Solid, Checkerboard or scaled Texture (src/materials.js:27-131)
+    float c1[3];                  // solid colour / checker colour 1 / texture: the folded ScaledMaterialColor factor
+    int checker;                  // ColorKind
+    float c2[3];                  // checker colour 2; texture: c2[0] = factor applied to alpha (NaN after an array scale)
+    int tex;                      // texture index
 };
+enum ColorKind : int { CK_SOLID = 0, CK_CHECKER = 1, CK_TEXTURE = 2 };
+
+struct Texture {                  // TextureMaterialColor (src/materials.js:77-131): RGBA8 texels in `texels` at `offset`
+    int width, height;
+    int flags;                    // TextureFlags
+    int pad;
+    unsigned long long offset;    // byte offset of texel (0, 0)
+    unsigned long long pad2;
+};
+enum TextureFlags : int { TF_NEAREST = 1, TF_CLAMP_U = 2, TF_CLAMP_V = 4 };
 
 struct Material {                 // src/materials.js:145-476
     int kind;                     // MatKind
@@ -91,6 +101,11 @@ struct Material {                 // src/materials.js:145-476
     float ior;                    // refractiveIndexRatio (may be +Inf)
     float mirror_prob;
     Color ambient, diffusivity, specularity, reflectivity, transmissivity;   // M_SOLID/M_TRANSPARENT: colour in `ambient`, opacity in `smoothness`
+    // PositionalUVMaterial (src/materials.js:178-193) folded into its base material: UV = (u_axis . delta, v_axis . delta),
+    // delta = origin - position
+    int uv_from_position;
+    float uv_origin[3], u_axis[3], v_axis[3];
+    int pad[2];
 };
 
 struct Light {                    // src/lights.js

@@ -22,8 +22,48 @@ struct SurfaceData {           // the `data` object of materials.js
     float3 basecolor;          // SDF only; (1,1,1) otherwise
 };
 
-JSRT_DEV float3 color_eval(const Color& c, const SurfaceData& s) {
-    if (!c.checker) return f3(c.c1[0], c.c1[1], c.c1[2]);
+// TextureMaterialColor.color (src/materials.js:101-130) in the reference's arithmetic: f64 weights and sums, the
+// result stored as an f32 RGBA vector, then the folded ScaledMaterialColor factor.  `alpha` (optional) receives
+// the fourth component, which only matters where the reference takes squarednorm() of a colour (:277,284).
+JSRT_DEV double tex_normalize_uv(double c, bool clamp) {
+    if (clamp) return (c != c) ? c : fmin(fmax(c, 0.0), 1.0);
+    return fmod(fmod(c, 1.0) + 1.0, 1.0);
+}
+// (noinline, scalar arguments: the rare texture path must not cost the common path registers or a stack frame)
+__device__ __noinline__ float4 texture_eval(const Texture* __restrict__ textures, const unsigned char* __restrict__ texels, int tex_index,
+                                            float u, float v, float sr, float sg, float sb, float sa) {
+    const Texture t = textures[tex_index];
+    const double U = tex_normalize_uv((double)u, t.flags & TF_CLAMP_U), V = tex_normalize_uv((double)v, t.flags & TF_CLAMP_V);
+    const double fx = dsub(dmul(U, (double)t.width), 0.5), fy = dsub(dmul(dsub(1.0, V), (double)t.height), 0.5);
+    double xs[2], wx[2], ys[2], wy[2]; int n = 2;
+    if (t.flags & TF_NEAREST) { xs[0] = floor(fx + 0.5); wx[0] = 1.0; ys[0] = floor(fy + 0.5); wy[0] = 1.0; xs[1] = xs[0]; ys[1] = ys[0]; wx[1] = wy[1] = 0.0; n = 1; }
+    else {
+        xs[0] = floor(fx); xs[1] = xs[0] + 1.0; wx[1] = fmod(fx, 1.0); wx[0] = dsub(1.0, wx[1]);
+        ys[0] = floor(fy); ys[1] = ys[0] + 1.0; wy[1] = fmod(fy, 1.0); wy[0] = dsub(1.0, wy[1]);
+    }
+    double r[4] = {0.0, 0.0, 0.0, 0.0};
+    const uchar4* tex = reinterpret_cast<const uchar4*>(texels + t.offset);
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            const double cy = fmin(fmax(ys[b], 0.0), (double)(t.height - 1)), cx = fmin(fmax(xs[a], 0.0), (double)(t.width - 1));
+            const long long index = (long long)(cy * (double)t.width + cx);
+            const uchar4 p = (cx == cx && cy == cy) ? tex[index] : make_uchar4(0, 0, 0, 0);
+            const double w = dmul(wx[a], wy[b]);
+            r[0] = dadd(r[0], dmul(w, (double)p.x / 255.0)); r[1] = dadd(r[1], dmul(w, (double)p.y / 255.0));
+            r[2] = dadd(r[2], dmul(w, (double)p.z / 255.0)); r[3] = dadd(r[3], dmul(w, (double)p.w / 255.0));
+        }
+    return make_float4((float)((double)(float)r[0] * (double)sr), (float)((double)(float)r[1] * (double)sg), (float)((double)(float)r[2] * (double)sb),
+                       (float)((double)(float)r[3] * (double)sa));
+}
+
+JSRT_DEV float3 color_eval(const DeviceScene& sc, const Color& c, const SurfaceData& s, float* alpha = nullptr) {
+    if (alpha) *alpha = 0.f;
+    if (c.checker == CK_SOLID) return f3(c.c1[0], c.c1[1], c.c1[2]);
+    if (c.checker == CK_TEXTURE) {
+        const float4 t = texture_eval(sc.textures, sc.texels, c.tex, s.has_uv ? s.uv.x : 0.f, s.has_uv ? s.uv.y : 0.f, c.c1[0], c.c1[1], c.c1[2], c.c2[0]);
+        if (alpha) *alpha = t.w;
+        return f3(t.x, t.y, t.z);
+    }
     // CheckerboardMaterialColor.color src/materials.js:72-75 (f64: UV can be huge towards the horizon)
     const double u = s.has_uv ? (double)s.uv.x : 0.0, v = s.has_uv ? (double)s.uv.y : 0.0;
     const double a = floor(u) + floor(v);
@@ -192,18 +232,19 @@ struct PhongFactors {          // PhongMaterial.getBaseFactors src/materials.js:
     float3 ambient, diffusivity, specularity, reflectivity, transmissivity;
     float smoothness;
     float kr; bool has_refr; float3 refr;
+    float refl_alpha, trans_alpha;      // texture colours are RGBA: alpha takes part in the reference's `squarednorm() > 0` tests
 };
 
-JSRT_DEV void base_factors(const Material& m, const SurfaceData& s, float3 ray_dir, PhongFactors& f) {
+JSRT_DEV void base_factors(const DeviceScene& sc, const Material& m, const SurfaceData& s, float3 ray_dir, PhongFactors& f) {
     f.V = normalized3(ray_dir) * -1.f;
     f.N = normalized3(s.normal); f.backside = false; f.vdotn = dot3(f.V, f.N);
     if (f.vdotn < 0.f) { f.N = f.N * -1.f; f.backside = true; f.vdotn = -f.vdotn; }
     f.R = normalized3(f.N * (2.f * f.vdotn) - f.V);
-    f.ambient = s.basecolor * color_eval(m.ambient, s);
-    f.diffusivity = s.basecolor * color_eval(m.diffusivity, s);
-    f.specularity = color_eval(m.specularity, s);
-    f.reflectivity = color_eval(m.reflectivity, s);
-    f.transmissivity = color_eval(m.transmissivity, s);
+    f.ambient = s.basecolor * color_eval(sc, m.ambient, s);
+    f.diffusivity = s.basecolor * color_eval(sc, m.diffusivity, s);
+    f.specularity = color_eval(sc, m.specularity, s);
+    f.reflectivity = color_eval(sc, m.reflectivity, s, &f.refl_alpha);
+    f.transmissivity = color_eval(sc, m.transmissivity, s, &f.trans_alpha);
     f.smoothness = m.smoothness;
     f.kr = 1.f; f.has_refr = false; f.refr = f3(0.f, 0.f, 0.f);
     if (m.kind == M_FRESNEL || m.kind == M_PATH) {

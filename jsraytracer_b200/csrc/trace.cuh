@@ -22,6 +22,8 @@ struct DeviceScene {
     const SdfInstr* sdf_code;
     const int* bvh_tops;       // indices of the T_BVH entries of `tops`
     const int* sdf_tops;       // indices of the T_SDF entries of `tops`
+    const Texture* textures;   // TextureMaterialColor table + RGBA8 texels
+    const unsigned char* texels;
     int n_sdf_tops, pad0, pad1, pad2;
     int n_top, n_lights, light_samples, max_depth;
     float bg[3];

@@ -56,8 +56,57 @@ class CheckerboardMaterialColor(MaterialColor):  # src/materials.js:63-76
         self.color2 = MaterialColor.coerce(color2)
 
 
+class ImageData(JSObject):
+    """Stand-in for the browser `ImageData` a TextureMaterialColor holds (`context.getImageData`,
+    src/materials.js:91-96): width, height and RGBA8 `data`.  The reference's serializer writes a browser
+    ImageData as an empty object (its fields are prototype getters — SURVEY.md §8b hazard 2), so the wire form is
+    defined by this glue: `{width, height, data}` with `data` a msgpack bin / JSON array of w*h*4 bytes."""
+    JS_NAME = "ImageData"
+
+    def __init__(self, width, height, data):
+        data = bytes(data)
+        if len(data) != width * height * 4:
+            raise ValueError("ImageData: data must hold width*height*4 bytes")
+        self.width, self.height, self.data = int(width), int(height), data
+
+    @staticmethod
+    def from_array(rgba):
+        """(H, W, 4) uint8 array -> ImageData."""
+        h, w, c = rgba.shape
+        if c != 4:
+            raise ValueError("ImageData.from_array: need RGBA")
+        return ImageData(w, h, rgba.astype("uint8").tobytes())
+
+    def serialize(self, ser):
+        return {"width": self.width, "height": self.height, "data": self.data}
+
+
+class TextureMaterialColor(MaterialColor):  # src/materials.js:77-131
+    JS_NAME = "TextureMaterialColor"
+
+    def __init__(self, imgdata, mode="bilinear", clampU=True, clampV=True):
+        if mode not in ("bilinear", "nearest"):
+            raise ValueError("Unsupported texture mode " + str(mode))          # src/materials.js:119
+        self._imgdata = imgdata
+        self.width = imgdata.width
+        self.height = imgdata.height
+        self.mode = mode
+        self.clampU = clampU
+        self.clampV = clampV
+
+
 class Material(JSObject):
     pass
+
+
+class PositionalUVMaterial(Material):  # src/materials.js:178-193
+    JS_NAME = "PositionalUVMaterial"
+
+    def __init__(self, baseMaterial, origin=None, u_axis=None, v_axis=None):
+        self.baseMaterial = baseMaterial
+        self.origin = origin if origin is not None else Vec.of(0, 0, 0)
+        self.u_axis = u_axis if u_axis is not None else Vec.of(1, 0, 0)
+        self.v_axis = v_axis if v_axis is not None else Vec.of(0, 0, 1)
 
 
 class SolidColorMaterial(Material):  # src/materials.js:145-156

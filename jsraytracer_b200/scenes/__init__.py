@@ -22,7 +22,8 @@ from ..sdf import (SDFGeometry, UnionSDF, IntersectionSDF, DifferenceSDF, Smooth
                    RecursiveTransformUnionSDF, SDFTransformerSequence, SDFRecursiveTransformer,
                    SDFMatrixTransformer, SDFReflectionTransformer, SDFInfiniteRepetitionTransformer)
 from ..materials import (CheckerboardMaterialColor, PhongMaterial, FresnelPhongMaterial, PhongPathTracingMaterial,
-                         SimplePointLight, RandomSampleAreaLight)
+                         SimplePointLight, RandomSampleAreaLight, ImageData, TextureMaterialColor, ScaledMaterialColor,
+                         PositionalUVMaterial, SolidColorMaterial)
 from ..world import World, Primitive, Aggregate, BVHAggregate
 from ..cameras import PerspectiveCamera, DepthOfFieldPerspectiveCamera
 from ..renderers import SimpleRenderer, IncrementalMultisamplingRenderer
@@ -318,6 +319,35 @@ def tie_fighter(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=I
     return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height)
 
 
+# Not a reference scene: exercises TextureMaterialColor (bilinear / nearest, clamp / wrap, scaled like the OBJ loader's
+# map_Kd * Kd: src/objloader.js:1-7,11) and PositionalUVMaterial on the BoxBall layout with a procedural RGBA texture.
+def procedural_texture(w=16, h=8):
+    import numpy as np
+    y, x = np.mgrid[0:h, 0:w]
+    rgba = np.zeros((h, w, 4), dtype=np.uint8)
+    rgba[..., 0] = (x * 255) // max(1, w - 1)
+    rgba[..., 1] = (y * 255) // max(1, h - 1)
+    rgba[..., 2] = ((x ^ y) & 1) * 200 + 30
+    rgba[..., 3] = 255
+    return ImageData.from_array(rgba)
+
+
+def textured(aspect=1, width=600, height=600, spp=4, depth=3, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = _make_camera(_boxball_camera_transform(), aspect, None)
+    img = procedural_texture()
+    bil = TextureMaterialColor(img, "bilinear", True, True)
+    wrap = TextureMaterialColor(img, "nearest", False, False)
+    floor_mat = PositionalUVMaterial(PhongMaterial(ScaledMaterialColor(wrap, [0.9, 0.8, 1.0]), 0.2, 0.6, 0.3, 20, 0.2),
+                                     Vec.of(0.25, 0, 0.5), Vec.of(0.31, 0, 0.05), Vec.of(-0.04, 0, 0.27))
+    objs = [
+        Primitive(Plane(), floor_mat, Mat4.translation([0, -1, 0]).times(Mat4.rotation(PI / 2, Vec.of(1, 0, 0)))),
+        Primitive(Sphere(), PhongMaterial(bil, 0.3, 0.7, 0.4, 40, 0.1), Mat4.translation([-2.5, 0.2, -4]).times(Mat4.scale(1.2))),
+        Primitive(Square(), PhongMaterial(ScaledMaterialColor(bil, 0.8), 0.4, 0.6), Mat4.translation([-1.0, 0.3, -6]).times(Mat4.scale(3))),
+        Primitive(UnitBox(), SolidColorMaterial(wrap), Mat4.translation([-4.5, -0.5, -2.0])),
+    ]
+    return _finish(objs, _point_light_default(), camera, renderer_cls, spp, depth, width, height)
+
+
 # tests/Aggregates/test.mjs: plain Aggregates, one nested in another, a primitive shared between them
 def Aggregates(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
     camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([-7, 0.5, 4]))
@@ -436,7 +466,7 @@ def SDF_Sierpinski(aspect=1, width=600, height=600, spp=16, depth=4, dof=None,
 
 REGISTRY = {f.__name__: f for f in (
     BoxBall, BoxBall_DOF, BoxBall_path, ASimpleScene, spheres010, refraction, refraction_path, cornell_box_path,
-    bunny, bunny_path, dragon, AHollowTetrahedron, starwars, tie_fighter, Aggregates, dragon_grid, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
+    bunny, bunny_path, dragon, AHollowTetrahedron, starwars, tie_fighter, textured, Aggregates, dragon_grid, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
     SDF_Sierpinski)}
 
 

@@ -33,7 +33,7 @@ class Serializer:
 
     # src/serializer.js:12-60
     def serialize_step(self, obj):
-        if obj is None or isinstance(obj, (bool, int, float, str)):
+        if obj is None or isinstance(obj, (bool, int, float, str, bytes)):      # bytes: RGBA texels (ImageData.data)
             return obj
         key = id(obj)
         rid = self._ids.get(key)
@@ -83,8 +83,8 @@ class Serializer:
         `-Infinity` / `NaN` tokens, which both readers in this repo accept and
         which lose nothing (IOR and SDF box sizes are legitimately infinite)."""
         if js_compatible:
-            return json.dumps(_nonfinite_to_null(self.data), separators=(",", ":"))
-        return json.dumps(self.data, separators=(",", ":"))
+            return json.dumps(_nonfinite_to_null(self.data), separators=(",", ":"), default=list)
+        return json.dumps(self.data, separators=(",", ":"), default=list)      # default: bytes -> array of numbers
 
     def to_msgpack(self) -> bytes:
         import msgpack

@@ -465,6 +465,37 @@ struct CheckerboardMaterialColor : MaterialColor {
     }
 };
 
+// TextureMaterialColor.color src/materials.js:101-130 (RGBA8 ImageData; bilinear or nearest; V flipped)
+struct TextureMaterialColor : MaterialColor {
+    int width = 0, height = 0; bool bilinear = true, clampU = true, clampV = true;
+    std::vector<unsigned char> data;
+    static double normalizeUV(double c, bool doClamp) {           // :97-100; JS `%` is fmod
+        if (doClamp) return js_min(js_max(c, 0), 1);
+        return std::fmod(std::fmod(c, 1) + 1, 1);
+    }
+    Vec color(const MatData& d) const override {
+        const double U = normalizeUV(d.hasUV ? d.UV[0] : 0, clampU), V = normalizeUV(d.hasUV ? d.UV[1] : 0, clampV);
+        const double fx = U * width - 0.5, fy = (1.0 - V) * height - 0.5;
+        double xs[2][2], ys[2][2]; int nx = 0, ny = 0;
+        if (bilinear) {
+            const double mx = std::floor(fx), my = std::floor(fy);
+            xs[0][0] = mx; xs[0][1] = 1 - std::fmod(fx, 1); xs[1][0] = mx + 1; xs[1][1] = std::fmod(fx, 1); nx = 2;
+            ys[0][0] = my; ys[0][1] = 1 - std::fmod(fy, 1); ys[1][0] = my + 1; ys[1][1] = std::fmod(fy, 1); ny = 2;
+        } else {
+            xs[0][0] = std::floor(fx + 0.5); xs[0][1] = 1; nx = 1;      // Math.round
+            ys[0][0] = std::floor(fy + 0.5); ys[0][1] = 1; ny = 1;
+        }
+        double ret[4] = {0, 0, 0, 0};
+        for (int a = 0; a < nx; ++a)
+            for (int b = 0; b < ny; ++b) {
+                const double cy = js_min(js_max(ys[b][0], 0), height - 1), cx = js_min(js_max(xs[a][0], 0), width - 1);
+                const long index = (long)(cy * width + cx);
+                for (int i = 0; i < 4; ++i) ret[i] += xs[a][1] * ys[b][1] * (data[(size_t)index * 4 + i] / 255.0);
+            }
+        return Vec::of(ret[0], ret[1], ret[2], ret[3]);          // Vec.from(ret): a 4-vector (RGBA), f32
+    }
+};
+
 // ---------------------------------------------------------------------------
 struct LightSample { Vec direction, color; };
 struct Light { virtual ~Light() {} virtual int sampleCount() const = 0; virtual LightSample sample(const Vec& pos, double u0, double u1) const = 0; };
@@ -603,6 +634,14 @@ struct World {                        // src/world.js:1-42
 struct SolidColorMaterial : Material {
     MaterialColor* c;
     Vec color(MatData& d, World&, int, uint32_t, Ctx&) override { return c->color(d); }
+};
+struct PositionalUVMaterial : Material {      // src/materials.js:178-193
+    Material* base; Vec origin, u_axis, v_axis;
+    Vec color(MatData& d, World& world, int depth, uint32_t node, Ctx& ctx) override {
+        const Vec delta = origin.minus(d.position);
+        d.hasUV = true; d.UV = Vec::of(u_axis.dot(delta), v_axis.dot(delta));
+        return base->color(d, world, depth, node, ctx);
+    }
 };
 struct TransparentMaterial : Material {
     MaterialColor* c; double opacity;
@@ -860,6 +899,21 @@ MaterialColor* Scene::mcolor(const Node* n) {
         else { s->isArray = true; s->sv = vec(sc); }
         r = s;
     } else if (t == "CheckerboardMaterialColor") { auto* s = new CheckerboardMaterialColor; s->c1 = mcolor(n->get("color1")); s->c2 = mcolor(n->get("color2")); r = s; }
+    else if (t == "TextureMaterialColor") {
+        auto* s = new TextureMaterialColor;
+        const Node* img = n->get("_imgdata");
+        s->width = (int)img->get("width")->num(); s->height = (int)img->get("height")->num();
+        const Node* dn = img->get("data");
+        if (!dn || dn->kind != Node::RAW || !dn->raw || dn->raw->t != JV::ARR || (long)dn->raw->arr.size() != (long)s->width * s->height * 4)
+            throw std::runtime_error("oracle: TextureMaterialColor needs _imgdata.data as an array of width*height*4 numbers");
+        s->data.reserve(dn->raw->arr.size());
+        for (const JV* x : dn->raw->arr) s->data.push_back((unsigned char)x->num);
+        const Node* mode = n->get("mode");
+        s->bilinear = !(mode && mode->kind == Node::RAW && mode->raw && mode->raw->t == JV::STR && mode->raw->s == "nearest");
+        s->clampU = n->get("clampU") ? n->get("clampU")->boolean() : true;
+        s->clampV = n->get("clampV") ? n->get("clampV")->boolean() : true;
+        r = s;
+    }
     else throw std::runtime_error("oracle: unsupported MaterialColor " + t);
     mcs.emplace_back(r); memo[n] = r; return r;
 }
@@ -878,6 +932,10 @@ Material* Scene::material(const Node* n) {
         r = p;
     } else if (t == "SolidColorMaterial") { auto* s = new SolidColorMaterial; s->c = mcolor(n->get("_color")); r = s; }
     else if (t == "TransparentMaterial") { auto* s = new TransparentMaterial; s->c = mcolor(n->get("_color")); s->opacity = n->get("_opacity")->num(); r = s; }
+    else if (t == "PositionalUVMaterial") {
+        auto* s = new PositionalUVMaterial; s->base = material(n->get("baseMaterial"));
+        s->origin = vec(n->get("origin")); s->u_axis = vec(n->get("u_axis")); s->v_axis = vec(n->get("v_axis")); r = s;
+    }
     else throw std::runtime_error("oracle: unsupported material " + t);
     mats.emplace_back(r); memo[n] = r; return r;
 }
