@@ -31,8 +31,8 @@ namespace jsrt {
 namespace {
 
 constexpr int kBlock = 256;
-#ifndef JSRT_SHADE_SORT
-#define JSRT_SHADE_SORT 1
+#ifndef JSRT_SHADE_MIN_BLOCKS
+#define JSRT_SHADE_MIN_BLOCKS 3
 #endif
 #ifndef JSRT_BVH_MIN_BLOCKS
 #define JSRT_BVH_MIN_BLOCKS 4      // 64 registers: 4 CTAs / SM (measured against 3 and 5: profiles/r1_ncu_summary.md)
@@ -153,27 +153,30 @@ __device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float3 
 // shade: World.color's miss / hit handling (src/world.js:31-41), Primitive.color
 // (:125-137), Material.color (src/materials.js).  Emits ambient, pushes shadow rays
 // and children.
-template <bool HAS_SDF>
-__global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : 3) shade_kernel(const __grid_constant__ DeviceScene sc, RayQueue q, const int* __restrict__ count,
+template <bool HAS_SDF, bool SORT>
+__global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ DeviceScene sc, RayQueue q, const int* __restrict__ count,
                                                         const float4* __restrict__ hits, RayQueue next, int* next_count, int next_cap,
                                                         ShadowQueue sq, int* shadow_count, int shadow_cap, float4* __restrict__ accum,
                                                         unsigned long long seed, unsigned long long* stats, int* overflow, const float4* __restrict__ sdf_normals) {
     const int n = *count;
     const int stride = gridDim.x * blockDim.x;
     unsigned long long my_shaded = 0;
-#if JSRT_SHADE_SORT
-    // Shading sorted by material: the kBlock rays of a tile are permuted inside the CTA by a counting sort on
-    // (miss | material index) before they are shaded, so that a warp runs one material's code path instead of
-    // the union of its 32 rays' paths (profiles/: 18 of 32 threads active per instruction without it at the
-    // deeper levels).  The permutation stays inside a 4 KB window of each queue array, so the loads still hit
-    // whole sectors.  Results do not depend on the order (the RNG is keyed by pixel / pass / path node).
+    // Shading sorted by material (SORT): the kBlock rays of a tile are permuted inside the CTA by a counting sort on
+    // (miss | material index) before they are shaded, so that a warp runs one material's code path instead of the
+    // union of its 32 rays' paths.  The permutation stays inside a 4 KB window of each queue array, so the loads
+    // still hit whole sectors, and results do not depend on the order (the RNG is keyed by pixel / pass / path
+    // node).  The price is three CTA barriers per tile, which tie the fast warps (misses) to the slow ones; measured
+    // (profiles/r1_ab.md): -6 % shade time on cornell_box_path (closed box, 12 analytic primitives with their own
+    // materials, depth 8), +5..10 % on bunny_path / dragon / starwars, whose camera and shadow-side rays are coherent
+    // already.  The host turns it on for scenes without BVH aggregates (JSRT_SHADE_SORT=0/1 overrides).
     __shared__ int s_hist[64], s_off[64];
     __shared__ unsigned short s_perm[kBlock];
-    if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
-    __syncthreads();
-    for (int tile = blockIdx.x * blockDim.x; tile < n; tile += stride) {
-        int i;
-        {
+    if (SORT) { if (threadIdx.x < 64) s_hist[threadIdx.x] = 0; __syncthreads(); }
+    const int n_round = SORT ? ((n + kBlock - 1) / kBlock) * kBlock : ((n + 31) & ~31);      // block- / warp-uniform trip count
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_round; i0 += stride) {
+        int i = i0;
+        if (SORT) {
+            const int tile = i0 - (int)threadIdx.x;
             const int j = tile + threadIdx.x, lane_s = threadIdx.x & 31;
             int key = 63;
             if (j < n) {
@@ -202,10 +205,6 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : 3) shade_kernel(const __
             __syncthreads();
             i = tile + s_perm[threadIdx.x];
         }
-#else
-    const int n_round = (n + 31) & ~31;      // warp-uniform trip count: every lane reaches the ballots
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-#endif
         const bool active = i < n;
         bool hit = false;
         uint32_t pixel = 0, node = 0; int depth_rem = 0, pass = 0;
@@ -420,7 +419,7 @@ struct Renderer::Impl {
     size_t scene_bytes = 0, queue_bytes = 0;
     int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0, grid_bvh = 0, grid_sdf = 0;
     unsigned long long launches = 0;
-    bool profiling = false, has_sdf = false;
+    bool profiling = false, has_sdf = false, sort_shade = false;
     double ms[4] = {0, 0, 0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uchar4* rgba = nullptr; int* hit_ids = nullptr; float* hit_t = nullptr;
@@ -503,7 +502,11 @@ struct Renderer::Impl {
         has_sdf = !hs.sdfs.empty();
         grid_extend = has_sdf ? grid_for((const void*)prims_kernel<TM_EXTEND, false, true>) : grid_for((const void*)prims_kernel<TM_EXTEND, false, false>);
         grid_bvh = has_sdf ? grid_for((const void*)bvh_kernel<TM_EXTEND, false, true>) : grid_for((const void*)bvh_kernel<TM_EXTEND, false, false>);
-        grid_shade = has_sdf ? grid_for((const void*)shade_kernel<true>) : grid_for((const void*)shade_kernel<false>);
+        // material-sorted shading: on for scenes made of analytic primitives only (see shade_kernel)
+        sort_shade = bvh_tops_host.empty();
+        if (const char* e = getenv("JSRT_SHADE_SORT")) sort_shade = atoi(e) != 0;
+        grid_shade = has_sdf ? (sort_shade ? grid_for((const void*)shade_kernel<true, true>) : grid_for((const void*)shade_kernel<true, false>))
+                             : (sort_shade ? grid_for((const void*)shade_kernel<false, true>) : grid_for((const void*)shade_kernel<false, false>));
         grid_shadow = has_sdf ? grid_for((const void*)prims_kernel<TM_SHADOW, false, true>) : grid_for((const void*)prims_kernel<TM_SHADOW, false, false>);
         grid_gen = grid_for((const void*)generate_kernel);
         grid_sdf = grid_for((const void*)sdf_kernel<TM_EXTEND, false>);
@@ -644,10 +647,11 @@ struct Renderer::Impl {
             for (int level = 0; level < hs.max_depth; ++level) {
                 launchExtend(cur, count_work);
                 timed(2, [&] {
-                    if (has_sdf) shade_kernel<true><<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap,
-                                                                                       sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow, sdf_normals);
-                    else shade_kernel<false><<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap,
-                                                                                sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow, nullptr);
+                    #define JSRT_SHADE(S, O) shade_kernel<S, O><<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap, \
+                                                                                              sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow, has_sdf ? sdf_normals : nullptr)
+                    if (has_sdf) { if (sort_shade) JSRT_SHADE(true, true); else JSRT_SHADE(true, false); }
+                    else { if (sort_shade) JSRT_SHADE(false, true); else JSRT_SHADE(false, false); }
+                    #undef JSRT_SHADE
                 });
                 if (hs.light_samples > 0) launchShadow(count_work);
                 level_end_kernel<<<1, 1, 0, stream>>>(counters, cur, level, ray_cap, shadow_cap); ++launches;
