@@ -27,6 +27,28 @@ function installTriangleSerializeFix() {
     };
 }
 
+// A TextureMaterialColor holds a browser ImageData whose width / height / data are prototype getters, so the
+// reference's serializer writes it as an empty object (src/serializer.js:54-57; src/materials.js:88-90 then reads
+// `data.imgdata`, which is never written).  Give the texture a serialize() that emits the wire form the C ABI
+// reads: `_imgdata: {_t, _v: {width, height, data}}` with `data` the RGBA8 bytes (msgpack bin via Uint8Array; a
+// plain array of numbers under JSON) — the same form jsraytracer_b200/materials.py:ImageData emits.
+class ImageDataWire {          // stand-in that serialises: own serialize(), so serializeStep leaves `data` alone
+    constructor(img, binary) { this.img = img; this.binary = binary; }
+    serialize(serializer) {
+        const d = this.img.data, bytes = new Uint8Array(d.buffer, d.byteOffset, d.byteLength);
+        return { width: this.img.width, height: this.img.height, data: this.binary ? bytes : Array.from(bytes) };
+    }
+}
+function installTextureSerializeFix() {
+    if (typeof TextureMaterialColor === "undefined") return;
+    TextureMaterialColor.prototype.serialize = function (serializer) {
+        return {
+            _imgdata: serializer.serializeStep(new ImageDataWire(this._imgdata, !!serializer.binary)),
+            width: this.width, height: this.height, mode: this.mode, clampU: this.clampU, clampV: this.clampV,
+        };
+    };
+}
+
 class CUDARenderer extends IncrementalMultisamplingRenderer {
     constructor(world, camera, samplesPerPixel, maxRecursionDepth = 3, options = {}) {
         super(world, camera, samplesPerPixel, maxRecursionDepth);
@@ -48,17 +70,18 @@ class CUDARenderer extends IncrementalMultisamplingRenderer {
             return this._scene;
         if (this._scene) this._addon().destroyScene(this._scene);
         installTriangleSerializeFix();
-        const plain = new Serializer({ renderer: this, width: w, height: h }).plain();
+        installTextureSerializeFix();
+        let msgpack = null;
+        try { msgpack = require("@msgpack/msgpack"); } catch (e) { msgpack = null; }
+        const ser = Object.create(Serializer.prototype);      // like `new Serializer(data)`, with a flag the texture fix reads
+        ser.SER_ID = "_SID" + Serializer.SER_UID_GEN++; ser.REF_UID_GEN = 0; ser.refs = {}; ser.ref_counts = {}; ser.type_map = {};
+        ser.binary = !!msgpack;
+        const plain = ser.serializeStep({ renderer: this, width: w, height: h });
         // msgpack keeps Infinity (IOR, SDF box sizes); JSON.stringify would write null, which the
         // reader maps back to +Infinity at those fields, so both work (tests/test_to_json.js:36-38).
         let blob, format;
-        try {
-            blob = Buffer.from(require("@msgpack/msgpack").encode(plain));
-            format = 1;
-        } catch (e) {
-            blob = Buffer.from(JSON.stringify(plain), "utf8");
-            format = 0;
-        }
+        if (msgpack) { blob = Buffer.from(msgpack.encode(plain)); format = 1; }
+        else { blob = Buffer.from(JSON.stringify(plain), "utf8"); format = 0; }
         this._scene = this._addon().createScene(blob, format, this._opt.device);   // throws Error(jsrt_last_error())
         this._size = [w, h];
         return this._scene;
@@ -93,4 +116,4 @@ class CUDARenderer extends IncrementalMultisamplingRenderer {
     }
 }
 
-if (typeof module !== "undefined") module.exports = { CUDARenderer, installTriangleSerializeFix };
+if (typeof module !== "undefined") module.exports = { CUDARenderer, installTriangleSerializeFix, installTextureSerializeFix };
