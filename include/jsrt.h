@@ -125,6 +125,8 @@ typedef struct jsrt_stats {
     uint64_t bvh_prims[3];      /* leaf object intersect calls, src/aggregates.js:211-212 */
     uint64_t top_prims[3];      /* top-level / list primitive intersect calls, src/world.js:9-10 */
     uint64_t sdf_evals[3];      /* root_sdf.distance() calls while marching, src/sdf.js:24 */
+    /* profiling only: ms_extend / ms_shadow split by kernel (prims_kernel, bvh_kernel, sdf_kernel) */
+    double ms_extend_prims, ms_extend_bvh, ms_extend_sdf, ms_shadow_prims, ms_shadow_bvh, ms_shadow_sdf;
 } jsrt_stats;
 /* Counters accumulated since the last jsrt_stats_reset; synchronises the scene's stream. */
 int jsrt_stats_get(jsrt_scene*, jsrt_stats*);

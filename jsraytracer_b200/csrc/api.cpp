@@ -100,6 +100,8 @@ int jsrt_stats_get(jsrt_scene* s, jsrt_stats* o) {
         o->launches = r.launches; o->camera_samples = r.camera_samples;
         o->ms_generate = r.ms[0]; o->ms_extend = r.ms[1]; o->ms_shade = r.ms[2]; o->ms_shadow = r.ms[3];
         for (int k = 0; k < 3; ++k) { o->bvh_nodes[k] = r.nodes[k]; o->bvh_prims[k] = r.leaf_prims[k]; o->top_prims[k] = r.top_prims[k]; o->sdf_evals[k] = r.sdf_evals[k]; }
+        o->ms_extend_prims = r.ms_part[0]; o->ms_extend_bvh = r.ms_part[1]; o->ms_extend_sdf = r.ms_part[2];
+        o->ms_shadow_prims = r.ms_part[3]; o->ms_shadow_bvh = r.ms_part[4]; o->ms_shadow_sdf = r.ms_part[5];
         o->n_generate = r.kernel_launches[0]; o->n_extend = r.kernel_launches[1]; o->n_shade = r.kernel_launches[2]; o->n_shadow = r.kernel_launches[3];
         return 0;
     } catch (const std::exception& e) { return failWith(e); }

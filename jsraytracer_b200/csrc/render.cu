@@ -420,7 +420,7 @@ struct Renderer::Impl {
     int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0, grid_bvh = 0, grid_sdf = 0;
     unsigned long long launches = 0;
     bool profiling = false, has_sdf = false, sort_shade = false;
-    double ms[4] = {0, 0, 0, 0};
+    double ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};     // 0-3: kernel classes; 4-9: prims / bvh / sdf kernels of extend, shadow
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uchar4* rgba = nullptr; int* hit_ids = nullptr; float* hit_t = nullptr;
 
@@ -563,7 +563,7 @@ struct Renderer::Impl {
     // around each launch on the launching stream and only read back (after a stream
     // sync) when the statistics are fetched.
     struct EvPair { cudaEvent_t a, b; int which; };
-    std::vector<EvPair> pending;
+    std::vector<EvPair> pending, pending_parts;
     std::vector<cudaEvent_t> free_events;
     unsigned long long kernel_launches[4] = {0, 0, 0, 0};
     cudaEvent_t getEvent() {
@@ -571,10 +571,18 @@ struct Renderer::Impl {
         cudaEvent_t e; CK(cudaEventCreate(&e)); return e;
     }
     void flushEvents() {
-        if (pending.empty()) return;
+        if (pending.empty() && pending_parts.empty()) return;
         CK(cudaStreamSynchronize(stream));
         for (auto& p : pending) { float t = 0; CK(cudaEventElapsedTime(&t, p.a, p.b)); ms[p.which] += t; free_events.push_back(p.a); free_events.push_back(p.b); }
         pending.clear();
+        // the per-kernel parts share their boundary events: each event is released once
+        for (size_t i = 0; i < pending_parts.size(); ++i) {
+            auto& p = pending_parts[i];
+            float t = 0; CK(cudaEventElapsedTime(&t, p.a, p.b)); ms[p.which] += t;
+            if (i % 3 == 0) free_events.push_back(p.a);
+            free_events.push_back(p.b);
+        }
+        pending_parts.clear();
     }
     template <class F> void timed(int which, F&& launch) {
         EvPair p{nullptr, nullptr, which};
@@ -590,20 +598,31 @@ struct Renderer::Impl {
         const bool has_bvh = ds.n_bvh > 0, has_sdf_tops = ds.n_sdf_tops > 0;
         io.final_pass = has_sdf_tops ? 0 : 1;        // prims_wave finishes the rays that need no BVH walk unless an SDF march follows
         #define JSRT_LAUNCH(K, G, C, S) K<MODE, C, S><<<G, kBlock, 0, stream>>>(ds, io)
+        // profiling: the three kernels of a trace wave are also timed one by one (ms[4..9])
+        const int part0 = 4 + 3 * MODE;
+        cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr}; int np = 0;
+        auto mark = [&] { if (profiling) { pe[np] = getEvent(); CK(cudaEventRecord(pe[np], stream)); ++np; } };
+        mark();
         if (count_work) { if (has_sdf) JSRT_LAUNCH(prims_kernel, grid_prims, true, true); else JSRT_LAUNCH(prims_kernel, grid_prims, true, false); }
         else { if (has_sdf) JSRT_LAUNCH(prims_kernel, grid_prims, false, true); else JSRT_LAUNCH(prims_kernel, grid_prims, false, false); }
+        mark();
         if (has_bvh) {
             ++launches;
             io.final_pass = has_sdf_tops ? 0 : 1;
             if (count_work) { if (has_sdf) JSRT_LAUNCH(bvh_kernel, grid_bvh, true, true); else JSRT_LAUNCH(bvh_kernel, grid_bvh, true, false); }
             else { if (has_sdf) JSRT_LAUNCH(bvh_kernel, grid_bvh, false, true); else JSRT_LAUNCH(bvh_kernel, grid_bvh, false, false); }
         }
+        mark();
         if (has_sdf_tops) {
             ++launches;
             io.final_pass = 1;
             io.cursor = io0.cursor + 2;          // cursor_extend_sdf / cursor_shadow_sdf
             if (count_work) sdf_kernel<MODE, true><<<grid_sdf, kBlock, 0, stream>>>(ds, io);
             else sdf_kernel<MODE, false><<<grid_sdf, kBlock, 0, stream>>>(ds, io);
+        }
+        mark();
+        if (profiling) {
+            for (int k = 0; k < 3; ++k) pending_parts.push_back(EvPair{pe[k], pe[k + 1], part0 + k});
         }
         #undef JSRT_LAUNCH
     }
@@ -720,6 +739,7 @@ void Renderer::getStats(RenderStats& s) {
     s.shaded_hits = c.stats[ST_SHADED]; s.camera_samples = c.stats[ST_SAMPLES]; s.launches = impl_->launches;
     for (int k = 0; k < 3; ++k) { s.nodes[k] = c.stats[ST_NODES + k]; s.leaf_prims[k] = c.stats[ST_LEAF_PRIMS + k]; s.top_prims[k] = c.stats[ST_TOP_PRIMS + k]; s.sdf_evals[k] = c.stats[ST_SDF_EVALS + k]; }
     for (int i = 0; i < 4; ++i) { s.ms[i] = impl_->ms[i]; s.kernel_launches[i] = impl_->kernel_launches[i]; }
+    for (int i = 0; i < 6; ++i) s.ms_part[i] = impl_->ms[4 + i];
 }
 void Renderer::resetStats() {
     synchronize();

@@ -11,6 +11,7 @@ namespace jsrt {
 struct RenderStats {
     uint64_t rays_primary = 0, rays_secondary = 0, rays_shadow = 0, shaded_hits = 0, camera_samples = 0, launches = 0;
     double ms[4] = {0, 0, 0, 0};   // generate, extend, shade, shadow (profiling mode only)
+    double ms_part[6] = {0, 0, 0, 0, 0, 0};   // extend: prims, bvh, sdf kernels | shadow: prims, bvh, sdf kernels
     uint64_t kernel_launches[4] = {0, 0, 0, 0};
     // per ray class (primary, secondary, shadow); only counted by JSRT_FLAG_COUNT_WORK renders
     uint64_t nodes[3] = {0, 0, 0}, leaf_prims[3] = {0, 0, 0}, top_prims[3] = {0, 0, 0}, sdf_evals[3] = {0, 0, 0};

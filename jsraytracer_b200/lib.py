@@ -43,7 +43,9 @@ class Stats(C.Structure):
                                           "camera_samples")] + \
                [(n, C.c_double) for n in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow")] + \
                [(n, C.c_uint64) for n in ("n_generate", "n_extend", "n_shade", "n_shadow")] + \
-               [(n, C.c_uint64 * 3) for n in ("bvh_nodes", "bvh_prims", "top_prims", "sdf_evals")]
+               [(n, C.c_uint64 * 3) for n in ("bvh_nodes", "bvh_prims", "top_prims", "sdf_evals")] + \
+               [(n, C.c_double) for n in ("ms_extend_prims", "ms_extend_bvh", "ms_extend_sdf",
+                                          "ms_shadow_prims", "ms_shadow_bvh", "ms_shadow_sdf")]
 
     def as_dict(self):
         d = {n: (list(getattr(self, n)) if hasattr(getattr(self, n), "__len__") else getattr(self, n))

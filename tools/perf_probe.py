@@ -18,7 +18,7 @@ def main():
     kw = {}
     for a in sys.argv[5:]:                      # extra scene keywords, e.g. n=3
         k, v = a.split("=")
-        kw[k] = int(v)
+        kw[k] = (9.2, 0.2) if k == "dof" else int(v)     # dof=1: the BoxBall_DOF camera (BASELINE configs[3])
     ser = Serializer(scenes.configure(name, width=W, height=H, aspect=W / H, **kw))
     sc = lib.Scene(ser.to_msgpack(), lib.FORMAT_MSGPACK, device=0)
     sc.render(0, passes, seed=1)
@@ -37,6 +37,7 @@ def main():
     rays = st["rays"]
     out = {"scene": name, "size": [W, H], "passes": passes, "wall_ms": dt * 1e3, "Mrays_s": rays / dt / 1e6,
            "ms": {k: round(st["ms_" + k], 3) for k in ("generate", "extend", "shade", "shadow")},
+           "ms_parts": {k: round(st["ms_" + k], 3) for k in ("extend_prims", "extend_bvh", "extend_sdf", "shadow_prims", "shadow_bvh", "shadow_sdf")},
            "rays": {k: st["rays_" + k] for k in ("primary", "secondary", "shadow")},
            "per_ray": {cls: {"nodes": cw["bvh_nodes"][i] / max(1, cw["rays_" + cls]), "leaf_prims": cw["bvh_prims"][i] / max(1, cw["rays_" + cls]),
                              "top_prims": cw["top_prims"][i] / max(1, cw["rays_" + cls]), "sdf_evals": cw["sdf_evals"][i] / max(1, cw["rays_" + cls])}
