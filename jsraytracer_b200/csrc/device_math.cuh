@@ -201,18 +201,34 @@ JSRT_DEV float triangle_intersect(const Tri* __restrict__ tris, int idx, float3 
 // The program is straight-line (sdf_compile.cpp unrolls every loop), so all lanes
 // of a warp run the same instruction stream; only the REFL fold is predicated.
 //
-// Arithmetic is the reference's, operation for operation: points are f32 vectors,
-// every scalar (distance, scale, dot product, matrix entry) is f64, and each
-// Vec-returning step rounds to f32.  Sphere tracing stops on `distance <= epsilon`
-// (src/sdf.js:32) and the normal is a forward difference over a 1e-3 step
-// (src/sdf.js:42-46); both turn a one-ulp difference into a visibly different pixel on
-// fractal SDFs, so FP32 evaluation cannot meet the parity bar here.  B200's FP64 pipe
-// runs at half the FP32 rate, which this path pays knowingly.
+// Arithmetic is the reference's, bit for bit: points are f32 vectors, every scalar
+// (distance, scale, dot product, matrix entry) is f64, and each Vec-returning step
+// rounds to f32.  Sphere tracing stops on `distance <= epsilon` (src/sdf.js:32) and
+// the normal is a forward difference over a 1e-3 step (src/sdf.js:42-46); both turn a
+// one-ulp difference into a visibly different pixel on fractal SDFs, so plain FP32
+// evaluation cannot meet the parity bar here (measured: 47.8 dB on SDF_Menger).
+// What keeps the f64 work small without changing a bit:
+//  * a single +, -, * of two f32 values computed in f64 and rounded to f32 equals the FP32
+//    operation (53 >= 2*24 + 2 bits: double rounding is innocuous), so those steps are FP32;
+//  * the square of an f32 value, and the product of an f32 value with a matrix entry that is
+//    itself representable in f32, are exact in f64, so mul + add chains over them are DFMAs;
+//  * the top of every stack lives in registers; leaf + min/max and scale + min are single
+//    instructions (sdf_compile.cpp fuses them), scale groups that cannot round are elided.
 // Mat.times(Vec) with an f64 3x4 matrix: result[r] = b.dot(row r) stored f32 (src/math.js:392-397)
 JSRT_DEV float3 xf64_apply(const double* __restrict__ m, float3 p, double w) {
     return f3((float)ddot4(p.x, p.y, p.z, w, __ldg(m + 0), __ldg(m + 1), __ldg(m + 2), __ldg(m + 3)),
               (float)ddot4(p.x, p.y, p.z, w, __ldg(m + 4), __ldg(m + 5), __ldg(m + 6), __ldg(m + 7)),
               (float)ddot4(p.x, p.y, p.z, w, __ldg(m + 8), __ldg(m + 9), __ldg(m + 10), __ldg(m + 11)));
+}
+// The same for a point (w = 1) and a matrix whose twelve entries are all representable in f32: every product
+// is exact, so ((x m0 + y m1) + z m2) + m3 rounds exactly like the fused chain below.
+JSRT_DEV float3 xf64_apply_exact(const double* __restrict__ m, float3 p) {
+    const double2* r = reinterpret_cast<const double2*>(m);
+    const double2 a0 = __ldg(r), a1 = __ldg(r + 1), b0 = __ldg(r + 2), b1 = __ldg(r + 3), c0 = __ldg(r + 4), c1 = __ldg(r + 5);
+    const double x = p.x, y = p.y, z = p.z;
+    return f3((float)dadd(fma(z, a1.x, fma(y, a0.y, dmul(x, a0.x))), a1.y),
+              (float)dadd(fma(z, b1.x, fma(y, b0.y, dmul(x, b0.x))), b1.y),
+              (float)dadd(fma(z, c1.x, fma(y, c0.y, dmul(x, c0.x))), c1.y));
 }
 JSRT_DEV double sdf_smooth_min(double a, double b, double k) {   // src/sdf.js:128-131
     const double h = jsd_max(dsub(k, fabs(dsub(a, b))), 0.0) / k;
@@ -224,8 +240,11 @@ JSRT_DEV double sdf_smooth_min(double a, double b, double k) {   // src/sdf.js:1
 // equals the decimal round trip except when |x| * 10^k lands within an ulp of a half-way point.
 __device__ const double kPow10[32] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
                                       1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22, 1e23, 1e24, 1e25, 1e26, 1e27, 1e28, 1e29, 1e30, 1e31};
-JSRT_DEV double js_to_precision8(double x) {
-    if (x == 0.0 || !isfinite(x)) return x;
+// correctly rounded reciprocals of the exact powers (the compiler folds these IEEE divisions)
+__device__ const double kInvPow10[23] = {1.0 / 1e0, 1.0 / 1e1, 1.0 / 1e2, 1.0 / 1e3, 1.0 / 1e4, 1.0 / 1e5, 1.0 / 1e6, 1.0 / 1e7, 1.0 / 1e8, 1.0 / 1e9,
+                                         1.0 / 1e10, 1.0 / 1e11, 1.0 / 1e12, 1.0 / 1e13, 1.0 / 1e14, 1.0 / 1e15, 1.0 / 1e16, 1.0 / 1e17, 1.0 / 1e18,
+                                         1.0 / 1e19, 1.0 / 1e20, 1.0 / 1e21, 1.0 / 1e22};
+JSRT_DEV double js_to_precision8_slow(double x) {
     const double ax = fabs(x);
     int e = (int)floor((double)(ilogb(ax)) * 0.30102999566398120);      // floor(log10(ax)) or one less
     int k = 7 - e;
@@ -242,80 +261,115 @@ JSRT_DEV double js_to_precision8(double x) {
     const double r = (k >= 0) ? nn / kPow10[k] : dmul(nn, kPow10[-k]);
     return copysign(r, x);
 }
+JSRT_DEV double js_to_precision8(double x) {
+    if (x == 0.0 || !isfinite(x)) return x;
+    // fast path, 1e-15 <= |x| < 1e8 (every coordinate an SDF scene produces): binary exponent from the bits,
+    // floor(e2 log10 2) in integers (exact for |e2| <= 64), and N / 10^k as a Markstein division with the
+    // tabulated reciprocal: q0 = N y, r = N - q0 10^k (exact, fused), q = q0 + r y — the correctly rounded
+    // quotient, which is what the IEEE division of the general path returns.
+    const int e2 = ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
+    if (e2 < -46 || e2 > 26) return js_to_precision8_slow(x);                // keeps k within the exact powers 10^0 .. 10^21
+    const double ax = fabs(x);
+    int k = 7 - ((e2 * 1233) >> 12);                                     // 7 - floor(log10(2^e2)); one too large when the mantissa crosses a decade
+    double y = dmul(ax, __ldg(kPow10 + k));
+    if (y >= 1e8) { --k; y = dmul(ax, __ldg(kPow10 + k)); }
+    if (k < 0) return js_to_precision8_slow(x);
+    const double nn = rint(y);
+    const double p10 = __ldg(kPow10 + k), inv = __ldg(kInvPow10 + k);
+    const double q0 = dmul(nn, inv);
+    const double q = fma(fma(-q0, p10, nn), inv, q0);
+    return copysign(q, x);
+}
 JSRT_DEV double js_fmod(double a, double b) {
     // a / b: for a power-of-two period the product with the (exact) reciprocal is the same number
     int e; const bool pow2 = frexp(b, &e) == 0.5;
     const double q = pow2 ? dmul(a, 1.0 / b) : a / b;
     return js_to_precision8(dsub(a, dmul(floor(q), b)));
 }
+// the same with the exact reciprocal of a power-of-two period supplied by the compiler (sdf_compile.cpp)
+JSRT_DEV double js_fmod_pow2(double a, double b, double inv_b) { return js_to_precision8(dsub(a, dmul(floor(dmul(a, inv_b)), b))); }
 
 JSRT_DEV double sdf_eval(const SdfInstr* __restrict__ code, const Xform64* __restrict__ xforms64, float3 p0) {
+    // the tops of the three stacks are registers (p, s, dtop); the arrays hold what lies below them
     float3 P[8]; double S[12]; double D[8];
-    int sp = 0, ss = 0, dp = 0;
-    P[0] = p0; S[0] = 1.0;
+    int sp = 0, ss = 0, dp = 0;           // dp: distances on the stack (dtop is element dp - 1)
+    float3 p = p0; double s = 1.0, dtop = 0.0;
+    int4 i0 = __ldg(reinterpret_cast<const int4*>(code));
+    float4 fv = __ldg(reinterpret_cast<const float4*>(code) + 1);
     for (int pc = 0;; ++pc) {
-        const int4 i0 = __ldg(reinterpret_cast<const int4*>(code + pc));
-        const float4 fv = __ldg(reinterpret_cast<const float4*>(code + pc) + 1);
-        const int op = i0.x;
+        const int op = i0.x, idx = i0.y;
         const double a0 = __hiloint2double(i0.w, i0.z);
-        switch (op) {
-            case S_END: return D[0];
-            case S_SPHERE: {                                                                              // src/sdf.js:232-234: p.to4(0).norm() - radius
-                const float3 p = P[sp];
-                D[dp++] = dsub(sqrt(ddot4(p.x, p.y, p.z, 0.0, p.x, p.y, p.z, 0.0)), a0); break;
-            }
-            case S_BOX: {                                                                                 // src/sdf.js:276-279
-                const float3 p = P[sp];
-                const float qx = (float)dsub(fabsf(p.x), fv.x), qy = (float)dsub(fabsf(p.y), fv.y), qz = (float)dsub(fabsf(p.z), fv.z);
-                const double mx = fmax((double)qx, 0.0), my = fmax((double)qy, 0.0), mz = fmax((double)qz, 0.0);   // Vec.max(q, 0): q.w = 0
+        const float4 f = fv;
+        // the next instruction is fetched while this one executes (straight-line code: pc + 1 always exists before S_END)
+        if (op != S_END) { i0 = __ldg(reinterpret_cast<const int4*>(code + pc + 1)); fv = __ldg(reinterpret_cast<const float4*>(code + pc + 1) + 1); }
+        if (op <= S_TETRA) {
+            if (op == S_END) return dtop;
+            double v;
+            if (op == S_BOX) {                                                                            // src/sdf.js:276-279
+                // q = |p| - size: one f64 subtraction of f32 values stored f32 = the FP32 subtraction
+                const float qx = __fsub_rn(fabsf(p.x), f.x), qy = __fsub_rn(fabsf(p.y), f.y), qz = __fsub_rn(fabsf(p.z), f.z);
+                const float mx = fmaxf(qx, 0.f), my = fmaxf(qy, 0.f), mz = fmaxf(qz, 0.f);                    // Vec.max(q, 0): q.w = 0
                 // |max(q, 0)|: with at most one positive component the f64 square of an f32 value is exact and
-                // its correctly rounded root is that value again, so the sqrt can be skipped without changing a bit
+                // its correctly rounded root is that value again, so the sqrt can be skipped without changing a bit;
+                // otherwise the squares are exact in f64 and the sum rounds like the fused chain
                 double len;
-                if (my == 0.0 && mz == 0.0) len = mx;
-                else if (mx == 0.0 && mz == 0.0) len = my;
-                else if (mx == 0.0 && my == 0.0) len = mz;
-                else len = sqrt(ddot4(mx, my, mz, 0.0, mx, my, mz, 0.0));
-                D[dp++] = dadd(len, fmin(fmax(fmax((double)qx, (double)qy), (double)qz), 0.0));
-                break;
-            }
-            case S_TETRA: {                                                                               // src/sdf.js:305-308
-                const float3 p = P[sp];
+                if (my == 0.f && mz == 0.f) len = mx;
+                else if (mx == 0.f && mz == 0.f) len = my;
+                else if (mx == 0.f && my == 0.f) len = mz;
+                else { const double x = mx, y = my, z = mz; len = sqrt(fma(z, z, fma(y, y, dmul(x, x)))); }
+                const float inner = fminf(fmaxf(fmaxf(qx, qy), qz), 0.f);
+                v = (qx != qx || qy != qy || qz != qz) ? CUDART_NAN : dadd(len, (double)inner);            // Math.max / min propagate NaN
+            } else if (op == S_SPHERE) {                                                                  // src/sdf.js:232-234: p.to4(0).norm() - radius
+                const double x = p.x, y = p.y, z = p.z;
+                v = dsub(sqrt(fma(z, z, fma(y, y, dmul(x, x)))), a0);
+            } else {                                                                                      // S_TETRA, src/sdf.js:305-308
                 const double a = dsub(fabs(dadd(p.x, p.y)), p.z), b = dadd(fabs(dsub(p.x, p.y)), p.z);
-                D[dp++] = dsub(fmax(a, b), 1.0) / sqrt(3.0);
-                break;
+                v = dsub(jsd_max(a, b), 1.0) / sqrt(3.0);
             }
-            case S_MIN: { --dp; D[dp - 1] = jsd_min(D[dp - 1], D[dp]); break; }
-            case S_MAX: { --dp; D[dp - 1] = jsd_max(D[dp - 1], D[dp]); break; }
-            case S_NEG: D[dp - 1] = -D[dp - 1]; break;
-            case S_ADDC: D[dp - 1] = dadd(D[dp - 1], a0); break;
-            case S_SMIN: { --dp; D[dp - 1] = sdf_smooth_min(D[dp - 1], D[dp], a0); break; }
-            case S_SMIN_NEGA: { --dp; D[dp - 1] = -sdf_smooth_min(-D[dp - 1], D[dp], a0); break; }
-            case S_SMIN_NEGAB: { --dp; D[dp - 1] = -sdf_smooth_min(-D[dp - 1], -D[dp], a0); break; }
-            case S_PUSHP: { P[sp + 1] = P[sp]; ++sp; S[++ss] = 1.0; break; }
-            case S_POPP: --sp; --ss; break;
-            case S_SBEGIN: S[++ss] = 1.0; break;
-            case S_SEND: { --ss; S[ss] = dmul(S[ss], S[ss + 1]); break; }
-            case S_MULS: D[dp - 1] = dmul(D[dp - 1], S[ss]); break;
+            // idx: fused Union / Intersection step with the distance below (FOLD_MIN / FOLD_MAX), else push
+            if (idx == 1) dtop = jsd_min(dtop, v);
+            else if (idx == 2) dtop = jsd_max(dtop, v);
+            else { if (dp > 0) D[dp - 1] = dtop; dtop = v; ++dp; }
+            continue;
+        }
+        switch (op) {
+            case S_MIN: { --dp; dtop = jsd_min(D[dp - 1], dtop); break; }
+            case S_MAX: { --dp; dtop = jsd_max(D[dp - 1], dtop); break; }
+            case S_NEG: dtop = -dtop; break;
+            case S_ADDC: dtop = dadd(dtop, a0); break;
+            case S_SMIN: { --dp; dtop = sdf_smooth_min(D[dp - 1], dtop, a0); break; }
+            case S_SMIN_NEGA: { --dp; dtop = -sdf_smooth_min(-D[dp - 1], dtop, a0); break; }
+            case S_SMIN_NEGAB: { --dp; dtop = -sdf_smooth_min(-D[dp - 1], -dtop, a0); break; }
+            case S_PUSHP: { P[sp++] = p; S[ss++] = s; s = 1.0; break; }
+            case S_POPP: { p = P[--sp]; s = S[--ss]; break; }
+            case S_SBEGIN: { S[ss++] = s; s = 1.0; break; }
+            case S_SEND: { s = dmul(S[--ss], s); break; }
+            case S_MULS: dtop = dmul(dtop, s); break;
+            case S_MULS_MIN: { --dp; dtop = jsd_min(dmul(dtop, s), D[dp - 1]); break; }                     // src/sdf.js:353-354
             case S_XFORM: {                                                                               // src/sdf.js:433-435
-                P[sp] = xf64_apply(xforms64[i0.y].m, P[sp], 1.0);
-                S[ss] = dmul(S[ss], a0);
+                p = (f.x != 0.f) ? xf64_apply_exact(xforms64[idx].m, p) : xf64_apply(xforms64[idx].m, p, 1.0);
+                s = dmul(s, a0);
                 break;
             }
             case S_REFL: {                                                                                // src/sdf.js:450-455
-                const float3 p = P[sp];
-                const double dt = dsub(ddot4(fv.x, fv.y, fv.z, 0.0, p.x, p.y, p.z, 1.0), a0);
+                const double dt = dsub(ddot4(f.x, f.y, f.z, 0.0, p.x, p.y, p.z, 1.0), a0);
                 if (dt < 0.0) {
                     const double k = dmul(2.0, dt);
-                    const float nx = (float)dmul(fv.x, k), ny = (float)dmul(fv.y, k), nz = (float)dmul(fv.z, k);
-                    P[sp] = f3((float)dsub(p.x, nx), (float)dsub(p.y, ny), (float)dsub(p.z, nz));
+                    const float nx = (float)dmul(f.x, k), ny = (float)dmul(f.y, k), nz = (float)dmul(f.z, k);
+                    p = f3(__fsub_rn(p.x, nx), __fsub_rn(p.y, ny), __fsub_rn(p.z, nz));
                 }
                 break;
             }
             case S_REP: {                                                                                 // src/sdf.js:471-473
-                const float3 p = P[sp];
-                const double sx = fv.x, sy = fv.y, sz = fv.z;
-                P[sp] = f3((float)dsub(js_fmod(dadd(p.x, sx / 2), sx), sx / 2), (float)dsub(js_fmod(dadd(p.y, sy / 2), sy), sy / 2),
-                           (float)dsub(js_fmod(dadd(p.z, sz / 2), sz), sz / 2));
+                const double sx = f.x, sy = f.y, sz = f.z;
+                if (idx == 1) {                                                                           // one power-of-two period, a0 = 1 / period
+                    const double h = sx / 2;
+                    p = f3((float)dsub(js_fmod_pow2(dadd(p.x, h), sx, a0), h), (float)dsub(js_fmod_pow2(dadd(p.y, h), sx, a0), h),
+                           (float)dsub(js_fmod_pow2(dadd(p.z, h), sx, a0), h));
+                    break;
+                }
+                p = f3((float)dsub(js_fmod(dadd(p.x, sx / 2), sx), sx / 2), (float)dsub(js_fmod(dadd(p.y, sy / 2), sy), sy / 2),
+                       (float)dsub(js_fmod(dadd(p.z, sz / 2), sz), sz / 2));
                 break;
             }
             default: return CUDART_NAN;
@@ -345,7 +399,8 @@ JSRT_DEV bool aabb_intersects_f64(float3 c, float3 h, float3 o, float3 d, double
 }
 
 JSRT_DEV float3 ray_point_f64(float3 o, float3 d, double t) {   // origin.plus(direction.times(t)) with an f64 t
-    return f3((float)dadd(o.x, (float)dmul(d.x, t)), (float)dadd(o.y, (float)dmul(d.y, t)), (float)dadd(o.z, (float)dmul(d.z, t)));
+    // (the sum of two f32 values rounded through f64 is the FP32 sum)
+    return f3(__fadd_rn(o.x, (float)dmul(d.x, t)), __fadd_rn(o.y, (float)dmul(d.y, t)), __fadd_rn(o.z, (float)dmul(d.z, t)));
 }
 
 // SDFGeometry.intersect src/sdf.js:12-40.  Returns the hit distance as f64 (NaN-free:

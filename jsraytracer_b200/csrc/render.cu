@@ -142,12 +142,7 @@ __global__ void __launch_bounds__(kBlock, JSRT_BVH_MIN_BLOCKS) bvh_kernel(const 
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
 
-__device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float3 c) {
-    float* a = reinterpret_cast<float*>(accum + pixel);
-    if (c.x != 0.f) atomicAdd(a + 0, c.x);
-    if (c.y != 0.f) atomicAdd(a + 1, c.y);
-    if (c.z != 0.f) atomicAdd(a + 2, c.z);
-}
+__device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float3 c) { accum_add3(accum, pixel, c); }
 
 // ---------------------------------------------------------------------------------
 // shade: World.color's miss / hit handling (src/world.js:31-41), Primitive.color
@@ -440,11 +435,32 @@ struct Renderer::Impl {
         sdf_tops_host.clear();
         for (size_t i = 0; i < hs.tops.size(); ++i) if (hs.tops[i].kind == T_SDF) sdf_tops_host.push_back((int)i);
         ds.sdf_tops = up(sdf_tops_host); ds.n_sdf_tops = (int)sdf_tops_host.size();
+        // analytic-primitive table of prims_wave: Primitives outside BVHAggregates, grouped by geometry kind; the shadow
+        // copy leaves out primitives with does_cast_shadow = false (src/world.js:117-118) and geometries that never hit
+        atab_host.clear();
+        for (int tab = 0; tab < 2; ++tab)
+            for (int grp = 0; grp < AG_COUNT; ++grp) {
+                for (size_t ti = 0; ti < hs.tops.size(); ++ti) {
+                    const Top& t = hs.tops[ti];
+                    if (t.kind != T_PRIM && t.kind != T_LIST) continue;
+                    for (int k = 0; k < t.prim_count; ++k) {
+                        const Prim& p = hs.prims[t.first_prim + k];
+                        const int g = p.geom_kind == G_PLANE ? AG_PLANE : p.geom_kind == G_SQUARE ? AG_SQUARE : p.geom_kind == G_BOX ? AG_BOX
+                                    : p.geom_kind == G_SPHERE ? AG_SPHERE : AG_OTHER;
+                        if (g != grp || p.geom_kind == G_NEVER) continue;
+                        if (tab == 1 && !(p.flags & PF_CASTS_SHADOW)) continue;
+                        atab_host.push_back(APrim{t.first_prim + k, (int)ti, (t.kind == T_LIST && t.xform != 0) ? t.xform : -1, p.xform, p.geom_index, p.flags, 0, 0});
+                    }
+                }
+                ds.atab_end[tab][grp] = (int)atab_host.size();
+            }
+        ds.atab = up(atab_host);
         ds.n_top = (int)hs.tops.size(); ds.n_lights = (int)hs.lights.size(); ds.light_samples = hs.light_samples; ds.max_depth = hs.max_depth;
         for (int i = 0; i < 3; ++i) ds.bg[i] = hs.bg[i];
     }
     std::vector<void*> scene_allocs;
     std::vector<int> bvh_tops_host, sdf_tops_host;
+    std::vector<APrim> atab_host;
     size_t up_index = 0;
     template <class T> T* up(const std::vector<T>& vec) {
         T* p;

@@ -78,6 +78,18 @@ struct Top {                      // one entry of world.objects (src/world.js:7-
     int n_layouts;                // 8: one node layout per ray-direction octant (near child first); 1: reference order only
 };
 
+// One row of the analytic-primitive table: 32 bytes, read with two warp-uniform 128-bit loads.
+struct APrim {
+    int prim;        // placed primitive index (ties between equal distances go to the lower (top, prim): the reference's order)
+    int top;         // index into world.objects
+    int agg_xform;   // >= 0: member of a plain Aggregate, the ray is first mapped by this inv_transform (src/aggregates.js:15)
+    int xform;       // the primitive's own inv_transform
+    int geom_index;  // G_BOX with a non-unit AABB: index into boxes, else -1
+    int flags;       // PrimFlags
+    int pad0, pad1;
+};
+enum AGroup : int { AG_PLANE = 0, AG_SQUARE = 1, AG_BOX = 2, AG_SPHERE = 3, AG_OTHER = 4, AG_COUNT = 5 };
+
 struct Color {                    // a MaterialColor folded to Solid, Checkerboard or scaled Texture (src/materials.js:27-131)
     float c1[3];                  // solid colour / checker colour 1 / texture: the folded ScaledMaterialColor factor
     int checker;                  // ColorKind
@@ -125,6 +137,7 @@ struct Light {                    // src/lights.js
 // a hard threshold and forward-difference normals amplify one-ulp differences.
 enum SdfOp : int {
     S_END = 0,
+    // the three leaves come first; their idx = 1 / 2 folds the new distance into the one below with min / max instead of pushing
     S_SPHERE,      // a0 = radius                        push |p| - r
     S_BOX,         // f32 size in (a1,a2) as 4 packed floats   push box distance
     S_TETRA,       //                                     push tetrahedron distance
@@ -137,12 +150,13 @@ enum SdfOp : int {
     S_PUSHP,       //                                     duplicate the point, push scale 1
     S_POPP,        //                                     drop the point and scale
     S_MULS,        //                                     top distance *= current scale
-    S_XFORM,       // idx = Xform64 index, a0 = scale     p = M p; scale *= a0
+    S_XFORM,       // idx = Xform64 index, a0 = scale     p = M p; scale *= a0   (f[0] != 0: every matrix entry is an f32 value)
     S_REFL,        // f32 normal in (a1,a2), a0 = delta
     S_REP,         // f32 sizes in (a1,a2)
     S_SBEGIN,      //                                     push a local scale accumulator (= 1)
     S_SEND,        //                                     pop it; enclosing scale *= popped   (Sequence / Recursive transformers
                    //                                     return their own product, src/sdf.js:387-394,408-415)
+    S_MULS_MIN,    //                                     pop d; top = min(top, d * scale)   (RecursiveTransformUnion step, src/sdf.js:353-354)
     // ---- material program (getMaterialData, src/sdf.js:86-88,102-104,119-121,149-154,...): straight-line code over a
     // stack of {distance, basecolor, UV}; every leaf is evaluated, selections / blends fold them bottom-up.
     MP_END = 32,

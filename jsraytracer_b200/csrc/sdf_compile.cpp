@@ -11,6 +11,7 @@
 //   Union/Intersection  : c0; c1; MIN|MAX; c2; MIN|MAX ...      (:83-101)
 //   Difference          : pos; neg; NEG; MAX                    (:116-118)
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <unordered_map>
@@ -33,7 +34,24 @@ struct SdfCompiler {
 
     SdfCompiler(const WireDoc& d, HostScene& o) : doc(d), out(o) {}
 
+    // Peephole fusion (JSRT_SDF_FUSE=0 emits the plain code): the interpreter pays a fetch + dispatch per instruction,
+    // and on the fractal scenes two thirds of the stream were stack shuffles.
+    //   leaf; MIN|MAX      -> leaf with idx = 1|2 (folds into the distance below instead of pushing)
+    //   MULS; MIN          -> MULS_MIN
+    //   SBEGIN ... SEND    -> elided when the group cannot round differently: it multiplies the scale at most once
+    //                         (1 * a = a exactly), or the enclosing scale is still exactly 1 (src/sdf.js:387-394)
+    bool fuse = true;
+    size_t prog_first = 0;                 // first instruction of the program being emitted (no fusion across programs)
+    bool scale_is_one = true;              // the current scale accumulator has not been multiplied yet
+    std::vector<bool> one_stack;
     void emit(int op, double a0 = 0, float f0 = 0, float f1 = 0, float f2 = 0, int idx = 0) {
+        if (fuse && out.sdf_code.size() > prog_first) {
+            SdfInstr& last = out.sdf_code.back();
+            if ((op == S_MIN || op == S_MAX) && last.op >= S_SPHERE && last.op <= S_TETRA && last.idx == 0) {
+                last.idx = (op == S_MIN) ? 1 : 2; --depth_dist; return;
+            }
+            if (op == S_MIN && last.op == S_MULS) { last.op = S_MULS_MIN; --depth_dist; return; }
+        }
         SdfInstr i{}; i.op = op; i.idx = idx; i.a0 = a0; i.f[0] = f0; i.f[1] = f1; i.f[2] = f2; i.f[3] = 0;
         out.sdf_code.push_back(i);
         switch (op) {
@@ -70,6 +88,7 @@ struct SdfCompiler {
         if (it != dist_prog.end()) return it->second;
         const int first = (int)out.sdf_code.size();
         depth_points = 1; depth_dist = 0; depth_scale = 1;
+        prog_first = out.sdf_code.size(); scale_is_one = true; one_stack.clear();
         node(n); emit(S_END);
         return dist_prog[n] = first;
     }
@@ -99,30 +118,47 @@ struct SdfCompiler {
         else fail("jsrt: unsupported SDF node '" + ty + "'");
     }
 
+    // how many times transformer `t` multiplies its caller's scale accumulator by something other than a literal 1
+    int scaleMultiplications(const Val* t) {
+        t = doc.resolve(t);
+        const std::string& ty = doc.typeName(t);
+        if (ty == "SDFTransformerSequence") { int m = 0; const Val* ts = doc.field(t, "transformers"); for (uint32_t i = 0; i < doc.length(ts); ++i) m += scaleMultiplications(doc.at(ts, i)); return m; }
+        if (ty == "SDFRecursiveTransformer") return (int)doc.number(doc.field(t, "iterations"), 0) * scaleMultiplications(doc.field(t, "transformer"));
+        return ty == "SDFMatrixTransformer" ? 1 : 0;
+    }
     void transformer(const Val* t) {
         t = doc.resolve(t);
         const std::string& ty = doc.typeName(t);
-        if (ty == "SDFTransformerSequence") {
-            const Val* ts = doc.field(t, "transformers");
-            emit(S_SBEGIN);
-            for (uint32_t i = 0; i < doc.length(ts); ++i) transformer(doc.at(ts, i));
-            emit(S_SEND);
-        } else if (ty == "SDFRecursiveTransformer") {
-            const int n = (int)doc.number(doc.field(t, "iterations"), 0);
-            emit(S_SBEGIN);
-            for (int i = 0; i < n; ++i) transformer(doc.field(t, "transformer"));
-            emit(S_SEND);
+        if (ty == "SDFTransformerSequence" || ty == "SDFRecursiveTransformer") {
+            // `let s = 1; for (...) s = s * st; return [p, s]` (src/sdf.js:387-394,408-415): a local scale accumulator
+            const bool seq = ty == "SDFTransformerSequence";
+            const Val* ts = seq ? doc.field(t, "transformers") : nullptr;
+            const int n = seq ? (int)doc.length(ts) : (int)doc.number(doc.field(t, "iterations"), 0);
+            int mults = 0;
+            for (int i = 0; i < n; ++i) mults += scaleMultiplications(seq ? doc.at(ts, i) : doc.field(t, "transformer"));
+            const bool elide = fuse && (mults <= 1 || scale_is_one);
+            if (!elide) { emit(S_SBEGIN); one_stack.push_back(scale_is_one); scale_is_one = true; }
+            for (int i = 0; i < n; ++i) transformer(seq ? doc.at(ts, i) : doc.field(t, "transformer"));
+            if (!elide) { emit(S_SEND); scale_is_one = one_stack.back() && scale_is_one; one_stack.pop_back(); }
         } else if (ty == "SDFMatrixTransformer") {
             double m[16]; doc.mat4(doc.field(t, "_inv_transform"), m);
             Xform x; Xform64 y; for (int i = 0; i < 12; ++i) { x.m[i] = (float)m[i]; y.m[i] = m[i]; }
             out.xforms.push_back(x); out.xforms64.push_back(y);
-            emit(S_XFORM, doc.number(doc.field(t, "_scale"), 1), 0, 0, 0, (int)out.xforms.size() - 1);
+            // every entry an f32 value: its product with an f32 coordinate is exact in f64 (device_math.cuh, xf64_apply_exact)
+            bool exact = fuse;
+            for (int i = 0; i < 12; ++i) if ((double)(float)m[i] != m[i]) exact = false;
+            emit(S_XFORM, doc.number(doc.field(t, "_scale"), 1), exact ? 1.f : 0.f, 0, 0, (int)out.xforms.size() - 1);
+            scale_is_one = false;
         } else if (ty == "SDFReflectionTransformer") {
             double n[4]; doc.vec(doc.field(t, "normal"), n);
             emit(S_REFL, doc.number(doc.field(t, "delta"), 0), (float)n[0], (float)n[1], (float)n[2]);
         } else if (ty == "SDFInfiniteRepetitionTransformer") {
             double s[4]; doc.vec(doc.field(t, "sizes"), s, kInf);
-            emit(S_REP, 0, (float)s[0], (float)s[1], (float)s[2]);
+            // one power-of-two period on all axes: the interpreter multiplies by its exact reciprocal (a0) instead of dividing
+            int e = 0;
+            const float s0 = (float)s[0];
+            const bool pow2 = fuse && (float)s[1] == s0 && (float)s[2] == s0 && std::isfinite(s0) && s0 > 0 && std::frexp((double)s0, &e) == 0.5;
+            emit(S_REP, pow2 ? 1.0 / (double)s0 : 0.0, s0, (float)s[1], (float)s[2], pow2 ? 1 : 0);
         } else fail("jsrt: unsupported SDF transformer '" + ty + "'");
     }
 
@@ -144,14 +180,17 @@ struct SdfCompiler {
         else if (ty == "SmoothDifferenceSDF") { node(doc.field(n, "positive")); node(doc.field(n, "negative")); emit(S_SMIN_NEGA, doc.number(doc.field(n, "k"), 1)); }
         else if (ty == "RoundSDF") { node(doc.field(n, "child_sdf")); emit(S_ADDC, -doc.number(doc.field(n, "rounding"), 0)); }
         else if (ty == "TransformSDF") {
-            emit(S_PUSHP); transformer(doc.field(n, "transformer")); node(doc.field(n, "child_sdf")); emit(S_MULS); emit(S_POPP);
+            emit(S_PUSHP); one_stack.push_back(scale_is_one); scale_is_one = true;
+            transformer(doc.field(n, "transformer")); node(doc.field(n, "child_sdf")); emit(S_MULS); emit(S_POPP);
+            scale_is_one = one_stack.back(); one_stack.pop_back();
         }
         else if (ty == "RecursiveTransformUnionSDF") {
             const int it = (int)doc.number(doc.field(n, "iterations"), 0);
-            emit(S_PUSHP);
+            emit(S_PUSHP); one_stack.push_back(scale_is_one); scale_is_one = true;
             node(doc.field(n, "sdf"));
             for (int i = 0; i < it; ++i) { transformer(doc.field(n, "transformer")); node(doc.field(n, "sdf")); emit(S_MULS); emit(S_MIN); }
             emit(S_POPP);
+            scale_is_one = one_stack.back(); one_stack.pop_back();
         }
         else fail("jsrt: unsupported SDF node '" + ty + "'");
     }
@@ -161,8 +200,10 @@ struct SdfCompiler {
 
 int compileSdf(const WireDoc& doc, const Val* g, HostScene& out) {
     SdfCompiler c(doc, out);
+    if (const char* e = getenv("JSRT_SDF_FUSE")) c.fuse = atoi(e) != 0;
     SdfProgram p{};
     p.first_instr = (int)out.sdf_code.size();
+    c.prog_first = out.sdf_code.size();
     c.node(doc.field(g, "root_sdf"));
     c.emit(S_END);
     p.instr_count = (int)out.sdf_code.size() - p.first_instr;

@@ -24,6 +24,11 @@ struct DeviceScene {
     const int* sdf_tops;       // indices of the T_SDF entries of `tops`
     const Texture* textures;   // TextureMaterialColor table + RGBA8 texels
     const unsigned char* texels;
+    // Analytic-primitive table (prims_wave): every Primitive of world.objects that is not inside a BVHAggregate and is
+    // not a top-level SDF, grouped by geometry kind so that each group runs its own tight loop.  Two copies: all of them
+    // (closest-hit rays) and the shadow casters only (shadow rays, src/world.js:117-118).
+    const APrim* atab;
+    int atab_end[2][AG_COUNT]; // [0: closest-hit table | 1: shadow table][group]: end offset of the group within `atab`
     int n_sdf_tops, pad0, pad1, pad2;
     int n_top, n_lights, light_samples, max_depth;
     float bg[3];
@@ -156,11 +161,21 @@ struct TraceIO {
     int* list_count;                    //   prims_wave with warp-aggregated appends, consumed by bvh_wave
 };
 
+// One radiance term into the pixel's sum.  sm_90+ has a 128-bit vector reduction (red.global.add.v4.f32): one L2
+// operation per term instead of three scalar ones (JSRT_ACCUM_VEC4=0 keeps the scalar form for A/B runs).
+#ifndef JSRT_ACCUM_VEC4
+#define JSRT_ACCUM_VEC4 1
+#endif
 JSRT_DEV void accum_add3(float4* accum, uint32_t pixel, float3 c) {
+#if JSRT_ACCUM_VEC4
+    if (c.x != 0.f || c.y != 0.f || c.z != 0.f)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(accum + pixel), "f"(c.x), "f"(c.y), "f"(c.z), "f"(0.f) : "memory");
+#else
     float* a = reinterpret_cast<float*>(accum + pixel);
     if (c.x != 0.f) atomicAdd(a + 0, c.x);
     if (c.y != 0.f) atomicAdd(a + 1, c.y);
     if (c.z != 0.f) atomicAdd(a + 2, c.z);
+#endif
 }
 
 JSRT_DEV bool better_hit(float t, int top, const Hit& best) { return t < best.t || (t == best.t && top < best.top); }
@@ -235,6 +250,24 @@ JSRT_DEV bool slab_any(const float4 n0, const float4 n1, const LocalRay& r, floa
     return r.par ? slab_general(n0, n1, r, minD, maxD, bound) : slab_fast(n0, n1, r, minD, fminf(maxD, bound));
 }
 
+// AABB.intersect (src/geometry.js:173-179) over AABB.get_intersects (:189-209) for a box primitive.  Rays without a
+// parallel axis take the sign-ordered form of slab_fast (the per-axis sort of (p+h)/d, (p-h)/d is known from the sign
+// of d; products with 1/d instead of six divisions); the others the reference's general form.
+JSRT_DEV float box_prim_intersect(float3 c, float3 h, float3 o, float3 d, float minD, float maxD) {
+    float t0, t1;
+    if (!(fabsf(d.x) > 0.0000001f) || !(fabsf(d.y) > 0.0000001f) || !(fabsf(d.z) > 0.0000001f)) {
+        if (!aabb_intersects(c, h, o, d, minD, maxD, t0, t1)) return -CUDART_INF_F;
+    } else {
+        const float ix = 1.0f / d.x, iy = 1.0f / d.y, iz = 1.0f / d.z;
+        const float px = c.x - o.x, py = c.y - o.y, pz = c.z - o.z;
+        const float sx = copysignf(h.x, d.x), sy = copysignf(h.y, d.y), sz = copysignf(h.z, d.z);
+        t0 = fmaxf(fmaxf((px - sx) * ix, (py - sy) * iy), (pz - sz) * iz);
+        t1 = fminf(fminf((px + sx) * ix, (py + sy) * iy), (pz + sz) * iz);
+        if (!(t0 <= t1) || t1 < minD || t0 > maxD) return -CUDART_INF_F;
+    }
+    return (t0 >= minD) ? t0 : t1;
+}
+
 // prims_wave: every top-level Primitive / plain Aggregate against every ray of the queue, one ray per thread,
 // then the root box of every BVHAggregate (the first test of BVHAggregateNode.intersect, src/aggregates.js:208-209).
 // Rays that hit no root box are finished here (most rays: 92 % of bunny_path's camera rays miss the mesh's
@@ -259,19 +292,72 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_pr
             float minD, maxD; bool primary;
             ray_window<MODE>(d4, minD, maxD, primary);
             Work* work = (COUNT && primary) ? work_primary : work_other;
-            for (int ti = 0; ti < sc.n_top; ++ti) {
-                const int4 ta = __ldg(reinterpret_cast<const int4*>(sc.tops + ti));          // kind, xform, first_prim, prim_count
-                if (ta.x == T_BVH || ta.x == T_SDF) continue;
-                float3 lo = o, ld = d;
-                if (ta.x == T_LIST) { const XformReg m = load_xform(sc.xforms, ta.y); lo = xf_point(m, o); ld = xf_dir(m, d); }   // src/aggregates.js:15
-                for (int k = 0; k < ta.w; ++k) {
-                    if (COUNT) ++work->top_prims;
-                    float tl = 0.f;
-                    const float t = placed_prim_intersect<HAS_SDF>(sc, ta.z + k, lo, ld, minD, maxD, best.t, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
-                    if (t > minD && t < maxD && t < best.t) { best.t = t; best.prim = ta.z + k; best.top = ti; best.t_lo = tl; if (ANY_HIT) break; }
-                }
+            // World.getMinimumIntersection (src/world.js:7-15) over the analytic primitives, one tight loop per geometry
+            // kind (a single loop over world.objects with a switch cost 285 instructions per test on cornell_box_path,
+            // the compiler having hoisted the sphere's f64 set-up in front of the switch: profiles/r1_s3).  The
+            // reference's "first object wins exact ties" is the static rank (top, prim), so the order of the tests is free.
+            const APrim* const tab = sc.atab;
+            const int tb = ANY_HIT ? 1 : 0;
+            int k = (ANY_HIT ? sc.atab_end[0][AG_COUNT - 1] : 0);
+            #define JSRT_ACCEPT(T, TL)                                                                                              \
+                if ((T) > minD && (T) < maxD && ((T) < best.t || ((T) == best.t && (e0.y < best.top || (e0.y == best.top && e0.x < best.prim))))) { \
+                    best.t = (T); best.prim = e0.x; best.top = e0.y; best.t_lo = (TL); }
+            #define JSRT_ENTRY()                                                                                                    \
+                const int4 e0 = __ldg(reinterpret_cast<const int4*>(tab + k));     /* prim, top, agg_xform, xform */                \
+                const int4 e1 = __ldg(reinterpret_cast<const int4*>(tab + k) + 1); /* geom_index, flags */                          \
+                if (COUNT) ++work->top_prims;
+            // ray.getTransformed(inv_transform) (src/world.js:120), after the enclosing Aggregate's own map if there is one
+            #define JSRT_LOCAL_RAY()                                                                                                \
+                float3 lo = o, ld = d;                                                                                              \
+                if (e0.z >= 0) { const XformReg ma = load_xform(sc.xforms, e0.z); lo = xf_point(ma, o); ld = xf_dir(ma, d); }         \
+                if (!(e1.y & PF_IDENTITY_XFORM)) { const XformReg m = load_xform(sc.xforms, e0.w); const float3 a = xf_point(m, lo), b = xf_dir(m, ld); lo = a; ld = b; }
+            for (; k < sc.atab_end[tb][AG_PLANE]; ++k) {                           // SimplePlane.intersect src/geometry.js:246-248
+                JSRT_ENTRY()
+                float oz, dz;
+                if (e0.z < 0 && !(e1.y & PF_IDENTITY_XFORM)) {                     // only the z row of the local ray is needed
+                    const float4 r2 = __ldg(reinterpret_cast<const float4*>(sc.xforms + e0.w) + 2);
+                    oz = r2.x * o.x + r2.y * o.y + r2.z * o.z + r2.w; dz = r2.x * d.x + r2.y * d.y + r2.z * d.z;
+                } else { JSRT_LOCAL_RAY() oz = lo.z; dz = ld.z; }
+                const float t = (dz != 0.f) ? -oz / dz : -CUDART_INF_F;
+                JSRT_ACCEPT(t, 0.f)
                 if (ANY_HIT && best.prim >= 0) break;
             }
+            if (!(ANY_HIT && best.prim >= 0)) for (; k < sc.atab_end[tb][AG_SQUARE]; ++k) {   // Square.intersect src/geometry.js:287-291
+                JSRT_ENTRY()
+                JSRT_LOCAL_RAY()
+                const float t = plane_t(lo, ld);
+                const float x = __fadd_rn(lo.x, __fmul_rn(ld.x, t)), y = __fadd_rn(lo.y, __fmul_rn(ld.y, t));
+                if (-0.5f <= x && x <= 0.5f && -0.5f <= y && y <= 0.5f) { JSRT_ACCEPT(t, 0.f) }
+                if (ANY_HIT && best.prim >= 0) break;
+            }
+            if (!(ANY_HIT && best.prim >= 0)) for (; k < sc.atab_end[tb][AG_BOX]; ++k) {      // AABB.intersect src/geometry.js:173-179
+                JSRT_ENTRY()
+                JSRT_LOCAL_RAY()
+                float3 c = f3(0.f, 0.f, 0.f), h = f3(0.5f, 0.5f, 0.5f);
+                if (e1.x >= 0) { const float* b = sc.boxes + 8 * e1.x; c = f3(__ldg(b), __ldg(b + 1), __ldg(b + 2)); h = f3(__ldg(b + 4), __ldg(b + 5), __ldg(b + 6)); }
+                const float t = box_prim_intersect(c, h, lo, ld, minD, maxD);
+                JSRT_ACCEPT(t, 0.f)
+                if (ANY_HIT && best.prim >= 0) break;
+            }
+            if (!(ANY_HIT && best.prim >= 0)) for (; k < sc.atab_end[tb][AG_SPHERE]; ++k) {      // Sphere.staticIntersect src/geometry.js:429-442
+                JSRT_ENTRY()
+                JSRT_LOCAL_RAY()
+                const float t = sphere_intersect(lo, ld, minD);
+                JSRT_ACCEPT(t, 0.f)
+                if (ANY_HIT && best.prim >= 0) break;
+            }
+            if (!(ANY_HIT && best.prim >= 0)) for (; k < sc.atab_end[tb][AG_OTHER]; ++k) {    // every other geometry: the general code
+                JSRT_ENTRY()
+                float3 lo = o, ld = d;
+                if (e0.z >= 0) { const XformReg ma = load_xform(sc.xforms, e0.z); lo = xf_point(ma, o); ld = xf_dir(ma, d); }
+                float tl = 0.f;
+                const float t = placed_prim_intersect<HAS_SDF>(sc, e0.x, lo, ld, minD, maxD, best.t, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
+                JSRT_ACCEPT(t, tl)
+                if (ANY_HIT && best.prim >= 0) break;
+            }
+            #undef JSRT_ACCEPT
+            #undef JSRT_ENTRY
+            #undef JSRT_LOCAL_RAY
             if (!(ANY_HIT && best.prim >= 0)) {
                 for (int b = 0; b < sc.n_bvh; ++b) {
                     const int4* tp = reinterpret_cast<const int4*>(sc.tops + __ldg(sc.bvh_tops + b));
@@ -546,9 +632,16 @@ JSRT_DEV void sdf_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     };
 
     for (;;) {
+        // ---- write finished rays, hand out new ones.  Repeated until fewer than REFILL_T lanes are idle or the queue is
+        // empty: a new ray that misses the SDF's box (or needs no march) is done at once, and one evaluation of the
+        // interpreter costs thousands of instructions, so no lane should enter it empty-handed while rays are waiting
+        // (measured before: 17 of 32 lanes active, profiles/r1_s3) ----
+        bool all_done = false;
+        for (;;) {
         const unsigned idle_mask = __ballot_sync(FULL, cur < 0 || done);
         const int n_idle = __popc(idle_mask);
-        if (n_idle >= REFILL_T || idle_mask == FULL) {
+        if (!(n_idle >= REFILL_T || idle_mask == FULL)) break;
+        {
             if (cur >= 0 && done) {
                 finish_ray<MODE>(io, cur, best, o4);
                 if (MODE == TM_EXTEND && io.aux) io.aux[cur] = make_float4(nrm.x, nrm.y, nrm.z, has_nrm ? 1.f : 0.f);
@@ -578,8 +671,10 @@ JSRT_DEV void sdf_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                     else enter();
                 }
                 pool_next += min(avail, n_idle);
-            } else if (exhausted && __all_sync(FULL, cur < 0)) break;
+            } else { all_done = exhausted && __all_sync(FULL, cur < 0); break; }
         }
+        }
+        if (all_done) break;
         if (cur >= 0 && !done) {
             // ---- one distance evaluation per iteration: a step of the sphere-tracing loop (src/sdf.js:22-38)
             // or one of the four samples of the forward-difference normal (src/sdf.js:42-46) -----------------
