@@ -34,6 +34,11 @@ extern "C" {
 #define JSRT_FLAG_COUNT_WORK 2  /* instrumented kernels: count BVH nodes visited / primitives tested / SDF evaluations
                                    per ray class (slower; defines the roofline's algorithmic bytes, never timed) */
 
+#define JSRT_FLAG_AOV 4         /* also accumulate the GL path's auxiliary buffers for these passes: first-hit normal and
+                                   distance sums and the running per-pixel variance (gl/src/WebGLRendererAdapter.js:352-356,
+                                   376-379); read them with jsrt_read_aov.  Radiance then goes through a per-sample buffer
+                                   (slower); the image is the same up to FP32 summation order */
+
 typedef struct jsrt_scene jsrt_scene;
 
 /* Number of CUDA devices visible to the process (0 if none / no driver). */
@@ -87,6 +92,13 @@ int jsrt_resolve_rgba8(jsrt_scene*, uint8_t* out);
 /* Reads the raw accumulation buffer: out = W*H*4 floats (sum r, g, b, sample
  * count per pixel); *passes = passes accumulated since the last reset. */
 int jsrt_read_accum(jsrt_scene*, float* out, int* passes);
+
+/* Replaces: the GL renderer's auxiliary render targets (gl/src/WebGLRendererAdapter.js:352-356 `outNormalSum`,
+ * `outSampleVariance`; :376-379 first-hit distance / normal), filled by passes rendered with JSRT_FLAG_AOV.
+ * normal_depth = W*H*4 floats: sum over samples of the first hit's world normal (xyz) and of its distance from the
+ * ray origin (w).  variance = W*H*4 floats: xyz = the GL shader's running variance sums (divide by the sample count
+ * like its display pass does), w = number of samples whose camera ray hit something.  Zero if no AOV pass was rendered. */
+int jsrt_read_aov(jsrt_scene*, float* normal_depth, float* variance);
 
 /* Device pointer of the W*H float4 accumulation buffer (for NCCL reductions
  * across GPUs issued by the host process). */

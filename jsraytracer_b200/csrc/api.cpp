@@ -74,6 +74,11 @@ int jsrt_reset_accum(jsrt_scene* s) { if (needDevice(s)) return 1; JSRT_TRY(s->r
 int jsrt_synchronize(jsrt_scene* s) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->synchronize()) }
 int jsrt_resolve_rgba8(jsrt_scene* s, uint8_t* out) { if (needDevice(s)) return 1; if (!out) { g_error = "jsrt: null output buffer"; return 1; } JSRT_TRY(s->renderer->resolve(out)) }
 int jsrt_read_accum(jsrt_scene* s, float* out, int* passes) { if (needDevice(s)) return 1; if (!out) { g_error = "jsrt: null output buffer"; return 1; } JSRT_TRY(s->renderer->readAccum(out, passes)) }
+int jsrt_read_aov(jsrt_scene* s, float* normal_depth, float* variance) {
+    if (needDevice(s)) return 1;
+    if (!normal_depth || !variance) { g_error = "jsrt: null output buffer"; return 1; }
+    JSRT_TRY(s->renderer->readAov(normal_depth, variance))
+}
 void* jsrt_accum_device_ptr(jsrt_scene* s) { return (s && s->renderer) ? s->renderer->accumPtr() : nullptr; }
 int jsrt_add_passes(jsrt_scene* s, int n) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->addPasses(n)) }
 int jsrt_primary_hits(jsrt_scene* s, int32_t* prim_id, float* t) { if (needDevice(s)) return 1; if (!prim_id || !t) { g_error = "jsrt: null output buffer"; return 1; } JSRT_TRY(s->renderer->primaryHits(prim_id, t)) }

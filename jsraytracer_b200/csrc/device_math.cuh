@@ -244,7 +244,8 @@ __device__ const double kPow10[32] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e
 __device__ const double kInvPow10[23] = {1.0 / 1e0, 1.0 / 1e1, 1.0 / 1e2, 1.0 / 1e3, 1.0 / 1e4, 1.0 / 1e5, 1.0 / 1e6, 1.0 / 1e7, 1.0 / 1e8, 1.0 / 1e9,
                                          1.0 / 1e10, 1.0 / 1e11, 1.0 / 1e12, 1.0 / 1e13, 1.0 / 1e14, 1.0 / 1e15, 1.0 / 1e16, 1.0 / 1e17, 1.0 / 1e18,
                                          1.0 / 1e19, 1.0 / 1e20, 1.0 / 1e21, 1.0 / 1e22};
-JSRT_DEV double js_to_precision8_slow(double x) {
+// (out of line: never taken by coordinates an SDF scene produces, and its exp10 / log10 would sit in the interpreter's hot code)
+__device__ __noinline__ double js_to_precision8_slow(double x) {
     const double ax = fabs(x);
     int e = (int)floor((double)(ilogb(ax)) * 0.30102999566398120);      // floor(log10(ax)) or one less
     int k = 7 - e;

@@ -34,6 +34,15 @@ constexpr int kBlock = 256;
 #ifndef JSRT_SHADE_MIN_BLOCKS
 #define JSRT_SHADE_MIN_BLOCKS 3
 #endif
+// SDF march: the interpreter stalls on fixed-latency f64 dependency chains ("wait" 37 % of stall samples at 2 CTAs / SM,
+// FP64 pipe 7.5 % busy), so occupancy beats registers: SDF_Menger 1080p extend 177.7 / 134.6 / 125.5 ms and shadow
+// 68.8 / 56.5 / 61.2 ms per 16 passes at 2 / 3 / 4 CTAs per SM (128 / 80 / 64 registers; profiles/r1_s3)
+#ifndef JSRT_SDF_MIN_BLOCKS
+#define JSRT_SDF_MIN_BLOCKS 4
+#endif
+#ifndef JSRT_SDF_SHADOW_MIN_BLOCKS
+#define JSRT_SDF_SHADOW_MIN_BLOCKS 3
+#endif
 #ifndef JSRT_BVH_MIN_BLOCKS
 #define JSRT_BVH_MIN_BLOCKS 4      // 64 registers: 4 CTAs / SM (measured against 3 and 5: profiles/r1_ncu_summary.md)
 #endif
@@ -130,7 +139,7 @@ __global__ void __launch_bounds__(kBlock) prims_kernel(const __grid_constant__ D
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(kBlock) sdf_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
+__global__ void __launch_bounds__(kBlock, MODE == TM_SHADOW ? JSRT_SDF_SHADOW_MIN_BLOCKS : JSRT_SDF_MIN_BLOCKS) sdf_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
     Work wp, ws;
     sdf_wave<MODE, COUNT>(sc, io, &wp, &ws);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
@@ -152,7 +161,8 @@ template <bool HAS_SDF, bool SORT>
 __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ DeviceScene sc, RayQueue q, const int* __restrict__ count,
                                                         const float4* __restrict__ hits, RayQueue next, int* next_count, int next_cap,
                                                         ShadowQueue sq, int* shadow_count, int shadow_cap, float4* __restrict__ accum,
-                                                        unsigned long long seed, unsigned long long* stats, int* overflow, const float4* __restrict__ sdf_normals) {
+                                                        unsigned long long seed, unsigned long long* stats, int* overflow, const float4* __restrict__ sdf_normals,
+                                                        int accum_stride, int pass0, float4* __restrict__ aov_nd, float4* __restrict__ aov_var) {
     const int n = *count;
     const int stride = gridDim.x * blockDim.x;
     unsigned long long my_shaded = 0;
@@ -213,10 +223,11 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
             o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z); thr = f3(w4.x, w4.y, w4.z);
             pixel = (uint32_t)__float_as_int(o4.w); node = (uint32_t)__float_as_int(d4.w);
             const int packed = __float_as_int(w4.w); depth_rem = packed & 0xff; pass = packed >> 8;
+            const uint32_t slot = pixel + (uint32_t)(pass - pass0) * (uint32_t)accum_stride;      // JSRT_FLAG_AOV: radiance slot of this sample (stride 0 otherwise)
             const int prim = __float_as_int(h4.y), top = __float_as_int(h4.z);
             const float t = h4.x;
             if (prim < 0) {
-                accum_add(accum, pixel, thr * f3(sc.bg[0], sc.bg[1], sc.bg[2]));      // `return this.bg_color`
+                accum_add(accum, slot, thr * f3(sc.bg[0], sc.bg[1], sc.bg[2]));      // `return this.bg_color`
             } else {
                 hit = true; ++my_shaded;
                 const int4* pp = reinterpret_cast<const int4*>(sc.prims + prim);
@@ -251,6 +262,13 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
                 material_data<HAS_SDF>(sc, pa.x, pa.y, flags, lp, ln, s.uv, s.has_uv, s.basecolor, &sn);
                 s.normal = normalized3(xf_normal(inv, ln));
                 s.position = ray_point_f64(o, d, td);
+                if (aov_nd && node == 1u) {
+                    // first-hit AOVs of the GL path (gl/src/WebGLRendererAdapter.js:376-379: `initial_intersection_distance =
+                    // length(r.o - intersect_position)`, `first_hit_normal.xyz = intersect_normal`), summed per pixel
+                    const float3 e = s.position - o;
+                    accum_add3w(aov_nd, pixel, s.normal, sqrtf(dot3(e, e)));
+                    atomicAdd(&aov_var[pixel].w, 1.0f);
+                }
                 mat = sc.materials + pa.z;
                 if (mat->uv_from_position) {          // PositionalUVMaterial.color src/materials.js:188-192
                     const float dx = (float)dsub(mat->uv_origin[0], s.position.x), dy = (float)dsub(mat->uv_origin[1], s.position.y), dz = (float)dsub(mat->uv_origin[2], s.position.z);
@@ -259,13 +277,13 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
                 }
                 node_key = rng_node_key(rng_sample_key(seed, pixel, (uint32_t)pass), node);
                 if (mat->kind == M_SOLID) {
-                    accum_add(accum, pixel, thr * color_eval(sc, mat->ambient, s));
+                    accum_add(accum, slot, thr * color_eval(sc, mat->ambient, s));
                     hit = false;                 // no lights, no children (src/materials.js:153-155)
                 } else if (mat->kind == M_TRANSPARENT) {
-                    accum_add(accum, pixel, thr * (color_eval(sc, mat->ambient, s) * mat->smoothness));
+                    accum_add(accum, slot, thr * (color_eval(sc, mat->ambient, s) * mat->smoothness));
                 } else {
                     base_factors(sc, *mat, s, d, f);
-                    accum_add(accum, pixel, thr * f.ambient);      // `let ret = data.ambient`
+                    accum_add(accum, slot, thr * f.ambient);      // `let ret = data.ambient`
                 }
             }
         }
@@ -319,7 +337,7 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
                     const int slot = base_s + j * n_lit + rank_s;
                     if (slot < shadow_cap) {
                         sq.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
-                        sq.d[slot] = make_float4(ls.direction.x, ls.direction.y, ls.direction.z, 0.f);
+                        sq.d[slot] = make_float4(ls.direction.x, ls.direction.y, ls.direction.z, __int_as_float(pass));
                         sq.c[slot] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
                     } else *overflow = 1;
                 }
@@ -347,6 +365,41 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
     // per-warp reduction of the shaded-hit count, one atomic per warp
     for (int off = 16; off; off >>= 1) my_shaded += __shfl_down_sync(0xffffffffu, my_shaded, off);
     if ((threadIdx.x & 31) == 0 && my_shaded) atomicAdd(stats + ST_SHADED, my_shaded);
+}
+
+// JSRT_FLAG_AOV: the batch's per-sample radiance -> pixel sums + running variance, one thread per pixel, samples of a
+// pixel in pass order.  The recurrence is the GL path's (gl/src/WebGLRendererAdapter.js:352-356), evaluated in FP32 like
+// its shader: count1 = n + 1; mean = sum / count1 (sum and n before this sample); delta = sample - mean;
+// delta2 = sample - (delta / count1 + mean); variance += delta * delta2; sum += sample.
+__global__ void __launch_bounds__(kBlock) fold_samples_kernel(const __grid_constant__ GenParams g, int pass0, int span, float4* __restrict__ sample_rad,
+                                                            float4* __restrict__ accum, float4* __restrict__ var, int npix) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < g.npix_active; idx += stride) {
+        const int py = idx / g.ncols, px = g.x_offset + (idx % g.ncols) * g.x_delt;
+        const int pixel = py * g.width + px;
+        int members = 0;
+        for (int p = 0; p < span; ++p) {
+            const long long gs = (long long)(pass0 + p - g.first_pass) * g.npix_active + idx;
+            if (gs >= g.first_sample && gs < g.first_sample + g.n_samples) ++members;
+        }
+        if (!members) continue;
+        float4 a = accum[pixel], v = var[pixel];
+        float n = a.w - (float)members;             // generate_kernel has already counted this batch's samples
+        for (int p = 0; p < span; ++p) {
+            const long long gs = (long long)(pass0 + p - g.first_pass) * g.npix_active + idx;
+            if (!(gs >= g.first_sample && gs < g.first_sample + g.n_samples)) continue;
+            const size_t slot = (size_t)p * npix + pixel;
+            const float4 L = sample_rad[slot];
+            sample_rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float count1 = n + 1.f;
+            const float mx = a.x / count1, my = a.y / count1, mz = a.z / count1;
+            const float dx = L.x - mx, dy = L.y - my, dz = L.z - mz;
+            v.x += dx * (L.x - (dx / count1 + mx)); v.y += dy * (L.y - (dy / count1 + my)); v.z += dz * (L.z - (dz / count1 + mz));
+            a.x += L.x; a.y += L.y; a.z += L.z;
+            n += 1.f;
+        }
+        accum[pixel] = a; var[pixel] = v;
+    }
 }
 
 // bookkeeping between levels: fold queue sizes into the ray statistics and recycle the counters
@@ -406,13 +459,17 @@ struct Renderer::Impl {
     float4* accum = nullptr;
     RayQueue rq[2]{}; float4* hits = nullptr; float4* shadow_hits = nullptr; ShadowQueue sq{};
     float4* sdf_normals = nullptr;
+    // JSRT_FLAG_AOV (allocated on first use): first-hit normal / distance sums, variance sums (w: first hits), and the
+    // per-sample radiance of the batch in flight (`sample_span` frames)
+    float4 *aov_nd = nullptr, *aov_var = nullptr, *sample_rad = nullptr;
+    int sample_span = 0;
     int2* work_list = nullptr;          // BVH work list (trace.cuh), shared by the extend and the shadow wave of a level
     Counters* counters = nullptr;
     int* overflow = nullptr;
     int ray_cap = 0, shadow_cap = 0, batch = 0;
     int passes = 0;
     size_t scene_bytes = 0, queue_bytes = 0;
-    int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0, grid_bvh = 0, grid_sdf = 0;
+    int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0, grid_bvh = 0, grid_sdf[2] = {0, 0};
     unsigned long long launches = 0;
     bool profiling = false, has_sdf = false, sort_shade = false;
     double ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};     // 0-3: kernel classes; 4-9: prims / bvh / sdf kernels of extend, shadow
@@ -525,7 +582,8 @@ struct Renderer::Impl {
                              : (sort_shade ? grid_for((const void*)shade_kernel<false, true>) : grid_for((const void*)shade_kernel<false, false>));
         grid_shadow = has_sdf ? grid_for((const void*)prims_kernel<TM_SHADOW, false, true>) : grid_for((const void*)prims_kernel<TM_SHADOW, false, false>);
         grid_gen = grid_for((const void*)generate_kernel);
-        grid_sdf = grid_for((const void*)sdf_kernel<TM_EXTEND, false>);
+        grid_sdf[TM_EXTEND] = grid_for((const void*)sdf_kernel<TM_EXTEND, false>);
+        grid_sdf[TM_SHADOW] = grid_for((const void*)sdf_kernel<TM_SHADOW, false>);
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
         CK(cudaStreamSynchronize(stream));
         setupAccumPersistence(prop);
@@ -633,8 +691,8 @@ struct Renderer::Impl {
             ++launches;
             io.final_pass = 1;
             io.cursor = io0.cursor + 2;          // cursor_extend_sdf / cursor_shadow_sdf
-            if (count_work) sdf_kernel<MODE, true><<<grid_sdf, kBlock, 0, stream>>>(ds, io);
-            else sdf_kernel<MODE, false><<<grid_sdf, kBlock, 0, stream>>>(ds, io);
+            if (count_work) sdf_kernel<MODE, true><<<grid_sdf[MODE], kBlock, 0, stream>>>(ds, io);
+            else sdf_kernel<MODE, false><<<grid_sdf[MODE], kBlock, 0, stream>>>(ds, io);
         }
         mark();
         if (profiling) {
@@ -648,11 +706,26 @@ struct Renderer::Impl {
         io.list = work_list; io.list_count = &counters->list_extend;
         timed(1, [&] { launchTrace<TM_EXTEND>(io, count_work, grid_extend); });
     }
-    void launchShadow(bool count_work) {
-        TraceIO io{}; io.o = sq.o; io.d = sq.d; io.c = sq.c; io.hits = shadow_hits; io.accum = accum; io.count = &counters->shadow; io.cap = shadow_cap;
+    void launchShadow(bool count_work, float4* radiance, int accum_stride, int pass0) {
+        TraceIO io{}; io.o = sq.o; io.d = sq.d; io.c = sq.c; io.hits = shadow_hits; io.accum = radiance; io.count = &counters->shadow; io.cap = shadow_cap;
+        io.accum_stride = accum_stride; io.pass0 = pass0;
         io.cursor = &counters->cursor_shadow; io.stats = counters->stats;
         io.list = work_list; io.list_count = &counters->list_shadow;
         timed(3, [&] { launchTrace<TM_SHADOW>(io, count_work, grid_shadow); });
+    }
+
+    void ensureAov(int npix_active) {
+        const size_t npix = (size_t)hs.width * hs.height;
+        if (!aov_nd) {
+            aov_nd = dalloc<float4>(npix); aov_var = dalloc<float4>(npix);
+            CK(cudaMemsetAsync(aov_nd, 0, npix * sizeof(float4), stream)); CK(cudaMemsetAsync(aov_var, 0, npix * sizeof(float4), stream));
+        }
+        const int need = batch / std::max(1, npix_active) + 2;        // frames a batch of camera samples can touch
+        if (need > sample_span) {
+            // (the old, smaller buffer stays in `allocs` until the scene is destroyed: this happens at most when the striping changes)
+            sample_rad = dalloc<float4>(npix * (size_t)need); sample_span = need;
+            CK(cudaMemsetAsync(sample_rad, 0, npix * (size_t)need * sizeof(float4), stream));
+        }
     }
 
     GenParams genParams(int first_pass, uint64_t seed, int x_offset, int x_delt, int flags) const {
@@ -672,10 +745,18 @@ struct Renderer::Impl {
         if (x_offset < 0) throw std::runtime_error("jsrt: x_offset must be >= 0");
         GenParams g = genParams(first_pass, seed, x_offset, x_delt, flags);
         const bool count_work = (flags & 2) != 0;
+        const bool aov = (flags & 4) != 0;
+        const int npix = hs.width * hs.height;
+        if (aov) ensureAov(g.npix_active);
         const long long total = (long long)g.npix_active * n_passes;
         for (long long done = 0; done < total; done += batch) {
             g.first_sample = done;
             g.n_samples = (int)std::min<long long>(batch, total - done);
+            // AOV renders: radiance terms land in the per-sample buffer, folded into the pixel sums after the batch
+            const int pass0 = first_pass + (int)(done / std::max(1, g.npix_active));
+            const int span = aov ? first_pass + (int)((done + g.n_samples - 1) / std::max(1, g.npix_active)) - pass0 + 1 : 0;
+            float4* const radiance = aov ? sample_rad : accum;
+            const int rstride = aov ? npix : 0;
             set_count_kernel<<<1, 1, 0, stream>>>(counters, 0, g.n_samples, 1); ++launches;
             timed(0, [&] { generate_kernel<<<grid_gen, kBlock, 0, stream>>>(g, rq[0], accum); });
             int cur = 0;
@@ -683,15 +764,17 @@ struct Renderer::Impl {
                 launchExtend(cur, count_work);
                 timed(2, [&] {
                     #define JSRT_SHADE(S, O) shade_kernel<S, O><<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap, \
-                                                                                              sq, &counters->shadow, shadow_cap, accum, seed, counters->stats, overflow, has_sdf ? sdf_normals : nullptr)
+                                                                                              sq, &counters->shadow, shadow_cap, radiance, seed, counters->stats, overflow, has_sdf ? sdf_normals : nullptr, \
+                                                                                              rstride, pass0, aov ? aov_nd : nullptr, aov ? aov_var : nullptr)
                     if (has_sdf) { if (sort_shade) JSRT_SHADE(true, true); else JSRT_SHADE(true, false); }
                     else { if (sort_shade) JSRT_SHADE(false, true); else JSRT_SHADE(false, false); }
                     #undef JSRT_SHADE
                 });
-                if (hs.light_samples > 0) launchShadow(count_work);
+                if (hs.light_samples > 0) launchShadow(count_work, radiance, rstride, pass0);
                 level_end_kernel<<<1, 1, 0, stream>>>(counters, cur, level, ray_cap, shadow_cap); ++launches;
                 cur ^= 1;
             }
+            if (aov) { fold_samples_kernel<<<grid_gen, kBlock, 0, stream>>>(g, pass0, span, sample_rad, accum, aov_var, npix); ++launches; }
         }
         CK(cudaGetLastError());
         if (x_offset == 0 && g.x_delt == 1) passes += n_passes; else passes = std::max(passes, first_pass + n_passes);
@@ -712,6 +795,18 @@ void Renderer::resetAccum() {
     CK(cudaSetDevice(impl_->device));
     CK(cudaMemsetAsync(impl_->accum, 0, (size_t)impl_->hs.width * impl_->hs.height * sizeof(float4), impl_->stream));
     impl_->passes = 0;
+    if (impl_->aov_nd) {
+        const size_t bytes = (size_t)impl_->hs.width * impl_->hs.height * sizeof(float4);
+        CK(cudaMemsetAsync(impl_->aov_nd, 0, bytes, impl_->stream)); CK(cudaMemsetAsync(impl_->aov_var, 0, bytes, impl_->stream));
+    }
+}
+void Renderer::readAov(float* normal_depth, float* variance) {
+    CK(cudaSetDevice(impl_->device));
+    const size_t bytes = (size_t)impl_->hs.width * impl_->hs.height * sizeof(float4);
+    if (!impl_->aov_nd) { memset(normal_depth, 0, bytes); memset(variance, 0, bytes); return; }
+    CK(cudaMemcpyAsync(normal_depth, impl_->aov_nd, bytes, cudaMemcpyDeviceToHost, impl_->stream));
+    CK(cudaMemcpyAsync(variance, impl_->aov_var, bytes, cudaMemcpyDeviceToHost, impl_->stream));
+    synchronize();
 }
 void Renderer::resolve(uint8_t* out) {
     CK(cudaSetDevice(impl_->device));

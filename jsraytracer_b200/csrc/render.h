@@ -28,6 +28,7 @@ public:
     void resetAccum();
     void resolve(uint8_t* out_rgba);
     void readAccum(float* out, int* passes);
+    void readAov(float* normal_depth, float* variance);
     void* accumPtr();
     void addPasses(int n);
     void primaryHits(int32_t* prim_id, float* t);

@@ -159,6 +159,9 @@ struct TraceIO {
     int final_pass;                     // 1 if no further tracing kernel follows for this wave (the last one writes results)
     int2* __restrict__ list;            // BVH work list: (ray index, first BVH whose root box the ray hits), written by
     int* list_count;                    //   prims_wave with warp-aggregated appends, consumed by bvh_wave
+    // JSRT_FLAG_AOV renders: radiance goes to a per-sample buffer (`accum` then points at it) so that the per-pixel
+    // variance can be formed from whole samples; slot = pixel + (pass - pass0) * accum_stride.  0 otherwise.
+    int accum_stride, pass0;
 };
 
 // One radiance term into the pixel's sum.  sm_90+ has a 128-bit vector reduction (red.global.add.v4.f32): one L2
@@ -197,6 +200,11 @@ JSRT_DEV bool slab_test(const float4 n0, const float4 n1, float3 lo, float3 inv,
     return !miss && !(b0 > b1) && !(b1 < minD) && !(b0 > maxD);
 }
 
+// four components at once (first-hit AOVs: normal.xyz, distance)
+JSRT_DEV void accum_add3w(float4* buf, uint32_t pixel, float3 c, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(buf + pixel), "f"(c.x), "f"(c.y), "f"(c.z), "f"(w) : "memory");
+}
+
 template <int MODE>
 JSRT_DEV void ray_window(const float4 d4, float& minD, float& maxD, bool& primary) {
     if (MODE == TM_EXTEND) {
@@ -210,7 +218,9 @@ JSRT_DEV void finish_ray(const TraceIO& io, int i, const Hit& best, const float4
     if (MODE == TM_EXTEND) io.hits[i] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
     else if (best.prim < 0) {            // unoccluded: the light sample counts (src/materials.js:251-253)
         const float4 c4 = io.c[i];
-        accum_add3(io.accum, (uint32_t)__float_as_int(o4.w), f3(c4.x, c4.y, c4.z));
+        uint32_t slot = (uint32_t)__float_as_int(o4.w);
+        if (io.accum_stride) slot += (uint32_t)(__float_as_int(io.d[i].w) - io.pass0) * (uint32_t)io.accum_stride;   // shadow rays carry their pass in d.w
+        accum_add3(io.accum, slot, f3(c4.x, c4.y, c4.z));
     }
 }
 
@@ -281,13 +291,32 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_pr
     const int stride = gridDim.x * blockDim.x;
     const int n_round = (n + 31) & ~31;                // warp-uniform trip count: every lane reaches the ballot
     const int lane = threadIdx.x & 31;
+    // The queue is streamed once (32 B per ray in, 16-24 B out) and the arithmetic per ray is short, so the kernel lives
+    // on bytes in flight: the next ray of this thread is fetched before the current one is processed
+    // (JSRT_PRIMS_PREFETCH=0: plain loads; measured in profiles/r1_s3).
+#ifndef JSRT_PRIMS_PREFETCH
+#define JSRT_PRIMS_PREFETCH 1      // 2: the same with evict-first (ld.global.cs) loads
+#endif
+#define JSRT_PRIMS_LD(p) ((JSRT_PRIMS_PREFETCH == 2) ? __ldcs(p) : *(p))
+    float4 no4 = make_float4(0, 0, 0, 0), nd4 = no4;
+    {
+        const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (JSRT_PRIMS_PREFETCH && i0 < n) { no4 = JSRT_PRIMS_LD(io.o + i0); nd4 = JSRT_PRIMS_LD(io.d + i0); }
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         int first_bvh = -1;
         Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
         float4 o4 = make_float4(0, 0, 0, 0);
+        const unsigned live = __ballot_sync(FULL, i < n);
+        float4 cur_d4 = nd4;
+        if (JSRT_PRIMS_PREFETCH) {
+            o4 = no4;
+            const int inext = i + stride;
+            if (inext < n) { no4 = JSRT_PRIMS_LD(io.o + inext); nd4 = JSRT_PRIMS_LD(io.d + inext); }
+        }
         if (i < n) {
-            o4 = io.o[i];
-            const float4 d4 = io.d[i];
+            if (!JSRT_PRIMS_PREFETCH) { o4 = io.o[i]; cur_d4 = io.d[i]; }
+            const float4 d4 = cur_d4;
             const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
             float minD, maxD; bool primary;
             ray_window<MODE>(d4, minD, maxD, primary);
@@ -311,6 +340,11 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_pr
                 float3 lo = o, ld = d;                                                                                              \
                 if (e0.z >= 0) { const XformReg ma = load_xform(sc.xforms, e0.z); lo = xf_point(ma, o); ld = xf_dir(ma, d); }         \
                 if (!(e1.y & PF_IDENTITY_XFORM)) { const XformReg m = load_xform(sc.xforms, e0.w); const float3 a = xf_point(m, lo), b = xf_dir(m, ld); lo = a; ld = b; }
+            // Shadow rays: no per-lane early exit inside these loops.  A lane that leaves a loop on its own runs the rest of
+            // the body apart from its warp (measured on cornell_box_path: 8.7 of 32 lanes active in the box loop, each
+            // group of lanes running it separately); instead every lane runs every test of a group and the warp skips the
+            // remaining groups together once all of its rays are occluded.
+            #define JSRT_GROUP_DONE() (ANY_HIT && __all_sync(live, best.prim >= 0))
             for (; k < sc.atab_end[tb][AG_PLANE]; ++k) {                           // SimplePlane.intersect src/geometry.js:246-248
                 JSRT_ENTRY()
                 float oz, dz;
@@ -320,41 +354,38 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_pr
                 } else { JSRT_LOCAL_RAY() oz = lo.z; dz = ld.z; }
                 const float t = (dz != 0.f) ? -oz / dz : -CUDART_INF_F;
                 JSRT_ACCEPT(t, 0.f)
-                if (ANY_HIT && best.prim >= 0) break;
             }
-            if (!(ANY_HIT && best.prim >= 0)) for (; k < sc.atab_end[tb][AG_SQUARE]; ++k) {   // Square.intersect src/geometry.js:287-291
+            if (!JSRT_GROUP_DONE()) for (; k < sc.atab_end[tb][AG_SQUARE]; ++k) {   // Square.intersect src/geometry.js:287-291
                 JSRT_ENTRY()
                 JSRT_LOCAL_RAY()
                 const float t = plane_t(lo, ld);
                 const float x = __fadd_rn(lo.x, __fmul_rn(ld.x, t)), y = __fadd_rn(lo.y, __fmul_rn(ld.y, t));
                 if (-0.5f <= x && x <= 0.5f && -0.5f <= y && y <= 0.5f) { JSRT_ACCEPT(t, 0.f) }
-                if (ANY_HIT && best.prim >= 0) break;
             }
-            if (!(ANY_HIT && best.prim >= 0)) for (; k < sc.atab_end[tb][AG_BOX]; ++k) {      // AABB.intersect src/geometry.js:173-179
+            if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_SQUARE]; k < sc.atab_end[tb][AG_BOX]; ++k) {      // AABB.intersect src/geometry.js:173-179
                 JSRT_ENTRY()
                 JSRT_LOCAL_RAY()
                 float3 c = f3(0.f, 0.f, 0.f), h = f3(0.5f, 0.5f, 0.5f);
                 if (e1.x >= 0) { const float* b = sc.boxes + 8 * e1.x; c = f3(__ldg(b), __ldg(b + 1), __ldg(b + 2)); h = f3(__ldg(b + 4), __ldg(b + 5), __ldg(b + 6)); }
                 const float t = box_prim_intersect(c, h, lo, ld, minD, maxD);
                 JSRT_ACCEPT(t, 0.f)
-                if (ANY_HIT && best.prim >= 0) break;
             }
-            if (!(ANY_HIT && best.prim >= 0)) for (; k < sc.atab_end[tb][AG_SPHERE]; ++k) {      // Sphere.staticIntersect src/geometry.js:429-442
+            if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_BOX]; k < sc.atab_end[tb][AG_SPHERE]; ++k) {      // Sphere.staticIntersect src/geometry.js:429-442
                 JSRT_ENTRY()
                 JSRT_LOCAL_RAY()
                 const float t = sphere_intersect(lo, ld, minD);
                 JSRT_ACCEPT(t, 0.f)
-                if (ANY_HIT && best.prim >= 0) break;
             }
-            if (!(ANY_HIT && best.prim >= 0)) for (; k < sc.atab_end[tb][AG_OTHER]; ++k) {    // every other geometry: the general code
+            if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_SPHERE]; k < sc.atab_end[tb][AG_OTHER]; ++k) {    // every other geometry: the general code
+                if (ANY_HIT && best.prim >= 0) break;
                 JSRT_ENTRY()
                 float3 lo = o, ld = d;
                 if (e0.z >= 0) { const XformReg ma = load_xform(sc.xforms, e0.z); lo = xf_point(ma, o); ld = xf_dir(ma, d); }
                 float tl = 0.f;
                 const float t = placed_prim_intersect<HAS_SDF>(sc, e0.x, lo, ld, minD, maxD, best.t, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
                 JSRT_ACCEPT(t, tl)
-                if (ANY_HIT && best.prim >= 0) break;
             }
+            #undef JSRT_GROUP_DONE
             #undef JSRT_ACCEPT
             #undef JSRT_ENTRY
             #undef JSRT_LOCAL_RAY

@@ -20,6 +20,7 @@ FORMAT_JSON = 0
 FORMAT_MSGPACK = 1
 FLAG_NO_JITTER = 1
 FLAG_COUNT_WORK = 2
+FLAG_AOV = 4
 
 _LIB = None
 
@@ -63,7 +64,7 @@ class BvhNode(C.Structure):
 EXPORTS = [
     "jsrt_device_count", "jsrt_scene_create", "jsrt_scene_create_host", "jsrt_scene_destroy", "jsrt_scene_upload",
     "jsrt_scene_set_stream", "jsrt_render", "jsrt_reset_accum", "jsrt_synchronize", "jsrt_resolve_rgba8",
-    "jsrt_read_accum", "jsrt_accum_device_ptr", "jsrt_add_passes", "jsrt_primary_hits", "jsrt_scene_info",
+    "jsrt_read_accum", "jsrt_read_aov", "jsrt_accum_device_ptr", "jsrt_add_passes", "jsrt_primary_hits", "jsrt_scene_info",
     "jsrt_stats_get", "jsrt_stats_reset", "jsrt_set_profiling", "jsrt_last_error", "jsrt_bvh_build",
     "jsrt_bvh_node_count", "jsrt_bvh_leaf_object_count", "jsrt_bvh_copy", "jsrt_bvh_free", "jsrt_measure_read_bandwidth",
 ]
@@ -93,6 +94,7 @@ def load():
     L.jsrt_synchronize.argtypes = [vp]
     L.jsrt_resolve_rgba8.argtypes = [vp, vp]
     L.jsrt_read_accum.argtypes = [vp, vp, vp]
+    L.jsrt_read_aov.argtypes = [vp, vp, vp]
     L.jsrt_accum_device_ptr.restype = vp
     L.jsrt_accum_device_ptr.argtypes = [vp]
     L.jsrt_add_passes.argtypes = [vp, i32]
@@ -198,6 +200,14 @@ class Scene:
         passes = C.c_int()
         self._ck(self._L.jsrt_read_accum(self._h, out.ctypes.data, C.byref(passes)))
         return out, passes.value
+
+    def read_aov(self):
+        """(normal_depth, variance): the GL path's auxiliary buffers of the passes rendered with FLAG_AOV (include/jsrt.h)."""
+        W, H = self.size
+        nd = np.empty((H, W, 4), dtype=np.float32)
+        var = np.empty((H, W, 4), dtype=np.float32)
+        self._ck(self._L.jsrt_read_aov(self._h, nd.ctypes.data, var.ctypes.data))
+        return nd, var
 
     def accum_device_ptr(self):
         return self._L.jsrt_accum_device_ptr(self._h)

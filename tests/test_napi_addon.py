@@ -26,6 +26,13 @@ def build_mock():
     return SO
 
 
+class Value:
+    """An opaque napi_value handed back by the addon (the scene external)."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+
 class Addon:
     """`require('./napi/build/Release/jsrt_addon.node')` under the mock runtime."""
 
@@ -68,7 +75,8 @@ class Addon:
             ty = {np.dtype(np.uint8): NAPI_UINT8_CLAMPED, np.dtype(np.int32): NAPI_INT32_ARRAY, np.dtype(np.float32): NAPI_FLOAT32_ARRAY,
                   np.dtype(np.int8): 0}[a.dtype]
             return self.m.mock_typedarray(self.env, ty, a.ctypes.data, a.size)
-        return a                                       # an opaque napi_value (the scene external)
+        assert isinstance(a, Value), type(a)
+        return a.ptr
 
     def call(self, name, *args):
         argv = (C.c_void_p * max(1, len(args)))(*[self.wrap(a) for a in args])
@@ -78,7 +86,7 @@ class Addon:
             raise RuntimeError(exc.decode())           # what Node would throw into JS
         if r and self.m.mock_is_number(r):
             return int(self.m.mock_number_value(r))
-        return r
+        return Value(r) if r else None
 
 
 @pytest.fixture(scope="module")
@@ -117,7 +125,7 @@ def test_addon_renders_the_same_bytes_as_the_ctypes_binding(addon):
     blob = ser.to_msgpack()
     # reference-facing sequence of js/cuda_renderer.js
     scene = addon.call("createScene", blob, 1, 0)
-    assert addon.m.mock_is_external(scene)
+    assert addon.m.mock_is_external(scene.ptr)
     addon.call("resetAccum", scene)
     for done in range(0, 4, 2):
         addon.call("render", scene, done, 2, 1, 0, 1, 0)

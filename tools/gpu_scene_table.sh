@@ -7,8 +7,8 @@ run BoxBall 512 512 16
 run cornell_box_path 1024 1024 8
 run bunny_path 1920 1080 16
 run dragon 1920 1080 16
-run SDF_Menger 1920 1080 4 dof=1
-run SDF_Sierpinski 1920 1080 4 dof=1
+run SDF_Menger 1920 1080 16 dof=1
+run SDF_Sierpinski 1920 1080 16 dof=1
 run starwars 1920 1080 8
 run dragon_grid 1920 1080 8 n=3
 python - "$out" <<'PY'
