@@ -464,6 +464,7 @@ struct Renderer::Impl {
     float4 *aov_nd = nullptr, *aov_var = nullptr, *sample_rad = nullptr;
     int sample_span = 0;
     int2* work_list = nullptr;          // BVH work list (trace.cuh), shared by the extend and the shadow wave of a level
+    float4* walker_rec[3] = {nullptr, nullptr, nullptr};   // JSRT_WALKER_RECORDS: the same list as 48-byte walker records (SoA)
     Counters* counters = nullptr;
     int* overflow = nullptr;
     int ray_cap = 0, shadow_cap = 0, batch = 0;
@@ -550,7 +551,8 @@ struct Renderer::Impl {
         // depth-8 Cornell box, which runs in sub-frame batches.
         double worst = 1; for (int l = 1; l < hs.max_depth; ++l) worst *= hs.fanout;
         if (worst > 1e6) worst = 1e6;
-        const double per_sample = worst * (2.0 * 48 + 16 + (hs.sdfs.empty() ? 0 : 16) + 72.0 * std::max(1, hs.light_samples));
+        const double list_bytes = (JSRT_WALKER_RECORDS && !bvh_tops_host.empty()) ? 48.0 : (JSRT_WALKER_RECORDS ? 0.0 : 8.0);   // work-list entry per (shadow) ray
+        const double per_sample = worst * (2.0 * 48 + 16 + (hs.sdfs.empty() ? 0 : 16) + (64.0 + list_bytes) * std::max(1, hs.light_samples));
         double b = (double)queue_budget / per_sample;
         // up to 16 passes per wave (JSRT_BATCH_PASSES overrides): the persistent trace kernels end with a tail of
         // long walks, so bigger waves are faster (bunny_path 1080p: 2.75 / 3.47 / 3.78 / 3.90 Grays/s at 1 / 3.2 / 8 / 16 passes)
@@ -566,9 +568,14 @@ struct Renderer::Impl {
         hits = dalloc<float4>(ray_cap);
         sq.o = dalloc<float4>(shadow_cap); sq.d = dalloc<float4>(shadow_cap); sq.c = dalloc<float4>(shadow_cap);
         shadow_hits = dalloc<float4>(shadow_cap);
+#if JSRT_WALKER_RECORDS
+        if (!bvh_tops_host.empty()) for (auto& p : walker_rec) p = dalloc<float4>(std::max(ray_cap, shadow_cap));
+        work_list = dalloc<int2>(1);
+#else
         work_list = dalloc<int2>(std::max(ray_cap, shadow_cap));
+#endif
         if (!hs.sdfs.empty()) { sdf_normals = dalloc<float4>(ray_cap); CK(cudaMemsetAsync(sdf_normals, 0, (size_t)ray_cap * sizeof(float4), stream)); }
-        queue_bytes = (size_t)ray_cap * (2 * 48 + 16) + (size_t)shadow_cap * (48 + 16) + (size_t)std::max(ray_cap, shadow_cap) * 8;
+        queue_bytes = (size_t)ray_cap * (2 * 48 + 16) + (size_t)shadow_cap * (48 + 16) + (size_t)((double)std::max(ray_cap, shadow_cap) * list_bytes);
 
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
         auto grid_for = [&](const void* fn) { int per = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, kBlock, 0)); return prop.multiProcessorCount * std::max(1, per); };
@@ -703,14 +710,14 @@ struct Renderer::Impl {
     void launchExtend(int cur, bool count_work) {
         TraceIO io{}; io.o = rq[cur].o; io.d = rq[cur].d; io.hits = hits; io.count = &counters->ray[cur]; io.cap = ray_cap;
         io.cursor = &counters->cursor_extend; io.stats = counters->stats; io.aux = sdf_normals;
-        io.list = work_list; io.list_count = &counters->list_extend;
+        io.list = work_list; io.list_count = &counters->list_extend; io.rec0 = walker_rec[0]; io.rec1 = walker_rec[1]; io.rec2 = walker_rec[2];
         timed(1, [&] { launchTrace<TM_EXTEND>(io, count_work, grid_extend); });
     }
     void launchShadow(bool count_work, float4* radiance, int accum_stride, int pass0) {
         TraceIO io{}; io.o = sq.o; io.d = sq.d; io.c = sq.c; io.hits = shadow_hits; io.accum = radiance; io.count = &counters->shadow; io.cap = shadow_cap;
         io.accum_stride = accum_stride; io.pass0 = pass0;
         io.cursor = &counters->cursor_shadow; io.stats = counters->stats;
-        io.list = work_list; io.list_count = &counters->list_shadow;
+        io.list = work_list; io.list_count = &counters->list_shadow; io.rec0 = walker_rec[0]; io.rec1 = walker_rec[1]; io.rec2 = walker_rec[2];
         timed(3, [&] { launchTrace<TM_SHADOW>(io, count_work, grid_shadow); });
     }
 

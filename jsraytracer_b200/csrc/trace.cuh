@@ -143,6 +143,13 @@ JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, floa
 #ifndef JSRT_NODE_STEPS
 #define JSRT_NODE_STEPS 8
 #endif
+// Work list as 48-byte walker records instead of (ray index, BVH) pairs (see TraceIO).  Measured (profiles/r1_s3,
+// ab_s3_rec_*): the BVH kernels gain 2.5-7 % (coalesced, shorter refill) but prims_kernel pays for the wider
+// records — bunny_path 5 692 -> 5 602, dragon 4 900 -> 4 936, starwars 4 325 -> 4 394 Mrays/s, +21 GB of queue
+// memory — so the refill gather is not what the long-scoreboard stalls of the walk are made of.  Off by default.
+#ifndef JSRT_WALKER_RECORDS
+#define JSRT_WALKER_RECORDS 0
+#endif
 enum TraceMode { TM_EXTEND = 0, TM_SHADOW = 1 };
 
 struct TraceIO {
@@ -159,6 +166,12 @@ struct TraceIO {
     int final_pass;                     // 1 if no further tracing kernel follows for this wave (the last one writes results)
     int2* __restrict__ list;            // BVH work list: (ray index, first BVH whose root box the ray hits), written by
     int* list_count;                    //   prims_wave with warp-aggregated appends, consumed by bvh_wave
+    // JSRT_WALKER_RECORDS: the work list carries the whole walker instead — three float4 per entry (SoA), so that a
+    // refilling lane reads 48 contiguous, coalesced bytes instead of gathering the ray, its direction and its partial
+    // hit through the index (three half-used sectors behind a dependent load) and re-deriving the local ray:
+    //   rec0 = local origin.xyz | ray index     rec1 = local direction.xyz | closest hit so far (t)
+    //   rec2 = first BVH | top-level index of that hit | primary-ray flag | -
+    float4* __restrict__ rec0; float4* __restrict__ rec1; float4* __restrict__ rec2;
     // JSRT_FLAG_AOV renders: radiance goes to a per-sample buffer (`accum` then points at it) so that the per-pixel
     // variance can be formed from whole samples; slot = pixel + (pass - pass0) * accum_stride.  0 otherwise.
     int accum_stride, pass0;
@@ -307,6 +320,7 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_pr
         int first_bvh = -1;
         Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
         float4 o4 = make_float4(0, 0, 0, 0);
+        float3 w_lo = f3(0, 0, 0), w_ld = f3(0, 0, 1); bool w_primary = false;      // the walker handed to bvh_wave
         const unsigned live = __ballot_sync(FULL, i < n);
         float4 cur_d4 = nd4;
         if (JSRT_PRIMS_PREFETCH) {
@@ -396,16 +410,26 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_pr
                     const LocalRay r = make_local_ray(load_xform(sc.xforms, ta.y), o, d);
                     const float4* root = reinterpret_cast<const float4*>(sc.nodes + first_node);
                     if (COUNT) ++work->nodes;
-                    if (slab_any(__ldg(root), __ldg(root + 1), r, minD, maxD, best.t)) { first_bvh = b; break; }
+                    if (slab_any(__ldg(root), __ldg(root + 1), r, minD, maxD, best.t)) { first_bvh = b; w_lo = r.lo; w_ld = r.ld; break; }
                 }
             }
+            w_primary = primary;
         }
         const unsigned walkers = __ballot_sync(FULL, first_bvh >= 0);
         if (walkers) {
             int base = 0;
             if (lane == 0) base = atomicAdd(io.list_count, __popc(walkers));
             base = __shfl_sync(FULL, base, 0);
+#if JSRT_WALKER_RECORDS
+            if (first_bvh >= 0) {
+                const int e = base + __popc(walkers & ((1u << lane) - 1u));
+                io.rec0[e] = make_float4(w_lo.x, w_lo.y, w_lo.z, __int_as_float(i));
+                io.rec1[e] = make_float4(w_ld.x, w_ld.y, w_ld.z, best.t);
+                io.rec2[e] = make_float4(__int_as_float(first_bvh), __int_as_float(best.top), __int_as_float(w_primary ? 1 : 0), 0.f);
+            }
+#else
             if (first_bvh >= 0) io.list[base + __popc(walkers & ((1u << lane) - 1u))] = make_int2(i, first_bvh);
+#endif
         }
         if (i < n) {
             if (io.final_pass && first_bvh < 0) finish_ray<MODE>(io, i, best, o4);
@@ -461,10 +485,16 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     const float4* const all_nodes = reinterpret_cast<const float4*>(sc.nodes);
 
     // enter BVH number `bi` of the scene (Aggregate.intersect / BVHAggregate.intersect, src/aggregates.js:43-46)
-    auto enter = [&](float3 o, float3 d) {
+    // `local`: (o, d) is already the ray in the aggregate's space (a walker record of prims_wave)
+    auto enter = [&](float3 o, float3 d, bool local) {
         const int4* tp = reinterpret_cast<const int4*>(sc.tops + __ldg(sc.bvh_tops + bi));
         const int4 ta = __ldg(tp), tb = __ldg(tp + 1);      // kind, xform, first_prim, prim_count | first_node, node_count, tri_base, n_layouts
-        r = make_local_ray(load_xform(sc.xforms, ta.y), o, d);
+        if (local) {
+            r.lo = o; r.ld = d;
+            r.par = !(fabsf(d.x) > 0.0000001f) || !(fabsf(d.y) > 0.0000001f) || !(fabsf(d.z) > 0.0000001f);
+            r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            r.sgn = f3(d.x < 0.f ? -1.f : 1.f, d.y < 0.f ? -1.f : 1.f, d.z < 0.f ? -1.f : 1.f);
+        } else r = make_local_ray(load_xform(sc.xforms, ta.y), o, d);
         // closest-hit rays pick the layout that visits the nearer child first; any-hit (shadow) rays gain nothing from
         // it (measured: +18 % nodes per shadow ray on bunny_path) and keep the reference order
         // (layout 7 = higher child first on every axis = the reference's greater-child-first order)
@@ -482,8 +512,16 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
             if (n_idle >= REFILL_T || idle_mask == FULL) {
                 if (cur < -1) {
                     const int ray = -2 - cur;
+#if JSRT_WALKER_RECORDS
+                    // prims_wave has stored the closest hit outside the BVHs in hits[ray]; it is replaced only by a closer
+                    // BVH hit (best.prim >= 0 means "found in a BVH": the record does not carry the earlier primitive)
+                    if (MODE == TM_EXTEND) { if (best.prim >= 0) io.hits[ray] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo); }
+                    else if (io.final_pass) finish_ray<MODE>(io, ray, best, io.o[ray]);
+                    else io.hits[ray] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
+#else
                     if (io.final_pass) finish_ray<MODE>(io, ray, best, io.o[ray]);
                     else io.hits[ray] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
+#endif
                     cur = -1;
                 }
                 if (pool_next >= pool_end && !exhausted) {
@@ -499,6 +537,16 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                     const int rank = __popc(idle_mask & ((1u << lane) - 1u));
                     if (rank < avail) {             // only idle lanes have a rank that is meaningful: cur < 0 here for them
                         if (cur < 0) {
+#if JSRT_WALKER_RECORDS
+                            const int e = pool_next + rank;
+                            const float4 r0 = __ldcs(io.rec0 + e), r1 = __ldcs(io.rec1 + e), r2 = __ldcs(io.rec2 + e);
+                            cur = __float_as_int(r0.w); bi = __float_as_int(r2.x);
+                            const bool primary = __float_as_int(r2.z) != 0;
+                            minD_v = (MODE == TM_EXTEND && primary) ? 0.f : 0.0001f;
+                            if (COUNT) work = primary ? work_primary : work_other;
+                            best.t = r1.w; best.prim = -1; best.top = __float_as_int(r2.y); best.t_lo = 0.f;
+                            enter(f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), true);
+#else
                             const int2 e = __ldg(reinterpret_cast<const int2*>(io.list) + pool_next + rank);
                             cur = e.x; bi = e.y;
                             const float4 o4 = io.o[cur], d4 = io.d[cur], h4 = io.hits[cur];
@@ -506,7 +554,8 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                             ray_window<MODE>(d4, minD_v, mx, primary);
                             if (COUNT) work = primary ? work_primary : work_other;
                             best.t = h4.x; best.prim = __float_as_int(h4.y); best.top = __float_as_int(h4.z); best.t_lo = h4.w;
-                            enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
+                            enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), false);
+#endif
                             // prims_wave has tested this tree's root box; an inner root needs no second test
                             if (__float_as_int(__ldg(all_nodes + 2 * node_i + 1).w) == -1) ++node_i;
                         }
@@ -564,7 +613,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 }
                 ++bi;
                 if (bi >= sc.n_bvh || (ANY_HIT && best.prim >= 0)) cur = -2 - cur;
-                else { const float4 o4 = io.o[cur], d4 = io.d[cur]; enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z)); }
+                else { const float4 o4 = io.o[cur], d4 = io.d[cur]; enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), false); }
             } else {
                 // ---- phase 3: up to NODE_STEPS nodes of BVHAggregateNode.intersect (src/aggregates.js:207-225)
                 // per iteration, so the warp votes of phases 1-2 are paid once per few nodes

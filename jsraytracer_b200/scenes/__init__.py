@@ -464,10 +464,176 @@ def SDF_Sierpinski(aspect=1, width=600, height=600, spp=16, depth=4, dof=None,
     return _sdf_scene([prim], aspect, width, height, spp, depth, dof, renderer_cls)
 
 
+# ---- further reference scenes (parity cases; each follows its tests/<name>/test.mjs) --------------------------------
+# tests/spheres050/test.mjs, tests/spheres100/test.mjs: the spheres010 grid with NI, NJ, NK = 5, 5, 2 / 5, 5, 4
+def _spheres(ni, nj, nk, aspect, width, height, spp, depth, renderer_cls):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([-7, 0.5, 4]))
+    lights = [SimplePointLight(Vec.of(10, 7, 10, 1), Vec.of(1, 1, 1), 10000)]
+    objects = [Primitive(Plane(), PhongMaterial(Vec.of(0.5, 0.5, 0.5), 0.1, 0.4, 0.6, 100, 0.5),
+                         Mat4.translation([0, -6, 0]).times(Mat4.rotation(PI / 2, Vec.of(1, 0, 0))))]
+    for i in range(ni):
+        for j in range(nj):
+            for k in range(nk):
+                objects.append(Primitive(Sphere(), PhongMaterial(Vec.of(0.1, 0.1, 1), 0.2, 0.4, 0.6, 100, 0.5),
+                                         Mat4.translation([-11 + 2 * i, -3.7 + 2 * j, -12 - 2 * k])))
+    return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+def spheres050(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    return _spheres(5, 5, 2, aspect, width, height, spp, depth, renderer_cls)
+
+
+def spheres100(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    return _spheres(5, 5, 4, aspect, width, height, spp, depth, renderer_cls)
+
+
+# tests/refraction_simple/test.mjs: one Fresnel sphere, three point lights
+def refraction_simple(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([0, 0, 0]))
+    lights = [SimplePointLight(Vec.of(0.75, 0, -10, 1), Vec.of(1, 0.01, 0.01), 300),
+              SimplePointLight(Vec.of(0, 0.75, -10, 1), Vec.of(0.01, 0.01, 1), 300),
+              SimplePointLight(Vec.of(0.75, 0.75, -4, 1), Vec.of(1, 1, 1), 30)]
+    objects = [Primitive(Sphere(), FresnelPhongMaterial(Vec.of(1, 1, 1), 0.05, 0.4, 0.9, 100, 1.3), Mat4.translation([0, 0, -5]))]
+    return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+def _cornell_room(mat, floor, ceiling_light_material=None):
+    """The room shared by tests/cornell_box/test.mjs and tests/cornell_box_emissive/test.mjs (:6-53)."""
+    X, Y = Vec.of(1, 0, 0), Vec.of(0, 1, 0)
+    ceilingmaterial = mat(Vec.of(1, 1, 1), *((0.1, 0.4) if mat is PhongMaterial else (0, 0.4)))
+    return [
+        Primitive(Plane(), floor, Mat4.rotation(PI / 2, X)),
+        Primitive(Square(), mat(Vec.of(1, 1, 1), 0, 0.4), Mat4.translation([0, 5, -5]).times(Mat4.scale([10, 10, 1]))),
+        Primitive(Square(), mat(Vec.of(1, 0.1, 0.1), 0, 0.4),
+                  Mat4.translation([5, 5, 0]).times(Mat4.scale([1, 10, 10])).times(Mat4.rotation(PI / 2, Y))),
+        Primitive(Square(), mat(Vec.of(0.1, 1, 0.1), 0, 0.4),
+                  Mat4.translation([-5, 5, 0]).times(Mat4.scale([1, 10, 10])).times(Mat4.rotation(-PI / 2, Y))),
+        Primitive(Square(), ceiling_light_material or ceilingmaterial,
+                  Mat4.translation([0, 10.5, 0]).times(Mat4.scale([2, 1, 2])).times(Mat4.rotation(PI / 2, X))),
+        Primitive(UnitBox(), ceilingmaterial, Mat4.translation([0, 10, 3]).times(Mat4.scale([10, 1, 4]))),
+        Primitive(UnitBox(), ceilingmaterial, Mat4.translation([0, 10, -3]).times(Mat4.scale([10, 1, 4]))),
+        Primitive(UnitBox(), ceilingmaterial, Mat4.translation([3, 10, 0]).times(Mat4.scale([4, 1, 2]))),
+        Primitive(UnitBox(), ceilingmaterial, Mat4.translation([-3, 10, 0]).times(Mat4.scale([4, 1, 2]))),
+    ]
+
+
+# tests/cornell_box/test.mjs: the Whitted (PhongMaterial) Cornell box, area light x 4 samples, depth 7
+def cornell_box(aspect=1, width=600, height=600, spp=128, depth=7, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([0, 5, 15]))
+    lights = [RandomSampleAreaLight(Square(), Mat4.translation([0, 10, 0]).times(Mat4.rotation(-PI / 2, Vec.of(1, 0, 0)))
+                                    .times(Mat4.scale([1, 1, 1])), Vec.of(1, 1, 1), 2000, 4)]
+    floor = PhongMaterial(CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0.1, 0.1, 0.1)), 0.1, 0.4)
+    objects = _cornell_room(PhongMaterial, floor)
+    objects += [Primitive(Sphere(), PhongMaterial(Vec.of(1, 1, 1), 0.2, 0.2, 0.001, 1000), Mat4.translation([1, 2, -1]).times(Mat4.scale(2))),
+                Primitive(Sphere(), PhongMaterial(Vec.of(1, 1, 1), 0.2, 0.2, 0.01, 100), Mat4.translation([-2, 1, 1.5]))]
+    return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+# tests/cornell_box_emissive/test.mjs: no lights at all; the ceiling square emits (ambient 1000), path tracing
+def cornell_box_emissive(aspect=1, width=600, height=600, spp=128, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([0, 5, 15]))
+    PT = PhongPathTracingMaterial
+    floor = PT(CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0, 0, 0)), 0, 0.4)
+    objects = _cornell_room(PT, floor, PT(Vec.of(1, 1, 1), 1000))
+    objects += [Primitive(Sphere(), PT(Vec.of(1, 1, 1), 0, 0.4, 0.6, 1000), Mat4.translation([1, 2, -1]).times(Mat4.scale(2))),
+                Primitive(Sphere(), PT(Vec.of(1, 1, 1), 0, 0.4, 0.6, 100), Mat4.translation([-2, 1, 1.5]))]
+    return _finish(objects, [], camera, renderer_cls, spp, depth, width, height)
+
+
+# tests/AMultipleBVH/test.mjs: two different meshes in two BVHs + a sphere that casts no shadow
+def AMultipleBVH(aspect=1, width=600, height=600, spp=1, depth=4, renderer_cls=SimpleRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.identity())
+    lights = [SimplePointLight(Vec.of(10, 5, 10, 1), Vec.of(1, 0.87, 0), 5000)]
+    objects = [Primitive(Plane(), PhongMaterial(Vec.of(0.7, 0.7, 1), 0.1, 0.4, 0.6, 100, 0.2),
+                         Mat4.translation([0, -1, 0]).times(Mat4.rotation(PI / 2, Vec.of(1, 0, 0)))),
+               Primitive(Sphere(), PhongMaterial(Vec.of(0, 0, 1), 0.2, 0.4, 0.6, 100, 0.5),
+                         Mat4.translation([-2, 0.3, -9]), Mat4.translation([2, -0.3, 9]), False)]
+    trans1 = Mat4.translation([-0.5, -1.5, -5]).times(Mat4.rotation(0.3, Vec.of(0, 1, 0))).times(Mat4.scale(0.3))
+    trans2 = (Mat4.translation([0.59, 0.58, -3.5]).times(Mat4.rotation(0.4, Vec.of(0, 1, 0)))
+              .times(Mat4.rotation(1.5, Vec.of(1, 0, 0))).times(Mat4.scale(0.3)))
+    default = PhongMaterial(Vec.of(1, 0.7, 0.7), 0.1, 0.4, 0.6, 100, 0.4)
+    objects += [BVHAggregate.build(load_mesh("hollow_tetrahedron", default), trans1),
+                BVHAggregate.build(load_mesh("star", default), trans2)]
+    return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+def _mesh_on_plane(mesh, mesh_material, transform, plane_material, plane_y, camera_transform, lights, aspect, width, height, spp, depth,
+                   renderer_cls, bg=None):
+    X = Vec.of(1, 0, 0)
+    camera = PerspectiveCamera(PI / 4, aspect, camera_transform)
+    objs = [Primitive(Plane(), plane_material, Mat4.translation([0, plane_y, 0]).times(Mat4.rotation(PI / 2, X)))]
+    objs.append(BVHAggregate.build(load_mesh(mesh, mesh_material), transform))
+    return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height, bg)
+
+
+# tests/cat/test.mjs
+def cat(aspect=1, width=600, height=600, spp=1, depth=4, renderer_cls=SimpleRenderer):
+    return _mesh_on_plane("cat", PhongMaterial(Vec.of(1, 0, 0), 0.1, 0.4, 0.6, 100, 0.6),
+                          Mat4.scale(0.05).times(Mat4.translation([30, -370, -150])),
+                          PhongMaterial(Vec.of(0, 0, 1), 0.1, 0.4, 0.6, 100), -1.5, Mat4.identity(),
+                          [SimplePointLight(Vec.of(-15, 5, 12, 1), Vec.of(1, 1, 1), 5000)], aspect, width, height, spp, depth, renderer_cls)
+
+
+# tests/diamond/test.mjs: Fresnel mesh (IOR 2.4), two point lights, grey background
+def diamond(aspect=1, width=600, height=600, spp=1, depth=4, renderer_cls=SimpleRenderer):
+    X, Y = Vec.of(1, 0, 0), Vec.of(0, 1, 0)
+    lights = [SimplePointLight(Vec.of(-15, 5, 12, 1), Vec.of(1, 1, 1), 7000),
+              SimplePointLight(Vec.of(-10, 10, -100, 1), Vec.of(1.0, 1.0, 0.8), 75000)]
+    return _mesh_on_plane("diamond", FresnelPhongMaterial(Vec.of(0.827, 0.827, 0.827), 0.1, 0.4, 0.8, 100, 2.4),
+                          Mat4.translation([-0.2, 1.5, -10]).times(Mat4.rotation(-0.4, Y)).times(Mat4.rotation(0.1, X)).times(Mat4.scale(1)),
+                          PhongMaterial(CheckerboardMaterialColor(Vec.of(0.5, 0.5, 0.5), Vec.of(0.1, 0.1, 0.1)), 0.1, 0.4, 0.6, 2, 0.5), -1,
+                          Mat4.translation([0, 4, -3]).times(Mat4.rotation(-0.6, X)), lights, aspect, width, height, spp, depth, renderer_cls,
+                          bg=Vec.of(0.9, 0.9, 0.9))
+
+
+# tests/heart/test.mjs: lit by a *spherical* area light (Sphere.sampleSurface, src/geometry.js:446-448), one sample
+def heart(aspect=1, width=600, height=600, spp=1, depth=4, renderer_cls=SimpleRenderer):
+    X, Y = Vec.of(1, 0, 0), Vec.of(0, 1, 0)
+    lights = [RandomSampleAreaLight(Sphere(), Mat4.translation(Vec.of(-15, 5, 12, 1)), Vec.of(1, 1, 1), 7000)]
+    return _mesh_on_plane("heart", PhongMaterial(Vec.of(1, 0, 0), 0.1, 0.4, 0.6, 100, 0.6),
+                          Mat4.translation([-0.2, -1, -7]).times(Mat4.rotation(-0.5, Y)).times(Mat4.scale(0.05)),
+                          PhongMaterial(Vec.of(0, 0, 1), 0.1, 0.5, 0.2, 100), -1,
+                          Mat4.translation([0, 2, 0]).times(Mat4.rotation(-0.2, X)), lights, aspect, width, height, spp, depth, renderer_cls)
+
+
+# tests/utah_teapot/test.mjs (high-poly-teapot.obj)
+def utah_teapot(aspect=1, width=600, height=600, spp=8, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    X, Y = Vec.of(1, 0, 0), Vec.of(0, 1, 0)
+    return _mesh_on_plane("high-poly-teapot", PhongMaterial(Vec.of(1, 1, 1), 0.1, 0.4, 0.6, 100, 0.6),
+                          Mat4.translation([-0.4, -1.5, -6]).times(Mat4.rotation(-0.5, Y)).times(Mat4.rotation(-PI / 2, X)).times(Mat4.scale(0.15)),
+                          PhongMaterial(Vec.of(0, 0, 1), 0.1, 0.4, 0.6, 100, 0.4), -1.5,
+                          Mat4.translation([0, 1.5, 1]).times(Mat4.rotation(-0.4, X)),
+                          [SimplePointLight(Vec.of(-15, 5, 12, 1), Vec.of(1, 1, 1), 7000)], aspect, width, height, spp, depth, renderer_cls)
+
+
+# tests/x-wing/test.mjs
+def x_wing(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    X, Y = Vec.of(1, 0, 0), Vec.of(0, 1, 0)
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([0, 2, 0]).times(Mat4.rotation(-0.2, X)))
+    lights = [SimplePointLight(Vec.of(-10, 10, -12, 1), Vec.of(1, 1, 1), 5000),
+              RandomSampleAreaLight(Square(), Mat4.translation([-0.15, 1.86, -2.73]).times(Mat4.rotation(0.4, Y))
+                                    .times(Mat4.scale([0.01, 0.01, 1.5])).times(Mat4.rotation(PI / 2, X)), Vec.of(0, 1, 0), 10, 4)]
+    objs = [Primitive(Plane(), PhongMaterial(Vec.of(0.3, 0.3, 0.3), 0.3, 0.4, 0.6, 100, 0.4),
+                      Mat4.translation([0, 1, 0]).times(Mat4.rotation(PI / 2, X)))]
+    st = Mat4.translation([-0.15, 1.86, -2.73]).times(Mat4.rotation(0.4, Y)).times(Mat4.scale([0.01, 0.01, 1.5]))
+    objs.append(Primitive(Sphere(), FresnelPhongMaterial(Vec.of(0, 1, 0), 0.2, 0.4, 0.5, 100, 1.3), st, Mat4.inverse(st), False))
+    tris = load_mesh("x_wing_fighter", PhongMaterial(Vec.of(1, 0, 0.5), 0.1, 0.4, 0.6, 100, 0.5))
+    objs.append(BVHAggregate.build(tris, Mat4.translation([-0.75, 1, -4]).times(Mat4.rotation(-0.8, Y)).times(Mat4.scale(0.01))))
+    return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height)
+
+
+# tests/SDF_SphereRepetition/test.mjs: infinite repetition with a period that is not a power of two (the division path of Math.fmod)
+def SDF_SphereRepetition(aspect=1, width=600, height=600, spp=16, depth=4, dof=None, renderer_cls=IncrementalMultisamplingRenderer):
+    prim = Primitive(SDFGeometry(TransformSDF(SphereSDF(), SDFInfiniteRepetitionTransformer(Vec.of(5, 5, 5))), 300, 0.0001, 100),
+                     PhongMaterial(Vec.of(0.1, 0.1, 1), 0.2, 0.4, 0.6, 100, 0.5))
+    return _sdf_scene([prim], aspect, width, height, spp, depth, dof, renderer_cls)
+
+
 REGISTRY = {f.__name__: f for f in (
     BoxBall, BoxBall_DOF, BoxBall_path, ASimpleScene, spheres010, refraction, refraction_path, cornell_box_path,
     bunny, bunny_path, dragon, AHollowTetrahedron, starwars, tie_fighter, textured, Aggregates, dragon_grid, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
-    SDF_Sierpinski)}
+    SDF_Sierpinski, spheres050, spheres100, refraction_simple, cornell_box, cornell_box_emissive, AMultipleBVH, cat, diamond, heart,
+    utah_teapot, x_wing, SDF_SphereRepetition)}
 
 
 def configure(name, **overrides):

@@ -36,6 +36,15 @@ PRIMARY = [
     ("Aggregates", dict(width=256, height=256)),                   # plain Aggregates, nested, with a shared primitive
     ("dragon_grid", dict(width=320, height=180, aspect=16 / 9, n=2)),   # 8 instances of one kdtree (Toledo-scale stand-in)
     ("starwars", dict(width=480, height=270, aspect=16 / 9)),      # 4 BVH instances (3 share a kdtree), MTL materials; stands in for Toledo
+    ("spheres100", dict(width=200, height=200)),                   # 101 top-level primitives in the linear world list
+    ("cornell_box", dict(width=256, height=256)),
+    ("AMultipleBVH", dict(width=256, height=256)),                 # two different meshes in two BVHs, a sphere that casts no shadow
+    ("cat", dict(width=256, height=256)),
+    ("diamond", dict(width=256, height=256)),
+    ("heart", dict(width=256, height=256)),
+    ("utah_teapot", dict(width=256, height=256)),                  # high-poly-teapot.obj, 6 320 faces
+    ("x_wing", dict(width=256, height=256)),                       # 18 849 triangles, many slivers
+    ("SDF_SphereRepetition", dict(width=160, height=160)),         # Math.fmod with a period that is not a power of two
 ]
 
 
@@ -78,6 +87,13 @@ WHITTED = [
     ("SDF_BoxBall", dict(width=160, height=160), 1),            # per-leaf basecolor through UnionSDF.getMaterialData
     ("SDF_Combinations", dict(width=192, height=192), 1),       # all six combinators incl. the smooth blends
     ("SDF_Simple", dict(width=128, height=128), 1),
+    ("SDF_SphereRepetition", dict(width=160, height=160), 1),
+    ("spheres050", dict(width=256, height=256), 1),
+    ("refraction_simple", dict(width=512, height=512), 1),      # one Fresnel sphere, three coloured point lights
+    ("AMultipleBVH", dict(width=256, height=256), 1),
+    ("cat", dict(width=256, height=256), 1),
+    ("utah_teapot", dict(width=256, height=256), 1),
+    ("diamond", dict(width=384, height=384), 1),                # Fresnel mesh, IOR 2.4, non-black background
 ]
 
 
@@ -101,6 +117,10 @@ STOCHASTIC = [
     ("bunny_path", dict(width=480, height=270, aspect=16 / 9), 4),
     ("refraction_path", dict(width=192, height=192), 4),
     ("starwars", dict(width=320, height=180, aspect=16 / 9), 2),   # DOF + 3 square area lights x 4 samples + point light
+    ("cornell_box", dict(width=192, height=192), 2),               # Whitted materials under the area light, depth 7
+    ("cornell_box_emissive", dict(width=192, height=192), 4),      # world.lights = []: emissive ceiling only
+    ("heart", dict(width=256, height=256), 2),                     # spherical area light (Sphere.sampleSurface)
+    ("x_wing", dict(width=256, height=256), 2),
 ]
 
 

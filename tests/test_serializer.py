@@ -71,3 +71,21 @@ def test_infinity_json_variants_and_msgpack_agree(blobs):
 def test_integer_valued_numbers_print_like_js():
     s = Serializer({"v": Vec.of(1, 0.5, -0.0)}).to_json()
     assert '"_v":[1,0.5,0]' in s
+
+
+def test_every_registered_scene_flattens_through_the_c_abi():
+    """Host-only parse + flatten (jsrt_scene_create_host: no CUDA call) of every transcribed reference scene, in both wire
+    formats the serializer emits (tests/test_to_json.js:36-38): same primitive / node / triangle / SDF counts."""
+    from jsraytracer_b200 import lib, scenes
+    from jsraytracer_b200.serializer import Serializer
+    skip = {"dragon", "dragon_grid"}          # 100 k triangles: covered on the GPU box, too slow to build twice here
+    for name in sorted(scenes.REGISTRY):
+        if name in skip:
+            continue
+        ser = Serializer(scenes.configure(name, width=32, height=24))
+        a = lib.Scene(ser.to_msgpack(), lib.FORMAT_MSGPACK, device=None).info
+        b = lib.Scene(ser.to_json(), lib.FORMAT_JSON, device=None).info
+        for k in ("width", "height", "n_top", "n_prims", "n_ext_prims", "n_nodes", "n_tris", "n_materials", "n_lights", "n_sdfs",
+                  "n_sdf_instrs", "light_samples", "fanout", "max_depth"):
+            assert a[k] == b[k], (name, k, a[k], b[k])
+        assert a["width"] == 32 and a["height"] == 24 and a["n_prims"] >= 1, name

@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 from jsraytracer_b200.objloader import parse_obj_text  # noqa: E402
 
 ASSETS = ["bunny2", "dragon", "hollow_tetrahedron", "star", "tetrahedron", "cube", "teapot", "Tie_Fighter",
-          "x_wing_fighter"]
+          "x_wing_fighter", "cat", "diamond", "heart", "high-poly-teapot"]
 
 
 def main():
