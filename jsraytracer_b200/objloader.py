@@ -21,7 +21,7 @@ import numpy as np
 
 from .jsmath import Vec, Mat4
 from .geometry import Triangle
-from .materials import (MaterialColor, ScaledMaterialColor, PhongMaterial)
+from .materials import (MaterialColor, ScaledMaterialColor, PhongMaterial, TextureMaterialColor, ImageData)
 from .world import Primitive
 
 _SKIP = re.compile(r"^\s*($|#)")
@@ -47,19 +47,24 @@ class ParsedObj:
     material_names: list = field(default_factory=list)
     mtllibs: list = field(default_factory=list)
     mtl_texts: list = field(default_factory=list)   # contents of the mtllibs (fixtures only; parse_obj_text leaves it empty)
+    textures: dict = field(default_factory=dict)    # map_K* file name -> decoded (H,W,4) uint8 RGBA (fixtures only)
 
     def save(self, path):
+        tex = {"tex_%d" % i: np.ascontiguousarray(a, dtype=np.uint8) for i, a in enumerate(self.textures.values())}
         np.savez_compressed(path, positions=self.positions, texcoords=self.texcoords, normals=self.normals,
                             faces=self.faces, face_material=self.face_material,
                             material_names=np.array(self.material_names, dtype="U"),
-                            mtllibs=np.array(self.mtllibs, dtype="U"), mtl_texts=np.array(self.mtl_texts, dtype="U"))
+                            mtllibs=np.array(self.mtllibs, dtype="U"), mtl_texts=np.array(self.mtl_texts, dtype="U"),
+                            texture_names=np.array(list(self.textures.keys()), dtype="U"), **tex)
 
     @staticmethod
     def load(path):
         z = np.load(path, allow_pickle=False)
         return ParsedObj(z["positions"], z["texcoords"], z["normals"], z["faces"], z["face_material"],
                          [str(s) for s in z["material_names"]], [str(s) for s in z["mtllibs"]],
-                         [str(s) for s in z["mtl_texts"]] if "mtl_texts" in z.files else [])
+                         [str(s) for s in z["mtl_texts"]] if "mtl_texts" in z.files else [],
+                         {str(n): z["tex_%d" % i] for i, n in enumerate(z["texture_names"])}
+                         if "texture_names" in z.files else {})
 
 
 def parse_obj_text(data: str) -> ParsedObj:
@@ -143,7 +148,8 @@ def triangles_from_parsed(parsed: ParsedObj, defaultMaterial=None, transform=Non
 def _make_material_color(a, b, default=None):
     default = default if default is not None else Vec.of(0, 0, 0)
     if isinstance(a, MaterialColor):
-        return ScaledMaterialColor(a, b) if b else a
+        # `new ScaledMaterialColor(a, b)` with b a Vec: Vec.times(Vec) is component-wise (src/math.js:209-211)
+        return ScaledMaterialColor(a, [float(x) for x in b.v] if isinstance(b, Vec) else b) if b else a
     if a or b:
         # MaterialColor.coerce(a, b) with a undefined and b a Vec -> Solid(b)
         return MaterialColor.coerce2(a, b) if b is not None else MaterialColor.coerce(a)
@@ -160,7 +166,23 @@ def _make_material(d):
     return PhongMaterial(Vec.of(1, 1, 1), ambient, diffuse, specular, smoothness)
 
 
-def parse_mtl_text(text: str):
+def mtl_texture_names(text: str):
+    """The pre-scan of parseMtlFile (src/objloader.js:61-70): file names the MTL's texture maps refer to."""
+    names = []
+    for l in text.split("\n"):
+        if _SKIP.match(l):
+            continue
+        t = re.findall(r"\S+", l)
+        if t[0] in ("map_Ka", "map_Kd", "map_Ks", "map_Ns"):
+            names.append(t[-1])
+    return names
+
+
+def parse_mtl_text(text: str, textures=None):
+    """parseMtlFile (src/objloader.js:58-116).  `textures`: file name -> TextureMaterialColor, the table
+    `loadTextures` (:43-56) fills from decoded bitmaps; the browser's image decode has no counterpart here, so
+    the caller supplies decoded RGBA (`TextureMaterialColor(ImageData.from_array(rgba))` = `fromBitmap`, :91-96)."""
+    textures = textures or {}
     ret, curr, name = {}, None, None
     for l in text.split("\n"):
         if _SKIP.match(l):
@@ -177,7 +199,9 @@ def parse_mtl_text(text: str):
         elif vals[0] in ("Ns", "Ni", "illum", "d", "Tr"):
             curr[vals[0]] = vals[1]
         elif vals[0] in ("map_Ka", "map_Kd", "map_Ks"):
-            raise NotImplementedError("TextureMaterialColor (src/materials.js:77-131) is SURVEY §8(f) 'next'")
+            if not textures.get(vals[-1]):
+                raise ValueError("Unknown texture: " + str(vals[-1]))             # src/objloader.js:101-102
+            curr[vals[0]] = textures[vals[-1]]
         else:
             raise ValueError("Unsupported material parameter: " + vals[0])
     if curr is not None:
@@ -185,8 +209,9 @@ def parse_mtl_text(text: str):
     return ret
 
 
-def loadObjFile(filename, defaultMaterial=None, transform=None, minArea=0.00001):
-    """src/objloader.js:240-247 (synchronous; returns the Primitive list)."""
+def loadObjFile(filename, defaultMaterial=None, transform=None, minArea=0.00001, decode_image=None):
+    """src/objloader.js:240-247 (synchronous; returns the Primitive list).  `decode_image(path) -> (H,W,4) uint8`
+    stands in for the browser's `createImageBitmap` (:34-41) when the MTL names texture maps."""
     with open(filename, "r", encoding="utf8") as fh:
         text = fh.read()
     parsed = parse_obj_text(text)
@@ -194,5 +219,11 @@ def loadObjFile(filename, defaultMaterial=None, transform=None, minArea=0.00001)
     materials = {}
     for lib in parsed.mtllibs:
         with open(prefix + lib, "r", encoding="utf8") as fh:
-            materials.update(parse_mtl_text(fh.read()))
+            mtl = fh.read()
+        textures = {}
+        for tname in mtl_texture_names(mtl):
+            if decode_image is None:
+                raise ValueError("MTL texture map %s: loadObjFile needs a decode_image callback" % tname)
+            textures[tname] = TextureMaterialColor(ImageData.from_array(decode_image(prefix + tname)))
+        materials.update(parse_mtl_text(mtl, textures))
     return triangles_from_parsed(parsed, defaultMaterial, transform, minArea, materials)

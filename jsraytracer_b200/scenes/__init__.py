@@ -38,8 +38,11 @@ def load_mesh(name, defaultMaterial=None, transform=None, minArea=0.00001):
     """`loadObjFile("../assets/<name>.obj", ...)` (src/objloader.js:240-247)."""
     parsed = ParsedObj.load(os.path.join(DATA_DIR, name + ".npz"))
     materials = {}
+    # loadTextures -> TextureMaterialColor.fromBitmap (src/objloader.js:43-56, src/materials.js:91-96); the decoded
+    # RGBA comes with the fixture (tools/import_reference_assets.py)
+    textures = {n: TextureMaterialColor(ImageData.from_array(a)) for n, a in parsed.textures.items()}
     for text in parsed.mtl_texts:                      # loadMtlFiles, src/objloader.js:124-142
-        materials.update(parse_mtl_text(text))
+        materials.update(parse_mtl_text(text, textures))
     return triangles_from_parsed(parsed, defaultMaterial, transform, minArea, materials)
 
 
@@ -622,6 +625,17 @@ def x_wing(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=Increm
     return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height)
 
 
+# tests/bottle/test.mjs: MTL `map_Kd` texture on a mesh (potion_bottle.mtl -> bottle_mana.jpg), UVs blended per hit
+def bottle(aspect=1, width=600, height=600, spp=1, depth=4, renderer_cls=SimpleRenderer):
+    X, Y = Vec.of(1, 0, 0), Vec.of(0, 1, 0)
+    lights = [SimplePointLight(Vec.of(-15, 5, 12, 1), Vec.of(1, 1, 1), 7000),
+              SimplePointLight(Vec.of(-15, 5, -12, 1), Vec.of(1, 1, 1), 7000)]
+    return _mesh_on_plane("Potion_bottle", PhongMaterial(Vec.of(1, 0, 0), 0.1, 0.4, 0.6, 100, 0.6),
+                          Mat4.translation([-0.2, 0, -7]).times(Mat4.rotation(0.2, Y)).times(Mat4.rotation(-PI / 2, X)).times(Mat4.scale(0.05)),
+                          PhongMaterial(Vec.of(0, 0, 1), 0.1, 0.5, 0.2, 100), -1,
+                          Mat4.translation([0, 2, 0]).times(Mat4.rotation(-0.2, X)), lights, aspect, width, height, spp, depth, renderer_cls)
+
+
 # tests/SDF_SphereRepetition/test.mjs: infinite repetition with a period that is not a power of two (the division path of Math.fmod)
 def SDF_SphereRepetition(aspect=1, width=600, height=600, spp=16, depth=4, dof=None, renderer_cls=IncrementalMultisamplingRenderer):
     prim = Primitive(SDFGeometry(TransformSDF(SphereSDF(), SDFInfiniteRepetitionTransformer(Vec.of(5, 5, 5))), 300, 0.0001, 100),
@@ -633,7 +647,7 @@ REGISTRY = {f.__name__: f for f in (
     BoxBall, BoxBall_DOF, BoxBall_path, ASimpleScene, spheres010, refraction, refraction_path, cornell_box_path,
     bunny, bunny_path, dragon, AHollowTetrahedron, starwars, tie_fighter, textured, Aggregates, dragon_grid, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
     SDF_Sierpinski, spheres050, spheres100, refraction_simple, cornell_box, cornell_box_emissive, AMultipleBVH, cat, diamond, heart,
-    utah_teapot, x_wing, SDF_SphereRepetition)}
+    utah_teapot, x_wing, SDF_SphereRepetition, bottle)}
 
 
 def configure(name, **overrides):

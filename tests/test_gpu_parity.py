@@ -45,6 +45,7 @@ PRIMARY = [
     ("utah_teapot", dict(width=256, height=256)),                  # high-poly-teapot.obj, 6 320 faces
     ("x_wing", dict(width=256, height=256)),                       # 18 849 triangles, many slivers
     ("SDF_SphereRepetition", dict(width=160, height=160)),         # Math.fmod with a period that is not a power of two
+    ("bottle", dict(width=256, height=256)),                       # MTL map_Kd texture on a mesh
 ]
 
 
@@ -94,6 +95,7 @@ WHITTED = [
     ("cat", dict(width=256, height=256), 1),
     ("utah_teapot", dict(width=256, height=256), 1),
     ("diamond", dict(width=384, height=384), 1),                # Fresnel mesh, IOR 2.4, non-black background
+    ("bottle", dict(width=256, height=256), 1),                 # TextureMaterialColor from the MTL, UVs blended per triangle hit
 ]
 
 

@@ -1,5 +1,6 @@
 """OBJ loading restatement (src/objloader.js:144-247) and the committed mesh fixtures."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -38,6 +39,40 @@ def test_mtl_materials_are_always_phong():
     m = mats["a"]
     assert m.JS_NAME == "PhongMaterial" and m.smoothness == 32      # makeMaterial lacks `return` (src/objloader.js:16-19)
     assert m.diffusivity._color.tolist() == Vec.of(0.3, 0.8, 0.7).tolist()
+
+
+def test_mtl_texture_maps():
+    """parseMtlFile's map_K* handling (src/objloader.js:61-70,100-105) and makeMaterialColor (:1-7)."""
+    from jsraytracer_b200.materials import ImageData, TextureMaterialColor
+    from jsraytracer_b200.objloader import mtl_texture_names
+    text = "newmtl a\nmap_Kd a.jpg\nKs 0.1 0.1 0.1\nNs 1000\nnewmtl b\nmap_Kd -o 1 1 b.png\nKd 0.5 1 0.25\n"
+    assert mtl_texture_names(text) == ["a.jpg", "b.png"]                       # the last token is the file name
+    tex = {n: TextureMaterialColor(ImageData.from_array(np.full((2, 2, 4), 255, np.uint8))) for n in ("a.jpg", "b.png")}
+    mats = parse_mtl_text(text, tex)
+    assert mats["a"].diffusivity is tex["a.jpg"]                                # map without K: the texture itself
+    assert mats["a"].ambient._color.tolist() == [0, 0, 0]                       # neither Ka nor map_Ka: default black
+    b = mats["b"].diffusivity
+    assert b.JS_NAME == "ScaledMaterialColor" and b._mc is tex["b.png"] and b._scale == [0.5, 1.0, 0.25]
+    with pytest.raises(ValueError, match="Unknown texture"):
+        parse_mtl_text(text, {"a.jpg": tex["a.jpg"]})
+
+
+def test_bottle_fixture_has_decoded_textures():
+    """tests/bottle: potion_bottle.mtl names two JPEGs; the fixture carries them decoded to RGBA."""
+    fix = ParsedObj.load(os.path.join(scenes.DATA_DIR, "Potion_bottle.npz"))
+    assert sorted(fix.textures) == ["bottle_health.jpg", "bottle_mana.jpg"]
+    assert all(a.shape == (256, 256, 4) and a.dtype == np.uint8 and (a[..., 3] == 255).all() for a in fix.textures.values())
+    test = scenes.configure("bottle", width=8, height=8)
+    bvh = test["renderer"].world.objects[1]
+    mats = {id(p.material): p.material for p in bvh.objects}
+    assert len(bvh.objects) == 198 and len(mats) == 1                             # one usemtl: bottle_blue
+    m = next(iter(mats.values()))
+    assert m.diffusivity.JS_NAME == "TextureMaterialColor" and m.diffusivity.width == 256 and m.smoothness == 1000
+    ref = os.path.join(REF_ASSETS, "potion_bottle", "bottle_mana.jpg")
+    if os.path.exists(ref):
+        sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+        from import_reference_assets import decode_rgba
+        assert np.array_equal(decode_rgba(ref), fix.textures["bottle_mana.jpg"])
 
 
 @pytest.mark.parametrize("name", ["bunny2", "dragon", "hollow_tetrahedron", "star", "teapot"])
