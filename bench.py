@@ -162,13 +162,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    from jsraytracer_b200.parallel import pass_block, reduce_accum
+    from jsraytracer_b200.parallel import pass_block, reduce_accum, column_stripe, gather_columns
     step_no = [0]
+    columns = args.shard == "columns" and world > 1
 
     def step():
-        first, n = pass_block(step_no[0], rank, world, P)
-        scene.render(first, n, seed=1)
+        if columns:     # the reference's own split (src/worker.js:30-32): every rank renders its interleaved columns of the same passes
+            x_offset, x_delt = column_stripe(rank, world)
+            scene.render(step_no[0] * P, P, seed=1, x_offset=x_offset, x_delt=x_delt)
+        else:
+            first, n = pass_block(step_no[0], rank, world, P)
+            scene.render(first, n, seed=1)
         step_no[0] += 1
+
+    def combine():
+        if columns:
+            gather_columns(accum_t, dst=0)
+        else:
+            reduce_accum(accum_t, dst=0)
 
     # ---- warm-up ------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -186,7 +197,7 @@ def run_ours(args):
     ev0.record(stream)
     for _ in range(args.steps):
         step()
-    reduce_accum(accum_t, dst=0)
+    combine()
     ev1.record(stream)
     barrier()
     sampler.stop_flag.set()
@@ -201,7 +212,7 @@ def run_ours(args):
     ms = float(tmax.item())
     total_rays, total_launches = float(rays[0].item()), int(rays[1].item())
     value = total_rays / (ms * 1e-3) / 1e6
-    spp_per_s = args.steps * P * world / (ms * 1e-3)
+    spp_per_s = args.steps * P * (1 if columns else world) / (ms * 1e-3)
 
     # ---- end-to-end leg: host buffers in, host image out, every step ---------------------
     # scene arrays host->device (jsrt_scene_upload), P passes, 8-bit resolve device->host
@@ -332,10 +343,11 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if columns else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "spp_per_s": spp_per_s,
         "config": {"workload": WORKLOAD if args.scene == "bunny_path" and args.width == 1920 else "%s %dx%d" % (args.scene, W, H),
-                   "passes_per_step": P, "parallelism": "pass-sharded x%d, scene replicated, 1 NCCL reduce" % world if world > 1 else "single GPU",
+                   "passes_per_step": P, "parallelism": ("single GPU" if world == 1 else "column-striped x%d (x_offset = rank, x_delt = %d), scene replicated, 1 NCCL gather" % (world, world) if columns
+                                   else "pass-sharded x%d, scene replicated, 1 NCCL reduce" % world),
                    "rng": "counter-based, seed 1", "l2": "wavefront queues (%.2f GB) exceed L2; the scene itself is L2-resident by nature" % (info["queue_bytes"] / 1e9),
                    "scene_create_s": create_s},
         "clocks": sampler.summary(),
@@ -362,6 +374,8 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--passes-per-step", type=int, default=16)
+    ap.add_argument("--shard", default="passes", choices=["passes", "columns"],
+                    help="N > 1: shard sample passes (weak scaling, one reduce) or interleaved columns like the reference's workers (strong scaling, one gather)")
     ap.add_argument("--cpu-passes", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

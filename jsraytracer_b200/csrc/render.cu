@@ -132,8 +132,14 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(const __grid_constant_
 // extend: closest hit for every ray of the level (World.cast, src/world.js:28-30);
 // shadow: `world.cast(new Ray(position, direction), 0.0001, 1, false)`, the sample is
 // dropped iff 0 < t < 1 (src/materials.js:250-252).  Two kernels each: trace.cuh.
+// prims_kernel streams the queue.  Without a bound ptxas gives it 72 registers = 3 CTAs / SM; measured
+// (profiles/r1_s4/ab_s4_prims_*.jsonl, 3 / 4 / 5 / 6 / 8 CTAs per SM): cornell_box_path 9 924 / 10 545 / 10 627 / 10 411 /
+// 10 036 Mrays/s, bunny_path 5 705 / 5 723 / 5 540 / 5 388 / 5 320 (spills from 5 on).  4 = 64 registers, no spills.
+#ifndef JSRT_PRIMS_MIN_BLOCKS
+#define JSRT_PRIMS_MIN_BLOCKS 4
+#endif
 template <int MODE, bool COUNT, bool HAS_SDF>
-__global__ void __launch_bounds__(kBlock) prims_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
+__global__ void __launch_bounds__(kBlock, (JSRT_PRIMS_MIN_BLOCKS > 0 && !HAS_SDF && !COUNT) ? JSRT_PRIMS_MIN_BLOCKS : 1) prims_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
     Work wp, ws;
     prims_wave<MODE, COUNT, HAS_SDF>(sc, io, &wp, &ws);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }

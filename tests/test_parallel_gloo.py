@@ -58,6 +58,38 @@ def test_pass_sharding_and_reduce_world2(tmp_path, blobs):
     assert np.allclose(z["acc"], serial, rtol=1e-5, atol=1e-6)
 
 
+def _stripe_worker(rank, world, port, js, passes, out_path):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from jsraytracer_b200.parallel import column_stripe, gather_columns
+    from oracle.oracle import OracleScene
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = OracleScene(js)
+    full, _ = orc.render(passes, seed=1, threads=2)
+    x_offset, x_delt = column_stripe(rank, world)
+    acc = np.zeros_like(full)
+    acc[:, x_offset::x_delt, :] = full[:, x_offset::x_delt, :]      # what render(img, .., x_offset, x_delt) fills in
+    t = torch.from_numpy(acc)
+    gather_columns(t, dst=0)
+    if rank == 0:
+        np.savez(out_path, acc=t.numpy(), full=full)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("width", [48, 47])          # 47: the stripes have different widths
+def test_column_stripes_and_gather_world2(tmp_path, blobs, width):
+    """The reference's own sharding (interleaved columns per worker, src/worker.js:30-32) + one gather."""
+    import torch.multiprocessing as mp
+    js, _ = blobs("BoxBall", width=width, height=32)
+    out = str(tmp_path / "s0.npz")
+    mp.spawn(_stripe_worker, args=(2, _free_port(), js, 2, out), nprocs=2, join=True)
+    z = np.load(out)
+    assert np.array_equal(z["acc"], z["full"])
+
+
 def test_pass_block_and_shard_helpers():
     from jsraytracer_b200.parallel import pass_block, shard_passes
     seen = []
