@@ -17,6 +17,8 @@
 //   shadow: o.xyz | pixel      d.xyz (unnormalised, light at t=1) | -      contribution.rgb | -
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,7 +53,7 @@ struct RayQueue { float4* o; float4* d; float4* w; };
 struct ShadowQueue { float4* o; float4* d; float4* c; };
 
 // counters[0], [1]: ray queue counts (ping-pong); [2]: shadow queue count
-struct Counters { int ray[2]; int shadow; int pad; int cursor_extend; int cursor_shadow; int cursor_extend_sdf; int cursor_shadow_sdf; int list_extend; int list_shadow; unsigned long long stats[24]; };
+struct Counters { int ray[2]; int shadow; int ties; int cursor_extend; int cursor_shadow; int cursor_extend_sdf; int cursor_shadow_sdf; int list_extend; int list_shadow; unsigned long long stats[24]; };
 enum { ST_PRIMARY = 0, ST_SECONDARY = 1, ST_SHADOW = 2, ST_SHADED = 3, ST_SAMPLES = 4,
        ST_NODES = 8, ST_LEAF_PRIMS = 11, ST_TOP_PRIMS = 14, ST_SDF_EVALS = 17 };   // + ray class (0 primary, 1 secondary, 2 shadow)
 
@@ -156,6 +158,8 @@ __global__ void __launch_bounds__(kBlock, JSRT_BVH_MIN_BLOCKS) bvh_kernel(const 
     bvh_wave<MODE, COUNT, HAS_SDF>(sc, io, &wp, &ws);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
+
+__global__ void __launch_bounds__(kBlock) tie_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) { tie_wave(sc, io); }
 
 __device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float3 c) { accum_add3(accum, pixel, c); }
 
@@ -414,11 +418,11 @@ __global__ void level_end_kernel(Counters* c, int cur, int level, int next_cap, 
     c->stats[ST_SHADOW] += (unsigned long long)min(c->shadow, shadow_cap);
     c->ray[cur] = 0;
     c->shadow = 0;
-    c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0; c->list_extend = 0; c->list_shadow = 0;
+    c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0; c->list_extend = 0; c->list_shadow = 0; c->ties = 0;
     if (c->ray[cur ^ 1] > next_cap) c->ray[cur ^ 1] = next_cap;
 }
 __global__ void set_count_kernel(Counters* c, int which, int n, int count_samples) {
-    c->ray[which] = n; c->ray[which ^ 1] = 0; c->shadow = 0; c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0; c->list_extend = 0; c->list_shadow = 0;
+    c->ray[which] = n; c->ray[which ^ 1] = 0; c->shadow = 0; c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0; c->list_extend = 0; c->list_shadow = 0; c->ties = 0;
     if (count_samples) c->stats[ST_SAMPLES] += (unsigned long long)n;
 }
 
@@ -469,6 +473,8 @@ struct Renderer::Impl {
     // per-sample radiance of the batch in flight (`sample_span` frames)
     float4 *aov_nd = nullptr, *aov_var = nullptr, *sample_rad = nullptr;
     int sample_span = 0;
+    int4* tie_list = nullptr;           // FP32 near-ties between triangles reported by bvh_kernel<extend> (trace.cuh: tie_wave)
+    static constexpr int kTieCap = 1 << 20;
     int2* work_list = nullptr;          // BVH work list (trace.cuh), shared by the extend and the shadow wave of a level
     float4* walker_rec[3] = {nullptr, nullptr, nullptr};   // JSRT_WALKER_RECORDS: the same list as 48-byte walker records (SoA)
     Counters* counters = nullptr;
@@ -496,6 +502,38 @@ struct Renderer::Impl {
         ds.lights = up(hs.lights); ds.sdfs = up(hs.sdfs); ds.sdf_code = up(hs.sdf_code);
         ds.textures = up(hs.textures); ds.texels = up(hs.texels);
         ds.bvh_tops = up(bvh_tops_host); ds.n_bvh = (int)bvh_tops_host.size();
+        // padded world-space box of every BVHAggregate (trace.cuh: wbox_hit): the root box (centre c, half h, aggregate
+        // space) under the aggregate's transform M = inv_transform^-1 is centre M c, half |M3x3| h
+        wboxes_host.clear();
+        for (int ti : bvh_tops_host) {
+            const Top& t = hs.tops[ti];
+            const BvhNode& root = hs.nodes[t.first_node];
+            const double* a = hs.xforms64[t.xform].m;          // rows of the affine inv_transform
+            const double det = a[0] * (a[5] * a[10] - a[6] * a[9]) - a[1] * (a[4] * a[10] - a[6] * a[8]) + a[2] * (a[4] * a[9] - a[5] * a[8]);
+            double m[9] = {(a[5] * a[10] - a[6] * a[9]) / det, (a[2] * a[9] - a[1] * a[10]) / det, (a[1] * a[6] - a[2] * a[5]) / det,
+                           (a[6] * a[8] - a[4] * a[10]) / det, (a[0] * a[10] - a[2] * a[8]) / det, (a[2] * a[4] - a[0] * a[6]) / det,
+                           (a[4] * a[9] - a[5] * a[8]) / det, (a[1] * a[8] - a[0] * a[9]) / det, (a[0] * a[5] - a[1] * a[4]) / det};
+            const double c[3] = {root.cx - a[3], root.cy - a[7], root.cz - a[11]};      // M c = A^-1 (c - translation of inv_transform)
+            const double h[3] = {root.hx, root.hy, root.hz};
+            double wc[3], wh[3], hmax = 0, cmax = 0;
+            bool finite = std::isfinite(det) && det != 0.0;
+            for (int i = 0; i < 3; ++i) {
+                wc[i] = m[3 * i] * c[0] + m[3 * i + 1] * c[1] + m[3 * i + 2] * c[2];
+                wh[i] = std::fabs(m[3 * i]) * h[0] + std::fabs(m[3 * i + 1]) * h[1] + std::fabs(m[3 * i + 2]) * h[2];
+                finite = finite && std::isfinite(wc[i]) && std::isfinite(wh[i]);
+                hmax = std::max(hmax, wh[i]); cmax = std::max(cmax, std::fabs(wc[i]));
+            }
+            float4 b0, b1;
+            if (!finite) { b0 = make_float4(0.f, 0.f, 0.f, INFINITY); b1 = make_float4(INFINITY, INFINITY, 0.f, 0.f); }     // never rejects
+            else {
+                const double pad = 1e-3 * hmax + 1e-4 * cmax + 1e-6;        // far above the f32 rounding of either test
+                b0 = make_float4((float)wc[0], (float)wc[1], (float)wc[2], (float)(wh[0] + pad));
+                b1 = make_float4((float)(wh[1] + pad), (float)(wh[2] + pad), 0.f, 0.f);
+            }
+            wboxes_host.push_back(b0); wboxes_host.push_back(b1);
+        }
+        ds.wboxes = up(wboxes_host);
+        { const char* e = getenv("JSRT_WBOX"); ds.use_wbox = e ? atoi(e) : (ds.n_bvh >= 2 ? 1 : 0); }
         sdf_tops_host.clear();
         for (size_t i = 0; i < hs.tops.size(); ++i) if (hs.tops[i].kind == T_SDF) sdf_tops_host.push_back((int)i);
         ds.sdf_tops = up(sdf_tops_host); ds.n_sdf_tops = (int)sdf_tops_host.size();
@@ -524,6 +562,7 @@ struct Renderer::Impl {
     }
     std::vector<void*> scene_allocs;
     std::vector<int> bvh_tops_host, sdf_tops_host;
+    std::vector<float4> wboxes_host;
     std::vector<APrim> atab_host;
     size_t up_index = 0;
     template <class T> T* up(const std::vector<T>& vec) {
@@ -580,6 +619,7 @@ struct Renderer::Impl {
 #else
         work_list = dalloc<int2>(std::max(ray_cap, shadow_cap));
 #endif
+        tie_list = dalloc<int4>(bvh_tops_host.empty() ? 1 : kTieCap);
         if (!hs.sdfs.empty()) { sdf_normals = dalloc<float4>(ray_cap); CK(cudaMemsetAsync(sdf_normals, 0, (size_t)ray_cap * sizeof(float4), stream)); }
         queue_bytes = (size_t)ray_cap * (2 * 48 + 16) + (size_t)shadow_cap * (48 + 16) + (size_t)((double)std::max(ray_cap, shadow_cap) * list_bytes);
 
@@ -698,6 +738,7 @@ struct Renderer::Impl {
             io.final_pass = has_sdf_tops ? 0 : 1;
             if (count_work) { if (has_sdf) JSRT_LAUNCH(bvh_kernel, grid_bvh, true, true); else JSRT_LAUNCH(bvh_kernel, grid_bvh, true, false); }
             else { if (has_sdf) JSRT_LAUNCH(bvh_kernel, grid_bvh, false, true); else JSRT_LAUNCH(bvh_kernel, grid_bvh, false, false); }
+            if (MODE == TM_EXTEND && JSRT_TRI_TIE) { ++launches; tie_kernel<<<4, kBlock, 0, stream>>>(ds, io); }      // a few dozen entries per frame
         }
         mark();
         if (has_sdf_tops) {
@@ -716,6 +757,7 @@ struct Renderer::Impl {
     void launchExtend(int cur, bool count_work) {
         TraceIO io{}; io.o = rq[cur].o; io.d = rq[cur].d; io.hits = hits; io.count = &counters->ray[cur]; io.cap = ray_cap;
         io.cursor = &counters->cursor_extend; io.stats = counters->stats; io.aux = sdf_normals;
+        io.tie_list = tie_list; io.tie_count = &counters->ties; io.tie_cap = kTieCap;
         io.list = work_list; io.list_count = &counters->list_extend; io.rec0 = walker_rec[0]; io.rec1 = walker_rec[1]; io.rec2 = walker_rec[2];
         timed(1, [&] { launchTrace<TM_EXTEND>(io, count_work, grid_extend); });
     }

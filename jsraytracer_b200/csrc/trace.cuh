@@ -29,7 +29,12 @@ struct DeviceScene {
     // (closest-hit rays) and the shadow casters only (shadow rays, src/world.js:117-118).
     const APrim* atab;
     int atab_end[2][AG_COUNT]; // [0: closest-hit table | 1: shadow table][group]: end offset of the group within `atab`
-    int n_sdf_tops, pad0, pad1, pad2;
+    // World-space boxes of the BVHAggregates (two float4 each: centre | half x, half y | half z), padded: a cheap
+    // reject in front of the per-aggregate ray transform + root-box test when a scene holds several aggregates
+    // (use_wbox).  Conservative — a ray that misses the padded world box misses the local root box — so results are
+    // those of the reference's linear walk over world.objects (src/world.js:7-15).
+    const float4* wboxes;
+    int n_sdf_tops, use_wbox, pad1, pad2;
     int n_top, n_lights, light_samples, max_depth;
     float bg[3];
     int n_bvh;
@@ -147,6 +152,10 @@ JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, floa
 // ab_s3_rec_*): the BVH kernels gain 2.5-7 % (coalesced, shorter refill) but prims_kernel pays for the wider
 // records — bunny_path 5 692 -> 5 602, dragon 4 900 -> 4 936, starwars 4 325 -> 4 394 Mrays/s, +21 GB of queue
 // memory — so the refill gather is not what the long-scoreboard stalls of the walk are made of.  Off by default.
+// FP32 near-ties between two triangles of a mesh settled in the reference's f64 (tie_wave); 0 = off (A/B runs).
+#ifndef JSRT_TRI_TIE
+#define JSRT_TRI_TIE 1
+#endif
 #ifndef JSRT_WALKER_RECORDS
 #define JSRT_WALKER_RECORDS 0
 #endif
@@ -175,6 +184,7 @@ struct TraceIO {
     // JSRT_FLAG_AOV renders: radiance goes to a per-sample buffer (`accum` then points at it) so that the per-pixel
     // variance can be formed from whole samples; slot = pixel + (pass - pass0) * accum_stride.  0 otherwise.
     int accum_stride, pass0;
+    int4* __restrict__ tie_list; int* tie_count; int tie_cap;      // extend: FP32 near-ties between triangles (tie_wave)
 };
 
 // One radiance term into the pixel's sum.  sm_90+ has a 128-bit vector reduction (red.global.add.v4.f32): one L2
@@ -291,6 +301,21 @@ JSRT_DEV float box_prim_intersect(float3 c, float3 h, float3 o, float3 d, float 
     return (t0 >= minD) ? t0 : t1;
 }
 
+// World-space reject for BVHAggregate number b (DeviceScene::wboxes): slab test with the world ray's reciprocal
+// direction against the same visit window as BVHAggregateNode.intersect (src/aggregates.js:209).  NaNs (0 * inf:
+// origin exactly on a padded slab plane of an axis the ray is parallel to) drop out of fminf / fmaxf, which then
+// reports a miss — correct, since the true box lies strictly inside the padded one.
+JSRT_DEV bool wbox_hit(const float4* __restrict__ wb, int b, float3 o, float3 inv, float minD, float hi) {
+    const float4 a = __ldg(wb + 2 * b), c = __ldg(wb + 2 * b + 1);
+    const float px = a.x - o.x, py = a.y - o.y, pz = a.z - o.z;
+    const float x0 = (px - a.w) * inv.x, x1 = (px + a.w) * inv.x;
+    const float y0 = (py - c.x) * inv.y, y1 = (py + c.x) * inv.y;
+    const float z0 = (pz - c.y) * inv.z, z1 = (pz + c.y) * inv.z;
+    const float n = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+    const float f = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    return n <= f && f >= minD && n <= hi;
+}
+
 // prims_wave: every top-level Primitive / plain Aggregate against every ray of the queue, one ray per thread,
 // then the root box of every BVHAggregate (the first test of BVHAggregateNode.intersect, src/aggregates.js:208-209).
 // Rays that hit no root box are finished here (most rays: 92 % of bunny_path's camera rays miss the mesh's
@@ -404,7 +429,10 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_pr
             #undef JSRT_ENTRY
             #undef JSRT_LOCAL_RAY
             if (!(ANY_HIT && best.prim >= 0)) {
+                float3 winv = f3(0.f, 0.f, 0.f);
+                if (sc.use_wbox) winv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
                 for (int b = 0; b < sc.n_bvh; ++b) {
+                    if (sc.use_wbox && !wbox_hit(sc.wboxes, b, o, winv, minD, fminf(maxD, best.t))) continue;
                     const int4* tp = reinterpret_cast<const int4*>(sc.tops + __ldg(sc.bvh_tops + b));
                     const int4 ta = __ldg(tp); const int first_node = __ldg(reinterpret_cast<const int*>(tp + 1));
                     const LocalRay r = make_local_ray(load_xform(sc.xforms, ta.y), o, d);
@@ -446,6 +474,55 @@ JSRT_DEV void load_node(const float4* p, float4& a, float4& b) {
 #else
     a = __ldg(p); b = __ldg(p + 1);
 #endif
+}
+
+// Two triangles of one mesh whose FP32 hit distances agree to the last bits (a ray through coincident or overlapping
+// coplanar faces, or through a shared edge: both pass the inside test).  The reference decides `t < ret.distance`
+// (src/aggregates.js:213) on f64 distances computed from f32 vectors, so the winner is settled by rounding noise ~1e-8
+// that FP32 cannot see (x-wing at 256 x 256: 18 of 65 536 camera rays picked the neighbour).  bvh_wave keeps its FP32
+// winner and appends (ray, BVH, winner, loser) to a tie list; tie_wave — a few dozen entries per frame — re-derives the
+// local ray exactly as the reference does (f64 matrix times f32 vector, rounded to f32: src/math.js:294-296,392-397),
+// forms both distances as Triangle.intersect forms them (src/geometry.js:345,368-370, un-contracted) and corrects the
+// hit record.  Settling it inside the walk instead cost 6 % of bvh_kernel<extend> (one more live value in a 64-register
+// kernel: profiles/r1_s4).
+JSRT_DEV double triangle_t64(const Tri* __restrict__ tris, int idx, float3 o, float3 d) {
+    const float4* tp = reinterpret_cast<const float4*>(tris + idx);
+    const float4 a = __ldg(tp), b = __ldg(tp + 1);                      // normal | . , p0 | .
+    const double den = ddot4(a.x, a.y, a.z, 0.0, d.x, d.y, d.z, 0.0);
+    const double delta = ddot4(a.x, a.y, a.z, 0.0, b.x, b.y, b.z, 1.0);   // this.normal.dot(ps[0])
+    return (den != 0.0) ? dsub(delta, ddot4(a.x, a.y, a.z, 0.0, o.x, o.y, o.z, 1.0)) / den : -CUDART_INF;
+}
+// Every reported candidate challenges the ray's current hit under the total order (f64 distance, rank) with a 64-bit
+// compare-and-swap on (t, prim), so the outcome is the minimum over all candidates whatever the order of the entries
+// (three-way ties on a shared vertex or on stacked duplicate faces included).
+JSRT_DEV void tie_wave(const DeviceScene& sc, const TraceIO& io) {
+    const int n = min(*io.tie_count, io.tie_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 e = io.tie_list[i];                                  // ray, BVH, FP32 winner, FP32 loser (placed primitives)
+        const int top_i = __ldg(sc.bvh_tops + e.y);
+        const int4* tp = reinterpret_cast<const int4*>(sc.tops + top_i);
+        const int4 ta = __ldg(tp), tb = __ldg(tp + 1);                  // kind, xform, first_prim, prim_count | first_node, node_count, tri_base, n_layouts
+        if (__float_as_int(io.hits[e.x].z) != top_i) continue;          // the closest hit lies in another object by now
+        const float4 o4 = io.o[e.x], d4 = io.d[e.x];
+        const double* m = sc.xforms64[ta.y].m;
+        const float3 lo = xf64_apply(m, f3(o4.x, o4.y, o4.z), 1.0), ld = xf64_apply(m, f3(d4.x, d4.y, d4.z), 0.0);
+        unsigned long long* slot = reinterpret_cast<unsigned long long*>(io.hits + e.x);      // low word: t, high word: prim
+        for (int c = 0; c < 2; ++c) {
+            const int cand = c ? e.w : e.z;
+            const double t_c = triangle_t64(sc.tris, tb.z + (cand - ta.z), lo, ld);
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(slot);
+            for (;;) {
+                const int champ = (int)(unsigned)(cur >> 32);
+                if (champ == cand || champ < ta.z || champ >= ta.z + ta.w) break;
+                const double t_h = triangle_t64(sc.tris, tb.z + (champ - ta.z), lo, ld);
+                if (!(t_c < t_h || (t_c == t_h && cand < champ))) break;   // strict `<`; the first in the reference's order wins exact ties
+                const unsigned long long nv = ((unsigned long long)(unsigned)cand << 32) | (unsigned long long)__float_as_uint((float)t_c);
+                const unsigned long long old = atomicCAS(slot, cur, nv);
+                if (old == cur) break;
+                cur = old;
+            }
+        }
+    }
 }
 
 // bvh_wave: BVHAggregateNode.intersect (src/aggregates.js:207-225) for the rays of the work list.
@@ -586,8 +663,18 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                         if (COUNT) ++work->leaf_prims;
                         const int pi = first_prim + rel + k;
                         const float t = triangle_intersect(sc.tris, tri_base + rel + k, r.lo, r.ld, JSRT_MIND, hi);
-                        // :213 with the rank tie rule (see the header comment)
-                        if (t > JSRT_MIND && t < JSRT_MAXD && (t < local_best || (t == local_best && pi < local_prim))) { local_best = t; local_prim = pi; local_lo = 0.f; }
+                        // :213 with the rank tie rule (see the header comment).  Closest-hit rays report FP32 near-ties between
+                        // two triangles to the tie list (rare: one atomic + one store); tie_wave settles them in f64 afterwards
+                        if (t > JSRT_MIND && t < JSRT_MAXD) {
+                            const bool take = t < local_best || (t == local_best && pi < local_prim);
+#if JSRT_TRI_TIE
+                            if (!ANY_HIT && fabsf(t - local_best) <= 1e-6f * fabsf(t)) {        // (never true while local_best is +Inf)
+                                const int e = atomicAdd(io.tie_count, 1);
+                                if (e < io.tie_cap) io.tie_list[e] = make_int4(cur, bi, take ? pi : local_prim, take ? local_prim : pi);
+                            }
+#endif
+                            if (take) { local_best = t; local_prim = pi; local_lo = 0.f; }
+                        }
                     }
                 } else {
                     for (int k = 0; k < cnt; ++k) {
@@ -599,7 +686,9 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                     }
                 }
                 pending = -1;
-                hi = fminf(hi, local_best);
+                // (closest-hit: the bound keeps 2 ppm of slack so that a candidate tied with the current hit in FP32 still
+                // reaches the tie-break above; acceptance itself compares against local_best)
+                hi = fminf(hi, (ANY_HIT || !JSRT_TRI_TIE) ? local_best : fmaf(fabsf(local_best), 2e-6f, local_best));
                 if (ANY_HIT && local_prim >= 0) node_i = node_end;
             }
         }
@@ -613,7 +702,16 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 }
                 ++bi;
                 if (bi >= sc.n_bvh || (ANY_HIT && best.prim >= 0)) cur = -2 - cur;
-                else { const float4 o4 = io.o[cur], d4 = io.d[cur]; enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), false); }
+                else {
+                    const float4 o4 = io.o[cur], d4 = io.d[cur];
+                    if (sc.use_wbox) {          // skip the aggregates whose world box the ray misses (or reaches behind the closest hit)
+                        const float3 winv = f3(1.0f / d4.x, 1.0f / d4.y, 1.0f / d4.z);
+                        const float whi = fminf(JSRT_MAXD, best.t);
+                        while (bi < sc.n_bvh && !wbox_hit(sc.wboxes, bi, f3(o4.x, o4.y, o4.z), winv, JSRT_MIND, whi)) ++bi;
+                    }
+                    if (bi >= sc.n_bvh) cur = -2 - cur;
+                    else enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), false);
+                }
             } else {
                 // ---- phase 3: up to NODE_STEPS nodes of BVHAggregateNode.intersect (src/aggregates.js:207-225)
                 // per iteration, so the warp votes of phases 1-2 are paid once per few nodes
