@@ -184,6 +184,8 @@ def run_ours(args):
     # ---- warm-up ------------------------------------------------------------------
     for _ in range(args.warmup):
         step()
+    if world > 1:
+        combine()       # NCCL sets up its channels (and the send/recv connections of a gather) on first use
     scene.synchronize()
 
     # ---- timed region (device-resident inputs) ------------------------------------------
