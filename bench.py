@@ -109,7 +109,8 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = rays / dt / 1e6
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC if args.scene == "bunny_path" and args.width == 1920 else "Mrays/s on %s %dx%d" % (args.scene, args.width, args.height),
+        "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "spp_per_s": args.steps * ppass / dt,
         "config": {"workload": WORKLOAD if args.scene == "bunny_path" and args.width == 1920 else "%s %dx%d" % (args.scene, args.width, args.height),
@@ -279,6 +280,9 @@ def run_ours(args):
         rays_t = st["rays_shadow"]
     nodes_per_ray, prims_per_ray = o_nodes / max(1, o_rays), o_prims / max(1, o_rays)
     bytes_per_ray = 32 * nodes_per_ray + 36 * prims_per_ray
+    no_bvh = o_nodes == 0           # a scene of analytic primitives only (cornell_box_path): prims_kernel streams the queue
+    if no_bvh:
+        bytes_per_ray = 48.0        # 32 B ray record read + 16 B hit / contribution written
     flops_per_ray = 27 * nodes_per_ray + 40 * prims_per_ray
     avg_ms = kern_ms[dominant] / max(1, kern_n[dominant])
     rays_per_launch = rays_t / max(1, kern_n[dominant])
@@ -297,6 +301,8 @@ def run_ours(args):
     except Exception:
         l2_gbs = None
     kernel_name = {"extend": "bvh_kernel<extend> (+ prims_kernel<extend>)", "shadow": "bvh_kernel<shadow> (+ prims_kernel<shadow>)"}[dominant]
+    if no_bvh:
+        kernel_name = "prims_kernel<%s>" % dominant
     traffic = None
     try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -344,7 +350,8 @@ def run_ours(args):
     roofline["kernels"] = kernels
 
     line = {
-        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if args.scene == "bunny_path" and args.width == 1920 else "Mrays/s on %s %dx%d" % (args.scene, args.width, args.height),
+        "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if columns else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "spp_per_s": spp_per_s,
         "config": {"workload": WORKLOAD if args.scene == "bunny_path" and args.width == 1920 else "%s %dx%d" % (args.scene, W, H),
