@@ -76,6 +76,35 @@ class CUDARenderer(IncrementalMultisamplingRenderer):
             self._scene = None
 
 
+class WireRenderer:
+    """The renderer of a scene that only exists as a wire blob (`Serializer.deserializeJSON`, the reference's
+    tests/dragon_json and tests/toledo_json): same `render(img, timelimit, callback, x_offset, x_delt)`; class,
+    samplesPerPixel and maxRecursionDepth are read from the blob by the library's own parser (host-only, no CUDA)."""
+
+    def __init__(self, blob, fmt, info, seed=1, device=0):
+        self._wire = (blob, fmt)
+        self.samplesPerPixel = info["samples_per_pixel"]
+        self.maxRecursionDepth = info["max_depth"]
+        self._jitter = bool(info["jitter"])          # False for a serialised SimpleRenderer (src/renderers.js:21-25)
+        self._seed, self._device, self._passes_per_call, self._scene = seed, device, None, None
+
+    @staticmethod
+    def from_blob(blob, fmt):
+        from . import lib
+        host = lib.Scene(blob, fmt, device=None)     # parse + flatten only: validates the blob, yields the header fields
+        info = host.info
+        host.close()
+        return {"renderer": WireRenderer(blob, fmt, info), "width": info["width"], "height": info["height"]}
+
+    def render(self, img, timelimit=0, callback=False, x_offset=0, x_delt=1):
+        return _cuda_render(self, img, timelimit, callback, x_offset, x_delt)
+
+    def close(self):
+        if self._scene is not None:
+            self._scene.close()
+            self._scene = None
+
+
 def _cuda_render(renderer, img, timelimit, callback, x_offset, x_delt):
     """Shared body of every renderer's `render()` (src/renderers.js:10-41,70-117):
     serialise `{renderer, width, height}`, hand it to the C-ABI library, run the
@@ -87,12 +116,19 @@ def _cuda_render(renderer, img, timelimit, callback, x_offset, x_delt):
 
     scene = getattr(renderer, "_scene", None)
     if scene is None or scene.size != (img.width(), img.height()):
-        blob = Serializer({"renderer": renderer, "width": img.width(), "height": img.height()}).to_msgpack()
-        scene = lib.Scene(blob, lib.FORMAT_MSGPACK, device=getattr(renderer, "_device", 0))
+        wire = getattr(renderer, "_wire", None)
+        if wire is not None:                    # a scene that only exists in wire form: handed over as is
+            blob, fmt = wire
+        else:
+            blob, fmt = Serializer({"renderer": renderer, "width": img.width(), "height": img.height()}).to_msgpack(), lib.FORMAT_MSGPACK
+        scene = lib.Scene(blob, fmt, device=getattr(renderer, "_device", 0))
+        if scene.size != (img.width(), img.height()):
+            scene.close()
+            raise ValueError("render: the serialised scene is %dx%d, the image %dx%d" % (scene.size + (img.width(), img.height())))
         if hasattr(renderer, "_scene"):
             renderer._scene = scene
     spp = getattr(renderer, "samplesPerPixel", 1)
-    jitter = not type(renderer) is SimpleRenderer
+    jitter = getattr(renderer, "_jitter", not type(renderer) is SimpleRenderer)
     if not jitter:
         spp = 1
     flags = 0 if jitter else lib.FLAG_NO_JITTER

@@ -74,6 +74,22 @@ class Serializer:
             raise TypeError("Cannot serialize %r" % type(obj))
         return ref
 
+    # -- the *_json scenes (tests/dragon_json/test.mjs, tests/toledo_json/test.mjs) --------------------
+    @staticmethod
+    def deserializeJSON(text):
+        """`Serializer.deserializeJSON(text)` (src/serializer.js:69-75) as the *_json scenes use it: the
+        `{renderer, width, height}` of a scene that exists only in wire form.  The reference rebuilds the JS
+        object graph; here the blob itself is what the C ABI consumes, so the returned renderer keeps it and
+        `render()` hands it over untouched (`renderers.WireRenderer`)."""
+        from .renderers import WireRenderer
+        return WireRenderer.from_blob(text.encode("utf8") if isinstance(text, str) else bytes(text), 0)
+
+    @staticmethod
+    def deserializeMsgpack(blob):
+        """The msgpack form of the same (tests/toledo_json/test.mjs:4-12, tests/test_to_json.js:38)."""
+        from .renderers import WireRenderer
+        return WireRenderer.from_blob(bytes(blob), 1)
+
     def plain(self):
         return self.data
 

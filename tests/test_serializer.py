@@ -89,3 +89,40 @@ def test_every_registered_scene_flattens_through_the_c_abi():
                   "n_sdf_instrs", "light_samples", "fanout", "max_depth"):
             assert a[k] == b[k], (name, k, a[k], b[k])
         assert a["width"] == 32 and a["height"] == 24 and a["n_prims"] >= 1, name
+
+
+def test_deserialize_json_gives_a_wire_renderer():
+    """tests/dragon_json, tests/toledo_json: `Serializer.deserializeJSON(text)` -> {renderer, width, height} of a scene that
+    exists only in wire form (src/serializer.js:69-75); class / spp / depth come from the blob (host-only parse)."""
+    import pytest
+    from jsraytracer_b200 import scenes
+    from jsraytracer_b200.pixelbuffer import PixelBuffer
+    from jsraytracer_b200.serializer import Serializer
+    ser = Serializer(scenes.configure("BoxBall", width=40, height=30, spp=3, depth=5))
+    for test in (Serializer.deserializeJSON(ser.to_json()), Serializer.deserializeMsgpack(ser.to_msgpack())):
+        r = test["renderer"]
+        assert (test["width"], test["height"]) == (40, 30)
+        assert r.samplesPerPixel == 3 and r.maxRecursionDepth == 5 and r._jitter is True
+    simple = Serializer.deserializeJSON(Serializer(scenes.configure("bunny", width=16, height=16)).to_json())["renderer"]
+    assert simple._jitter is False                                   # a serialised SimpleRenderer: un-jittered, one pass
+    with pytest.raises(Exception):
+        Serializer.deserializeJSON("{\"not\": \"a scene\"}")
+
+
+@pytest.mark.gpu
+def test_wire_renderer_renders_like_the_live_graph():
+    """The *_json path end to end: the image from the wire-only renderer equals the one from the scene graph it was
+    serialised from (same library, same seed)."""
+    from jsraytracer_b200 import scenes
+    from jsraytracer_b200.pixelbuffer import PixelBuffer
+    from jsraytracer_b200.renderers import CUDARenderer
+    from jsraytracer_b200.serializer import Serializer
+    live = scenes.configure("BoxBall", width=64, height=48, spp=2, renderer_cls=CUDARenderer)
+    a = live["renderer"].render(PixelBuffer(64, 48)).as_array().copy()
+    wire = Serializer.deserializeJSON(Serializer(live).to_json())
+    b = wire["renderer"].render(PixelBuffer(wire["width"], wire["height"])).as_array().copy()
+    assert a.shape == (48, 64, 4) and int(a[..., :3].max()) > 0
+    assert (a == b).all()
+    with pytest.raises(ValueError):
+        wire["renderer"].close()
+        wire["renderer"].render(PixelBuffer(32, 32))
