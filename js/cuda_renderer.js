@@ -64,11 +64,31 @@ class CUDARenderer extends IncrementalMultisamplingRenderer {
         return this._opt.addon;
     }
 
+    // The *_json scenes (tests/dragon_json/test.mjs, tests/toledo_json/test.mjs): a scene that only exists in wire form.
+    // `Serializer.deserializeJSON` would rebuild the whole JS object graph just to serialise it again; here the blob
+    // goes to the library as is.  Returns what `configureTest` hands to its callback: {renderer, width, height}.
+    //   CUDARenderer.fromWire(fs.readFileSync("tests/dragon/test.json"), 0)        // JSON text
+    //   CUDARenderer.fromWire(fs.readFileSync("tests/toledo/test.msgpack"), 1)     // msgpack
+    static fromWire(blob, format = 0, options = {}) {
+        const r = new CUDARenderer(null, null, 1, 3, options);
+        const head = new Int32Array(5);
+        r._addon().sceneHeader(blob, format, head);               // throws Error(jsrt_last_error()) on a malformed blob
+        r.samplesPerPixel = head[4] ? head[2] : 1;                // a serialised SimpleRenderer: one un-jittered pass
+        r.maxRecursionDepth = head[3];
+        Object.defineProperty(r, "_wire", { value: { blob, format, jitter: !!head[4] }, enumerable: false });
+        return { renderer: r, width: head[0], height: head[1] };
+    }
+
     _ensureScene(img) {
         const w = img.width(), h = img.height();
         if (this._scene && this._size[0] === w && this._size[1] === h)
             return this._scene;
         if (this._scene) this._addon().destroyScene(this._scene);
+        if (this._wire) {
+            this._scene = this._addon().createScene(this._wire.blob, this._wire.format, this._opt.device);
+            this._size = [w, h];
+            return this._scene;
+        }
         installTriangleSerializeFix();
         installTextureSerializeFix();
         let msgpack = null;
@@ -95,7 +115,7 @@ class CUDARenderer extends IncrementalMultisamplingRenderer {
         let last = Date.now();
         for (let done = 0; done < spp; ) {
             const n = Math.min(step, spp - done);
-            addon.render(scene, done, n, this._opt.seed, x_offset, x_delt, 0);      // asynchronous on the scene's stream
+            addon.render(scene, done, n, this._opt.seed, x_offset, x_delt, (this._wire && !this._wire.jitter) ? 1 : 0);      // asynchronous on the scene's stream; flag 1 = no jitter
             done += n;
             if (timelimit && callback) {
                 addon.synchronize(scene);

@@ -85,6 +85,39 @@ static napi_value PrimaryHits(napi_env env, napi_callback_info info) {
     if (jsrt_primary_hits(s, (int32_t*)d1, (float*)d2)) return throw_last(env);
     return NULL;
 }
+// sceneHeader(blob: Buffer, format: 0|1, out: Int32Array(5)) — width, height, samplesPerPixel, maxRecursionDepth, jitter of a
+// serialised scene, read by the library's own parser without touching a GPU (jsrt_scene_create_host).  What
+// CUDARenderer.fromWire needs for a scene that only exists in wire form (tests/dragon_json, tests/toledo_json).
+static napi_value SceneHeader(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value a[3]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    void* data = NULL; size_t len = 0;
+    NAPI_OK(napi_get_buffer_info(env, a[0], &data, &len));
+    napi_typedarray_type ty; size_t n = 0; void* out = NULL; napi_value ab; size_t off = 0;
+    NAPI_OK(napi_get_typedarray_info(env, a[2], &ty, &n, &out, &ab, &off));
+    if (ty != napi_int32_array || n < 5) { napi_throw_range_error(env, NULL, "output must be an Int32Array of 5"); return NULL; }
+    jsrt_scene* s = jsrt_scene_create_host((const uint8_t*)data, len, int_arg(env, a[1]));
+    if (!s) return throw_last(env);
+    jsrt_info inf; const int rc = jsrt_scene_info(s, &inf);
+    jsrt_scene_destroy(s);
+    if (rc) return throw_last(env);
+    int32_t* o = (int32_t*)out;
+    o[0] = inf.width; o[1] = inf.height; o[2] = inf.samples_per_pixel; o[3] = inf.max_depth; o[4] = inf.jitter;
+    return NULL;
+}
+// readAccum(scene, out: Float32Array of W*H*4) -> passes accumulated so far (the f32 sums behind the 8-bit image)
+static napi_value ReadAccum(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value a[2]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    jsrt_scene* s = scene_arg(env, a[0]); if (!s) return NULL;
+    napi_typedarray_type ty; size_t n = 0; void* data = NULL; napi_value ab; size_t off = 0;
+    NAPI_OK(napi_get_typedarray_info(env, a[1], &ty, &n, &data, &ab, &off));
+    jsrt_info inf; if (jsrt_scene_info(s, &inf)) return throw_last(env);
+    if (ty != napi_float32_array || n < (size_t)inf.width * inf.height * 4) {
+        napi_throw_range_error(env, NULL, "output must be a Float32Array of width*height*4"); return NULL;
+    }
+    int passes = 0;
+    if (jsrt_read_accum(s, (float*)data, &passes)) return throw_last(env);
+    napi_value v; NAPI_OK(napi_create_int32(env, passes, &v)); return v;
+}
 static napi_value DeviceCount(napi_env env, napi_callback_info info) {
     (void)info; napi_value v; NAPI_OK(napi_create_int32(env, jsrt_device_count(), &v)); return v;
 }
@@ -92,7 +125,8 @@ static napi_value DeviceCount(napi_env env, napi_callback_info info) {
 static napi_value Init(napi_env env, napi_value exports) {
     const struct { const char* name; napi_callback fn; } fns[] = {
         {"createScene", CreateScene}, {"destroyScene", DestroyScene}, {"render", Render}, {"resetAccum", ResetAccum},
-        {"synchronize", Synchronize}, {"resolveRGBA8", ResolveRGBA8}, {"primaryHits", PrimaryHits}, {"deviceCount", DeviceCount}};
+        {"synchronize", Synchronize}, {"resolveRGBA8", ResolveRGBA8}, {"primaryHits", PrimaryHits}, {"deviceCount", DeviceCount},
+        {"sceneHeader", SceneHeader}, {"readAccum", ReadAccum}};
     for (size_t i = 0; i < sizeof fns / sizeof fns[0]; ++i) {
         napi_value f; NAPI_OK(napi_create_function(env, fns[i].name, NAPI_AUTO_LENGTH, fns[i].fn, NULL, &f));
         NAPI_OK(napi_set_named_property(env, exports, fns[i].name, f));

@@ -97,7 +97,8 @@ def addon():
 def test_addon_registers_the_functions_cuda_renderer_js_calls(addon):
     src = open(os.path.join(ROOT, "js", "cuda_renderer.js")).read()
     ex = addon.exports()
-    assert set(ex) == {"createScene", "destroyScene", "render", "resetAccum", "synchronize", "resolveRGBA8", "primaryHits", "deviceCount"}
+    assert set(ex) == {"createScene", "destroyScene", "render", "resetAccum", "synchronize", "resolveRGBA8", "primaryHits", "deviceCount",
+                       "sceneHeader", "readAccum"}
     import re
     used = set(re.findall(r"(?:addon|_addon\(\))\.(\w+)\(", src))
     assert used and used <= set(ex), used - set(ex)
@@ -114,6 +115,21 @@ def test_addon_argument_errors_become_js_exceptions(addon):
         # no GPU here: jsrt_scene_create fails, and its message must surface as a thrown Error (no CPU fallback)
         with pytest.raises(RuntimeError, match="Error: "):
             addon.call("createScene", b'{"renderer": null}', 0, 0)
+
+
+def test_addon_scene_header_reads_a_wire_blob_without_a_gpu(addon):
+    """CUDARenderer.fromWire (the *_json scenes): width / height / spp / depth / jitter straight from the blob."""
+    from jsraytracer_b200 import scenes
+    from jsraytracer_b200.serializer import Serializer
+    ser = Serializer(scenes.configure("BoxBall", width=40, height=30, spp=3, depth=5))
+    for blob, fmt in ((ser.to_json().encode(), 0), (ser.to_msgpack(), 1)):
+        head = np.zeros(5, np.int32)
+        addon.call("sceneHeader", blob, fmt, head)
+        assert head.tolist() == [40, 30, 3, 5, 1]
+    with pytest.raises(RuntimeError, match="RangeError"):
+        addon.call("sceneHeader", ser.to_msgpack(), 1, np.zeros(4, np.int32))
+    with pytest.raises(RuntimeError, match="Error: "):
+        addon.call("sceneHeader", b"{}", 0, np.zeros(5, np.int32))
 
 
 @pytest.mark.gpu
@@ -134,6 +150,10 @@ def test_addon_renders_the_same_bytes_as_the_ctypes_binding(addon):
     addon.call("resolveRGBA8", scene, img)
     with pytest.raises(RuntimeError, match="RangeError"):
         addon.call("resolveRGBA8", scene, np.zeros(16, np.uint8))
+    acc = np.zeros(W * H * 4, np.float32)
+    assert addon.call("readAccum", scene, acc) == 4                 # passes accumulated
+    with pytest.raises(RuntimeError, match="RangeError"):
+        addon.call("readAccum", scene, np.zeros(8, np.float32))
     ids, t = np.zeros(W * H, np.int32), np.zeros(W * H, np.float32)
     addon.call("primaryHits", scene, ids, t)
     addon.call("destroyScene", scene)
@@ -142,6 +162,8 @@ def test_addon_renders_the_same_bytes_as_the_ctypes_binding(addon):
     sc.render(0, 4, seed=1)
     ref = np.zeros(W * H * 4, np.uint8)
     sc.resolve_rgba8(ref)
+    racc, rpasses = sc.read_accum()
     rid, rt = sc.primary_hits()
     assert np.array_equal(img, ref)
+    assert rpasses == 4 and np.allclose(acc.reshape(racc.shape), racc, rtol=1e-5, atol=1e-6)      # (atomic float sums: order may differ)
     assert np.array_equal(ids, rid.ravel()) and np.array_equal(t, rt.ravel())
