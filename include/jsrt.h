@@ -125,6 +125,12 @@ typedef struct jsrt_info {
 } jsrt_info;
 int jsrt_scene_info(jsrt_scene*, jsrt_info*);
 
+/* Diagnostic (works on host-only handles): the padded world-space box the device tests in front of each
+ * BVHAggregate's ray transform (Aggregate.intersect, src/aggregates.js:14-18,43-46), in world.objects order.
+ * out = 8 floats per aggregate (centre xyz, 0, half-size xyz, 0), at most `cap` aggregates are written;
+ * returns the number of BVHAggregates (-1 on error). */
+int jsrt_bvh_world_boxes(jsrt_scene*, float* out, int cap);
+
 typedef struct jsrt_stats {
     uint64_t rays_primary, rays_secondary, rays_shadow;   /* World.cast calls, src/world.js:28-30 */
     uint64_t shaded_hits;

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "../../include/jsrt.h"
 #include "host_scene.h"
@@ -94,6 +95,17 @@ int jsrt_scene_info(jsrt_scene* s, jsrt_info* o) {
     o->max_bvh_depth = h.max_bvh_depth;
     if (s->renderer) { o->batch_samples = s->renderer->batchSamples(); o->scene_bytes = s->renderer->sceneBytes(); o->queue_bytes = s->renderer->queueBytes(); }
     return 0;
+}
+
+int jsrt_bvh_world_boxes(jsrt_scene* s, float* out, int cap) {
+    if (!s) { g_error = "jsrt: null scene handle"; return -1; }
+    try {
+        std::vector<float> wb;
+        computeWorldBoxes(s->host, wb);
+        const int n = (int)(wb.size() / 8);
+        if (out) memcpy(out, wb.data(), sizeof(float) * 8 * (size_t)(n < cap ? n : (cap < 0 ? 0 : cap)));
+        return n;
+    } catch (const std::exception& e) { failWith(e); return -1; }
 }
 
 int jsrt_stats_get(jsrt_scene* s, jsrt_stats* o) {

@@ -39,6 +39,11 @@ struct HostScene {
 
 void flattenScene(const WireDoc& doc, HostScene& out);
 
+// Padded world-space box of every BVHAggregate with nodes, in world.objects order: 8 floats each (centre xyz, 0, half xyz, 0).
+// The device tests a ray against it before paying for the aggregate's ray transform and local root-box test
+// (trace.cuh: wbox_hit); it must contain the aggregate's root box mapped to world space.
+void computeWorldBoxes(const HostScene& hs, std::vector<float>& out);
+
 // SDF tree -> bytecode (sdf_compile.cpp).  Returns the index of the new program.
 int compileSdf(const WireDoc& doc, const Val* sdf_geometry, HostScene& out);
 

@@ -502,35 +502,15 @@ struct Renderer::Impl {
         ds.lights = up(hs.lights); ds.sdfs = up(hs.sdfs); ds.sdf_code = up(hs.sdf_code);
         ds.textures = up(hs.textures); ds.texels = up(hs.texels);
         ds.bvh_tops = up(bvh_tops_host); ds.n_bvh = (int)bvh_tops_host.size();
-        // padded world-space box of every BVHAggregate (trace.cuh: wbox_hit): the root box (centre c, half h, aggregate
-        // space) under the aggregate's transform M = inv_transform^-1 is centre M c, half |M3x3| h
-        wboxes_host.clear();
-        for (int ti : bvh_tops_host) {
-            const Top& t = hs.tops[ti];
-            const BvhNode& root = hs.nodes[t.first_node];
-            const double* a = hs.xforms64[t.xform].m;          // rows of the affine inv_transform
-            const double det = a[0] * (a[5] * a[10] - a[6] * a[9]) - a[1] * (a[4] * a[10] - a[6] * a[8]) + a[2] * (a[4] * a[9] - a[5] * a[8]);
-            double m[9] = {(a[5] * a[10] - a[6] * a[9]) / det, (a[2] * a[9] - a[1] * a[10]) / det, (a[1] * a[6] - a[2] * a[5]) / det,
-                           (a[6] * a[8] - a[4] * a[10]) / det, (a[0] * a[10] - a[2] * a[8]) / det, (a[2] * a[4] - a[0] * a[6]) / det,
-                           (a[4] * a[9] - a[5] * a[8]) / det, (a[1] * a[8] - a[0] * a[9]) / det, (a[0] * a[5] - a[1] * a[4]) / det};
-            const double c[3] = {root.cx - a[3], root.cy - a[7], root.cz - a[11]};      // M c = A^-1 (c - translation of inv_transform)
-            const double h[3] = {root.hx, root.hy, root.hz};
-            double wc[3], wh[3], hmax = 0, cmax = 0;
-            bool finite = std::isfinite(det) && det != 0.0;
-            for (int i = 0; i < 3; ++i) {
-                wc[i] = m[3 * i] * c[0] + m[3 * i + 1] * c[1] + m[3 * i + 2] * c[2];
-                wh[i] = std::fabs(m[3 * i]) * h[0] + std::fabs(m[3 * i + 1]) * h[1] + std::fabs(m[3 * i + 2]) * h[2];
-                finite = finite && std::isfinite(wc[i]) && std::isfinite(wh[i]);
-                hmax = std::max(hmax, wh[i]); cmax = std::max(cmax, std::fabs(wc[i]));
+        // padded world-space box of every BVHAggregate (scene_flatten.cpp: computeWorldBoxes; trace.cuh: wbox_hit)
+        {
+            std::vector<float> wb;
+            computeWorldBoxes(hs, wb);
+            wboxes_host.clear();
+            for (size_t i = 0; i + 8 <= wb.size(); i += 8) {
+                wboxes_host.push_back(make_float4(wb[i], wb[i + 1], wb[i + 2], wb[i + 4]));        // centre | half x
+                wboxes_host.push_back(make_float4(wb[i + 5], wb[i + 6], 0.f, 0.f));               // half y, half z
             }
-            float4 b0, b1;
-            if (!finite) { b0 = make_float4(0.f, 0.f, 0.f, INFINITY); b1 = make_float4(INFINITY, INFINITY, 0.f, 0.f); }     // never rejects
-            else {
-                const double pad = 1e-3 * hmax + 1e-4 * cmax + 1e-6;        // far above the f32 rounding of either test
-                b0 = make_float4((float)wc[0], (float)wc[1], (float)wc[2], (float)(wh[0] + pad));
-                b1 = make_float4((float)(wh[1] + pad), (float)(wh[2] + pad), 0.f, 0.f);
-            }
-            wboxes_host.push_back(b0); wboxes_host.push_back(b1);
         }
         ds.wboxes = up(wboxes_host);
         { const char* e = getenv("JSRT_WBOX"); ds.use_wbox = e ? atoi(e) : (ds.n_bvh >= 2 ? 1 : 0); }

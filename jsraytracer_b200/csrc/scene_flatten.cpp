@@ -5,6 +5,7 @@
 // SURVEY.md §8b; src/world.js, src/aggregates.js, src/materials.js,
 // src/lights.js, src/cameras.js, src/geometry.js constructors).  Setup code:
 // runs once per scene on the host, never per ray.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -515,6 +516,38 @@ struct Flattener {
 void flattenScene(const WireDoc& doc, HostScene& out) {
     Flattener f(doc, out);
     f.run();
+}
+
+// The root box (centre c, half h, aggregate space) under the aggregate's transform M = inv_transform^-1 has centre M c and
+// half |M3x3| h; the pad (1e-3 of the box, 1e-4 of its distance from the origin) is far above the f32 rounding of
+// either the world-space or the reference's local test, so a ray that misses the padded box misses the local one.
+// A singular / non-finite transform gives an infinite box (never rejects).
+void computeWorldBoxes(const HostScene& hs, std::vector<float>& out) {
+    out.clear();
+    for (const Top& t : hs.tops) {
+        if (t.kind != T_BVH || t.node_count <= 0) continue;
+        const BvhNode& root = hs.nodes[t.first_node];
+        const double* a = hs.xforms64[t.xform].m;          // rows of the affine inv_transform
+        const double det = a[0] * (a[5] * a[10] - a[6] * a[9]) - a[1] * (a[4] * a[10] - a[6] * a[8]) + a[2] * (a[4] * a[9] - a[5] * a[8]);
+        const double m[9] = {(a[5] * a[10] - a[6] * a[9]) / det, (a[2] * a[9] - a[1] * a[10]) / det, (a[1] * a[6] - a[2] * a[5]) / det,
+                             (a[6] * a[8] - a[4] * a[10]) / det, (a[0] * a[10] - a[2] * a[8]) / det, (a[2] * a[4] - a[0] * a[6]) / det,
+                             (a[4] * a[9] - a[5] * a[8]) / det, (a[1] * a[8] - a[0] * a[9]) / det, (a[0] * a[5] - a[1] * a[4]) / det};
+        const double c[3] = {root.cx - a[3], root.cy - a[7], root.cz - a[11]};      // M c = A^-1 (c - translation of inv_transform)
+        const double h[3] = {root.hx, root.hy, root.hz};
+        double wc[3], wh[3], hmax = 0, cmax = 0;
+        bool finite = std::isfinite(det) && det != 0.0;
+        for (int i = 0; i < 3; ++i) {
+            wc[i] = m[3 * i] * c[0] + m[3 * i + 1] * c[1] + m[3 * i + 2] * c[2];
+            wh[i] = std::fabs(m[3 * i]) * h[0] + std::fabs(m[3 * i + 1]) * h[1] + std::fabs(m[3 * i + 2]) * h[2];
+            finite = finite && std::isfinite(wc[i]) && std::isfinite(wh[i]);
+            hmax = std::max(hmax, wh[i]); cmax = std::max(cmax, std::fabs(wc[i]));
+        }
+        const double pad = 1e-3 * hmax + 1e-4 * cmax + 1e-6;
+        for (int i = 0; i < 3; ++i) out.push_back(finite ? (float)wc[i] : 0.f);
+        out.push_back(0.f);
+        for (int i = 0; i < 3; ++i) out.push_back(finite ? (float)(wh[i] + pad) : INFINITY);
+        out.push_back(0.f);
+    }
 }
 
 }  // namespace jsrt

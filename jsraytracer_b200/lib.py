@@ -67,6 +67,7 @@ EXPORTS = [
     "jsrt_read_accum", "jsrt_read_aov", "jsrt_accum_device_ptr", "jsrt_add_passes", "jsrt_primary_hits", "jsrt_scene_info",
     "jsrt_stats_get", "jsrt_stats_reset", "jsrt_set_profiling", "jsrt_last_error", "jsrt_bvh_build",
     "jsrt_bvh_node_count", "jsrt_bvh_leaf_object_count", "jsrt_bvh_copy", "jsrt_bvh_free", "jsrt_measure_read_bandwidth",
+    "jsrt_bvh_world_boxes",
 ]
 
 
@@ -112,6 +113,8 @@ def load():
     L.jsrt_bvh_free.argtypes = [vp]
     L.jsrt_bvh_free.restype = None
     L.jsrt_measure_read_bandwidth.argtypes = [i32, sz, i32, vp]
+    L.jsrt_bvh_world_boxes.restype = i32
+    L.jsrt_bvh_world_boxes.argtypes = [vp, vp, i32]
     _LIB = L
     return L
 
@@ -170,6 +173,16 @@ class Scene:
         i = Info()
         self._ck(self._L.jsrt_scene_info(self._h, C.byref(i)))
         return i.as_dict()
+
+    def bvh_world_boxes(self):
+        """(n, 2, 3) array: padded world-space (centre, half size) of every BVHAggregate (works on host-only handles)."""
+        import numpy as np
+        n = self._L.jsrt_bvh_world_boxes(self._h, None, 0)
+        if n < 0:
+            raise JsrtError(last_error())
+        out = np.zeros((max(n, 1), 8), dtype=np.float32)
+        self._L.jsrt_bvh_world_boxes(self._h, out.ctypes.data, n)
+        return out[:n].reshape(n, 2, 4)[:, :, :3].copy()
 
     def upload(self):
         self._ck(self._L.jsrt_scene_upload(self._h))

@@ -88,3 +88,27 @@ def test_dragon_tree_shape():
     bvh = test["renderer"].world.objects[1]
     assert len(bvh.objects) == 99968
     assert bvh.nodeCount() == 199935 and bvh.maxDepth() == 24
+
+
+@pytest.mark.parametrize("name,kw", [("starwars", {}), ("AMultipleBVH", {}), ("AHollowTetrahedron", {}), ("x_wing", {}), ("bottle", {})])
+def test_world_boxes_contain_the_aggregates(name, kw):
+    """The padded world-space box the device tests in front of each BVHAggregate (csrc/scene_flatten.cpp:
+    computeWorldBoxes) must contain every vertex of the aggregate mapped to world space — otherwise the reject would
+    drop hits the reference's walk over world.objects (src/world.js:7-15, src/aggregates.js:43-46) finds — and should
+    not be much larger than the tight box of those vertices."""
+    from jsraytracer_b200 import lib, scenes
+    from jsraytracer_b200.serializer import Serializer
+    from jsraytracer_b200.world import BVHAggregate
+    test = scenes.configure(name, width=16, height=16, **kw)
+    boxes = lib.Scene(Serializer(test).to_msgpack(), lib.FORMAT_MSGPACK, device=None).bvh_world_boxes()
+    aggs = [o for o in test["renderer"].world.objects if isinstance(o, BVHAggregate)]
+    assert len(boxes) == len(aggs) >= 1
+    for (c, h), agg in zip(boxes.astype(np.float64), aggs):
+        M = np.array(agg.transform.rows, dtype=np.float64)
+        pts = np.array([[float(x) for x in p.v[:3]] + [1.0] for prim in agg.objects for p in prim.geometry.ps], dtype=np.float64)
+        # triangles of an OBJ carry the loader's transform themselves (identity in these scenes); the aggregate's maps them to the world
+        pts = pts @ np.array(agg.objects[0].transform.rows, dtype=np.float64).T
+        w = (pts @ M.T)[:, :3]
+        lo, hi = w.min(axis=0), w.max(axis=0)
+        assert np.all(c - h <= lo) and np.all(c + h >= hi), (name, c, h, lo, hi)
+        assert np.all(h <= 0.5 * (hi - lo) * 1.75 + 1e-2 * (1 + np.abs(c).max())), (name, h, hi - lo)     # an AABB of a rotated AABB: bounded slack
