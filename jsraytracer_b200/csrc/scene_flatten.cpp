@@ -52,7 +52,12 @@ struct Flattener {
     }
 
     // ---- material colours (src/materials.js:2-76) ------------------------------
+    // nesting limits (NestGuard): material-colour / aggregate nesting, BVH depth (the reference's trees are ~log2 N deep;
+    // the dragon's is 24)
+    static constexpr int kMaxNest = 256, kMaxTreeDepth = 1024;
+    int nest = 0, tree_nest = 0;
     Folded fold(const Val* mc) {
+        NestGuard guard(nest, kMaxNest);
         mc = doc.resolve(mc);
         const std::string& t = doc.typeName(mc);
         Folded f{}; f.checker = false;
@@ -268,6 +273,7 @@ struct Flattener {
 
     // prim_id assignment: DFS of world.objects descending into Aggregate.objects
     void assignIds(const Val* objects) {
+        NestGuard guard(nest, kMaxNest);
         for (uint32_t i = 0; i < doc.length(objects); ++i) {
             const Val* o = doc.at(objects, i);
             const std::string& t = doc.typeName(o);
@@ -279,6 +285,7 @@ struct Flattener {
     // ---- BVH layout in reference visit order (src/aggregates.js:207-225) ------------
     // Number of objects below node `n` if they are all Triangles and there are at most `cap` of them, else cap + 1.
     int smallTriSubtree(const Val* n, int cap) {
+        NestGuard guard(tree_nest, kMaxTreeDepth);
         n = doc.resolve(n);
         if (doc.truthy(doc.field(n, "isLeaf"))) {
             const Val* objs = doc.field(n, "objects");
@@ -297,6 +304,7 @@ struct Flattener {
     }
     // the objects below `n` in the reference's visit order (greater child first)
     void placeSubtree(const Val* n) {
+        NestGuard guard(tree_nest, kMaxTreeDepth);
         n = doc.resolve(n);
         if (doc.truthy(doc.field(n, "isLeaf"))) {
             const Val* objs = doc.field(n, "objects");
@@ -315,6 +323,7 @@ struct Flattener {
     int leaf_tris = 2;                 // measured: profiles/r1_ab.md (2 is the best of 1..8 on bunny_path, dragon and starwars)
     int collapsed_nodes = 0;           // reference nodes folded into multi-triangle leaves
     void refStats(const Val* n, int depth) {
+        NestGuard guard(tree_nest, kMaxTreeDepth);
         n = doc.resolve(n);
         if (depth > out.max_bvh_depth) out.max_bvh_depth = depth;
         if (doc.truthy(doc.field(n, "isLeaf"))) return;
@@ -323,6 +332,7 @@ struct Flattener {
         refStats(doc.field(n, "lesser_node"), depth + 1);
     }
     void layoutNode(const Val* n, int first_node, int first_prim, int depth) {
+        NestGuard guard(tree_nest, kMaxTreeDepth);
         n = doc.resolve(n);
         if (depth > out.max_bvh_depth) out.max_bvh_depth = depth;
         const int me = (int)out.nodes.size();
@@ -370,6 +380,7 @@ struct Flattener {
     }
 
     void listMembers(const Val* objects, const double* outer) {
+        NestGuard guard(nest, kMaxNest);
         for (uint32_t i = 0; i < doc.length(objects); ++i) {
             const Val* o = doc.at(objects, i);
             const std::string& t = doc.typeName(o);

@@ -17,6 +17,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <algorithm>
+
 #include "host_scene.h"
 
 namespace jsrt {
@@ -34,6 +36,12 @@ struct SdfCompiler {
 
     SdfCompiler(const WireDoc& d, HostScene& o) : doc(d), out(o) {}
 
+    // guards against malformed blobs: cyclic `_r` references (NestGuard) and iteration counts that would unroll into
+    // an unbounded program (the reference's scenes: 22..41 instructions per distance query, <= 10 iterations)
+    static constexpr int kMaxNest = 256;
+    static constexpr size_t kMaxInstrs = 1u << 20;
+    int nest = 0;
+
     // Peephole fusion (JSRT_SDF_FUSE=0 emits the plain code): the interpreter pays a fetch + dispatch per instruction,
     // and on the fractal scenes two thirds of the stream were stack shuffles.
     //   leaf; MIN|MAX      -> leaf with idx = 1|2 (folds into the distance below instead of pushing)
@@ -45,6 +53,7 @@ struct SdfCompiler {
     bool scale_is_one = true;              // the current scale accumulator has not been multiplied yet
     std::vector<bool> one_stack;
     void emit(int op, double a0 = 0, float f0 = 0, float f1 = 0, float f2 = 0, int idx = 0) {
+        if (out.sdf_code.size() >= kMaxInstrs) fail("jsrt: SDF program too long (more than 2^20 instructions after unrolling)");
         if (fuse && out.sdf_code.size() > prog_first) {
             SdfInstr& last = out.sdf_code.back();
             if ((op == S_MIN || op == S_MAX) && last.op >= S_SPHERE && last.op <= S_TETRA && last.idx == 0) {
@@ -95,6 +104,7 @@ struct SdfCompiler {
     void attach(const Val* n) { memit(MP_ATTACH, distanceProgram(n)); }
     // pushes node.getMaterialData(p) (the point is NOT transformed on the way down: src/sdf.js:334-336,358-361)
     void material(const Val* n) {
+        NestGuard guard(nest, kMaxNest);
         n = doc.resolve(n);
         const std::string& ty = doc.typeName(n);
         auto base = [&](float c[3]) { double v[4] = {1, 1, 1, 0}; if (const Val* b = doc.field(n, "basecolor")) doc.vec(b, v); for (int i = 0; i < 3; ++i) c[i] = (float)v[i]; };
@@ -120,20 +130,26 @@ struct SdfCompiler {
 
     // how many times transformer `t` multiplies its caller's scale accumulator by something other than a literal 1
     int scaleMultiplications(const Val* t) {
+        NestGuard guard(nest, kMaxNest);
         t = doc.resolve(t);
         const std::string& ty = doc.typeName(t);
         if (ty == "SDFTransformerSequence") { int m = 0; const Val* ts = doc.field(t, "transformers"); for (uint32_t i = 0; i < doc.length(ts); ++i) m += scaleMultiplications(doc.at(ts, i)); return m; }
-        if (ty == "SDFRecursiveTransformer") return (int)doc.number(doc.field(t, "iterations"), 0) * scaleMultiplications(doc.field(t, "transformer"));
+        if (ty == "SDFRecursiveTransformer") {
+            const double m = std::min(doc.number(doc.field(t, "iterations"), 0), 2e9) * (double)scaleMultiplications(doc.field(t, "transformer"));
+            return (int)std::min(m, 2e9);
+        }
         return ty == "SDFMatrixTransformer" ? 1 : 0;
     }
     void transformer(const Val* t) {
+        NestGuard guard(nest, kMaxNest);
         t = doc.resolve(t);
         const std::string& ty = doc.typeName(t);
         if (ty == "SDFTransformerSequence" || ty == "SDFRecursiveTransformer") {
             // `let s = 1; for (...) s = s * st; return [p, s]` (src/sdf.js:387-394,408-415): a local scale accumulator
             const bool seq = ty == "SDFTransformerSequence";
             const Val* ts = seq ? doc.field(t, "transformers") : nullptr;
-            const int n = seq ? (int)doc.length(ts) : (int)doc.number(doc.field(t, "iterations"), 0);
+            const int n = seq ? (int)doc.length(ts) : (int)std::min(doc.number(doc.field(t, "iterations"), 0), 2e9);
+            if (n > (int)kMaxInstrs) fail("jsrt: SDF transformer iteration count out of range");
             int mults = 0;
             for (int i = 0; i < n; ++i) mults += scaleMultiplications(seq ? doc.at(ts, i) : doc.field(t, "transformer"));
             const bool elide = fuse && (mults <= 1 || scale_is_one);
@@ -163,6 +179,7 @@ struct SdfCompiler {
     }
 
     void node(const Val* n) {
+        NestGuard guard(nest, kMaxNest);
         n = doc.resolve(n);
         const std::string& ty = doc.typeName(n);
         if (ty == "SphereSDF") { noteBase(n); any_sphere_leaf = true; emit(S_SPHERE, doc.number(doc.field(n, "radius"), kInf)); }
@@ -185,7 +202,8 @@ struct SdfCompiler {
             scale_is_one = one_stack.back(); one_stack.pop_back();
         }
         else if (ty == "RecursiveTransformUnionSDF") {
-            const int it = (int)doc.number(doc.field(n, "iterations"), 0);
+            const int it = (int)std::min(doc.number(doc.field(n, "iterations"), 0), 2e9);
+            if (it > (int)kMaxInstrs) fail("jsrt: RecursiveTransformUnionSDF iteration count out of range");
             emit(S_PUSHP); one_stack.push_back(scale_is_one); scale_is_one = true;
             node(doc.field(n, "sdf"));
             for (int i = 0; i < it; ++i) { transformer(doc.field(n, "transformer")); node(doc.field(n, "sdf")); emit(S_MULS); emit(S_MIN); }

@@ -107,12 +107,15 @@ Val WireDoc::parseMsgpack(const uint8_t*& p, const uint8_t* e, int depth) {
     Val v;
     uint8_t t = *p++;
     auto str = [&](uint64_t n) { if ((uint64_t)(e - p) < n) fail("jsrt: truncated msgpack string"); v.type = Val::STR; v.str = (const char*)p; v.count = (uint32_t)n; p += n; };
+    // every element occupies at least one byte: a count beyond the remaining input is malformed (and must not be reserved)
     auto arr = [&](uint64_t n) {
+        if (n > (uint64_t)(e - p)) fail("jsrt: truncated msgpack array");
         v.type = Val::ARR; std::vector<Val> kids; kids.reserve(n);
         for (uint64_t i = 0; i < n; ++i) kids.push_back(parseMsgpack(p, e, depth + 1));
         v.count = (uint32_t)n; v.first = commit(kids);
     };
     auto map = [&](uint64_t n) {
+        if (2 * n > (uint64_t)(e - p)) fail("jsrt: truncated msgpack map");
         v.type = Val::MAP; std::vector<Val> kids; kids.reserve(2 * n);
         for (uint64_t i = 0; i < 2 * n; ++i) kids.push_back(parseMsgpack(p, e, depth + 1));
         v.count = (uint32_t)n; v.first = commit(kids);

@@ -69,4 +69,14 @@ private:
 
 [[noreturn]] inline void fail(const std::string& m) { throw std::runtime_error(m); }
 
+// Recursion guard for walks over the object graph: `_r` references can make a malformed blob cyclic, and a cycle
+// must end in an error, not in a stack overflow inside the host process.
+struct NestGuard {
+    int& depth;
+    NestGuard(int& d, int limit) : depth(d) { if (depth >= limit) fail("jsrt: scene graph nested too deep (cyclic reference?)"); ++depth; }
+    ~NestGuard() { --depth; }
+    NestGuard(const NestGuard&) = delete;
+    NestGuard& operator=(const NestGuard&) = delete;
+};
+
 }  // namespace jsrt
