@@ -105,7 +105,9 @@ struct Flattener {
         const Val* img = doc.field(mc, "_imgdata");
         if (!img) fail("jsrt: TextureMaterialColor without _imgdata");
         Texture t{};
-        t.width = (int)doc.number(doc.field(img, "width"), 0); t.height = (int)doc.number(doc.field(img, "height"), 0);
+        const double tw = doc.number(doc.field(img, "width"), 0), th = doc.number(doc.field(img, "height"), 0);
+        if (tw > 32768 || th > 32768) fail("jsrt: TextureMaterialColor larger than 32768 texels on a side");
+        t.width = tw >= 1 ? (int)tw : 0; t.height = th >= 1 ? (int)th : 0;
         if (t.width <= 0 || t.height <= 0) fail("jsrt: TextureMaterialColor with an empty image (a browser ImageData serialises empty: SURVEY.md §8b)");
         const size_t nbytes = (size_t)t.width * t.height * 4;
         while (out.texels.size() % 16) out.texels.push_back(0);
@@ -401,11 +403,18 @@ struct Flattener {
         if (!rend) fail("jsrt: scene blob has no 'renderer' (expected Serializer({renderer,width,height}))");
         out.renderer_type = doc.typeName(rend);
         out.jitter = out.renderer_type != "SimpleRenderer";
-        out.width = (int)doc.number(doc.field(root, "width"), 0);
-        out.height = (int)doc.number(doc.field(root, "height"), 0);
-        if (out.width <= 0 || out.height <= 0) fail("jsrt: scene blob has no positive width/height");
-        out.max_depth = (int)doc.number(doc.field(rend, "maxRecursionDepth"), 3);
-        out.samples_per_pixel = doc.field(rend, "samplesPerPixel") ? (int)doc.number(doc.field(rend, "samplesPerPixel"), 1) : 1;
+        // header numbers are range-checked before the casts (a double outside int's range is undefined behaviour in C++)
+        auto ranged = [&](const Val* v, double dflt, double lo, double hi, const char* what) {
+            const double x = doc.number(v, dflt);
+            if (!(x >= lo && x <= hi)) fail(std::string("jsrt: ") + what + " out of range");
+            return (int)x;
+        };
+        if (!doc.field(root, "width") || !doc.field(root, "height")) fail("jsrt: scene blob has no positive width/height");
+        out.width = ranged(doc.field(root, "width"), 0, 1, 65536, "width");
+        out.height = ranged(doc.field(root, "height"), 0, 1, 65536, "height");
+        if ((long long)out.width * out.height > (1LL << 28)) fail("jsrt: image larger than 2^28 pixels");
+        out.max_depth = ranged(doc.field(rend, "maxRecursionDepth"), 3, -1e9, 1e9, "maxRecursionDepth");      // jsrt_render accepts 1..255
+        out.samples_per_pixel = doc.field(rend, "samplesPerPixel") ? ranged(doc.field(rend, "samplesPerPixel"), 1, -1e9, 1e9, "samplesPerPixel") : 1;
 
         const Val* cam = doc.field(rend, "camera");
         if (!cam) fail("jsrt: renderer has no camera");
@@ -508,7 +517,9 @@ struct Flattener {
                 double p[4]; doc.vec(doc.field(l, "position"), p);
                 for (int k = 0; k < 4; ++k) d.pos[k] = (float)p[k];
             } else if (ty == "RandomSampleAreaLight") {
-                d.kind = L_AREA; d.samples = (int)doc.number(doc.field(l, "samples"), 1);
+                const double ns = doc.number(doc.field(l, "samples"), 1);
+                if (!(ns >= 0 && ns <= 65536)) fail("jsrt: RandomSampleAreaLight.samples out of range");
+                d.kind = L_AREA; d.samples = (int)ns;
                 const std::string& gt = doc.typeName(doc.field(l, "surface_geometry"));
                 if (gt == "Square") d.geom = G_SQUARE; else if (gt == "Circle") d.geom = G_CIRCLE; else if (gt == "Sphere") d.geom = G_SPHERE;
                 else fail("jsrt: area light surface '" + gt + "' has no sampleSurface in the reference");
