@@ -178,6 +178,21 @@ int jsrt_bvh_leaf_object_count(const jsrt_bvh*);
 int jsrt_bvh_copy(const jsrt_bvh*, jsrt_bvh_node* nodes, int32_t* leaf_objects);
 void jsrt_bvh_free(jsrt_bvh*);
 
+/* The geometry half of parseObjFile (src/objloader.js:149-238) on OBJ text: positions (x y z w), texcoords (u v w),
+ * normals (x y z 0) as f32, fan-triangulated faces as 9 ints per triangle ((v, vt, vn) x 3, 0-based, -1 = absent),
+ * the `usemtl` index of every triangle (-1 = none, names in order of first appearance) and the `mtllib` arguments.
+ * Same tokenisation, Number.parseFloat and index-regex semantics as the reference (csrc/obj_parse.cpp).
+ * jsrt_obj_parse always returns a handle; jsrt_obj_error is NULL on success, else the reference's parse-error text.
+ * counts = {positions, texcoords, normals, triangles, material names, mtllibs}. */
+typedef struct jsrt_obj jsrt_obj;
+jsrt_obj* jsrt_obj_parse(const char* text, size_t len);
+const char* jsrt_obj_error(const jsrt_obj*);
+void jsrt_obj_counts(const jsrt_obj*, int32_t counts[6]);
+void jsrt_obj_copy(const jsrt_obj*, float* positions, float* texcoords, float* normals, int32_t* faces, int32_t* face_material);
+const char* jsrt_obj_material_name(const jsrt_obj*, int i);
+const char* jsrt_obj_mtllib(const jsrt_obj*, int i);
+void jsrt_obj_free(jsrt_obj*);
+
 #ifdef __cplusplus
 }
 #endif

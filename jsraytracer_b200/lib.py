@@ -67,7 +67,8 @@ EXPORTS = [
     "jsrt_read_accum", "jsrt_read_aov", "jsrt_accum_device_ptr", "jsrt_add_passes", "jsrt_primary_hits", "jsrt_scene_info",
     "jsrt_stats_get", "jsrt_stats_reset", "jsrt_set_profiling", "jsrt_last_error", "jsrt_bvh_build",
     "jsrt_bvh_node_count", "jsrt_bvh_leaf_object_count", "jsrt_bvh_copy", "jsrt_bvh_free", "jsrt_measure_read_bandwidth",
-    "jsrt_bvh_world_boxes",
+    "jsrt_bvh_world_boxes", "jsrt_obj_parse", "jsrt_obj_error", "jsrt_obj_counts", "jsrt_obj_copy", "jsrt_obj_material_name",
+    "jsrt_obj_mtllib", "jsrt_obj_free",
 ]
 
 
@@ -113,6 +114,20 @@ def load():
     L.jsrt_bvh_free.argtypes = [vp]
     L.jsrt_bvh_free.restype = None
     L.jsrt_measure_read_bandwidth.argtypes = [i32, sz, i32, vp]
+    L.jsrt_obj_parse.restype = vp
+    L.jsrt_obj_parse.argtypes = [C.c_char_p, sz]
+    L.jsrt_obj_error.restype = C.c_char_p
+    L.jsrt_obj_error.argtypes = [vp]
+    L.jsrt_obj_counts.restype = None
+    L.jsrt_obj_counts.argtypes = [vp, vp]
+    L.jsrt_obj_copy.restype = None
+    L.jsrt_obj_copy.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.jsrt_obj_material_name.restype = C.c_char_p
+    L.jsrt_obj_material_name.argtypes = [vp, i32]
+    L.jsrt_obj_mtllib.restype = C.c_char_p
+    L.jsrt_obj_mtllib.argtypes = [vp, i32]
+    L.jsrt_obj_free.restype = None
+    L.jsrt_obj_free.argtypes = [vp]
     L.jsrt_bvh_world_boxes.restype = i32
     L.jsrt_bvh_world_boxes.argtypes = [vp, vp, i32]
     _LIB = L

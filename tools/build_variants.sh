@@ -9,14 +9,14 @@ OUT="$ROOT/jsraytracer_b200/variants"
 OBJ=/tmp/jsrt_variant_obj
 mkdir -p "$OUT" "$OBJ"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
-for f in api wire scene_flatten sdf_compile bvh_build; do
+for f in api wire scene_flatten sdf_compile bvh_build obj_parse; do
   nvcc $FLAGS -c "$CSRC/$f.cpp" -o "$OBJ/$f.o" &
 done
 wait
 for spec in "$@"; do
   name="${spec%%:*}"; defs="${spec#*:}"
   ( nvcc $FLAGS $defs -c "$CSRC/render.cu" -o "$OBJ/render_$name.o" && \
-    nvcc -shared -o "$OUT/libjsrt_$name.so" "$OBJ/render_$name.o" "$OBJ"/{api,wire,scene_flatten,sdf_compile,bvh_build}.o && echo "built $name ($defs)" ) &
+    nvcc -shared -o "$OUT/libjsrt_$name.so" "$OBJ/render_$name.o" "$OBJ"/{api,wire,scene_flatten,sdf_compile,bvh_build,obj_parse}.o && echo "built $name ($defs)" ) &
 done
 wait
 ls -la "$OUT"
