@@ -76,3 +76,40 @@ def test_unsupported_feature_is_an_error_not_a_guess():
     with pytest.raises(lib.JsrtError) as e:
         lib.Scene(Serializer(test).to_msgpack(), lib.FORMAT_MSGPACK, device=None)
     assert "TextureMaterialColor" in str(e.value)
+
+
+def test_degenerate_scenes_flatten_and_render_in_the_oracle():
+    """Edge cases of the boundary: an empty world (every ray returns bg_color, src/world.js:35), a world without lights
+    (ambient term only, src/materials.js:240-259), a 1x1 image, header values out of range."""
+    import json
+    from jsraytracer_b200 import scenes
+    from jsraytracer_b200.cameras import PerspectiveCamera
+    from jsraytracer_b200.jsmath import Mat4, Vec
+    from jsraytracer_b200.renderers import SimpleRenderer
+    from jsraytracer_b200.serializer import Serializer
+    from jsraytracer_b200.world import World
+    from oracle.oracle import OracleScene
+    cam = PerspectiveCamera(0.7, 1, Mat4.identity())
+    empty = {"renderer": SimpleRenderer(World([], [], Vec.of(0.25, 0.5, 0.75)), cam, 3), "width": 5, "height": 3}
+    ser = Serializer(empty)
+    info = lib.Scene(ser.to_msgpack(), lib.FORMAT_MSGPACK, device=None).info
+    assert (info["n_prims"], info["n_lights"], info["n_nodes"], info["light_samples"]) == (0, 0, 0, 0)
+    img, cnt = OracleScene(ser.to_json()).render(1, seed=1, jitter=False)
+    assert img.shape == (3, 5, 3) and np.allclose(img, [0.25, 0.5, 0.75]) and cnt["rays_primary"] == 15 and cnt["rays_shadow"] == 0
+    ids, t, _ = OracleScene(ser.to_json()).primary_hits()
+    assert (ids == -1).all()
+
+    one = scenes.configure("BoxBall", width=1, height=1)
+    one["renderer"].world.lights = []                                   # no lights: ambient + reflections only
+    ser = Serializer(one)
+    info = lib.Scene(ser.to_json(), lib.FORMAT_JSON, device=None).info
+    assert (info["width"], info["height"], info["n_lights"], info["light_samples"]) == (1, 1, 0, 0)
+    img, cnt = OracleScene(ser.to_json()).render(2, seed=1)
+    assert img.shape == (1, 1, 3) and np.isfinite(img).all() and cnt["rays_shadow"] == 0
+
+    doc = json.loads(Serializer(scenes.configure("BoxBall", width=8, height=8)).to_json())
+    for key, bad in (("width", 0), ("width", 1e12), ("height", -3), ("height", 70000)):
+        d = json.loads(json.dumps(doc))
+        d["_v"][key] = bad
+        with pytest.raises(lib.JsrtError, match="width|height"):
+            lib.Scene(json.dumps(d), lib.FORMAT_JSON, device=None)
