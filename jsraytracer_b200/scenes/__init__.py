@@ -650,6 +650,27 @@ REGISTRY = {f.__name__: f for f in (
     utah_teapot, x_wing, SDF_SphereRepetition, bottle)}
 
 
+# tests/dragon_json/test.mjs: `Serializer.deserializeJSON(fetch("../tests/dragon/test.json"))` — the dragon scene as a wire blob
+# (the file itself is not in the reference tree; tests/test_to_json.js writes it from tests/dragon/test.mjs)
+def dragon_json(**overrides):
+    from ..serializer import Serializer
+    return Serializer.deserializeJSON(Serializer(dragon(**overrides)).to_json())
+
+
+# tests/toledo/test.mjs and tests/toledo_json/test.mjs need assets/ToledoCity/Toledo.obj, which the reference tree lists under
+# .MISSING_LARGE_BLOBS: the scene is one BVHAggregate over that mesh (loadObjFile + BVHAggregate.build, like tests/x-wing).
+def toledo(**overrides):
+    raise FileNotFoundError("tests/toledo needs assets/ToledoCity/Toledo.obj, which is not part of the reference tree "
+                            "(.MISSING_LARGE_BLOBS); starwars and dragon_grid stand in for it (SURVEY.md §8d)")
+
+
+REGISTRY.update({"dragon_json": dragon_json, "toledo": toledo, "toledo_json": toledo})
+# names as they appear in the reference's tests/list.json
+ALIASES = {"x-wing": "x_wing"}
+# in tests/list.json but not transcribed: its transform is built from `Math.pi` (undefined -> NaN, tests/SDF_RecursiveUnionTest/test.mjs:42)
+NOT_TRANSCRIBED = {"SDF_RecursiveUnionTest"}
+
+
 def configure(name, **overrides):
     """`import(test.mjs).configureTest(cb)`: returns `{renderer, width, height}`."""
-    return REGISTRY[name](**overrides)
+    return REGISTRY[ALIASES.get(name, name)](**overrides)
