@@ -38,7 +38,11 @@ struct Counters {
     uint64_t top_tests[3] = {0, 0, 0};   // top-level list object intersect calls
     uint64_t sdf_evals[3] = {0, 0, 0};   // root_sdf.distance() calls while marching
     uint64_t shaded_hits = 0;
+    // diagnostic (not part of the reference's algorithm): inner nodes whose box was hit at a depth that is a multiple of
+    // 2 / of 3 — the node records a 4-wide / 8-wide collapse of the same tree would fetch for the same ray
+    uint64_t wide4[3] = {0, 0, 0}, wide8[3] = {0, 0, 0};
     void add(const Counters& o) {
+        for (int i = 0; i < 3; ++i) { wide4[i] += o.wide4[i]; wide8[i] += o.wide8[i]; }
         for (int i = 0; i < 3; ++i) { rays[i] += o.rays[i]; bvh_nodes[i] += o.bvh_nodes[i]; bvh_prims[i] += o.bvh_prims[i]; top_tests[i] += o.top_tests[i]; sdf_evals[i] += o.sdf_evals[i]; }
         shaded_hits += o.shaded_hits;
     }
@@ -578,10 +582,11 @@ struct Aggregate : WorldObject {      // src/aggregates.js:1-19
 
 struct BVHNode {                      // src/aggregates.js:63-232
     bool isLeaf = false; std::vector<WorldObject*> objects; AABBox aabb; BVHNode *lesser = nullptr, *greater = nullptr;
-    void intersect(const Ray& ray, Intersection& ret, double minDist, double maxDist, bool intersectTransparent, Ctx& ctx) const {
+    void intersect(const Ray& ray, Intersection& ret, double minDist, double maxDist, bool intersectTransparent, Ctx& ctx, int depth = 0) const {
         if (ctx.c) ctx.c->bvh_nodes[ctx.rc]++;
         auto ts = aabb.get_intersects(ray, minDist, maxDist);
         if (ts.hit && ts.min <= maxDist && ts.max >= minDist && ts.min <= ret.distance) {
+            if (ctx.c && !isLeaf) { if (depth % 2 == 0) ctx.c->wide4[ctx.rc]++; if (depth % 3 == 0) ctx.c->wide8[ctx.rc]++; }
             if (isLeaf) {
                 for (auto* o : objects) {
                     if (ctx.c) ctx.c->bvh_prims[ctx.rc]++;
@@ -592,8 +597,8 @@ struct BVHNode {                      // src/aggregates.js:63-232
                     }
                 }
             } else {
-                greater->intersect(ray, ret, minDist, maxDist, intersectTransparent, ctx);
-                lesser->intersect(ray, ret, minDist, maxDist, intersectTransparent, ctx);
+                greater->intersect(ray, ret, minDist, maxDist, intersectTransparent, ctx, depth + 1);
+                lesser->intersect(ray, ret, minDist, maxDist, intersectTransparent, ctx, depth + 1);
             }
         }
     }
@@ -1063,7 +1068,7 @@ int orc_primary_hits(void* h, int W, int H, int32_t* prim_id, double* tout, int 
                 tout[i] = in.distance;
             }
         });
-        if (counters) { Counters t; for (auto& c : cs) t.add(c); for (int i = 0; i < 3; ++i) { counters[i] = t.rays[i]; counters[3 + i] = t.bvh_nodes[i]; counters[6 + i] = t.bvh_prims[i]; counters[9 + i] = t.top_tests[i]; counters[12 + i] = t.sdf_evals[i]; } counters[15] = t.shaded_hits; }
+        if (counters) { Counters t; for (auto& c : cs) t.add(c); for (int i = 0; i < 3; ++i) { counters[i] = t.rays[i]; counters[3 + i] = t.bvh_nodes[i]; counters[6 + i] = t.bvh_prims[i]; counters[9 + i] = t.top_tests[i]; counters[12 + i] = t.sdf_evals[i]; } counters[15] = t.shaded_hits; for (int i = 0; i < 3; ++i) { counters[16 + i] = t.wide4[i]; counters[19 + i] = t.wide8[i]; } }
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
@@ -1072,7 +1077,7 @@ int orc_primary_hits(void* h, int W, int H, int32_t* prim_id, double* tout, int 
 // [first_pass, first_pass+n_passes): `sum` (W*H*3 f32, row-major) is the
 // reference's `buffer[px][py]` and is accumulated in f32 like `Vec.plus`.
 // flags bit0: no pixel jitter (SimpleRenderer sampling, :21-25).
-// counters[16]: rays[3], bvh_nodes[3], bvh_prims[3], top_tests[3], sdf_evals[3], shaded_hits
+// counters[22]: rays[3], bvh_nodes[3], bvh_prims[3], top_tests[3], sdf_evals[3], shaded_hits, wide4[3], wide8[3]
 int orc_render(void* h, int W, int H, int first_pass, int n_passes, uint64_t seed, int flags, int x_offset, int x_delt,
                float* sum, int nthreads, uint64_t* counters) {
     Scene* s = (Scene*)h;
@@ -1099,7 +1104,7 @@ int orc_render(void* h, int W, int H, int first_pass, int n_passes, uint64_t see
                 }
             }
         });
-        if (counters) { Counters t; for (auto& c : cs) t.add(c); for (int i = 0; i < 3; ++i) { counters[i] = t.rays[i]; counters[3 + i] = t.bvh_nodes[i]; counters[6 + i] = t.bvh_prims[i]; counters[9 + i] = t.top_tests[i]; counters[12 + i] = t.sdf_evals[i]; } counters[15] = t.shaded_hits; }
+        if (counters) { Counters t; for (auto& c : cs) t.add(c); for (int i = 0; i < 3; ++i) { counters[i] = t.rays[i]; counters[3 + i] = t.bvh_nodes[i]; counters[6 + i] = t.bvh_prims[i]; counters[9 + i] = t.top_tests[i]; counters[12 + i] = t.sdf_evals[i]; } counters[15] = t.shaded_hits; for (int i = 0; i < 3; ++i) { counters[16 + i] = t.wide4[i]; counters[19 + i] = t.wide8[i]; } }
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }

@@ -17,7 +17,9 @@ COUNTER_NAMES = ["rays_primary", "rays_secondary", "rays_shadow",
                  "bvh_nodes_primary", "bvh_nodes_secondary", "bvh_nodes_shadow",
                  "bvh_prims_primary", "bvh_prims_secondary", "bvh_prims_shadow",
                  "top_tests_primary", "top_tests_secondary", "top_tests_shadow",
-                 "sdf_evals_primary", "sdf_evals_secondary", "sdf_evals_shadow", "shaded_hits"]
+                 "sdf_evals_primary", "sdf_evals_secondary", "sdf_evals_shadow", "shaded_hits",
+                 # diagnostic: node records a 4-wide / 8-wide collapse of the reference's tree would fetch for the same rays
+                 "wide4_primary", "wide4_secondary", "wide4_shadow", "wide8_primary", "wide8_secondary", "wide8_shadow"]
 
 
 def build():
@@ -89,7 +91,7 @@ class OracleScene:
         W, H = width or self.width, height or self.height
         ids = np.empty(W * H, dtype=np.int32)
         t = np.empty(W * H, dtype=np.float64)
-        cnt = np.zeros(16, dtype=np.uint64)
+        cnt = np.zeros(22, dtype=np.uint64)
         rc = self._L.orc_primary_hits(self._h, W, H, ids.ctypes.data, t.ctypes.data, threads or default_threads(),
                                       cnt.ctypes.data)
         if rc:
@@ -102,7 +104,7 @@ class OracleScene:
         W, H = width or self.width, height or self.height
         if accum is None:
             accum = np.zeros((H, W, 3), dtype=np.float32)
-        cnt = np.zeros(16, dtype=np.uint64)
+        cnt = np.zeros(22, dtype=np.uint64)
         rc = self._L.orc_render(self._h, W, H, first_pass, n_passes, seed, 0 if jitter else 1, x_offset, x_delt,
                                 accum.ctypes.data, threads or default_threads(), cnt.ctypes.data)
         if rc:
