@@ -245,3 +245,57 @@ def test_resolve_rounds_like_pixelbuffer_setcolor():
     assert out[0, 1].tolist() == [255, 0, 64, 255]             # clamped; Math.round(63.75) = 64
     out2 = O.resolve_rgba8(acc, 2)                              # two passes: mean = sum / 2
     assert out2[0, 2].tolist() == [64, 191, 255, 255]          # 0.25098 -> 64, 0.75 -> Math.round(191.25) = 191, 1.5 -> clamped
+
+
+def test_area_light_falloff_and_cosine_factor():
+    """RandomSampleAreaLight.sampleIterator (src/lights.js:80-93): colour * falloff(delta) * |normalize(delta) . n_light| with
+    n_light = normalize((T^-1)^T n_local).  A 1e-6-sized Square makes the sampled point independent of the random numbers."""
+    from jsraytracer_b200.geometry import Square
+    from jsraytracer_b200.jsmath import Mat4, Vec
+    from jsraytracer_b200.materials import PhongMaterial, RandomSampleAreaLight
+    I = 36 * math.pi * 0.8
+    wall = _wall(-5, PhongMaterial(Vec.of(1, 1, 1), 0.1, 0.5, 0, 7))
+    for tilt, cosine in ((0.0, 1.0), (math.pi / 3, 0.5), (math.pi / 2 - 1e-3, math.sin(1e-3))):
+        T = Mat4.translation([0, 0, -2]).times(Mat4.rotation(tilt, Vec.of(1, 0, 0))).times(Mat4.scale(1e-6))
+        light = RandomSampleAreaLight(Square(), T, Vec.of(1, 0.5, 0.25), I, 3)          # three samples, averaged
+        img, cnt = _scene([wall], [light], 1).render(1, seed=5, jitter=False)
+        expect = np.array([0.1, 0.1, 0.1]) + 0.5 * 0.8 * cosine * np.array([1, 0.5, 0.25])
+        assert np.allclose(img[1, 1], expect, atol=2e-6), (tilt, img[1, 1], expect)
+        assert cnt["rays_shadow"] == 4 * 3                                             # one shadow ray per sample per shaded hit
+
+
+def test_path_tracing_diffuse_weight_has_no_pdf_division():
+    """PhongPathTracingMaterial.scatter (src/materials.js:398-412): with mirrorProbability 0 and no specular lobe the
+    diffuse branch is always taken and weighs the scattered radiance by diffusivity / pi — as written, without dividing by
+    the selection probability or the cosine pdf.  Above an infinite wall every scattered ray escapes to bg_color, so the
+    pixel is ambient + bg * diffusivity / pi whatever the random numbers are."""
+    from jsraytracer_b200.jsmath import Vec
+    from jsraytracer_b200.materials import PhongPathTracingMaterial
+    bg = Vec.of(0.3, 0.6, 0.9)
+    mat = PhongPathTracingMaterial(Vec.of(1, 0.5, 1), 0.1, 0.6, 0, 5)                   # IOR infinite: kr = 1, no refraction branch
+    img, cnt = _scene([_wall(-4, mat)], [], 2, bg=bg).render(1, seed=9, jitter=False)
+    base = np.array([1, 0.5, 1])
+    expect = 0.1 * base + np.array([0.3, 0.6, 0.9]) * (0.6 * base) / math.pi
+    assert np.allclose(img[1, 1], expect, atol=3e-7), (img[1, 1], expect)
+    assert np.allclose(img[0, 0], expect, atol=3e-7)                                   # every pixel: the wall fills the frame
+    assert cnt["rays_secondary"] == 4
+    # depth 3: the escaped ray adds nothing more
+    img3, _ = _scene([_wall(-4, mat)], [], 3, bg=bg).render(1, seed=9, jitter=False)
+    assert np.allclose(img3, img, atol=1e-7)
+
+
+def test_fresnel_branch_weights_at_normal_incidence():
+    """FresnelPhongMaterial.color (src/materials.js:309-333): reflection weighted kr, refraction weighted 1 - kr, both traced;
+    unpolarised Fresnel at normal incidence: kr = ((n - 1) / (n + 1))^2 (:366-386).  A Fresnel sheet in front of an ambient-only
+    wall: the pixel is kr * bg (mirror ray escapes behind the camera) + (1 - kr) * wall colour."""
+    from jsraytracer_b200.jsmath import Vec
+    from jsraytracer_b200.materials import FresnelPhongMaterial, PhongMaterial
+    bg = Vec.of(0.2, 0.4, 0.8)
+    back = PhongMaterial(Vec.of(0.9, 0.6, 0.3), 1)                               # ambient = its colour, nothing else
+    for n in (1.5, 2.4):
+        sheet = FresnelPhongMaterial(Vec.of(1, 1, 1), 0, 0, 0, 5, n)
+        img, cnt = _scene([_wall(-3, sheet), _wall(-6, back)], [], 2, bg=bg).render(1, seed=1, jitter=False)
+        kr = ((n - 1) / (n + 1)) ** 2
+        expect = kr * np.array([0.2, 0.4, 0.8]) + (1 - kr) * np.array([0.9, 0.6, 0.3])
+        assert np.allclose(img[1, 1], expect, atol=3e-7), (n, img[1, 1], expect)
+        assert cnt["rays_secondary"] == 8                                          # two children per camera ray
