@@ -299,3 +299,74 @@ def test_fresnel_branch_weights_at_normal_incidence():
         expect = kr * np.array([0.2, 0.4, 0.8]) + (1 - kr) * np.array([0.9, 0.6, 0.3])
         assert np.allclose(img[1, 1], expect, atol=3e-7), (n, img[1, 1], expect)
         assert cnt["rays_secondary"] == 8                                          # two children per camera ray
+
+
+def test_vertex_normals_are_blended_by_barycentrics():
+    """Triangle.materialData / blend (src/geometry.js:376-385,397-409): the shading normal is the barycentric mix of the
+    per-vertex normals, normalised by Primitive.color (src/world.js:134).  Hit point (0,0,-5) has barycentrics
+    (0.25, 0.25, 0.5) in the triangle below; with n2 tilted 45 degrees the blend is tilted 22.5 degrees: L.N = cos(22.5 deg)."""
+    from jsraytracer_b200.geometry import Triangle
+    from jsraytracer_b200.jsmath import Vec
+    from jsraytracer_b200.materials import PhongMaterial, SimplePointLight
+    from jsraytracer_b200.world import Primitive
+    I = 36 * math.pi * 0.8
+    ps = [Vec.of(-4, -4, -5, 1), Vec.of(4, -4, -5, 1), Vec.of(0, 4, -5, 1)]
+    s = math.sqrt(0.5)
+    mat = PhongMaterial(Vec.of(1, 1, 1), 0.1, 0.5, 0, 7)
+    light = SimplePointLight(Vec.of(0, 0, -2, 1), Vec.of(1, 1, 1), I)
+    flat = Primitive(Triangle(ps, {}), mat)
+    smooth = Primitive(Triangle(ps, {"normal": [Vec.of(0, 0, 1, 0), Vec.of(0, 0, 1, 0), Vec.of(0, s, s, 0)]}), mat)
+    a, _ = _scene([flat], [light], 1).render(1, seed=1, jitter=False)
+    b, _ = _scene([smooth], [light], 1).render(1, seed=1, jitter=False)
+    assert np.allclose(a[1, 1], 0.1 + 0.5 * 0.8, atol=2e-7)
+    assert np.allclose(b[1, 1], 0.1 + 0.5 * 0.8 * math.cos(math.pi / 8), atol=3e-7), b[1, 1]
+
+
+def test_depth_of_field_rays_meet_on_the_focal_plane():
+    """DepthOfFieldPerspectiveCamera.getRayForPixel (src/cameras.js:46-52): origin += lens offset, direction =
+    normalize(dir * focus_distance - offset) — every lens sample of a pixel passes through the pinhole ray's point at
+    parameter focus_distance, i.e. on the plane z = -focus_distance for this camera.  A checkerboard wall exactly there
+    renders identically for any sensor size; the same wall nearer or farther does not."""
+    from jsraytracer_b200.cameras import DepthOfFieldPerspectiveCamera
+    from jsraytracer_b200.geometry import Plane
+    from jsraytracer_b200.jsmath import Mat4, Vec
+    from jsraytracer_b200.materials import CheckerboardMaterialColor, PhongMaterial
+    from jsraytracer_b200.renderers import SimpleRenderer
+    from jsraytracer_b200.serializer import Serializer
+    from jsraytracer_b200.world import Primitive, World
+
+    def render(z, sensor):
+        wall = Primitive(Plane(), PhongMaterial(CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0, 0, 0)), 1), Mat4.translation([0.25, 0.25, z]))
+        cam = DepthOfFieldPerspectiveCamera(math.pi / 2, 1, Mat4.identity(), 4.0, sensor)
+        test = {"renderer": SimpleRenderer(World([wall], []), cam, 1), "width": 16, "height": 16}
+        return O.OracleScene(Serializer(test).to_json()).render(1, seed=3, jitter=False)[0]
+
+    sharp = render(-4.0, 0.0)
+    assert 0.3 < sharp.mean() < 0.7                                      # a checkerboard, not a flat frame
+    assert np.array_equal(render(-4.0, 0.6), sharp)                      # in focus: the lens does not matter
+    assert not np.array_equal(render(-8.0, 0.6), render(-8.0, 0.0))      # out of focus: it does
+
+
+def test_sphere_tracing_converges_from_outside_within_epsilon():
+    """SDFGeometry.intersect (src/sdf.js:12-40): clip to the SDF's box, then t += distance / |d| until distance <= epsilon.
+    On a unit SphereSDF the march approaches the analytic root from the near side and stops within epsilon of it (in units of
+    distance; the returned t is parametric, so an unnormalised direction scales it); a ray through the centre lands on the
+    surface in one step; a ray that misses the sphere inside its box reports no hit."""
+    from jsraytracer_b200.jsmath import Vec
+    from jsraytracer_b200.materials import PhongMaterial
+    from jsraytracer_b200.sdf import SDFGeometry, SphereSDF
+    from jsraytracer_b200.world import Primitive
+    eps = 1e-5
+    prim = Primitive(SDFGeometry(SphereSDF(1), 300, eps, 100), PhongMaterial(Vec.of(1, 1, 1), 1))
+    sc = _scene([prim], [], 1)
+    pid, t = sc.cast((0, 0, 5), (0, 0, -1))
+    assert pid == 0 and abs(t - 4.0) <= eps
+    root = 5 - math.sqrt(1 - 0.25)
+    pid, t = sc.cast((0.5, 0, 5), (0, 0, -1))
+    assert pid == 0 and 0 <= root - t <= 3 * eps
+    pid, t2 = sc.cast((0.5, 0, 5), (0, 0, -2))                 # unnormalised direction: same point, half the parameter
+    assert pid == 0 and 0 <= root / 2 - t2 <= 3 * eps
+    pid, t = sc.cast((0.99, 0.99, 5), (0, 0, -1))              # inside the box's corner, outside the sphere
+    assert pid == -1 and t == INF
+    pid, t = sc.cast((0, 0, 5), (0, 0, -1), 0.0, 3.9)          # maxDistance in front of the surface
+    assert pid == -1
