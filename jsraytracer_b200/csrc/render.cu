@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
             const int slot = base_c + rank0;
             if (slot < next_cap) {
                 next.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
-                next.d[slot] = make_float4(dir0.x, dir0.y, dir0.z, __int_as_float((int)(2u * node)));
+                next.d[slot] = make_float4(dir0.x, dir0.y, dir0.z, __int_as_float((int)rng_child_node(node, 0u)));
                 next.w[slot] = make_float4(w0.x, w0.y, w0.z, __int_as_float(packed_next));
             } else *overflow = 1;
         }
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
             const int slot = base_c + rank1;
             if (slot < next_cap) {
                 next.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
-                next.d[slot] = make_float4(dir1.x, dir1.y, dir1.z, __int_as_float((int)(2u * node + 1u)));
+                next.d[slot] = make_float4(dir1.x, dir1.y, dir1.z, __int_as_float((int)rng_child_node(node, 1u)));
                 next.w[slot] = make_float4(w1.x, w1.y, w1.z, __int_as_float(packed_next));
             } else *overflow = 1;
         }

@@ -27,6 +27,12 @@ JSRT_HD uint32_t rng_sample_key(uint64_t seed, uint32_t pixel, uint32_t pass) {
     return k;
 }
 JSRT_HD uint32_t rng_node_key(uint32_t sample_key, uint32_t node) { return hash32(sample_key + 0x85ebca6bU * node); }
+// path-tree node id of child `which` (0 reflection, 1 transmission / refraction): 2k + which while that fits
+// (levels <= 30), a hash with the top bit set beyond (never 0 or 1, never back in the doubling range), so that
+// maxRecursionDepth up to 255 keeps distinct RNG keys and never re-creates the camera ray's id
+JSRT_HD uint32_t rng_child_node(uint32_t node, uint32_t which) {
+    return (node < 0x40000000U) ? 2U * node + which : (hash32(node ^ (0x9e3779b9U + which)) | 0x80000000U);
+}
 // U[0,1) with 24 bits: exactly representable in f32 and f64
 JSRT_HD float rng_u01(uint32_t node_key, uint32_t dim) {
     return (float)(hash32(node_key + 0xc2b2ae35U * (dim + 1)) >> 8) * (1.0f / 16777216.0f);

@@ -651,7 +651,7 @@ struct PositionalUVMaterial : Material {      // src/materials.js:178-193
 struct TransparentMaterial : Material {
     MaterialColor* c; double opacity;
     Vec color(MatData& d, World& world, int depth, uint32_t node, Ctx& ctx) override {
-        return c->color(d).times(opacity).plus(world.color(Ray(d.position, d.ray.direction), depth, 0.0001, 2 * node, ctx).times(1 - opacity));
+        return c->color(d).times(opacity).plus(world.color(Ray(d.position, d.ray.direction), depth, 0.0001, rng_child_node(node, 0), ctx).times(1 - opacity));
     }
 };
 
@@ -701,9 +701,9 @@ struct PhongMaterial : Material {
         getBaseFactors(d);
         Vec surfaceColor = colorFromLights(d, world, node, ctx);
         if (d.reflectivity.squarednorm() > 0)
-            surfaceColor = surfaceColor.plus(world.color(Ray(d.position, d.R), depth, 0.0001, 2 * node, ctx).mult_pairs(d.reflectivity));
+            surfaceColor = surfaceColor.plus(world.color(Ray(d.position, d.R), depth, 0.0001, rng_child_node(node, 0), ctx).mult_pairs(d.reflectivity));
         if (d.transmissivity.squarednorm() > 0)
-            surfaceColor = surfaceColor.plus(world.color(Ray(d.position, d.ray.direction.normalized()), depth, 0.0001, 2 * node + 1, ctx).mult_pairs(d.transmissivity));
+            surfaceColor = surfaceColor.plus(world.color(Ray(d.position, d.ray.direction.normalized()), depth, 0.0001, rng_child_node(node, 1), ctx).mult_pairs(d.transmissivity));
         return surfaceColor;
     }
 };
@@ -753,12 +753,12 @@ struct FresnelPhongMaterial : PhongMaterial {
         if (d.kr > 0) {
             Vec dir, col;
             if (scatter(&d.R, d.N, d, node, sb, ctx, dir, col))
-                surfaceColor = surfaceColor.plus(world.color(Ray(d.position, dir), depth, 0.0001, 2 * node, ctx).times(col).times(d.reflectivity).times(d.kr));
+                surfaceColor = surfaceColor.plus(world.color(Ray(d.position, dir), depth, 0.0001, rng_child_node(node, 0), ctx).times(col).times(d.reflectivity).times(d.kr));
         }
         if (d.kr < 1) {
             Vec dir, col;
             if (scatter(d.hasRefr ? &d.refractionDirection : nullptr, d.N.times(-1), d, node, sb + 4, ctx, dir, col))
-                surfaceColor = surfaceColor.plus(world.color(Ray(d.position, dir), depth, 0.0001, 2 * node + 1, ctx).times(col).times(d.transmissivity).times(1 - d.kr));
+                surfaceColor = surfaceColor.plus(world.color(Ray(d.position, dir), depth, 0.0001, rng_child_node(node, 1), ctx).times(col).times(d.transmissivity).times(1 - d.kr));
         }
         return surfaceColor;
     }
