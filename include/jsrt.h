@@ -44,13 +44,17 @@ typedef struct jsrt_scene jsrt_scene;
 /* Number of CUDA devices visible to the process (0 if none / no driver). */
 int jsrt_device_count(void);
 
-/* Replaces: worker.js:23-26 (each worker rebuilding the scene from test.mjs).
+/* Replaces: worker.js:23-26 (each worker rebuilding the scene from test.mjs) and the
+ * worker pool of src/raytrace_launcher.js:65-101.
  * Parses the serializer blob `{renderer:{world,camera,maxRecursionDepth
  * [,samplesPerPixel]},width,height}` (src/serializer.js:4-63), flattens it
  * (BVH nodes in reference visit order, triangle constants, material / light
- * tables, SDF bytecode) and uploads it to device `devices[0]`.  One process
- * drives one GPU (multi-GPU = one process per GPU, scene replicated, passes
- * sharded); ndev must be 1.  Returns NULL on failure. */
+ * tables, SDF bytecode) and uploads it to every device in `devices[0..ndev)`
+ * (NULL / 0 = device 0).  With ndev > 1 the scene is replicated, every
+ * jsrt_render call deals its passes to the devices in contiguous blocks, and
+ * jsrt_resolve_rgba8 / jsrt_read_accum sum the per-device accumulation buffers
+ * on devices[0] by reading the others over NVLink peer access inside the
+ * resolve kernel (the devices must be peers).  Returns NULL on failure. */
 jsrt_scene* jsrt_scene_create(const uint8_t* blob, size_t len, int format, const int* devices, int ndev);
 
 /* Parse + flatten only (no CUDA calls): lets hosts without a GPU validate a
@@ -99,6 +103,14 @@ int jsrt_read_accum(jsrt_scene*, float* out, int* passes);
  * ray origin (w).  variance = W*H*4 floats: xyz = the GL shader's running variance sums (divide by the sample count
  * like its display pass does), w = number of samples whose camera ray hit something.  Zero if no AOV pass was rendered. */
 int jsrt_read_aov(jsrt_scene*, float* normal_depth, float* variance);
+
+/* One process per GPU (torchrun-style launches): every process exports its accumulation buffer as a 64-byte CUDA
+ * IPC handle (jsrt_accum_export), the handles travel over the host's own channel, and the process that owns the image
+ * maps the others' buffers with jsrt_accum_attach(handles = n x 64 bytes); from then on its jsrt_resolve_rgba8 /
+ * jsrt_read_accum sum them like the helper devices of an ndev > 1 scene.  The caller orders the processes (a barrier
+ * after every process's jsrt_synchronize, before the owner resolves).  n = 0 detaches. */
+int jsrt_accum_export(jsrt_scene*, uint8_t* handle /* 64 bytes */);
+int jsrt_accum_attach(jsrt_scene*, const uint8_t* handles, int n);
 
 /* Device pointer of the W*H float4 accumulation buffer (for NCCL reductions
  * across GPUs issued by the host process). */

@@ -15,7 +15,10 @@ struct HostScene {
     Camera camera{};
     float bg[4] = {0, 0, 0, 0};
 
-    std::vector<Top> tops;
+    std::vector<Top> tops;              // flattened top-level entries in the reference's visit order (scene_flatten.cpp)
+    std::vector<int> top_world;         // parallel to tops: the entry of world.objects each one came from
+    int world_object_count = 0;
+    int n_staged = 0;                   // nodes[0, n_staged): the top levels of every tree (staged in shared memory by bvh_kernel)
     std::vector<Prim> prims;
     std::vector<Xform> xforms;          // xforms[0] is the identity
     std::vector<Xform64> xforms64;      // parallel to xforms

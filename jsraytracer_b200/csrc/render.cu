@@ -45,8 +45,11 @@ constexpr int kBlock = 256;
 #ifndef JSRT_SDF_SHADOW_MIN_BLOCKS
 #define JSRT_SDF_SHADOW_MIN_BLOCKS 3
 #endif
+#ifndef JSRT_BVH_BLOCK
+#define JSRT_BVH_BLOCK 1024        // threads per CTA of bvh_kernel (see there)
+#endif
 #ifndef JSRT_BVH_MIN_BLOCKS
-#define JSRT_BVH_MIN_BLOCKS 4      // 64 registers: 4 CTAs / SM (measured against 3 and 5: profiles/r1_ncu_summary.md)
+#define JSRT_BVH_MIN_BLOCKS 1      // x 1024 threads = 64 registers each, the same 32 warps per SM as round 1's 4 x 256
 #endif
 
 struct RayQueue { float4* o; float4* d; float4* w; };
@@ -67,66 +70,16 @@ __device__ __forceinline__ void flush_work(unsigned long long* stats, int cls, c
     }
 }
 
-struct GenParams {
-    Camera cam;
-    int width, height, x_offset, x_delt, ncols, npix_active;
-    int first_pass, jitter, max_depth, use_lens, count_samples;
-    unsigned long long seed;
-    long long first_sample;      // index of the batch's first sample within the call
-    int n_samples;               // samples in this batch
-};
-
 // ---------------------------------------------------------------------------------
-// generate: camera.getRayForPixel for sample s of the batch (src/cameras.js:29-34,46-52)
-// with the pixel / jitter arithmetic of src/renderers.js:89-96, all in f64 so the
-// primary ray is the reference's bit for bit.
-__device__ void camera_ray(const GenParams& g, int px, int py, uint32_t sample_key, bool jitter, bool use_lens, float3& o, float3& d) {
-    const uint32_t nk = rng_node_key(sample_key, 1);
-    double x = dsub(dmul(2.0, (double)px / (double)g.width), 1.0);
-    double y = dadd(dmul(-2.0, (double)py / (double)g.height), 1.0);
-    if (jitter) {
-        x = dadd(x, dmul(2.0 / (double)g.width, dsub((double)rng_u01(nk, DIM_JITTER_X), 0.5)));
-        y = dadd(y, dmul(2.0 / (double)g.height, dsub((double)rng_u01(nk, DIM_JITTER_Y), 0.5)));
-    }
-    const Camera& c = g.cam;
-    const float dx = (float)dmul(dmul(x, c.tan_fov), c.aspect), dy = (float)dmul(y, c.tan_fov), dz = -1.f;   // Vec.of(...) stores f32
-    const double* t = c.t;
-    // transform.times(direction): f64 dot of the f32 vector with each row, stored f32 (w = 0)
-    float3 dir = f3((float)ddot4(dx, dy, dz, 0.0, t[0], t[1], t[2], t[3]), (float)ddot4(dx, dy, dz, 0.0, t[4], t[5], t[6], t[7]),
-                    (float)ddot4(dx, dy, dz, 0.0, t[8], t[9], t[10], t[11]));
-    float3 org = f3((float)t[3], (float)t[7], (float)t[11]);       // transform.column(3)
-    if (c.dof && use_lens) {
-        // Vec.circlePick src/math.js:175-179, then DepthOfFieldPerspectiveCamera.getRayForPixel (src/cameras.js:46-52)
-        const double a = dmul(dmul((double)rng_u01(nk, DIM_LENS_A), 2.0), 3.141592653589793), r = sqrt((double)rng_u01(nk, DIM_LENS_R));
-        const float cx = (float)dmul(r, cos(a)), cy = (float)dmul(r, sin(a));
-        const float sx = (float)dmul(cx, c.sensor_size), sy = (float)dmul(cy, c.sensor_size);
-        const float3 off = f3((float)ddot4(sx, sy, 0.0, 0.0, t[0], t[1], t[2], t[3]), (float)ddot4(sx, sy, 0.0, 0.0, t[4], t[5], t[6], t[7]),
-                              (float)ddot4(sx, sy, 0.0, 0.0, t[8], t[9], t[10], t[11]));
-        org = f3((float)dadd(org.x, off.x), (float)dadd(org.y, off.y), (float)dadd(org.z, off.z));
-        const float fx = (float)dmul(dir.x, c.focus_distance), fy = (float)dmul(dir.y, c.focus_distance), fz = (float)dmul(dir.z, c.focus_distance);
-        const float mx = (float)dsub(fx, off.x), my = (float)dsub(fy, off.y), mz = (float)dsub(fz, off.z);
-        const double nn = sqrt(ddot4(mx, my, mz, 0.0, mx, my, mz, 0.0));
-        if (nn > 0.00001) { const double inv = 1.0 / nn; dir = f3((float)dmul(mx, inv), (float)dmul(my, inv), (float)dmul(mz, inv)); }
-        else dir = f3(mx, my, mz);
-    }
-    o = org; d = dir;
-}
-
-__global__ void __launch_bounds__(kBlock) generate_kernel(const __grid_constant__ GenParams g, RayQueue q, float4* __restrict__ accum) {
+// generate: the camera rays of a batch as a kernel of its own (jsrt_primary_hits, JSRT_FUSE_GEN=0); renders normally
+// let prims_kernel<extend, GEN> compute them (trace.cuh: generate_sample).
+__global__ void __launch_bounds__(kBlock) generate_kernel(const __grid_constant__ GenParams g) {
     const int stride = gridDim.x * blockDim.x;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < g.n_samples; s += stride) {
-        const long long gs = g.first_sample + s;
-        const int pass = g.first_pass + (int)(gs / g.npix_active);
-        const int idx = (int)(gs % g.npix_active);
-        const int py = idx / g.ncols, px = g.x_offset + (idx % g.ncols) * g.x_delt;
-        const uint32_t pixel = (uint32_t)(py * g.width + px);
-        const uint32_t key = rng_sample_key(g.seed, pixel, (uint32_t)pass);
-        float3 o, d;
-        camera_ray(g, px, py, key, g.jitter != 0, g.use_lens != 0, o, d);
-        q.o[s] = make_float4(o.x, o.y, o.z, __int_as_float((int)pixel));
-        q.d[s] = make_float4(d.x, d.y, d.z, __int_as_float(1));
-        q.w[s] = make_float4(1.f, 1.f, 1.f, __int_as_float((pass << 8) | g.max_depth));
-        if (g.count_samples) atomicAdd(&accum[pixel].w, 1.0f);      // samples taken for this pixel
+        float4 o4, d4, w4; uint32_t pixel;
+        generate_sample(g, s, o4, d4, w4, pixel);
+        g.qo[s] = o4; g.qd[s] = d4; g.qw[s] = w4;
+        if (g.count_samples) atomicAdd(&g.accum[pixel].w, 1.0f);      // samples taken for this pixel
     }
 }
 
@@ -140,10 +93,10 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(const __grid_constant_
 #ifndef JSRT_PRIMS_MIN_BLOCKS
 #define JSRT_PRIMS_MIN_BLOCKS 4
 #endif
-template <int MODE, bool COUNT, bool HAS_SDF>
-__global__ void __launch_bounds__(kBlock, (JSRT_PRIMS_MIN_BLOCKS > 0 && !HAS_SDF && !COUNT) ? JSRT_PRIMS_MIN_BLOCKS : 1) prims_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
+template <int MODE, bool COUNT, bool HAS_SDF, bool GEN>
+__global__ void __launch_bounds__(kBlock, (JSRT_PRIMS_MIN_BLOCKS > 0 && !HAS_SDF && !COUNT && !GEN) ? JSRT_PRIMS_MIN_BLOCKS : 1) prims_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io, const __grid_constant__ GenParams gen) {
     Work wp, ws;
-    prims_wave<MODE, COUNT, HAS_SDF>(sc, io, &wp, &ws);
+    prims_wave<MODE, COUNT, HAS_SDF, GEN>(sc, io, &gen, &wp, &ws);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
 template <int MODE, bool COUNT>
@@ -152,10 +105,19 @@ __global__ void __launch_bounds__(kBlock, MODE == TM_SHADOW ? JSRT_SDF_SHADOW_MI
     sdf_wave<MODE, COUNT>(sc, io, &wp, &ws);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
-template <int MODE, bool COUNT, bool HAS_SDF>
-__global__ void __launch_bounds__(kBlock, JSRT_BVH_MIN_BLOCKS) bvh_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
+// One big CTA per SM (JSRT_BVH_BLOCK threads = 64 registers each) so that the staged top levels of the trees exist once
+// per SM: up to 7 168 nodes = 224 KB of shared memory, 4 096 = 128 KB by default (the other half of the unified array
+// stays L1 for the deep nodes, the triangles and the ray records).
+extern __shared__ float4 s_staged_nodes[];
+template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT>
+__global__ void __launch_bounds__(JSRT_BVH_BLOCK, JSRT_BVH_MIN_BLOCKS) bvh_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
+    {
+        const float4* src = reinterpret_cast<const float4*>(sc.nodes);
+        for (int k = threadIdx.x; k < 2 * sc.n_staged; k += blockDim.x) s_staged_nodes[k] = __ldg(src + k);
+        __syncthreads();
+    }
     Work wp, ws;
-    bvh_wave<MODE, COUNT, HAS_SDF>(sc, io, &wp, &ws);
+    bvh_wave<MODE, COUNT, HAS_SDF, DIRECT>(sc, io, &wp, &ws, s_staged_nodes);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
 
@@ -167,15 +129,31 @@ __device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float3 
 // shade: World.color's miss / hit handling (src/world.js:31-41), Primitive.color
 // (:125-137), Material.color (src/materials.js).  Emits ambient, pushes shadow rays
 // and children.
-template <bool HAS_SDF, bool SORT>
-__global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ DeviceScene sc, RayQueue q, const int* __restrict__ count,
-                                                        const float4* __restrict__ hits, RayQueue next, int* next_count, int next_cap,
-                                                        ShadowQueue sq, int* shadow_count, int shadow_cap, float4* __restrict__ accum,
-                                                        unsigned long long seed, unsigned long long* stats, int* overflow, const float4* __restrict__ sdf_normals,
-                                                        int accum_stride, int pass0, float4* __restrict__ aov_nd, float4* __restrict__ aov_var) {
-    const int n = *count;
+struct ShadeIO {
+    RayQueue q; const int* count; const float4* hits;
+    RayQueue next; int* next_count; int next_cap;
+    ShadowQueue sq; int* shadow_count; int shadow_cap;
+    float4* accum;                      // radiance destination: the pixel sums, or the per-sample buffer (JSRT_FLAG_AOV), or the batch scratch
+    unsigned long long seed; unsigned long long* stats; int* overflow;
+    const float4* sdf_normals;
+    int accum_stride, pass0;
+    float4* aov_nd; float4* aov_var;
+};
+// FUSE (scenes without SDFs): the shadow ray of every light sample is tested here against everything that needs no
+// walk — the analytic shadow casters and the root boxes of the BVHAggregates (trace.cuh: analytic_hits,
+// first_bvh_hit).  An occluded sample is dropped, an unoccluded one that reaches no BVH is added to its pixel at once,
+// and only the walkers go to the shadow queue (with their first BVH), which bvh_kernel<shadow, DIRECT> consumes as its
+// work list.  Round 1 wrote all of them (64 B each) for prims_kernel<shadow> to read back and find that most need no walk
+// (bunny_path: 2/3 of the shadow rays; cornell_box_path: all of them — its shadow queue is never touched now).
+template <bool HAS_SDF, bool SORT, bool FUSE, bool COUNT>
+__global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ ShadeIO io) {
+    const RayQueue& q = io.q; const RayQueue& next = io.next; const ShadowQueue& sq = io.sq;
+    const float4* __restrict__ hits = io.hits;
+    float4* __restrict__ accum = io.accum;
+    const int n = *io.count;
     const int stride = gridDim.x * blockDim.x;
-    unsigned long long my_shaded = 0;
+    unsigned long long my_shaded = 0, my_shadow = 0;
+    Work ws;
     // Shading sorted by material (SORT): the kBlock rays of a tile are permuted inside the CTA by a counting sort on
     // (miss | material index) before they are shaded, so that a warp runs one material's code path instead of the
     // union of its 32 rays' paths.  The permutation stays inside a 4 KB window of each queue array, so the loads
@@ -222,7 +200,7 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
         }
         const bool active = i < n;
         bool hit = false;
-        uint32_t pixel = 0, node = 0; int depth_rem = 0, pass = 0;
+        uint32_t pixel = 0, node = 0, slot = 0; int depth_rem = 0, pass = 0;
         float3 o = f3(0, 0, 0), d = f3(0, 0, 1), thr = f3(0, 0, 0);
         SurfaceData s; s.position = f3(0, 0, 0); s.normal = f3(0, 0, 1); s.uv = make_float2(0, 0); s.has_uv = false; s.basecolor = f3(1, 1, 1);
         PhongFactors f;
@@ -233,7 +211,7 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
             o = f3(o4.x, o4.y, o4.z); d = f3(d4.x, d4.y, d4.z); thr = f3(w4.x, w4.y, w4.z);
             pixel = (uint32_t)__float_as_int(o4.w); node = (uint32_t)__float_as_int(d4.w);
             const int packed = __float_as_int(w4.w); depth_rem = packed & 0xff; pass = packed >> 8;
-            const uint32_t slot = pixel + (uint32_t)(pass - pass0) * (uint32_t)accum_stride;      // JSRT_FLAG_AOV: radiance slot of this sample (stride 0 otherwise)
+            slot = pixel + (uint32_t)(pass - io.pass0) * (uint32_t)io.accum_stride;      // JSRT_FLAG_AOV: radiance slot of this sample (stride 0 otherwise)
             const int prim = __float_as_int(h4.y), top = __float_as_int(h4.z);
             const float t = h4.x;
             if (prim < 0) {
@@ -268,16 +246,16 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
                     lp = ray_point_f64(lo, ld, td);
                 }
                 float3 ln; float4 sn = make_float4(0, 0, 0, 0);
-                if (HAS_SDF && sdf_normals && ta.x == T_SDF) sn = sdf_normals[i];
+                if (HAS_SDF && io.sdf_normals && ta.x == T_SDF) sn = io.sdf_normals[i];
                 material_data<HAS_SDF>(sc, pa.x, pa.y, flags, lp, ln, s.uv, s.has_uv, s.basecolor, &sn);
                 s.normal = normalized3(xf_normal(inv, ln));
                 s.position = ray_point_f64(o, d, td);
-                if (aov_nd && node == 1u) {
+                if (io.aov_nd && node == 1u) {
                     // first-hit AOVs of the GL path (gl/src/WebGLRendererAdapter.js:376-379: `initial_intersection_distance =
                     // length(r.o - intersect_position)`, `first_hit_normal.xyz = intersect_normal`), summed per pixel
                     const float3 e = s.position - o;
-                    accum_add3w(aov_nd, pixel, s.normal, sqrtf(dot3(e, e)));
-                    atomicAdd(&aov_var[pixel].w, 1.0f);
+                    accum_add3w(io.aov_nd, pixel, s.normal, sqrtf(dot3(e, e)));
+                    atomicAdd(&io.aov_var[pixel].w, 1.0f);
                 }
                 mat = sc.materials + pa.z;
                 if (mat->uv_from_position) {          // PositionalUVMaterial.color src/materials.js:188-192
@@ -285,7 +263,7 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
                     s.uv = make_float2((float)ddot3(mat->u_axis[0], mat->u_axis[1], mat->u_axis[2], dx, dy, dz), (float)ddot3(mat->v_axis[0], mat->v_axis[1], mat->v_axis[2], dx, dy, dz));
                     s.has_uv = true;
                 }
-                node_key = rng_node_key(rng_sample_key(seed, pixel, (uint32_t)pass), node);
+                node_key = rng_node_key(rng_sample_key(io.seed, pixel, (uint32_t)pass), node);
                 if (mat->kind == M_SOLID) {
                     accum_add(accum, slot, thr * color_eval(sc, mat->ambient, s));
                     hit = false;                 // no lights, no children (src/materials.js:153-155)
@@ -314,22 +292,44 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
                 if (f.kr < 1.f && scatter(*mat, f, f.has_refr, f.refr, f.N * -1.f, node_key, sb + 4, dir1, col)) { want1 = true; w1 = thr * (col * f.transmissivity * (1.f - f.kr)); }
             }
         }
-        // ---- queue space: ONE atomicAdd per warp per queue per iteration, issued here and consumed
-        // after the light-sample arithmetic below.  (One atomic per appended item made the return
+        // ---- queue space: ONE atomicAdd per warp per queue per iteration.  (One atomic per appended item made the return
         // latency of the contended counter 60 % of this kernel's stall samples: profiles/r1_ncu_summary.md.)
         const int lane = threadIdx.x & 31;
         const unsigned lit_mask = __ballot_sync(0xffffffffu, lit), m0 = __ballot_sync(0xffffffffu, want0), m1 = __ballot_sync(0xffffffffu, want1);
         const int n_lit = __popc(lit_mask), n0 = __popc(m0), n1 = __popc(m1);
         int base_s = 0, base_c = 0;
         if (lane == 0) {
-            if (n_lit) base_s = atomicAdd(shadow_count, n_lit * sc.light_samples);
-            if (n0 + n1) base_c = atomicAdd(next_count, n0 + n1);
+            if (!FUSE && n_lit) base_s = atomicAdd(io.shadow_count, n_lit * sc.light_samples);
+            if (n0 + n1) base_c = atomicAdd(io.next_count, n0 + n1);
         }
         const unsigned lt = (1u << lane) - 1u;
         const int rank_s = __popc(lit_mask & lt), rank0 = __popc(m0 & lt), rank1 = n0 + __popc(m1 & lt);
+        const int packed_next = (pass << 8) | (depth_rem - 1);
+        auto write_children = [&]() {
+            base_c = __shfl_sync(0xffffffffu, base_c, 0);
+            if (want0) {
+                const int cs = base_c + rank0;
+                if (cs < io.next_cap) {
+                    next.o[cs] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
+                    next.d[cs] = make_float4(dir0.x, dir0.y, dir0.z, __int_as_float((int)rng_child_node(node, 0u)));
+                    next.w[cs] = make_float4(w0.x, w0.y, w0.z, __int_as_float(packed_next));
+                } else *io.overflow = 1;
+            }
+            if (want1) {
+                const int cs = base_c + rank1;
+                if (cs < io.next_cap) {
+                    next.o[cs] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
+                    next.d[cs] = make_float4(dir1.x, dir1.y, dir1.z, __int_as_float((int)rng_child_node(node, 1u)));
+                    next.w[cs] = make_float4(w1.x, w1.y, w1.z, __int_as_float(packed_next));
+                } else *io.overflow = 1;
+            }
+        };
+        // FUSE: the children leave before the light loop (their twelve values would otherwise stay live across the
+        // intersection tests); otherwise after it, so that the counter's return latency hides behind the light arithmetic
+        if (FUSE) write_children();
+        if (lit) my_shadow += (unsigned long long)sc.light_samples;
 
-        // ---- shadow rays: one per light sample (src/materials.js:244-257); sample j of the warp's lit
-        // lanes occupies slots [base_s + j * n_lit, base_s + (j + 1) * n_lit): coalesced per sample
+        // ---- shadow rays: one per light sample (src/materials.js:244-257)
         uint32_t dim = DIM_LIGHTS;
         int j = 0;
         bool have_base = false;
@@ -337,44 +337,60 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
             const Light& L = sc.lights[li];
             const int ns = L.samples;
             for (int k = 0; k < ns; ++k, dim += 2, ++j) {
-                LightSample ls; float3 contrib = f3(0, 0, 0);
+                LightSample ls; ls.direction = f3(0, 0, 1); float3 contrib = f3(0, 0, 0);
                 if (lit) {
                     ls = light_sample(L, s.position, rng_u01(node_key, dim), rng_u01(node_key, dim + 1));
                     contrib = thr * (color_from_light_sample(*mat, f, ls) * (1.0f / (float)ns));
                 }
-                if (!have_base) { base_s = __shfl_sync(0xffffffffu, base_s, 0); have_base = true; }
-                if (lit) {
-                    const int slot = base_s + j * n_lit + rank_s;
-                    if (slot < shadow_cap) {
-                        sq.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
-                        sq.d[slot] = make_float4(ls.direction.x, ls.direction.y, ls.direction.z, __int_as_float(pass));
-                        sq.c[slot] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
-                    } else *overflow = 1;
+                if (FUSE) {
+                    // world.cast(new Ray(position, direction), 0.0001, 1, false) as far as it goes without a walk
+                    int fb = -1; bool walker = false;
+                    if (lit) {
+                        Hit sb; sb.t = CUDART_INF_F; sb.prim = -1; sb.top = -1; sb.t_lo = 0.f;
+                        analytic_hits<true, COUNT, false>(sc, s.position, ls.direction, 0.0001f, 1.0f, lit_mask, sb, &ws);
+                        if (sb.prim < 0) {
+                            LocalRay lr;
+                            fb = first_bvh_hit<COUNT>(sc, s.position, ls.direction, 0.0001f, 1.0f, CUDART_INF_F, &ws, lr);
+                            if (fb < 0) accum_add(accum, slot, contrib);       // unoccluded: the light sample counts (src/materials.js:251-253)
+                            else walker = true;
+                        }
+                    }
+                    const unsigned wm = __ballot_sync(0xffffffffu, walker);
+                    if (wm) {
+                        const int leader = __ffs(wm) - 1;
+                        int base = 0;
+                        if (lane == leader) base = atomicAdd(io.shadow_count, __popc(wm));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (walker) {
+                            const int e = base + __popc(wm & lt);
+                            if (e < io.shadow_cap) {
+                                sq.o[e] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
+                                sq.d[e] = make_float4(ls.direction.x, ls.direction.y, ls.direction.z, __int_as_float(pass));
+                                sq.c[e] = make_float4(contrib.x, contrib.y, contrib.z, __int_as_float(fb));
+                            } else *io.overflow = 1;
+                        }
+                    }
+                } else {
+                    // sample j of the warp's lit lanes occupies slots [base_s + j * n_lit, base_s + (j + 1) * n_lit): coalesced per sample
+                    if (!have_base) { base_s = __shfl_sync(0xffffffffu, base_s, 0); have_base = true; }
+                    if (lit) {
+                        const int e = base_s + j * n_lit + rank_s;
+                        if (e < io.shadow_cap) {
+                            sq.o[e] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
+                            sq.d[e] = make_float4(ls.direction.x, ls.direction.y, ls.direction.z, __int_as_float(pass));
+                            sq.c[e] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                        } else *io.overflow = 1;
+                    }
                 }
             }
         }
-        base_c = __shfl_sync(0xffffffffu, base_c, 0);
-        const int packed_next = (pass << 8) | (depth_rem - 1);
-        if (want0) {
-            const int slot = base_c + rank0;
-            if (slot < next_cap) {
-                next.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
-                next.d[slot] = make_float4(dir0.x, dir0.y, dir0.z, __int_as_float((int)rng_child_node(node, 0u)));
-                next.w[slot] = make_float4(w0.x, w0.y, w0.z, __int_as_float(packed_next));
-            } else *overflow = 1;
-        }
-        if (want1) {
-            const int slot = base_c + rank1;
-            if (slot < next_cap) {
-                next.o[slot] = make_float4(s.position.x, s.position.y, s.position.z, __int_as_float((int)pixel));
-                next.d[slot] = make_float4(dir1.x, dir1.y, dir1.z, __int_as_float((int)rng_child_node(node, 1u)));
-                next.w[slot] = make_float4(w1.x, w1.y, w1.z, __int_as_float(packed_next));
-            } else *overflow = 1;
-        }
+        if (!FUSE) write_children();
     }
-    // per-warp reduction of the shaded-hit count, one atomic per warp
-    for (int off = 16; off; off >>= 1) my_shaded += __shfl_down_sync(0xffffffffu, my_shaded, off);
-    if ((threadIdx.x & 31) == 0 && my_shaded) atomicAdd(stats + ST_SHADED, my_shaded);
+    // per-warp reduction of the shaded-hit / shadow-ray counts, one atomic per warp
+    for (int off = 16; off; off >>= 1) { my_shaded += __shfl_down_sync(0xffffffffu, my_shaded, off); my_shadow += __shfl_down_sync(0xffffffffu, my_shadow, off); }
+    if ((threadIdx.x & 31) == 0 && my_shaded) atomicAdd(io.stats + ST_SHADED, my_shaded);
+    if (FUSE && (threadIdx.x & 31) == 0 && my_shadow) atomicAdd(io.stats + ST_SHADOW, my_shadow);
+    if (FUSE && COUNT) flush_work(io.stats, 2, ws);
 }
 
 // JSRT_FLAG_AOV: the batch's per-sample radiance -> pixel sums + running variance, one thread per pixel, samples of a
@@ -413,9 +429,10 @@ __global__ void __launch_bounds__(kBlock) fold_samples_kernel(const __grid_const
 }
 
 // bookkeeping between levels: fold queue sizes into the ray statistics and recycle the counters
-__global__ void level_end_kernel(Counters* c, int cur, int level, int next_cap, int shadow_cap) {
+// (fused: shade_kernel<FUSE> has counted the shadow rays itself — the queue only holds the walkers)
+__global__ void level_end_kernel(Counters* c, int cur, int level, int next_cap, int shadow_cap, int fused) {
     c->stats[level == 0 ? ST_PRIMARY : ST_SECONDARY] += (unsigned long long)c->ray[cur];
-    c->stats[ST_SHADOW] += (unsigned long long)min(c->shadow, shadow_cap);
+    if (!fused) c->stats[ST_SHADOW] += (unsigned long long)min(c->shadow, shadow_cap);
     c->ray[cur] = 0;
     c->shadow = 0;
     c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0; c->list_extend = 0; c->list_shadow = 0; c->ties = 0;
@@ -426,11 +443,22 @@ __global__ void set_count_kernel(Counters* c, int which, int n, int count_sample
     if (count_samples) c->stats[ST_SAMPLES] += (unsigned long long)n;
 }
 
+// Accumulation buffers of the other GPUs that render passes of the same frame (jsrt_scene_create with ndev > 1:
+// peer pointers of this process; jsrt_accum_attach: CUDA IPC mappings of other processes' buffers).  The kernels below
+// read them straight over NVLink: the cross-GPU sum is fused into the resolve / read-back, there is no staging copy
+// and no separate reduction pass.  Replaces the compositing of src/raytrace_launcher.js:92-97.
+constexpr int kMaxPeers = 15;
+struct PeerAccum { const float4* p[kMaxPeers]; int n; };
+__device__ __forceinline__ float4 summed_pixel(const float4* __restrict__ accum, const PeerAccum& peers, int i) {
+    float4 a = accum[i];
+    for (int k = 0; k < peers.n; ++k) { const float4 b = __ldcs(peers.p[k] + i); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    return a;
+}
 // PixelBuffer.setColor on buffer.times(1/(iter+1)) (src/renderers.js:98, src/pixelbuffer.js:39-49)
-__global__ void resolve_kernel(const float4* __restrict__ accum, uchar4* __restrict__ out, int npix) {
+__global__ void resolve_kernel(const float4* __restrict__ accum, const __grid_constant__ PeerAccum peers, uchar4* __restrict__ out, int npix) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
-    const float4 a = accum[i];
+    const float4 a = summed_pixel(accum, peers, i);
     if (!(a.w > 0.f)) { out[i] = make_uchar4(0, 0, 0, 0); return; }
     const double inv = 1.0 / (double)a.w;
     float c[3] = {(float)((double)a.x * inv), (float)((double)a.y * inv), (float)((double)a.z * inv)};
@@ -441,6 +469,17 @@ __global__ void resolve_kernel(const float4* __restrict__ accum, uchar4* __restr
         r[k] = (unsigned char)floor(255.0 * comp + 0.5);      // Math.round
     }
     out[i] = make_uchar4(r[0], r[1], r[2], 255);
+}
+__global__ void sum_peers_kernel(const float4* __restrict__ accum, const __grid_constant__ PeerAccum peers, float4* __restrict__ out, int npix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npix) out[i] = summed_pixel(accum, peers, i);
+}
+// optimistic queue sizing: a batch that did not overflow is folded from its scratch buffer into the pixel sums
+__global__ void add_scratch_kernel(float4* __restrict__ accum, float4* __restrict__ scratch, int npix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const float4 b = scratch[i];
+    if (b.x != 0.f || b.y != 0.f || b.z != 0.f || b.w != 0.f) { float4 a = accum[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; accum[i] = a; }
 }
 
 // parity probe: hits of the un-jittered pinhole primary rays -> (prim_id, t)
@@ -456,6 +495,7 @@ __global__ void hits_to_ids_kernel(const __grid_constant__ DeviceScene sc, const
 
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) throw std::runtime_error(std::string("jsrt: CUDA error: ") + cudaGetErrorString(e__) + " at " #call); } while (0)
 
+int envInt(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
 }  // namespace
 
@@ -467,6 +507,7 @@ struct Renderer::Impl {
     DeviceScene ds{};
     std::vector<void*> allocs;
     float4* accum = nullptr;
+    float4* scratch = nullptr;          // W x H float4: radiance of the batch in flight (optimistic sizing) / peer sums (readAccum)
     RayQueue rq[2]{}; float4* hits = nullptr; float4* shadow_hits = nullptr; ShadowQueue sq{};
     float4* sdf_normals = nullptr;
     // JSRT_FLAG_AOV (allocated on first use): first-hit normal / distance sums, variance sums (w: first hits), and the
@@ -475,19 +516,23 @@ struct Renderer::Impl {
     int sample_span = 0;
     int4* tie_list = nullptr;           // FP32 near-ties between triangles reported by bvh_kernel<extend> (trace.cuh: tie_wave)
     static constexpr int kTieCap = 1 << 20;
-    int2* work_list = nullptr;          // BVH work list (trace.cuh), shared by the extend and the shadow wave of a level
-    float4* walker_rec[3] = {nullptr, nullptr, nullptr};   // JSRT_WALKER_RECORDS: the same list as 48-byte walker records (SoA)
+    int2* work_list = nullptr;          // BVH work list (trace.cuh): extend wave; shadow wave too unless the shadow tests are fused into shade
     Counters* counters = nullptr;
+    unsigned long long* stats_backup = nullptr;
     int* overflow = nullptr;
     int ray_cap = 0, shadow_cap = 0, batch = 0;
+    bool optimistic = false;            // queues sized for an expected, not the worst, fan-out: every batch is checked and re-run smaller on overflow
     int passes = 0;
     size_t scene_bytes = 0, queue_bytes = 0;
-    int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0, grid_bvh = 0, grid_sdf[2] = {0, 0};
+    int grid_extend = 0, grid_extend_gen = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0, grid_bvh = 0, grid_sdf[2] = {0, 0};
+    size_t bvh_smem = 0;
     unsigned long long launches = 0;
-    bool profiling = false, has_sdf = false, sort_shade = false;
+    bool profiling = false, has_sdf = false, sort_shade = false, fuse_shadow = false, fuse_gen = true;
     double ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};     // 0-3: kernel classes; 4-9: prims / bvh / sdf kernels of extend, shadow
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uchar4* rgba = nullptr; int* hit_ids = nullptr; float* hit_t = nullptr;
+    PeerAccum peers{};                  // other GPUs' accumulation buffers (summed by resolve / readAccum)
+    std::vector<void*> ipc_mapped;
 
     explicit Impl(const HostScene& h) : hs(h) {}
 
@@ -502,6 +547,7 @@ struct Renderer::Impl {
         ds.lights = up(hs.lights); ds.sdfs = up(hs.sdfs); ds.sdf_code = up(hs.sdf_code);
         ds.textures = up(hs.textures); ds.texels = up(hs.texels);
         ds.bvh_tops = up(bvh_tops_host); ds.n_bvh = (int)bvh_tops_host.size();
+        ds.n_staged = std::min<int>(hs.n_staged, (int)hs.nodes.size());
         // padded world-space box of every BVHAggregate (scene_flatten.cpp: computeWorldBoxes; trace.cuh: wbox_hit)
         {
             std::vector<float> wb;
@@ -513,7 +559,7 @@ struct Renderer::Impl {
             }
         }
         ds.wboxes = up(wboxes_host);
-        { const char* e = getenv("JSRT_WBOX"); ds.use_wbox = e ? atoi(e) : (ds.n_bvh >= 2 ? 1 : 0); }
+        ds.use_wbox = envInt("JSRT_WBOX", ds.n_bvh >= 2 ? 1 : 0);
         sdf_tops_host.clear();
         for (size_t i = 0; i < hs.tops.size(); ++i) if (hs.tops[i].kind == T_SDF) sdf_tops_host.push_back((int)i);
         ds.sdf_tops = up(sdf_tops_host); ds.n_sdf_tops = (int)sdf_tops_host.size();
@@ -561,70 +607,88 @@ struct Renderer::Impl {
         CK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
         stream = own_stream;
         uploadScene();
+        has_sdf = !hs.sdfs.empty();
+        // shadow tests fused into shade_kernel (scenes without SDFs: an SDF march cannot run inside the shade loop)
+        fuse_shadow = !has_sdf && envInt("JSRT_FUSE_SHADOW", 1) != 0;
+        fuse_gen = envInt("JSRT_FUSE_GEN", 1) != 0;
         const size_t npix = (size_t)hs.width * hs.height;
         accum = dalloc<float4>(npix);
         CK(cudaMemsetAsync(accum, 0, npix * sizeof(float4), stream));
         rgba = dalloc<uchar4>(npix); hit_ids = dalloc<int>(npix); hit_t = dalloc<float>(npix);
-        counters = dalloc<Counters>(1); overflow = dalloc<int>(1);
+        counters = dalloc<Counters>(1); overflow = dalloc<int>(1); stats_backup = dalloc<unsigned long long>(24);
         CK(cudaMemsetAsync(counters, 0, sizeof(Counters), stream));
         CK(cudaMemsetAsync(overflow, 0, sizeof(int), stream));
 
-        // Queue sizing: a camera sample owns at most fanout^L rays at level L and
-        // light_samples shadow rays per ray, so the worst case over the levels is at
-        // the deepest one.  The batch (camera samples in flight) is the largest that
-        // fits the budget; whole frames fit for every BASELINE config but the
-        // depth-8 Cornell box, which runs in sub-frame batches.
-        double worst = 1; for (int l = 1; l < hs.max_depth; ++l) worst *= hs.fanout;
-        if (worst > 1e6) worst = 1e6;
-        const double list_bytes = (JSRT_WALKER_RECORDS && !bvh_tops_host.empty()) ? 48.0 : (JSRT_WALKER_RECORDS ? 0.0 : 8.0);   // work-list entry per (shadow) ray
-        const double per_sample = worst * (2.0 * 48 + 16 + (hs.sdfs.empty() ? 0 : 16) + (64.0 + list_bytes) * std::max(1, hs.light_samples));
-        double b = (double)queue_budget / per_sample;
+        // Queue sizing.  A camera sample owns at most fanout^L rays at level L and light_samples shadow rays per ray, so
+        // the worst case over the levels is at the deepest one.  When a useful batch fits the budget at that worst case
+        // (every BASELINE config), overflow is impossible by construction and nothing is checked while rendering.
+        // Otherwise (fan-out 2 beyond depth ~13: 2^12 rays per sample) the queues are sized for an expected fan-out
+        // (JSRT_QUEUE_GROWTH, default 4 rays per camera sample at the widest level — most paths die early, which is why the
+        // reference can render such scenes at all) and every batch renders into a scratch buffer that is only folded into
+        // the pixel sums if the overflow flag stayed clear; an overflowing batch is re-run with half the samples.
+        const int ls = std::max(1, hs.light_samples);
+        double worst = 1; for (int l = 1; l < hs.max_depth; ++l) { worst *= hs.fanout; if (worst > 1e12) break; }
+        const double ray_bytes = 2.0 * 48 + 16 + (has_sdf ? 16 : 0) + 8;                           // two queues, hit record, (SDF normal), work-list entry
+        const double shadow_bytes = fuse_shadow ? 48.0 : 48.0 + 16 + 8;                            // queue (+ partial hit, work-list entry)
+        const double per_ray = ray_bytes + shadow_bytes * ls;
         // up to 16 passes per wave (JSRT_BATCH_PASSES overrides): the persistent trace kernels end with a tail of
         // long walks, so bigger waves are faster (bunny_path 1080p: 2.75 / 3.47 / 3.78 / 3.90 Grays/s at 1 / 3.2 / 8 / 16 passes)
         double batch_passes = 16;
         if (const char* e = getenv("JSRT_BATCH_PASSES")) { const double v = atof(e); if (v >= 0.01) batch_passes = v; }
-        const double want = (double)npix * batch_passes;
-        if (b > want) b = want;
-        if (b < 65536) b = 65536;
-        batch = (int)b;
-        ray_cap = (int)std::min<double>((double)batch * worst, 2.0e9);
-        shadow_cap = (int)std::min<double>((double)ray_cap * std::max(1, hs.light_samples), 2.0e9);
+        const double want = std::max(1.0, (double)npix * batch_passes);
+        const double min_batch = std::min(want, 65536.0);
+        double growth = worst;
+        double b = (double)queue_budget / (per_ray * worst);
+        if (const char* e = getenv("JSRT_QUEUE_GROWTH")) { const double v = atof(e); if (v >= 1.0 && v < worst) { growth = v; optimistic = true; b = (double)queue_budget / (per_ray * growth); } }
+        if (!optimistic && b < min_batch) {
+            optimistic = true; growth = std::min(worst, 4.0);
+            b = (double)queue_budget / (per_ray * growth);
+        }
+        b = std::min(std::max(b, min_batch), want);
+        // (the floor can exceed a tiny budget: the budget is a target, 65 536 samples in flight are the minimum that keeps 148 SMs busy)
+        if (b * growth > 1.0e9) b = 1.0e9 / growth;
+        batch = std::max(1, (int)b);
+        ray_cap = (int)std::min<double>(std::ceil((double)batch * growth), 2.0e9);
+        shadow_cap = (int)std::min<double>((double)ray_cap * ls, 2.0e9);
         for (int k = 0; k < 2; ++k) { rq[k].o = dalloc<float4>(ray_cap); rq[k].d = dalloc<float4>(ray_cap); rq[k].w = dalloc<float4>(ray_cap); }
         hits = dalloc<float4>(ray_cap);
         sq.o = dalloc<float4>(shadow_cap); sq.d = dalloc<float4>(shadow_cap); sq.c = dalloc<float4>(shadow_cap);
-        shadow_hits = dalloc<float4>(shadow_cap);
-#if JSRT_WALKER_RECORDS
-        if (!bvh_tops_host.empty()) for (auto& p : walker_rec) p = dalloc<float4>(std::max(ray_cap, shadow_cap));
-        work_list = dalloc<int2>(1);
-#else
-        work_list = dalloc<int2>(std::max(ray_cap, shadow_cap));
-#endif
+        if (!fuse_shadow) shadow_hits = dalloc<float4>(shadow_cap);
+        work_list = dalloc<int2>(fuse_shadow ? ray_cap : std::max(ray_cap, shadow_cap));
         tie_list = dalloc<int4>(bvh_tops_host.empty() ? 1 : kTieCap);
-        if (!hs.sdfs.empty()) { sdf_normals = dalloc<float4>(ray_cap); CK(cudaMemsetAsync(sdf_normals, 0, (size_t)ray_cap * sizeof(float4), stream)); }
-        queue_bytes = (size_t)ray_cap * (2 * 48 + 16) + (size_t)shadow_cap * (48 + 16) + (size_t)((double)std::max(ray_cap, shadow_cap) * list_bytes);
+        if (has_sdf) { sdf_normals = dalloc<float4>(ray_cap); CK(cudaMemsetAsync(sdf_normals, 0, (size_t)ray_cap * sizeof(float4), stream)); }
+        if (optimistic) { scratch = dalloc<float4>(npix); CK(cudaMemsetAsync(scratch, 0, npix * sizeof(float4), stream)); }
+        queue_bytes = (size_t)((double)ray_cap * ray_bytes + (double)shadow_cap * shadow_bytes);
 
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
-        auto grid_for = [&](const void* fn) { int per = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, kBlock, 0)); return prop.multiProcessorCount * std::max(1, per); };
-        has_sdf = !hs.sdfs.empty();
-        grid_extend = has_sdf ? grid_for((const void*)prims_kernel<TM_EXTEND, false, true>) : grid_for((const void*)prims_kernel<TM_EXTEND, false, false>);
-        grid_bvh = has_sdf ? grid_for((const void*)bvh_kernel<TM_EXTEND, false, true>) : grid_for((const void*)bvh_kernel<TM_EXTEND, false, false>);
+        auto grid_for = [&](const void* fn, int block = kBlock, size_t smem = 0) {
+            int per = 1; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, block, smem)); return prop.multiProcessorCount * std::max(1, per);
+        };
+        grid_extend = has_sdf ? grid_for((const void*)prims_kernel<TM_EXTEND, false, true, false>) : grid_for((const void*)prims_kernel<TM_EXTEND, false, false, false>);
+        grid_extend_gen = has_sdf ? grid_for((const void*)prims_kernel<TM_EXTEND, false, true, true>) : grid_for((const void*)prims_kernel<TM_EXTEND, false, false, true>);
+        // bvh_kernel: dynamic shared memory for the staged top levels (opt-in above 48 KB)
+        bvh_smem = (size_t)ds.n_staged * sizeof(BvhNode);
+        if ((int)bvh_smem > prop.sharedMemPerBlockOptin) throw std::runtime_error("jsrt: staged BVH block exceeds the shared memory of an SM (lower JSRT_STAGE_NODES)");
+        #define JSRT_BVH_ATTR(...) CK(cudaFuncSetAttribute((const void*)bvh_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bvh_smem))
+        if (has_sdf) { JSRT_BVH_ATTR(TM_EXTEND, false, true, false); JSRT_BVH_ATTR(TM_EXTEND, true, true, false); JSRT_BVH_ATTR(TM_SHADOW, false, true, false); JSRT_BVH_ATTR(TM_SHADOW, true, true, false); }
+        else { JSRT_BVH_ATTR(TM_EXTEND, false, false, false); JSRT_BVH_ATTR(TM_EXTEND, true, false, false); JSRT_BVH_ATTR(TM_SHADOW, false, false, false); JSRT_BVH_ATTR(TM_SHADOW, true, false, false);
+               JSRT_BVH_ATTR(TM_SHADOW, false, false, true); JSRT_BVH_ATTR(TM_SHADOW, true, false, true); }
+        #undef JSRT_BVH_ATTR
+        grid_bvh = has_sdf ? grid_for((const void*)bvh_kernel<TM_EXTEND, false, true, false>, JSRT_BVH_BLOCK, bvh_smem)
+                           : grid_for((const void*)bvh_kernel<TM_EXTEND, false, false, false>, JSRT_BVH_BLOCK, bvh_smem);
         // material-sorted shading: on for scenes made of analytic primitives only (see shade_kernel)
         sort_shade = bvh_tops_host.empty();
         if (const char* e = getenv("JSRT_SHADE_SORT")) sort_shade = atoi(e) != 0;
-        grid_shade = has_sdf ? (sort_shade ? grid_for((const void*)shade_kernel<true, true>) : grid_for((const void*)shade_kernel<true, false>))
-                             : (sort_shade ? grid_for((const void*)shade_kernel<false, true>) : grid_for((const void*)shade_kernel<false, false>));
-        grid_shadow = has_sdf ? grid_for((const void*)prims_kernel<TM_SHADOW, false, true>) : grid_for((const void*)prims_kernel<TM_SHADOW, false, false>);
+        grid_shade = has_sdf ? (sort_shade ? grid_for((const void*)shade_kernel<true, true, false, false>) : grid_for((const void*)shade_kernel<true, false, false, false>))
+                   : fuse_shadow ? (sort_shade ? grid_for((const void*)shade_kernel<false, true, true, false>) : grid_for((const void*)shade_kernel<false, false, true, false>))
+                                 : (sort_shade ? grid_for((const void*)shade_kernel<false, true, false, false>) : grid_for((const void*)shade_kernel<false, false, false, false>));
+        grid_shadow = has_sdf ? grid_for((const void*)prims_kernel<TM_SHADOW, false, true, false>) : grid_for((const void*)prims_kernel<TM_SHADOW, false, false, false>);
         grid_gen = grid_for((const void*)generate_kernel);
         grid_sdf[TM_EXTEND] = grid_for((const void*)sdf_kernel<TM_EXTEND, false>);
         grid_sdf[TM_SHADOW] = grid_for((const void*)sdf_kernel<TM_SHADOW, false>);
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
         CK(cudaStreamSynchronize(stream));
         setupAccumPersistence(prop);
-        if (getenv("JSRT_DEBUG_PTRS"))
-            fprintf(stderr, "jsrt ptrs: tops %p prims %p xforms %p nodes %p tris %p tri_shade %p materials %p lights %p bvh_tops %p accum %p counters %p rq0 %p %p %p rq1 %p %p %p hits %p sq %p %p %p shits %p list %p\n",
-                    (void*)ds.tops, (void*)ds.prims, (void*)ds.xforms, (void*)ds.nodes, (void*)ds.tris, (void*)ds.tri_shade, (void*)ds.materials, (void*)ds.lights, (void*)ds.bvh_tops,
-                    (void*)accum, (void*)counters, (void*)rq[0].o, (void*)rq[0].d, (void*)rq[0].w, (void*)rq[1].o, (void*)rq[1].d, (void*)rq[1].w, (void*)hits, (void*)sq.o, (void*)sq.d, (void*)sq.c,
-                    (void*)shadow_hits, (void*)work_list);
     }
 
     // Every radiance term is added to its pixel with an FP32 reduction (RED) in L2.  Between two touches of one
@@ -634,12 +698,12 @@ struct Renderer::Impl {
     // the persisting part of L2 (cudaAccessPolicyWindow); the queues stay on the normal (streaming) policy.
     bool accum_persist = false;
     void setupAccumPersistence(const cudaDeviceProp& prop) {
-        if (const char* e = getenv("JSRT_ACCUM_PERSIST")) { if (atoi(e) == 0) return; }
+        if (envInt("JSRT_ACCUM_PERSIST", 1) == 0) return;
         const size_t bytes = (size_t)hs.width * hs.height * sizeof(float4);
         if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
         const size_t carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes);
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
-        l2_window.base_ptr = accum;
+        l2_window.base_ptr = optimistic ? scratch : accum;
         l2_window.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
         l2_window.hitRatio = (float)std::min(1.0, (double)carve / (double)l2_window.num_bytes);
         l2_window.hitProp = cudaAccessPropertyPersisting;
@@ -657,6 +721,7 @@ struct Renderer::Impl {
     ~Impl() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
+        for (void* p : ipc_mapped) cudaIpcCloseMemHandle(p);
         for (void* p : allocs) cudaFree(p);
         for (void* p : scene_allocs) cudaFree(p);
         for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -700,24 +765,39 @@ struct Renderer::Impl {
         if (profiling) { CK(cudaEventRecord(p.b, stream)); pending.push_back(p); if (pending.size() >= 8192) flushEvents(); }
     }
 
-    template <int MODE> void launchTrace(const TraceIO& io0, bool count_work, int grid_prims) {
+    // One trace wave: prims_kernel (analytic primitives + root boxes; `gen`: level 0, camera rays computed in place),
+    // bvh_kernel over the work list, tie_kernel, sdf_kernel.  `direct`: the fused shadow wave — the queue holds walkers
+    // only, so just bvh_kernel<shadow, DIRECT>.
+    template <int MODE> void launchTrace(const TraceIO& io0, bool count_work, int grid_prims, const GenParams* gen, bool direct) {
         TraceIO io = io0;
         const bool has_bvh = ds.n_bvh > 0, has_sdf_tops = ds.n_sdf_tops > 0;
         io.final_pass = has_sdf_tops ? 0 : 1;        // prims_wave finishes the rays that need no BVH walk unless an SDF march follows
-        #define JSRT_LAUNCH(K, G, C, S) K<MODE, C, S><<<G, kBlock, 0, stream>>>(ds, io)
+        static const GenParams no_gen{};
+        const GenParams& gp = gen ? *gen : no_gen;
         // profiling: the three kernels of a trace wave are also timed one by one (ms[4..9])
         const int part0 = 4 + 3 * MODE;
         cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr}; int np = 0;
         auto mark = [&] { if (profiling) { pe[np] = getEvent(); CK(cudaEventRecord(pe[np], stream)); ++np; } };
         mark();
-        if (count_work) { if (has_sdf) JSRT_LAUNCH(prims_kernel, grid_prims, true, true); else JSRT_LAUNCH(prims_kernel, grid_prims, true, false); }
-        else { if (has_sdf) JSRT_LAUNCH(prims_kernel, grid_prims, false, true); else JSRT_LAUNCH(prims_kernel, grid_prims, false, false); }
+        if (!direct) {
+            #define JSRT_PRIMS(C, S, G) prims_kernel<MODE, C, S, G><<<grid_prims, kBlock, 0, stream>>>(ds, io, gp)
+            if (gen && MODE == TM_EXTEND) {
+                if (count_work) { if (has_sdf) JSRT_PRIMS(true, true, (MODE == TM_EXTEND)); else JSRT_PRIMS(true, false, (MODE == TM_EXTEND)); }
+                else { if (has_sdf) JSRT_PRIMS(false, true, (MODE == TM_EXTEND)); else JSRT_PRIMS(false, false, (MODE == TM_EXTEND)); }
+            } else {
+                if (count_work) { if (has_sdf) JSRT_PRIMS(true, true, false); else JSRT_PRIMS(true, false, false); }
+                else { if (has_sdf) JSRT_PRIMS(false, true, false); else JSRT_PRIMS(false, false, false); }
+            }
+            #undef JSRT_PRIMS
+        }
         mark();
         if (has_bvh) {
             ++launches;
-            io.final_pass = has_sdf_tops ? 0 : 1;
-            if (count_work) { if (has_sdf) JSRT_LAUNCH(bvh_kernel, grid_bvh, true, true); else JSRT_LAUNCH(bvh_kernel, grid_bvh, true, false); }
-            else { if (has_sdf) JSRT_LAUNCH(bvh_kernel, grid_bvh, false, true); else JSRT_LAUNCH(bvh_kernel, grid_bvh, false, false); }
+            #define JSRT_BVH(C, S, D) bvh_kernel<MODE, C, S, D><<<grid_bvh, JSRT_BVH_BLOCK, bvh_smem, stream>>>(ds, io)
+            if (direct) { if (count_work) JSRT_BVH(true, false, (MODE == TM_SHADOW)); else JSRT_BVH(false, false, (MODE == TM_SHADOW)); }
+            else if (count_work) { if (has_sdf) JSRT_BVH(true, true, false); else JSRT_BVH(true, false, false); }
+            else { if (has_sdf) JSRT_BVH(false, true, false); else JSRT_BVH(false, false, false); }
+            #undef JSRT_BVH
             if (MODE == TM_EXTEND && JSRT_TRI_TIE) { ++launches; tie_kernel<<<4, kBlock, 0, stream>>>(ds, io); }      // a few dozen entries per frame
         }
         mark();
@@ -732,21 +812,21 @@ struct Renderer::Impl {
         if (profiling) {
             for (int k = 0; k < 3; ++k) pending_parts.push_back(EvPair{pe[k], pe[k + 1], part0 + k});
         }
-        #undef JSRT_LAUNCH
     }
-    void launchExtend(int cur, bool count_work) {
+    void launchExtend(int cur, bool count_work, const GenParams* gen) {
         TraceIO io{}; io.o = rq[cur].o; io.d = rq[cur].d; io.hits = hits; io.count = &counters->ray[cur]; io.cap = ray_cap;
         io.cursor = &counters->cursor_extend; io.stats = counters->stats; io.aux = sdf_normals;
         io.tie_list = tie_list; io.tie_count = &counters->ties; io.tie_cap = kTieCap;
-        io.list = work_list; io.list_count = &counters->list_extend; io.rec0 = walker_rec[0]; io.rec1 = walker_rec[1]; io.rec2 = walker_rec[2];
-        timed(1, [&] { launchTrace<TM_EXTEND>(io, count_work, grid_extend); });
+        io.list = work_list; io.list_count = &counters->list_extend;
+        timed(1, [&] { launchTrace<TM_EXTEND>(io, count_work, gen ? grid_extend_gen : grid_extend, gen, false); });
     }
     void launchShadow(bool count_work, float4* radiance, int accum_stride, int pass0) {
         TraceIO io{}; io.o = sq.o; io.d = sq.d; io.c = sq.c; io.hits = shadow_hits; io.accum = radiance; io.count = &counters->shadow; io.cap = shadow_cap;
         io.accum_stride = accum_stride; io.pass0 = pass0;
         io.cursor = &counters->cursor_shadow; io.stats = counters->stats;
-        io.list = work_list; io.list_count = &counters->list_shadow; io.rec0 = walker_rec[0]; io.rec1 = walker_rec[1]; io.rec2 = walker_rec[2];
-        timed(3, [&] { launchTrace<TM_SHADOW>(io, count_work, grid_shadow); });
+        io.list = work_list; io.list_count = &counters->list_shadow;
+        if (fuse_shadow && ds.n_bvh == 0) return;          // nothing can be queued: every shadow ray was settled in shade_kernel
+        timed(3, [&] { launchTrace<TM_SHADOW>(io, count_work, grid_shadow, nullptr, fuse_shadow); });
     }
 
     void ensureAov(int npix_active) {
@@ -771,7 +851,33 @@ struct Renderer::Impl {
         g.npix_active = g.ncols * hs.height;
         g.first_pass = first_pass; g.jitter = (flags & 1) ? 0 : 1; g.max_depth = hs.max_depth; g.seed = seed;
         g.use_lens = 1; g.count_samples = 1;
+        g.qo = rq[0].o; g.qd = rq[0].d; g.qw = rq[0].w; g.accum = accum;
         return g;
+    }
+
+    // one batch of camera samples through all levels; radiance terms go to `radiance`
+    void runBatch(GenParams& g, uint64_t seed, bool count_work, bool aov, float4* radiance, int rstride, int pass0) {
+        set_count_kernel<<<1, 1, 0, stream>>>(counters, 0, g.n_samples, 1); ++launches;
+        if (!fuse_gen) timed(0, [&] { generate_kernel<<<grid_gen, kBlock, 0, stream>>>(g); });
+        int cur = 0;
+        for (int level = 0; level < hs.max_depth; ++level) {
+            launchExtend(cur, count_work, (level == 0 && fuse_gen) ? &g : nullptr);
+            timed(2, [&] {
+                ShadeIO io{};
+                io.q = rq[cur]; io.count = &counters->ray[cur]; io.hits = hits; io.next = rq[cur ^ 1]; io.next_count = &counters->ray[cur ^ 1]; io.next_cap = ray_cap;
+                io.sq = sq; io.shadow_count = &counters->shadow; io.shadow_cap = shadow_cap; io.accum = radiance; io.seed = seed; io.stats = counters->stats;
+                io.overflow = overflow; io.sdf_normals = has_sdf ? sdf_normals : nullptr; io.accum_stride = rstride; io.pass0 = pass0;
+                io.aov_nd = aov ? aov_nd : nullptr; io.aov_var = aov ? aov_var : nullptr;
+                #define JSRT_SHADE(S, O, F, C) shade_kernel<S, O, F, C><<<grid_shade, kBlock, 0, stream>>>(ds, io)
+                if (has_sdf) { if (count_work) JSRT_SHADE(true, false, false, true); else if (sort_shade) JSRT_SHADE(true, true, false, false); else JSRT_SHADE(true, false, false, false); }
+                else if (fuse_shadow) { if (count_work) JSRT_SHADE(false, false, true, true); else if (sort_shade) JSRT_SHADE(false, true, true, false); else JSRT_SHADE(false, false, true, false); }
+                else { if (count_work) JSRT_SHADE(false, false, false, true); else if (sort_shade) JSRT_SHADE(false, true, false, false); else JSRT_SHADE(false, false, false, false); }
+                #undef JSRT_SHADE
+            });
+            if (hs.light_samples > 0) launchShadow(count_work, radiance, rstride, pass0);
+            level_end_kernel<<<1, 1, 0, stream>>>(counters, cur, level, ray_cap, shadow_cap, fuse_shadow ? 1 : 0); ++launches;
+            cur ^= 1;
+        }
     }
 
     void render(int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags) {
@@ -782,37 +888,49 @@ struct Renderer::Impl {
         const bool count_work = (flags & 2) != 0;
         const bool aov = (flags & 4) != 0;
         const int npix = hs.width * hs.height;
+        if (aov && optimistic) throw std::runtime_error("jsrt: JSRT_FLAG_AOV needs worst-case queue sizing (this scene's depth x fan-out does not fit JSRT_QUEUE_BYTES)");
         if (aov) ensureAov(g.npix_active);
         const long long total = (long long)g.npix_active * n_passes;
-        for (long long done = 0; done < total; done += batch) {
+        int cur_batch = batch;
+        for (long long done = 0; done < total;) {
             g.first_sample = done;
-            g.n_samples = (int)std::min<long long>(batch, total - done);
+            g.n_samples = (int)std::min<long long>(cur_batch, total - done);
             // AOV renders: radiance terms land in the per-sample buffer, folded into the pixel sums after the batch
             const int pass0 = first_pass + (int)(done / std::max(1, g.npix_active));
             const int span = aov ? first_pass + (int)((done + g.n_samples - 1) / std::max(1, g.npix_active)) - pass0 + 1 : 0;
-            float4* const radiance = aov ? sample_rad : accum;
-            const int rstride = aov ? npix : 0;
-            set_count_kernel<<<1, 1, 0, stream>>>(counters, 0, g.n_samples, 1); ++launches;
-            timed(0, [&] { generate_kernel<<<grid_gen, kBlock, 0, stream>>>(g, rq[0], accum); });
-            int cur = 0;
-            for (int level = 0; level < hs.max_depth; ++level) {
-                launchExtend(cur, count_work);
-                timed(2, [&] {
-                    #define JSRT_SHADE(S, O) shade_kernel<S, O><<<grid_shade, kBlock, 0, stream>>>(ds, rq[cur], &counters->ray[cur], hits, rq[cur ^ 1], &counters->ray[cur ^ 1], ray_cap, \
-                                                                                              sq, &counters->shadow, shadow_cap, radiance, seed, counters->stats, overflow, has_sdf ? sdf_normals : nullptr, \
-                                                                                              rstride, pass0, aov ? aov_nd : nullptr, aov ? aov_var : nullptr)
-                    if (has_sdf) { if (sort_shade) JSRT_SHADE(true, true); else JSRT_SHADE(true, false); }
-                    else { if (sort_shade) JSRT_SHADE(false, true); else JSRT_SHADE(false, false); }
-                    #undef JSRT_SHADE
-                });
-                if (hs.light_samples > 0) launchShadow(count_work, radiance, rstride, pass0);
-                level_end_kernel<<<1, 1, 0, stream>>>(counters, cur, level, ray_cap, shadow_cap); ++launches;
-                cur ^= 1;
+            if (!optimistic) {
+                runBatch(g, seed, count_work, aov, aov ? sample_rad : accum, aov ? npix : 0, pass0);
+                if (aov) { fold_samples_kernel<<<grid_gen, kBlock, 0, stream>>>(g, pass0, span, sample_rad, accum, aov_var, npix); ++launches; }
+                done += g.n_samples;
+                continue;
             }
-            if (aov) { fold_samples_kernel<<<grid_gen, kBlock, 0, stream>>>(g, pass0, span, sample_rad, accum, aov_var, npix); ++launches; }
+            // optimistic sizing: render into the scratch buffer, check, fold in or re-run smaller
+            CK(cudaMemcpyAsync(stats_backup, counters->stats, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToDevice, stream));
+            g.accum = scratch;
+            runBatch(g, seed, count_work, false, scratch, 0, pass0);
+            int ov = 0;
+            CK(cudaMemcpyAsync(&ov, overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            if (!ov) {
+                add_scratch_kernel<<<(npix + 255) / 256, 256, 0, stream>>>(accum, scratch, npix); ++launches;
+                CK(cudaMemsetAsync(scratch, 0, (size_t)npix * sizeof(float4), stream));
+                done += g.n_samples;
+            } else {
+                CK(cudaMemsetAsync(overflow, 0, sizeof(int), stream));
+                CK(cudaMemsetAsync(scratch, 0, (size_t)npix * sizeof(float4), stream));
+                CK(cudaMemcpyAsync(counters->stats, stats_backup, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToDevice, stream));
+                if (g.n_samples <= 256) throw std::runtime_error("jsrt: wavefront queues overflow even with 256 camera samples in flight; raise JSRT_QUEUE_BYTES");
+                cur_batch = std::max(256, g.n_samples / 2);
+            }
         }
         CK(cudaGetLastError());
         if (x_offset == 0 && g.x_delt == 1) passes += n_passes; else passes = std::max(passes, first_pass + n_passes);
+    }
+
+    // peers' work must be finished before their buffers are read: the caller orders that (events / barriers)
+    void sumPeersInto(float4* dst) {
+        const int npix = hs.width * hs.height;
+        sum_peers_kernel<<<(npix + 255) / 256, 256, 0, stream>>>(accum, peers, dst, npix); ++launches;
     }
 };
 
@@ -821,14 +939,21 @@ Renderer::~Renderer() { delete impl_; }
 void Renderer::render(int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags) { impl_->render(first_pass, n_passes, seed, x_offset, x_delt, flags); }
 void Renderer::upload() { CK(cudaSetDevice(impl_->device)); impl_->uploadScene(); CK(cudaStreamSynchronize(impl_->stream)); }
 void Renderer::setStream(void* s) { impl_->stream = s ? (cudaStream_t)s : impl_->own_stream; impl_->applyAccumPersistence(); }
+void* Renderer::stream() const { return (void*)impl_->stream; }
+int Renderer::device() const { return impl_->device; }
 void Renderer::synchronize() {
     CK(cudaSetDevice(impl_->device)); CK(cudaStreamSynchronize(impl_->stream));
     int ov = 0; CK(cudaMemcpy(&ov, impl_->overflow, sizeof(int), cudaMemcpyDeviceToHost));
-    if (ov) throw std::runtime_error("jsrt: wavefront queue overflow (internal sizing error)");
+    if (ov) {
+        // reported once: the flag is cleared so that the handle stays usable (jsrt_reset_accum + a smaller JSRT_BATCH_PASSES)
+        CK(cudaMemset(impl_->overflow, 0, sizeof(int)));
+        throw std::runtime_error("jsrt: wavefront queue overflow (internal sizing error): the image of this call is incomplete");
+    }
 }
 void Renderer::resetAccum() {
     CK(cudaSetDevice(impl_->device));
     CK(cudaMemsetAsync(impl_->accum, 0, (size_t)impl_->hs.width * impl_->hs.height * sizeof(float4), impl_->stream));
+    CK(cudaMemsetAsync(impl_->overflow, 0, sizeof(int), impl_->stream));
     impl_->passes = 0;
     if (impl_->aov_nd) {
         const size_t bytes = (size_t)impl_->hs.width * impl_->hs.height * sizeof(float4);
@@ -846,18 +971,49 @@ void Renderer::readAov(float* normal_depth, float* variance) {
 void Renderer::resolve(uint8_t* out) {
     CK(cudaSetDevice(impl_->device));
     const int npix = impl_->hs.width * impl_->hs.height;
-    resolve_kernel<<<(npix + 255) / 256, 256, 0, impl_->stream>>>(impl_->accum, impl_->rgba, npix); ++impl_->launches;
+    resolve_kernel<<<(npix + 255) / 256, 256, 0, impl_->stream>>>(impl_->accum, impl_->peers, impl_->rgba, npix); ++impl_->launches;
     CK(cudaMemcpyAsync(out, impl_->rgba, (size_t)npix * 4, cudaMemcpyDeviceToHost, impl_->stream));
     synchronize();
 }
 void Renderer::readAccum(float* out, int* passes) {
     CK(cudaSetDevice(impl_->device));
-    CK(cudaMemcpyAsync(out, impl_->accum, (size_t)impl_->hs.width * impl_->hs.height * sizeof(float4), cudaMemcpyDeviceToHost, impl_->stream));
+    Impl& m = *impl_;
+    const size_t npix = (size_t)m.hs.width * m.hs.height;
+    const float4* src = m.accum;
+    if (m.peers.n > 0) {
+        if (!m.scratch) { m.scratch = m.dalloc<float4>(npix); }
+        m.sumPeersInto(m.scratch); src = m.scratch;
+    }
+    CK(cudaMemcpyAsync(out, src, npix * sizeof(float4), cudaMemcpyDeviceToHost, m.stream));
     synchronize();
-    if (passes) *passes = impl_->passes;
+    if (m.peers.n > 0 && m.optimistic) CK(cudaMemsetAsync(m.scratch, 0, npix * sizeof(float4), m.stream));
+    if (passes) *passes = m.passes;
 }
 void* Renderer::accumPtr() { return impl_->accum; }
 void Renderer::addPasses(int n) { impl_->passes += n; }
+void Renderer::setPeers(const void* const* ptrs, int n) {
+    if (n < 0 || n > kMaxPeers) throw std::runtime_error("jsrt: too many peer accumulation buffers");
+    impl_->peers.n = n;
+    for (int i = 0; i < n; ++i) impl_->peers.p[i] = (const float4*)ptrs[i];
+}
+void Renderer::exportAccum(void* handle64) {
+    CK(cudaSetDevice(impl_->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h; CK(cudaIpcGetMemHandle(&h, impl_->accum));
+    memcpy(handle64, &h, 64);
+}
+void Renderer::attachAccum(const void* handles64, int n) {
+    CK(cudaSetDevice(impl_->device));
+    Impl& m = *impl_;
+    for (void* p : m.ipc_mapped) cudaIpcCloseMemHandle(p);
+    m.ipc_mapped.clear(); m.peers.n = 0;
+    if (n > kMaxPeers) throw std::runtime_error("jsrt: too many peer accumulation buffers");
+    for (int i = 0; i < n; ++i) {
+        cudaIpcMemHandle_t h; memcpy(&h, (const char*)handles64 + 64 * (size_t)i, 64);
+        void* p = nullptr; CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        m.ipc_mapped.push_back(p); m.peers.p[m.peers.n++] = (const float4*)p;
+    }
+}
 void Renderer::primaryHits(int32_t* prim_id, float* t) {
     CK(cudaSetDevice(impl_->device));
     Impl& m = *impl_;
@@ -867,8 +1023,8 @@ void Renderer::primaryHits(int32_t* prim_id, float* t) {
     for (int done = 0; done < npix; done += m.batch) {
         g.first_sample = done; g.n_samples = std::min(m.batch, npix - done);
         set_count_kernel<<<1, 1, 0, m.stream>>>(m.counters, 0, g.n_samples, 0); ++m.launches;
-        generate_kernel<<<m.grid_gen, kBlock, 0, m.stream>>>(g, m.rq[0], m.accum); ++m.launches;
-        m.launchExtend(0, false);
+        generate_kernel<<<m.grid_gen, kBlock, 0, m.stream>>>(g); ++m.launches;
+        m.launchExtend(0, false, nullptr);
         hits_to_ids_kernel<<<(g.n_samples + 255) / 256, 256, 0, m.stream>>>(m.ds, m.hits, m.rq[0].o, g.n_samples, m.hit_ids, m.hit_t); ++m.launches;
         set_count_kernel<<<1, 1, 0, m.stream>>>(m.counters, 0, 0, 0); ++m.launches;
     }
@@ -928,5 +1084,23 @@ double measureReadBandwidth(int device, size_t bytes, int iters) {
 }
 
 int deviceCount() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+void enablePeerAccess(int a, int b) {
+    if (a == b) return;
+    int can = 0; CK(cudaDeviceCanAccessPeer(&can, a, b));
+    if (!can) throw std::runtime_error("jsrt: CUDA devices " + std::to_string(a) + " and " + std::to_string(b) + " are not peers (no NVLink / P2P path)");
+    CK(cudaSetDevice(a));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else CK(e);
+}
+void orderAfter(Renderer& consumer, Renderer& producer) {
+    cudaEvent_t ev;
+    CK(cudaSetDevice(producer.device()));
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, (cudaStream_t)producer.stream()));
+    CK(cudaSetDevice(consumer.device()));
+    CK(cudaStreamWaitEvent((cudaStream_t)consumer.stream(), ev, 0));
+    CK(cudaEventDestroy(ev));          // released once the wait has consumed it
+}
 
 }  // namespace jsrt

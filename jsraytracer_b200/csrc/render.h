@@ -31,6 +31,12 @@ public:
     void readAov(float* normal_depth, float* variance);
     void* accumPtr();
     void addPasses(int n);
+    // other GPUs' accumulation buffers, summed into this one's by resolve() / readAccum() (read over NVLink by the kernels)
+    void setPeers(const void* const* device_ptrs, int n);
+    void exportAccum(void* ipc_handle_64_bytes);                  // cudaIpcGetMemHandle of the accumulation buffer
+    void attachAccum(const void* ipc_handles, int n);             // maps n exported buffers of other processes as peers
+    void* stream() const;
+    int device() const;
     void primaryHits(int32_t* prim_id, float* t);
     void getStats(RenderStats& s);
     void resetStats();
@@ -46,6 +52,10 @@ private:
 };
 
 int deviceCount();
+// device `a` may read device `b`'s memory (cudaDeviceEnablePeerAccess); throws if the GPUs are not peers
+void enablePeerAccess(int a, int b);
+// work queued so far on `producer`'s stream happens before anything queued later on `consumer`'s stream (cross-device event)
+void orderAfter(Renderer& consumer, Renderer& producer);
 double measureReadBandwidth(int device, size_t bytes, int iters);
 
 }  // namespace jsrt

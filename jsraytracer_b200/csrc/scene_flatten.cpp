@@ -29,8 +29,14 @@ struct Flattener {
     std::unordered_map<const Val*, int> material_of;   // Material -> index
     std::unordered_map<const Val*, int> tri_of;        // Triangle geometry -> index
     std::unordered_map<const Val*, int> sdf_of;        // SDFGeometry -> program index
-    struct TreeRef { int first_node, node_count, first_prim, prim_count, tri_base, n_layouts; };
-    std::unordered_map<const Val*, TreeRef> tree_of;   // kdtree root -> laid-out tree (shared-tree instancing)
+    // One distinct kdtree (shared-tree instancing: several BVHAggregates may point at it).  Its node layouts are kept
+    // tree-relative in depth-first visit order (hit successor = i + 1, skip = relative index, leaf = -1 for inner
+    // nodes) until assembleNodes() gives every node its place in the scene's node array.
+    struct TreeBuild { std::vector<std::vector<BvhNode>> layouts; int first_prim = 0, prim_count = 0, tri_base = -1, root = 0, stride = 0, n_layouts = 1; };
+    std::vector<TreeBuild> trees;
+    std::unordered_map<const Val*, int> tree_of;       // kdtree root -> index into trees
+    std::vector<int> top_tree;                         // per entry of out.tops: its tree, or -1
+    std::unordered_map<const Val*, int> tree_pure;     // kdtree root -> 1 if every leaf object is a Primitive
     bool any_tri_data = false;
 
     Flattener(const WireDoc& d, HostScene& o) : doc(d), out(o) {}
@@ -333,18 +339,18 @@ struct Flattener {
         refStats(doc.field(n, "greater_node"), depth + 1);
         refStats(doc.field(n, "lesser_node"), depth + 1);
     }
-    void layoutNode(const Val* n, int first_node, int first_prim, int depth) {
+    void layoutNode(const Val* n, std::vector<BvhNode>& nodes, int first_prim, int depth) {
         NestGuard guard(tree_nest, kMaxTreeDepth);
         n = doc.resolve(n);
         if (depth > out.max_bvh_depth) out.max_bvh_depth = depth;
-        const int me = (int)out.nodes.size();
+        const int me = (int)nodes.size();
         BvhNode b{};
         const Val* box = doc.field(n, "aabb");
         double c[4], h[4];
         doc.vec(doc.field(box, "center"), c); doc.vec(doc.field(box, "half_size"), h, kInf);
         b.cx = (float)c[0]; b.cy = (float)c[1]; b.cz = (float)c[2]; b.hx = (float)h[0]; b.hy = (float)h[1]; b.hz = (float)h[2];
         b.leaf = -1;
-        out.nodes.push_back(b);
+        nodes.push_back(b);
         const bool is_leaf = doc.truthy(doc.field(n, "isLeaf"));
         if (is_leaf || (leaf_tris > 1 && smallTriSubtree(n, leaf_tris) <= leaf_tris)) {
             const int first = (int)out.prims.size() - first_prim;
@@ -353,12 +359,12 @@ struct Flattener {
             if (!is_leaf) refStats(n, depth);          // Info.n_nodes / max_bvh_depth keep describing the reference's tree
             const uint32_t cnt = (uint32_t)((int)out.prims.size() - first_prim - first);
             if (cnt > 127) fail("jsrt: BVH leaf with more than 127 objects");
-            out.nodes[me].leaf = (int)((cnt << 24) | (uint32_t)first);
+            nodes[me].leaf = (int)((cnt << 24) | (uint32_t)first);
         } else {
-            layoutNode(doc.field(n, "greater_node"), first_node, first_prim, depth + 1);
-            layoutNode(doc.field(n, "lesser_node"), first_node, first_prim, depth + 1);
+            layoutNode(doc.field(n, "greater_node"), nodes, first_prim, depth + 1);
+            layoutNode(doc.field(n, "lesser_node"), nodes, first_prim, depth + 1);
         }
-        out.nodes[me].skip = (int)out.nodes.size() - first_node;
+        nodes[me].skip = (int)nodes.size();
     }
 
     // Octant layouts: re-emit the tree rooted at layout-0 node `i` (children: i+1 = greater,
@@ -381,18 +387,188 @@ struct Flattener {
         dst[me].skip = (int)dst.size();
     }
 
-    void listMembers(const Val* objects, const double* outer) {
+    // ---- world.objects -> flattened top-level entries ------------------------------------
+    // The reference nests freely: an Aggregate's or a BVHAggregate's members may be Primitives or further aggregates
+    // (Aggregate.intersect / BVHAggregate.intersect push themselves onto `ancestors`, src/aggregates.js:14-18,43-49), and
+    // every level maps the ray by its own inv_transform.  On the device there are only three kinds of entries — a
+    // Primitive, a run of Primitives sharing an enclosing Aggregate (T_LIST), and a BVHAggregate whose leaves are all
+    // Primitives (T_BVH) — emitted in the reference's visit order (world.objects order, members in array order, the
+    // objects of a BVHAggregate with non-Primitive members in its tree's leaf visit order).  Visit order is what decides
+    // exact ties (`<` in src/world.js:9-13, src/aggregates.js:213), so "lower entry index, then lower primitive index"
+    // stays the tie rule.  Transforms of enclosing aggregates are folded into one matrix per entry / primitive.
+    bool treeIsPure(const Val* n) {
+        NestGuard guard(tree_nest, kMaxTreeDepth);
+        n = doc.resolve(n);
+        if (doc.truthy(doc.field(n, "isLeaf"))) {
+            const Val* objs = doc.field(n, "objects");
+            for (uint32_t i = 0; objs && i < doc.length(objs); ++i)
+                if (doc.typeName(doc.at(objs, i)) != "Primitive") return false;
+            return true;
+        }
+        return treeIsPure(doc.field(n, "greater_node")) && treeIsPure(doc.field(n, "lesser_node"));
+    }
+    bool pureBvh(const Val* agg) {
+        const Val* tree = doc.field(agg, "kdtree");
+        if (!tree) fail("jsrt: BVHAggregate without kdtree");
+        auto it = tree_pure.find(tree);
+        if (it == tree_pure.end()) it = tree_pure.emplace(tree, treeIsPure(tree) ? 1 : 0).first;
+        return it->second != 0;
+    }
+    int world_index = 0;               // entry of world.objects being flattened
+    int open_list = -1;                // index into out.tops of the T_LIST run that is collecting primitives, or -1
+    void closeList() {
+        if (open_list >= 0) out.tops[open_list].prim_count = (int)out.prims.size() - out.tops[open_list].first_prim;
+        open_list = -1;
+    }
+    void pushTop(const Top& t, int tree) { out.tops.push_back(t); top_tree.push_back(tree); out.top_world.push_back(world_index); }
+
+    // One BVHAggregate whose leaf objects are all Primitives.  `inv` = its inv_transform composed with every enclosing aggregate's.
+    void emitBvh(const Val* o, const double inv[16]) {
+        closeList();
+        Top top{}; top.kind = T_BVH; top.tri_base = -1; top.layouts = 1;
+        top.xform = addXform(inv);
+        const Val* tree = doc.field(o, "kdtree");
+        auto it = tree_of.find(tree);
+        if (it == tree_of.end()) {
+            TreeBuild tb;
+            tb.first_prim = (int)out.prims.size();
+            const int first_tri = (int)out.tris.size();
+            collapsed_nodes = 0;
+            tb.layouts.emplace_back();
+            layoutNode(tree, tb.layouts[0], tb.first_prim, 0);
+            const int node_count = (int)tb.layouts[0].size();
+            tb.prim_count = (int)out.prims.size() - tb.first_prim;
+            // mesh fast path: all leaf objects are fresh identity-transform shadow-casting triangles in leaf order
+            bool pure = tb.prim_count > 0 && (int)out.tris.size() - first_tri == tb.prim_count;
+            for (int k = 0; pure && k < tb.prim_count; ++k) {
+                const Prim& p = out.prims[tb.first_prim + k];
+                pure = p.geom_kind == G_TRIANGLE && p.geom_index == first_tri + k && (p.flags & PF_IDENTITY_XFORM) && (p.flags & PF_CASTS_SHADOW);
+            }
+            tb.tri_base = pure ? first_tri : -1;
+            out.tree_node_count += node_count + collapsed_nodes; collapsed_nodes = 0;
+            // Eight octant layouts (closest-hit rays use the layout of their direction octant, shadow rays layout 7,
+            // which is the reference's greater-child-first order).  Pays on big meshes (dragon 1080p: extend 11.9 -> 9.8 ms per 16
+            // passes); on small ones the reference order is as good and 8 layouts only cost L1 hits (bunny:
+            // 10.6 -> 10.8 ms).  Default: trees with >= 32768 nodes; JSRT_OCTANT_LAYOUTS=0/1 forces it.
+            bool octants = node_count >= 32768;
+            if (const char* e = getenv("JSRT_OCTANT_LAYOUTS")) octants = atoi(e) != 0;
+            if (node_count > 1 && octants) {
+                const std::vector<BvhNode> ref = tb.layouts[0];
+                tb.layouts.clear();
+                for (int q = 0; q < 8; ++q) {
+                    tb.layouts.emplace_back(); tb.layouts.back().reserve(ref.size());
+                    emitOctant(ref, 0, q, tb.layouts.back());
+                }
+            }
+            trees.push_back(std::move(tb));
+            it = tree_of.emplace(tree, (int)trees.size() - 1).first;
+        }
+        const TreeBuild& tb = trees[it->second];
+        top.first_prim = tb.first_prim; top.prim_count = tb.prim_count; top.tri_base = tb.tri_base;
+        top.node_count = (int)tb.layouts[0].size();
+        pushTop(top, it->second);
+    }
+
+    // the objects below node `n` of a BVHAggregate with non-Primitive members, in the reference's visit order
+    void mixedTreeMembers(const Val* n, const double* rel, const double* root_inv) {
+        NestGuard guard(tree_nest, kMaxTreeDepth);
+        n = doc.resolve(n);
+        if (doc.truthy(doc.field(n, "isLeaf"))) {
+            const Val* objs = doc.field(n, "objects");
+            for (uint32_t i = 0; objs && i < doc.length(objs); ++i) member(doc.at(objs, i), rel, root_inv);
+        } else {
+            mixedTreeMembers(doc.field(n, "greater_node"), rel, root_inv);
+            mixedTreeMembers(doc.field(n, "lesser_node"), rel, root_inv);
+        }
+    }
+    // One member of an aggregate.  `root_inv`: inv_transform of the outermost enclosing aggregate (kept apart, like the
+    // reference's first ray.getTransformed, for the primitives of its T_LIST runs); `rel`: the inv_transforms of the
+    // aggregates between that one and this member, composed (null = identity).
+    void member(const Val* o, const double* rel, const double* root_inv) {
         NestGuard guard(nest, kMaxNest);
-        for (uint32_t i = 0; i < doc.length(objects); ++i) {
-            const Val* o = doc.at(objects, i);
-            const std::string& t = doc.typeName(o);
-            if (t == "Primitive") placePrim(o, outer);
-            else if (t == "Aggregate") {
-                // nested list: the ray is mapped by outer^-1 then inner^-1; fold into one matrix
-                double inner[16]; doc.mat4(doc.field(o, "inv_transform"), inner);
-                if (outer) { double c[16]; mul44(inner, outer, c); listMembers(doc.field(o, "objects"), c); }
-                else listMembers(doc.field(o, "objects"), inner);
-            } else fail("jsrt: '" + t + "' nested inside a plain Aggregate is not supported");
+        const std::string& t = doc.typeName(o);
+        if (t == "Primitive") {
+            if (open_list < 0) {
+                Top top{}; top.kind = T_LIST; top.tri_base = -1; top.layouts = 1;
+                top.xform = addXform(root_inv);
+                top.first_prim = (int)out.prims.size();
+                pushTop(top, -1);
+                open_list = (int)out.tops.size() - 1;
+            }
+            placePrim(o, rel);
+        } else if (t == "Aggregate" || t == "BVHAggregate") {
+            double inner[16], c[16]; doc.mat4(doc.field(o, "inv_transform"), inner);
+            if (rel) mul44(inner, rel, c); else memcpy(c, inner, sizeof c);
+            if (t == "BVHAggregate" && pureBvh(o)) { double full[16]; mul44(c, root_inv, full); emitBvh(o, full); }
+            else if (t == "BVHAggregate") mixedTreeMembers(doc.field(o, "kdtree"), c, root_inv);
+            else { const Val* objs = doc.field(o, "objects"); for (uint32_t i = 0; objs && i < doc.length(objs); ++i) member(doc.at(objs, i), c, root_inv); }
+        } else fail("jsrt: '" + t + "' inside an aggregate is not supported");
+    }
+
+    // Gives every node of every tree layout its place in the scene's node array and turns the tree-relative links into
+    // absolute ones.  Front block: the first `take` nodes of every layout in breadth-first order — the top levels every
+    // ray walks through, staged in shared memory by bvh_kernel (DeviceScene::n_staged); behind it the remaining nodes of
+    // each layout in depth-first order (siblings' subtrees stay close together for the L1 / L2 lines).
+    void assembleNodes() {
+        int budget = 4096;                                   // nodes in the staged block: 128 KB of shared memory (JSRT_STAGE_NODES)
+        if (const char* e = getenv("JSRT_STAGE_NODES")) { const int v = atoi(e); if (v >= 0 && v <= 7168) budget = v; }
+        size_t n_layouts = 0, total = 0;
+        for (const TreeBuild& tb : trees) { n_layouts += tb.layouts.size(); for (auto& l : tb.layouts) total += l.size(); }
+        if (total >= (size_t)kNodeEnd) fail("jsrt: more than 2^31 BVH nodes");
+        out.nodes.assign(total, BvhNode{});
+        // every layout owns at least its root in the front block (the root of layout q is found at root + q * stride)
+        std::vector<int> take(trees.size(), 0);
+        {
+            long long left = budget;
+            for (size_t t = 0; t < trees.size(); ++t) { take[t] = 1; left -= (long long)trees[t].layouts.size(); }
+            // hand the rest out in rounds, one level-ish at a time, so that small trees do not strand budget
+            bool grew = true;
+            while (left > 0 && grew) {
+                grew = false;
+                for (size_t t = 0; t < trees.size() && left > 0; ++t) {
+                    const int size = (int)trees[t].layouts[0].size(), nl = (int)trees[t].layouts.size();
+                    const int want = std::min(size, take[t] * 2 + 1) - take[t];
+                    const int can = (int)std::min<long long>(want, left / nl);
+                    if (can > 0) { take[t] += can; left -= (long long)can * nl; grew = true; }
+                }
+            }
+        }
+        size_t front = 0;
+        for (size_t t = 0; t < trees.size(); ++t) { trees[t].root = (int)front; trees[t].stride = take[t]; front += (size_t)take[t] * trees[t].layouts.size(); }
+        out.n_staged = (int)front;
+        size_t rest = front;
+        std::vector<int> place, bfs;
+        for (size_t t = 0; t < trees.size(); ++t) {
+            TreeBuild& tb = trees[t];
+            for (size_t q = 0; q < tb.layouts.size(); ++q) {
+                const std::vector<BvhNode>& L = tb.layouts[q];
+                const int n = (int)L.size();
+                place.assign(n, -1); bfs.clear();
+                bfs.push_back(0);
+                for (size_t h = 0; h < bfs.size() && (int)bfs.size() < take[t]; ++h) {
+                    const int i = bfs[h];
+                    if (L[i].leaf != -1) continue;
+                    bfs.push_back(i + 1);
+                    if ((int)bfs.size() < take[t]) bfs.push_back(L[i + 1].skip);
+                }
+                const int base = tb.root + (int)q * tb.stride;
+                for (size_t k = 0; k < bfs.size(); ++k) place[bfs[k]] = base + (int)k;
+                // (bfs.size() == take[t] unless the loop ran out of inner nodes, which cannot happen for take <= n)
+                for (int i = 0; i < n; ++i) if (place[i] < 0) place[i] = (int)rest++;
+                for (int i = 0; i < n; ++i) {
+                    BvhNode b = L[i];
+                    b.skip = (L[i].skip >= n) ? kNodeEnd : place[L[i].skip];
+                    if (L[i].leaf == -1) b.leaf = kNodeInner | place[i + 1];
+                    out.nodes[place[i]] = b;
+                }
+            }
+            tb.n_layouts = (int)tb.layouts.size();
+            tb.layouts.clear(); tb.layouts.shrink_to_fit();
+        }
+        for (size_t i = 0; i < out.tops.size(); ++i) {
+            if (top_tree[i] < 0) continue;
+            const TreeBuild& tb = trees[top_tree[i]];
+            out.tops[i].first_node = tb.root;
         }
     }
 
@@ -439,69 +615,34 @@ struct Flattener {
         const Val* objects = doc.field(world, "objects");
         assignIds(objects);
         out.ext_prim_count = (int)ext_id.size();
+        out.world_object_count = (int)doc.length(objects);
         for (uint32_t i = 0; i < doc.length(objects); ++i) {
             const Val* o = doc.at(objects, i);
             const std::string& ty = doc.typeName(o);
-            Top top{}; top.tri_base = -1; top.n_layouts = 1;
+            world_index = (int)i;
             if (ty == "Primitive") {
+                Top top{}; top.tri_base = -1; top.layouts = 1;
                 top.kind = T_PRIM; top.first_prim = (int)out.prims.size(); top.prim_count = 1;
                 placePrim(o, nullptr);
                 if (out.prims.back().geom_kind == G_SDF) top.kind = T_SDF;
-            } else if (ty == "BVHAggregate") {
-                top.kind = T_BVH;
+                pushTop(top, -1);
+            } else if (ty == "BVHAggregate" || ty == "Aggregate") {
                 double inv[16]; doc.mat4(doc.field(o, "inv_transform"), inv);
-                top.xform = addXform(inv);
-                const Val* tree = doc.field(o, "kdtree");
-                auto it = tree_of.find(tree);
-                if (it == tree_of.end()) {
-                    TreeRef r{(int)out.nodes.size(), 0, (int)out.prims.size(), 0, -1, 1};
-                    const int first_tri = (int)out.tris.size();
-                    collapsed_nodes = 0;
-                    layoutNode(tree, r.first_node, r.first_prim, 0);
-                    r.node_count = (int)out.nodes.size() - r.first_node;
-                    r.prim_count = (int)out.prims.size() - r.first_prim;
-                    // mesh fast path: all leaf objects are fresh identity-transform shadow-casting triangles in leaf order
-                    bool pure = r.prim_count > 0 && (int)out.tris.size() - first_tri == r.prim_count;
-                    for (int k = 0; pure && k < r.prim_count; ++k) {
-                        const Prim& p = out.prims[r.first_prim + k];
-                        pure = p.geom_kind == G_TRIANGLE && p.geom_index == first_tri + k && (p.flags & PF_IDENTITY_XFORM) && (p.flags & PF_CASTS_SHADOW);
-                    }
-                    r.tri_base = pure ? first_tri : -1;
-                    out.tree_node_count += r.node_count + collapsed_nodes; collapsed_nodes = 0;
-                    // Eight octant layouts (closest-hit rays use the layout of their direction octant, shadow rays layout 7,
-                    // which is the reference's greater-child-first order).  Pays on big meshes (dragon 1080p: extend 11.9 -> 9.8 ms per 16
-                    // passes); on small ones the reference order is as good and 8 layouts only cost L1 hits (bunny:
-                    // 10.6 -> 10.8 ms).  Default: trees with >= 32768 nodes; JSRT_OCTANT_LAYOUTS=0/1 forces it.
-                    bool octants = r.node_count >= 32768;
-                    if (const char* e = getenv("JSRT_OCTANT_LAYOUTS")) octants = atoi(e) != 0;
-                    if (r.node_count > 1 && octants) {
-                        const std::vector<BvhNode> ref(out.nodes.begin() + r.first_node, out.nodes.end());
-                        out.nodes.resize(r.first_node);
-                        for (int q = 0; q < 8; ++q) {
-                            std::vector<BvhNode> dst; dst.reserve(ref.size());
-                            emitOctant(ref, 0, q, dst);
-                            out.nodes.insert(out.nodes.end(), dst.begin(), dst.end());
-                        }
-                        r.n_layouts = 8;
-                    }
-                    // the device walk uses absolute node indices (no per-tree base pointer in registers)
-                    for (int q = 0; q < r.n_layouts; ++q)
-                        for (int k = 0; k < r.node_count; ++k) out.nodes[r.first_node + q * r.node_count + k].skip += r.first_node + q * r.node_count;
-                    it = tree_of.emplace(tree, r).first;
-                }
-                top.first_node = it->second.first_node; top.node_count = it->second.node_count;
-                top.first_prim = it->second.first_prim; top.prim_count = it->second.prim_count;
-                top.tri_base = it->second.tri_base; top.n_layouts = it->second.n_layouts;
-            } else if (ty == "Aggregate") {
-                top.kind = T_LIST;
-                double inv[16]; doc.mat4(doc.field(o, "inv_transform"), inv);
-                top.xform = addXform(inv);
-                top.first_prim = (int)out.prims.size();
-                listMembers(doc.field(o, "objects"), nullptr);
-                top.prim_count = (int)out.prims.size() - top.first_prim;
+                if (ty == "BVHAggregate" && pureBvh(o)) emitBvh(o, inv);
+                else if (ty == "BVHAggregate") mixedTreeMembers(doc.field(o, "kdtree"), nullptr, inv);
+                else { const Val* objs = doc.field(o, "objects"); for (uint32_t k = 0; objs && k < doc.length(objs); ++k) member(doc.at(objs, k), nullptr, inv); }
+                closeList();
+                // (an aggregate without members leaves no entry: it can never be hit)
             } else fail("jsrt: unsupported world object type '" + ty + "'");
-            out.tops.push_back(top);
         }
+        assembleNodes();
+        // the layout word of every BVH entry: 8 link orders or 1, and the distance between their roots
+        for (size_t i = 0; i < out.tops.size(); ++i)
+            if (top_tree[i] >= 0) {
+                const TreeBuild& tb = trees[top_tree[i]];
+                const int nl = (out.tops[i].node_count > 1 && tb.stride > 0 && tb.n_layouts == 8) ? 8 : 1;
+                out.tops[i].layouts = nl | (tb.stride << 8);
+            }
         if (!any_tri_data) out.tri_shade.clear();
 
         const Val* lights = doc.field(world, "lights");

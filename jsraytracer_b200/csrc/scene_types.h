@@ -53,29 +53,34 @@ struct TriShade {                 // per-vertex shading data (only read for shad
     float pad[2];
 };
 
-// BVH node, 32 bytes = two 128-bit loads.  Nodes are laid out in visit order so a
-// stackless walk `i -> i+1` on hit / `i -> skip` on miss needs no stack.  Placed
-// primitives are stored in the reference's visit order (greater child first,
-// src/aggregates.js:221-222), which makes "lower primitive index" the reference's tie
-// rule; the node array exists in eight orders, one per ray-direction octant, each
-// visiting the nearer child first (trace.cuh).
+// BVH node, 32 bytes = two 128-bit loads.  The walk is stackless: box hit -> the node's hit link (inner) or its leaf
+// (then the skip link), box missed -> the skip link.  Both links are explicit absolute indices, so the nodes may be
+// stored in any order; scene_flatten.cpp puts the top levels of every tree (breadth-first) in one block at the front of
+// the scene's node array — the block bvh_kernel stages in shared memory — and the rest of each tree depth-first.
+// Placed primitives are stored in the reference's visit order (greater child first, src/aggregates.js:221-222), which
+// makes "lower primitive index" the reference's tie rule; big trees exist in eight link orders, one per ray-direction
+// octant, each visiting the nearer child first (trace.cuh).
 struct BvhNode {
     float cx, cy, cz, hx;         // AABB centre, half-size x   (centre/half form: src/geometry.js:189-209)
     float hy, hz;
-    int skip;                     // next node when this subtree is done (absolute index into the scene's node array)
-    int leaf;                     // inner: -1; leaf: (count << 24) | first placed-primitive index (relative to the aggregate's first primitive)
+    int skip;                     // next node when this subtree is done (absolute index), kNodeEnd when the walk is over
+    int leaf;                     // inner: kNodeInner | hit link (absolute index of the first child to visit);
+                                  // leaf: (count << 24) | first placed-primitive index (relative to the aggregate's first primitive), count <= 127
 };
+constexpr int kNodeEnd = 0x7fffffff;
+constexpr int kNodeInner = (int)0x80000000u;
 
 struct Top {                      // one entry of world.objects (src/world.js:7-15 walks them in order)
     int kind;                     // TopKind
     int xform;                    // T_BVH / T_LIST: the aggregate's inv_transform
     int first_prim;               // first placed primitive
     int prim_count;               // T_PRIM: 1
-    int first_node;               // T_BVH: first BvhNode of layout 0; layout q starts at first_node + q * node_count
-    int node_count;
+    int first_node;               // T_BVH: root BvhNode of layout 0; the root of layout q is first_node + q * (layouts >> 8)
+    int node_count;               // nodes of one layout (host-side bookkeeping)
     int tri_base;                 // >= 0: every leaf object is an identity-transform, shadow-casting Triangle and
                                   // triangle index = tri_base + (placed primitive index - first_prim); else -1
-    int n_layouts;                // 8: one node layout per ray-direction octant (near child first); 1: reference order only
+    int layouts;                  // low byte: 8 = one link order per ray-direction octant (near child first), 1 = reference order only;
+                                  // upper bits: distance between the roots of consecutive layouts
 };
 
 // One row of the analytic-primitive table: 32 bytes, read with two warp-uniform 128-bit loads.

@@ -4,6 +4,7 @@
 // (src/aggregates.js:14-18,43-49) and BVHAggregateNode.intersect (:207-225).
 #pragma once
 #include "device_math.cuh"
+#include "rng.h"
 
 namespace jsrt {
 
@@ -34,7 +35,9 @@ struct DeviceScene {
     // (use_wbox).  Conservative — a ray that misses the padded world box misses the local root box — so results are
     // those of the reference's linear walk over world.objects (src/world.js:7-15).
     const float4* wboxes;
-    int n_sdf_tops, use_wbox, pad1, pad2;
+    int n_sdf_tops, use_wbox;
+    int n_staged;              // nodes[0, n_staged): the top levels of every tree, staged in shared memory by bvh_kernel
+    int pad2;
     int n_top, n_lights, light_samples, max_depth;
     float bg[3];
     int n_bvh;
@@ -136,9 +139,6 @@ JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, floa
 #ifndef JSRT_PROG_T
 #define JSRT_PROG_T 33     // > 32: parked leaves are tested after every round of node steps (measured best: profiles/r2_ab.md)
 #endif
-#ifndef JSRT_NODE_PREFETCH
-#define JSRT_NODE_PREFETCH 0
-#endif
 #ifndef JSRT_NODE_LDG256
 #define JSRT_NODE_LDG256 0
 #endif
@@ -148,16 +148,9 @@ JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, floa
 #ifndef JSRT_NODE_STEPS
 #define JSRT_NODE_STEPS 8
 #endif
-// Work list as 48-byte walker records instead of (ray index, BVH) pairs (see TraceIO).  Measured (profiles/r1_s3,
-// ab_s3_rec_*): the BVH kernels gain 2.5-7 % (coalesced, shorter refill) but prims_kernel pays for the wider
-// records — bunny_path 5 692 -> 5 602, dragon 4 900 -> 4 936, starwars 4 325 -> 4 394 Mrays/s, +21 GB of queue
-// memory — so the refill gather is not what the long-scoreboard stalls of the walk are made of.  Off by default.
 // FP32 near-ties between two triangles of a mesh settled in the reference's f64 (tie_wave); 0 = off (A/B runs).
 #ifndef JSRT_TRI_TIE
 #define JSRT_TRI_TIE 1
-#endif
-#ifndef JSRT_WALKER_RECORDS
-#define JSRT_WALKER_RECORDS 0
 #endif
 enum TraceMode { TM_EXTEND = 0, TM_SHADOW = 1 };
 
@@ -175,12 +168,6 @@ struct TraceIO {
     int final_pass;                     // 1 if no further tracing kernel follows for this wave (the last one writes results)
     int2* __restrict__ list;            // BVH work list: (ray index, first BVH whose root box the ray hits), written by
     int* list_count;                    //   prims_wave with warp-aggregated appends, consumed by bvh_wave
-    // JSRT_WALKER_RECORDS: the work list carries the whole walker instead — three float4 per entry (SoA), so that a
-    // refilling lane reads 48 contiguous, coalesced bytes instead of gathering the ray, its direction and its partial
-    // hit through the index (three half-used sectors behind a dependent load) and re-deriving the local ray:
-    //   rec0 = local origin.xyz | ray index     rec1 = local direction.xyz | closest hit so far (t)
-    //   rec2 = first BVH | top-level index of that hit | primary-ray flag | -
-    float4* __restrict__ rec0; float4* __restrict__ rec1; float4* __restrict__ rec2;
     // JSRT_FLAG_AOV renders: radiance goes to a per-sample buffer (`accum` then points at it) so that the per-pixel
     // variance can be formed from whole samples; slot = pixel + (pass - pass0) * accum_stride.  0 otherwise.
     int accum_stride, pass0;
@@ -316,16 +303,171 @@ JSRT_DEV bool wbox_hit(const float4* __restrict__ wb, int b, float3 o, float3 in
     return n <= f && f >= minD && n <= hi;
 }
 
+// World.getMinimumIntersection (src/world.js:7-15) over the analytic primitives — every Primitive of world.objects
+// outside the BVHAggregates — one tight loop per geometry kind (a single loop over world.objects with a switch cost 285
+// instructions per test on cornell_box_path, the compiler having hoisted the sphere's f64 set-up in front of the
+// switch: profiles/r1_s3).  The reference's "first object wins exact ties" is the static rank (top, prim), so the order
+// of the tests is free.  Called together by the lanes of `mask` (a converged subset of the warp).
+// Shadow rays (ANY_HIT): no per-lane early exit inside the loops.  A lane that leaves a loop on its own runs the rest of
+// the body apart from its warp (measured on cornell_box_path: 8.7 of 32 lanes active in the box loop, each group of
+// lanes running it separately); instead every lane runs every test of a group and the lanes of `mask` skip the
+// remaining groups together once all of their rays are occluded.
+template <bool ANY_HIT, bool COUNT, bool HAS_SDF>
+JSRT_DEV void analytic_hits(const DeviceScene& sc, const float3 o, const float3 d, const float minD, const float maxD, const unsigned mask, Hit& best, Work* work) {
+    const APrim* const tab = sc.atab;
+    const int tb = ANY_HIT ? 1 : 0;
+    int k = (ANY_HIT ? sc.atab_end[0][AG_COUNT - 1] : 0);
+    #define JSRT_ACCEPT(T, TL)                                                                                              \
+        if ((T) > minD && (T) < maxD && ((T) < best.t || ((T) == best.t && (e0.y < best.top || (e0.y == best.top && e0.x < best.prim))))) { \
+            best.t = (T); best.prim = e0.x; best.top = e0.y; best.t_lo = (TL); }
+    #define JSRT_ENTRY()                                                                                                    \
+        const int4 e0 = __ldg(reinterpret_cast<const int4*>(tab + k));     /* prim, top, agg_xform, xform */                \
+        const int4 e1 = __ldg(reinterpret_cast<const int4*>(tab + k) + 1); /* geom_index, flags */                          \
+        if (COUNT) ++work->top_prims;
+    // ray.getTransformed(inv_transform) (src/world.js:120), after the enclosing Aggregate's own map if there is one
+    #define JSRT_LOCAL_RAY()                                                                                                \
+        float3 lo = o, ld = d;                                                                                              \
+        if (e0.z >= 0) { const XformReg ma = load_xform(sc.xforms, e0.z); lo = xf_point(ma, o); ld = xf_dir(ma, d); }         \
+        if (!(e1.y & PF_IDENTITY_XFORM)) { const XformReg m = load_xform(sc.xforms, e0.w); const float3 a = xf_point(m, lo), b = xf_dir(m, ld); lo = a; ld = b; }
+    #define JSRT_GROUP_DONE() (ANY_HIT && __all_sync(mask, best.prim >= 0))
+    for (; k < sc.atab_end[tb][AG_PLANE]; ++k) {                           // SimplePlane.intersect src/geometry.js:246-248
+        JSRT_ENTRY()
+        float oz, dz;
+        if (e0.z < 0 && !(e1.y & PF_IDENTITY_XFORM)) {                     // only the z row of the local ray is needed
+            const float4 r2 = __ldg(reinterpret_cast<const float4*>(sc.xforms + e0.w) + 2);
+            oz = r2.x * o.x + r2.y * o.y + r2.z * o.z + r2.w; dz = r2.x * d.x + r2.y * d.y + r2.z * d.z;
+        } else { JSRT_LOCAL_RAY() oz = lo.z; dz = ld.z; }
+        const float t = (dz != 0.f) ? -oz / dz : -CUDART_INF_F;
+        JSRT_ACCEPT(t, 0.f)
+    }
+    if (!JSRT_GROUP_DONE()) for (; k < sc.atab_end[tb][AG_SQUARE]; ++k) {   // Square.intersect src/geometry.js:287-291
+        JSRT_ENTRY()
+        JSRT_LOCAL_RAY()
+        const float t = plane_t(lo, ld);
+        const float x = __fadd_rn(lo.x, __fmul_rn(ld.x, t)), y = __fadd_rn(lo.y, __fmul_rn(ld.y, t));
+        if (-0.5f <= x && x <= 0.5f && -0.5f <= y && y <= 0.5f) { JSRT_ACCEPT(t, 0.f) }
+    }
+    if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_SQUARE]; k < sc.atab_end[tb][AG_BOX]; ++k) {      // AABB.intersect src/geometry.js:173-179
+        JSRT_ENTRY()
+        JSRT_LOCAL_RAY()
+        float3 c = f3(0.f, 0.f, 0.f), h = f3(0.5f, 0.5f, 0.5f);
+        if (e1.x >= 0) { const float* b = sc.boxes + 8 * e1.x; c = f3(__ldg(b), __ldg(b + 1), __ldg(b + 2)); h = f3(__ldg(b + 4), __ldg(b + 5), __ldg(b + 6)); }
+        const float t = box_prim_intersect(c, h, lo, ld, minD, maxD);
+        JSRT_ACCEPT(t, 0.f)
+    }
+    if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_BOX]; k < sc.atab_end[tb][AG_SPHERE]; ++k) {      // Sphere.staticIntersect src/geometry.js:429-442
+        JSRT_ENTRY()
+        JSRT_LOCAL_RAY()
+        const float t = sphere_intersect(lo, ld, minD);
+        JSRT_ACCEPT(t, 0.f)
+    }
+    if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_SPHERE]; k < sc.atab_end[tb][AG_OTHER]; ++k) {    // every other geometry: the general code
+        if (ANY_HIT && best.prim >= 0) break;
+        JSRT_ENTRY()
+        float3 lo = o, ld = d;
+        if (e0.z >= 0) { const XformReg ma = load_xform(sc.xforms, e0.z); lo = xf_point(ma, o); ld = xf_dir(ma, d); }
+        float tl = 0.f;
+        const float t = placed_prim_intersect<HAS_SDF>(sc, e0.x, lo, ld, minD, maxD, best.t, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
+        JSRT_ACCEPT(t, tl)
+    }
+    #undef JSRT_GROUP_DONE
+    #undef JSRT_ACCEPT
+    #undef JSRT_ENTRY
+    #undef JSRT_LOCAL_RAY
+}
+
+// The root box of every BVHAggregate in world.objects order (the first test of BVHAggregateNode.intersect,
+// src/aggregates.js:208-209), behind the padded world-space reject when the scene holds several aggregates.
+// Returns the ordinal of the first aggregate whose root box the ray hits within (minD, min(maxD, best_t)], or -1;
+// `lr` receives the ray in that aggregate's space.
+template <bool COUNT>
+JSRT_DEV int first_bvh_hit(const DeviceScene& sc, const float3 o, const float3 d, const float minD, const float maxD, const float best_t, Work* work, LocalRay& lr) {
+    float3 winv = f3(0.f, 0.f, 0.f);
+    if (sc.use_wbox) winv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    for (int b = 0; b < sc.n_bvh; ++b) {
+        if (sc.use_wbox && !wbox_hit(sc.wboxes, b, o, winv, minD, fminf(maxD, best_t))) continue;
+        const int4* tp = reinterpret_cast<const int4*>(sc.tops + __ldg(sc.bvh_tops + b));
+        const int4 ta = __ldg(tp); const int first_node = __ldg(reinterpret_cast<const int*>(tp + 1));
+        const LocalRay r = make_local_ray(load_xform(sc.xforms, ta.y), o, d);
+        const float4* root = reinterpret_cast<const float4*>(sc.nodes + first_node);
+        if (COUNT) ++work->nodes;
+        if (slab_any(__ldg(root), __ldg(root + 1), r, minD, maxD, best_t)) { lr = r; return b; }
+    }
+    return -1;
+}
+
+// Camera rays (generate): what prims_kernel<extend, GEN> computes itself instead of reading a queue entry.
+struct GenParams {
+    Camera cam;
+    int width, height, x_offset, x_delt, ncols, npix_active;
+    int first_pass, jitter, max_depth, use_lens, count_samples;
+    unsigned long long seed;
+    long long first_sample;      // index of the batch's first sample within the call
+    int n_samples;               // samples in this batch
+    float4 *qo, *qd, *qw;        // the level-0 ray queue (written), the pixel sums (sample counts)
+    float4* accum;
+};
+
+// camera.getRayForPixel for sample s of the batch (src/cameras.js:29-34,46-52) with the pixel / jitter arithmetic of
+// src/renderers.js:89-96, all in f64 so the primary ray is the reference's bit for bit.
+JSRT_DEV void camera_ray(const GenParams& g, int px, int py, uint32_t sample_key, bool jitter, bool use_lens, float3& o, float3& d) {
+    const uint32_t nk = rng_node_key(sample_key, 1);
+    double x = dsub(dmul(2.0, (double)px / (double)g.width), 1.0);
+    double y = dadd(dmul(-2.0, (double)py / (double)g.height), 1.0);
+    if (jitter) {
+        x = dadd(x, dmul(2.0 / (double)g.width, dsub((double)rng_u01(nk, DIM_JITTER_X), 0.5)));
+        y = dadd(y, dmul(2.0 / (double)g.height, dsub((double)rng_u01(nk, DIM_JITTER_Y), 0.5)));
+    }
+    const Camera& c = g.cam;
+    const float dx = (float)dmul(dmul(x, c.tan_fov), c.aspect), dy = (float)dmul(y, c.tan_fov), dz = -1.f;   // Vec.of(...) stores f32
+    const double* t = c.t;
+    // transform.times(direction): f64 dot of the f32 vector with each row, stored f32 (w = 0)
+    float3 dir = f3((float)ddot4(dx, dy, dz, 0.0, t[0], t[1], t[2], t[3]), (float)ddot4(dx, dy, dz, 0.0, t[4], t[5], t[6], t[7]),
+                    (float)ddot4(dx, dy, dz, 0.0, t[8], t[9], t[10], t[11]));
+    float3 org = f3((float)t[3], (float)t[7], (float)t[11]);       // transform.column(3)
+    if (c.dof && use_lens) {
+        // Vec.circlePick src/math.js:175-179, then DepthOfFieldPerspectiveCamera.getRayForPixel (src/cameras.js:46-52)
+        const double a = dmul(dmul((double)rng_u01(nk, DIM_LENS_A), 2.0), 3.141592653589793), r = sqrt((double)rng_u01(nk, DIM_LENS_R));
+        const float cx = (float)dmul(r, cos(a)), cy = (float)dmul(r, sin(a));
+        const float sx = (float)dmul(cx, c.sensor_size), sy = (float)dmul(cy, c.sensor_size);
+        const float3 off = f3((float)ddot4(sx, sy, 0.0, 0.0, t[0], t[1], t[2], t[3]), (float)ddot4(sx, sy, 0.0, 0.0, t[4], t[5], t[6], t[7]),
+                              (float)ddot4(sx, sy, 0.0, 0.0, t[8], t[9], t[10], t[11]));
+        org = f3((float)dadd(org.x, off.x), (float)dadd(org.y, off.y), (float)dadd(org.z, off.z));
+        const float fx = (float)dmul(dir.x, c.focus_distance), fy = (float)dmul(dir.y, c.focus_distance), fz = (float)dmul(dir.z, c.focus_distance);
+        const float mx = (float)dsub(fx, off.x), my = (float)dsub(fy, off.y), mz = (float)dsub(fz, off.z);
+        const double nn = sqrt(ddot4(mx, my, mz, 0.0, mx, my, mz, 0.0));
+        if (nn > 0.00001) { const double inv = 1.0 / nn; dir = f3((float)dmul(mx, inv), (float)dmul(my, inv), (float)dmul(mz, inv)); }
+        else dir = f3(mx, my, mz);
+    }
+    o = org; d = dir;
+}
+// sample s of the batch -> (pixel, pass) and the three queue words of its camera ray
+JSRT_DEV void generate_sample(const GenParams& g, int s, float4& o4, float4& d4, float4& w4, uint32_t& pixel) {
+    const long long gs = g.first_sample + s;
+    const int pass = g.first_pass + (int)(gs / g.npix_active);
+    const int idx = (int)(gs % g.npix_active);
+    const int py = idx / g.ncols, px = g.x_offset + (idx % g.ncols) * g.x_delt;
+    pixel = (uint32_t)(py * g.width + px);
+    const uint32_t key = rng_sample_key(g.seed, pixel, (uint32_t)pass);
+    float3 o, d;
+    camera_ray(g, px, py, key, g.jitter != 0, g.use_lens != 0, o, d);
+    o4 = make_float4(o.x, o.y, o.z, __int_as_float((int)pixel));
+    d4 = make_float4(d.x, d.y, d.z, __int_as_float(1));
+    w4 = make_float4(1.f, 1.f, 1.f, __int_as_float((pass << 8) | g.max_depth));
+}
+
 // prims_wave: every top-level Primitive / plain Aggregate against every ray of the queue, one ray per thread,
 // then the root box of every BVHAggregate (the first test of BVHAggregateNode.intersect, src/aggregates.js:208-209).
 // Rays that hit no root box are finished here (most rays: 92 % of bunny_path's camera rays miss the mesh's
 // box); the others are appended to the BVH work list, compacted with a warp ballot + prefix popcount and one
 // atomicAdd per warp, so that bvh_wave only ever sees rays that walk.
-template <int MODE, bool COUNT, bool HAS_SDF>
-JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other) {
+// GEN (level 0 of a batch): the ray of entry i is the camera ray of sample i, computed here and written to the queue for
+// the later kernels, instead of being written by a generate kernel and read back (92 % of them only ever meet the plane).
+template <int MODE, bool COUNT, bool HAS_SDF, bool GEN>
+JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, const GenParams* gen, Work* work_primary, Work* work_other) {
     constexpr bool ANY_HIT = (MODE == TM_SHADOW);
     const unsigned FULL = 0xffffffffu;
-    const int n = min(*io.count, io.cap);
+    const int n = GEN ? gen->n_samples : min(*io.count, io.cap);
     const int stride = gridDim.x * blockDim.x;
     const int n_round = (n + 31) & ~31;                // warp-uniform trip count: every lane reaches the ballot
     const int lane = threadIdx.x & 31;
@@ -336,128 +478,44 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, Work* work_pr
 #define JSRT_PRIMS_PREFETCH 1      // 2: the same with evict-first (ld.global.cs) loads
 #endif
 #define JSRT_PRIMS_LD(p) ((JSRT_PRIMS_PREFETCH == 2) ? __ldcs(p) : *(p))
+    constexpr bool PREFETCH = JSRT_PRIMS_PREFETCH && !GEN;
     float4 no4 = make_float4(0, 0, 0, 0), nd4 = no4;
     {
         const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-        if (JSRT_PRIMS_PREFETCH && i0 < n) { no4 = JSRT_PRIMS_LD(io.o + i0); nd4 = JSRT_PRIMS_LD(io.d + i0); }
+        if (PREFETCH && i0 < n) { no4 = JSRT_PRIMS_LD(io.o + i0); nd4 = JSRT_PRIMS_LD(io.d + i0); }
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         int first_bvh = -1;
         Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
         float4 o4 = make_float4(0, 0, 0, 0);
-        float3 w_lo = f3(0, 0, 0), w_ld = f3(0, 0, 1); bool w_primary = false;      // the walker handed to bvh_wave
         const unsigned live = __ballot_sync(FULL, i < n);
         float4 cur_d4 = nd4;
-        if (JSRT_PRIMS_PREFETCH) {
+        if (PREFETCH) {
             o4 = no4;
             const int inext = i + stride;
             if (inext < n) { no4 = JSRT_PRIMS_LD(io.o + inext); nd4 = JSRT_PRIMS_LD(io.d + inext); }
         }
         if (i < n) {
-            if (!JSRT_PRIMS_PREFETCH) { o4 = io.o[i]; cur_d4 = io.d[i]; }
+            if (GEN) {
+                float4 w4; uint32_t pixel;
+                generate_sample(*gen, i, o4, cur_d4, w4, pixel);
+                gen->qo[i] = o4; gen->qd[i] = cur_d4; gen->qw[i] = w4;
+                if (gen->count_samples) atomicAdd(&gen->accum[pixel].w, 1.0f);      // samples taken for this pixel
+            } else if (!PREFETCH) { o4 = io.o[i]; cur_d4 = io.d[i]; }
             const float4 d4 = cur_d4;
             const float3 o = f3(o4.x, o4.y, o4.z), d = f3(d4.x, d4.y, d4.z);
             float minD, maxD; bool primary;
             ray_window<MODE>(d4, minD, maxD, primary);
             Work* work = (COUNT && primary) ? work_primary : work_other;
-            // World.getMinimumIntersection (src/world.js:7-15) over the analytic primitives, one tight loop per geometry
-            // kind (a single loop over world.objects with a switch cost 285 instructions per test on cornell_box_path,
-            // the compiler having hoisted the sphere's f64 set-up in front of the switch: profiles/r1_s3).  The
-            // reference's "first object wins exact ties" is the static rank (top, prim), so the order of the tests is free.
-            const APrim* const tab = sc.atab;
-            const int tb = ANY_HIT ? 1 : 0;
-            int k = (ANY_HIT ? sc.atab_end[0][AG_COUNT - 1] : 0);
-            #define JSRT_ACCEPT(T, TL)                                                                                              \
-                if ((T) > minD && (T) < maxD && ((T) < best.t || ((T) == best.t && (e0.y < best.top || (e0.y == best.top && e0.x < best.prim))))) { \
-                    best.t = (T); best.prim = e0.x; best.top = e0.y; best.t_lo = (TL); }
-            #define JSRT_ENTRY()                                                                                                    \
-                const int4 e0 = __ldg(reinterpret_cast<const int4*>(tab + k));     /* prim, top, agg_xform, xform */                \
-                const int4 e1 = __ldg(reinterpret_cast<const int4*>(tab + k) + 1); /* geom_index, flags */                          \
-                if (COUNT) ++work->top_prims;
-            // ray.getTransformed(inv_transform) (src/world.js:120), after the enclosing Aggregate's own map if there is one
-            #define JSRT_LOCAL_RAY()                                                                                                \
-                float3 lo = o, ld = d;                                                                                              \
-                if (e0.z >= 0) { const XformReg ma = load_xform(sc.xforms, e0.z); lo = xf_point(ma, o); ld = xf_dir(ma, d); }         \
-                if (!(e1.y & PF_IDENTITY_XFORM)) { const XformReg m = load_xform(sc.xforms, e0.w); const float3 a = xf_point(m, lo), b = xf_dir(m, ld); lo = a; ld = b; }
-            // Shadow rays: no per-lane early exit inside these loops.  A lane that leaves a loop on its own runs the rest of
-            // the body apart from its warp (measured on cornell_box_path: 8.7 of 32 lanes active in the box loop, each
-            // group of lanes running it separately); instead every lane runs every test of a group and the warp skips the
-            // remaining groups together once all of its rays are occluded.
-            #define JSRT_GROUP_DONE() (ANY_HIT && __all_sync(live, best.prim >= 0))
-            for (; k < sc.atab_end[tb][AG_PLANE]; ++k) {                           // SimplePlane.intersect src/geometry.js:246-248
-                JSRT_ENTRY()
-                float oz, dz;
-                if (e0.z < 0 && !(e1.y & PF_IDENTITY_XFORM)) {                     // only the z row of the local ray is needed
-                    const float4 r2 = __ldg(reinterpret_cast<const float4*>(sc.xforms + e0.w) + 2);
-                    oz = r2.x * o.x + r2.y * o.y + r2.z * o.z + r2.w; dz = r2.x * d.x + r2.y * d.y + r2.z * d.z;
-                } else { JSRT_LOCAL_RAY() oz = lo.z; dz = ld.z; }
-                const float t = (dz != 0.f) ? -oz / dz : -CUDART_INF_F;
-                JSRT_ACCEPT(t, 0.f)
-            }
-            if (!JSRT_GROUP_DONE()) for (; k < sc.atab_end[tb][AG_SQUARE]; ++k) {   // Square.intersect src/geometry.js:287-291
-                JSRT_ENTRY()
-                JSRT_LOCAL_RAY()
-                const float t = plane_t(lo, ld);
-                const float x = __fadd_rn(lo.x, __fmul_rn(ld.x, t)), y = __fadd_rn(lo.y, __fmul_rn(ld.y, t));
-                if (-0.5f <= x && x <= 0.5f && -0.5f <= y && y <= 0.5f) { JSRT_ACCEPT(t, 0.f) }
-            }
-            if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_SQUARE]; k < sc.atab_end[tb][AG_BOX]; ++k) {      // AABB.intersect src/geometry.js:173-179
-                JSRT_ENTRY()
-                JSRT_LOCAL_RAY()
-                float3 c = f3(0.f, 0.f, 0.f), h = f3(0.5f, 0.5f, 0.5f);
-                if (e1.x >= 0) { const float* b = sc.boxes + 8 * e1.x; c = f3(__ldg(b), __ldg(b + 1), __ldg(b + 2)); h = f3(__ldg(b + 4), __ldg(b + 5), __ldg(b + 6)); }
-                const float t = box_prim_intersect(c, h, lo, ld, minD, maxD);
-                JSRT_ACCEPT(t, 0.f)
-            }
-            if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_BOX]; k < sc.atab_end[tb][AG_SPHERE]; ++k) {      // Sphere.staticIntersect src/geometry.js:429-442
-                JSRT_ENTRY()
-                JSRT_LOCAL_RAY()
-                const float t = sphere_intersect(lo, ld, minD);
-                JSRT_ACCEPT(t, 0.f)
-            }
-            if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_SPHERE]; k < sc.atab_end[tb][AG_OTHER]; ++k) {    // every other geometry: the general code
-                if (ANY_HIT && best.prim >= 0) break;
-                JSRT_ENTRY()
-                float3 lo = o, ld = d;
-                if (e0.z >= 0) { const XformReg ma = load_xform(sc.xforms, e0.z); lo = xf_point(ma, o); ld = xf_dir(ma, d); }
-                float tl = 0.f;
-                const float t = placed_prim_intersect<HAS_SDF>(sc, e0.x, lo, ld, minD, maxD, best.t, ANY_HIT, COUNT ? &work->sdf_evals : nullptr, &tl);
-                JSRT_ACCEPT(t, tl)
-            }
-            #undef JSRT_GROUP_DONE
-            #undef JSRT_ACCEPT
-            #undef JSRT_ENTRY
-            #undef JSRT_LOCAL_RAY
-            if (!(ANY_HIT && best.prim >= 0)) {
-                float3 winv = f3(0.f, 0.f, 0.f);
-                if (sc.use_wbox) winv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                for (int b = 0; b < sc.n_bvh; ++b) {
-                    if (sc.use_wbox && !wbox_hit(sc.wboxes, b, o, winv, minD, fminf(maxD, best.t))) continue;
-                    const int4* tp = reinterpret_cast<const int4*>(sc.tops + __ldg(sc.bvh_tops + b));
-                    const int4 ta = __ldg(tp); const int first_node = __ldg(reinterpret_cast<const int*>(tp + 1));
-                    const LocalRay r = make_local_ray(load_xform(sc.xforms, ta.y), o, d);
-                    const float4* root = reinterpret_cast<const float4*>(sc.nodes + first_node);
-                    if (COUNT) ++work->nodes;
-                    if (slab_any(__ldg(root), __ldg(root + 1), r, minD, maxD, best.t)) { first_bvh = b; w_lo = r.lo; w_ld = r.ld; break; }
-                }
-            }
-            w_primary = primary;
+            analytic_hits<ANY_HIT, COUNT, HAS_SDF>(sc, o, d, minD, maxD, live, best, work);
+            if (!(ANY_HIT && best.prim >= 0)) { LocalRay lr; first_bvh = first_bvh_hit<COUNT>(sc, o, d, minD, maxD, best.t, work, lr); }
         }
         const unsigned walkers = __ballot_sync(FULL, first_bvh >= 0);
         if (walkers) {
             int base = 0;
             if (lane == 0) base = atomicAdd(io.list_count, __popc(walkers));
             base = __shfl_sync(FULL, base, 0);
-#if JSRT_WALKER_RECORDS
-            if (first_bvh >= 0) {
-                const int e = base + __popc(walkers & ((1u << lane) - 1u));
-                io.rec0[e] = make_float4(w_lo.x, w_lo.y, w_lo.z, __int_as_float(i));
-                io.rec1[e] = make_float4(w_ld.x, w_ld.y, w_ld.z, best.t);
-                io.rec2[e] = make_float4(__int_as_float(first_bvh), __int_as_float(best.top), __int_as_float(w_primary ? 1 : 0), 0.f);
-            }
-#else
             if (first_bvh >= 0) io.list[base + __popc(walkers & ((1u << lane) - 1u))] = make_int2(i, first_bvh);
-#endif
         }
         if (i < n) {
             if (io.final_pass && first_bvh < 0) finish_ray<MODE>(io, i, best, o4);
@@ -529,8 +587,20 @@ JSRT_DEV void tie_wave(const DeviceScene& sc, const TraceIO& io) {
 // Persistent threads, one ray per lane, lanes refilled individually from a warp-local pool of list
 // entries (one atomicAdd per JSRT_POOL_BATCH rays): a lane whose walk ends takes the next ray instead of
 // idling while its neighbours finish (walk lengths differ by two orders of magnitude).
-template <int MODE, bool COUNT, bool HAS_SDF>
-JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other) {
+//
+// Shared-memory staging.  The first sc.n_staged nodes of the scene's node array — the top levels of every tree, in
+// breadth-first order (scene_flatten.cpp: assembleNodes) — are copied into shared memory when the CTA starts; a node
+// step reads its 32 bytes from there when the index is below n_staged and through L1 otherwise.  Every ray walks
+// through the top levels, and a warp's 32 lanes fetch 32 different nodes: in L1 that is one wavefront per 128-byte
+// line touched (32 per load instruction, l1tex was at 51-60 % of its peak in round 1) and an L2 round trip for each
+// of the 13-17 % that miss; in shared memory it is a bank-conflicted but local access.  With one 1 024-thread CTA per
+// SM and 128 KB staged, bunny_path's tree (5.5 k nodes with two-triangle leaves) is three quarters resident.
+//
+// DIRECT (shadow rays of scenes without SDFs): the queue holds walkers only — shade_kernel has already run the analytic
+// primitives and the root boxes and accumulated or dropped every ray that needs no walk — so entry i of the queue is
+// ray i: o.xyz | pixel, d.xyz | pass, contribution.rgb | first BVH.  No work list, no partial-hit buffer.
+template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT>
+JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other, const float4* __restrict__ s_nodes) {
     constexpr bool ANY_HIT = (MODE == TM_SHADOW);
     constexpr int BATCH = JSRT_POOL_BATCH;      // list entries fetched per atomicAdd
     // A warp runs three phases per iteration, each only when enough lanes need it, so that the
@@ -541,12 +611,12 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     constexpr int PROG_T = JSRT_PROG_T;         // ... or when fewer than this many lanes can still walk
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int n = min(*io.list_count, io.cap);
+    const int n = DIRECT ? min(*io.count, io.cap) : min(*io.list_count, io.cap);
+    const int n_staged = sc.n_staged;
     int pool_next = 0, pool_end = 0;      // warp-uniform
     bool exhausted = false;               // warp-uniform
-    // per-lane ray state, kept small (64 registers at 4 CTAs / SM): the world-space ray is not kept — it is
-    // re-read from the queue in the rare case that a second BVH has to be entered — and node indices are
-    // absolute (scene_flatten.cpp stores absolute skip links), so no per-tree base pointer is carried.
+    // per-lane ray state, kept small (64 registers): the world-space ray is not kept — it is re-read from the queue in
+    // the rare case that a second BVH has to be entered — and node links are absolute, so no per-tree base is carried.
     int cur = -1;                         // >= 0: ray index, walking; -1: none; <= -2: ray -2 - cur has finished, result not yet written
     int pending = -1;                     // postponed leaf word; -(leaf + 2): a second leaf is waiting behind it
     LocalRay r; r.lo = f3(0, 0, 0); r.ld = f3(0, 0, 1); r.inv = r.ld; r.sgn = r.ld; r.par = false;
@@ -556,27 +626,21 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     float hi = CUDART_INF_F;              // min(maxD, local_best, best.t): the pruning bound of :209
     Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
     int bi = 0;
-    int node_i = 0, node_end = 0, first_prim = 0, tri_base = -1;
+    int node_i = kNodeEnd, first_prim = 0, tri_base = -1;
     float local_best = CUDART_INF_F, local_lo = 0.f; int local_prim = -1;
     Work* work = work_other;
     const float4* const all_nodes = reinterpret_cast<const float4*>(sc.nodes);
 
     // enter BVH number `bi` of the scene (Aggregate.intersect / BVHAggregate.intersect, src/aggregates.js:43-46)
-    // `local`: (o, d) is already the ray in the aggregate's space (a walker record of prims_wave)
-    auto enter = [&](float3 o, float3 d, bool local) {
+    auto enter = [&](float3 o, float3 d) {
         const int4* tp = reinterpret_cast<const int4*>(sc.tops + __ldg(sc.bvh_tops + bi));
-        const int4 ta = __ldg(tp), tb = __ldg(tp + 1);      // kind, xform, first_prim, prim_count | first_node, node_count, tri_base, n_layouts
-        if (local) {
-            r.lo = o; r.ld = d;
-            r.par = !(fabsf(d.x) > 0.0000001f) || !(fabsf(d.y) > 0.0000001f) || !(fabsf(d.z) > 0.0000001f);
-            r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-            r.sgn = f3(d.x < 0.f ? -1.f : 1.f, d.y < 0.f ? -1.f : 1.f, d.z < 0.f ? -1.f : 1.f);
-        } else r = make_local_ray(load_xform(sc.xforms, ta.y), o, d);
-        // closest-hit rays pick the layout that visits the nearer child first; any-hit (shadow) rays gain nothing from
+        const int4 ta = __ldg(tp), tb = __ldg(tp + 1);      // kind, xform, first_prim, prim_count | first_node, node_count, tri_base, layouts
+        r = make_local_ray(load_xform(sc.xforms, ta.y), o, d);
+        // closest-hit rays pick the link order that visits the nearer child first; any-hit (shadow) rays gain nothing from
         // it (measured: +18 % nodes per shadow ray on bunny_path) and keep the reference order
         // (layout 7 = higher child first on every axis = the reference's greater-child-first order)
-        const int octant = (tb.w != 8) ? 0 : ANY_HIT ? 7 : ((r.ld.x < 0.f ? 1 : 0) | (r.ld.y < 0.f ? 2 : 0) | (r.ld.z < 0.f ? 4 : 0));
-        node_i = tb.x + octant * tb.y; node_end = node_i + tb.y; first_prim = ta.z; tri_base = tb.z;
+        const int octant = ((tb.w & 0xff) != 8) ? 0 : ANY_HIT ? 7 : ((r.ld.x < 0.f ? 1 : 0) | (r.ld.y < 0.f ? 2 : 0) | (r.ld.z < 0.f ? 4 : 0));
+        node_i = tb.x + octant * (tb.w >> 8); first_prim = ta.z; tri_base = tb.z;
         local_best = CUDART_INF_F; local_prim = -1; local_lo = 0.f; pending = -1;
         hi = fminf(JSRT_MAXD, best.t);
     };
@@ -589,16 +653,8 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
             if (n_idle >= REFILL_T || idle_mask == FULL) {
                 if (cur < -1) {
                     const int ray = -2 - cur;
-#if JSRT_WALKER_RECORDS
-                    // prims_wave has stored the closest hit outside the BVHs in hits[ray]; it is replaced only by a closer
-                    // BVH hit (best.prim >= 0 means "found in a BVH": the record does not carry the earlier primitive)
-                    if (MODE == TM_EXTEND) { if (best.prim >= 0) io.hits[ray] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo); }
-                    else if (io.final_pass) finish_ray<MODE>(io, ray, best, io.o[ray]);
+                    if (DIRECT || io.final_pass) finish_ray<MODE>(io, ray, best, io.o[ray]);
                     else io.hits[ray] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
-#else
-                    if (io.final_pass) finish_ray<MODE>(io, ray, best, io.o[ray]);
-                    else io.hits[ray] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
-#endif
                     cur = -1;
                 }
                 if (pool_next >= pool_end && !exhausted) {
@@ -614,27 +670,26 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                     const int rank = __popc(idle_mask & ((1u << lane) - 1u));
                     if (rank < avail) {             // only idle lanes have a rank that is meaningful: cur < 0 here for them
                         if (cur < 0) {
-#if JSRT_WALKER_RECORDS
-                            const int e = pool_next + rank;
-                            const float4 r0 = __ldcs(io.rec0 + e), r1 = __ldcs(io.rec1 + e), r2 = __ldcs(io.rec2 + e);
-                            cur = __float_as_int(r0.w); bi = __float_as_int(r2.x);
-                            const bool primary = __float_as_int(r2.z) != 0;
-                            minD_v = (MODE == TM_EXTEND && primary) ? 0.f : 0.0001f;
-                            if (COUNT) work = primary ? work_primary : work_other;
-                            best.t = r1.w; best.prim = -1; best.top = __float_as_int(r2.y); best.t_lo = 0.f;
-                            enter(f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), true);
-#else
-                            const int2 e = __ldg(reinterpret_cast<const int2*>(io.list) + pool_next + rank);
-                            cur = e.x; bi = e.y;
-                            const float4 o4 = io.o[cur], d4 = io.d[cur], h4 = io.hits[cur];
-                            bool primary; float mx;
-                            ray_window<MODE>(d4, minD_v, mx, primary);
-                            if (COUNT) work = primary ? work_primary : work_other;
-                            best.t = h4.x; best.prim = __float_as_int(h4.y); best.top = __float_as_int(h4.z); best.t_lo = h4.w;
-                            enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), false);
-#endif
-                            // prims_wave has tested this tree's root box; an inner root needs no second test
-                            if (__float_as_int(__ldg(all_nodes + 2 * node_i + 1).w) == -1) ++node_i;
+                            float4 o4, d4;
+                            if (DIRECT) {
+                                cur = pool_next + rank;
+                                o4 = io.o[cur]; d4 = io.d[cur];
+                                bi = __float_as_int(io.c[cur].w);
+                                best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
+                            } else {
+                                const int2 e = __ldg(reinterpret_cast<const int2*>(io.list) + pool_next + rank);
+                                cur = e.x; bi = e.y;
+                                o4 = io.o[cur]; d4 = io.d[cur];
+                                const float4 h4 = io.hits[cur];
+                                bool primary; float mx;
+                                ray_window<MODE>(d4, minD_v, mx, primary);
+                                if (COUNT) work = primary ? work_primary : work_other;
+                                best.t = h4.x; best.prim = __float_as_int(h4.y); best.top = __float_as_int(h4.z); best.t_lo = h4.w;
+                            }
+                            enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
+                            // the producer has tested this tree's root box; an inner root needs no second test
+                            const int root_word = __float_as_int(__ldg(all_nodes + 2 * node_i + 1).w);
+                            if (root_word < 0) node_i = root_word & 0x7fffffff;
                         }
                     }
                     pool_next += min(avail, n_idle);
@@ -651,7 +706,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
         // walk (the others are parked, blocked or idle): a blocked or finished lane waits for company instead of
         // dragging the whole warp through the triangle code with a handful of lanes.
         const unsigned pend_mask = __ballot_sync(FULL, active && pending != -1);
-        const unsigned prog_mask = __ballot_sync(FULL, active && node_i < node_end && pending >= -1);
+        const unsigned prog_mask = __ballot_sync(FULL, active && node_i != kNodeEnd && pending >= -1);
         if (pend_mask && (__popc(pend_mask) >= LEAF_T || __popc(prog_mask) < PROG_T)) {
             if (active && pending != -1) {
                 const int leaf = (pending < -1) ? -(pending + 2) : pending;      // a blocked lane stores -(leaf + 2)
@@ -689,12 +744,12 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 // (closest-hit: the bound keeps 2 ppm of slack so that a candidate tied with the current hit in FP32 still
                 // reaches the tie-break above; acceptance itself compares against local_best)
                 hi = fminf(hi, (ANY_HIT || !JSRT_TRI_TIE) ? local_best : fmaf(fabsf(local_best), 2e-6f, local_best));
-                if (ANY_HIT && local_prim >= 0) node_i = node_end;
+                if (ANY_HIT && local_prim >= 0) node_i = kNodeEnd;
             }
         }
 
         if (active) {
-            if (node_i >= node_end && pending == -1) {
+            if (node_i == kNodeEnd && pending == -1) {
                 // ---- tree finished: merge into the running closest hit, next BVH or done -------
                 const int top_i = __ldg(sc.bvh_tops + bi);
                 if (local_best > JSRT_MIND && local_best < JSRT_MAXD && better_hit(local_best, top_i, best)) {
@@ -710,29 +765,24 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                         while (bi < sc.n_bvh && !wbox_hit(sc.wboxes, bi, f3(o4.x, o4.y, o4.z), winv, JSRT_MIND, whi)) ++bi;
                     }
                     if (bi >= sc.n_bvh) cur = -2 - cur;
-                    else enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), false);
+                    else enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
                 }
             } else {
                 // ---- phase 3: up to NODE_STEPS nodes of BVHAggregateNode.intersect (src/aggregates.js:207-225)
                 // per iteration, so the warp votes of phases 1-2 are paid once per few nodes
                 #pragma unroll 1
-                for (int rep = 0; rep < NODE_STEPS && node_i < node_end && pending >= -1; ++rep) {
+                for (int rep = 0; rep < NODE_STEPS && node_i != kNodeEnd && pending >= -1; ++rep) {
                     float4 n0, n1;
-                    load_node(all_nodes + 2 * node_i, n0, n1);
-#if JSRT_NODE_PREFETCH & 1
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(all_nodes + 2 * node_i + 2));      // the hit successor
-#endif
-                    const int skip = __float_as_int(n1.z), leaf = __float_as_int(n1.w);
-#if JSRT_NODE_PREFETCH & 2
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(all_nodes + 2 * skip));            // the miss successor
-#endif
+                    if (node_i < n_staged) { n0 = s_nodes[2 * node_i]; n1 = s_nodes[2 * node_i + 1]; }
+                    else load_node(all_nodes + 2 * node_i, n0, n1);
+                    const int skip = __float_as_int(n1.z), word = __float_as_int(n1.w);
                     if (COUNT) ++work->nodes;
                     const bool hit_box = r.par ? slab_general(n0, n1, r, JSRT_MIND, JSRT_MAXD, hi) : slab_fast(n0, n1, r, JSRT_MIND, hi);
                     if (hit_box) {
-                        if (leaf != -1) {
-                            if (pending == -1) { pending = leaf; node_i = skip; }
+                        if (word >= 0) {            // leaf
+                            if (pending == -1) { pending = word; node_i = skip; }
                             else pending = -(pending + 2);      // one leaf already parked: block here until it is tested
-                        } else ++node_i;
+                        } else node_i = word & 0x7fffffff;      // inner: the hit link
                     } else node_i = skip;
                 }
             }

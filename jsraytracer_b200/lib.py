@@ -68,7 +68,7 @@ EXPORTS = [
     "jsrt_stats_get", "jsrt_stats_reset", "jsrt_set_profiling", "jsrt_last_error", "jsrt_bvh_build",
     "jsrt_bvh_node_count", "jsrt_bvh_leaf_object_count", "jsrt_bvh_copy", "jsrt_bvh_free", "jsrt_measure_read_bandwidth",
     "jsrt_bvh_world_boxes", "jsrt_obj_parse", "jsrt_obj_error", "jsrt_obj_counts", "jsrt_obj_copy", "jsrt_obj_material_name",
-    "jsrt_obj_mtllib", "jsrt_obj_free",
+    "jsrt_obj_mtllib", "jsrt_obj_free", "jsrt_accum_export", "jsrt_accum_attach",
 ]
 
 
@@ -100,6 +100,8 @@ def load():
     L.jsrt_accum_device_ptr.restype = vp
     L.jsrt_accum_device_ptr.argtypes = [vp]
     L.jsrt_add_passes.argtypes = [vp, i32]
+    L.jsrt_accum_export.argtypes = [vp, vp]
+    L.jsrt_accum_attach.argtypes = [vp, vp, i32]
     L.jsrt_primary_hits.argtypes = [vp, vp, vp]
     L.jsrt_scene_info.argtypes = [vp, vp]
     L.jsrt_stats_get.argtypes = [vp, vp]
@@ -153,8 +155,9 @@ def device_count():
 class Scene:
     """Owns one `jsrt_scene*`."""
 
-    def __init__(self, blob: bytes, fmt: int = FORMAT_MSGPACK, device: int | None = 0):
-        """device=None: parse + flatten only (no CUDA); rendering then fails."""
+    def __init__(self, blob: bytes, fmt: int = FORMAT_MSGPACK, device=0):
+        """device=None: parse + flatten only (no CUDA); rendering then fails.  A list / tuple of device indices
+        replicates the scene on all of them (jsrt_scene_create with ndev > 1)."""
         self._L = load()
         if isinstance(blob, str):
             blob = blob.encode("utf8")
@@ -162,8 +165,9 @@ class Scene:
         if device is None:
             self._h = self._L.jsrt_scene_create_host(buf, len(blob), fmt)
         else:
-            dev = (C.c_int * 1)(device)
-            self._h = self._L.jsrt_scene_create(buf, len(blob), fmt, dev, 1)
+            devs = list(device) if isinstance(device, (list, tuple)) else [device]
+            dev = (C.c_int * len(devs))(*devs)
+            self._h = self._L.jsrt_scene_create(buf, len(blob), fmt, dev, len(devs))
         if not self._h:
             raise JsrtError(last_error())
         self.info = self.get_info()
@@ -239,6 +243,19 @@ class Scene:
 
     def accum_device_ptr(self):
         return self._L.jsrt_accum_device_ptr(self._h)
+
+    def accum_export(self) -> bytes:
+        """64-byte CUDA IPC handle of the accumulation buffer (one process per GPU: jsrt_accum_export)."""
+        h = (C.c_ubyte * 64)()
+        self._ck(self._L.jsrt_accum_export(self._h, h))
+        return bytes(h)
+
+    def accum_attach(self, handles):
+        """Map other processes' accumulation buffers (list of 64-byte handles) as peers of this scene."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        buf = (C.c_ubyte * max(1, len(blob))).from_buffer_copy(blob or b"\0")
+        self._ck(self._L.jsrt_accum_attach(self._h, buf, len(handles)))
 
     def add_passes(self, n):
         self._ck(self._L.jsrt_add_passes(self._h, n))

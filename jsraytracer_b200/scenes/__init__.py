@@ -367,6 +367,30 @@ def Aggregates(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=In
     return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
 
 
+# Not a reference test file: aggregates nested the ways the reference's API allows (src/aggregates.js:14-18,43-49 —
+# `ancestors.unshift(this)` at every level) and none of its own scenes exercises: a BVHAggregate as a member of a plain
+# Aggregate (next to a Primitive), and a BVHAggregate built over two instances of another BVHAggregate plus a Primitive
+# (BVHAggregate.build accepts any WorldObject with a finite bounding box, src/aggregates.js:34-42).
+def nested_aggregates(aspect=1, width=600, height=600, spp=16, depth=4, renderer_cls=IncrementalMultisamplingRenderer):
+    camera = PerspectiveCamera(PI / 4, aspect, Mat4.translation([0, 1.2, 6]).times(Mat4.rotation(-0.15, Vec.of(1, 0, 0))))
+    lights = [SimplePointLight(Vec.of(8, 9, 10, 1), Vec.of(1, 1, 1), 6000)]
+    objs = [_checker_floor(PhongMaterial, (CheckerboardMaterialColor(Vec.of(1, 1, 1), Vec.of(0.1, 0.1, 0.1)),
+                                           0.2, 0.4, 0.6, 100, 0.4), y=-1)]
+    tris = load_mesh("tetrahedron", PhongMaterial(Vec.of(1, 0.3, 0.2), 0.2, 0.5, 0.5, 50, 0.3))
+    mesh = BVHAggregate.build(tris, Mat4.translation([-1.6, 0, -4]).times(Mat4.rotation(0.5, Vec.of(0, 1, 0))))
+    ball = Primitive(Sphere(), PhongMaterial(Vec.of(0.2, 0.3, 1), 0.2, 0.4, 0.6, 100, 0.5), Mat4.translation([1.4, 0.2, -1.5]).times(Mat4.scale(0.6)))
+    # a BVHAggregate and a Primitive inside a plain, transformed Aggregate
+    objs.append(Aggregate([ball, mesh, Primitive(UnitBox(), PhongMaterial(Vec.of(0.2, 0.9, 0.3), 0.2, 0.4, 0.6, 100, 0.3),
+                                                 Mat4.translation([0, -0.5, -6]))],
+                          Mat4.translation([0.3, 0, 0]).times(Mat4.rotation(0.2, Vec.of(0, 1, 0)))))
+    # a BVHAggregate over two more instances of the same tree and a Primitive
+    inst = [BVHAggregate(tris, mesh.kdtree, Mat4.translation([x, 0.1, -7]).times(Mat4.rotation(0.4 * x, Vec.of(0, 1, 0))).times(Mat4.scale(1.3)))
+            for x in (-2.5, 2.2)]
+    moon = Primitive(Sphere(), FresnelPhongMaterial(Vec.of(1, 1, 0.4), 0.1, 0.4, 0.5, 100, 1.4), Mat4.translation([0, 2.4, -7]).times(Mat4.scale(0.8)))
+    objs.append(BVHAggregate.build(inst + [moon], Mat4.translation([0, 0.2, 0])))
+    return _finish(objs, lights, camera, renderer_cls, spp, depth, width, height, bg=Vec.of(0.1, 0.1, 0.15))
+
+
 # Stand-in for the scale of BASELINE configs[4] (tests/toledo: asset missing): a 3 x 3 x 3 grid of
 # dragon instances sharing one kdtree (27 x 99 968 = 2.7 M triangle instances), built with the reference's own
 # instancing idiom `new BVHAggregate(triangles, bvh.kdtree, transform)` (tests/starwars/test.mjs:57-62).
@@ -645,7 +669,7 @@ def SDF_SphereRepetition(aspect=1, width=600, height=600, spp=16, depth=4, dof=N
 
 REGISTRY = {f.__name__: f for f in (
     BoxBall, BoxBall_DOF, BoxBall_path, ASimpleScene, spheres010, refraction, refraction_path, cornell_box_path,
-    bunny, bunny_path, dragon, AHollowTetrahedron, starwars, tie_fighter, textured, Aggregates, dragon_grid, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
+    bunny, bunny_path, dragon, AHollowTetrahedron, starwars, tie_fighter, textured, Aggregates, nested_aggregates, dragon_grid, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
     SDF_Sierpinski, spheres050, spheres100, refraction_simple, cornell_box, cornell_box_emissive, AMultipleBVH, cat, diamond, heart,
     utah_teapot, x_wing, SDF_SphereRepetition, bottle)}
 
