@@ -104,7 +104,7 @@ int jsrt_read_accum(jsrt_scene*, float* out, int* passes);
  * like its display pass does), w = number of samples whose camera ray hit something.  Zero if no AOV pass was rendered. */
 int jsrt_read_aov(jsrt_scene*, float* normal_depth, float* variance);
 
-/* One process per GPU (torchrun-style launches): every process exports its accumulation buffer as a 64-byte CUDA
+/* One process per GPU: every process exports its accumulation buffer as a 64-byte CUDA
  * IPC handle (jsrt_accum_export), the handles travel over the host's own channel, and the process that owns the image
  * maps the others' buffers with jsrt_accum_attach(handles = n x 64 bytes); from then on its jsrt_resolve_rgba8 /
  * jsrt_read_accum sum them like the helper devices of an ndev > 1 scene.  The caller orders the processes (a barrier

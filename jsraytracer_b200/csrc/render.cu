@@ -608,9 +608,15 @@ struct Renderer::Impl {
         stream = own_stream;
         uploadScene();
         has_sdf = !hs.sdfs.empty();
-        // shadow tests fused into shade_kernel (scenes without SDFs: an SDF march cannot run inside the shade loop)
-        fuse_shadow = !has_sdf && envInt("JSRT_FUSE_SHADOW", 1) != 0;
+        // Shadow tests fused into shade_kernel: scenes without SDFs (a march cannot run inside the shade loop) whose shadow
+        // rays mostly die at a BVH root box and meet few analytic shadow casters.  Measured (profiles/r2_ab.md): bunny_path
+        // (1 plane, 2 point lights) shade + shadow 19.5 -> 18.7 ms per 16 passes; cornell_box_path (12 analytic primitives,
+        // 4 light samples, no BVH) 21.0 -> 23.7 ms — there the tests run better in prims_kernel<shadow>, one compacted ray
+        // per lane at 4 CTAs / SM, than under shade's 80 registers with only the lit lanes of each warp at work.
+        const int n_shadow_casters = ds.atab_end[1][AG_COUNT - 1] - ds.atab_end[0][AG_COUNT - 1];
+        fuse_shadow = !has_sdf && envInt("JSRT_FUSE_SHADOW", (ds.n_bvh > 0 && n_shadow_casters <= 4) ? 1 : 0) != 0;
         fuse_gen = envInt("JSRT_FUSE_GEN", 1) != 0;
+        coalesce = envInt("JSRT_COALESCE", 1) != 0;
         const size_t npix = (size_t)hs.width * hs.height;
         accum = dalloc<float4>(npix);
         CK(cudaMemsetAsync(accum, 0, npix * sizeof(float4), stream));
@@ -880,10 +886,32 @@ struct Renderer::Impl {
         }
     }
 
-    void render(int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags) {
-        CK(cudaSetDevice(device));
+    // Submission coalescing.  jsrt_render is asynchronous, and small waves are slow (the persistent trace kernels end with a
+    // tail of long walks: 2.75 / 3.9 Grays/s at 1 / 16 passes per wave on bunny_path), so consecutive calls that continue
+    // each other — same seed, striping and flags, first_pass = the previous call's end — are held back and rendered as one
+    // wave once a full batch is pending or anything observes the scene (synchronize, resolve, read-back, statistics,
+    // upload, reset).  A host that hands over one pass per call (the reference's per-pass loop, src/renderers.js:87; a
+    // strong-scaling split that leaves each GPU two passes per step) gets big waves anyway.  JSRT_COALESCE=0 disables.
+    struct Pending { bool any = false; int first = 0, n = 0; uint64_t seed = 0; int x_offset = 0, x_delt = 1, flags = 0; } pend;
+    bool coalesce = true;
+    void submit(int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags) {
         if (hs.max_depth <= 0 || hs.max_depth > 255) throw std::runtime_error("jsrt: maxRecursionDepth must be in 1..255");
         if (x_offset < 0) throw std::runtime_error("jsrt: x_offset must be >= 0");
+        if (x_delt < 1) x_delt = 1;
+        if (pend.any && !(seed == pend.seed && x_offset == pend.x_offset && x_delt == pend.x_delt && flags == pend.flags && first_pass == pend.first + pend.n)) flush();
+        if (!pend.any) { pend.any = true; pend.first = first_pass; pend.n = 0; pend.seed = seed; pend.x_offset = x_offset; pend.x_delt = x_delt; pend.flags = flags; }
+        pend.n += n_passes;
+        if (x_offset == 0 && x_delt == 1) passes += n_passes; else passes = std::max(passes, first_pass + n_passes);
+        const long long ncols = x_offset < hs.width ? (hs.width - x_offset + x_delt - 1) / x_delt : 0;
+        if (!coalesce || (flags & 6) || ncols * hs.height * (long long)pend.n >= (long long)batch) flush();
+    }
+    void flush() {
+        if (!pend.any) return;
+        pend.any = false;
+        renderNow(pend.first, pend.n, pend.seed, pend.x_offset, pend.x_delt, pend.flags);
+    }
+    void renderNow(int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags) {
+        CK(cudaSetDevice(device));
         GenParams g = genParams(first_pass, seed, x_offset, x_delt, flags);
         const bool count_work = (flags & 2) != 0;
         const bool aov = (flags & 4) != 0;
@@ -924,7 +952,6 @@ struct Renderer::Impl {
             }
         }
         CK(cudaGetLastError());
-        if (x_offset == 0 && g.x_delt == 1) passes += n_passes; else passes = std::max(passes, first_pass + n_passes);
     }
 
     // peers' work must be finished before their buffers are read: the caller orders that (events / barriers)
@@ -936,12 +963,14 @@ struct Renderer::Impl {
 
 Renderer::Renderer(const HostScene& hs, int device, size_t queue_budget) : impl_(new Impl(hs)) { impl_->init(device, queue_budget); }
 Renderer::~Renderer() { delete impl_; }
-void Renderer::render(int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags) { impl_->render(first_pass, n_passes, seed, x_offset, x_delt, flags); }
-void Renderer::upload() { CK(cudaSetDevice(impl_->device)); impl_->uploadScene(); CK(cudaStreamSynchronize(impl_->stream)); }
-void Renderer::setStream(void* s) { impl_->stream = s ? (cudaStream_t)s : impl_->own_stream; impl_->applyAccumPersistence(); }
+void Renderer::render(int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags) { impl_->submit(first_pass, n_passes, seed, x_offset, x_delt, flags); }
+void Renderer::flushPending() { impl_->flush(); }
+void Renderer::upload() { impl_->flush(); CK(cudaSetDevice(impl_->device)); impl_->uploadScene(); CK(cudaStreamSynchronize(impl_->stream)); }
+void Renderer::setStream(void* s) { impl_->flush(); impl_->stream = s ? (cudaStream_t)s : impl_->own_stream; impl_->applyAccumPersistence(); }
 void* Renderer::stream() const { return (void*)impl_->stream; }
 int Renderer::device() const { return impl_->device; }
 void Renderer::synchronize() {
+    impl_->flush();
     CK(cudaSetDevice(impl_->device)); CK(cudaStreamSynchronize(impl_->stream));
     int ov = 0; CK(cudaMemcpy(&ov, impl_->overflow, sizeof(int), cudaMemcpyDeviceToHost));
     if (ov) {
@@ -951,6 +980,7 @@ void Renderer::synchronize() {
     }
 }
 void Renderer::resetAccum() {
+    impl_->flush();
     CK(cudaSetDevice(impl_->device));
     CK(cudaMemsetAsync(impl_->accum, 0, (size_t)impl_->hs.width * impl_->hs.height * sizeof(float4), impl_->stream));
     CK(cudaMemsetAsync(impl_->overflow, 0, sizeof(int), impl_->stream));
@@ -961,6 +991,7 @@ void Renderer::resetAccum() {
     }
 }
 void Renderer::readAov(float* normal_depth, float* variance) {
+    impl_->flush();
     CK(cudaSetDevice(impl_->device));
     const size_t bytes = (size_t)impl_->hs.width * impl_->hs.height * sizeof(float4);
     if (!impl_->aov_nd) { memset(normal_depth, 0, bytes); memset(variance, 0, bytes); return; }
@@ -969,6 +1000,7 @@ void Renderer::readAov(float* normal_depth, float* variance) {
     synchronize();
 }
 void Renderer::resolve(uint8_t* out) {
+    impl_->flush();
     CK(cudaSetDevice(impl_->device));
     const int npix = impl_->hs.width * impl_->hs.height;
     resolve_kernel<<<(npix + 255) / 256, 256, 0, impl_->stream>>>(impl_->accum, impl_->peers, impl_->rgba, npix); ++impl_->launches;
@@ -976,6 +1008,7 @@ void Renderer::resolve(uint8_t* out) {
     synchronize();
 }
 void Renderer::readAccum(float* out, int* passes) {
+    impl_->flush();
     CK(cudaSetDevice(impl_->device));
     Impl& m = *impl_;
     const size_t npix = (size_t)m.hs.width * m.hs.height;
@@ -1015,6 +1048,7 @@ void Renderer::attachAccum(const void* handles64, int n) {
     }
 }
 void Renderer::primaryHits(int32_t* prim_id, float* t) {
+    impl_->flush();
     CK(cudaSetDevice(impl_->device));
     Impl& m = *impl_;
     GenParams g = m.genParams(0, 0, 0, 1, 1);
@@ -1049,7 +1083,7 @@ void Renderer::resetStats() {
     impl_->flushEvents();
     impl_->launches = 0; for (double& m : impl_->ms) m = 0; for (auto& k : impl_->kernel_launches) k = 0;
 }
-void Renderer::setProfiling(bool on) { impl_->profiling = on; }
+void Renderer::setProfiling(bool on) { impl_->flush(); impl_->profiling = on; }
 int Renderer::passes() const { return impl_->passes; }
 int Renderer::batchSamples() const { return impl_->batch; }
 size_t Renderer::sceneBytes() const { return impl_->scene_bytes; }
@@ -1094,6 +1128,7 @@ void enablePeerAccess(int a, int b) {
     if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else CK(e);
 }
 void orderAfter(Renderer& consumer, Renderer& producer) {
+    producer.flushPending();
     cudaEvent_t ev;
     CK(cudaSetDevice(producer.device()));
     CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));

@@ -22,6 +22,7 @@ public:
     Renderer(const HostScene& hs, int device, size_t queue_budget_bytes);
     ~Renderer();
     void render(int first_pass, int n_passes, uint64_t seed, int x_offset, int x_delt, int flags);
+    void flushPending();          // launches what jsrt_render calls have been holding back (submission coalescing, render.cu)
     void upload();
     void setStream(void* cuda_stream);
     void synchronize();

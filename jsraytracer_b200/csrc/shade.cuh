@@ -77,12 +77,24 @@ JSRT_DEV float3 color_eval(const DeviceScene& sc, const Color& c, const SurfaceD
 JSRT_DEV float2 cartesian_to_spherical(float3 n) {
     return make_float2(0.5f + atan2f(n.z, n.x) / (2.f * CUDART_PI_F), 0.5f - asinf(n.y) / CUDART_PI_F);
 }
-// Vec.spherePick src/math.js:180-188
+// Vec.spherePick src/math.js:180-188: theta = 2 pi u0, phi = acos(2 u1 - 1), (cos theta sin phi, cos phi, sin theta sin phi).
+// cos(acos x) = x and sin(acos x) = sqrt(1 - x^2), and sin / cos of 2 pi u0 come from the pi-scaled routine (exact argument
+// reduction, no slow path): the same point to FP32 rounding, a fifth of the instructions of acosf + sincosf + sinf + cosf
+// (shade_kernel lost 40 % of its stall samples to instruction fetch: profiles/r2_ncu_summary.md).
 JSRT_DEV float3 sphere_pick(float u0, float u1) {
-    const float theta = 2.0f * CUDART_PI_F * u0, phi = acosf(2.0f * u1 - 1.0f);
-    float st, ct; sincosf(theta, &st, &ct);
-    const float sin_phi = sinf(phi);
-    return f3(ct * sin_phi, cosf(phi), st * sin_phi);
+    const float c = 2.0f * u1 - 1.0f, sin_phi = sqrtf(fmaxf(0.f, 1.0f - c * c));
+    float st, ct; sincospif(2.0f * u0, &st, &ct);
+    return f3(ct * sin_phi, c, st * sin_phi);
+}
+// Math.pow(base, exponent) for base >= 0 (a clamped cosine) and a finite exponent >= 0 (smoothness): exp2(e log2 b) on the
+// special-function unit.  Relative error ~ e * 2^-22 (1e-5 at smoothness 100), far below the image tolerance; the general
+// powf is ~150 instructions with several slow paths.  Math.pow(x, 0) = 1 for every x including 0 (src/materials.js:390
+// defaults smoothness to 0), Math.pow(0, e > 0) = 0.
+JSRT_DEV float pow_clamped(float b, float e) {
+    if (e == 0.f) return 1.f;
+    if (!(b > 0.f)) return (b == 0.f) ? 0.f : powf(b, e);          // NaN / negative: the library's answer
+    if (!(e < 3.0e38f)) return powf(b, e);                            // infinite smoothness
+    return exp2f(e * __log2f(b));
 }
 
 // SDF material program (sdf_compile.cpp): root_sdf.getMaterialData(p) -> basecolor, UV.
@@ -273,14 +285,14 @@ JSRT_DEV float3 color_from_light_sample(const Material& m, const PhongFactors& f
     float diffuse, specular;
     if (m.kind == M_PHONG) {
         diffuse = fmaxf(dot3(L, f.N), 0.f);
-        specular = powf(fmaxf(dot3(L, f.R), 0.f), f.smoothness);
+        specular = pow_clamped(fmaxf(dot3(L, f.R), 0.f), f.smoothness);
     } else {
         const float ldotn = dot3(L, f.N);
         diffuse = 0.f; specular = 0.f;
-        if (f.kr > 0.f && ldotn >= 0.f) { diffuse += f.kr * ldotn; specular += f.kr * powf(fmaxf(dot3(L, f.R), 0.f), f.smoothness); }
+        if (f.kr > 0.f && ldotn >= 0.f) { diffuse += f.kr * ldotn; specular += f.kr * pow_clamped(fmaxf(dot3(L, f.R), 0.f), f.smoothness); }
         if (f.kr < 1.f && ldotn <= 0.f) {
             diffuse += (1.f - f.kr) * -ldotn;
-            specular += (1.f - f.kr) * powf(fmaxf(f.has_refr ? dot3(L, f.refr) : 0.f, 0.f), f.smoothness);
+            specular += (1.f - f.kr) * pow_clamped(fmaxf(f.has_refr ? dot3(L, f.refr) : 0.f, 0.f), f.smoothness);
         }
     }
     return ls.color * (f.diffusivity * diffuse) + ls.color * (f.specularity * specular);

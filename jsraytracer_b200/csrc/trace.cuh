@@ -534,6 +534,12 @@ JSRT_DEV void load_node(const float4* p, float4& a, float4& b) {
 #endif
 }
 
+// the same from the staged block in shared memory (32-bit shared-window address)
+JSRT_DEV void lds_node(unsigned addr, float4& a, float4& b) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(addr));
+}
+
 // Two triangles of one mesh whose FP32 hit distances agree to the last bits (a ray through coincident or overlapping
 // coplanar faces, or through a shared edge: both pass the inside test).  The reference decides `t < ret.distance`
 // (src/aggregates.js:213) on f64 distances computed from f32 vectors, so the winner is settled by rounding noise ~1e-8
@@ -630,6 +636,9 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     float local_best = CUDART_INF_F, local_lo = 0.f; int local_prim = -1;
     Work* work = work_other;
     const float4* const all_nodes = reinterpret_cast<const float4*>(sc.nodes);
+    // 32-bit shared-window address of the staged block, formed once (the generic pointer made the compiler rebuild it
+    // from SR_CgaCtaId at every node step: 4 of the 52 instructions of the loop)
+    const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_nodes);
 
     // enter BVH number `bi` of the scene (Aggregate.intersect / BVHAggregate.intersect, src/aggregates.js:43-46)
     auto enter = [&](float3 o, float3 d) {
@@ -773,7 +782,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 #pragma unroll 1
                 for (int rep = 0; rep < NODE_STEPS && node_i != kNodeEnd && pending >= -1; ++rep) {
                     float4 n0, n1;
-                    if (node_i < n_staged) { n0 = s_nodes[2 * node_i]; n1 = s_nodes[2 * node_i + 1]; }
+                    if (node_i < n_staged) lds_node(s_base + 32u * (unsigned)node_i, n0, n1);
                     else load_node(all_nodes + 2 * node_i, n0, n1);
                     const int skip = __float_as_int(n1.z), word = __float_as_int(n1.w);
                     if (COUNT) ++work->nodes;

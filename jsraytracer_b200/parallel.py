@@ -24,6 +24,12 @@ def pass_block(step: int, rank: int, world: int, passes_per_step: int):
     return first, passes_per_step
 
 
+def strong_share(passes_per_step: int, rank: int, world: int) -> int:
+    """Strong scaling of a fixed frame: how many of a step's `passes_per_step` passes `rank` renders (the shares differ by
+    at most one and add up to the step)."""
+    return passes_per_step // world + (1 if rank < passes_per_step % world else 0)
+
+
 def shard_passes(total_passes: int, rank: int, world: int):
     """Strong-scaling split of `total_passes` pass indices: rank r gets {p : p % world == r}
     as a list of (first_pass, n_passes) runs of length 1."""

@@ -133,15 +133,17 @@ def _cuda_render(renderer, img, timelimit, callback, x_offset, x_delt):
         spp = 1
     flags = 0 if jitter else lib.FLAG_NO_JITTER
     seed = getattr(renderer, "_seed", 1)
-    step = getattr(renderer, "_passes_per_call", None) or (1 if (timelimit and callback) else spp)
+    # One library call per pass, like the reference's loop (src/renderers.js:87): the library coalesces consecutive
+    # calls into full waves.  With a progress callback the passes go out in groups of 8 and the host synchronises once
+    # per group — not per pass — to look at the clock (src/renderers.js:103-112: at most one callback per `timelimit` ms).
+    group = getattr(renderer, "_passes_per_call", None) or 8
     scene.reset_accum()
     last = time.monotonic()
     done = 0
     while done < spp:
-        n = min(step, spp - done)
-        scene.render(done, n, seed, x_offset, x_delt, flags)
-        done += n
-        if timelimit and callback:
+        scene.render(done, 1, seed, x_offset, x_delt, flags)
+        done += 1
+        if timelimit and callback and (done % group == 0 or done == spp):
             scene.synchronize()
             now = time.monotonic()
             if (now - last) * 1000.0 >= timelimit:

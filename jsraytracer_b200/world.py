@@ -96,7 +96,8 @@ class BVHAggregate(Aggregate):  # src/aggregates.js:26-61
             if not o.getBoundingBox().isFinite():
                 raise ValueError("Infinite objects not allowed in")
         if native is None:
-            native = len(objects) > 2000
+            import os
+            native = len(objects) > 2000 and not os.environ.get("JSRT_PY_BVH")     # JSRT_PY_BVH=1: never touch the native library
         if native:
             from . import bvh_native
             tree = bvh_native.build_tree(objects, maxDepth, minNodeSize)

@@ -111,7 +111,9 @@ def test_cornell_box_path_converges_to_oracle_mean():
     """north_star: "path-traced images converge to within a stated per-pixel 3 sigma tolerance of a high-spp reference
     render".  Reference R = 384-spp oracle render with its per-pixel sample variance; tolerance
     |mean_64 - R| <= 3 sqrt(var / 64 + var / 384) + 2e-3 per channel.  The GPU's 64-spp mean (its own seed) must satisfy
-    it on >= 97 % of the pixels and on no fewer (-1 %) than an independent 64-spp oracle render does."""
+    it on no fewer pixels (-1 %) than an independent 64-spp *oracle* render does — this scene's samples are heavy-tailed (a
+    small area light seen through depth-8 paths), so a Gaussian 3 sigma bound is missed by the reference itself on ~7 % of
+    the pixels (measured: control 0.930, CUDA 0.930); the control run sets the achievable rate, 90 % is the floor."""
     W = H = 64
     sc, orc = _pair("cornell_box_path", width=W, height=H)
     n, nref = 64, 384
@@ -127,5 +129,5 @@ def test_cornell_box_path_converges_to_oracle_mean():
     ctrl = orc.render(n, seed=4242)[0] / n
     frac_gpu = float((np.abs(g - ref) <= tol).all(axis=-1).mean())
     frac_ctrl = float((np.abs(ctrl - ref) <= tol).all(axis=-1).mean())
-    assert frac_gpu >= 0.97 and frac_gpu >= frac_ctrl - 0.01, (frac_gpu, frac_ctrl)
+    assert frac_gpu >= 0.90 and frac_gpu >= frac_ctrl - 0.01, (frac_gpu, frac_ctrl)
     assert abs(float(g.mean()) - float(ref.mean())) < 0.01 * float(ref.mean()) + 1e-3

@@ -100,3 +100,11 @@ def test_pass_block_and_shard_helpers():
     assert sorted(seen) == list(range(96))
     allp = sum([[p for p, _ in shard_passes(10, r, 3)] for r in range(3)], [])
     assert sorted(allp) == list(range(10))
+
+
+def test_strong_share_partitions_a_step():
+    from jsraytracer_b200.parallel import strong_share
+    for P in (1, 2, 7, 16, 33):
+        for world in (1, 2, 3, 4, 8, 16):
+            shares = [strong_share(P, r, world) for r in range(world)]
+            assert sum(shares) == P and max(shares) - min(shares) <= 1 and shares == sorted(shares, reverse=True)
