@@ -312,7 +312,8 @@ def run_ours(args):
     kern_ms = {"generate": st["ms_generate"], "extend": st["ms_extend"], "shade": st["ms_shade"], "shadow": st["ms_shadow"]}
     kern_n = {"generate": st["n_generate"], "extend": st["n_extend"], "shade": st["n_shade"], "shadow": st["n_shadow"]}
     part_ms = {k: st["ms_" + k] for k in ("extend_prims", "extend_bvh", "extend_sdf", "shadow_prims", "shadow_bvh", "shadow_sdf")}
-    dominant = max(("extend", "shadow"), key=lambda k: kern_ms[k])
+    has_walk = (part_ms["extend_bvh"] + part_ms["shadow_bvh"]) > 0.05 * (kern_ms["extend"] + kern_ms["shadow"])
+    dominant = max(("extend", "shadow"), key=lambda k: part_ms[k + "_bvh"] if has_walk else kern_ms[k])     # the wave whose walk kernel is the longest
     if dominant == "extend":
         o_rays = ocnt["rays_primary"] + ocnt["rays_secondary"]
         o_nodes = ocnt["bvh_nodes_primary"] + ocnt["bvh_nodes_secondary"]
@@ -398,7 +399,7 @@ def run_ours(args):
         _k("bvh_kernel<extend>", st["ms_extend_bvh"], n_ext * ext_bpr, l2_peak, "l2", ext_bpr, "rays (reference nodes x 32 B + triangles x 36 B)"),
         _k("shade_kernel", st["ms_shade"], n_ext * 64.0 + n_sec * 48.0 + st["shaded_hits"] * 16.0, hbm_peak, "hbm", None,
            "64 B per ray read, 48 B per child (and per shadow walker, not counted) written, 16 B reduction per shaded hit"),
-        _k("prims_kernel<shadow>", st["ms_shadow_prims"], 0.0 if st["ms_shadow_prims"] < 1e-3 * max(1.0, st["ms_shade"]) else n_sh * 48.0, hbm_peak, "hbm", 48,
+        _k("prims_kernel<shadow>", st["ms_shadow_prims"], 0.0 if st["ms_shadow_prims"] < 0.02 * max(1e-9, st["ms_shadow"]) else n_sh * 48.0, hbm_peak, "hbm", 48,
            "shadow rays (only scenes whose shadow tests are not fused into shade_kernel)"),
         _k("bvh_kernel<shadow>", st["ms_shadow_bvh"], n_sh * sh_bpr, l2_peak, "l2", sh_bpr, "shadow rays (reference nodes x 32 B + triangles x 36 B)"),
     ]
