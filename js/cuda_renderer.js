@@ -58,6 +58,12 @@ class CUDARenderer extends IncrementalMultisamplingRenderer {
         Object.defineProperty(this, "_size", { value: null, enumerable: false, writable: true });
     }
 
+    // options.devices = [0, 1, ...]: the scene is replicated on every listed GPU, each render() call's passes are dealt to
+    // them and the image is composed on the first one (the in-process successor of src/raytrace_launcher.js's worker pool)
+    _devices() {
+        return (this._opt.devices && this._opt.devices.length) ? Int32Array.from(this._opt.devices) : this._opt.device;
+    }
+
     _addon() {
         if (!this._opt.addon)
             this._opt.addon = require("./napi/build/Release/jsrt_addon.node");
@@ -85,7 +91,12 @@ class CUDARenderer extends IncrementalMultisamplingRenderer {
             return this._scene;
         if (this._scene) this._addon().destroyScene(this._scene);
         if (this._wire) {
-            this._scene = this._addon().createScene(this._wire.blob, this._wire.format, this._opt.device);
+            // a wire blob carries its own size: the image handed to render() must match it (rows would be written with the wrong stride)
+            const head = new Int32Array(5);
+            this._addon().sceneHeader(this._wire.blob, this._wire.format, head);
+            if (head[0] !== w || head[1] !== h)
+                throw new Error("render: the serialised scene is " + head[0] + "x" + head[1] + ", the image " + w + "x" + h);
+            this._scene = this._addon().createScene(this._wire.blob, this._wire.format, this._devices());
             this._size = [w, h];
             return this._scene;
         }
@@ -102,22 +113,32 @@ class CUDARenderer extends IncrementalMultisamplingRenderer {
         let blob, format;
         if (msgpack) { blob = Buffer.from(msgpack.encode(plain)); format = 1; }
         else { blob = Buffer.from(JSON.stringify(plain), "utf8"); format = 0; }
-        this._scene = this._addon().createScene(blob, format, this._opt.device);   // throws Error(jsrt_last_error())
+        this._scene = this._addon().createScene(blob, format, this._devices());   // throws Error(jsrt_last_error())
         this._size = [w, h];
         return this._scene;
+    }
+
+    // The uploaded scene is kept between render() calls (serialising a 100 000-triangle world takes seconds in JS).  The
+    // reference's renderers re-read this.world / this.camera on every call; after editing either (camera.setTransform,
+    // a material change, another samplesPerPixel is fine) call invalidate() so that the next render() serialises again.
+    invalidate() {
+        if (this._scene) { this._addon().destroyScene(this._scene); this._scene = null; }
     }
 
     render(img, timelimit = 0, callback = false, x_offset = 0, x_delt = 1) {
         const addon = this._addon(), scene = this._ensureScene(img);
         const spp = this.samplesPerPixel;
-        const step = (timelimit && callback) ? 1 : spp;
+        const flags = (this._wire && !this._wire.jitter) ? 1 : 0;      // flag 1 = no jitter
+        // One library call per pass, like the reference's loop (src/renderers.js:87): the library coalesces consecutive calls
+        // into full waves.  With a progress callback the host synchronises once per group of 8 passes — not per pass — to
+        // look at the clock (src/renderers.js:103-112: at most one callback per `timelimit` ms).
+        const group = this._opt.passesPerGroup || 8;
         addon.resetAccum(scene);
         let last = Date.now();
         for (let done = 0; done < spp; ) {
-            const n = Math.min(step, spp - done);
-            addon.render(scene, done, n, this._opt.seed, x_offset, x_delt, (this._wire && !this._wire.jitter) ? 1 : 0);      // asynchronous on the scene's stream; flag 1 = no jitter
-            done += n;
-            if (timelimit && callback) {
+            addon.render(scene, done, 1, this._opt.seed, x_offset, x_delt, flags);      // asynchronous on the scene's stream
+            done += 1;
+            if (timelimit && callback && (done % group === 0 || done === spp)) {
                 addon.synchronize(scene);
                 const now = Date.now();
                 if (now - last >= timelimit) {

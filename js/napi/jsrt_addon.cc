@@ -9,6 +9,7 @@
 #include <node_api.h>
 
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/jsrt.h"
@@ -17,10 +18,24 @@
 
 static napi_value throw_last(napi_env env) { napi_throw_error(env, "JSRT", jsrt_last_error()); return NULL; }
 
-static jsrt_scene* scene_arg(napi_env env, napi_value v) {
+// The external wraps a small box, not the scene itself: destroyScene() empties the box, so a stale handle throws instead of
+// double-freeing, and the finalizer frees whatever is still alive when the JS object is collected.
+typedef struct { jsrt_scene* scene; } scene_box;
+static void scene_finalize(napi_env env, void* data, void* hint) {
+    (void)env; (void)hint;
+    scene_box* b = (scene_box*)data;
+    if (b) { if (b->scene) jsrt_scene_destroy(b->scene); free(b); }
+}
+static scene_box* box_arg(napi_env env, napi_value v) {
     void* p = NULL;
     if (napi_get_value_external(env, v, &p) != napi_ok || !p) { napi_throw_type_error(env, NULL, "scene handle expected"); return NULL; }
-    return (jsrt_scene*)p;
+    return (scene_box*)p;
+}
+static jsrt_scene* scene_arg(napi_env env, napi_value v) {
+    scene_box* b = box_arg(env, v);
+    if (!b) return NULL;
+    if (!b->scene) { napi_throw_error(env, "JSRT", "scene handle used after destroyScene()"); return NULL; }
+    return b->scene;
 }
 static int32_t int_arg(napi_env env, napi_value v) { int32_t x = 0; napi_get_value_int32(env, v, &x); return x; }
 
@@ -30,15 +45,29 @@ static napi_value CreateScene(napi_env env, napi_callback_info info) {
     NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
     void* data = NULL; size_t len = 0;
     NAPI_OK(napi_get_buffer_info(env, a[0], &data, &len));
-    int dev = argc > 2 ? int_arg(env, a[2]) : 0;
-    jsrt_scene* s = jsrt_scene_create((const uint8_t*)data, len, int_arg(env, a[1]), &dev, 1);
+    // device: a number, or an Int32Array of device indices (the scene is replicated and every render call's passes are
+    // dealt to them: jsrt_scene_create with ndev > 1)
+    int devs[16]; int ndev = 1; devs[0] = 0;
+    if (argc > 2) {
+        napi_typedarray_type ty; size_t n = 0; void* d = NULL; napi_value ab; size_t off = 0;
+        if (napi_get_typedarray_info(env, a[2], &ty, &n, &d, &ab, &off) == napi_ok) {
+            if (ty != napi_int32_array || n < 1 || n > 16) { napi_throw_range_error(env, NULL, "devices must be an Int32Array of 1..16 indices"); return NULL; }
+            ndev = (int)n; memcpy(devs, d, n * sizeof(int));
+        } else devs[0] = int_arg(env, a[2]);
+    }
+    jsrt_scene* s = jsrt_scene_create((const uint8_t*)data, len, int_arg(env, a[1]), devs, ndev);
     if (!s) return throw_last(env);
-    napi_value ext; NAPI_OK(napi_create_external(env, s, NULL, NULL, &ext));
+    scene_box* b = (scene_box*)malloc(sizeof *b);
+    if (!b) { jsrt_scene_destroy(s); napi_throw_error(env, NULL, "out of memory"); return NULL; }
+    b->scene = s;
+    napi_value ext;
+    if (napi_create_external(env, b, scene_finalize, NULL, &ext) != napi_ok) { scene_finalize(env, b, NULL); napi_throw_error(env, NULL, "napi_create_external failed"); return NULL; }
     return ext;
 }
 static napi_value DestroyScene(napi_env env, napi_callback_info info) {
     size_t argc = 1; napi_value a[1]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
-    jsrt_scene* s = scene_arg(env, a[0]); if (s) jsrt_scene_destroy(s);
+    scene_box* b = box_arg(env, a[0]);
+    if (b && b->scene) { jsrt_scene_destroy(b->scene); b->scene = NULL; }       // idempotent
     return NULL;
 }
 // render(scene, firstPass, nPasses, seed, xOffset, xDelt, flags)
@@ -79,9 +108,14 @@ static napi_value ResolveRGBA8(napi_env env, napi_callback_info info) {
 static napi_value PrimaryHits(napi_env env, napi_callback_info info) {
     size_t argc = 3; napi_value a[3]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
     jsrt_scene* s = scene_arg(env, a[0]); if (!s) return NULL;
-    napi_typedarray_type ty; size_t n1 = 0, n2 = 0; void *d1 = NULL, *d2 = NULL; napi_value ab; size_t off;
-    NAPI_OK(napi_get_typedarray_info(env, a[1], &ty, &n1, &d1, &ab, &off));
-    NAPI_OK(napi_get_typedarray_info(env, a[2], &ty, &n2, &d2, &ab, &off));
+    napi_typedarray_type ty1, ty2; size_t n1 = 0, n2 = 0; void *d1 = NULL, *d2 = NULL; napi_value ab; size_t off;
+    NAPI_OK(napi_get_typedarray_info(env, a[1], &ty1, &n1, &d1, &ab, &off));
+    NAPI_OK(napi_get_typedarray_info(env, a[2], &ty2, &n2, &d2, &ab, &off));
+    jsrt_info inf; if (jsrt_scene_info(s, &inf)) return throw_last(env);
+    const size_t npix = (size_t)inf.width * inf.height;
+    if (ty1 != napi_int32_array || ty2 != napi_float32_array || n1 < npix || n2 < npix) {
+        napi_throw_range_error(env, NULL, "primaryHits needs an Int32Array and a Float32Array of width*height"); return NULL;
+    }
     if (jsrt_primary_hits(s, (int32_t*)d1, (float*)d2)) return throw_last(env);
     return NULL;
 }

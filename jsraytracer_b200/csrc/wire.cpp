@@ -86,10 +86,19 @@ Val WireDoc::parseJson(const char*& p, const char* e, int depth) {
     if (lit(p, e, "NaN")) { v.num = std::nan(""); return v; }
     if (lit(p, e, "Infinity")) { v.num = std::numeric_limits<double>::infinity(); return v; }
     if (lit(p, e, "-Infinity")) { v.num = -std::numeric_limits<double>::infinity(); return v; }
+    // The blob is (pointer, length), not a C string (a Node Buffer, an mmap): the numeric token is copied, bounded by
+    // `e`, into a terminated local buffer before strtod sees it.
+    char tok[64]; size_t n = 0;
+    while (p + n < e && n < sizeof tok - 1) {
+        const char ch = p[n];
+        if (!((ch >= '0' && ch <= '9') || ch == '-' || ch == '+' || ch == '.' || ch == 'e' || ch == 'E')) break;
+        tok[n] = ch; ++n;
+    }
+    tok[n] = 0;
     char* end = nullptr;
-    v.num = strtod(p, &end);
-    if (end == p) fail("jsrt: JSON value expected");
-    p = end;
+    v.num = strtod(tok, &end);
+    if (end == tok) fail("jsrt: JSON value expected");
+    p += end - tok;
     return v;
 }
 
@@ -194,12 +203,15 @@ void WireDoc::indexGraph() {
             if (t) {
                 if (t->type == Val::ARR && t->count == 2) {
                     const Val* nm = child(t, 0); const Val* ix = child(t, 1);
+                    // `_t` = [className, typeIndex]: the index is a small integer (one per class that occurs in the scene)
+                    if (nm->type != Val::STR || ix->type != Val::NUM || !(ix->num >= 0 && ix->num < 65536) || ix->num != (double)(long long)ix->num)
+                        fail("jsrt: malformed _t in scene blob (expected [className, typeIndex])");
                     size_t idx = (size_t)ix->num;
                     if (typenames_.size() <= idx) typenames_.resize(idx + 1);
                     typenames_[idx] = std::string(nm->str, nm->count);
                 }
                 const Val* r = mapGet(v, "_r");
-                if (r && r->type == Val::NUM) refs_[(long long)r->num] = v;
+                if (r && r->type == Val::NUM && r->num >= -9e15 && r->num <= 9e15) refs_[(long long)r->num] = v;
             }
             for (uint32_t i = v->count; i-- > 0;) stack.push_back(&arena_[v->first + 2 * i + 1]);
         } else if (v->type == Val::ARR) {
@@ -213,6 +225,7 @@ const Val* WireDoc::resolve(const Val* v) const {
     if (mapGet(v, "_t")) return v;
     const Val* r = mapGet(v, "_r");
     if (!r) return v;
+    if (r->type != Val::NUM || !(r->num >= -9e15 && r->num <= 9e15)) fail("jsrt: malformed reference _r in scene blob");
     auto it = refs_.find((long long)r->num);
     if (it == refs_.end()) fail("jsrt: dangling reference _r in scene blob");
     return it->second;
@@ -223,7 +236,9 @@ bool WireDoc::isObject(const Val* v) const { return v && v->type == Val::MAP && 
 const std::string& WireDoc::typeName(const Val* v) const {
     if (!isObject(v)) return empty_;
     const Val* t = mapGet(v, "_t");
-    size_t idx = (t->type == Val::ARR) ? (size_t)child(t, 1)->num : (size_t)t->num;
+    const Val* ix = (t->type == Val::ARR && t->count == 2) ? child(t, 1) : t;
+    if (ix->type != Val::NUM || !(ix->num >= 0 && ix->num < 65536)) fail("jsrt: malformed _t in scene blob");
+    const size_t idx = (size_t)ix->num;
     if (idx >= typenames_.size()) fail("jsrt: type index without a name in scene blob");
     return typenames_[idx];
 }

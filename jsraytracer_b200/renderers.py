@@ -75,6 +75,11 @@ class CUDARenderer(IncrementalMultisamplingRenderer):
             self._scene.close()
             self._scene = None
 
+    def invalidate(self):
+        """The uploaded scene is kept between render() calls; the reference's renderers re-read `world` / `camera` on
+        every call, so after editing either (camera.setTransform, a material) call this: the next render() serialises again."""
+        self.close()
+
 
 class WireRenderer:
     """The renderer of a scene that only exists as a wire blob (`Serializer.deserializeJSON`, the reference's

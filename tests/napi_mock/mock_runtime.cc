@@ -19,6 +19,7 @@ struct napi_value__ {
     size_t len = 0;
     napi_typedarray_type tt = napi_uint8_array;
     napi_callback cb = nullptr;
+    napi_finalize fin = nullptr; void* fin_hint = nullptr;      // externals: run when the env is destroyed (garbage collection)
     std::string name;
     std::vector<std::pair<std::string, napi_value>> props;
 };
@@ -61,7 +62,9 @@ napi_status napi_get_typedarray_info(napi_env env, napi_value v, napi_typedarray
 napi_status napi_get_value_int32(napi_env, napi_value v, int32_t* r) { if (!v || v->kind != K_NUMBER) return napi_number_expected; *r = (int32_t)(int64_t)v->num; return napi_ok; }
 napi_status napi_get_value_int64(napi_env, napi_value v, int64_t* r) { if (!v || v->kind != K_NUMBER) return napi_number_expected; *r = (int64_t)v->num; return napi_ok; }
 napi_status napi_get_value_external(napi_env, napi_value v, void** r) { if (!v || v->kind != K_EXTERNAL) return napi_invalid_arg; *r = v->ptr; return napi_ok; }
-napi_status napi_create_external(napi_env env, void* data, napi_finalize, void*, napi_value* r) { *r = env->make(K_EXTERNAL); (*r)->ptr = data; return napi_ok; }
+napi_status napi_create_external(napi_env env, void* data, napi_finalize fin, void* hint, napi_value* r) {
+    *r = env->make(K_EXTERNAL); (*r)->ptr = data; (*r)->fin = fin; (*r)->fin_hint = hint; return napi_ok;
+}
 napi_status napi_create_int32(napi_env env, int32_t x, napi_value* r) { *r = env->make(K_NUMBER); (*r)->num = x; return napi_ok; }
 napi_status napi_create_function(napi_env env, const char* name, size_t, napi_callback cb, void*, napi_value* r) {
     *r = env->make(K_FUNCTION); (*r)->cb = cb; (*r)->name = name ? name : ""; return napi_ok;
@@ -85,7 +88,15 @@ napi_env mock_env_create(void) {
     if (r && r->kind == K_OBJECT) env->exports = r;
     return env;
 }
-void mock_env_destroy(napi_env env) { delete env; }
+// tearing the environment down collects every value: externals run their finalizers, like Node's garbage collector would
+void mock_env_destroy(napi_env env) {
+    for (auto& v : env->heap) if (v->kind == K_EXTERNAL && v->fin) { v->fin(env, v->ptr, v->fin_hint); v->fin = nullptr; }
+    delete env;
+}
+int mock_run_finalizer(napi_env env, napi_value v) {          // collect one external now
+    if (!v || v->kind != K_EXTERNAL || !v->fin) return 0;
+    v->fin(env, v->ptr, v->fin_hint); v->fin = nullptr; v->ptr = nullptr; return 1;
+}
 int mock_export_count(napi_env env) { return (int)env->exports->props.size(); }
 const char* mock_export_name(napi_env env, int i) { return env->exports->props[i].first.c_str(); }
 napi_value mock_number(napi_env env, double x) { napi_value v = env->make(K_NUMBER); v->num = x; return v; }

@@ -60,6 +60,7 @@ class Addon:
         m.mock_number_value.restype = C.c_double
         m.mock_number_value.argtypes = [C.c_void_p]
         m.mock_env_destroy.argtypes = [C.c_void_p]
+        m.mock_run_finalizer.argtypes = [C.c_void_p, C.c_void_p]
         self.env = m.mock_env_create()
 
     def exports(self):
@@ -156,7 +157,18 @@ def test_addon_renders_the_same_bytes_as_the_ctypes_binding(addon):
         addon.call("readAccum", scene, np.zeros(8, np.float32))
     ids, t = np.zeros(W * H, np.int32), np.zeros(W * H, np.float32)
     addon.call("primaryHits", scene, ids, t)
+    # wrong element type / short arrays must be refused, not written through
+    with pytest.raises(RuntimeError, match="RangeError"):
+        addon.call("primaryHits", scene, np.zeros(W * H, np.float32), t)
+    with pytest.raises(RuntimeError, match="RangeError"):
+        addon.call("primaryHits", scene, np.zeros(W * H - 1, np.int32), t)
     addon.call("destroyScene", scene)
+    addon.call("destroyScene", scene)                                # a second destroy is a no-op, not a double free
+    with pytest.raises(RuntimeError, match="after destroyScene"):
+        addon.call("synchronize", scene)
+    # a scene that is never destroyed explicitly is released by the external's finalizer
+    leaked = addon.call("createScene", blob, 1, 0)
+    assert addon.m.mock_run_finalizer(addon.env, leaked.ptr) == 1
     # the same through ctypes
     sc = lib.Scene(blob, lib.FORMAT_MSGPACK, device=0)
     sc.render(0, 4, seed=1)

@@ -123,3 +123,52 @@ def test_random_mutations_never_crash(name):
         print("fmt", fmt, "accepted", ok, "rejected", bad)
     """ % name)
     assert out.count("accepted") == 2
+
+
+def test_type_index_and_reference_ids_are_range_checked():
+    """`_t` = ["X", 1e9] made the type table resize to ~32 GB; negative / NaN / non-integer indices and
+    reference ids were cast unchecked (undefined behaviour)."""
+    out = _run("""
+    good = json.loads(Serializer(scenes.configure("BoxBall", width=8, height=8)).to_json())
+    def first_typed(o):
+        if isinstance(o, dict):
+            if isinstance(o.get("_t"), list): return o
+            for x in o.values():
+                r = first_typed(x)
+                if r: return r
+        elif isinstance(o, list):
+            for x in o:
+                r = first_typed(x)
+                if r: return r
+    for bad in (1e9, -1, 1.5, 70000):
+        doc = json.loads(json.dumps(good))
+        first_typed(doc)["_t"][1] = bad
+        print(rejected(json.dumps(doc), 0))
+    doc = json.loads(json.dumps(good))
+    first_typed(doc)["_t"][0] = 7                        # class name must be a string
+    print(rejected(json.dumps(doc), 0))
+    doc = json.loads(json.dumps(good))
+    doc["_v"]["renderer"] = {"_r": 1e300}                # reference id far outside any integer
+    print(rejected(json.dumps(doc), 0))
+    """)
+    assert out.count("malformed _t") == 5 and "malformed reference _r" in out
+
+
+def test_json_number_at_the_very_end_of_an_unterminated_buffer():
+    """strtod ran on a (pointer, length) blob that need not be NUL-terminated.  A blob whose last token is a
+    number, placed at the very end of a page-sized buffer followed by digits that are NOT part of the blob, must parse the
+    token as delimited by the length (here: fail cleanly, since the document is truncated) and never read the neighbours."""
+    out = _run("""
+    import ctypes as C
+    L = lib.load()
+    text = b'{"width": 12'                                # truncated document ending in a numeric token
+    buf = C.create_string_buffer(text + b"3456789" * 8)   # bytes after the blob that look like more digits
+    h = L.jsrt_scene_create_host(buf, len(text), 0)
+    assert not h
+    print(lib.last_error())
+    text2 = b'[1.5e3'
+    buf2 = C.create_string_buffer(text2 + b"99")
+    assert not L.jsrt_scene_create_host(buf2, len(text2), 0)
+    print(lib.last_error())
+    """)
+    assert "jsrt:" in out
