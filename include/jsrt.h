@@ -104,6 +104,14 @@ int jsrt_read_accum(jsrt_scene*, float* out, int* passes);
  * like its display pass does), w = number of samples whose camera ray hit something.  Zero if no AOV pass was rendered. */
 int jsrt_read_aov(jsrt_scene*, float* normal_depth, float* variance);
 
+/* Replaces: the GL path's display pass with its variance-guided denoiser (gl/src/WebGLRendererAdapter.js:183-246: `smartDeNoise`
+ * and `main` of the passthrough shader; defaults there: sigma 1, kSigma 2, threshold 5, colorLogScale 0, :15-22).  Filters
+ * the running mean with a circular Gaussian window of radius round(kSigma * sigma) whose taps are weighted down by their
+ * own per-pixel standard deviation (the variance buffer of JSRT_FLAG_AOV passes: render with that flag first).  Writes the
+ * filtered mean as W*H*4 floats (rgb, mean sample weight) to out_rgba and / or as 8-bit RGBA (clamped, rounded, alpha 255) to
+ * out_rgba8; either may be NULL.  Scenes created on several devices: AOV passes run on devices[0] only, and so does this. */
+int jsrt_denoise(jsrt_scene*, float sigma, float k_sigma, float threshold, float color_log_scale, float* out_rgba, uint8_t* out_rgba8);
+
 /* One process per GPU: every process exports its accumulation buffer as a 64-byte CUDA
  * IPC handle (jsrt_accum_export), the handles travel over the host's own channel, and the process that owns the image
  * maps the others' buffers with jsrt_accum_attach(handles = n x 64 bytes); from then on its jsrt_resolve_rgba8 /

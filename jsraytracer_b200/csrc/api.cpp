@@ -136,6 +136,11 @@ int jsrt_read_aov(jsrt_scene* s, float* normal_depth, float* variance) {
     if (!normal_depth || !variance) { g_error = "jsrt: null output buffer"; return 1; }
     JSRT_TRY(s->renderer->readAov(normal_depth, variance))
 }
+int jsrt_denoise(jsrt_scene* s, float sigma, float k_sigma, float threshold, float color_log_scale, float* out_rgba, uint8_t* out_rgba8) {
+    if (needDevice(s)) return 1;
+    if (!out_rgba && !out_rgba8) { g_error = "jsrt: null output buffer"; return 1; }
+    JSRT_TRY(s->renderer->denoise(sigma, k_sigma, threshold, color_log_scale, out_rgba, out_rgba8))
+}
 void* jsrt_accum_device_ptr(jsrt_scene* s) { return (s && s->renderer) ? s->renderer->accumPtr() : nullptr; }
 int jsrt_add_passes(jsrt_scene* s, int n) { if (needDevice(s)) return 1; JSRT_TRY(s->renderer->addPasses(n)) }
 int jsrt_primary_hits(jsrt_scene* s, int32_t* prim_id, float* t) { if (needDevice(s)) return 1; if (!prim_id || !t) { g_error = "jsrt: null output buffer"; return 1; } JSRT_TRY(s->renderer->primaryHits(prim_id, t)) }

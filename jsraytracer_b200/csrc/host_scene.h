@@ -18,6 +18,7 @@ struct HostScene {
     std::vector<Top> tops;              // flattened top-level entries in the reference's visit order (scene_flatten.cpp)
     std::vector<int> top_world;         // parallel to tops: the entry of world.objects each one came from
     int world_object_count = 0;
+    int tlas_root = -1;                 // root of the top-level BVH over the BVHAggregates (buildTlas), -1: linear walk
     int n_staged = 0;                   // nodes[0, n_staged): the top levels of every tree (staged in shared memory by bvh_kernel)
     std::vector<Prim> prims;
     std::vector<Xform> xforms;          // xforms[0] is the identity
@@ -46,6 +47,10 @@ void flattenScene(const WireDoc& doc, HostScene& out);
 // The device tests a ray against it before paying for the aggregate's ray transform and local root-box test
 // (trace.cuh: wbox_hit); it must contain the aggregate's root box mapped to world space.
 void computeWorldBoxes(const HostScene& hs, std::vector<float>& out);
+
+// Appends a top-level BVH over the scene's BVHAggregates to hs.nodes (leaves = aggregate ordinals in world.objects order)
+// and returns its root index, or -1 if it cannot be built (an unbounded aggregate).
+int buildTlas(HostScene& hs);
 
 // SDF tree -> bytecode (sdf_compile.cpp).  Returns the index of the new program.
 int compileSdf(const WireDoc& doc, const Val* sdf_geometry, HostScene& out);

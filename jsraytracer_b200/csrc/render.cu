@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kBlock, MODE == TM_SHADOW ? JSRT_SDF_SHADOW_MI
 // per SM: up to 7 168 nodes = 224 KB of shared memory, 4 096 = 128 KB by default (the other half of the unified array
 // stays L1 for the deep nodes, the triangles and the ray records).
 extern __shared__ float4 s_staged_nodes[];
-template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT>
+template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT, bool TLAS>
 __global__ void __launch_bounds__(JSRT_BVH_BLOCK, JSRT_BVH_MIN_BLOCKS) bvh_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
     {
         const float4* src = reinterpret_cast<const float4*>(sc.nodes);
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(JSRT_BVH_BLOCK, JSRT_BVH_MIN_BLOCKS) bvh_kerne
         __syncthreads();
     }
     Work wp, ws;
-    bvh_wave<MODE, COUNT, HAS_SDF, DIRECT>(sc, io, &wp, &ws, s_staged_nodes);
+    bvh_wave<MODE, COUNT, HAS_SDF, DIRECT, TLAS>(sc, io, &wp, &ws, s_staged_nodes);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
 
@@ -474,6 +474,56 @@ __global__ void sum_peers_kernel(const float4* __restrict__ accum, const __grid_
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < npix) out[i] = summed_pixel(accum, peers, i);
 }
+// The GL path's display pass with its variance-guided denoiser (gl/src/WebGLRendererAdapter.js:183-246, `smartDeNoise` +
+// `main` of the passthrough shader), over the HBM-resident buffers: `accum` = the shader's uSampleSumTexture (colour sums;
+// w = sample count here), `var` = uVarianceTexture (the running variance sums written by fold_samples_kernel).  FP32 like
+// the shader.  Per pixel: a circular Gaussian window of radius round(kSigma * sigma) whose taps are weighted down by their
+// OWN standard deviation (`exp(-|std|^2 / (2 threshold^2))`: the shader's active line :210), textures sampled NEAREST with
+// coordinates clamped to [0, 1] (gl/src/WebGLUtilHelpers.js:452-453).  The row offsets follow the shader literally:
+// d.y runs from -sqrt(r^2 - d.x^2) in steps of 1, so they are not integers off the centre column.
+__global__ void denoise_kernel(const float4* __restrict__ accum, const float4* __restrict__ var, float4* __restrict__ out, int W, int H,
+                               float sigma, float k_sigma, float threshold, float color_log_scale) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float INV_PI = 0.31830988618379067153776752674503f, INV_SQRT_OF_2PI = 0.39894228040143267793994605993439f;
+    const float radius = rintf(k_sigma * sigma), radQ = radius * radius;
+    const float invSigmaQx2 = .5f / (sigma * sigma), invSigmaQx2PI = INV_PI * invSigmaQx2;
+    const float invThresholdSqx2 = .5f / (threshold * threshold), invThresholdSqrt2PI = INV_SQRT_OF_2PI / threshold;
+    const float u = ((float)x + 0.5f) / (float)W, v = ((float)y + 0.5f) / (float)H;
+    float zBuff = 0.f; float3 aBuff = f3(0.f, 0.f, 0.f); float aW = 0.f;
+    for (float dx = -radius; dx <= radius; dx += 1.f) {
+        const float pt = sqrtf(radQ - dx * dx);
+        for (float dy = -pt; dy <= pt; dy += 1.f) {
+            const float blurFactor = expf(-(dx * dx + dy * dy) * invSigmaQx2) * invSigmaQx2PI;
+            const float cu = fmaxf(fminf(u + dx / (float)W, 1.0f), 0.0f), cv = fmaxf(fminf(v + dy / (float)H, 1.0f), 0.0f);
+            const int tx = min(max((int)floorf(cu * (float)W), 0), W - 1), ty = min(max((int)floorf(cv * (float)H), 0), H - 1);
+            const float4 a = accum[ty * W + tx], q = var[ty * W + tx];
+            const float tf = 1.0f / fmaxf(a.w, 1.0f);                  // texture_factor = 1 / max(uSampleCount + 1, 1)
+            const float3 walkPx = f3(a.x * tf, a.y * tf, a.z * tf);
+            const float3 stdPx = f3(sqrtf(q.x * tf), sqrtf(q.y * tf), sqrtf(q.z * tf));
+            const float deltaFactor = expf(-dot3(stdPx, stdPx) * invThresholdSqx2) * invThresholdSqrt2PI * blurFactor;
+            zBuff += deltaFactor;
+            aBuff = aBuff + walkPx * deltaFactor; aW += deltaFactor * (a.w * tf);
+        }
+    }
+    float3 c = aBuff; float alpha = aW;
+    if (zBuff != 0.f) { c = c * (1.0f / zBuff); alpha = alpha / zBuff; }
+    // the shader's diagnostics colours (:233-238), then the optional log scale (:240-241)
+    if (c.x != c.x || c.y != c.y || c.z != c.z) c = f3(1.0f, 0.0f, 0.5f);
+    else if (isinf(c.x) || isinf(c.y) || isinf(c.z)) c = f3(0.0f, 1.0f, 0.5f);
+    else if (c.x < 0.f || c.y < 0.f || c.z < 0.f) c = f3(0.5f, 0.0f, 1.0f);
+    if (color_log_scale > 0.f) c = f3(logf(c.x + 1.0f) / color_log_scale, logf(c.y + 1.0f) / color_log_scale, logf(c.z + 1.0f) / color_log_scale);
+    out[y * W + x] = make_float4(c.x, c.y, c.z, alpha);
+}
+// float RGBA -> 8-bit like the canvas the shader draws to (clamp, round to nearest; alpha 255)
+__global__ void quantize_kernel(const float4* __restrict__ in, uchar4* __restrict__ out, int npix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const float4 c = in[i];
+    out[i] = make_uchar4((unsigned char)floorf(255.f * fminf(fmaxf(c.x, 0.f), 1.f) + 0.5f), (unsigned char)floorf(255.f * fminf(fmaxf(c.y, 0.f), 1.f) + 0.5f),
+                         (unsigned char)floorf(255.f * fminf(fmaxf(c.z, 0.f), 1.f) + 0.5f), 255);
+}
+
 // optimistic queue sizing: a batch that did not overflow is folded from its scratch buffer into the pixel sums
 __global__ void add_scratch_kernel(float4* __restrict__ accum, float4* __restrict__ scratch, int npix) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -513,6 +563,7 @@ struct Renderer::Impl {
     // JSRT_FLAG_AOV (allocated on first use): first-hit normal / distance sums, variance sums (w: first hits), and the
     // per-sample radiance of the batch in flight (`sample_span` frames)
     float4 *aov_nd = nullptr, *aov_var = nullptr, *sample_rad = nullptr;
+    float4* denoised = nullptr;         // output of denoise_kernel (allocated on first use)
     int sample_span = 0;
     int4* tie_list = nullptr;           // FP32 near-ties between triangles reported by bvh_kernel<extend> (trace.cuh: tie_wave)
     static constexpr int kTieCap = 1 << 20;
@@ -559,7 +610,8 @@ struct Renderer::Impl {
             }
         }
         ds.wboxes = up(wboxes_host);
-        ds.use_wbox = envInt("JSRT_WBOX", ds.n_bvh >= 2 ? 1 : 0);
+        ds.tlas_root = (hs.tlas_root >= 0 && hs.tlas_root < (int)hs.nodes.size() && hs.sdfs.empty()) ? hs.tlas_root : -1;   // (SDF scenes keep the linear walk)
+        ds.use_wbox = envInt("JSRT_WBOX", (ds.n_bvh >= 2 && ds.tlas_root < 0) ? 1 : 0);
         sdf_tops_host.clear();
         for (size_t i = 0; i < hs.tops.size(); ++i) if (hs.tops[i].kind == T_SDF) sdf_tops_host.push_back((int)i);
         ds.sdf_tops = up(sdf_tops_host); ds.n_sdf_tops = (int)sdf_tops_host.size();
@@ -676,12 +728,16 @@ struct Renderer::Impl {
         bvh_smem = (size_t)ds.n_staged * sizeof(BvhNode);
         if ((int)bvh_smem > prop.sharedMemPerBlockOptin) throw std::runtime_error("jsrt: staged BVH block exceeds the shared memory of an SM (lower JSRT_STAGE_NODES)");
         #define JSRT_BVH_ATTR(...) CK(cudaFuncSetAttribute((const void*)bvh_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bvh_smem))
-        if (has_sdf) { JSRT_BVH_ATTR(TM_EXTEND, false, true, false); JSRT_BVH_ATTR(TM_EXTEND, true, true, false); JSRT_BVH_ATTR(TM_SHADOW, false, true, false); JSRT_BVH_ATTR(TM_SHADOW, true, true, false); }
-        else { JSRT_BVH_ATTR(TM_EXTEND, false, false, false); JSRT_BVH_ATTR(TM_EXTEND, true, false, false); JSRT_BVH_ATTR(TM_SHADOW, false, false, false); JSRT_BVH_ATTR(TM_SHADOW, true, false, false);
-               JSRT_BVH_ATTR(TM_SHADOW, false, false, true); JSRT_BVH_ATTR(TM_SHADOW, true, false, true); }
+        if (has_sdf) { JSRT_BVH_ATTR(TM_EXTEND, false, true, false, false); JSRT_BVH_ATTR(TM_EXTEND, true, true, false, false); JSRT_BVH_ATTR(TM_SHADOW, false, true, false, false); JSRT_BVH_ATTR(TM_SHADOW, true, true, false, false); }
+        else {
+            JSRT_BVH_ATTR(TM_EXTEND, false, false, false, false); JSRT_BVH_ATTR(TM_EXTEND, true, false, false, false); JSRT_BVH_ATTR(TM_SHADOW, false, false, false, false); JSRT_BVH_ATTR(TM_SHADOW, true, false, false, false);
+            JSRT_BVH_ATTR(TM_SHADOW, false, false, true, false); JSRT_BVH_ATTR(TM_SHADOW, true, false, true, false);
+            JSRT_BVH_ATTR(TM_EXTEND, false, false, false, true); JSRT_BVH_ATTR(TM_EXTEND, true, false, false, true); JSRT_BVH_ATTR(TM_SHADOW, false, false, false, true); JSRT_BVH_ATTR(TM_SHADOW, true, false, false, true);
+            JSRT_BVH_ATTR(TM_SHADOW, false, false, true, true); JSRT_BVH_ATTR(TM_SHADOW, true, false, true, true);
+        }
         #undef JSRT_BVH_ATTR
-        grid_bvh = has_sdf ? grid_for((const void*)bvh_kernel<TM_EXTEND, false, true, false>, JSRT_BVH_BLOCK, bvh_smem)
-                           : grid_for((const void*)bvh_kernel<TM_EXTEND, false, false, false>, JSRT_BVH_BLOCK, bvh_smem);
+        grid_bvh = has_sdf ? grid_for((const void*)bvh_kernel<TM_EXTEND, false, true, false, false>, JSRT_BVH_BLOCK, bvh_smem)
+                           : grid_for((const void*)bvh_kernel<TM_EXTEND, false, false, false, false>, JSRT_BVH_BLOCK, bvh_smem);
         // material-sorted shading: on for scenes made of analytic primitives only (see shade_kernel)
         sort_shade = bvh_tops_host.empty();
         if (const char* e = getenv("JSRT_SHADE_SORT")) sort_shade = atoi(e) != 0;
@@ -799,10 +855,14 @@ struct Renderer::Impl {
         mark();
         if (has_bvh) {
             ++launches;
-            #define JSRT_BVH(C, S, D) bvh_kernel<MODE, C, S, D><<<grid_bvh, JSRT_BVH_BLOCK, bvh_smem, stream>>>(ds, io)
-            if (direct) { if (count_work) JSRT_BVH(true, false, (MODE == TM_SHADOW)); else JSRT_BVH(false, false, (MODE == TM_SHADOW)); }
-            else if (count_work) { if (has_sdf) JSRT_BVH(true, true, false); else JSRT_BVH(true, false, false); }
-            else { if (has_sdf) JSRT_BVH(false, true, false); else JSRT_BVH(false, false, false); }
+            const bool tlas = ds.tlas_root >= 0;
+            #define JSRT_BVH(C, S, D, T) bvh_kernel<MODE, C, S, D, T><<<grid_bvh, JSRT_BVH_BLOCK, bvh_smem, stream>>>(ds, io)
+            if (has_sdf) { if (count_work) JSRT_BVH(true, true, false, false); else JSRT_BVH(false, true, false, false); }
+            else if (direct) {
+                if (tlas) { if (count_work) JSRT_BVH(true, false, (MODE == TM_SHADOW), true); else JSRT_BVH(false, false, (MODE == TM_SHADOW), true); }
+                else { if (count_work) JSRT_BVH(true, false, (MODE == TM_SHADOW), false); else JSRT_BVH(false, false, (MODE == TM_SHADOW), false); }
+            } else if (tlas) { if (count_work) JSRT_BVH(true, false, false, true); else JSRT_BVH(false, false, false, true); }
+            else { if (count_work) JSRT_BVH(true, false, false, false); else JSRT_BVH(false, false, false, false); }
             #undef JSRT_BVH
             if (MODE == TM_EXTEND && JSRT_TRI_TIE) { ++launches; tie_kernel<<<4, kBlock, 0, stream>>>(ds, io); }      // a few dozen entries per frame
         }
@@ -997,6 +1057,23 @@ void Renderer::readAov(float* normal_depth, float* variance) {
     if (!impl_->aov_nd) { memset(normal_depth, 0, bytes); memset(variance, 0, bytes); return; }
     CK(cudaMemcpyAsync(normal_depth, impl_->aov_nd, bytes, cudaMemcpyDeviceToHost, impl_->stream));
     CK(cudaMemcpyAsync(variance, impl_->aov_var, bytes, cudaMemcpyDeviceToHost, impl_->stream));
+    synchronize();
+}
+void Renderer::denoise(float sigma, float k_sigma, float threshold, float color_log_scale, float* out_rgba, uint8_t* out_rgba8) {
+    impl_->flush();
+    CK(cudaSetDevice(impl_->device));
+    Impl& m = *impl_;
+    if (!m.aov_var) throw std::runtime_error("jsrt: the denoiser needs the variance buffer: render the passes with JSRT_FLAG_AOV");
+    if (!(sigma > 0.f) || !(k_sigma >= 0.f) || !(threshold > 0.f) || k_sigma * sigma > 64.f) throw std::runtime_error("jsrt: denoise parameters out of range (sigma > 0, kSigma >= 0, kSigma * sigma <= 64, threshold > 0)");
+    const int W = m.hs.width, H = m.hs.height, npix = W * H;
+    if (!m.denoised) m.denoised = m.dalloc<float4>(npix);
+    const dim3 blk(32, 8), grd((W + 31) / 32, (H + 7) / 8);
+    denoise_kernel<<<grd, blk, 0, m.stream>>>(m.accum, m.aov_var, m.denoised, W, H, sigma, k_sigma, threshold, color_log_scale); ++m.launches;
+    if (out_rgba) CK(cudaMemcpyAsync(out_rgba, m.denoised, (size_t)npix * sizeof(float4), cudaMemcpyDeviceToHost, m.stream));
+    if (out_rgba8) {
+        quantize_kernel<<<(npix + 255) / 256, 256, 0, m.stream>>>(m.denoised, m.rgba, npix); ++m.launches;
+        CK(cudaMemcpyAsync(out_rgba8, m.rgba, (size_t)npix * 4, cudaMemcpyDeviceToHost, m.stream));
+    }
     synchronize();
 }
 void Renderer::resolve(uint8_t* out) {

@@ -30,6 +30,7 @@ public:
     void resolve(uint8_t* out_rgba);
     void readAccum(float* out, int* passes);
     void readAov(float* normal_depth, float* variance);
+    void denoise(float sigma, float k_sigma, float threshold, float color_log_scale, float* out_rgba, uint8_t* out_rgba8);
     void* accumPtr();
     void addPasses(int n);
     // other GPUs' accumulation buffers, summed into this one's by resolve() / readAccum() (read over NVLink by the kernels)

@@ -679,6 +679,12 @@ struct Flattener {
 void flattenScene(const WireDoc& doc, HostScene& out) {
     Flattener f(doc, out);
     f.run();
+    // a top-level BVH over the aggregates once there are enough of them for it to beat the linear walk (JSRT_TLAS_MIN, 0 = never)
+    int n_bvh = 0;
+    for (const Top& t : out.tops) if (t.kind == T_BVH && t.node_count > 0) ++n_bvh;
+    int tlas_min = 6;
+    if (const char* e = getenv("JSRT_TLAS_MIN")) tlas_min = atoi(e);
+    if (tlas_min > 0 && n_bvh >= tlas_min) out.tlas_root = buildTlas(out);
 }
 
 // The root box (centre c, half h, aggregate space) under the aggregate's transform M = inv_transform^-1 has centre M c and
@@ -711,6 +717,81 @@ void computeWorldBoxes(const HostScene& hs, std::vector<float>& out) {
         for (int i = 0; i < 3; ++i) out.push_back(finite ? (float)(wh[i] + pad) : INFINITY);
         out.push_back(0.f);
     }
+}
+
+// Top-level BVH over the BVHAggregates of a scene with many of them (27 dragon instances: the reference's linear walk over
+// world.objects costs 27 ray transforms + root-box tests per ray, 8.7 after the world-box reject).  Built here, by a
+// plain surface-area-heuristic sweep over the instances' padded world boxes (computeWorldBoxes); the reference has no
+// counterpart and needs none, because the structure only prunes: every aggregate whose box the ray reaches within the
+// current bound is still entered, and exact ties are settled by the static rank (entry index, primitive index) whatever
+// the order of the visits.  Nodes use the device's stackless format with leaves = (1 << 24) | aggregate ordinal.
+namespace {
+struct TlasItem { double lo[3], hi[3]; int ordinal; };
+void tlasEmit(std::vector<TlasItem>& items, int begin, int end, std::vector<BvhNode>& out) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+    for (int i = begin; i < end; ++i)
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], items[i].lo[a]); hi[a] = std::max(hi[a], items[i].hi[a]);
+            const double c = 0.5 * (items[i].lo[a] + items[i].hi[a]);
+            clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c);
+        }
+    const int me = (int)out.size();
+    BvhNode b{};
+    const double c[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+    b.cx = (float)c[0]; b.cy = (float)c[1]; b.cz = (float)c[2];
+    // half sizes rounded outwards so that the f32 box contains the f64 union
+    auto up = [](double h, double cc, float cf) { const double need = h + std::fabs(cc - (double)cf); float f = (float)need; while ((double)f < need) f = std::nextafter(f, INFINITY); return f; };
+    b.hx = up(0.5 * (hi[0] - lo[0]), c[0], b.cx); b.hy = up(0.5 * (hi[1] - lo[1]), c[1], b.cy); b.hz = up(0.5 * (hi[2] - lo[2]), c[2], b.cz);
+    b.leaf = -1;
+    out.push_back(b);
+    if (end - begin == 1) { out[me].leaf = (1 << 24) | items[begin].ordinal; out[me].skip = (int)out.size(); return; }
+    int ax = 0; for (int a = 1; a < 3; ++a) if (chi[a] - clo[a] > chi[ax] - clo[ax]) ax = a;
+    std::sort(items.begin() + begin, items.begin() + end, [ax](const TlasItem& x, const TlasItem& y) { return x.lo[ax] + x.hi[ax] < y.lo[ax] + y.hi[ax]; });
+    // SAH sweep along that axis
+    const int n = end - begin;
+    auto area = [](const double l[3], const double h[3]) { const double d[3] = {std::max(0.0, h[0] - l[0]), std::max(0.0, h[1] - l[1]), std::max(0.0, h[2] - l[2])}; return d[0] * d[1] + d[1] * d[2] + d[2] * d[0]; };
+    std::vector<double> right(n, 0.0);
+    { double l[3] = {1e300, 1e300, 1e300}, h[3] = {-1e300, -1e300, -1e300};
+      for (int i = n - 1; i > 0; --i) { for (int a = 0; a < 3; ++a) { l[a] = std::min(l[a], items[begin + i].lo[a]); h[a] = std::max(h[a], items[begin + i].hi[a]); } right[i] = area(l, h); } }
+    int best = n / 2; double best_cost = 1e300;
+    { double l[3] = {1e300, 1e300, 1e300}, h[3] = {-1e300, -1e300, -1e300};
+      for (int i = 1; i < n; ++i) {
+          for (int a = 0; a < 3; ++a) { l[a] = std::min(l[a], items[begin + i - 1].lo[a]); h[a] = std::max(h[a], items[begin + i - 1].hi[a]); }
+          const double cost = area(l, h) * i + right[i] * (n - i);
+          if (cost < best_cost) { best_cost = cost; best = i; }
+      } }
+    tlasEmit(items, begin, begin + best, out);
+    tlasEmit(items, begin + best, end, out);
+    out[me].skip = (int)out.size();
+}
+}  // namespace
+
+int buildTlas(HostScene& hs) {
+    std::vector<float> wb;
+    computeWorldBoxes(hs, wb);
+    const int n = (int)(wb.size() / 8);
+    std::vector<TlasItem> items;
+    for (int k = 0; k < n; ++k) {
+        TlasItem it; it.ordinal = k;
+        for (int a = 0; a < 3; ++a) {
+            const double c = wb[8 * k + a], h = wb[8 * k + 4 + a];
+            if (!std::isfinite(c) || !std::isfinite(h)) return -1;          // an unbounded aggregate: keep the linear walk
+            it.lo[a] = c - h; it.hi[a] = c + h;
+        }
+        items.push_back(it);
+    }
+    if (items.empty() || items.size() >= (1u << 24)) return -1;
+    std::vector<BvhNode> rel;
+    tlasEmit(items, 0, n, rel);
+    const int base = (int)hs.nodes.size();
+    if ((size_t)base + rel.size() >= (size_t)kNodeEnd) return -1;
+    for (size_t i = 0; i < rel.size(); ++i) {
+        BvhNode b = rel[i];
+        b.skip = (rel[i].skip >= (int)rel.size()) ? kNodeEnd : base + rel[i].skip;
+        if (rel[i].leaf == -1) b.leaf = kNodeInner | (base + (int)i + 1);
+        hs.nodes.push_back(b);
+    }
+    return base;
 }
 
 }  // namespace jsrt

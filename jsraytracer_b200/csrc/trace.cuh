@@ -37,7 +37,7 @@ struct DeviceScene {
     const float4* wboxes;
     int n_sdf_tops, use_wbox;
     int n_staged;              // nodes[0, n_staged): the top levels of every tree, staged in shared memory by bvh_kernel
-    int pad2;
+    int tlas_root;             // >= 0: root node of the top-level BVH over the BVHAggregates (scene_flatten.cpp: buildTlas)
     int n_top, n_lights, light_samples, max_depth;
     float bg[3];
     int n_bvh;
@@ -248,6 +248,15 @@ JSRT_DEV LocalRay make_local_ray(const XformReg& m, float3 o, float3 d) {
     r.sgn = f3(r.ld.x < 0.f ? -1.f : 1.f, r.ld.y < 0.f ? -1.f : 1.f, r.ld.z < 0.f ? -1.f : 1.f);
     return r;
 }
+// the same for a ray that is already in the right space (the top-level BVH is walked with the world ray)
+JSRT_DEV LocalRay make_ray(float3 o, float3 d) {
+    LocalRay r;
+    r.lo = o; r.ld = d;
+    r.par = !(fabsf(d.x) > 0.0000001f) || !(fabsf(d.y) > 0.0000001f) || !(fabsf(d.z) > 0.0000001f);
+    r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.sgn = f3(d.x < 0.f ? -1.f : 1.f, d.y < 0.f ? -1.f : 1.f, d.z < 0.f ? -1.f : 1.f);
+    return r;
+}
 // AABB.get_intersects (src/geometry.js:189-209) + the visit condition of BVHAggregateNode.intersect (:209) for
 // a ray without parallel axes.  The reference sorts (p+h)/d and (p-h)/d per axis; which of the two is the
 // smaller is known from the sign of d, so the entry distance of an axis is (p - sgn*h) * (1/d) and the exit
@@ -382,6 +391,13 @@ JSRT_DEV void analytic_hits(const DeviceScene& sc, const float3 o, const float3 
 // `lr` receives the ray in that aggregate's space.
 template <bool COUNT>
 JSRT_DEV int first_bvh_hit(const DeviceScene& sc, const float3 o, const float3 d, const float minD, const float maxD, const float best_t, Work* work, LocalRay& lr) {
+    if (sc.tlas_root >= 0) {           // many aggregates: the walk starts at the top-level BVH; here only its root box
+        const LocalRay r = make_ray(o, d);
+        const float4* root = reinterpret_cast<const float4*>(sc.nodes + sc.tlas_root);
+        if (COUNT) ++work->nodes;
+        if (slab_any(__ldg(root), __ldg(root + 1), r, minD, maxD, best_t)) { lr = r; return 0; }
+        return -1;
+    }
     float3 winv = f3(0.f, 0.f, 0.f);
     if (sc.use_wbox) winv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     for (int b = 0; b < sc.n_bvh; ++b) {
@@ -605,7 +621,7 @@ JSRT_DEV void tie_wave(const DeviceScene& sc, const TraceIO& io) {
 // DIRECT (shadow rays of scenes without SDFs): the queue holds walkers only — shade_kernel has already run the analytic
 // primitives and the root boxes and accumulated or dropped every ray that needs no walk — so entry i of the queue is
 // ray i: o.xyz | pixel, d.xyz | pass, contribution.rgb | first BVH.  No work list, no partial-hit buffer.
-template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT>
+template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT, bool TLAS>
 JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other, const float4* __restrict__ s_nodes) {
     constexpr bool ANY_HIT = (MODE == TM_SHADOW);
     constexpr int BATCH = JSRT_POOL_BATCH;      // list entries fetched per atomicAdd
@@ -633,6 +649,12 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
     int bi = 0;
     int node_i = kNodeEnd, first_prim = 0, tri_base = -1;
+    // Top-level BVH (scenes with many aggregates): the lane walks it with the world ray (tri_base == kTlasLevel marks that
+    // level); a leaf names an aggregate (`want`), which is entered like any BVH, and when that tree is finished the walk
+    // resumes at the top-level node `resume`.  One level of nesting, one extra register.
+    constexpr int kTlasLevel = -2;
+    constexpr bool use_tlas = TLAS;          // (a template flag: the extra state must not cost the single-mesh kernels registers)
+    int want = -1, resume = kNodeEnd;
     float local_best = CUDART_INF_F, local_lo = 0.f; int local_prim = -1;
     Work* work = work_other;
     const float4* const all_nodes = reinterpret_cast<const float4*>(sc.nodes);
@@ -695,7 +717,12 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                                 if (COUNT) work = primary ? work_primary : work_other;
                                 best.t = h4.x; best.prim = __float_as_int(h4.y); best.top = __float_as_int(h4.z); best.t_lo = h4.w;
                             }
-                            enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
+                            if (use_tlas) {
+                                r = make_ray(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
+                                node_i = sc.tlas_root; tri_base = kTlasLevel; want = -1; resume = kNodeEnd; pending = -1;
+                                local_best = CUDART_INF_F; local_prim = -1; local_lo = 0.f;
+                                hi = fminf(JSRT_MAXD, best.t);
+                            } else enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
                             // the producer has tested this tree's root box; an inner root needs no second test
                             const int root_word = __float_as_int(__ldg(all_nodes + 2 * node_i + 1).w);
                             if (root_word < 0) node_i = root_word & 0x7fffffff;
@@ -758,7 +785,28 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
         }
 
         if (active) {
-            if (node_i == kNodeEnd && pending == -1) {
+            if (use_tlas && want >= 0) {
+                // ---- a leaf of the top-level BVH: enter that aggregate -------------------------
+                const float4 o4 = io.o[cur], d4 = io.d[cur];
+                bi = want; want = -1;
+                enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
+            } else if (use_tlas && node_i == kNodeEnd && pending == -1) {
+                if (tri_base != kTlasLevel) {
+                    // ---- an aggregate's tree is finished: merge, back to the top-level walk ----
+                    const int top_i = __ldg(sc.bvh_tops + bi);
+                    if (local_best > JSRT_MIND && local_best < JSRT_MAXD && better_hit(local_best, top_i, best)) {
+                        best.t = local_best; best.prim = local_prim; best.top = top_i; best.t_lo = local_lo;
+                    }
+                    if (resume == kNodeEnd || (ANY_HIT && best.prim >= 0)) cur = -2 - cur;
+                    else {
+                        const float4 o4 = io.o[cur], d4 = io.d[cur];
+                        r = make_ray(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
+                        node_i = resume; resume = kNodeEnd; tri_base = kTlasLevel;
+                        local_best = CUDART_INF_F; local_prim = -1; local_lo = 0.f;
+                        hi = fminf(JSRT_MAXD, best.t);
+                    }
+                } else cur = -2 - cur;              // the top-level walk is over
+            } else if (node_i == kNodeEnd && pending == -1) {
                 // ---- tree finished: merge into the running closest hit, next BVH or done -------
                 const int top_i = __ldg(sc.bvh_tops + bi);
                 if (local_best > JSRT_MIND && local_best < JSRT_MAXD && better_hit(local_best, top_i, best)) {
@@ -789,7 +837,8 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                     const bool hit_box = r.par ? slab_general(n0, n1, r, JSRT_MIND, JSRT_MAXD, hi) : slab_fast(n0, n1, r, JSRT_MIND, hi);
                     if (hit_box) {
                         if (word >= 0) {            // leaf
-                            if (pending == -1) { pending = word; node_i = skip; }
+                            if (tri_base == kTlasLevel) { want = word & 0xffffff; resume = skip; node_i = kNodeEnd; }      // an aggregate: entered after the loop
+                            else if (pending == -1) { pending = word; node_i = skip; }
                             else pending = -(pending + 2);      // one leaf already parked: block here until it is tested
                         } else node_i = word & 0x7fffffff;      // inner: the hit link
                     } else node_i = skip;

@@ -68,7 +68,7 @@ EXPORTS = [
     "jsrt_stats_get", "jsrt_stats_reset", "jsrt_set_profiling", "jsrt_last_error", "jsrt_bvh_build",
     "jsrt_bvh_node_count", "jsrt_bvh_leaf_object_count", "jsrt_bvh_copy", "jsrt_bvh_free", "jsrt_measure_read_bandwidth",
     "jsrt_bvh_world_boxes", "jsrt_obj_parse", "jsrt_obj_error", "jsrt_obj_counts", "jsrt_obj_copy", "jsrt_obj_material_name",
-    "jsrt_obj_mtllib", "jsrt_obj_free", "jsrt_accum_export", "jsrt_accum_attach",
+    "jsrt_obj_mtllib", "jsrt_obj_free", "jsrt_accum_export", "jsrt_accum_attach", "jsrt_denoise",
 ]
 
 
@@ -100,6 +100,7 @@ def load():
     L.jsrt_accum_device_ptr.restype = vp
     L.jsrt_accum_device_ptr.argtypes = [vp]
     L.jsrt_add_passes.argtypes = [vp, i32]
+    L.jsrt_denoise.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
     L.jsrt_accum_export.argtypes = [vp, vp]
     L.jsrt_accum_attach.argtypes = [vp, vp, i32]
     L.jsrt_primary_hits.argtypes = [vp, vp, vp]
@@ -240,6 +241,15 @@ class Scene:
         var = np.empty((H, W, 4), dtype=np.float32)
         self._ck(self._L.jsrt_read_aov(self._h, nd.ctypes.data, var.ctypes.data))
         return nd, var
+
+    def denoise(self, sigma=1.0, k_sigma=2.0, threshold=5.0, color_log_scale=0.0, rgba8=False):
+        """The GL path's variance-guided denoiser over the passes rendered with FLAG_AOV (include/jsrt.h: jsrt_denoise);
+        returns the filtered mean (H, W, 4) f32, and the 8-bit image too if `rgba8`."""
+        W, H = self.size
+        out = np.empty((H, W, 4), dtype=np.float32)
+        img = np.empty((H, W, 4), dtype=np.uint8) if rgba8 else None
+        self._ck(self._L.jsrt_denoise(self._h, sigma, k_sigma, threshold, color_log_scale, out.ctypes.data, img.ctypes.data if rgba8 else None))
+        return (out, img) if rgba8 else out
 
     def accum_device_ptr(self):
         return self._L.jsrt_accum_device_ptr(self._h)

@@ -134,3 +134,61 @@ def resolve_rgba8(accum, passes):
     a = np.ascontiguousarray(accum, dtype=np.float32)
     lib().orc_resolve_rgba8(a.ctypes.data, H * W, passes, out.ctypes.data)
     return out
+
+
+def denoise_passthrough(accum, variance, sigma=1.0, k_sigma=2.0, threshold=5.0, color_log_scale=0.0):
+    """TEST INFRASTRUCTURE — numpy restatement (FP32) of the GL path's display pass with its variance-guided denoiser:
+    `smartDeNoise` + `main` of the passthrough shader, gl/src/WebGLRendererAdapter.js:183-246.
+    accum = (H, W, 4) colour sums with the per-pixel sample count in w (the shader's uSampleSumTexture and
+    1 / texture_factor); variance = (H, W, >=3) running variance sums (uVarianceTexture, :352-356).  Textures are sampled
+    NEAREST with coordinates clamped to [0, 1] (gl/src/WebGLUtilHelpers.js:452-453).  Returns (H, W, 4) f32: rgb + mean weight."""
+    f = np.float32
+    a = np.asarray(accum, dtype=f)
+    q = np.asarray(variance, dtype=f)
+    H, W = a.shape[:2]
+    tf = (f(1.0) / np.maximum(a[..., 3], f(1.0))).astype(f)
+    mean = (a[..., :3] * tf[..., None]).astype(f)
+    std = np.sqrt((q[..., :3] * tf[..., None]).astype(f)).astype(f)
+    wmean = (a[..., 3] * tf).astype(f)
+    radius = f(np.rint(f(k_sigma) * f(sigma)))                      # GLSL round(); rintf on the device
+    radQ = f(radius * radius)
+    invSigmaQx2 = f(f(.5) / f(f(sigma) * f(sigma)))
+    invSigmaQx2PI = f(f(0.31830988618379067153776752674503) * invSigmaQx2)
+    invThresholdSqx2 = f(f(.5) / f(f(threshold) * f(threshold)))
+    invThresholdSqrt2PI = f(f(0.39894228040143267793994605993439) / f(threshold))
+    xs = ((np.arange(W, dtype=f) + f(0.5)) / f(W)).astype(f)
+    ys = ((np.arange(H, dtype=f) + f(0.5)) / f(H)).astype(f)
+    z = np.zeros((H, W), dtype=f)
+    acc = np.zeros((H, W, 3), dtype=f)
+    accw = np.zeros((H, W), dtype=f)
+    dx = f(-radius)
+    while dx <= radius:
+        pt = f(np.sqrt(f(radQ - f(dx * dx))))
+        dy = f(-pt)
+        while dy <= pt:
+            blur = f(f(np.exp(f(-f(f(dx * dx) + f(dy * dy)) * invSigmaQx2))) * invSigmaQx2PI)
+            cu = np.maximum(np.minimum((xs + f(dx / f(W))).astype(f), f(1.0)), f(0.0))
+            cv = np.maximum(np.minimum((ys + f(dy / f(H))).astype(f), f(1.0)), f(0.0))
+            tx = np.clip(np.floor((cu * f(W)).astype(f)).astype(np.int64), 0, W - 1)
+            ty = np.clip(np.floor((cv * f(H)).astype(f)).astype(np.int64), 0, H - 1)
+            walk = mean[ty][:, tx]
+            s2 = (std[ty][:, tx] ** 2).astype(f)
+            dots = (s2[..., 0] + s2[..., 1] + s2[..., 2]).astype(f)
+            delta = (np.exp((-dots * invThresholdSqx2).astype(f)).astype(f) * invThresholdSqrt2PI * blur).astype(f)
+            z = (z + delta).astype(f)
+            acc = (acc + delta[..., None] * walk).astype(f)
+            accw = (accw + delta * wmean[ty][:, tx]).astype(f)
+            dy = f(dy + f(1.0))
+        dx = f(dx + f(1.0))
+    nz = z != 0
+    out = np.zeros((H, W, 4), dtype=f)
+    out[..., :3] = np.where(nz[..., None], acc / np.where(nz, z, f(1.0))[..., None], acc)
+    out[..., 3] = np.where(nz, accw / np.where(nz, z, f(1.0)), accw)
+    c = out[..., :3]
+    nan = np.isnan(c).any(-1)
+    inf = np.isinf(c).any(-1) & ~nan
+    neg = (c < 0).any(-1) & ~nan & ~inf
+    c[nan] = (1.0, 0.0, 0.5); c[inf] = (0.0, 1.0, 0.5); c[neg] = (0.5, 0.0, 1.0)
+    if color_log_scale > 0:
+        c[...] = (np.log(c + f(1.0)) / f(color_log_scale)).astype(f)
+    return out

@@ -141,3 +141,18 @@ def test_two_devices_one_handle():
     assert np.all(b[..., 3] == 5)
     ia, ib = one.resolve_rgba8().astype(int), two.resolve_rgba8().astype(int)
     assert np.abs(ia - ib).max() <= 1
+
+
+def test_top_level_bvh_equals_linear_walk():
+    """dragon_grid (8 instances of one kdtree): the top-level BVH over the aggregates (scene_flatten.cpp: buildTlas) only
+    prunes — hit IDs, ray census and image equal those of the reference's linear walk over world.objects."""
+    _, mp = scene_blobs("dragon_grid", width=320, height=180, aspect=16 / 9, n=2)
+    lin, tl = _scene(mp, JSRT_TLAS_MIN=0), _scene(mp)
+    ids0, t0 = lin.primary_hits()
+    ids1, t1 = tl.primary_hits()
+    assert np.array_equal(ids0, ids1) and np.array_equal(t0, t1)
+    a, sa = _render(lin, 2)
+    b, sb = _render(tl, 2)
+    for k in CENSUS:
+        assert sa[k] == sb[k], (k, sa[k], sb[k])
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-5)
