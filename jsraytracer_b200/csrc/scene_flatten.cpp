@@ -682,7 +682,10 @@ void flattenScene(const WireDoc& doc, HostScene& out) {
     // a top-level BVH over the aggregates once there are enough of them for it to beat the linear walk (JSRT_TLAS_MIN, 0 = never)
     int n_bvh = 0;
     for (const Top& t : out.tops) if (t.kind == T_BVH && t.node_count > 0) ++n_bvh;
-    int tlas_min = 6;
+    // Measured on the 27-instance dragon grid (profiles/r2_ab.md): the in-walk top-level BVH is 4 % SLOWER than the linear walk
+    // behind the world-box reject (27 cheap, coherent slab tests in prims_kernel against divergent level changes in the
+    // walk, each re-reading the world ray), so it is only used where the linear cost must lose: from 48 aggregates on.
+    int tlas_min = 48;
     if (const char* e = getenv("JSRT_TLAS_MIN")) tlas_min = atoi(e);
     if (tlas_min > 0 && n_bvh >= tlas_min) out.tlas_root = buildTlas(out);
 }

@@ -147,7 +147,7 @@ def test_top_level_bvh_equals_linear_walk():
     """dragon_grid (8 instances of one kdtree): the top-level BVH over the aggregates (scene_flatten.cpp: buildTlas) only
     prunes — hit IDs, ray census and image equal those of the reference's linear walk over world.objects."""
     _, mp = scene_blobs("dragon_grid", width=320, height=180, aspect=16 / 9, n=2)
-    lin, tl = _scene(mp, JSRT_TLAS_MIN=0), _scene(mp)
+    lin, tl = _scene(mp, JSRT_TLAS_MIN=0), _scene(mp, JSRT_TLAS_MIN=2)
     ids0, t0 = lin.primary_hits()
     ids1, t1 = tl.primary_hits()
     assert np.array_equal(ids0, ids1) and np.array_equal(t0, t1)
