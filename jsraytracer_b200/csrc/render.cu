@@ -117,8 +117,7 @@ __global__ void __launch_bounds__(JSRT_BVH_BLOCK, JSRT_BVH_MIN_BLOCKS) bvh_kerne
         __syncthreads();
     }
     Work wp, ws;
-    // (JSRT_COOP_LEAF: the warps' candidate queues live behind the staged nodes)
-    bvh_wave<MODE, COUNT, HAS_SDF, DIRECT, TLAS>(sc, io, &wp, &ws, s_staged_nodes, reinterpret_cast<CoopWarp*>(s_staged_nodes + 2 * sc.n_staged));
+    bvh_wave<MODE, COUNT, HAS_SDF, DIRECT, TLAS>(sc, io, &wp, &ws, s_staged_nodes);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
 
@@ -726,7 +725,7 @@ struct Renderer::Impl {
         grid_extend = has_sdf ? grid_for((const void*)prims_kernel<TM_EXTEND, false, true, false>) : grid_for((const void*)prims_kernel<TM_EXTEND, false, false, false>);
         grid_extend_gen = has_sdf ? grid_for((const void*)prims_kernel<TM_EXTEND, false, true, true>) : grid_for((const void*)prims_kernel<TM_EXTEND, false, false, true>);
         // bvh_kernel: dynamic shared memory for the staged top levels (opt-in above 48 KB)
-        bvh_smem = (size_t)ds.n_staged * sizeof(BvhNode) + (JSRT_COOP_LEAF ? sizeof(CoopWarp) * (JSRT_BVH_BLOCK / 32) : 0);
+        bvh_smem = (size_t)ds.n_staged * sizeof(BvhNode);
         if ((int)bvh_smem > prop.sharedMemPerBlockOptin) throw std::runtime_error("jsrt: staged BVH block exceeds the shared memory of an SM (lower JSRT_STAGE_NODES)");
         #define JSRT_BVH_ATTR(...) CK(cudaFuncSetAttribute((const void*)bvh_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bvh_smem))
         if (has_sdf) { JSRT_BVH_ATTR(TM_EXTEND, false, true, false, false); JSRT_BVH_ATTR(TM_EXTEND, true, true, false, false); JSRT_BVH_ATTR(TM_SHADOW, false, true, false, false); JSRT_BVH_ATTR(TM_SHADOW, true, true, false, false); }

@@ -608,25 +608,6 @@ JSRT_DEV void tie_wave(const DeviceScene& sc, const TraceIO& io) {
     }
 }
 
-// Warp-cooperative leaf tests (JSRT_COOP_LEAF, triangle meshes).  With every lane testing its own parked leaf, the
-// triangle code ran with 9 of 32 lanes and took a quarter of bvh_kernel's issue slots (profiles/r2_ncu_summary.md).
-// Instead a lane that reaches a leaf appends (lane, triangle) candidates to a queue of its warp in shared memory and
-// keeps walking; once 32 candidates wait (or lanes wait for nothing else) the WHOLE warp tests one candidate per
-// lane, reading the owner's ray from shared memory and returning the result through a shared atomic (an occlusion
-// bit per lane for shadow rays; min over (distance, primitive) — exactly the tie rule — for closest-hit rays).
-#ifndef JSRT_COOP_LEAF
-#define JSRT_COOP_LEAF 0
-#endif
-constexpr int kCoopCap = 96;
-struct CoopWarp {
-    float ray[8][32];               // per lane: local origin, local direction, minD, pruning bound
-    int meta[4][32];                // per lane: first_prim - tri_base, ray index, BVH ordinal, primary-ray flag
-    unsigned long long best[32];    // closest-hit: (float bits of t) << 32 | placed primitive
-    unsigned cand[kCoopCap];        // lane << 27 | triangle index
-    float cand_t[kCoopCap];
-    int ncand; unsigned hit; int pad[2];
-};
-
 // bvh_wave: BVHAggregateNode.intersect (src/aggregates.js:207-225) for the rays of the work list.
 // Persistent threads, one ray per lane, lanes refilled individually from a warp-local pool of list
 // entries (one atomicAdd per JSRT_POOL_BATCH rays): a lane whose walk ends takes the next ray instead of
@@ -644,7 +625,7 @@ struct CoopWarp {
 // primitives and the root boxes and accumulated or dropped every ray that needs no walk — so entry i of the queue is
 // ray i: o.xyz | pixel, d.xyz | pass, contribution.rgb | first BVH.  No work list, no partial-hit buffer.
 template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT, bool TLAS>
-JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other, const float4* __restrict__ s_nodes, CoopWarp* coop) {
+JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other, const float4* __restrict__ s_nodes) {
     constexpr bool ANY_HIT = (MODE == TM_SHADOW);
     constexpr int BATCH = JSRT_POOL_BATCH;      // list entries fetched per atomicAdd
     // A warp runs three phases per iteration, each only when enough lanes need it, so that the
@@ -665,11 +646,6 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     int pending = -1;                     // postponed leaf word; -(leaf + 2): a second leaf is waiting behind it
     LocalRay r; r.lo = f3(0, 0, 0); r.ld = f3(0, 0, 1); r.inv = r.ld; r.sgn = r.ld; r.par = false;
     float minD_v = 0.f;                   // extend only (the shadow window is a constant)
-#if JSRT_COOP_LEAF
-    #define JSRT_COOP_FULL full
-#else
-    #define JSRT_COOP_FULL false
-#endif
     #define JSRT_MIND ((MODE == TM_SHADOW) ? 0.0001f : minD_v)
     #define JSRT_MAXD ((MODE == TM_SHADOW) ? 1.0f : CUDART_INF_F)
     float hi = CUDART_INF_F;              // min(maxD, local_best, best.t): the pruning bound of :209
@@ -682,16 +658,6 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     constexpr int kTlasLevel = -2;
     constexpr bool use_tlas = TLAS;          // (a template flag: the extra state must not cost the single-mesh kernels registers)
     int want = -1, resume = kNodeEnd;
-#if JSRT_COOP_LEAF
-    CoopWarp& cw = coop[threadIdx.x >> 5];
-    int my_out = 0;                       // candidates of this lane waiting in the warp's queue
-    bool full = false;                    // the queue had no room for this lane's leaf: retry after the next test phase
-    if (lane == 0) { cw.ncand = 0; cw.hit = 0; }
-    cw.best[lane] = ~0ull;
-    __syncwarp();
-#else
-    (void)coop;
-#endif
     float local_best = CUDART_INF_F, local_lo = 0.f; int local_prim = -1;
     Work* work = work_other;
     const float4* const all_nodes = reinterpret_cast<const float4*>(sc.nodes);
@@ -711,12 +677,6 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
         node_i = tb.x + octant * (tb.w >> 8); first_prim = ta.z; tri_base = tb.z;
         local_best = CUDART_INF_F; local_prim = -1; local_lo = 0.f; pending = -1;
         hi = fminf(JSRT_MAXD, best.t);
-#if JSRT_COOP_LEAF
-        cw.ray[0][lane] = r.lo.x; cw.ray[1][lane] = r.lo.y; cw.ray[2][lane] = r.lo.z;
-        cw.ray[3][lane] = r.ld.x; cw.ray[4][lane] = r.ld.y; cw.ray[5][lane] = r.ld.z;
-        cw.ray[6][lane] = JSRT_MIND; cw.ray[7][lane] = hi;
-        cw.meta[0][lane] = first_prim - tri_base; cw.meta[1][lane] = cur; cw.meta[2][lane] = bi; cw.meta[3][lane] = (COUNT && work == work_primary) ? 1 : 0;
-#endif
     };
 
     for (;;) {
@@ -784,82 +744,6 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
         // Policy: run the leaf phase when LEAF_T lanes hold a leaf, or when fewer than PROG_T lanes could still
         // walk (the others are parked, blocked or idle): a blocked or finished lane waits for company instead of
         // dragging the whole warp through the triangle code with a handful of lanes.
-#if JSRT_COOP_LEAF
-        {
-            __syncwarp();
-            const int nc = min(*reinterpret_cast<volatile int*>(&cw.ncand), kCoopCap);
-            const unsigned wait_mask = __ballot_sync(FULL, active && my_out > 0 && node_i == kNodeEnd && pending == -1);
-            const unsigned full_mask = __ballot_sync(FULL, active && full);
-            const unsigned walk_mask = __ballot_sync(FULL, active && node_i != kNodeEnd && pending >= -1 && !full);
-            if (nc > 0 && (nc >= 32 || full_mask != 0u || __popc(wait_mask) >= 8 || walk_mask == 0u)) {
-                for (int base = 0; base < nc; base += 32) {
-                    const int e = base + lane;
-                    if (e < nc) {
-                        const unsigned c = cw.cand[e];
-                        const int owner = (int)(c >> 27), tri = (int)(c & 0x7ffffffu);
-                        const float3 lo = f3(cw.ray[0][owner], cw.ray[1][owner], cw.ray[2][owner]), ld = f3(cw.ray[3][owner], cw.ray[4][owner], cw.ray[5][owner]);
-                        const float mn = cw.ray[6][owner], h = cw.ray[7][owner];
-                        if (COUNT) { Work* w = cw.meta[3][owner] ? work_primary : work_other; ++w->leaf_prims; }
-                        float t = triangle_intersect(sc.tris, tri, lo, ld, mn, h);
-                        if (t > mn && t < JSRT_MAXD) {          // :213 (the owner applies the rank tie rule through the packed minimum)
-                            if (ANY_HIT) atomicOr(&cw.hit, 1u << owner);
-                            else atomicMin(&cw.best[owner], ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)(tri + cw.meta[0][owner]));
-                        } else t = -CUDART_INF_F;
-                        cw.cand_t[e] = t;
-                    }
-                }
-                __syncwarp();
-#if JSRT_TRI_TIE
-                if (!ANY_HIT) {
-                    // FP32 near-ties between a candidate and its ray's winner of this round go to the tie list (tie_wave)
-                    for (int base = 0; base < nc; base += 32) {
-                        const int e = base + lane;
-                        if (e < nc) {
-                            const float t = cw.cand_t[e];
-                            if (t > 0.f) {
-                                const unsigned c = cw.cand[e];
-                                const int owner = (int)(c >> 27), pi = (int)(c & 0x7ffffffu) + cw.meta[0][owner];
-                                const unsigned long long key = cw.best[owner];
-                                const int bp = (int)(unsigned)key; const float bt = __uint_as_float((unsigned)(key >> 32));
-                                if (pi != bp && fabsf(t - bt) <= 1e-6f * fabsf(t)) {
-                                    const int k = atomicAdd(io.tie_count, 1);
-                                    if (k < io.tie_cap) io.tie_list[k] = make_int4(cw.meta[1][owner], cw.meta[2][owner], bp, pi);
-                                }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-#endif
-                if (active && my_out > 0) {
-                    if (ANY_HIT) {
-                        if ((*reinterpret_cast<volatile unsigned*>(&cw.hit) >> lane) & 1u) { local_best = 0.5f; local_prim = first_prim; local_lo = 0.f; node_i = kNodeEnd; pending = -1; }
-                    } else {
-                        const unsigned long long key = cw.best[lane];
-                        if (key != ~0ull) {
-                            const float t = __uint_as_float((unsigned)(key >> 32)); const int pi = (int)(unsigned)key;
-                            const bool take = t < local_best || (t == local_best && pi < local_prim);
-#if JSRT_TRI_TIE
-                            if (local_prim >= 0 && pi != local_prim && fabsf(t - local_best) <= 1e-6f * fabsf(t)) {
-                                const int k = atomicAdd(io.tie_count, 1);
-                                if (k < io.tie_cap) io.tie_list[k] = make_int4(cur, bi, take ? pi : local_prim, take ? local_prim : pi);
-                            }
-#endif
-                            if (take) { local_best = t; local_prim = pi; local_lo = 0.f; }
-                            cw.best[lane] = ~0ull;
-                            hi = fminf(hi, JSRT_TRI_TIE ? fmaf(fabsf(local_best), 2e-6f, local_best) : local_best);
-                            cw.ray[7][lane] = hi;
-                        }
-                    }
-                    my_out = 0;
-                }
-                full = false;
-                __syncwarp();
-                if (lane == 0) { cw.ncand = 0; cw.hit = 0; }
-                __syncwarp();
-            }
-        }
-#endif
         const unsigned pend_mask = __ballot_sync(FULL, active && pending != -1);
         const unsigned prog_mask = __ballot_sync(FULL, active && node_i != kNodeEnd && pending >= -1);
         if (pend_mask && (__popc(pend_mask) >= LEAF_T || __popc(prog_mask) < PROG_T)) {
@@ -904,17 +788,12 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
         }
 
         if (active) {
-#if JSRT_COOP_LEAF
-            #define JSRT_COOP_DRAINED (my_out == 0)
-#else
-            #define JSRT_COOP_DRAINED true
-#endif
             if (use_tlas && want >= 0) {
                 // ---- a leaf of the top-level BVH: enter that aggregate -------------------------
                 const float4 o4 = io.o[cur], d4 = io.d[cur];
                 bi = want; want = -1;
                 enter(f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
-            } else if (use_tlas && node_i == kNodeEnd && pending == -1 && JSRT_COOP_DRAINED) {
+            } else if (use_tlas && node_i == kNodeEnd && pending == -1) {
                 if (tri_base != kTlasLevel) {
                     // ---- an aggregate's tree is finished: merge, back to the top-level walk ----
                     const int top_i = __ldg(sc.bvh_tops + bi);
@@ -930,7 +809,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                         hi = fminf(JSRT_MAXD, best.t);
                     }
                 } else cur = -2 - cur;              // the top-level walk is over
-            } else if (node_i == kNodeEnd && pending == -1 && JSRT_COOP_DRAINED) {
+            } else if (node_i == kNodeEnd && pending == -1) {
                 // ---- tree finished: merge into the running closest hit, next BVH or done -------
                 const int top_i = __ldg(sc.bvh_tops + bi);
                 if (local_best > JSRT_MIND && local_best < JSRT_MAXD && better_hit(local_best, top_i, best)) {
@@ -952,7 +831,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 // ---- phase 3: up to NODE_STEPS nodes of BVHAggregateNode.intersect (src/aggregates.js:207-225)
                 // per iteration, so the warp votes of phases 1-2 are paid once per few nodes
                 #pragma unroll 1
-                for (int rep = 0; rep < NODE_STEPS && node_i != kNodeEnd && pending >= -1 && !JSRT_COOP_FULL; ++rep) {
+                for (int rep = 0; rep < NODE_STEPS && node_i != kNodeEnd && pending >= -1; ++rep) {
                     float4 n0, n1;
 #if JSRT_LDS_ASM
                     if (node_i < n_staged) lds_node(s_base + 32u * (unsigned)node_i, n0, n1);
@@ -966,16 +845,6 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                     if (hit_box) {
                         if (word >= 0) {            // leaf
                             if (tri_base == kTlasLevel) { want = word & 0xffffff; resume = skip; node_i = kNodeEnd; }      // an aggregate: entered after the loop
-#if JSRT_COOP_LEAF
-                            else if (tri_base >= 0) {           // triangle mesh: the leaf's triangles join the warp's queue, the walk goes on
-                                const int cnt = (int)((unsigned)word >> 24), rel = word & 0xffffff;
-                                const int pos = atomicAdd(&cw.ncand, cnt);
-                                if (pos + cnt <= kCoopCap) {
-                                    for (int k = 0; k < cnt; ++k) cw.cand[pos + k] = ((unsigned)lane << 27) | (unsigned)(tri_base + rel + k);
-                                    my_out += cnt; node_i = skip;
-                                } else { atomicSub(&cw.ncand, cnt); full = true; }     // no room: this node is tested again after the next test phase
-                            }
-#endif
                             else if (pending == -1) { pending = word; node_i = skip; }
                             else pending = -(pending + 2);      // one leaf already parked: block here until it is tested
                         } else node_i = word & 0x7fffffff;      // inner: the hit link
@@ -986,8 +855,6 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     }
     #undef JSRT_MIND
     #undef JSRT_MAXD
-    #undef JSRT_COOP_DRAINED
-    #undef JSRT_COOP_FULL
 }
 
 // ---------------------------------------------------------------------------------

@@ -19,6 +19,13 @@ Phong terms with falloff, the shadow-ray walk through the 10 712-triangle BVH (l
 plane pixel), reflection rays that miss (black, `src/world.js:32-36`), accumulation over 16 jittered passes and the
 8-bit resolve (`src/pixelbuffer.js:39-49`).  Bar: every such pixel within 2 levels, >= 99.9 % within 1 level,
 >= 94 % bit-identical.  The mesh silhouette against the sky is compared too (hit / no hit, away from edges).
+
+The green channel was examined for a statistical pin of the RandomSampleAreaLight (G - R on plane pixels = the area
+light's term: the plane's colour is grey and the light's is (0,1,0)) and cannot be used: the two screenshots disagree
+with EACH OTHER by 2-3x in that term (mean G - R on the lit plane 2.92 vs 6.27 levels, on the shadowed plane 5.18 vs
+15.17) and their ratio to a render of today's test.mjs varies from 0.57 to 4.9 across the image, i.e. the bolt light was
+moved / resized between the two screenshots and again before test.mjs was committed.  test_area_light_term_is_stale
+pins that finding, so that the exclusion of G is a checked fact rather than a convenience.
 """
 import math
 import os
@@ -98,6 +105,22 @@ def test_fixture_is_the_reference_png():
         pytest.skip("reference tree not mounted (GPU box)")
     from PIL import Image
     assert np.array_equal(np.asarray(Image.open(ref).convert("RGB")), np.load(FIXTURE)["shot10"])
+
+
+def test_area_light_term_is_stale():
+    """G - R on plane pixels (the green area light's contribution) differs between the reference's own two screenshots by
+    more than any sampling noise could explain (16 spp x 4 light samples over ~195 000 pixels): they were not rendered
+    from one scene, so neither pins the area light of today's tests/tie_fighter/test.mjs:12-20."""
+    _, _, cls, interior = _setup()
+    shots = np.load(FIXTURE)
+    g_minus_r = {k: shots[k][..., 1].astype(np.int32) - shots[k][..., 0] for k in ("shot10", "shot11")}
+    for c, lo in ((1, 1.8), (2, 2.5)):
+        m = interior & (cls == c)
+        a, b = g_minus_r["shot10"][m].mean(), g_minus_r["shot11"][m].mean()
+        assert b / a > lo, (c, a, b)
+        # ... while R and B agree between them to within one grey level on the same pixels (the pinned part)
+        d = np.abs(shots["shot10"][..., [0, 2]].astype(np.int32) - shots["shot11"][..., [0, 2]])[m]
+        assert d.max() <= 4 and (d <= 1).mean() > 0.99
 
 
 def test_oracle_matches_reference_screenshot():
