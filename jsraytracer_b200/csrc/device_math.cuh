@@ -158,8 +158,8 @@ JSRT_DEV float split_t(double t, float* t_lo) {
 // dot products and the Cramer solve are f64 (see the note on struct Tri), the result is stored f32.
 JSRT_DEV float3 triangle_bary(const Tri* __restrict__ tris, int idx, float3 P) {
     const float4* tp = reinterpret_cast<const float4*>(tris + idx);
-    const float4 b = __ldg(tp + 1), c = __ldg(tp + 2), e = __ldg(tp + 3);
-    const double2 g = __ldg(reinterpret_cast<const double2*>(tp + 4)), h = __ldg(reinterpret_cast<const double2*>(tp + 5));
+    const float4 b = __ldg(tp + 1), c = __ldg(tp + 4), e = __ldg(tp + 5);
+    const double2 g = __ldg(reinterpret_cast<const double2*>(tp + 6)), h = __ldg(reinterpret_cast<const double2*>(tp + 7));
     const float v2x = (float)dsub(P.x, b.x), v2y = (float)dsub(P.y, b.y), v2z = (float)dsub(P.z, b.z);
     const double d20 = ddot3(v2x, v2y, v2z, c.x, c.y, c.z), d21 = ddot3(v2x, v2y, v2z, e.x, e.y, e.z);
     const double v = dmul(dsub(dmul(g.y, d20), dmul(h.x, d21)), h.y), w = dmul(dsub(dmul(g.x, d21), dmul(h.x, d20)), h.y);
@@ -170,22 +170,22 @@ JSRT_DEV float3 triangle_bary(const Tri* __restrict__ tris, int idx, float3 P) {
 // its own strict tests and the tie rule); the reference evaluates the barycentrics regardless and the
 // caller filters, which gives the same result as skipping them for a t that will be rejected anyway.
 JSRT_DEV float triangle_intersect(const Tri* __restrict__ tris, int idx, float3 o, float3 d, float accept_lo, float accept_hi) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(tris + idx));
+    const float4* tp = reinterpret_cast<const float4*>(tris + idx);
+    const float4 a = __ldg(tp);
     const float den = a.x * d.x + a.y * d.y + a.z * d.z;
-    const float t = (den != 0.f) ? (a.w - (a.x * o.x + a.y * o.y + a.z * o.z)) / den : -CUDART_INF_F;
+    // (delta - n.o) / den with the SFU reciprocal (2 ulp) instead of the IEEE sequence (13 instructions with a branch):
+    // distances already carry FP32 noise of that size, near-ties are settled in f64 by tie_wave (1e-6 window)
+    const float t = (den != 0.f) ? __fdividef(a.w - (a.x * o.x + a.y * o.y + a.z * o.z), den) : -CUDART_INF_F;
     if (!(t > accept_lo && t <= accept_hi) || t < 0.f || isinf(t)) return -CUDART_INF_F;
     const float3 P = ray_point(o, d, t);
     {
         // FP32 fast path: the reference tests the f32-rounded barycentrics against [0, 1]; for a well-conditioned
-        // triangle the FP32 Cramer solve is within ~1e-6 of them, so any point whose barycentrics clear 0 and 1
-        // by 1e-4 is decided here (hit or miss); everything else (edges, slivers via the NaN in d00f) falls
-        // through to the reference's arithmetic below.
-        const float4* tp = reinterpret_cast<const float4*>(tris + idx);
-        const float4 b = __ldg(tp + 1), c = __ldg(tp + 2), e = __ldg(tp + 3);
+        // triangle the FP32 solve (two dot products with host-folded vectors, struct Tri) is within ~1e-6 of them, so
+        // any point whose barycentrics clear 0 and 1 by 1e-4 is decided here (hit or miss); everything else (edges,
+        // slivers via the NaNs in ax / bx) falls through to the reference's arithmetic below.
+        const float4 b = __ldg(tp + 1), A = __ldg(tp + 2), B = __ldg(tp + 3);
         const float v2x = P.x - b.x, v2y = P.y - b.y, v2z = P.z - b.z;
-        const float d20 = v2x * c.x + v2y * c.y + v2z * c.z, d21 = v2x * e.x + v2y * e.y + v2z * e.z;
-        const float inv = 1.0f / (c.w * e.w - b.w * b.w);
-        const float v = (e.w * d20 - b.w * d21) * inv, w = (c.w * d21 - b.w * d20) * inv, u = 1.f - v - w;
+        const float v = v2x * A.x + v2y * A.y + v2z * A.z, w = v2x * B.x + v2y * B.y + v2z * B.z, u = 1.f - v - w;
         const float m = 1e-4f;
         // (all three NaN for a sliver: both tests fail and the f64 path decides)
         const float lo3 = fminf(fminf(u, v), w), hi3 = fmaxf(fmaxf(u, v), w);

@@ -209,8 +209,11 @@ struct Flattener {
             t.inv_denom = 1.0 / (t.d00 * t.d11 - t.d01 * t.d01);
             // f32 fast path only for well-conditioned triangles: sin^2 of the corner angle = denom / (d00 d11)
             const double cond = (t.d00 * t.d11 - t.d01 * t.d01) / (t.d00 * t.d11);
-            t.d00f = (cond > 1e-2) ? (float)t.d00 : std::numeric_limits<float>::quiet_NaN();
-            t.d11f = (float)t.d11; t.d01f = (float)t.d01;
+            for (int k = 0; k < 3; ++k) {
+                (&t.ax)[k] = (float)((t.d11 * v0[k] - t.d01 * v1[k]) * t.inv_denom);
+                (&t.bx)[k] = (float)((t.d00 * v1[k] - t.d01 * v0[k]) * t.inv_denom);
+            }
+            if (!(cond > 1e-2)) t.ax = t.bx = std::numeric_limits<float>::quiet_NaN();      // u, v, w all NaN: every comparison fails
             TriShade s{};
             // psdata: {UV:[..], normal:[..]} — an Array here means the reference's
             // lossy Triangle.serialize (src/geometry.js:355-357) wrote `ps` twice.

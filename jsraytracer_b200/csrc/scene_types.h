@@ -36,14 +36,20 @@ struct Prim {
 };
 
 // Triangle constants, computed like the reference constructor (src/geometry.js:335-354) in f64 from
-// the f32 vertices.  96 bytes = six 128-bit loads; the plane test needs only the first.  The
+// the f32 vertices.  128 bytes = one cache line, eight 128-bit loads; the plane test needs only the first, the FP32
+// inside test of a candidate the next three, the reference-arithmetic test (edges, slivers) the rest.  The
 // barycentric constants stay f64: for sliver triangles (d00 d11 - d01^2 -> 0) their f32 roundings alone
 // are larger than the determinant, and real meshes are full of slivers (x_wing_fighter.obj).
 struct Tri {
     float nx, ny, nz, delta;      // normal (normalised v0 x v1), delta = normal . p0
-    float p0x, p0y, p0z, d01f;    // f32 copies of the barycentric constants for the fast path;
-    float v0x, v0y, v0z, d00f;    // d00f is NaN for ill-conditioned (sliver) triangles, which sends every
-    float v1x, v1y, v1z, d11f;    // test of such a triangle down the f64 path
+    float p0x, p0y, p0z, pad0;
+    // FP32 fast path: the Cramer solve of Triangle.toBarycentric folded into two vectors on the host (in f64),
+    // v = (P - p0) . A, w = (P - p0) . B with A = (d11 v0 - d01 v1) / denom, B = (d00 v1 - d01 v0) / denom.
+    // ax and bx are NaN for ill-conditioned (sliver) triangles, which sends every test of such a triangle down the f64 path
+    float ax, ay, az, pad1;
+    float bx, by, bz, pad2;
+    float v0x, v0y, v0z, pad3;
+    float v1x, v1y, v1z, pad4;
     double d00, d11;
     double d01, inv_denom;        // 1 / (d00 d11 - d01^2)
 };

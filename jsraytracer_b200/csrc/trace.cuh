@@ -663,7 +663,8 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     const float4* const all_nodes = reinterpret_cast<const float4*>(sc.nodes);
     // 32-bit shared-window address of the staged block, formed once (the generic pointer made the compiler rebuild it
     // from SR_CgaCtaId at every node step: 4 of the 52 instructions of the loop)
-    const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_nodes);
+    unsigned s_base = (unsigned)__cvta_generic_to_shared(s_nodes);
+    asm volatile("" : "+r"(s_base));      // opaque: otherwise it is rebuilt from SR_CgaCtaId (an S2R + two LEAs) at every node step
 
     // enter BVH number `bi` of the scene (Aggregate.intersect / BVHAggregate.intersect, src/aggregates.js:43-46)
     auto enter = [&](float3 o, float3 d) {
@@ -830,26 +831,40 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
             } else {
                 // ---- phase 3: up to NODE_STEPS nodes of BVHAggregateNode.intersect (src/aggregates.js:207-225)
                 // per iteration, so the warp votes of phases 1-2 are paid once per few nodes
-                #pragma unroll 1
-                for (int rep = 0; rep < NODE_STEPS && node_i != kNodeEnd && pending >= -1; ++rep) {
-                    float4 n0, n1;
-#if JSRT_LDS_ASM
-                    if (node_i < n_staged) lds_node(s_base + 32u * (unsigned)node_i, n0, n1);
-#else
-                    if (node_i < n_staged) { n0 = s_nodes[2 * node_i]; n1 = s_nodes[2 * node_i + 1]; }
-#endif
-                    else load_node(all_nodes + 2 * node_i, n0, n1);
-                    const int skip = __float_as_int(n1.z), word = __float_as_int(n1.w);
-                    if (COUNT) ++work->nodes;
-                    const bool hit_box = r.par ? slab_general(n0, n1, r, JSRT_MIND, JSRT_MAXD, hi) : slab_fast(n0, n1, r, JSRT_MIND, hi);
-                    if (hit_box) {
-                        if (word >= 0) {            // leaf
-                            if (tri_base == kTlasLevel) { want = word & 0xffffff; resume = skip; node_i = kNodeEnd; }      // an aggregate: entered after the loop
-                            else if (pending == -1) { pending = word; node_i = skip; }
-                            else pending = -(pending + 2);      // one leaf already parked: block here until it is tested
-                        } else node_i = word & 0x7fffffff;      // inner: the hit link
-                    } else node_i = skip;
+                // The step is branch-free after the box test (selects instead of the nested if / else: the compiler's version
+                // spent 25 issue slots per step on BSSY / BRA / BSYNC with 3-13 lanes, profiles/r2/ncu_r2h_*), and rays with a
+                // parallel axis (AABB.get_intersects' `else` rule, src/geometry.js:194,205) take their own copy of the loop so
+                // that the common one carries no test for them.
+                #define JSRT_NODE_STEP(SLAB)                                                                                       \
+                    {                                                                                                              \
+                        float4 n0, n1;                                                                                             \
+                        if (node_i < n_staged) lds_node(s_base + 32u * (unsigned)node_i, n0, n1);                                  \
+                        else load_node(all_nodes + 2 * node_i, n0, n1);                                                            \
+                        const int skip = __float_as_int(n1.z), word = __float_as_int(n1.w);                                        \
+                        if (COUNT) ++work->nodes;                                                                                  \
+                        const bool hit_box = SLAB;                                                                                 \
+                        const bool leaf_hit = hit_box && word >= 0;                                                                \
+                        int next = hit_box ? (word & 0x7fffffff) : skip;              /* inner: the hit link; missed: the skip link */ \
+                        if (use_tlas && tri_base == kTlasLevel) {                                                                  \
+                            if (leaf_hit) { want = word & 0xffffff; resume = skip; next = kNodeEnd; }   /* an aggregate: entered after the loop */ \
+                        } else {                                                                                                   \
+                            /* leaf: park it and go on; one leaf already parked: block here (same node again) until it is tested */ \
+                            const bool park = pending == -1;                                                                       \
+                            const int parked = park ? word : -(pending + 2);                                                       \
+                            const int after = park ? skip : node_i;                                                                \
+                            pending = leaf_hit ? parked : pending;                                                                 \
+                            next = leaf_hit ? after : next;                                                                        \
+                        }                                                                                                          \
+                        node_i = next;                                                                                             \
+                    }
+                if (!r.par) {
+                    #pragma unroll 1
+                    for (int rep = 0; rep < NODE_STEPS && node_i != kNodeEnd && pending >= -1; ++rep) JSRT_NODE_STEP(slab_fast(n0, n1, r, JSRT_MIND, hi))
+                } else {
+                    #pragma unroll 1
+                    for (int rep = 0; rep < NODE_STEPS && node_i != kNodeEnd && pending >= -1; ++rep) JSRT_NODE_STEP(slab_general(n0, n1, r, JSRT_MIND, JSRT_MAXD, hi))
                 }
+                #undef JSRT_NODE_STEP
             }
         }
     }
