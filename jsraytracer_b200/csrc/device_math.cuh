@@ -23,7 +23,21 @@ JSRT_DEV float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, 
 JSRT_DEV float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 JSRT_DEV float3 cross3(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 // Vec.normalized(): unchanged when the norm is <= 1e-5 (src/math.js:242-245)
-JSRT_DEV float3 normalized3(float3 a) { const float n = sqrtf(dot3(a, a)); return (n > 0.00001f) ? a * (1.0f / n) : a; }
+// (FP32 with the SFU reciprocal square root, ~2 ulp, instead of IEEE sqrt + IEEE division: 26 -> 10 instructions, and
+// shade_kernel normalises ten vectors per hit — 8.5 % of its instructions, profiles/r2/ncu_r2j_*.  JSRT_FAST_NORMALIZE=0: A/B)
+#ifndef JSRT_FAST_NORMALIZE
+#define JSRT_FAST_NORMALIZE 1
+#endif
+JSRT_DEV float3 normalized3(float3 a) {
+#if JSRT_FAST_NORMALIZE
+    const float n2 = dot3(a, a);
+    return (n2 > 0.00001f * 0.00001f) ? a * rsqrtf(n2) : a;
+#else
+    const float n = sqrtf(dot3(a, a)); return (n > 0.00001f) ? a * (1.0f / n) : a;
+#endif
+}
+// 1 / x on the SFU (1 ulp, denormals flushed): reciprocal ray directions of the slab tests
+JSRT_DEV float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 // Ray.getPoint: two f32 roundings (product, then sum)
 JSRT_DEV float3 ray_point(float3 o, float3 d, float t) {
     return f3(__fadd_rn(o.x, __fmul_rn(d.x, t)), __fadd_rn(o.y, __fmul_rn(d.y, t)), __fadd_rn(o.z, __fmul_rn(d.z, t)));
@@ -303,10 +317,30 @@ JSRT_DEV double sdf_eval(const SdfInstr* __restrict__ code, const Xform64* __res
         const float4 f = fv;
         // the next instruction is fetched while this one executes (straight-line code: pc + 1 always exists before S_END)
         if (op != S_END) { i0 = __ldg(reinterpret_cast<const int4*>(code + pc + 1)); fv = __ldg(reinterpret_cast<const float4*>(code + pc + 1) + 1); }
-        if (op <= S_TETRA) {
+        if (op <= S_TETRA || op == S_CROSS) {
             if (op == S_END) return dtop;
             double v;
-            if (op == S_BOX) {                                                                            // src/sdf.js:276-279
+            if (op == S_CROSS) {
+                // min over BoxSDF(Inf, a, a), BoxSDF(a, Inf, a), BoxSDF(a, a, Inf) (src/sdf.js:276-279 under :83-88): the
+                // component of q on a bar's infinite axis is -Inf, so max(q, 0) is 0 there and the bar's distance is the 2-D
+                // box distance of the other two — exactly the S_BOX arithmetic below with that component dropped (adding
+                // 0 * 0 to the sum of squares does not round) — and all three share q = |p| - a.
+                const float qx = __fsub_rn(fabsf(p.x), f.x), qy = __fsub_rn(fabsf(p.y), f.x), qz = __fsub_rn(fabsf(p.z), f.x);
+                const float mx = fmaxf(qx, 0.f), my = fmaxf(qy, 0.f), mz = fmaxf(qz, 0.f);
+                const int npos = (mx > 0.f) + (my > 0.f) + (mz > 0.f);
+                double lx, ly, lz;                    // |max(q, 0)| of the bar along x, y, z
+                if (npos <= 1) { lx = (double)(my + mz); ly = (double)(mx + mz); lz = (double)(mx + my); }      // at most one term: exact
+                else {
+                    const double x2 = dmul((double)mx, (double)mx), y2 = dmul((double)my, (double)my);
+                    lx = (my > 0.f && mz > 0.f) ? sqrt(fma((double)mz, (double)mz, y2)) : (double)(my + mz);
+                    ly = (mx > 0.f && mz > 0.f) ? sqrt(fma((double)mz, (double)mz, x2)) : (double)(mx + mz);
+                    lz = (mx > 0.f && my > 0.f) ? sqrt(fma((double)my, (double)my, x2)) : (double)(mx + my);
+                }
+                const double bx = dadd(lx, (double)fminf(fmaxf(qy, qz), 0.f)), by = dadd(ly, (double)fminf(fmaxf(qx, qz), 0.f)),
+                             bz = dadd(lz, (double)fminf(fmaxf(qx, qy), 0.f));
+                // (NaN like the three boxes: a NaN coordinate, or an infinite one — |p| - Inf on that bar's own axis)
+                v = (qx != qx || qy != qy || qz != qz || isinf(qx) || isinf(qy) || isinf(qz)) ? CUDART_NAN : jsd_min(jsd_min(bx, by), bz);
+            } else if (op == S_BOX) {                                                                            // src/sdf.js:276-279
                 // q = |p| - size: one f64 subtraction of f32 values stored f32 = the FP32 subtraction
                 const float qx = __fsub_rn(fabsf(p.x), f.x), qy = __fsub_rn(fabsf(p.y), f.y), qz = __fsub_rn(fabsf(p.z), f.z);
                 const float mx = fmaxf(qx, 0.f), my = fmaxf(qy, 0.f), mz = fmaxf(qz, 0.f);                    // Vec.max(q, 0): q.w = 0

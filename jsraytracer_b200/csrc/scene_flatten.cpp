@@ -513,10 +513,14 @@ struct Flattener {
     // ray walks through, staged in shared memory by bvh_kernel (DeviceScene::n_staged); behind it the remaining nodes of
     // each layout in depth-first order (siblings' subtrees stay close together for the L1 / L2 lines).
     void assembleNodes() {
-        int budget = 4096;                                   // nodes in the staged block: 128 KB of shared memory (JSRT_STAGE_NODES)
-        if (const char* e = getenv("JSRT_STAGE_NODES")) { const int v = atoi(e); if (v >= 0 && v <= 7168) budget = v; }
         size_t n_layouts = 0, total = 0;
         for (const TreeBuild& tb : trees) { n_layouts += tb.layouts.size(); for (auto& l : tb.layouts) total += l.size(); }
+        // Nodes in the staged block (JSRT_STAGE_NODES overrides): everything when the scene's trees fit the 224 KB a CTA can
+        // have (bunny_path: 5.5 k nodes, +2 % over a 4 096-node block), otherwise 4 096 = 128 KB, which leaves the other
+        // half of the SM's unified array to L1 for the deep nodes (dragon, 200 k nodes: 7 168 staged is 2.3 % slower than
+        // 4 096, 2 048 within noise of it: profiles/r2/ab_r2j_stage_*)
+        int budget = total <= 7168 ? 7168 : 4096;
+        if (const char* e = getenv("JSRT_STAGE_NODES")) { const int v = atoi(e); if (v >= 0 && v <= 7168) budget = v; }
         if (total >= (size_t)kNodeEnd) fail("jsrt: more than 2^31 BVH nodes");
         out.nodes.assign(total, BvhNode{});
         // every layout owns at least its root in the front block (the root of layout q is found at root + q * stride)

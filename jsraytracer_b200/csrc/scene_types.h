@@ -168,6 +168,8 @@ enum SdfOp : int {
     S_SEND,        //                                     pop it; enclosing scale *= popped   (Sequence / Recursive transformers
                    //                                     return their own product, src/sdf.js:387-394,408-415)
     S_MULS_MIN,    //                                     pop d; top = min(top, d * scale)   (RecursiveTransformUnion step, src/sdf.js:353-354)
+    S_CROSS,       // f[0] = a: UnionSDF of BoxSDF(Inf, a, a), BoxSDF(a, Inf, a), BoxSDF(a, a, Inf) — the Menger "cross" — as one leaf
+                   //           (idx = 1 / 2 folds like the other leaves): three box distances from one q = |p| - a
     // ---- material program (getMaterialData, src/sdf.js:86-88,102-104,119-121,149-154,...): straight-line code over a
     // stack of {distance, basecolor, UV}; every leaf is evaluated, selections / blends fold them bottom-up.
     MP_END = 32,

@@ -131,13 +131,13 @@ JSRT_DEV float placed_prim_intersect(const DeviceScene& sc, int prim_index, floa
 // (hit/miss-link) layouts of the same tree that visit the nearer child first.
 // tuning constants of bvh_wave (measured on bunny_path / dragon 1080p, profiles/r1_ncu_summary.md)
 #ifndef JSRT_REFILL_T
-#define JSRT_REFILL_T 8
+#define JSRT_REFILL_T 12
 #endif
 #ifndef JSRT_LEAF_T
-#define JSRT_LEAF_T 16
+#define JSRT_LEAF_T 12
 #endif
 #ifndef JSRT_PROG_T
-#define JSRT_PROG_T 33     // > 32: parked leaves are tested after every round of node steps (measured best: profiles/r2_ab.md)
+#define JSRT_PROG_T 20     // parked leaves are tested when 12 lanes hold one or fewer than 20 can still walk (profiles/r2/ab_r2j_*: grid over 16..33 x 8..16 x refill 8..16)
 #endif
 #ifndef JSRT_NODE_LDG256
 #define JSRT_NODE_LDG256 0
@@ -236,6 +236,16 @@ JSRT_DEV void finish_ray(const TraceIO& io, int i, const Hit& best, const float4
 
 // Per-ray constants of a walk through one BVHAggregate: the ray in the aggregate's space
 // (Aggregate.intersect, src/aggregates.js:15) and what the slab test needs.
+// The slab tests multiply by 1 / d; with JSRT_FAST_RCP that reciprocal comes from the SFU (1 ulp) instead of
+// the IEEE sequence: three divisions per ray and BVH in every refill and in shade_kernel's fused root-box tests.
+#ifndef JSRT_FAST_RCP
+#define JSRT_FAST_RCP 1
+#endif
+#if JSRT_FAST_RCP
+#define JSRT_RCP(x) rcp_fast(x)
+#else
+#define JSRT_RCP(x) (1.0f / (x))
+#endif
 struct LocalRay {
     float3 lo, ld, inv, sgn;      // origin, direction, 1 / direction, sign of the direction (+-1)
     bool par;                     // some |d_i| <= 1e-7: AABB.get_intersects' parallel rule applies (src/geometry.js:194,205)
@@ -244,7 +254,7 @@ JSRT_DEV LocalRay make_local_ray(const XformReg& m, float3 o, float3 d) {
     LocalRay r;
     r.lo = xf_point(m, o); r.ld = xf_dir(m, d);              // ray.getTransformed(this.getInvTransform())
     r.par = !(fabsf(r.ld.x) > 0.0000001f) || !(fabsf(r.ld.y) > 0.0000001f) || !(fabsf(r.ld.z) > 0.0000001f);
-    r.inv = f3(1.0f / r.ld.x, 1.0f / r.ld.y, 1.0f / r.ld.z);
+    r.inv = f3(JSRT_RCP(r.ld.x), JSRT_RCP(r.ld.y), JSRT_RCP(r.ld.z));
     r.sgn = f3(r.ld.x < 0.f ? -1.f : 1.f, r.ld.y < 0.f ? -1.f : 1.f, r.ld.z < 0.f ? -1.f : 1.f);
     return r;
 }
@@ -253,7 +263,7 @@ JSRT_DEV LocalRay make_ray(float3 o, float3 d) {
     LocalRay r;
     r.lo = o; r.ld = d;
     r.par = !(fabsf(d.x) > 0.0000001f) || !(fabsf(d.y) > 0.0000001f) || !(fabsf(d.z) > 0.0000001f);
-    r.inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.inv = f3(JSRT_RCP(d.x), JSRT_RCP(d.y), JSRT_RCP(d.z));
     r.sgn = f3(d.x < 0.f ? -1.f : 1.f, d.y < 0.f ? -1.f : 1.f, d.z < 0.f ? -1.f : 1.f);
     return r;
 }
@@ -346,7 +356,8 @@ JSRT_DEV void analytic_hits(const DeviceScene& sc, const float3 o, const float3 
             const float4 r2 = __ldg(reinterpret_cast<const float4*>(sc.xforms + e0.w) + 2);
             oz = r2.x * o.x + r2.y * o.y + r2.z * o.z + r2.w; dz = r2.x * d.x + r2.y * d.y + r2.z * d.z;
         } else { JSRT_LOCAL_RAY() oz = lo.z; dz = ld.z; }
-        const float t = (dz != 0.f) ? -oz / dz : -CUDART_INF_F;
+        // (shadow rays only compare t with their window: SFU division)
+        const float t = (dz != 0.f) ? (ANY_HIT ? __fdividef(-oz, dz) : -oz / dz) : -CUDART_INF_F;
         JSRT_ACCEPT(t, 0.f)
     }
     if (!JSRT_GROUP_DONE()) for (; k < sc.atab_end[tb][AG_SQUARE]; ++k) {   // Square.intersect src/geometry.js:287-291
@@ -399,7 +410,7 @@ JSRT_DEV int first_bvh_hit(const DeviceScene& sc, const float3 o, const float3 d
         return -1;
     }
     float3 winv = f3(0.f, 0.f, 0.f);
-    if (sc.use_wbox) winv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    if (sc.use_wbox) winv = f3(JSRT_RCP(d.x), JSRT_RCP(d.y), JSRT_RCP(d.z));      // (the world boxes are padded by 1e-3)
     for (int b = 0; b < sc.n_bvh; ++b) {
         if (sc.use_wbox && !wbox_hit(sc.wboxes, b, o, winv, minD, fminf(maxD, best_t))) continue;
         const int4* tp = reinterpret_cast<const int4*>(sc.tops + __ldg(sc.bvh_tops + b));
@@ -821,7 +832,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 else {
                     const float4 o4 = io.o[cur], d4 = io.d[cur];
                     if (sc.use_wbox) {          // skip the aggregates whose world box the ray misses (or reaches behind the closest hit)
-                        const float3 winv = f3(1.0f / d4.x, 1.0f / d4.y, 1.0f / d4.z);
+                        const float3 winv = f3(JSRT_RCP(d4.x), JSRT_RCP(d4.y), JSRT_RCP(d4.z));
                         const float whi = fminf(JSRT_MAXD, best.t);
                         while (bi < sc.n_bvh && !wbox_hit(sc.wboxes, bi, f3(o4.x, o4.y, o4.z), winv, JSRT_MIND, whi)) ++bi;
                     }
