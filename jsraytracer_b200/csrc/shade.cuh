@@ -80,7 +80,7 @@ JSRT_DEV float2 cartesian_to_spherical(float3 n) {
 // Vec.spherePick src/math.js:180-188: theta = 2 pi u0, phi = acos(2 u1 - 1), (cos theta sin phi, cos phi, sin theta sin phi).
 // cos(acos x) = x and sin(acos x) = sqrt(1 - x^2), and sin / cos of 2 pi u0 come from the pi-scaled routine (exact argument
 // reduction, no slow path): the same point to FP32 rounding, a fifth of the instructions of acosf + sincosf + sinf + cosf
-// (shade_kernel lost 40 % of its stall samples to instruction fetch: profiles/r2_ncu_summary.md).
+// (shade_kernel lost 40 % of its stall samples to instruction fetch: profiles/r2_ab.md).
 JSRT_DEV float3 sphere_pick(float u0, float u1) {
     const float c = 2.0f * u1 - 1.0f, sin_phi = sqrtf(fmaxf(0.f, 1.0f - c * c));
     float st, ct; sincospif(2.0f * u0, &st, &ct);

@@ -763,7 +763,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 const int leaf = (pending < -1) ? -(pending + 2) : pending;      // a blocked lane stores -(leaf + 2)
                 const int cnt = (int)((unsigned)leaf >> 24), rel = leaf & 0xffffff;
                 // (two loops, so that the compiler cannot hoist the general primitives' ray setup in front of the
-                // triangle path: it did, 140 instructions with 25 FP64 ones per leaf — profiles/r2_ncu_summary.md)
+                // triangle path: it did, 140 instructions with 25 FP64 ones per leaf — profiles/r2_ab.md)
                 if (tri_base >= 0) {
                     for (int k = 0; k < cnt; ++k) {
                         if (COUNT) ++work->leaf_prims;
@@ -890,10 +890,15 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
 // range from 0 (ray misses the SDF's box) to max_samples, and the bytecode itself is
 // branch-free, so with per-lane refill every lane of a warp executes the interpreter
 // in lockstep.  Arithmetic: the reference's (device_math.cuh).
+// lanes idle before the warp stops to hand out new rays: one distance evaluation costs ~2 000 instructions and the
+// hand-over ~200, so a warp refills as soon as a few lanes are free (measured: profiles/r2/ab_r2l_*)
+#ifndef JSRT_SDF_REFILL_T
+#define JSRT_SDF_REFILL_T 8
+#endif
 template <int MODE, bool COUNT>
 JSRT_DEV void sdf_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other) {
     constexpr bool ANY_HIT = (MODE == TM_SHADOW);
-    constexpr int BATCH = 64, REFILL_T = 8;
+    constexpr int BATCH = 64, REFILL_T = JSRT_SDF_REFILL_T;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int n = min(*io.count, io.cap);
