@@ -152,6 +152,27 @@ class CUDARenderer extends IncrementalMultisamplingRenderer {
         return img;
     }
 
+    // The GL renderer's display path (gl/src/WebGLRendererAdapter.js:183-246,352-379): the same passes with the auxiliary
+    // buffers (running per-pixel variance, first-hit normal / distance sums: flag 4), then the variance-guided filter.
+    // options: {sigma = 1, kSigma = 2, threshold = 5, colorLogScale = 0} (the GL adapter's defaults, :15-22).
+    renderDenoised(img, options = {}, x_offset = 0, x_delt = 1) {
+        const addon = this._addon(), scene = this._ensureScene(img);
+        const flags = ((this._wire && !this._wire.jitter) ? 1 : 0) | 4;
+        addon.resetAccum(scene);
+        addon.render(scene, 0, this.samplesPerPixel, this._opt.seed, x_offset, x_delt, flags);
+        addon.denoise(scene, options.sigma ?? 1, options.kSigma ?? 2, options.threshold ?? 5, options.colorLogScale ?? 0, img.imgdata.data);
+        return img;
+    }
+    // {normalDepth, variance}: two Float32Array(W*H*4) — sums of the first hit's normal (xyz) and distance (w); the GL shader's
+    // variance sums (xyz) and the number of samples whose camera ray hit something (w)
+    readAov(img) {
+        const addon = this._addon(), scene = this._ensureScene(img);
+        const n = img.width() * img.height() * 4;      // PixelBuffer.width() / height(), src/pixelbuffer.js
+        const out = { normalDepth: new Float32Array(n), variance: new Float32Array(n) };
+        addon.readAov(scene, out.normalDepth, out.variance);
+        return out;
+    }
+
     close() {
         if (this._scene) { this._addon().destroyScene(this._scene); this._scene = null; }
     }

@@ -152,6 +152,43 @@ static napi_value ReadAccum(napi_env env, napi_callback_info info) {
     if (jsrt_read_accum(s, (float*)data, &passes)) return throw_last(env);
     napi_value v; NAPI_OK(napi_create_int32(env, passes, &v)); return v;
 }
+// readAov(scene, normalDepth: Float32Array(W*H*4), variance: Float32Array(W*H*4)): the GL path's auxiliary buffers
+// (gl/src/WebGLRendererAdapter.js:352-356,376-379) of the passes rendered with flag 4 (JSRT_FLAG_AOV)
+static int float_out(napi_env env, napi_value v, size_t need, float** out) {
+    napi_typedarray_type ty; size_t n = 0; void* data = NULL; napi_value ab; size_t off = 0;
+    if (napi_get_typedarray_info(env, v, &ty, &n, &data, &ab, &off) != napi_ok || ty != napi_float32_array || n < need) {
+        napi_throw_range_error(env, NULL, "output must be a Float32Array of width*height*4"); return 1;
+    }
+    *out = (float*)data; return 0;
+}
+static napi_value ReadAov(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value a[3]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    jsrt_scene* s = scene_arg(env, a[0]); if (!s) return NULL;
+    jsrt_info inf; if (jsrt_scene_info(s, &inf)) return throw_last(env);
+    const size_t need = (size_t)inf.width * inf.height * 4;
+    float *nd = NULL, *var = NULL;
+    if (float_out(env, a[1], need, &nd) || float_out(env, a[2], need, &var)) return NULL;
+    if (jsrt_read_aov(s, nd, var)) return throw_last(env);
+    return NULL;
+}
+// denoise(scene, sigma, kSigma, threshold, colorLogScale, out: Float32Array(W*H*4) | Uint8ClampedArray(W*H*4)): the GL path's
+// display pass with its variance-guided filter (gl/src/WebGLRendererAdapter.js:183-246; its defaults: 1, 2, 5, 0)
+static napi_value Denoise(napi_env env, napi_callback_info info) {
+    size_t argc = 6; napi_value a[6]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, NULL, NULL));
+    jsrt_scene* s = scene_arg(env, a[0]); if (!s) return NULL;
+    double p[4] = {1, 2, 5, 0};
+    for (int i = 0; i < 4; ++i)
+        if (napi_get_value_double(env, a[1 + i], &p[i]) != napi_ok) { napi_throw_type_error(env, NULL, "sigma, kSigma, threshold, colorLogScale must be numbers"); return NULL; }
+    jsrt_info inf; if (jsrt_scene_info(s, &inf)) return throw_last(env);
+    napi_typedarray_type ty; size_t n = 0; void* data = NULL; napi_value ab; size_t off = 0;
+    if (napi_get_typedarray_info(env, a[5], &ty, &n, &data, &ab, &off) != napi_ok || n < (size_t)inf.width * inf.height * 4 ||
+        (ty != napi_float32_array && ty != napi_uint8_clamped_array && ty != napi_uint8_array)) {
+        napi_throw_range_error(env, NULL, "output must be a Float32Array or Uint8ClampedArray of width*height*4"); return NULL;
+    }
+    const int f32 = ty == napi_float32_array;
+    if (jsrt_denoise(s, (float)p[0], (float)p[1], (float)p[2], (float)p[3], f32 ? (float*)data : NULL, f32 ? NULL : (uint8_t*)data)) return throw_last(env);
+    return NULL;
+}
 static napi_value DeviceCount(napi_env env, napi_callback_info info) {
     (void)info; napi_value v; NAPI_OK(napi_create_int32(env, jsrt_device_count(), &v)); return v;
 }
@@ -160,7 +197,7 @@ static napi_value Init(napi_env env, napi_value exports) {
     const struct { const char* name; napi_callback fn; } fns[] = {
         {"createScene", CreateScene}, {"destroyScene", DestroyScene}, {"render", Render}, {"resetAccum", ResetAccum},
         {"synchronize", Synchronize}, {"resolveRGBA8", ResolveRGBA8}, {"primaryHits", PrimaryHits}, {"deviceCount", DeviceCount},
-        {"sceneHeader", SceneHeader}, {"readAccum", ReadAccum}};
+        {"sceneHeader", SceneHeader}, {"readAccum", ReadAccum}, {"readAov", ReadAov}, {"denoise", Denoise}};
     for (size_t i = 0; i < sizeof fns / sizeof fns[0]; ++i) {
         napi_value f; NAPI_OK(napi_create_function(env, fns[i].name, NAPI_AUTO_LENGTH, fns[i].fn, NULL, &f));
         NAPI_OK(napi_set_named_property(env, exports, fns[i].name, f));

@@ -113,7 +113,11 @@ template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT, bool TLAS>
 __global__ void __launch_bounds__(JSRT_BVH_BLOCK, JSRT_BVH_MIN_BLOCKS) bvh_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
     {
         const float4* src = reinterpret_cast<const float4*>(sc.nodes);
-        for (int k = threadIdx.x; k < 2 * sc.n_staged; k += blockDim.x) s_staged_nodes[k] = __ldg(src + k);
+        // Stored as two arrays (first halves | second halves).  A lane's LDS.128 then lands on 16-byte slot (node mod 8) of
+        // the 128-byte bank row instead of only the even (or only the odd) slots of a 32-byte record, which halves the
+        // structural bank conflicts of a warp whose 32 lanes read 32 different nodes (JSRT_STAGE_SOA=0: records as in HBM).
+        const int ns = sc.n_staged;
+        for (int k = threadIdx.x; k < 2 * ns; k += blockDim.x) s_staged_nodes[JSRT_STAGE_SOA ? ((k >> 1) + (k & 1) * ns) : k] = __ldg(src + k);
         __syncthreads();
     }
     Work wp, ws;
@@ -129,6 +133,15 @@ __device__ __forceinline__ void accum_add(float4* accum, uint32_t pixel, float3 
 // shade: World.color's miss / hit handling (src/world.js:31-41), Primitive.color
 // (:125-137), Material.color (src/materials.js).  Emits ambient, pushes shadow rays
 // and children.
+#ifndef JSRT_SHADE_LOCKSTEP
+#define JSRT_SHADE_LOCKSTEP 2
+#endif
+// Shaded sphere / cylinder hits: the accepted root re-solved in f64 (device_math.cuh: sphere_intersect64); the f32 value is
+// kept if the two disagree about which root it was.  Out of line: f64 sqrt + two divisions that mesh scenes never execute.
+JSRT_RARE double round_hit_distance64(bool sphere, float lox, float loy, float loz, float ldx, float ldy, float ldz, double md, float t, double td) {
+    const double t64 = sphere ? sphere_intersect64(f3(lox, loy, loz), f3(ldx, ldy, ldz), md) : sphere_intersect64(f3(lox, loy, 0.f), f3(ldx, ldy, 0.f), md);
+    return (fabs(t64 - (double)t) <= 1e-4 * fabs((double)t)) ? t64 : td;
+}
 struct ShadeIO {
     RayQueue q; const int* count; const float4* hits;
     RayQueue next; int* next_count; int next_cap;
@@ -165,9 +178,16 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
     __shared__ int s_hist[64], s_off[64];
     __shared__ unsigned short s_perm[kBlock];
     if (SORT) { if (threadIdx.x < 64) s_hist[threadIdx.x] = 0; __syncthreads(); }
-    const int n_round = SORT ? ((n + kBlock - 1) / kBlock) * kBlock : ((n + 31) & ~31);      // block- / warp-uniform trip count
+    // Lockstep (JSRT_SHADE_LOCKSTEP, unsorted tiles): this kernel is 8 192 SASS instructions of which a ray executes ~1 500 once,
+    // and instruction fetch was 28-44 % of its stall samples (profiles/r2_ab.md §3).  CTA barriers at the loop top (1) and
+    // before the light loop (2; 3 = also at every light sample) keep the 8 warps of a CTA in the same stretch of the code,
+    // so that one instruction-cache fill serves them all: bunny_path shade 6.84 -> 6.60 / 6.48 / 6.58 ms, dragon and
+    // cornell_box_path (sorted tiles have their own barriers) within noise (profiles/r2/ab_r2o_*).
+    constexpr int LOCKSTEP = SORT ? 0 : JSRT_SHADE_LOCKSTEP;
+    const int n_round = (SORT || LOCKSTEP) ? ((n + kBlock - 1) / kBlock) * kBlock : ((n + 31) & ~31);      // block- / warp-uniform trip count
     for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_round; i0 += stride) {
         int i = i0;
+        if (LOCKSTEP >= 1) __syncthreads();
         if (SORT) {
             const int tile = i0 - (int)threadIdx.x;
             const int j = tile + threadIdx.x, lane_s = threadIdx.x & 31;
@@ -239,9 +259,7 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
                     if (pa.x == G_SPHERE || pa.x == G_CYLINDER) {
                         // re-solve the accepted hit in f64 (see sphere_intersect64); keep the f32 value if the
                         // two disagree about which root it was
-                        const double md = (node == 1u) ? 0.0 : 0.0001;
-                        const double t64 = (pa.x == G_SPHERE) ? sphere_intersect64(lo, ld, md) : sphere_intersect64(f3(lo.x, lo.y, 0.f), f3(ld.x, ld.y, 0.f), md);
-                        if (fabs(t64 - (double)t) <= 1e-4 * fabs((double)t)) td = t64;
+                        td = round_hit_distance64(pa.x == G_SPHERE, lo.x, lo.y, lo.z, ld.x, ld.y, ld.z, (node == 1u) ? 0.0 : 0.0001, t, td);
                     }
                     lp = ray_point_f64(lo, ld, td);
                 }
@@ -275,6 +293,7 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
                 }
             }
         }
+        if (LOCKSTEP >= 2) __syncthreads();
         const bool lit = hit && mat->kind != M_TRANSPARENT;
         // ---- children (src/materials.js:277-288, 315-330, 169-172).  world.color with
         // recursionDepth - 1 == 0 returns black without casting (src/world.js:32-33).
@@ -337,6 +356,7 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
             const Light& L = sc.lights[li];
             const int ns = L.samples;
             for (int k = 0; k < ns; ++k, dim += 2, ++j) {
+                if (LOCKSTEP >= 3) __syncthreads();
                 LightSample ls; ls.direction = f3(0, 0, 1); float3 contrib = f3(0, 0, 0);
                 if (lit) {
                     ls = light_sample(L, s.position, rng_u01(node_key, dim), rng_u01(node_key, dim + 1));

@@ -90,11 +90,37 @@ JSRT_DEV float3 sphere_pick(float u0, float u1) {
 // special-function unit.  Relative error ~ e * 2^-22 (1e-5 at smoothness 100), far below the image tolerance; the general
 // powf is ~150 instructions with several slow paths.  Math.pow(x, 0) = 1 for every x including 0 (src/materials.js:390
 // defaults smoothness to 0), Math.pow(0, e > 0) = 0.
+#ifndef JSRT_SHADE_OUTLINE
+#define JSRT_SHADE_OUTLINE 0      // 1: rare paths of shade_kernel (library powf, sphere / cylinder UVs, the f64 re-solve of round hits) out of
+                                  // line.  Measured 0.3-1.4 % SLOWER (bunny_path 7 275 -> 7 257, cornell_box_path 10 400 -> 10 344, refraction_path
+                                  // 15 547 -> 15 329: profiles/r2/ab_r2p_*): ptxas already lays those blocks out behind the hot path, and the
+                                  // call sequence costs registers; kept as a switch for A/B runs
+#endif
+#if JSRT_SHADE_OUTLINE
+#define JSRT_RARE __device__ __noinline__
+#else
+#define JSRT_RARE JSRT_DEV
+#endif
+JSRT_RARE float pow_library(float b, float e) { return powf(b, e); }
 JSRT_DEV float pow_clamped(float b, float e) {
     if (e == 0.f) return 1.f;
-    if (!(b > 0.f)) return (b == 0.f) ? 0.f : powf(b, e);          // NaN / negative: the library's answer
-    if (!(e < 3.0e38f)) return powf(b, e);                            // infinite smoothness
+    if (!(b > 0.f)) return (b == 0.f) ? 0.f : pow_library(b, e);   // NaN / negative: the library's answer
+    if (!(e < 3.0e38f)) return pow_library(b, e);                    // infinite smoothness
     return exp2f(e * __log2f(b));
+}
+// Sphere / Cylinder.materialData (src/geometry.js:449-455,479-487): normal + spherical / cylindrical UV (atan2, asin)
+JSRT_RARE void round_material_data(int geom_kind, float lx, float ly, float lz, float* out /* n.xyz, u, v */) {
+    const float3 lp = f3(lx, ly, lz);
+    float3 n; float2 uv;
+    if (geom_kind == G_SPHERE) {                           // position is a 4-vector with w = 1 (sic)
+        const float nn = sqrtf(lp.x * lp.x + lp.y * lp.y + lp.z * lp.z + 1.f);
+        n = (nn > 0.00001f) ? lp * (1.f / nn) : lp;
+        uv = cartesian_to_spherical(n);
+    } else {
+        n = normalized3(f3(lp.x, lp.y, 0.f));
+        uv = make_float2(0.5f + atan2f(lp.y, lp.x) / (2.f * CUDART_PI_F), 0.5f + lp.z);
+    }
+    out[0] = n.x; out[1] = n.y; out[2] = n.z; out[3] = uv.x; out[4] = uv.y;
 }
 
 // SDF material program (sdf_compile.cpp): root_sdf.getMaterialData(p) -> basecolor, UV.
@@ -163,14 +189,11 @@ JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index
             if (fabsf(cz) > norm_dist) { norm_dist = fabsf(cz); n = f3(0.f, 0.f, js_sign(cz)); }
             break;
         }
-        case G_SPHERE: {                                  // src/geometry.js:449-455: position is a 4-vector with w = 1 (sic)
-            const float nn = sqrtf(lp.x * lp.x + lp.y * lp.y + lp.z * lp.z + 1.f);
-            n = (nn > 0.00001f) ? lp * (1.f / nn) : lp;
-            uv = cartesian_to_spherical(n); has_uv = true; break;
+        case G_SPHERE: case G_CYLINDER: {                 // src/geometry.js:449-455,479-487
+            float r[5];
+            round_material_data(geom_kind, lp.x, lp.y, lp.z, r);
+            n = f3(r[0], r[1], r[2]); uv = make_float2(r[3], r[4]); has_uv = true; break;
         }
-        case G_CYLINDER:                                  // src/geometry.js:479-487
-            n = normalized3(f3(lp.x, lp.y, 0.f));
-            uv = make_float2(0.5f + atan2f(lp.y, lp.x) / (2.f * CUDART_PI_F), 0.5f + lp.z); has_uv = true; break;
         case G_TRIANGLE: {                                // src/geometry.js:376-385,397-409
             const float4 a = __ldg(reinterpret_cast<const float4*>(sc.tris + geom_index));
             n = f3(a.x, a.y, a.z);

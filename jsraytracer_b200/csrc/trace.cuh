@@ -565,9 +565,16 @@ JSRT_DEV void load_node(const float4* p, float4& a, float4& b) {
 #ifndef JSRT_LDS_ASM
 #define JSRT_LDS_ASM 1
 #endif
+#ifndef JSRT_STAGE_SOA
+#define JSRT_STAGE_SOA 1          // staged block stored as two arrays of halves (render.cu: bvh_kernel)
+#endif
 JSRT_DEV void lds_node(unsigned addr, float4& a, float4& b) {
     asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr));
     asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(addr));
+}
+JSRT_DEV void lds_node_soa(unsigned addr_lo, unsigned addr_hi, float4& a, float4& b) {
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr_lo));
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(addr_hi));
 }
 
 // Two triangles of one mesh whose FP32 hit distances agree to the last bits (a ray through coincident or overlapping
@@ -676,6 +683,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     // from SR_CgaCtaId at every node step: 4 of the 52 instructions of the loop)
     unsigned s_base = (unsigned)__cvta_generic_to_shared(s_nodes);
     asm volatile("" : "+r"(s_base));      // opaque: otherwise it is rebuilt from SR_CgaCtaId (an S2R + two LEAs) at every node step
+    const unsigned s_base_hi = s_base + 16u * (unsigned)n_staged;      // second halves of the staged records (JSRT_STAGE_SOA)
 
     // enter BVH number `bi` of the scene (Aggregate.intersect / BVHAggregate.intersect, src/aggregates.js:43-46)
     auto enter = [&](float3 o, float3 d) {
@@ -849,7 +857,10 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 #define JSRT_NODE_STEP(SLAB)                                                                                       \
                     {                                                                                                              \
                         float4 n0, n1;                                                                                             \
-                        if (node_i < n_staged) lds_node(s_base + 32u * (unsigned)node_i, n0, n1);                                  \
+                        if (node_i < n_staged) {                                                                                   \
+                            if (JSRT_STAGE_SOA) lds_node_soa(s_base + 16u * (unsigned)node_i, s_base_hi + 16u * (unsigned)node_i, n0, n1);  \
+                            else lds_node(s_base + 32u * (unsigned)node_i, n0, n1);                                                \
+                        }                                                                                                          \
                         else load_node(all_nodes + 2 * node_i, n0, n1);                                                            \
                         const int skip = __float_as_int(n1.z), word = __float_as_int(n1.w);                                        \
                         if (COUNT) ++work->nodes;                                                                                  \

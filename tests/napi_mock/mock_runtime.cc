@@ -61,6 +61,7 @@ napi_status napi_get_typedarray_info(napi_env env, napi_value v, napi_typedarray
 }
 napi_status napi_get_value_int32(napi_env, napi_value v, int32_t* r) { if (!v || v->kind != K_NUMBER) return napi_number_expected; *r = (int32_t)(int64_t)v->num; return napi_ok; }
 napi_status napi_get_value_int64(napi_env, napi_value v, int64_t* r) { if (!v || v->kind != K_NUMBER) return napi_number_expected; *r = (int64_t)v->num; return napi_ok; }
+napi_status napi_get_value_double(napi_env, napi_value v, double* r) { if (!v || v->kind != K_NUMBER) return napi_number_expected; *r = v->num; return napi_ok; }
 napi_status napi_get_value_external(napi_env, napi_value v, void** r) { if (!v || v->kind != K_EXTERNAL) return napi_invalid_arg; *r = v->ptr; return napi_ok; }
 napi_status napi_create_external(napi_env env, void* data, napi_finalize fin, void* hint, napi_value* r) {
     *r = env->make(K_EXTERNAL); (*r)->ptr = data; (*r)->fin = fin; (*r)->fin_hint = hint; return napi_ok;

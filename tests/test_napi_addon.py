@@ -99,7 +99,7 @@ def test_addon_registers_the_functions_cuda_renderer_js_calls(addon):
     src = open(os.path.join(ROOT, "js", "cuda_renderer.js")).read()
     ex = addon.exports()
     assert set(ex) == {"createScene", "destroyScene", "render", "resetAccum", "synchronize", "resolveRGBA8", "primaryHits", "deviceCount",
-                       "sceneHeader", "readAccum"}
+                       "sceneHeader", "readAccum", "readAov", "denoise"}
     import re
     used = set(re.findall(r"(?:addon|_addon\(\))\.(\w+)\(", src))
     assert used and used <= set(ex), used - set(ex)
@@ -162,6 +162,22 @@ def test_addon_renders_the_same_bytes_as_the_ctypes_binding(addon):
         addon.call("primaryHits", scene, np.zeros(W * H, np.float32), t)
     with pytest.raises(RuntimeError, match="RangeError"):
         addon.call("primaryHits", scene, np.zeros(W * H - 1, np.int32), t)
+    # the GL path's variance buffer + variance-guided display filter through the same shim (flag 4 = JSRT_FLAG_AOV)
+    addon.call("resetAccum", scene)
+    addon.call("render", scene, 0, 4, 1, 0, 1, 4)
+    nd, var = np.zeros(W * H * 4, np.float32), np.zeros(W * H * 4, np.float32)
+    addon.call("readAov", scene, nd, var)
+    assert var.reshape(H, W, 4)[..., 3].max() == 4 and np.isfinite(nd).all()           # first hits per pixel, normal / distance sums
+    den8, denf = np.zeros(W * H * 4, np.uint8), np.zeros(W * H * 4, np.float32)
+    addon.call("denoise", scene, 1.0, 2.0, 5.0, 0.0, den8)
+    addon.call("denoise", scene, 1.0, 2.0, 5.0, 0.0, denf)
+    assert den8.reshape(H, W, 4)[..., 3].min() == 255 and np.isfinite(denf).all()
+    with pytest.raises(RuntimeError, match="RangeError"):
+        addon.call("readAov", scene, nd, np.zeros(8, np.float32))
+    with pytest.raises(RuntimeError, match="RangeError"):
+        addon.call("denoise", scene, 1.0, 2.0, 5.0, 0.0, np.zeros(W * H, np.int32))
+    with pytest.raises(RuntimeError, match="TypeError"):
+        addon.call("denoise", scene, nd, 2.0, 5.0, 0.0, den8)
     addon.call("destroyScene", scene)
     addon.call("destroyScene", scene)                                # a second destroy is a no-op, not a double free
     with pytest.raises(RuntimeError, match="after destroyScene"):
