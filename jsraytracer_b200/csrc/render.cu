@@ -33,6 +33,11 @@ namespace jsrt {
 namespace {
 
 constexpr int kBlock = 256;
+// threads per CTA of shade_kernel (its warps run in lock-step, see there) and CTAs per SM
+#ifndef JSRT_SHADE_BLOCK
+#define JSRT_SHADE_BLOCK 256
+#endif
+constexpr int kShadeBlock = JSRT_SHADE_BLOCK;
 #ifndef JSRT_SHADE_MIN_BLOCKS
 #define JSRT_SHADE_MIN_BLOCKS 3
 #endif
@@ -159,7 +164,7 @@ struct ShadeIO {
 // work list.  Round 1 wrote all of them (64 B each) for prims_kernel<shadow> to read back and find that most need no walk
 // (bunny_path: 2/3 of the shadow rays; cornell_box_path: all of them — its shadow queue is never touched now).
 template <bool HAS_SDF, bool SORT, bool FUSE, bool COUNT>
-__global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ ShadeIO io) {
+__global__ void __launch_bounds__(kShadeBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ ShadeIO io) {
     const RayQueue& q = io.q; const RayQueue& next = io.next; const ShadowQueue& sq = io.sq;
     const float4* __restrict__ hits = io.hits;
     float4* __restrict__ accum = io.accum;
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
     // materials, depth 8), +5..10 % on bunny_path / dragon / starwars, whose camera and shadow-side rays are coherent
     // already.  The host turns it on for scenes without BVH aggregates (JSRT_SHADE_SORT=0/1 overrides).
     __shared__ int s_hist[64], s_off[64];
-    __shared__ unsigned short s_perm[kBlock];
+    __shared__ unsigned short s_perm[kShadeBlock];
     if (SORT) { if (threadIdx.x < 64) s_hist[threadIdx.x] = 0; __syncthreads(); }
     // Lockstep (JSRT_SHADE_LOCKSTEP, unsorted tiles): this kernel is 8 192 SASS instructions of which a ray executes ~1 500 once,
     // and instruction fetch was 28-44 % of its stall samples (profiles/r2_ab.md §3).  CTA barriers at the loop top (1) and
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
     // so that one instruction-cache fill serves them all: bunny_path shade 6.84 -> 6.60 / 6.48 / 6.58 ms, dragon and
     // cornell_box_path (sorted tiles have their own barriers) within noise (profiles/r2/ab_r2o_*).
     constexpr int LOCKSTEP = SORT ? 0 : JSRT_SHADE_LOCKSTEP;
-    const int n_round = (SORT || LOCKSTEP) ? ((n + kBlock - 1) / kBlock) * kBlock : ((n + 31) & ~31);      // block- / warp-uniform trip count
+    const int n_round = (SORT || LOCKSTEP) ? ((n + kShadeBlock - 1) / kShadeBlock) * kShadeBlock : ((n + 31) & ~31);      // block- / warp-uniform trip count
     for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_round; i0 += stride) {
         int i = i0;
         if (LOCKSTEP >= 1) __syncthreads();
@@ -359,7 +364,9 @@ __global__ void __launch_bounds__(kBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) s
                 if (LOCKSTEP >= 3) __syncthreads();
                 LightSample ls; ls.direction = f3(0, 0, 1); float3 contrib = f3(0, 0, 0);
                 if (lit) {
-                    ls = light_sample(L, s.position, rng_u01(node_key, dim), rng_u01(node_key, dim + 1));
+                    // (a point light draws no random numbers: the two hashes are only evaluated for area lights)
+                    const bool area = L.kind != L_POINT;
+                    ls = light_sample(L, s.position, area ? rng_u01(node_key, dim) : 0.f, area ? rng_u01(node_key, dim + 1) : 0.f);
                     contrib = thr * (color_from_light_sample(*mat, f, ls) * (1.0f / (float)ns));
                 }
                 if (FUSE) {
@@ -761,9 +768,9 @@ struct Renderer::Impl {
         // material-sorted shading: on for scenes made of analytic primitives only (see shade_kernel)
         sort_shade = bvh_tops_host.empty();
         if (const char* e = getenv("JSRT_SHADE_SORT")) sort_shade = atoi(e) != 0;
-        grid_shade = has_sdf ? (sort_shade ? grid_for((const void*)shade_kernel<true, true, false, false>) : grid_for((const void*)shade_kernel<true, false, false, false>))
-                   : fuse_shadow ? (sort_shade ? grid_for((const void*)shade_kernel<false, true, true, false>) : grid_for((const void*)shade_kernel<false, false, true, false>))
-                                 : (sort_shade ? grid_for((const void*)shade_kernel<false, true, false, false>) : grid_for((const void*)shade_kernel<false, false, false, false>));
+        grid_shade = has_sdf ? (sort_shade ? grid_for((const void*)shade_kernel<true, true, false, false>, kShadeBlock) : grid_for((const void*)shade_kernel<true, false, false, false>, kShadeBlock))
+                   : fuse_shadow ? (sort_shade ? grid_for((const void*)shade_kernel<false, true, true, false>, kShadeBlock) : grid_for((const void*)shade_kernel<false, false, true, false>, kShadeBlock))
+                                 : (sort_shade ? grid_for((const void*)shade_kernel<false, true, false, false>, kShadeBlock) : grid_for((const void*)shade_kernel<false, false, false, false>, kShadeBlock));
         grid_shadow = has_sdf ? grid_for((const void*)prims_kernel<TM_SHADOW, false, true, false>) : grid_for((const void*)prims_kernel<TM_SHADOW, false, false, false>);
         grid_gen = grid_for((const void*)generate_kernel);
         grid_sdf[TM_EXTEND] = grid_for((const void*)sdf_kernel<TM_EXTEND, false>);
@@ -954,7 +961,7 @@ struct Renderer::Impl {
                 io.sq = sq; io.shadow_count = &counters->shadow; io.shadow_cap = shadow_cap; io.accum = radiance; io.seed = seed; io.stats = counters->stats;
                 io.overflow = overflow; io.sdf_normals = has_sdf ? sdf_normals : nullptr; io.accum_stride = rstride; io.pass0 = pass0;
                 io.aov_nd = aov ? aov_nd : nullptr; io.aov_var = aov ? aov_var : nullptr;
-                #define JSRT_SHADE(S, O, F, C) shade_kernel<S, O, F, C><<<grid_shade, kBlock, 0, stream>>>(ds, io)
+                #define JSRT_SHADE(S, O, F, C) shade_kernel<S, O, F, C><<<grid_shade, kShadeBlock, 0, stream>>>(ds, io)
                 if (has_sdf) { if (count_work) JSRT_SHADE(true, false, false, true); else if (sort_shade) JSRT_SHADE(true, true, false, false); else JSRT_SHADE(true, false, false, false); }
                 else if (fuse_shadow) { if (count_work) JSRT_SHADE(false, false, true, true); else if (sort_shade) JSRT_SHADE(false, true, true, false); else JSRT_SHADE(false, false, true, false); }
                 else { if (count_work) JSRT_SHADE(false, false, false, true); else if (sort_shade) JSRT_SHADE(false, true, false, false); else JSRT_SHADE(false, false, false, false); }
