@@ -470,6 +470,29 @@ def SDF_Menger(aspect=1, width=600, height=600, spp=16, depth=4, dof=None, rende
     return _sdf_scene([prim], aspect, width, height, spp, depth, dof, renderer_cls)
 
 
+def SDF_CrossFolds(aspect=1, width=600, height=600, spp=16, depth=4, dof=None, renderer_cls=IncrementalMultisamplingRenderer):
+    """Not a scene of the reference: the Menger sponge's building block — the union of three axis bars — in the three positions
+    the bytecode compiler can meet it (pushed; folded into a union with `min`; folded into an intersection with `max`), next to
+    a trio of bars of unequal thickness that must NOT be fused (sdf_compile.cpp: fuseCross).  Parity case for S_CROSS."""
+    def bars(a, b=None, c=None):
+        b = a if b is None else b
+        c = a if c is None else c
+        return (BoxSDF(Vec.of(INF, a, a)), BoxSDF(Vec.of(b, INF, b)), BoxSDF(Vec.of(c, c, INF)))
+    mat = PhongMaterial(Vec.of(0.1, 0.1, 1), 0.2, 0.4, 0.6, 100, 0.15)
+    prims = [
+        # cross clipped to a cube: BOX; CROSS(push); MAX -> CROSS folds with max
+        Primitive(SDFGeometry(IntersectionSDF(BoxSDF(1), UnionSDF(*bars(0.25))), 300, 0.0001, 100), mat,
+                  Mat4.translation([-3.5, 0.5, -4.5]).times(Mat4.rotationY(0.5)).times(Mat4.rotationX(0.3))),
+        # sphere united with a (clipped) cross: the bars follow another child of the same UnionSDF -> CROSS folds with min
+        Primitive(SDFGeometry(IntersectionSDF(BoxSDF(1.2), UnionSDF(SphereSDF(0.7), *bars(0.2))), 300, 0.0001, 100), mat,
+                  Mat4.translation([-0.5, 0.7, -6.5]).times(Mat4.rotationY(-0.4)).times(Mat4.rotationX(0.2))),
+        # unequal bars: three plain BoxSDF leaves
+        Primitive(SDFGeometry(IntersectionSDF(BoxSDF(1), UnionSDF(*bars(0.3, 0.2, 0.1))), 300, 0.0001, 100), mat,
+                  Mat4.translation([2.2, 0.5, -8.5]).times(Mat4.rotationY(0.9)).times(Mat4.rotationX(-0.3))),
+    ]
+    return _sdf_scene(prims, aspect, width, height, spp, depth, dof, renderer_cls)
+
+
 def SDF_Sierpinski(aspect=1, width=600, height=600, spp=16, depth=4, dof=None,
                    renderer_cls=IncrementalMultisamplingRenderer):
     tv = TetrahedronSDF.vertices[0]
@@ -670,7 +693,7 @@ def SDF_SphereRepetition(aspect=1, width=600, height=600, spp=16, depth=4, dof=N
 REGISTRY = {f.__name__: f for f in (
     BoxBall, BoxBall_DOF, BoxBall_path, ASimpleScene, spheres010, refraction, refraction_path, cornell_box_path,
     bunny, bunny_path, dragon, AHollowTetrahedron, starwars, tie_fighter, textured, Aggregates, nested_aggregates, dragon_grid, SDF_Simple, SDF_BoxBall, SDF_Combinations, SDF_Menger,
-    SDF_Sierpinski, spheres050, spheres100, refraction_simple, cornell_box, cornell_box_emissive, AMultipleBVH, cat, diamond, heart,
+    SDF_CrossFolds, SDF_Sierpinski, spheres050, spheres100, refraction_simple, cornell_box, cornell_box_emissive, AMultipleBVH, cat, diamond, heart,
     utah_teapot, x_wing, SDF_SphereRepetition, bottle)}
 
 

@@ -32,6 +32,7 @@ PRIMARY = [
     ("AHollowTetrahedron", dict(width=256, height=256)),           # two BVHAggregates sharing one kdtree
     ("SDF_Sierpinski", dict(width=160, height=160)),
     ("SDF_Menger", dict(width=160, height=160)),
+    ("SDF_CrossFolds", dict(width=192, height=192)),               # the fused axis-bar leaf in its push / fold-min / fold-max forms
     ("spheres010", dict(width=200, height=200)),
     ("Aggregates", dict(width=256, height=256)),                   # plain Aggregates, nested, with a shared primitive
     ("dragon_grid", dict(width=320, height=180, aspect=16 / 9, n=2)),   # 8 instances of one kdtree (Toledo-scale stand-in)
@@ -85,6 +86,7 @@ WHITTED = [
     ("Aggregates", dict(width=256, height=256), 1),
     ("SDF_Sierpinski", dict(width=160, height=160), 1),
     ("SDF_Menger", dict(width=160, height=160), 1),
+    ("SDF_CrossFolds", dict(width=192, height=192), 1),
     ("SDF_BoxBall", dict(width=160, height=160), 1),            # per-leaf basecolor through UnionSDF.getMaterialData
     ("SDF_Combinations", dict(width=192, height=192), 1),       # all six combinators incl. the smooth blends
     ("SDF_Simple", dict(width=128, height=128), 1),
