@@ -180,7 +180,8 @@ def run_ours(args):
     info = scene.info
     W, H = scene.size
     P = args.passes_per_step
-    img = np.empty(W * H * 4, dtype=np.uint8)
+    # the host image the resolve writes into: pinned, so that the device->host copy of every step is one DMA
+    img = torch.empty(W * H * 4, dtype=torch.uint8, pin_memory=True).numpy()
 
     def barrier():
         if world > 1:

@@ -606,6 +606,7 @@ struct Renderer::Impl {
     size_t bvh_smem = 0;
     unsigned long long launches = 0;
     bool profiling = false, has_sdf = false, sort_shade = false, fuse_shadow = false, fuse_gen = true;
+    int sort_from = 0;                  // first level whose shading is sorted by material (camera rays are coherent as they come)
     double ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};     // 0-3: kernel classes; 4-9: prims / bvh / sdf kernels of extend, shadow
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uchar4* rgba = nullptr; int* hit_ids = nullptr; float* hit_t = nullptr;
@@ -768,6 +769,7 @@ struct Renderer::Impl {
         // material-sorted shading: on for scenes made of analytic primitives only (see shade_kernel)
         sort_shade = bvh_tops_host.empty();
         if (const char* e = getenv("JSRT_SHADE_SORT")) sort_shade = atoi(e) != 0;
+        sort_from = envInt("JSRT_SHADE_SORT_FROM", 0);
         grid_shade = has_sdf ? (sort_shade ? grid_for((const void*)shade_kernel<true, true, false, false>, kShadeBlock) : grid_for((const void*)shade_kernel<true, false, false, false>, kShadeBlock))
                    : fuse_shadow ? (sort_shade ? grid_for((const void*)shade_kernel<false, true, true, false>, kShadeBlock) : grid_for((const void*)shade_kernel<false, false, true, false>, kShadeBlock))
                                  : (sort_shade ? grid_for((const void*)shade_kernel<false, true, false, false>, kShadeBlock) : grid_for((const void*)shade_kernel<false, false, false, false>, kShadeBlock));
@@ -961,10 +963,11 @@ struct Renderer::Impl {
                 io.sq = sq; io.shadow_count = &counters->shadow; io.shadow_cap = shadow_cap; io.accum = radiance; io.seed = seed; io.stats = counters->stats;
                 io.overflow = overflow; io.sdf_normals = has_sdf ? sdf_normals : nullptr; io.accum_stride = rstride; io.pass0 = pass0;
                 io.aov_nd = aov ? aov_nd : nullptr; io.aov_var = aov ? aov_var : nullptr;
+                const bool sort_now = sort_shade && level >= sort_from;
                 #define JSRT_SHADE(S, O, F, C) shade_kernel<S, O, F, C><<<grid_shade, kShadeBlock, 0, stream>>>(ds, io)
-                if (has_sdf) { if (count_work) JSRT_SHADE(true, false, false, true); else if (sort_shade) JSRT_SHADE(true, true, false, false); else JSRT_SHADE(true, false, false, false); }
-                else if (fuse_shadow) { if (count_work) JSRT_SHADE(false, false, true, true); else if (sort_shade) JSRT_SHADE(false, true, true, false); else JSRT_SHADE(false, false, true, false); }
-                else { if (count_work) JSRT_SHADE(false, false, false, true); else if (sort_shade) JSRT_SHADE(false, true, false, false); else JSRT_SHADE(false, false, false, false); }
+                if (has_sdf) { if (count_work) JSRT_SHADE(true, false, false, true); else if (sort_now) JSRT_SHADE(true, true, false, false); else JSRT_SHADE(true, false, false, false); }
+                else if (fuse_shadow) { if (count_work) JSRT_SHADE(false, false, true, true); else if (sort_now) JSRT_SHADE(false, true, true, false); else JSRT_SHADE(false, false, true, false); }
+                else { if (count_work) JSRT_SHADE(false, false, false, true); else if (sort_now) JSRT_SHADE(false, true, false, false); else JSRT_SHADE(false, false, false, false); }
                 #undef JSRT_SHADE
             });
             if (hs.light_samples > 0) launchShadow(count_work, radiance, rstride, pass0);
