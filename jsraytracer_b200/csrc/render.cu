@@ -618,14 +618,14 @@ struct Renderer::Impl {
     template <class T> T* dalloc(size_t n) { T* p = nullptr; CK(cudaMalloc(&p, (n ? n : 1) * sizeof(T))); allocs.push_back(p); return p; }
     // First call allocates, later calls (jsrt_scene_upload) re-copy into the same buffers.
     void uploadScene() {
-        scene_bytes = 0; up_index = 0;
+        scene_bytes = 0; up_items.clear();
         bvh_tops_host.clear();
         for (size_t i = 0; i < hs.tops.size(); ++i) if (hs.tops[i].kind == T_BVH && hs.tops[i].node_count > 0) bvh_tops_host.push_back((int)i);
-        ds.tops = up(hs.tops); ds.prims = up(hs.prims); ds.xforms = up(hs.xforms); ds.xforms64 = up(hs.xforms64); ds.nodes = up(hs.nodes);
-        ds.tris = up(hs.tris); ds.tri_shade = up(hs.tri_shade); ds.boxes = up(hs.boxes); ds.materials = up(hs.materials);
-        ds.lights = up(hs.lights); ds.sdfs = up(hs.sdfs); ds.sdf_code = up(hs.sdf_code);
-        ds.textures = up(hs.textures); ds.texels = up(hs.texels);
-        ds.bvh_tops = up(bvh_tops_host); ds.n_bvh = (int)bvh_tops_host.size();
+        up(ds.tops, hs.tops); up(ds.prims, hs.prims); up(ds.xforms, hs.xforms); up(ds.xforms64, hs.xforms64); up(ds.nodes, hs.nodes);
+        up(ds.tris, hs.tris); up(ds.tri_shade, hs.tri_shade); up(ds.boxes, hs.boxes); up(ds.materials, hs.materials);
+        up(ds.lights, hs.lights); up(ds.sdfs, hs.sdfs); up(ds.sdf_code, hs.sdf_code);
+        up(ds.textures, hs.textures); up(ds.texels, hs.texels);
+        up(ds.bvh_tops, bvh_tops_host); ds.n_bvh = (int)bvh_tops_host.size();
         ds.n_staged = std::min<int>(hs.n_staged, (int)hs.nodes.size());
         // padded world-space box of every BVHAggregate (scene_flatten.cpp: computeWorldBoxes; trace.cuh: wbox_hit)
         {
@@ -637,12 +637,12 @@ struct Renderer::Impl {
                 wboxes_host.push_back(make_float4(wb[i + 5], wb[i + 6], 0.f, 0.f));               // half y, half z
             }
         }
-        ds.wboxes = up(wboxes_host);
+        up(ds.wboxes, wboxes_host);
         ds.tlas_root = (hs.tlas_root >= 0 && hs.tlas_root < (int)hs.nodes.size() && hs.sdfs.empty()) ? hs.tlas_root : -1;   // (SDF scenes keep the linear walk)
         ds.use_wbox = envInt("JSRT_WBOX", (ds.n_bvh >= 2 && ds.tlas_root < 0) ? 1 : 0);
         sdf_tops_host.clear();
         for (size_t i = 0; i < hs.tops.size(); ++i) if (hs.tops[i].kind == T_SDF) sdf_tops_host.push_back((int)i);
-        ds.sdf_tops = up(sdf_tops_host); ds.n_sdf_tops = (int)sdf_tops_host.size();
+        up(ds.sdf_tops, sdf_tops_host); ds.n_sdf_tops = (int)sdf_tops_host.size();
         // analytic-primitive table of prims_wave: Primitives outside BVHAggregates, grouped by geometry kind; the shadow
         // copy leaves out primitives with does_cast_shadow = false (src/world.js:117-118) and geometries that never hit
         atab_host.clear();
@@ -662,23 +662,38 @@ struct Renderer::Impl {
                 }
                 ds.atab_end[tab][grp] = (int)atab_host.size();
             }
-        ds.atab = up(atab_host);
+        up(ds.atab, atab_host);
+        commitUpload();
         ds.n_top = (int)hs.tops.size(); ds.n_lights = (int)hs.lights.size(); ds.light_samples = hs.light_samples; ds.max_depth = hs.max_depth;
         for (int i = 0; i < 3; ++i) ds.bg[i] = hs.bg[i];
     }
-    std::vector<void*> scene_allocs;
+    // The scene's arrays live in ONE device allocation and travel in ONE host->device copy from a pinned staging buffer
+    // (jsrt_scene_upload re-copies into the same blob): seventeen pageable cudaMemcpyAsync calls were ~0.4 ms of host time
+    // per upload, which the end-to-end path pays every step.
+    struct UpItem { const void** dst; const void* src; size_t bytes, offset; };
+    std::vector<UpItem> up_items;
+    unsigned char* scene_blob = nullptr; unsigned char* scene_stage = nullptr; size_t scene_blob_bytes = 0;
+    cudaEvent_t upload_done = nullptr;
     std::vector<int> bvh_tops_host, sdf_tops_host;
     std::vector<float4> wboxes_host;
     std::vector<APrim> atab_host;
-    size_t up_index = 0;
-    template <class T> T* up(const std::vector<T>& vec) {
-        T* p;
-        if (up_index < scene_allocs.size()) p = (T*)scene_allocs[up_index];
-        else { CK(cudaMalloc(&p, (vec.empty() ? 1 : vec.size()) * sizeof(T))); scene_allocs.push_back((void*)p); }
-        ++up_index;
-        if (!vec.empty()) CK(cudaMemcpyAsync(p, vec.data(), vec.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    template <class T> void up(const T*& dst, const std::vector<T>& vec) {
+        up_items.push_back(UpItem{(const void**)(void*)&dst, vec.data(), vec.size() * sizeof(T), 0});
         scene_bytes += vec.size() * sizeof(T);
-        return p;
+    }
+    void commitUpload() {
+        size_t total = 0;
+        for (UpItem& it : up_items) { it.offset = total; total += (std::max<size_t>(it.bytes, 16) + 255) & ~(size_t)255; }
+        if (!scene_blob || total > scene_blob_bytes) {
+            if (scene_blob) { CK(cudaStreamSynchronize(stream)); cudaFree(scene_blob); cudaFreeHost(scene_stage); scene_blob = nullptr; scene_stage = nullptr; }
+            CK(cudaMalloc(&scene_blob, total)); CK(cudaMallocHost(&scene_stage, total)); scene_blob_bytes = total;
+            if (!upload_done) CK(cudaEventCreateWithFlags(&upload_done, cudaEventDisableTiming));
+        } else CK(cudaEventSynchronize(upload_done));     // the previous copy out of the staging buffer must be over before it is refilled
+        for (const UpItem& it : up_items) if (it.bytes) memcpy(scene_stage + it.offset, it.src, it.bytes);
+        CK(cudaMemcpyAsync(scene_blob, scene_stage, total, cudaMemcpyHostToDevice, stream));
+        CK(cudaEventRecord(upload_done, stream));
+        for (const UpItem& it : up_items) *it.dst = scene_blob + it.offset;
+        up_items.clear();
     }
 
     void init(int dev, size_t queue_budget) {
@@ -814,7 +829,9 @@ struct Renderer::Impl {
         if (stream) cudaStreamSynchronize(stream);
         for (void* p : ipc_mapped) cudaIpcCloseMemHandle(p);
         for (void* p : allocs) cudaFree(p);
-        for (void* p : scene_allocs) cudaFree(p);
+        if (scene_blob) cudaFree(scene_blob);
+        if (scene_stage) cudaFreeHost(scene_stage);
+        if (upload_done) cudaEventDestroy(upload_done);
         for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
         for (auto e : free_events) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);

@@ -342,7 +342,7 @@ class Mat4:
         r[2][3] = m03 * m11 * m20 - m01 * m13 * m20 - m03 * m10 * m21 + m00 * m13 * m21 + m01 * m10 * m23 - m00 * m11 * m23
         r[3][0] = m12 * m21 * m30 - m11 * m22 * m30 - m12 * m20 * m31 + m10 * m22 * m31 + m11 * m20 * m32 - m10 * m21 * m32
         r[3][1] = m01 * m22 * m30 - m02 * m21 * m30 + m02 * m20 * m31 - m00 * m22 * m31 - m01 * m20 * m32 + m00 * m21 * m32
-        r[3][2] = m02 * m11 * m30 - m01 * m12 * m30 + m01 * m10 * m32 - m00 * m11 * m32 - m02 * m10 * m31 + m00 * m12 * m31
+        r[3][2] = m02 * m11 * m30 - m01 * m12 * m30 - m02 * m10 * m31 + m00 * m12 * m31 + m01 * m10 * m32 - m00 * m11 * m32
         r[3][3] = m01 * m12 * m20 - m02 * m11 * m20 + m02 * m10 * m21 - m00 * m12 * m21 - m01 * m10 * m22 + m00 * m11 * m22
         det = m00 * r[0][0] + m10 * r[0][1] + m20 * r[0][2] + m30 * r[0][3]
         inv = _jsdiv(1, det)
