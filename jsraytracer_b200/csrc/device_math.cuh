@@ -304,6 +304,54 @@ JSRT_DEV double js_fmod(double a, double b) {
 // the same with the exact reciprocal of a power-of-two period supplied by the compiler (sdf_compile.cpp)
 JSRT_DEV double js_fmod_pow2(double a, double b, double inv_b) { return js_to_precision8(dsub(a, dmul(floor(dmul(a, inv_b)), b))); }
 
+// min over BoxSDF(Inf, a, a), BoxSDF(a, Inf, a), BoxSDF(a, a, Inf) (src/sdf.js:276-279 under :83-88): the component of q
+// on a bar's infinite axis is -Inf, so max(q, 0) is 0 there and the bar's distance is the 2-D box distance of the other
+// two — exactly the S_BOX arithmetic with that component dropped (adding 0 * 0 to the sum of squares does not round) —
+// and all three share q = |p| - a.
+JSRT_DEV double sdf_cross(float3 p, float a) {
+    const float qx = __fsub_rn(fabsf(p.x), a), qy = __fsub_rn(fabsf(p.y), a), qz = __fsub_rn(fabsf(p.z), a);
+    const float mx = fmaxf(qx, 0.f), my = fmaxf(qy, 0.f), mz = fmaxf(qz, 0.f);
+    const int npos = (mx > 0.f) + (my > 0.f) + (mz > 0.f);
+    double lx, ly, lz;                    // |max(q, 0)| of the bar along x, y, z
+    if (npos <= 1) { lx = (double)(my + mz); ly = (double)(mx + mz); lz = (double)(mx + my); }      // at most one term: exact
+    else {
+        const double x2 = dmul((double)mx, (double)mx), y2 = dmul((double)my, (double)my);
+        lx = (my > 0.f && mz > 0.f) ? sqrt(fma((double)mz, (double)mz, y2)) : (double)(my + mz);
+        ly = (mx > 0.f && mz > 0.f) ? sqrt(fma((double)mz, (double)mz, x2)) : (double)(mx + mz);
+        lz = (mx > 0.f && my > 0.f) ? sqrt(fma((double)my, (double)my, x2)) : (double)(mx + my);
+    }
+    const double bx = dadd(lx, (double)fminf(fmaxf(qy, qz), 0.f)), by = dadd(ly, (double)fminf(fmaxf(qx, qz), 0.f)),
+                 bz = dadd(lz, (double)fminf(fmaxf(qx, qy), 0.f));
+    // (NaN like the three boxes: a NaN coordinate, or an infinite one — |p| - Inf on that bar's own axis)
+    return (qx != qx || qy != qy || qz != qz || isinf(qx) || isinf(qy) || isinf(qz)) ? CUDART_NAN : jsd_min(jsd_min(bx, by), bz);
+}
+// S_RTU_CROSS: the loop of RecursiveTransformUnionSDF.distance (src/sdf.js:349-357) for the step { matrix transformer (:433-435);
+// infinite repetition with one power-of-two period (:471-473); cross; bestDist = min(d * s, bestDist) } — the Menger recursion.
+// The case costs the interpreter registers (with it compiled in, SDF_Sierpinski fell from 1 090 to 700-840 Mrays/s, inline or
+// as a call: profiles/r2_ab.md §4), so the marching kernel exists in two builds and only scenes whose programs contain the
+// instruction run the one with it (sdf_eval<true>; render.cu: has_rtu).
+JSRT_DEV void sdf_rtu_cross(const double* __restrict__ m, bool exact, double scale, float period, float a, int n, float3& p, double& s, double& dtop) {
+    const double sx = period, hh = sx / 2, inv = 1.0 / sx;                                                // (a power of two: exact)
+    #pragma unroll 1
+    for (int it = 0; it < n; ++it) {
+        p = exact ? xf64_apply_exact(m, p) : xf64_apply(m, p, 1.0);
+        s = dmul(s, scale);
+        p = f3((float)dsub(js_fmod_pow2(dadd(p.x, hh), sx, inv), hh), (float)dsub(js_fmod_pow2(dadd(p.y, hh), sx, inv), hh),
+               (float)dsub(js_fmod_pow2(dadd(p.z, hh), sx, inv), hh));
+        dtop = jsd_min(dmul(sdf_cross(p, a), s), dtop);
+    }
+}
+// the same out of line, for the callers that must accept every program but almost never meet this instruction (shading's
+// material programs and fallback normals, SDF primitives inside aggregates)
+__device__ __noinline__ void sdf_rtu_cross_call(const double* __restrict__ m, bool exact, double scale, float period, float a, int n,
+                                                float3* p_io, double* s_io, double* d_io) {
+    float3 p = *p_io; double s = *s_io, dtop = *d_io;
+    sdf_rtu_cross(m, exact, scale, period, a, n, p, s, dtop);
+    *p_io = p; *s_io = s; *d_io = dtop;
+}
+// RTU: 1 = S_RTU_CROSS inline (the marching kernel of scenes that use it), 0 = programs are known not to contain it,
+// -1 = out-of-line call (everything else)
+template <int RTU = -1>
 JSRT_DEV double sdf_eval(const SdfInstr* __restrict__ code, const Xform64* __restrict__ xforms64, float3 p0) {
     // the tops of the three stacks are registers (p, s, dtop); the arrays hold what lies below them
     float3 P[8]; double S[12]; double D[8];
@@ -321,25 +369,7 @@ JSRT_DEV double sdf_eval(const SdfInstr* __restrict__ code, const Xform64* __res
             if (op == S_END) return dtop;
             double v;
             if (op == S_CROSS) {
-                // min over BoxSDF(Inf, a, a), BoxSDF(a, Inf, a), BoxSDF(a, a, Inf) (src/sdf.js:276-279 under :83-88): the
-                // component of q on a bar's infinite axis is -Inf, so max(q, 0) is 0 there and the bar's distance is the 2-D
-                // box distance of the other two — exactly the S_BOX arithmetic below with that component dropped (adding
-                // 0 * 0 to the sum of squares does not round) — and all three share q = |p| - a.
-                const float qx = __fsub_rn(fabsf(p.x), f.x), qy = __fsub_rn(fabsf(p.y), f.x), qz = __fsub_rn(fabsf(p.z), f.x);
-                const float mx = fmaxf(qx, 0.f), my = fmaxf(qy, 0.f), mz = fmaxf(qz, 0.f);
-                const int npos = (mx > 0.f) + (my > 0.f) + (mz > 0.f);
-                double lx, ly, lz;                    // |max(q, 0)| of the bar along x, y, z
-                if (npos <= 1) { lx = (double)(my + mz); ly = (double)(mx + mz); lz = (double)(mx + my); }      // at most one term: exact
-                else {
-                    const double x2 = dmul((double)mx, (double)mx), y2 = dmul((double)my, (double)my);
-                    lx = (my > 0.f && mz > 0.f) ? sqrt(fma((double)mz, (double)mz, y2)) : (double)(my + mz);
-                    ly = (mx > 0.f && mz > 0.f) ? sqrt(fma((double)mz, (double)mz, x2)) : (double)(mx + mz);
-                    lz = (mx > 0.f && my > 0.f) ? sqrt(fma((double)my, (double)my, x2)) : (double)(mx + my);
-                }
-                const double bx = dadd(lx, (double)fminf(fmaxf(qy, qz), 0.f)), by = dadd(ly, (double)fminf(fmaxf(qx, qz), 0.f)),
-                             bz = dadd(lz, (double)fminf(fmaxf(qx, qy), 0.f));
-                // (NaN like the three boxes: a NaN coordinate, or an infinite one — |p| - Inf on that bar's own axis)
-                v = (qx != qx || qy != qy || qz != qz || isinf(qx) || isinf(qy) || isinf(qz)) ? CUDART_NAN : jsd_min(jsd_min(bx, by), bz);
+                v = sdf_cross(p, f.x);
             } else if (op == S_BOX) {                                                                            // src/sdf.js:276-279
                 // q = |p| - size: one f64 subtraction of f32 values stored f32 = the FP32 subtraction
                 const float qx = __fsub_rn(fabsf(p.x), f.x), qy = __fsub_rn(fabsf(p.y), f.y), qz = __fsub_rn(fabsf(p.z), f.z);
@@ -384,6 +414,12 @@ JSRT_DEV double sdf_eval(const SdfInstr* __restrict__ code, const Xform64* __res
             case S_XFORM: {                                                                               // src/sdf.js:433-435
                 p = (f.x != 0.f) ? xf64_apply_exact(xforms64[idx].m, p) : xf64_apply(xforms64[idx].m, p, 1.0);
                 s = dmul(s, a0);
+                break;
+            }
+            case S_RTU_CROSS: {
+                if (RTU == 1) sdf_rtu_cross(xforms64[idx].m, f.w != 0.f, a0, f.x, f.y, (int)f.z, p, s, dtop);
+                else if (RTU == -1) sdf_rtu_cross_call(xforms64[idx].m, f.w != 0.f, a0, f.x, f.y, (int)f.z, &p, &s, &dtop);
+                else return CUDART_NAN;
                 break;
             }
             case S_REFL: {                                                                                // src/sdf.js:450-455

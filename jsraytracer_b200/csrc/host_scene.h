@@ -47,6 +47,7 @@ void flattenScene(const WireDoc& doc, HostScene& out);
 // The device tests a ray against it before paying for the aggregate's ray transform and local root-box test
 // (trace.cuh: wbox_hit); it must contain the aggregate's root box mapped to world space.
 void computeWorldBoxes(const HostScene& hs, std::vector<float>& out);
+void computeSdfWorldBoxes(const HostScene& hs, std::vector<float>& out);     // the same for the top-level SDF primitives
 
 // Appends a top-level BVH over the scene's BVHAggregates to hs.nodes (leaves = aggregate ordinals in world.objects order)
 // and returns its root index, or -1 if it cannot be built (an unbounded aggregate).

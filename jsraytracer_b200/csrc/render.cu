@@ -47,6 +47,9 @@ constexpr int kShadeBlock = JSRT_SHADE_BLOCK;
 #ifndef JSRT_SDF_MIN_BLOCKS
 #define JSRT_SDF_MIN_BLOCKS 4
 #endif
+#ifndef JSRT_SDF_RTU_MIN_BLOCKS
+#define JSRT_SDF_RTU_MIN_BLOCKS 4      // the build with S_RTU_CROSS: 2 / 3 / 4 CTAs per SM = 742 / 761 / 787 Mrays/s on SDF_Menger (profiles/r2_ab.md §4)
+#endif
 #ifndef JSRT_SDF_SHADOW_MIN_BLOCKS
 #define JSRT_SDF_SHADOW_MIN_BLOCKS 3
 #endif
@@ -104,10 +107,11 @@ __global__ void __launch_bounds__(kBlock, (JSRT_PRIMS_MIN_BLOCKS > 0 && !HAS_SDF
     prims_wave<MODE, COUNT, HAS_SDF, GEN>(sc, io, &gen, &wp, &ws);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
-template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(kBlock, MODE == TM_SHADOW ? JSRT_SDF_SHADOW_MIN_BLOCKS : JSRT_SDF_MIN_BLOCKS) sdf_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
+// RTU: the build whose interpreter knows S_RTU_CROSS (scenes whose programs contain it; device_math.cuh: sdf_rtu_cross)
+template <int MODE, bool COUNT, bool RTU>
+__global__ void __launch_bounds__(kBlock, RTU ? JSRT_SDF_RTU_MIN_BLOCKS : MODE == TM_SHADOW ? JSRT_SDF_SHADOW_MIN_BLOCKS : JSRT_SDF_MIN_BLOCKS) sdf_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
     Work wp, ws;
-    sdf_wave<MODE, COUNT>(sc, io, &wp, &ws);
+    sdf_wave<MODE, COUNT, RTU>(sc, io, &wp, &ws);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
 // One big CTA per SM (JSRT_BVH_BLOCK threads = 64 registers each) so that the staged top levels of the trees exist once
@@ -605,7 +609,7 @@ struct Renderer::Impl {
     int grid_extend = 0, grid_extend_gen = 0, grid_shade = 0, grid_shadow = 0, grid_gen = 0, grid_bvh = 0, grid_sdf[2] = {0, 0};
     size_t bvh_smem = 0;
     unsigned long long launches = 0;
-    bool profiling = false, has_sdf = false, sort_shade = false, fuse_shadow = false, fuse_gen = true;
+    bool profiling = false, has_sdf = false, has_rtu = false, sort_shade = false, fuse_shadow = false, fuse_gen = true;
     int sort_from = 0;                  // first level whose shading is sorted by material (camera rays are coherent as they come)
     double ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};     // 0-3: kernel classes; 4-9: prims / bvh / sdf kernels of extend, shadow
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -643,6 +647,16 @@ struct Renderer::Impl {
         sdf_tops_host.clear();
         for (size_t i = 0; i < hs.tops.size(); ++i) if (hs.tops[i].kind == T_SDF) sdf_tops_host.push_back((int)i);
         up(ds.sdf_tops, sdf_tops_host); ds.n_sdf_tops = (int)sdf_tops_host.size();
+        {
+            std::vector<float> wb;
+            computeSdfWorldBoxes(hs, wb);
+            sdf_wboxes_host.clear();
+            for (size_t i = 0; i + 8 <= wb.size(); i += 8) {
+                sdf_wboxes_host.push_back(make_float4(wb[i], wb[i + 1], wb[i + 2], wb[i + 4]));
+                sdf_wboxes_host.push_back(make_float4(wb[i + 5], wb[i + 6], 0.f, 0.f));
+            }
+        }
+        up(ds.sdf_wboxes, sdf_wboxes_host);
         // analytic-primitive table of prims_wave: Primitives outside BVHAggregates, grouped by geometry kind; the shadow
         // copy leaves out primitives with does_cast_shadow = false (src/world.js:117-118) and geometries that never hit
         atab_host.clear();
@@ -675,7 +689,7 @@ struct Renderer::Impl {
     unsigned char* scene_blob = nullptr; unsigned char* scene_stage = nullptr; size_t scene_blob_bytes = 0;
     cudaEvent_t upload_done = nullptr;
     std::vector<int> bvh_tops_host, sdf_tops_host;
-    std::vector<float4> wboxes_host;
+    std::vector<float4> wboxes_host, sdf_wboxes_host;
     std::vector<APrim> atab_host;
     template <class T> void up(const T*& dst, const std::vector<T>& vec) {
         up_items.push_back(UpItem{(const void**)(void*)&dst, vec.data(), vec.size() * sizeof(T), 0});
@@ -790,8 +804,10 @@ struct Renderer::Impl {
                                  : (sort_shade ? grid_for((const void*)shade_kernel<false, true, false, false>, kShadeBlock) : grid_for((const void*)shade_kernel<false, false, false, false>, kShadeBlock));
         grid_shadow = has_sdf ? grid_for((const void*)prims_kernel<TM_SHADOW, false, true, false>) : grid_for((const void*)prims_kernel<TM_SHADOW, false, false, false>);
         grid_gen = grid_for((const void*)generate_kernel);
-        grid_sdf[TM_EXTEND] = grid_for((const void*)sdf_kernel<TM_EXTEND, false>);
-        grid_sdf[TM_SHADOW] = grid_for((const void*)sdf_kernel<TM_SHADOW, false>);
+        has_rtu = false;
+        for (const SdfInstr& in : hs.sdf_code) if (in.op == S_RTU_CROSS) has_rtu = true;
+        grid_sdf[TM_EXTEND] = has_rtu ? grid_for((const void*)sdf_kernel<TM_EXTEND, false, true>) : grid_for((const void*)sdf_kernel<TM_EXTEND, false, false>);
+        grid_sdf[TM_SHADOW] = has_rtu ? grid_for((const void*)sdf_kernel<TM_SHADOW, false, true>) : grid_for((const void*)sdf_kernel<TM_SHADOW, false, false>);
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
         CK(cudaStreamSynchronize(stream));
         setupAccumPersistence(prop);
@@ -917,8 +933,10 @@ struct Renderer::Impl {
             ++launches;
             io.final_pass = 1;
             io.cursor = io0.cursor + 2;          // cursor_extend_sdf / cursor_shadow_sdf
-            if (count_work) sdf_kernel<MODE, true><<<grid_sdf[MODE], kBlock, 0, stream>>>(ds, io);
-            else sdf_kernel<MODE, false><<<grid_sdf[MODE], kBlock, 0, stream>>>(ds, io);
+            #define JSRT_SDF(C, R) sdf_kernel<MODE, C, R><<<grid_sdf[MODE], kBlock, 0, stream>>>(ds, io)
+            if (has_rtu) { if (count_work) JSRT_SDF(true, true); else JSRT_SDF(false, true); }
+            else { if (count_work) JSRT_SDF(true, false); else JSRT_SDF(false, false); }
+            #undef JSRT_SDF
         }
         mark();
         if (profiling) {

@@ -701,31 +701,47 @@ void flattenScene(const WireDoc& doc, HostScene& out) {
 // half |M3x3| h; the pad (1e-3 of the box, 1e-4 of its distance from the origin) is far above the f32 rounding of
 // either the world-space or the reference's local test, so a ray that misses the padded box misses the local one.
 // A singular / non-finite transform gives an infinite box (never rejects).
+static void worldBoxOf(const double* a /* rows of the affine inv_transform */, const float cf[3], const float hf[3], std::vector<float>& out) {
+    const double det = a[0] * (a[5] * a[10] - a[6] * a[9]) - a[1] * (a[4] * a[10] - a[6] * a[8]) + a[2] * (a[4] * a[9] - a[5] * a[8]);
+    const double m[9] = {(a[5] * a[10] - a[6] * a[9]) / det, (a[2] * a[9] - a[1] * a[10]) / det, (a[1] * a[6] - a[2] * a[5]) / det,
+                         (a[6] * a[8] - a[4] * a[10]) / det, (a[0] * a[10] - a[2] * a[8]) / det, (a[2] * a[4] - a[0] * a[6]) / det,
+                         (a[4] * a[9] - a[5] * a[8]) / det, (a[1] * a[8] - a[0] * a[9]) / det, (a[0] * a[5] - a[1] * a[4]) / det};
+    const double c[3] = {cf[0] - a[3], cf[1] - a[7], cf[2] - a[11]};      // M c = A^-1 (c - translation of inv_transform)
+    const double h[3] = {hf[0], hf[1], hf[2]};
+    double wc[3], wh[3], hmax = 0, cmax = 0;
+    bool finite = std::isfinite(det) && det != 0.0;
+    for (int i = 0; i < 3; ++i) {
+        wc[i] = m[3 * i] * c[0] + m[3 * i + 1] * c[1] + m[3 * i + 2] * c[2];
+        wh[i] = std::fabs(m[3 * i]) * h[0] + std::fabs(m[3 * i + 1]) * h[1] + std::fabs(m[3 * i + 2]) * h[2];
+        finite = finite && std::isfinite(wc[i]) && std::isfinite(wh[i]);
+        hmax = std::max(hmax, wh[i]); cmax = std::max(cmax, std::fabs(wc[i]));
+    }
+    const double pad = 1e-3 * hmax + 1e-4 * cmax + 1e-6;
+    for (int i = 0; i < 3; ++i) out.push_back(finite ? (float)wc[i] : 0.f);
+    out.push_back(0.f);
+    for (int i = 0; i < 3; ++i) out.push_back(finite ? (float)(wh[i] + pad) : INFINITY);
+    out.push_back(0.f);
+}
 void computeWorldBoxes(const HostScene& hs, std::vector<float>& out) {
     out.clear();
     for (const Top& t : hs.tops) {
         if (t.kind != T_BVH || t.node_count <= 0) continue;
         const BvhNode& root = hs.nodes[t.first_node];
-        const double* a = hs.xforms64[t.xform].m;          // rows of the affine inv_transform
-        const double det = a[0] * (a[5] * a[10] - a[6] * a[9]) - a[1] * (a[4] * a[10] - a[6] * a[8]) + a[2] * (a[4] * a[9] - a[5] * a[8]);
-        const double m[9] = {(a[5] * a[10] - a[6] * a[9]) / det, (a[2] * a[9] - a[1] * a[10]) / det, (a[1] * a[6] - a[2] * a[5]) / det,
-                             (a[6] * a[8] - a[4] * a[10]) / det, (a[0] * a[10] - a[2] * a[8]) / det, (a[2] * a[4] - a[0] * a[6]) / det,
-                             (a[4] * a[9] - a[5] * a[8]) / det, (a[1] * a[8] - a[0] * a[9]) / det, (a[0] * a[5] - a[1] * a[4]) / det};
-        const double c[3] = {root.cx - a[3], root.cy - a[7], root.cz - a[11]};      // M c = A^-1 (c - translation of inv_transform)
-        const double h[3] = {root.hx, root.hy, root.hz};
-        double wc[3], wh[3], hmax = 0, cmax = 0;
-        bool finite = std::isfinite(det) && det != 0.0;
-        for (int i = 0; i < 3; ++i) {
-            wc[i] = m[3 * i] * c[0] + m[3 * i + 1] * c[1] + m[3 * i + 2] * c[2];
-            wh[i] = std::fabs(m[3 * i]) * h[0] + std::fabs(m[3 * i + 1]) * h[1] + std::fabs(m[3 * i + 2]) * h[2];
-            finite = finite && std::isfinite(wc[i]) && std::isfinite(wh[i]);
-            hmax = std::max(hmax, wh[i]); cmax = std::max(cmax, std::fabs(wc[i]));
-        }
-        const double pad = 1e-3 * hmax + 1e-4 * cmax + 1e-6;
-        for (int i = 0; i < 3; ++i) out.push_back(finite ? (float)wc[i] : 0.f);
-        out.push_back(0.f);
-        for (int i = 0; i < 3; ++i) out.push_back(finite ? (float)(wh[i] + pad) : INFINITY);
-        out.push_back(0.f);
+        const float c[3] = {root.cx, root.cy, root.cz}, h[3] = {root.hx, root.hy, root.hz};
+        worldBoxOf(hs.xforms64[t.xform].m, c, h, out);
+    }
+}
+// The same for the top-level SDF primitives (SDFGeometry.aabb under the primitive's transform): sdf_kernel's hand-over
+// rejects the rays that miss the padded box with one FP32 slab test before it sets up the march in the reference's f64
+// arithmetic (most rays of an SDF scene never meet the SDF).  An infinite box (SDF_SphereRepetition) never rejects.
+void computeSdfWorldBoxes(const HostScene& hs, std::vector<float>& out) {
+    out.clear();
+    for (const Top& t : hs.tops) {
+        if (t.kind != T_SDF) continue;
+        const Prim& p = hs.prims[t.first_prim];
+        const SdfProgram& pr = hs.sdfs[p.geom_index];
+        const float c[3] = {pr.cx, pr.cy, pr.cz}, h[3] = {pr.hx, pr.hy, pr.hz};
+        worldBoxOf(hs.xforms64[p.xform].m, c, h, out);
     }
 }
 

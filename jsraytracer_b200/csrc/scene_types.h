@@ -170,6 +170,9 @@ enum SdfOp : int {
     S_MULS_MIN,    //                                     pop d; top = min(top, d * scale)   (RecursiveTransformUnion step, src/sdf.js:353-354)
     S_CROSS,       // f[0] = a: UnionSDF of BoxSDF(Inf, a, a), BoxSDF(a, Inf, a), BoxSDF(a, a, Inf) — the Menger "cross" — as one leaf
                    //           (idx = 1 / 2 folds like the other leaves): three box distances from one q = |p| - a
+    S_RTU_CROSS,   // idx = Xform64 index, a0 = its scale, f = (repetition period, cross a, iterations, xform-exact flag): the loop of a
+                   //           RecursiveTransformUnionSDF whose step is { XFORM; REP (one power-of-two period); CROSS; MULS_MIN } —
+                   //           the Menger sponge's recursion — run by one instruction instead of 4 x iterations dispatches
     // ---- material program (getMaterialData, src/sdf.js:86-88,102-104,119-121,149-154,...): straight-line code over a
     // stack of {distance, basecolor, UV}; every leaf is evaluated, selections / blends fold them bottom-up.
     MP_END = 32,

@@ -91,6 +91,28 @@ struct SdfCompiler {
         b0.op = S_CROSS; b0.f[0] = a; b0.f[1] = a; b0.f[2] = a;        // idx stays: 0 = push, 1 / 2 = fold into the distance below
         out.sdf_code.pop_back(); out.sdf_code.pop_back();
     }
+    //   n x { XFORM; REP (power-of-two period); CROSS; MULS_MIN }  -> RTU_CROSS: the whole loop of the Menger recursion as one
+    //                         instruction (same operations in the same order; the interpreter's fetch + decode + dispatch
+    //                         was a quarter of its instructions, profiles/r2_ab.md §4)
+    void fuseRtuCross(size_t first, int iterations) {
+        if (const char* e = getenv("JSRT_SDF_RTU")) if (atoi(e) == 0) return;          // A/B switch
+        if (!fuse || iterations < 2 || iterations > 64 || out.sdf_code.size() != first + 4 * (size_t)iterations || first < prog_first) return;
+        const SdfInstr x = out.sdf_code[first], r = out.sdf_code[first + 1], c = out.sdf_code[first + 2], m = out.sdf_code[first + 3];
+        if (x.op != S_XFORM || r.op != S_REP || r.idx != 1 || c.op != S_CROSS || c.idx != 0 || m.op != S_MULS_MIN) return;
+        for (int i = 1; i < iterations; ++i) {
+            // (every unrolled iteration pushed its own copy of the transformer's matrix: compare the matrices, not their indices)
+            SdfInstr xi = out.sdf_code[first + 4 * i];
+            if (xi.op != S_XFORM || memcmp(&out.xforms64[xi.idx], &out.xforms64[x.idx], sizeof(Xform64)) != 0) return;
+            xi.idx = x.idx;
+            if (memcmp(&xi, &x, sizeof(SdfInstr)) != 0) return;
+            for (int k = 1; k < 4; ++k)
+                if (memcmp(&out.sdf_code[first + 4 * i + k], &out.sdf_code[first + k], sizeof(SdfInstr)) != 0) return;
+        }
+        SdfInstr f{}; f.op = S_RTU_CROSS; f.idx = x.idx; f.a0 = x.a0;
+        f.f[0] = r.f[0]; f.f[1] = c.f[0]; f.f[2] = (float)iterations; f.f[3] = x.f[0];
+        out.sdf_code.resize(first);
+        out.sdf_code.push_back(f);
+    }
     void noteBase(const Val* n) {
         double c[4] = {1, 1, 1, 0};
         if (const Val* b = doc.field(n, "basecolor")) doc.vec(b, c);
@@ -223,7 +245,9 @@ struct SdfCompiler {
             if (it > (int)kMaxInstrs) fail("jsrt: RecursiveTransformUnionSDF iteration count out of range");
             emit(S_PUSHP); one_stack.push_back(scale_is_one); scale_is_one = true;
             node(doc.field(n, "sdf"));
+            const size_t loop_first = out.sdf_code.size();
             for (int i = 0; i < it; ++i) { transformer(doc.field(n, "transformer")); node(doc.field(n, "sdf")); emit(S_MULS); emit(S_MIN); }
+            fuseRtuCross(loop_first, it);
             emit(S_POPP);
             scale_is_one = one_stack.back(); one_stack.pop_back();
         }

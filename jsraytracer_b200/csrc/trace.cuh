@@ -35,6 +35,7 @@ struct DeviceScene {
     // (use_wbox).  Conservative — a ray that misses the padded world box misses the local root box — so results are
     // those of the reference's linear walk over world.objects (src/world.js:7-15).
     const float4* wboxes;
+    const float4* sdf_wboxes;  // the same for the top-level SDF primitives (sdf_tops order): sdf_wave's cheap reject in front of the f64 set-up
     int n_sdf_tops, use_wbox;
     int n_staged;              // nodes[0, n_staged): the top levels of every tree, staged in shared memory by bvh_kernel
     int tlas_root;             // >= 0: root node of the top-level BVH over the BVHAggregates (scene_flatten.cpp: buildTlas)
@@ -903,10 +904,13 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
 // in lockstep.  Arithmetic: the reference's (device_math.cuh).
 // lanes idle before the warp stops to hand out new rays: one distance evaluation costs ~2 000 instructions and the
 // hand-over ~200, so a warp refills as soon as a few lanes are free (measured: profiles/r2/ab_r2l_*)
+#ifndef JSRT_SDF_WBOX
+#define JSRT_SDF_WBOX 1       // FP32 reject against the SDF's padded world box in front of the f64 set-up (0: A/B)
+#endif
 #ifndef JSRT_SDF_REFILL_T
 #define JSRT_SDF_REFILL_T 8
 #endif
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, bool RTU>
 JSRT_DEV void sdf_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other) {
     constexpr bool ANY_HIT = (MODE == TM_SHADOW);
     constexpr int BATCH = 64, REFILL_T = JSRT_SDF_REFILL_T;
@@ -935,7 +939,11 @@ JSRT_DEV void sdf_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
     // set up the march through SDF primitive number `si` (Primitive.intersect + the head of SDFGeometry.intersect)
     auto enter = [&]() {
         marching = false;
+        const float3 winv = f3(JSRT_RCP(d.x), JSRT_RCP(d.y), JSRT_RCP(d.z));      // (three SFU reciprocals per call: cheaper than three registers kept across the march)
         while (si < sc.n_sdf_tops && !marching) {
+            // FP32 reject against the padded world box first: most rays of an SDF scene never meet the SDF, and the exact
+            // test below costs two f64 matrix products and six f64 divisions per ray
+            if (JSRT_SDF_WBOX && !wbox_hit(sc.sdf_wboxes, si, o, winv, minD, fminf(maxD, best.t))) { ++si; continue; }
             top_i = __ldg(sc.sdf_tops + si);
             prim_i = __ldg(&sc.tops[top_i].first_prim);
             const int4* pp = reinterpret_cast<const int4*>(sc.prims + prim_i);
@@ -1020,7 +1028,7 @@ JSRT_DEV void sdf_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 pt = f3(nphase == 1 ? (float)dadd(hp.x, fs) : hp.x, nphase == 2 ? (float)dadd(hp.y, fs) : hp.y, nphase == 3 ? (float)dadd(hp.z, fs) : hp.z);
                 pg = hprog;
             }
-            const double dist = sdf_eval(pg, sc.xforms64, pt);
+            const double dist = sdf_eval<RTU ? 1 : 0>(pg, sc.xforms64, pt);
             if (COUNT) ++work->sdf_evals;
             if (nphase >= 0) {
                 if (nphase == 0) nd0 = dist; else if (nphase == 1) ndx = dist; else if (nphase == 2) ndy = dist;

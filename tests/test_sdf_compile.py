@@ -23,8 +23,10 @@ def _instrs(name, env=None):
 def test_menger_cross_is_one_leaf():
     """DifferenceSDF(Box, RecursiveTransformUnion(Union of three axis bars, [scale, repeat], 6)) (tests/SDF_Menger/test.mjs:27-40):
     BOX; PUSHP; CROSS; 6 x {XFORM; REP; CROSS; MULS_MIN}; POPP; NEG; MAX; END = 31 — 45 before the bars were fused, 77
-    without any peephole (JSRT_SDF_FUSE=0 keeps the plain code for A/B runs)."""
-    assert _instrs("SDF_Menger") == (31, 1)
+    without any peephole (JSRT_SDF_FUSE=0 keeps the plain code for A/B runs) — and the six identical steps of the recursion
+    are one RTU_CROSS instruction: BOX; PUSHP; CROSS; RTU_CROSS; POPP; NEG; MAX; END = 8."""
+    assert _instrs("SDF_Menger") == (8, 1)
+    assert _instrs("SDF_Menger", {"JSRT_SDF_RTU": "0"}) == (31, 1)
     assert _instrs("SDF_Menger", {"JSRT_SDF_FUSE": "0"})[0] > 45
 
 
