@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kBlock, RTU ? JSRT_SDF_RTU_MIN_BLOCKS : MODE =
 // per SM: up to 7 168 nodes = 224 KB of shared memory, 4 096 = 128 KB by default (the other half of the unified array
 // stays L1 for the deep nodes, the triangles and the ray records).
 extern __shared__ float4 s_staged_nodes[];
-template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT, bool TLAS>
+template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT, bool TLAS, bool MESH = false>
 __global__ void __launch_bounds__(JSRT_BVH_BLOCK, JSRT_BVH_MIN_BLOCKS) bvh_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ TraceIO io) {
     {
         const float4* src = reinterpret_cast<const float4*>(sc.nodes);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(JSRT_BVH_BLOCK, JSRT_BVH_MIN_BLOCKS) bvh_kerne
         __syncthreads();
     }
     Work wp, ws;
-    bvh_wave<MODE, COUNT, HAS_SDF, DIRECT, TLAS>(sc, io, &wp, &ws, s_staged_nodes);
+    bvh_wave<MODE, COUNT, HAS_SDF, DIRECT, TLAS, MESH>(sc, io, &wp, &ws, s_staged_nodes);
     if (COUNT) { if (MODE == TM_EXTEND) { flush_work(io.stats, 0, wp); flush_work(io.stats, 1, ws); } else flush_work(io.stats, 2, ws); }
 }
 
@@ -167,7 +167,7 @@ struct ShadeIO {
 // and only the walkers go to the shadow queue (with their first BVH), which bvh_kernel<shadow, DIRECT> consumes as its
 // work list.  Round 1 wrote all of them (64 B each) for prims_kernel<shadow> to read back and find that most need no walk
 // (bunny_path: 2/3 of the shadow rays; cornell_box_path: all of them — its shadow queue is never touched now).
-template <bool HAS_SDF, bool SORT, bool FUSE, bool COUNT>
+template <bool HAS_SDF, bool SORT, bool FUSE, bool COUNT, int LEAN = 0>
 __global__ void __launch_bounds__(kShadeBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOCKS) shade_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ ShadeIO io) {
     const RayQueue& q = io.q; const RayQueue& next = io.next; const ShadowQueue& sq = io.sq;
     const float4* __restrict__ hits = io.hits;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kShadeBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOC
                     lp = ray_point_f64(xf64_apply(m64, o, 1.0), xf64_apply(m64, d, 0.0), (double)t + (double)h4.w);
                 } else {
                     const float3 lo = xf_point(inv, o), ld = xf_dir(inv, d);
-                    if (pa.x == G_SPHERE || pa.x == G_CYLINDER) {
+                    if (LEAN < 2 && (pa.x == G_SPHERE || pa.x == G_CYLINDER)) {
                         // re-solve the accepted hit in f64 (see sphere_intersect64); keep the f32 value if the
                         // two disagree about which root it was
                         td = round_hit_distance64(pa.x == G_SPHERE, lo.x, lo.y, lo.z, ld.x, ld.y, ld.z, (node == 1u) ? 0.0 : 0.0001, t, td);
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kShadeBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOC
                 }
                 float3 ln; float4 sn = make_float4(0, 0, 0, 0);
                 if (HAS_SDF && io.sdf_normals && ta.x == T_SDF) sn = io.sdf_normals[i];
-                material_data<HAS_SDF>(sc, pa.x, pa.y, flags, lp, ln, s.uv, s.has_uv, s.basecolor, &sn);
+                material_data<HAS_SDF, LEAN>(sc, pa.x, pa.y, flags, lp, ln, s.uv, s.has_uv, s.basecolor, &sn);
                 s.normal = normalized3(xf_normal(inv, ln));
                 s.position = ray_point_f64(o, d, td);
                 if (io.aov_nd && node == 1u) {
@@ -285,19 +285,19 @@ __global__ void __launch_bounds__(kShadeBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOC
                     atomicAdd(&io.aov_var[pixel].w, 1.0f);
                 }
                 mat = sc.materials + pa.z;
-                if (mat->uv_from_position) {          // PositionalUVMaterial.color src/materials.js:188-192
+                if (LEAN < 1 && mat->uv_from_position) {          // PositionalUVMaterial.color src/materials.js:188-192
                     const float dx = (float)dsub(mat->uv_origin[0], s.position.x), dy = (float)dsub(mat->uv_origin[1], s.position.y), dz = (float)dsub(mat->uv_origin[2], s.position.z);
                     s.uv = make_float2((float)ddot3(mat->u_axis[0], mat->u_axis[1], mat->u_axis[2], dx, dy, dz), (float)ddot3(mat->v_axis[0], mat->v_axis[1], mat->v_axis[2], dx, dy, dz));
                     s.has_uv = true;
                 }
                 node_key = rng_node_key(rng_sample_key(io.seed, pixel, (uint32_t)pass), node);
-                if (mat->kind == M_SOLID) {
-                    accum_add(accum, slot, thr * color_eval(sc, mat->ambient, s));
+                if (LEAN < 1 && mat->kind == M_SOLID) {
+                    accum_add(accum, slot, thr * color_eval<LEAN>(sc, mat->ambient, s));
                     hit = false;                 // no lights, no children (src/materials.js:153-155)
-                } else if (mat->kind == M_TRANSPARENT) {
-                    accum_add(accum, slot, thr * (color_eval(sc, mat->ambient, s) * mat->smoothness));
+                } else if (LEAN < 1 && mat->kind == M_TRANSPARENT) {
+                    accum_add(accum, slot, thr * (color_eval<LEAN>(sc, mat->ambient, s) * mat->smoothness));
                 } else {
-                    base_factors(sc, *mat, s, d, f);
+                    base_factors<LEAN>(sc, *mat, s, d, f);
                     accum_add(accum, slot, thr * f.ambient);      // `let ret = data.ambient`
                 }
             }
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kShadeBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOC
                 if (lit) {
                     // (a point light draws no random numbers: the two hashes are only evaluated for area lights)
                     const bool area = L.kind != L_POINT;
-                    ls = light_sample(L, s.position, area ? rng_u01(node_key, dim) : 0.f, area ? rng_u01(node_key, dim + 1) : 0.f);
+                    ls = light_sample<LEAN>(L, s.position, area ? rng_u01(node_key, dim) : 0.f, area ? rng_u01(node_key, dim + 1) : 0.f);
                     contrib = thr * (color_from_light_sample(*mat, f, ls) * (1.0f / (float)ns));
                 }
                 if (FUSE) {
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(kShadeBlock, HAS_SDF ? 1 : JSRT_SHADE_MIN_BLOC
                     int fb = -1; bool walker = false;
                     if (lit) {
                         Hit sb; sb.t = CUDART_INF_F; sb.prim = -1; sb.top = -1; sb.t_lo = 0.f;
-                        analytic_hits<true, COUNT, false>(sc, s.position, ls.direction, 0.0001f, 1.0f, lit_mask, sb, &ws);
+                        analytic_hits<true, COUNT, false, (LEAN >= 2)>(sc, s.position, ls.direction, 0.0001f, 1.0f, lit_mask, sb, &ws);
                         if (sb.prim < 0) {
                             LocalRay lr;
                             fb = first_bvh_hit<COUNT>(sc, s.position, ls.direction, 0.0001f, 1.0f, CUDART_INF_F, &ws, lr);
@@ -610,6 +610,8 @@ struct Renderer::Impl {
     size_t bvh_smem = 0;
     unsigned long long launches = 0;
     bool profiling = false, has_sdf = false, has_rtu = false, sort_shade = false, fuse_shadow = false, fuse_gen = true;
+    int lean = 0;                       // build of shade_kernel the scene can use (leanLevel)
+    bool mesh_only = false;             // every BVHAggregate is a pure triangle mesh: bvh_kernel's build without the general-primitive leaves
     int sort_from = 0;                  // first level whose shading is sorted by material (camera rays are coherent as they come)
     double ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};     // 0-3: kernel classes; 4-9: prims / bvh / sdf kernels of extend, shadow
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -710,6 +712,23 @@ struct Renderer::Impl {
         up_items.clear();
     }
 
+    // shade_kernel<..., LEAN> (shade.cuh): which build of the kernel the scene can use.  Level 2 — a ground plane + triangle
+    // meshes lit by point lights: 7 576 -> ~5 000 SASS instructions, no spills, shade 6.49 -> 5.13 ms per 16 passes of
+    // bunny_path (+6 % overall), dragon +3.7 %.  Level 1 — no textures / positional UVs / solid or transparent materials
+    // (profiles/r2_ab.md §3).  JSRT_SHADE_LEAN caps the level (0 = the general build).
+    int leanLevel() const {
+        const int cap = envInt("JSRT_SHADE_LEAN", 2);
+        if (cap <= 0 || !hs.sdfs.empty() || !hs.textures.empty()) return 0;
+        for (const Material& m : hs.materials) {
+            if (m.kind != M_PHONG && m.kind != M_FRESNEL && m.kind != M_PATH) return 0;
+            if (m.uv_from_position) return 0;
+            for (const Color* c : {&m.ambient, &m.diffusivity, &m.specularity, &m.reflectivity, &m.transmissivity}) if (c->checker == CK_TEXTURE) return 0;
+        }
+        if (cap < 2) return 1;
+        for (const Light& l : hs.lights) if (l.kind != L_POINT) return 1;
+        for (const Prim& p : hs.prims) if (p.geom_kind != G_PLANE && p.geom_kind != G_TRIANGLE) return 1;
+        return 2;
+    }
     void init(int dev, size_t queue_budget) {
         device = dev;
         CK(cudaSetDevice(device));
@@ -791,6 +810,10 @@ struct Renderer::Impl {
             JSRT_BVH_ATTR(TM_SHADOW, false, false, true, false); JSRT_BVH_ATTR(TM_SHADOW, true, false, true, false);
             JSRT_BVH_ATTR(TM_EXTEND, false, false, false, true); JSRT_BVH_ATTR(TM_EXTEND, true, false, false, true); JSRT_BVH_ATTR(TM_SHADOW, false, false, false, true); JSRT_BVH_ATTR(TM_SHADOW, true, false, false, true);
             JSRT_BVH_ATTR(TM_SHADOW, false, false, true, true); JSRT_BVH_ATTR(TM_SHADOW, true, false, true, true);
+            // the mesh-only builds (untimed COUNT variants keep the general one)
+            JSRT_BVH_ATTR(TM_EXTEND, false, false, false, false, true); JSRT_BVH_ATTR(TM_EXTEND, false, false, false, true, true);
+            JSRT_BVH_ATTR(TM_SHADOW, false, false, false, false, true); JSRT_BVH_ATTR(TM_SHADOW, false, false, false, true, true);
+            JSRT_BVH_ATTR(TM_SHADOW, false, false, true, false, true); JSRT_BVH_ATTR(TM_SHADOW, false, false, true, true, true);
         }
         #undef JSRT_BVH_ATTR
         grid_bvh = has_sdf ? grid_for((const void*)bvh_kernel<TM_EXTEND, false, true, false, false>, JSRT_BVH_BLOCK, bvh_smem)
@@ -799,6 +822,9 @@ struct Renderer::Impl {
         sort_shade = bvh_tops_host.empty();
         if (const char* e = getenv("JSRT_SHADE_SORT")) sort_shade = atoi(e) != 0;
         sort_from = envInt("JSRT_SHADE_SORT_FROM", 0);
+        lean = leanLevel();
+        mesh_only = envInt("JSRT_BVH_MESH", 1) != 0;
+        for (const Top& t : hs.tops) if (t.kind == T_BVH && t.node_count > 0 && t.tri_base < 0) mesh_only = false;
         grid_shade = has_sdf ? (sort_shade ? grid_for((const void*)shade_kernel<true, true, false, false>, kShadeBlock) : grid_for((const void*)shade_kernel<true, false, false, false>, kShadeBlock))
                    : fuse_shadow ? (sort_shade ? grid_for((const void*)shade_kernel<false, true, true, false>, kShadeBlock) : grid_for((const void*)shade_kernel<false, false, true, false>, kShadeBlock))
                                  : (sort_shade ? grid_for((const void*)shade_kernel<false, true, false, false>, kShadeBlock) : grid_for((const void*)shade_kernel<false, false, false, false>, kShadeBlock));
@@ -919,12 +945,15 @@ struct Renderer::Impl {
             ++launches;
             const bool tlas = ds.tlas_root >= 0;
             #define JSRT_BVH(C, S, D, T) bvh_kernel<MODE, C, S, D, T><<<grid_bvh, JSRT_BVH_BLOCK, bvh_smem, stream>>>(ds, io)
+            #define JSRT_BVH_MESH(D, T) bvh_kernel<MODE, false, false, D, T, true><<<grid_bvh, JSRT_BVH_BLOCK, bvh_smem, stream>>>(ds, io)
+            const bool mesh = mesh_only && !count_work && !has_sdf;
             if (has_sdf) { if (count_work) JSRT_BVH(true, true, false, false); else JSRT_BVH(false, true, false, false); }
             else if (direct) {
-                if (tlas) { if (count_work) JSRT_BVH(true, false, (MODE == TM_SHADOW), true); else JSRT_BVH(false, false, (MODE == TM_SHADOW), true); }
-                else { if (count_work) JSRT_BVH(true, false, (MODE == TM_SHADOW), false); else JSRT_BVH(false, false, (MODE == TM_SHADOW), false); }
-            } else if (tlas) { if (count_work) JSRT_BVH(true, false, false, true); else JSRT_BVH(false, false, false, true); }
-            else { if (count_work) JSRT_BVH(true, false, false, false); else JSRT_BVH(false, false, false, false); }
+                if (tlas) { if (mesh) JSRT_BVH_MESH((MODE == TM_SHADOW), true); else if (count_work) JSRT_BVH(true, false, (MODE == TM_SHADOW), true); else JSRT_BVH(false, false, (MODE == TM_SHADOW), true); }
+                else { if (mesh) JSRT_BVH_MESH((MODE == TM_SHADOW), false); else if (count_work) JSRT_BVH(true, false, (MODE == TM_SHADOW), false); else JSRT_BVH(false, false, (MODE == TM_SHADOW), false); }
+            } else if (tlas) { if (mesh) JSRT_BVH_MESH(false, true); else if (count_work) JSRT_BVH(true, false, false, true); else JSRT_BVH(false, false, false, true); }
+            else { if (mesh) JSRT_BVH_MESH(false, false); else if (count_work) JSRT_BVH(true, false, false, false); else JSRT_BVH(false, false, false, false); }
+            #undef JSRT_BVH_MESH
             #undef JSRT_BVH
             if (MODE == TM_EXTEND && JSRT_TRI_TIE) { ++launches; tie_kernel<<<4, kBlock, 0, stream>>>(ds, io); }      // a few dozen entries per frame
         }
@@ -1000,9 +1029,16 @@ struct Renderer::Impl {
                 io.aov_nd = aov ? aov_nd : nullptr; io.aov_var = aov ? aov_var : nullptr;
                 const bool sort_now = sort_shade && level >= sort_from;
                 #define JSRT_SHADE(S, O, F, C) shade_kernel<S, O, F, C><<<grid_shade, kShadeBlock, 0, stream>>>(ds, io)
+                #define JSRT_SHADE_L(O, F, L) shade_kernel<false, O, F, false, L><<<grid_shade, kShadeBlock, 0, stream>>>(ds, io)
                 if (has_sdf) { if (count_work) JSRT_SHADE(true, false, false, true); else if (sort_now) JSRT_SHADE(true, true, false, false); else JSRT_SHADE(true, false, false, false); }
-                else if (fuse_shadow) { if (count_work) JSRT_SHADE(false, false, true, true); else if (sort_now) JSRT_SHADE(false, true, true, false); else JSRT_SHADE(false, false, true, false); }
-                else { if (count_work) JSRT_SHADE(false, false, false, true); else if (sort_now) JSRT_SHADE(false, true, false, false); else JSRT_SHADE(false, false, false, false); }
+                else if (count_work) { if (fuse_shadow) JSRT_SHADE(false, false, true, true); else JSRT_SHADE(false, false, false, true); }
+                else if (lean >= 2 && !sort_now) { if (fuse_shadow) JSRT_SHADE_L(false, true, 2); else JSRT_SHADE_L(false, false, 2); }
+                else if (lean >= 1) {
+                    if (fuse_shadow) { if (sort_now) JSRT_SHADE_L(true, true, 1); else JSRT_SHADE_L(false, true, 1); }
+                    else { if (sort_now) JSRT_SHADE_L(true, false, 1); else JSRT_SHADE_L(false, false, 1); }
+                } else if (fuse_shadow) { if (sort_now) JSRT_SHADE(false, true, true, false); else JSRT_SHADE(false, false, true, false); }
+                else { if (sort_now) JSRT_SHADE(false, true, false, false); else JSRT_SHADE(false, false, false, false); }
+                #undef JSRT_SHADE_L
                 #undef JSRT_SHADE
             });
             if (hs.light_samples > 0) launchShadow(count_work, radiance, rstride, pass0);

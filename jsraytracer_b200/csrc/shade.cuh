@@ -56,10 +56,15 @@ __device__ __noinline__ float4 texture_eval(const Texture* __restrict__ textures
                        (float)((double)(float)r[3] * (double)sa));
 }
 
+// LEAN (here and below): builds of shade_kernel with the code of features the scene does not use compiled out (render.cu:
+// leanLevel).  1: no textures, positional UVs, solid or transparent materials (most scenes) — the texture path is a call,
+// and a call site costs the whole kernel registers.  2: level 1 and no area lights, round or box primitives, with planes as
+// the only analytic primitives — the ground-plane + mesh + point-light scenes.
+template <int LEAN = 0>
 JSRT_DEV float3 color_eval(const DeviceScene& sc, const Color& c, const SurfaceData& s, float* alpha = nullptr) {
     if (alpha) *alpha = 0.f;
     if (c.checker == CK_SOLID) return f3(c.c1[0], c.c1[1], c.c1[2]);
-    if (c.checker == CK_TEXTURE) {
+    if (LEAN < 1 && c.checker == CK_TEXTURE) {
         const float4 t = texture_eval(sc.textures, sc.texels, c.tex, s.has_uv ? s.uv.x : 0.f, s.has_uv ? s.uv.y : 0.f, c.c1[0], c.c1[1], c.c1[2], c.c2[0]);
         if (alpha) *alpha = t.w;
         return f3(t.x, t.y, t.z);
@@ -172,14 +177,14 @@ JSRT_DEV void sdf_material(const DeviceScene& sc, int first, float3 p, float3& b
 }
 
 // geometry.materialData in the primitive's local space -> local normal, UV, basecolor.
-template <bool HAS_SDF>
+template <bool HAS_SDF, int LEAN = 0>
 JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index, int flags, float3 lp,
                             float3& n, float2& uv, bool& has_uv, float3& base, const float4* sdf_normal = nullptr) {
     has_uv = false; uv = make_float2(0.f, 0.f); base = f3(1.f, 1.f, 1.f); n = f3(0.f, 0.f, 1.f);
     switch (geom_kind) {
         case G_PLANE: case G_SQUARE: case G_CIRCLE:       // src/geometry.js:249-254
             n = f3(0.f, 0.f, 1.f); uv = make_float2(lp.x, lp.y); has_uv = true; break;
-        case G_BOX: {                                     // AABB.materialData src/geometry.js:210-224
+        case G_BOX: if (LEAN < 2) {                                     // AABB.materialData src/geometry.js:210-224
             float3 c = f3(0.f, 0.f, 0.f), h = f3(0.5f, 0.5f, 0.5f);
             if (geom_index >= 0) { const float* b = sc.boxes + 8 * geom_index; c = f3(b[0], b[1], b[2]); h = f3(b[4], b[5], b[6]); }
             float norm_dist = 0.f; n = f3(0.f, 0.f, 0.f);
@@ -189,7 +194,7 @@ JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index
             if (fabsf(cz) > norm_dist) { norm_dist = fabsf(cz); n = f3(0.f, 0.f, js_sign(cz)); }
             break;
         }
-        case G_SPHERE: case G_CYLINDER: {                 // src/geometry.js:449-455,479-487
+        case G_SPHERE: case G_CYLINDER: if (LEAN < 2) {                 // src/geometry.js:449-455,479-487
             float r[5];
             round_material_data(geom_kind, lp.x, lp.y, lp.z, r);
             n = f3(r[0], r[1], r[2]); uv = make_float2(r[3], r[4]); has_uv = true; break;
@@ -236,10 +241,11 @@ JSRT_DEV void material_data(const DeviceScene& sc, int geom_kind, int geom_index
 struct LightSample { float3 direction; float3 color; };
 
 // Light.sampleIterator for sample `u0,u1` (src/lights.js:45-53,80-93)
+template <int LEAN = 0>
 JSRT_DEV LightSample light_sample(const Light& l, float3 P, float u0, float u1) {
     LightSample s;
     const float3 lc = f3(l.color[0], l.color[1], l.color[2]);
-    if (l.kind == L_POINT) {
+    if (LEAN >= 2 || l.kind == L_POINT) {
         s.direction = f3(l.pos[0], l.pos[1], l.pos[2]) - P;
         s.color = lc * (1.f / (4.f * CUDART_PI_F * dot3(s.direction, s.direction)));     // Light.falloff :21-23
         return s;
@@ -270,16 +276,17 @@ struct PhongFactors {          // PhongMaterial.getBaseFactors src/materials.js:
     float refl_alpha, trans_alpha;      // texture colours are RGBA: alpha takes part in the reference's `squarednorm() > 0` tests
 };
 
+template <int LEAN = 0>
 JSRT_DEV void base_factors(const DeviceScene& sc, const Material& m, const SurfaceData& s, float3 ray_dir, PhongFactors& f) {
     f.V = normalized3(ray_dir) * -1.f;
     f.N = normalized3(s.normal); f.backside = false; f.vdotn = dot3(f.V, f.N);
     if (f.vdotn < 0.f) { f.N = f.N * -1.f; f.backside = true; f.vdotn = -f.vdotn; }
     f.R = normalized3(f.N * (2.f * f.vdotn) - f.V);
-    f.ambient = s.basecolor * color_eval(sc, m.ambient, s);
-    f.diffusivity = s.basecolor * color_eval(sc, m.diffusivity, s);
-    f.specularity = color_eval(sc, m.specularity, s);
-    f.reflectivity = color_eval(sc, m.reflectivity, s, &f.refl_alpha);
-    f.transmissivity = color_eval(sc, m.transmissivity, s, &f.trans_alpha);
+    f.ambient = s.basecolor * color_eval<LEAN>(sc, m.ambient, s);
+    f.diffusivity = s.basecolor * color_eval<LEAN>(sc, m.diffusivity, s);
+    f.specularity = color_eval<LEAN>(sc, m.specularity, s);
+    f.reflectivity = color_eval<LEAN>(sc, m.reflectivity, s, &f.refl_alpha);
+    f.transmissivity = color_eval<LEAN>(sc, m.transmissivity, s, &f.trans_alpha);
     f.smoothness = m.smoothness;
     f.kr = 1.f; f.has_refr = false; f.refr = f3(0.f, 0.f, 0.f);
     if (m.kind == M_FRESNEL || m.kind == M_PATH) {

@@ -332,7 +332,8 @@ JSRT_DEV bool wbox_hit(const float4* __restrict__ wb, int b, float3 o, float3 in
 // the body apart from its warp (measured on cornell_box_path: 8.7 of 32 lanes active in the box loop, each group of
 // lanes running it separately); instead every lane runs every test of a group and the lanes of `mask` skip the
 // remaining groups together once all of their rays are occluded.
-template <bool ANY_HIT, bool COUNT, bool HAS_SDF>
+// PLANES_ONLY (shade_kernel's lean build): the table holds planes only, the loops of the other kinds are compiled out.
+template <bool ANY_HIT, bool COUNT, bool HAS_SDF, bool PLANES_ONLY = false>
 JSRT_DEV void analytic_hits(const DeviceScene& sc, const float3 o, const float3 d, const float minD, const float maxD, const unsigned mask, Hit& best, Work* work) {
     const APrim* const tab = sc.atab;
     const int tb = ANY_HIT ? 1 : 0;
@@ -361,14 +362,14 @@ JSRT_DEV void analytic_hits(const DeviceScene& sc, const float3 o, const float3 
         const float t = (dz != 0.f) ? (ANY_HIT ? __fdividef(-oz, dz) : -oz / dz) : -CUDART_INF_F;
         JSRT_ACCEPT(t, 0.f)
     }
-    if (!JSRT_GROUP_DONE()) for (; k < sc.atab_end[tb][AG_SQUARE]; ++k) {   // Square.intersect src/geometry.js:287-291
+    if (!PLANES_ONLY && !JSRT_GROUP_DONE()) for (; k < sc.atab_end[tb][AG_SQUARE]; ++k) {   // Square.intersect src/geometry.js:287-291
         JSRT_ENTRY()
         JSRT_LOCAL_RAY()
         const float t = plane_t(lo, ld);
         const float x = __fadd_rn(lo.x, __fmul_rn(ld.x, t)), y = __fadd_rn(lo.y, __fmul_rn(ld.y, t));
         if (-0.5f <= x && x <= 0.5f && -0.5f <= y && y <= 0.5f) { JSRT_ACCEPT(t, 0.f) }
     }
-    if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_SQUARE]; k < sc.atab_end[tb][AG_BOX]; ++k) {      // AABB.intersect src/geometry.js:173-179
+    if (!PLANES_ONLY && !JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_SQUARE]; k < sc.atab_end[tb][AG_BOX]; ++k) {      // AABB.intersect src/geometry.js:173-179
         JSRT_ENTRY()
         JSRT_LOCAL_RAY()
         float3 c = f3(0.f, 0.f, 0.f), h = f3(0.5f, 0.5f, 0.5f);
@@ -376,13 +377,13 @@ JSRT_DEV void analytic_hits(const DeviceScene& sc, const float3 o, const float3 
         const float t = box_prim_intersect(c, h, lo, ld, minD, maxD);
         JSRT_ACCEPT(t, 0.f)
     }
-    if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_BOX]; k < sc.atab_end[tb][AG_SPHERE]; ++k) {      // Sphere.staticIntersect src/geometry.js:429-442
+    if (!PLANES_ONLY && !JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_BOX]; k < sc.atab_end[tb][AG_SPHERE]; ++k) {      // Sphere.staticIntersect src/geometry.js:429-442
         JSRT_ENTRY()
         JSRT_LOCAL_RAY()
         const float t = sphere_intersect(lo, ld, minD);
         JSRT_ACCEPT(t, 0.f)
     }
-    if (!JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_SPHERE]; k < sc.atab_end[tb][AG_OTHER]; ++k) {    // every other geometry: the general code
+    if (!PLANES_ONLY && !JSRT_GROUP_DONE()) for (k = sc.atab_end[tb][AG_SPHERE]; k < sc.atab_end[tb][AG_OTHER]; ++k) {    // every other geometry: the general code
         if (ANY_HIT && best.prim >= 0) break;
         JSRT_ENTRY()
         float3 lo = o, ld = d;
@@ -643,7 +644,10 @@ JSRT_DEV void tie_wave(const DeviceScene& sc, const TraceIO& io) {
 // DIRECT (shadow rays of scenes without SDFs): the queue holds walkers only — shade_kernel has already run the analytic
 // primitives and the root boxes and accumulated or dropped every ray that needs no walk — so entry i of the queue is
 // ray i: o.xyz | pixel, d.xyz | pass, contribution.rgb | first BVH.  No work list, no partial-hit buffer.
-template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT, bool TLAS>
+// MESH: every BVHAggregate of the scene is a pure identity-transform triangle mesh (tri_base >= 0), so the leaf code of the
+// general primitives — a call into every geometry's intersect with its own ray transform — is compiled out: no spills
+// left in the kernel, bunny_path +4.9 %, dragon +4.5 % (profiles/r2_ab.md §2).
+template <int MODE, bool COUNT, bool HAS_SDF, bool DIRECT, bool TLAS, bool MESH>
 JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_primary, Work* work_other, const float4* __restrict__ s_nodes) {
     constexpr bool ANY_HIT = (MODE == TM_SHADOW);
     constexpr int BATCH = JSRT_POOL_BATCH;      // list entries fetched per atomicAdd
@@ -773,7 +777,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                 const int cnt = (int)((unsigned)leaf >> 24), rel = leaf & 0xffffff;
                 // (two loops, so that the compiler cannot hoist the general primitives' ray setup in front of the
                 // triangle path: it did, 140 instructions with 25 FP64 ones per leaf — profiles/r2_ab.md)
-                if (tri_base >= 0) {
+                if (MESH || tri_base >= 0) {
                     for (int k = 0; k < cnt; ++k) {
                         if (COUNT) ++work->leaf_prims;
                         const int pi = first_prim + rel + k;
@@ -791,7 +795,7 @@ JSRT_DEV void bvh_wave(const DeviceScene& sc, const TraceIO& io, Work* work_prim
                             if (take) { local_best = t; local_prim = pi; local_lo = 0.f; }
                         }
                     }
-                } else {
+                } else if (!MESH) {
                     for (int k = 0; k < cnt; ++k) {
                         if (COUNT) ++work->leaf_prims;
                         const int pi = first_prim + rel + k;
