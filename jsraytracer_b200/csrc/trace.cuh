@@ -513,6 +513,7 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, const GenPara
         const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
         if (PREFETCH && i0 < n) { no4 = JSRT_PRIMS_LD(io.o + i0); nd4 = JSRT_PRIMS_LD(io.d + i0); }
     }
+    bool p_any = false; int p_base = 0, p_rank = -1; int2 p_entry = make_int2(0, 0);      // the previous iteration's pending append
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         int first_bvh = -1;
         Hit best; best.t = CUDART_INF_F; best.prim = -1; best.top = -1; best.t_lo = 0.f;
@@ -539,17 +540,29 @@ JSRT_DEV void prims_wave(const DeviceScene& sc, const TraceIO& io, const GenPara
             analytic_hits<ANY_HIT, COUNT, HAS_SDF>(sc, o, d, minD, maxD, live, best, work);
             if (!(ANY_HIT && best.prim >= 0)) { LocalRay lr; first_bvh = first_bvh_hit<COUNT>(sc, o, d, minD, maxD, best.t, work, lr); }
         }
+        // Work-list append, software-pipelined: the atomicAdd that reserves this iteration's slots is issued here, its result
+        // is only consumed — and the entries stored — at the same point of the NEXT iteration, so the counter's round trip
+        // (~1 us under contention: it was 52 % of this kernel's stall samples, profiles/r2_ab.md §6) hides behind a whole
+        // iteration of work instead of stalling the warp.
         const unsigned walkers = __ballot_sync(FULL, first_bvh >= 0);
-        if (walkers) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(io.list_count, __popc(walkers));
-            base = __shfl_sync(FULL, base, 0);
-            if (first_bvh >= 0) io.list[base + __popc(walkers & ((1u << lane) - 1u))] = make_int2(i, first_bvh);
+        if (p_any) {
+            const int b = __shfl_sync(FULL, p_base, 0);
+            if (p_rank >= 0) io.list[b + p_rank] = p_entry;
+        }
+        p_any = walkers != 0u;
+        if (p_any) {
+            if (lane == 0) p_base = atomicAdd(io.list_count, __popc(walkers));
+            p_rank = (first_bvh >= 0) ? __popc(walkers & ((1u << lane) - 1u)) : -1;
+            p_entry = make_int2(i, first_bvh);
         }
         if (i < n) {
             if (io.final_pass && first_bvh < 0) finish_ray<MODE>(io, i, best, o4);
             else io.hits[i] = make_float4(best.t, __int_as_float(best.prim), __int_as_float(best.top), best.t_lo);
         }
+    }
+    if (p_any) {                                          // the last iteration's append
+        const int b = __shfl_sync(FULL, p_base, 0);
+        if (p_rank >= 0) io.list[b + p_rank] = p_entry;
     }
 }
 
