@@ -64,7 +64,15 @@ struct RayQueue { float4* o; float4* d; float4* w; };
 struct ShadowQueue { float4* o; float4* d; float4* c; };
 
 // counters[0], [1]: ray queue counts (ping-pong); [2]: shadow queue count
-struct Counters { int ray[2]; int shadow; int ties; int cursor_extend; int cursor_shadow; int cursor_extend_sdf; int cursor_shadow_sdf; int list_extend; int list_shadow; unsigned long long stats[24]; };
+// Every counter sits in a 128-byte line of its own (JSRT_COUNTER_PAD=0: packed as in round 1): the queue counters that one
+// kernel bumps concurrently — shade_kernel's children and shadow counts, a trace wave's work-list count and cursor — shared
+// one 32-byte sector, i.e. one L2 atomic unit serialised all of them (profiles/r2_ab.md §6).
+#ifndef JSRT_COUNTER_PAD
+#define JSRT_COUNTER_PAD 1
+#endif
+struct alignas(JSRT_COUNTER_PAD ? 128 : 4) Cnt { int v; };
+constexpr int kCntStride = (int)(sizeof(Cnt) / sizeof(int));      // distance between consecutive counters, in ints
+struct Counters { Cnt ray[2], shadow, ties, cursor_extend, cursor_shadow, cursor_extend_sdf, cursor_shadow_sdf, list_extend, list_shadow; unsigned long long stats[24]; };
 enum { ST_PRIMARY = 0, ST_SECONDARY = 1, ST_SHADOW = 2, ST_SHADED = 3, ST_SAMPLES = 4,
        ST_NODES = 8, ST_LEAF_PRIMS = 11, ST_TOP_PRIMS = 14, ST_SDF_EVALS = 17 };   // + ray class (0 primary, 1 secondary, 2 shadow)
 
@@ -462,15 +470,15 @@ __global__ void __launch_bounds__(kBlock) fold_samples_kernel(const __grid_const
 // bookkeeping between levels: fold queue sizes into the ray statistics and recycle the counters
 // (fused: shade_kernel<FUSE> has counted the shadow rays itself — the queue only holds the walkers)
 __global__ void level_end_kernel(Counters* c, int cur, int level, int next_cap, int shadow_cap, int fused) {
-    c->stats[level == 0 ? ST_PRIMARY : ST_SECONDARY] += (unsigned long long)c->ray[cur];
-    if (!fused) c->stats[ST_SHADOW] += (unsigned long long)min(c->shadow, shadow_cap);
-    c->ray[cur] = 0;
-    c->shadow = 0;
-    c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0; c->list_extend = 0; c->list_shadow = 0; c->ties = 0;
-    if (c->ray[cur ^ 1] > next_cap) c->ray[cur ^ 1] = next_cap;
+    c->stats[level == 0 ? ST_PRIMARY : ST_SECONDARY] += (unsigned long long)c->ray[cur].v;
+    if (!fused) c->stats[ST_SHADOW] += (unsigned long long)min(c->shadow.v, shadow_cap);
+    c->ray[cur].v = 0;
+    c->shadow.v = 0;
+    c->cursor_extend.v = 0; c->cursor_shadow.v = 0; c->cursor_extend_sdf.v = 0; c->cursor_shadow_sdf.v = 0; c->list_extend.v = 0; c->list_shadow.v = 0; c->ties.v = 0;
+    if (c->ray[cur ^ 1].v > next_cap) c->ray[cur ^ 1].v = next_cap;
 }
 __global__ void set_count_kernel(Counters* c, int which, int n, int count_samples) {
-    c->ray[which] = n; c->ray[which ^ 1] = 0; c->shadow = 0; c->cursor_extend = 0; c->cursor_shadow = 0; c->cursor_extend_sdf = 0; c->cursor_shadow_sdf = 0; c->list_extend = 0; c->list_shadow = 0; c->ties = 0;
+    c->ray[which].v = n; c->ray[which ^ 1].v = 0; c->shadow.v = 0; c->cursor_extend.v = 0; c->cursor_shadow.v = 0; c->cursor_extend_sdf.v = 0; c->cursor_shadow_sdf.v = 0; c->list_extend.v = 0; c->list_shadow.v = 0; c->ties.v = 0;
     if (count_samples) c->stats[ST_SAMPLES] += (unsigned long long)n;
 }
 
@@ -961,7 +969,7 @@ struct Renderer::Impl {
         if (has_sdf_tops) {
             ++launches;
             io.final_pass = 1;
-            io.cursor = io0.cursor + 2;          // cursor_extend_sdf / cursor_shadow_sdf
+            io.cursor = io0.cursor + 2 * kCntStride;          // cursor_extend_sdf / cursor_shadow_sdf (two counters further on)
             #define JSRT_SDF(C, R) sdf_kernel<MODE, C, R><<<grid_sdf[MODE], kBlock, 0, stream>>>(ds, io)
             if (has_rtu) { if (count_work) JSRT_SDF(true, true); else JSRT_SDF(false, true); }
             else { if (count_work) JSRT_SDF(true, false); else JSRT_SDF(false, false); }
@@ -973,17 +981,17 @@ struct Renderer::Impl {
         }
     }
     void launchExtend(int cur, bool count_work, const GenParams* gen) {
-        TraceIO io{}; io.o = rq[cur].o; io.d = rq[cur].d; io.hits = hits; io.count = &counters->ray[cur]; io.cap = ray_cap;
-        io.cursor = &counters->cursor_extend; io.stats = counters->stats; io.aux = sdf_normals;
-        io.tie_list = tie_list; io.tie_count = &counters->ties; io.tie_cap = kTieCap;
-        io.list = work_list; io.list_count = &counters->list_extend;
+        TraceIO io{}; io.o = rq[cur].o; io.d = rq[cur].d; io.hits = hits; io.count = &counters->ray[cur].v; io.cap = ray_cap;
+        io.cursor = &counters->cursor_extend.v; io.stats = counters->stats; io.aux = sdf_normals;
+        io.tie_list = tie_list; io.tie_count = &counters->ties.v; io.tie_cap = kTieCap;
+        io.list = work_list; io.list_count = &counters->list_extend.v;
         timed(1, [&] { launchTrace<TM_EXTEND>(io, count_work, gen ? grid_extend_gen : grid_extend, gen, false); });
     }
     void launchShadow(bool count_work, float4* radiance, int accum_stride, int pass0) {
-        TraceIO io{}; io.o = sq.o; io.d = sq.d; io.c = sq.c; io.hits = shadow_hits; io.accum = radiance; io.count = &counters->shadow; io.cap = shadow_cap;
+        TraceIO io{}; io.o = sq.o; io.d = sq.d; io.c = sq.c; io.hits = shadow_hits; io.accum = radiance; io.count = &counters->shadow.v; io.cap = shadow_cap;
         io.accum_stride = accum_stride; io.pass0 = pass0;
-        io.cursor = &counters->cursor_shadow; io.stats = counters->stats;
-        io.list = work_list; io.list_count = &counters->list_shadow;
+        io.cursor = &counters->cursor_shadow.v; io.stats = counters->stats;
+        io.list = work_list; io.list_count = &counters->list_shadow.v;
         if (fuse_shadow && ds.n_bvh == 0) return;          // nothing can be queued: every shadow ray was settled in shade_kernel
         timed(3, [&] { launchTrace<TM_SHADOW>(io, count_work, grid_shadow, nullptr, fuse_shadow); });
     }
@@ -1023,8 +1031,8 @@ struct Renderer::Impl {
             launchExtend(cur, count_work, (level == 0 && fuse_gen) ? &g : nullptr);
             timed(2, [&] {
                 ShadeIO io{};
-                io.q = rq[cur]; io.count = &counters->ray[cur]; io.hits = hits; io.next = rq[cur ^ 1]; io.next_count = &counters->ray[cur ^ 1]; io.next_cap = ray_cap;
-                io.sq = sq; io.shadow_count = &counters->shadow; io.shadow_cap = shadow_cap; io.accum = radiance; io.seed = seed; io.stats = counters->stats;
+                io.q = rq[cur]; io.count = &counters->ray[cur].v; io.hits = hits; io.next = rq[cur ^ 1]; io.next_count = &counters->ray[cur ^ 1].v; io.next_cap = ray_cap;
+                io.sq = sq; io.shadow_count = &counters->shadow.v; io.shadow_cap = shadow_cap; io.accum = radiance; io.seed = seed; io.stats = counters->stats;
                 io.overflow = overflow; io.sdf_normals = has_sdf ? sdf_normals : nullptr; io.accum_stride = rstride; io.pass0 = pass0;
                 io.aov_nd = aov ? aov_nd : nullptr; io.aov_var = aov ? aov_var : nullptr;
                 const bool sort_now = sort_shade && level >= sort_from;
