@@ -5,7 +5,9 @@
   * optimistic queue sizing: a batch that overflows its queues is re-run smaller, the image is unchanged;
   * maxRecursionDepth beyond 32 (path-tree node ids no longer wrap; ADVICE r1);
   * aggregates nested the ways src/aggregates.js:14-18,43-49 allows;
-  * one scene handle on two devices (jsrt_scene_create with ndev = 2): same image as one device.
+  * one scene handle on two devices (jsrt_scene_create with ndev = 2): same image as one device;
+  * kernel builds specialised on the scene's content (shade_kernel<LEAN>, bvh_kernel<MESH>) and the fused SDF instructions:
+    same rays, same image as the general builds / the plain bytecode.
 """
 import os
 from contextlib import contextmanager
@@ -63,6 +65,41 @@ def test_fused_paths_equal_the_unfused_ones(name, kw):
         for k in CENSUS:
             assert st[k] == sref[k], (toggles, k, st[k], sref[k])
         assert np.allclose(acc, ref, rtol=1e-5, atol=1e-5), toggles           # FP32 summation order only
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("bunny_path", dict(width=480, height=270, aspect=16 / 9)),      # LEAN 2 + MESH: plane + mesh, point lights
+    ("starwars", dict(width=320, height=180, aspect=16 / 9)),        # LEAN 1 + MESH: spheres + area light beside the meshes
+    ("cornell_box_path", dict(width=160, height=160)),               # LEAN 1, sorted tiles, no BVH
+    ("AHollowTetrahedron", dict(width=192, height=192)),             # two aggregates sharing one kdtree
+], ids=["bunny_path", "starwars", "cornell_box_path", "AHollowTetrahedron"])
+def test_specialised_builds_equal_the_general_ones(name, kw):
+    """shade_kernel<LEAN> and bvh_kernel<MESH> only drop code the scene cannot reach: same ray census, same image as the general
+    builds (JSRT_SHADE_LEAN=0 JSRT_BVH_MESH=0) up to FP32 summation order."""
+    _, mp = scene_blobs(name, **kw)
+    ref, sref = _render(_scene(mp, JSRT_SHADE_LEAN=0, JSRT_BVH_MESH=0), 3)
+    for toggles in (dict(), dict(JSRT_SHADE_LEAN=1), dict(JSRT_BVH_MESH=0), dict(JSRT_SHADE_LEAN=0)):
+        acc, st = _render(_scene(mp, **toggles), 3)
+        for k in CENSUS:
+            assert st[k] == sref[k], (toggles, k, st[k], sref[k])
+        assert np.allclose(acc, ref, rtol=1e-5, atol=1e-5), toggles
+
+
+def test_sdf_fused_instructions_equal_the_plain_program():
+    """S_CROSS / S_RTU_CROSS and the world-box reject are bit-for-bit the plain instruction stream: SDF_Menger rendered with the
+    peepholes off (JSRT_SDF_FUSE=0) gives the same hits, distances and image."""
+    from jsraytracer_b200 import lib
+    _, mp = scene_blobs("SDF_Menger", width=128, height=128)
+    plain = _scene(mp, JSRT_SDF_FUSE=0)
+    fused = _scene(mp)
+    assert fused.info["n_sdf_instrs"] == 8 and plain.info["n_sdf_instrs"] > 45
+    ids0, t0 = plain.primary_hits()
+    ids1, t1 = fused.primary_hits()
+    assert np.array_equal(ids0, ids1) and np.array_equal(t0, t1)
+    plain.render(0, 1, seed=1, flags=lib.FLAG_NO_JITTER)
+    fused.render(0, 1, seed=1, flags=lib.FLAG_NO_JITTER)
+    a0, a1 = plain.read_accum()[0], fused.read_accum()[0]
+    assert np.allclose(a0, a1, rtol=1e-6, atol=1e-7)                  # (the same arithmetic; only the order of the FP32 reductions may differ)
 
 
 def test_staged_walk_hit_ids_dragon():
