@@ -52,7 +52,11 @@ struct Ctx {
     uint32_t sample_key = 0;
     int rc = RC_PRIMARY;
     Counters* c = nullptr;
-    double u(uint32_t node, uint32_t dim) const { return rng_u01(rng_node_key(sample_key, node), dim); }
+    // tape mode (orc_render flags bit1): the draws of one pixel sample come from ONE sequential stream in call order,
+    // the way Math.random() serves the reference.  With the same stream behind Math.random (oracle/refjs.py) the
+    // restatement and the reference's own sources must then agree sample by sample — which also pins the ORDER of draws.
+    bool tape = false; mutable uint64_t tape_state = 0;
+    double u(uint32_t node, uint32_t dim) const { return tape ? rng_tape_next(tape_state) : rng_u01(rng_node_key(sample_key, node), dim); }
 };
 
 // ---------------------------------------------------------------------------
@@ -502,11 +506,13 @@ struct TextureMaterialColor : MaterialColor {
 
 // ---------------------------------------------------------------------------
 struct LightSample { Vec direction, color; };
-struct Light { virtual ~Light() {} virtual int sampleCount() const = 0; virtual LightSample sample(const Vec& pos, double u0, double u1) const = 0; };
+struct Light { virtual ~Light() {} virtual int sampleCount() const = 0; virtual LightSample sample(const Vec& pos, double u0, double u1) const = 0;
+               virtual bool draws() const { return true; } };   // does sample() consume its two random numbers? (tape mode must not draw for point lights)
 static double falloff(const Vec& delta) { return 1 / (4 * PI * delta.squarednorm()); }   // src/lights.js:21-23
 struct SimplePointLight : Light {     // src/lights.js:45-53
     Vec position; MaterialColor* color_mc;
     int sampleCount() const override { return 1; }
+    bool draws() const override { return false; }
     LightSample sample(const Vec& surface_position, double, double) const override {
         const Vec delta = position.minus(surface_position);
         MatData md; md.hasUV = true; md.UV = cartesianToSpherical(delta.normalized());
@@ -683,7 +689,9 @@ struct PhongMaterial : Material {
             int count = 0; Vec light_color = Vec::of(0, 0, 0);
             const int ns = l->sampleCount();
             for (int s = 0; s < ns; ++s) {
-                const double u0 = ctx.u(node, dim), u1 = ctx.u(node, dim + 1); dim += 2;
+                double u0 = 0, u1 = 0;
+                if (!ctx.tape || l->draws()) { u0 = ctx.u(node, dim); u1 = ctx.u(node, dim + 1); }
+                dim += 2;
                 const LightSample ls = l->sample(d.position, u0, u1);
                 ++count;
                 const int saved = ctx.rc; ctx.rc = RC_SHADOW;
@@ -773,7 +781,9 @@ struct PhongPathTracingMaterial : FresnelPhongMaterial {
         const double probSum = diffuseProb + specularProb;
         if (probSum == 0) return false;
         if (ctx.u(node, dimBase + 1) < (diffuseProb / probSum)) {
-            dir = N.plus(spherePick(ctx.u(node, dimBase + 2), ctx.u(node, dimBase + 3)).to4(false)).normalized();   // scatterDiffuse :438-440
+            const double ut = ctx.u(node, dimBase + 2);      // theta first, then phi (src/math.js:181-182): sequenced for tape mode
+            const double up = ctx.u(node, dimBase + 3);
+            dir = N.plus(spherePick(ut, up).to4(false)).normalized();   // scatterDiffuse :438-440
             col = d.diffusivity.times(1 / PI);
             return true;
         }
@@ -1076,7 +1086,7 @@ int orc_primary_hits(void* h, int W, int H, int32_t* prim_id, double* tout, int 
 // IncrementalMultisamplingRenderer.render (src/renderers.js:70-117) for passes
 // [first_pass, first_pass+n_passes): `sum` (W*H*3 f32, row-major) is the
 // reference's `buffer[px][py]` and is accumulated in f32 like `Vec.plus`.
-// flags bit0: no pixel jitter (SimpleRenderer sampling, :21-25).
+// flags bit0: no pixel jitter (SimpleRenderer sampling, :21-25).  bit1: tape mode (see Ctx).
 // counters[22]: rays[3], bvh_nodes[3], bvh_prims[3], top_tests[3], sdf_evals[3], shaded_hits, wide4[3], wide8[3]
 int orc_render(void* h, int W, int H, int first_pass, int n_passes, uint64_t seed, int flags, int x_offset, int x_delt,
                float* sum, int nthreads, uint64_t* counters) {
@@ -1096,6 +1106,7 @@ int orc_render(void* h, int W, int H, int first_pass, int n_passes, uint64_t see
                 float* acc = sum + (size_t)pixel * 3;
                 for (int iter = first_pass; iter < first_pass + n_passes; ++iter) {
                     ctx.sample_key = rng_sample_key(seed, pixel, (uint32_t)iter);
+                    if (flags & 2) { ctx.tape = true; ctx.tape_state = rng_tape_seed(seed, pixel, (uint32_t)iter); }
                     double sx = x, sy = y;
                     if (jitter) { sx = x + pixel_width * (ctx.u(1, DIM_JITTER_X) - 0.5); sy = y + pixel_height * (ctx.u(1, DIM_JITTER_Y) - 0.5); }
                     ctx.rc = RC_PRIMARY;

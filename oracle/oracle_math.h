@@ -139,6 +139,16 @@ inline uint32_t rng_child_node(uint32_t node, uint32_t which) {
 inline double rng_u01(uint32_t node_key, uint32_t dim) {
     return (double)(hash32(node_key + 0xc2b2ae35U * (dim + 1)) >> 8) * (1.0 / 16777216.0);
 }
+// tape mode: one sequential splitmix64 stream per pixel sample (the same few lines in Python: oracle/refjs.py)
+inline uint64_t rng_tape_seed(uint64_t seed, uint32_t pixel, uint32_t pass) { return (seed << 48) ^ ((uint64_t)pass << 32) ^ (uint64_t)pixel; }
+inline double rng_tape_next(uint64_t& state) {
+    state += 0x9E3779B97F4A7C15ULL;
+    uint64_t z = state;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
 enum { DIM_JITTER_X = 0, DIM_JITTER_Y = 1, DIM_LENS_A = 2, DIM_LENS_R = 3, DIM_LIGHTS = 8 };
 
 }  // namespace orc
