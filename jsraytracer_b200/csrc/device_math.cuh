@@ -252,12 +252,21 @@ JSRT_DEV double sdf_smooth_min(double a, double b, double k) {   // src/sdf.js:1
 // N = round(|x| * 10^k) with k chosen so that N has 8 digits, result = N / 10^k (or N * 10^-k for
 // |x| >= 1e8); 10^|k| is exact in f64 for |k| <= 22 and the final division is correctly rounded, so this
 // equals the decimal round trip except when |x| * 10^k lands within an ulp of a half-way point.
+// Exact half-way cases go UP in magnitude ("pick the larger n", ECMA-262 21.1.3.5; printf / rint would go to even):
+// they are common here, because a coordinate that came from an f32 has few significant bits (4.05078125 ->
+// 4.0507813).  js_round_half_up also looks at the rounding error of the product, so a product that merely ROUNDED to
+// n + 0.5 from below is not bumped.
 __device__ const double kPow10[32] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
                                       1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22, 1e23, 1e24, 1e25, 1e26, 1e27, 1e28, 1e29, 1e30, 1e31};
 // correctly rounded reciprocals of the exact powers (the compiler folds these IEEE divisions)
 __device__ const double kInvPow10[23] = {1.0 / 1e0, 1.0 / 1e1, 1.0 / 1e2, 1.0 / 1e3, 1.0 / 1e4, 1.0 / 1e5, 1.0 / 1e6, 1.0 / 1e7, 1.0 / 1e8, 1.0 / 1e9,
                                          1.0 / 1e10, 1.0 / 1e11, 1.0 / 1e12, 1.0 / 1e13, 1.0 / 1e14, 1.0 / 1e15, 1.0 / 1e16, 1.0 / 1e17, 1.0 / 1e18,
                                          1.0 / 1e19, 1.0 / 1e20, 1.0 / 1e21, 1.0 / 1e22};
+JSRT_DEV double js_round_half_up(double y, double ax, double p10) {   // y = rn(ax * p10), 0 < y < 2^27
+    double nn = floor(dadd(y, 0.5));
+    if (dsub(nn, y) == 0.5 && fma(ax, p10, -y) < 0.0) nn = dsub(nn, 1.0);
+    return nn;
+}
 // (out of line: never taken by coordinates an SDF scene produces, and its exp10 / log10 would sit in the interpreter's hot code)
 __device__ __noinline__ double js_to_precision8_slow(double x) {
     const double ax = fabs(x);
@@ -272,7 +281,7 @@ __device__ __noinline__ double js_to_precision8_slow(double x) {
     }
     double y = (k >= 0) ? dmul(ax, kPow10[k]) : ax / kPow10[-k];
     if (y >= 1e8) { --k; y = (k >= 0) ? dmul(ax, kPow10[k]) : ax / kPow10[-k]; }
-    const double nn = rint(y);
+    const double nn = (k >= 0) ? js_round_half_up(y, ax, kPow10[k]) : floor(dadd(y, 0.5));
     const double r = (k >= 0) ? nn / kPow10[k] : dmul(nn, kPow10[-k]);
     return copysign(r, x);
 }
@@ -289,8 +298,8 @@ JSRT_DEV double js_to_precision8(double x) {
     double y = dmul(ax, __ldg(kPow10 + k));
     if (y >= 1e8) { --k; y = dmul(ax, __ldg(kPow10 + k)); }
     if (k < 0) return js_to_precision8_slow(x);
-    const double nn = rint(y);
     const double p10 = __ldg(kPow10 + k), inv = __ldg(kInvPow10 + k);
+    const double nn = js_round_half_up(y, ax, p10);
     const double q0 = dmul(nn, inv);
     const double q = fma(fma(-q0, p10, nn), inv, q0);
     return copysign(q, x);

@@ -430,10 +430,14 @@ def median(arr):
 
 
 def js_to_precision8(x: float) -> float:
-    """Number(x.toPrecision(8)) — used by Math.fmod (src/math.js:27)."""
+    """Number(x.toPrecision(8)) — used by Math.fmod (src/math.js:27).  toPrecision rounds the exact decimal expansion
+    and breaks exact ties upwards in magnitude (ECMA-262 21.1.3.5: "pick the larger n"), where "%.7e" goes to even."""
     if x != x or x in (math.inf, -math.inf) or x == 0:
         return x
-    return float("%.7e" % x)
+    from decimal import Decimal, ROUND_HALF_UP
+    d = Decimal(abs(x))
+    r = d.quantize(Decimal(1).scaleb(d.adjusted() - 7), rounding=ROUND_HALF_UP)
+    return math.copysign(float(r), x)
 
 
 def fmod(a, b):  # src/math.js:27

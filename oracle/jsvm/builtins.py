@@ -1334,6 +1334,8 @@ def install(vm):
             return
         p.state = state
         p.value = value
+        if state == 'rejected' and not p.reactions:
+            vm.rejections.append(p)       # reported by the host if nothing ever handles it
         for r in p.reactions:
             schedule(p, r)
         p.reactions = []
@@ -1395,6 +1397,8 @@ def install(vm):
 
     def promise_then(this, args):
         child = new_promise()
+        if this in vm.rejections:
+            vm.rejections.remove(this)
         r = (arg(args, 0), arg(args, 1), child)
         if this.state == 'pending':
             this.reactions.append(r)

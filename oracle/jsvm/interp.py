@@ -110,6 +110,7 @@ class VM:
     def __init__(self):
         self.root = Scope(None)
         self.jobs = []          # promise reaction queue
+        self.rejections = []    # rejected promises nobody has handled (yet)
         self.random = None      # host-provided Math.random
         from . import builtins
         builtins.install(self)

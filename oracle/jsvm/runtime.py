@@ -192,7 +192,7 @@ def num_to_str(v):
         return '-Infinity'
     if v == 0:
         return '0'
-    if v == int(v) and abs(v) < 1e21:
+    if abs(v) < 9007199254740992.0 and v == int(v):
         return str(int(v))
     r = repr(abs(v))
     sign = '-' if v < 0 else ''

@@ -16,6 +16,7 @@
 // every matrix entry is f64, every Vec-returning op rounds to f32 on store.
 #pragma once
 #include <cmath>
+#include <cstring>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -104,9 +105,34 @@ struct Ray {
 };
 
 // Math.fmod src/math.js:27: Number((a - floor(a/b)*b).toPrecision(8))
+// Number.prototype.toPrecision rounds the EXACT decimal expansion of the double to 8 significant digits and, when two
+// 8-digit numbers are equally near, "picks the larger n" (ECMA-262 21.1.3.5 step 10.a; V8's bignum dtoa does the same:
+// the last digit is bumped when twice the remainder >= the denominator).  printf rounds such exact ties to even, so they
+// are detected and rounded up here.  Ties are not exotic on this path: a coordinate that came from an f32 has few
+// significant bits (4.05078125 -> "4.0507813", not "4.0507812"); found by the pin against the reference's own output
+// (tests/test_refjs_pin.py, SDF_SphereRepetition).
 inline double js_toPrecision8(double x) {
     if (!(x == x) || std::isinf(x) || x == 0) return x;
     char buf[64];
+    snprintf(buf, sizeof buf, "%.17e", x);             // [-]d.ddddddd|dddddddddd e+XX (itself correctly rounded)
+    const char* p = buf + (buf[0] == '-' ? 1 : 0);
+    bool maybe_tie = p[9] == '5';
+    for (int i = 10; maybe_tie && i <= 18; ++i) maybe_tie = p[i] == '0';
+    if (maybe_tie) {
+        char big[900];
+        snprintf(big, sizeof big, "%.800e", x);        // every digit a double can have (<= 767 significant)
+        const char* q = big + (big[0] == '-' ? 1 : 0);
+        bool tie = q[9] == '5';
+        const char* e = q + 10;
+        for (; tie && *e != 'e'; ++e) tie = *e == '0';
+        if (tie) {
+            unsigned long long n = 0;
+            for (int i = 0; i <= 8; ++i) if (q[i] != '.') n = n * 10 + (unsigned long long)(q[i] - '0');
+            const int ex = atoi(strchr(q, 'e') + 1);
+            snprintf(buf, sizeof buf, "%s%llue%d", big[0] == '-' ? "-" : "", n + 1, ex - 7);
+            return strtod(buf, nullptr);
+        }
+    }
     snprintf(buf, sizeof buf, "%.7e", x);
     return strtod(buf, nullptr);
 }

@@ -21,6 +21,7 @@ import numpy as np
 
 from .jsvm import VM, UNDEF, JSThrow, JSObject, JSArray, JSTypedArray
 
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_ROOT = os.environ.get("JSRT_REFERENCE_ROOT", "/root/reference")
 
 # src/worker.js:3-14, plus the serializer (tests/test_to_json.js:8-19 loads it the same way)
@@ -87,6 +88,12 @@ class RefJS:
             with open(os.path.join(root, "src", f)) as fh:
                 vm.run(fh.read(), f)
         vm.run(_PRELUDE, "<prelude>")
+        # The product's own host-side JavaScript, loaded the way its header says it is (as a classic script next to the
+        # reference's sources).  It carries the fix for the reference serializer's lossy Triangle.serialize
+        # (src/geometry.js:355-357 writes `psdata: serializeStep(this.ps)`: vertex normals never reach the wire).
+        G["require"] = vm.native("require", self._require)
+        with open(os.path.join(_REPO, "js", "cuda_renderer.js")) as fh:
+            vm.run(fh.read(), "js/cuda_renderer.js")
         self.test = None
         self._on_sample = None
 
@@ -94,7 +101,8 @@ class RefJS:
     def _fetch(self, this, args):
         vm = self.vm
         url = vm.tostr(args[0])
-        path = os.path.normpath(os.path.join(self.cwd, url))
+        # a worker resolves relative URLs against its own script, src/worker.js ("../assets/x.obj" -> <root>/assets/x.obj)
+        path = os.path.normpath(os.path.join(self.root, "src", url))
         resp = JSObject(vm.ObjectProto)
         if not os.path.isfile(path):
             resp.props["ok"] = False
@@ -106,6 +114,9 @@ class RefJS:
                 return vm.promise_resolve(fh.read())
         resp.props["text"] = vm.native("text", text)
         return vm.promise_resolve(resp)
+
+    def _require(self, this, args):
+        self.vm.throw("Error", "Cannot find module '%s'" % self.vm.tostr(args[0]))
 
     def _sample_done(self, this, args):
         if self._on_sample is not None:
@@ -124,6 +135,8 @@ class RefJS:
         vm.run_jobs()
         t = vm.root.vars.get("__test")
         if t is None or t is UNDEF:
+            for p in vm.rejections:
+                raise RuntimeError("configureTest failed: unhandled rejection: %s" % vm.inspect(p.value))
             raise RuntimeError("configureTest never called back (an asset failed to load?)")
         self.test = t
         return self.info()
@@ -137,11 +150,25 @@ class RefJS:
             "maxRecursionDepth": int(ev("__test.renderer.maxRecursionDepth")),
         }
 
-    def scene_json(self, width=None, height=None):
-        """the reference's own wire format of the configured test: `new Serializer(test)`, tests/test_to_json.js:30"""
+    def scene_json(self, width=None, height=None, triangle_fix=True):
+        """the reference's own wire format of the configured test: `new Serializer(test)`, tests/test_to_json.js:30.
+        triangle_fix: install js/cuda_renderer.js's `installTriangleSerializeFix()` first, as CUDARenderer does — without
+        it the reference's serializer drops the vertex normals its own worker path shades with."""
         if width is not None:
             self.vm.run("__test.width = %d; __test.height = %d;" % (width, height))
+        if triangle_fix:
+            self.vm.run("installTriangleSerializeFix();")
         return self.vm.eval_expr("JSON.stringify(new Serializer(__test).plain())")
+
+    def render_simple(self, width, height):
+        """the same world and camera through the reference's un-jittered `SimpleRenderer` (src/renderers.js:1-45) — for a
+        scene without random decisions this is a deterministic image that any implementation can be compared with"""
+        self.vm.run("var __saved = __test.renderer;"
+                    "__test.renderer = new SimpleRenderer(__saved.world, __saved.camera, __saved.maxRecursionDepth);")
+        try:
+            return self.render(width, height, 1)
+        finally:
+            self.vm.run("__test.renderer = __saved;")
 
     def render(self, width, height, passes=1, x_offset=0, x_delt=1, seed=1):
         """`test.renderer.render(new PixelBuffer(w, h), 1000, callback, workerIndex, workerCount)`, src/worker.js:26-32.

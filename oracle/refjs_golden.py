@@ -1,0 +1,99 @@
+"""TEST INFRASTRUCTURE — writes tests/golden/refjs_<scene>.npz: outputs of THE REFERENCE ITSELF (its unmodified
+src/*.js and tests/<scene>/test.mjs executed by oracle/jsvm through oracle/refjs.py), which the oracle is pinned to.
+
+    python -m oracle.refjs_golden                # every scene of the table below, in parallel
+    python -m oracle.refjs_golden BoxBall bunny  # some of them
+
+Runs only where /root/reference exists (this container).  Each fixture holds
+    json    the scene in the reference's own wire format (`new Serializer(test)`, zlib-compressed UTF-8)
+    mean    (H, W, 3) f32: the colour the reference's render loop hands to PixelBuffer.setColor after the last pass
+    rgba8   (H, W, 4) u8:  the ImageData the reference filled
+    draws   (H, W) i32:    Math.random() calls of each pixel's last sample
+    simple_mean / simple_rgba8   (scenes whose only random numbers are the pixel jitter) the same world and camera through
+            the reference's un-jittered SimpleRenderer: a deterministic image the CUDA path is compared with directly
+    meta    name, width, height, passes, seed, renderer class, depth, seconds, sha256 of the sources that ran
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+import time
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+# (scene of /root/reference/tests, width, height, passes).  Sizes are small because the interpreter is ~1000x slower than
+# V8; widths differ from heights so that a transposed image cannot pass.  Not covered: dragon / dragon_json / x-wing /
+# starwars (100 000+ triangles: hours in the interpreter), toledo* (asset missing from the reference tree), bottle
+# (needs createImageBitmap to decode a PNG texture).
+TABLE = [
+    ("BoxBall", 24, 16, 2), ("BoxBall_DOF", 24, 16, 2), ("BoxBall_path", 20, 12, 1), ("ASimpleScene", 24, 16, 2),
+    ("Aggregates", 24, 16, 1), ("AHollowTetrahedron", 24, 16, 1), ("AMultipleBVH", 24, 16, 1),
+    ("refraction", 24, 16, 2), ("refraction_simple", 24, 16, 2), ("refraction_path", 20, 12, 2),
+    ("cornell_box", 20, 12, 2), ("cornell_box_emissive", 20, 12, 2), ("cornell_box_path", 24, 16, 2),
+    ("spheres010", 24, 16, 1), ("spheres050", 20, 12, 1),
+    ("SDF_Simple", 20, 12, 2), ("SDF_BoxBall", 20, 12, 2), ("SDF_Combinations", 20, 12, 1), ("SDF_Menger", 20, 12, 2),
+    ("SDF_Sierpinski", 20, 12, 2), ("SDF_SphereRepetition", 20, 12, 1), ("SDF_RecursiveUnionTest", 16, 10, 1),
+    ("diamond", 24, 16, 1), ("heart", 24, 16, 1), ("cat", 24, 16, 1), ("utah_teapot", 20, 12, 1),
+    ("bunny", 24, 16, 1), ("bunny_path", 24, 16, 2), ("tie_fighter", 20, 12, 1),
+]
+
+
+def sources_digest(root, name):
+    from .refjs import SOURCES
+    h = hashlib.sha256()
+    for f in SOURCES:
+        h.update(open(os.path.join(root, "src", f), "rb").read())
+    h.update(open(os.path.join(root, "tests", name, "test.mjs"), "rb").read())
+    return h.hexdigest()
+
+
+def make(name, W, H, passes, seed=1):
+    from .refjs import RefJS, REF_ROOT
+    t0 = time.time()
+    r = RefJS()
+    info = r.load_test(name)
+    js = r.scene_json(W, H)
+    t1 = time.time()
+    mean, rgba, draws = r.render(W, H, passes, seed=seed)
+    extra = {}
+    if info["renderer"] != "SimpleRenderer" and draws.max() <= 2:
+        smean, srgba, sdraws = r.render_simple(W, H)
+        assert sdraws.max() == 0
+        extra = dict(simple_mean=smean, simple_rgba8=srgba)
+    meta = dict(name=name, width=W, height=H, passes=passes if info["renderer"] != "SimpleRenderer" else 1, seed=seed,
+                renderer=info["renderer"], depth=info["maxRecursionDepth"], ref_width=info["width"], ref_height=info["height"],
+                ref_spp=info["samplesPerPixel"], load_s=round(t1 - t0, 1), render_s=round(time.time() - t1, 1),
+                sources_sha256=sources_digest(REF_ROOT, name), json_bytes=len(js))
+    out = os.path.join(GOLDEN, "refjs_%s.npz" % name)
+    np.savez_compressed(out, json=np.frombuffer(zlib.compress(js.encode("utf8"), 9), dtype=np.uint8), mean=mean, rgba8=rgba,
+                        draws=draws, meta=np.array(json.dumps(meta)), **extra)
+    return meta
+
+
+def _worker(job):
+    name, W, H, passes = job
+    try:
+        return make(name, W, H, passes)
+    except Exception as e:      # noqa: BLE001 — reported per scene
+        return dict(name=name, error="%s: %s" % (type(e).__name__, e))
+
+
+def main(argv):
+    import multiprocessing as mp
+    jobs = [j for j in TABLE if not argv or j[0] in argv]
+    # longest first
+    slow = {"bunny": 9, "bunny_path": 9, "tie_fighter": 10, "utah_teapot": 8, "cat": 7, "cornell_box_path": 5, "SDF_Menger": 5}
+    jobs.sort(key=lambda j: -slow.get(j[0], 0))
+    with mp.Pool(min(len(jobs), max(1, (os.cpu_count() or 2) - 1))) as pool:
+        for meta in pool.imap_unordered(_worker, jobs):
+            print(json.dumps(meta), flush=True)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,180 @@
+"""Language-level checks of oracle/jsvm, the interpreter that executes the reference's sources for the fixtures of
+tests/test_refjs_pin.py.  Expected values are what ECMAScript specifies (each can be checked in any browser console);
+the cases concentrate on what the reference leans on: Float32Array subclasses (Vec), Array subclasses with a custom
+constructor (Mat) under map / slice / Array.of / Array.from, generators, destructuring, default parameters, closures,
+number formatting (Math.fmod uses toPrecision) and the numeric edge cases of the operators."""
+import math
+
+import pytest
+
+from oracle.jsvm import VM, JSThrow
+
+
+def js(src, expr):
+    vm = VM()
+    vm.random = lambda: 0.5
+    vm.run(src)
+    return vm.to_py(vm.eval_expr(expr))
+
+
+def ev(expr):
+    return js("", expr)
+
+
+CASES = [
+    # numbers and operators
+    ("0.1 + 0.2", 0.30000000000000004), ("7 % 3", 1), ("-7 % 3", -1), ("5.5 % 2", 1.5), ("2 ** 10", 1024), ("2 ** 3 ** 2", 512),
+    ("1 / 0", None), ("(1 / 0) === Infinity", True), ("(-1 / 0) === -Infinity", True), ("0 / 0 !== 0 / 0", True),
+    ("1 / -0 === -Infinity", True), ("5 | 0", 5), ("-5 >>> 0", 4294967291), ("1 << 31", -2147483648), ("~5", -6), ("7 & 3", 3),
+    ("(255).toString(16)", "ff"), ("'5' * '2'", 10), ("'5' + 2", "52"), ("5 + '2'", "52"), ("1 + true", 2), ("+'  12  '", 12),
+    ("null == undefined", True), ("null === undefined", False), ("0 == ''", True), ("'1' == 1", True), ("NaN == NaN", False),
+    ("[1, 2] + ''", "1,2"), ("typeof null", "object"), ("typeof undefined", "undefined"), ("typeof (() => 1)", "function"),
+    ("typeof notDeclared", "undefined"), ("1 < 2 && 2 < 3", True), ("'a' < 'b'", True), ("'10' < '9'", True), ("10 < 9", False),
+    ("null ?? 5", 5), ("0 ?? 5", 0), ("0 || 5", 5), ("undefined?.x", None), ("({a: {b: 2}}).a?.b", 2),
+    # Math
+    ("Math.round(2.5)", 3), ("Math.round(-2.5)", -2), ("Math.round(0.49999999999999994)", 0), ("Math.round(-0.4) === 0", True),
+    ("Math.max()", None), ("Math.max(1, 3, 2)", 3), ("Math.min(1, NaN) !== Math.min(1, NaN)", True), ("Math.sign(-3)", -1),
+    ("Math.sqrt(-1) !== Math.sqrt(-1)", True), ("Math.acos(2) !== Math.acos(2)", True), ("Math.log(0) === -Infinity", True),
+    ("Math.pow(2, 0.5)", math.sqrt(2)), ("Math.floor(-0.5)", -1), ("Math.ceil(0.2)", 1), ("Math.atan2(1, 1)", math.pi / 4),
+    ("Math.fround(0.1)", 0.10000000149011612), ("Math.abs(-3)", 3), ("Math.trunc(-2.7)", -2), ("Math.hypot(3, 4)", 5),
+    # number formatting
+    ("(0.1).toPrecision(3)", "0.100"), ("(123.456).toPrecision(4)", "123.5"), ("(0.000001234).toPrecision(2)", "0.0000012"),
+    ("(1234567).toPrecision(2)", "1.2e+6"), ("(100000005).toPrecision(8)", "1.0000001e+8"), ("(2.5).toFixed(0)", "3"),
+    ("(1.005).toFixed(2)", "1.00"), ("String(1e21)", "1e+21"), ("String(123456789012345680000)", "123456789012345680000"),
+    ("String(0.000001)", "0.000001"), ("String(1e-7)", "1e-7"), ("String(-1.5)", "-1.5"), ("String(100)", "100"),
+    ("String(0.1 + 0.2)", "0.30000000000000004"), ("Number('12.5')", 12.5), ("Number('abc') !== Number('abc')", True),
+    ("Number('')", 0), ("parseInt('42px')", 42), ("parseInt('ff', 16)", 255), ("parseFloat('3.14abc')", 3.14),
+    ("Number.parseInt('7') - 1", 6), ("isNaN(parseInt(''))", True), ("Number((5.3 - Math.floor(5.3 / 2) * 2).toPrecision(8))", 1.3),
+    # strings and regular expressions
+    ("'a,b,,c'.split(',').length", 4), ("'abc'.split('').reverse().join('')", "cba"), ("' x '.trim()", "x"),
+    ("'v 1.5 2  3'.match(/\\S+/g).length", 4), ("'f 1/2/3'.match(/(\\d+)(?:\\/(\\d*)(?:\\/(\\d+))?)?/).slice(1).join('|')", "1|2|3"),
+    ("'f 7'.match(/(\\d+)(?:\\/(\\d*)(?:\\/(\\d+))?)?/)[2] === undefined", True), ("/^\\s*($|#)/.test('  # c')", True),
+    ("/^\\s*($|#)/.test(' v 1')", False), ("'a/b/c.obj'.substring(0, 'a/b/c.obj'.lastIndexOf('/') + 1)", "a/b/"),
+    ("'abc'.length", 3), ("'abc'[1]", "b"), ("`x${1 + 1}y${'z'}`", "x2yz"), ("'aXbX'.replace(/X/g, '-')", "a-b-"),
+    ("/^#?([a-f\\d]{2})([a-f\\d]{2})([a-f\\d]{2})$/i.exec('#FF8000').slice(1).map(h => parseInt(h, 16)).join()", "255,128,0"),
+    # arrays
+    ("[3, 1, 2].sort().join()", "1,2,3"), ("[10, 9, 1].sort().join()", "1,10,9"), ("[10, 9, 1].sort((a, b) => a - b).join()", "1,9,10"),
+    ("[1, 2, 3].map(x => x * 2).join()", "2,4,6"), ("[1, 2, 3, 4].filter(x => x % 2).join()", "1,3"), ("[1, 2, 3].reduce((a, x) => a + x, 0)", 6),
+    ("[1, 2, 3].indexOf(2)", 1), ("[1, 2, 3].includes(4)", False), ("Array(3).fill(0).join()", "0,0,0"), ("new Array(2, 3).length", 2),
+    ("[1, 2, 3, 4, 5].slice(1, -1).join()", "2,3,4"), ("[1, 2, 3].concat([4], 5).join()", "1,2,3,4,5"), ("[...[1, 2], ...'ab'].join()", "1,2,a,b"),
+    ("(a => (a.splice(1, 1), a.join()))([1, 2, 3])", "1,3"), ("(a => (a.unshift(...a.splice(-1)), a.join()))([1, 2, 3])", "3,1,2"),
+    ("(a => (a.length = 1, a.join()))([1, 2, 3])", "1"), ("(a => (a[3] = 9, a.length))([1])", 4), ("[1, [2, [3]]].flat().length", 3),
+    ("Array.from({length: 3}, (x, i) => i * i).join()", "0,1,4"), ("Array.from(new Set([1, 1, 2])).join()", "1,2"), ("Array.isArray([])", True),
+    ("[[1, 'a'], [2, 'b']].map(([n, s]) => s + n).join()", "a1,b2"), ("[1, 2, 3].every(x => x > 0) && ![1, 2].some(x => x > 2)", True),
+    ("Object.entries({a: 1, b: 2}).map(([k, v]) => k + v).join()", "a1,b2"), ("Object.keys({b: 1, a: 2, 1: 0}).join()", "1,b,a"),
+    ("Object.assign({a: 1}, {b: 2}, null).b", 2), ("'x' in {x: 1}", True), ("(o => (delete o.x, 'x' in o))({x: 1})", False),
+    ("JSON.stringify({a: [1, 2.5, 'x', null, undefined], b: undefined, c: Infinity})", '{"a":[1,2.5,"x",null,null],"c":null}'),
+    ("JSON.parse('{\"a\": [1, {\"b\": 2}]}').a[1].b", 2),
+    # typed arrays
+    ("new Float32Array([0.1])[0]", 0.10000000149011612), ("new Float32Array(2).length", 2), ("new Float32Array([1e40])[0] === Infinity", True),
+    ("Float32Array.of(1, 2, 3).map(x => x / 3)[0]", 0.3333333432674408), ("new Uint8ClampedArray([300, -5, 1.5, 2.5, 254.5])  .join()", "255,0,2,2,254"),
+    ("new Uint8Array([257, -1])  .join()", "1,255"), ("new Int32Array([2147483648])[0]", -2147483648), ("Float32Array.from([1, 2]).reduce((a, x) => a + x, 0)", 3),
+    ("new Float32Array(3).fill(0.5).every(x => x == 0.5)", True), ("(a => (a[5] = 1, a.length))(new Float32Array(2))", 2),
+    ("new Float32Array([1, 2]) instanceof Float32Array", True), ("[...new Float32Array([1, 2])].length", 2),
+]
+
+
+@pytest.mark.parametrize("expr,want", CASES, ids=[c[0][:60] for c in CASES])
+def test_expression(expr, want):
+    got = ev(expr)
+    if isinstance(want, float) and not isinstance(want, bool):
+        assert got == pytest.approx(want, rel=0, abs=0)
+    else:
+        assert got == want
+
+
+def test_classes_super_statics_fields():
+    src = """
+    class A { static N = 0; tag = 'a'; constructor(x) { this.x = x; A.N++; } get2() { return this.x * 2; } static make() { return new this(5); }
+              toString() { return 'A(' + this.x + ')'; } }
+    class B extends A { constructor() { super(7); this.y = 1; } get2() { return super.get2() + this.y; } static make() { return super.make(); } }
+    class C extends B {}
+    var r = [new B().get2(), A.make().get2(), B.make().get2(), new C() instanceof A, A.N, new C().tag, '' + new A(3), C.name, new C().constructor === C];
+    """
+    assert js(src, "r") == [15, 10, 15, True, 4, "a", "A(3)", "C", True]
+
+
+def test_float32array_subclass_is_the_reference_vec_pattern():
+    # src/math.js:160-300: `class Vec extends Float32Array`, results of map() are Vecs with f32 rounding
+    src = """
+    class Vec extends Float32Array {
+        plus(b) { return (b && b.length) ? this.map((x, i) => x + b[i]) : this.map((x, i) => x + b); }
+        dot(b) { return this[0] * b[0] + this[1] * b[1] + this[2] * b[2]; }
+        to4(p) { return Vec.of(this[0], this[1] || 0, this[2] || 0, +p); }
+    }
+    var v = Vec.of(0.1, 0.2, 0.3).plus(Vec.from([1, 1, 1])), w = v.plus(1);
+    var r = [v instanceof Vec, w instanceof Vec, v[0], w[0], v.dot(v), v.to4(true).length, v.to4(true)[3], Array.from(v).length,
+             Vec.of(1, 2, 3).every((x, i) => x == i + 1), [...Vec.of(1, 2)].join('|')];
+    """
+    f = lambda x: float(__import__("numpy").float32(x))
+    v0 = f(f(0.1) + 1.0)
+    assert js(src, "r") == [True, True, v0, f(v0 + 1.0), js(src, "v[0]*v[0]+v[1]*v[1]+v[2]*v[2]"), 4, 1, 3, True, "1|2"]
+
+
+def test_array_subclass_with_custom_constructor_is_the_reference_mat_pattern():
+    # src/math.js:303-309: `class Mat extends Array { constructor(...args) { super(0); this.push(...args) } }` — Array.of /
+    # Array.from / map / slice all go through that constructor (ArraySpeciesCreate), with the spec's odd but exact results
+    src = """
+    class Mat extends Array {
+        constructor(...args) { super(0); this.push(...args); }
+        static identity(n) { let d = []; for (let i = 0; i < n; ++i) { let r = Array(n).fill(0); r[i] = 1; d.push(r); } return Mat.of.apply(Mat, d); }
+        times(s) { return this.map(r => r.map(x => s * x)); }
+        column(i) { return this.map(r => r[i]); }
+    }
+    var m = Mat.of([1, 2], [3, 4]), t = m.times(2), id = Mat.identity(3), s = m.slice(0, 1), f = Mat.from(m.map(r => r.slice()));
+    var r = [m.length, t.length, t instanceof Mat, t[1][1], id.length, id[2][2], id[0][1], s.length, s instanceof Mat, f.length,
+             m.column(1).join(), new Mat(5).length, new Mat(5)[0], (m.length = 0, m.push(...t), m[0][0])];
+    """
+    assert js(src, "r") == [2, 2, True, 8, 3, 1, 0, 1, True, 2, "2,4", 1, 5, 2]
+
+
+def test_generators_destructuring_closures_switch_try():
+    src = """
+    function* g(n) { for (let i = 0; i < n; ++i) { if (i == 1) continue; yield i * 2 } }
+    class L { *it(p) { const d = p * 2
+        yield { v: d, w: [d, d + 1] }; } }
+    var out = [];
+    for (const x of g(4)) out.push(x);
+    for (const {v, w: [a, b]} of new L().it(3)) out.push(v, a, b);
+    var it = g(1), n1 = it.next(), n2 = it.next();
+    out.push(n1.value, n1.done, n2.done);
+    let [p, q = 9, ...rest] = [1, undefined, 3, 4];
+    const {a, b: {c}, ...others} = {a: 1, b: {c: 2}, d: 3, e: 4};
+    out.push(p, q, rest.length, a + c, Object.keys(others).join());
+    var fs = []; for (let i = 0; i < 3; ++i) fs.push(() => i); out.push(fs.map(f => f()).join());
+    var gs = []; for (var j = 0; j < 3; ++j) gs.push(() => j); out.push(gs.map(f => f()).join());
+    function sw(x) { switch (x) { case 1: return 'one'; case 2: case 3: x = 'few'; break; default: x = 'many'; } return x; }
+    out.push(sw(1), sw(3), sw(9));
+    function tc() { try { throw "boom"; } catch (e) { return e + '!'; } finally { out.push('fin'); } }
+    out.push(tc());
+    function dflt(a, b = a + 1, ...c) { return a + b + c.length; } out.push(dflt(1), dflt(1, 5, 0, 0));
+    function hoist() { return inner(); function inner() { return typeof v + (v = 1); var v; } } out.push(hoist());
+    out.push((function () { return arguments.length; })(1, 2, 3));
+    var o = { n: 2, m() { return [1, 2].map(x => x * this.n).join(); } }; out.push(o.m());
+    var i = 0, k = (i++, i++, i); out.push(k, i++ + ++i);
+    out.push(new Function('a', 'b', 'return a * b')(3, 4), new Function('return this === window')());
+    var pr = []; Promise.resolve(1).then(x => { pr.push(x); return Promise.resolve(x + 1); }).then(x => pr.push(x)); pr.push(0);
+    """
+    assert js(src, "out") == [0, 4, 6, 6, 6, 7, 0, False, True, 1, 9, 2, 3, "d,e", "0,1,2", "3,3,3", "one", "few", "many", "fin", "boom!",
+                              3, 8, "undefined1", 3, "2,4", 2, 6, 12, True]
+    assert js(src, "pr") == [0, 1, 2]
+
+
+def test_asi_and_syntax_errors_are_reported():
+    assert js("var a = 1\nvar b = 2\nvar c = a\n+ b", "c") == 3
+    assert js("function f() { return\n5 }", "f()") is None
+    from oracle.jsvm.parser import JSSyntaxError
+    with pytest.raises(JSSyntaxError):
+        VM().run("var = 3;")
+
+
+def test_uncaught_throw_reaches_the_host_and_type_errors_are_js_errors():
+    vm = VM()
+    with pytest.raises(JSThrow) as e:
+        vm.run("throw 'Geometry subclass has not implemented intersect';")
+    assert e.value.value == "Geometry subclass has not implemented intersect"
+    assert js("var m; try { null.x } catch (e) { m = e instanceof TypeError }", "m") is True
+    assert js("var m; try { undefinedFn() } catch (e) { m = e instanceof ReferenceError }", "m") is True
+    with pytest.raises(RuntimeError):      # Math.random without a host generator is a host error, never silently 0
+        vm2 = VM()
+        vm2.run("Math.random()")
