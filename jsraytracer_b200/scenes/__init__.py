@@ -602,8 +602,9 @@ def AMultipleBVH(aspect=1, width=600, height=600, spp=1, depth=4, renderer_cls=S
     trans2 = (Mat4.translation([0.59, 0.58, -3.5]).times(Mat4.rotation(0.4, Vec.of(0, 1, 0)))
               .times(Mat4.rotation(1.5, Vec.of(1, 0, 0))).times(Mat4.scale(0.3)))
     default = PhongMaterial(Vec.of(1, 0.7, 0.7), 0.1, 0.4, 0.6, 100, 0.4)
-    objects += [BVHAggregate.build(load_mesh("hollow_tetrahedron", default), trans1),
-                BVHAggregate.build(load_mesh("star", default), trans2)]
+    shared = Mat4.identity()     # loadObjFiles evaluates its `transform=Mat4.identity()` default once for both files (src/objloader.js:249)
+    objects += [BVHAggregate.build(load_mesh("hollow_tetrahedron", default, shared), trans1),
+                BVHAggregate.build(load_mesh("star", default, shared), trans2)]
     return _finish(objects, lights, camera, renderer_cls, spp, depth, width, height)
 
 
