@@ -6,7 +6,7 @@ Only scenes without random decisions can be compared image to image (the device 
 generators).  The images are small (the interpreter is slow), so the bar is per pixel rather than a PSNR: the device
 works in FP32 where the reference has f64 scalars on f32 vectors, which may flip a pixel on a silhouette or a
 checkerboard edge; away from those the colours agree to 2e-3.  Scenes documented as ill-conditioned in
-tests/test_gpu_parity.py (chains of mirror or lens bounces) get the wider allowance written next to them."""
+tests/test_gpu_parity.py (chains of mirror bounces, rays along the horizon) get the allowance written next to them."""
 import glob
 import json
 import os
@@ -25,14 +25,18 @@ def _deterministic():
     for p in sorted(glob.glob(os.path.join(GOLDEN, "refjs_*.npz"))):
         z = np.load(p)
         meta = json.loads(str(z["meta"]))
-        if meta["renderer"] == "SimpleRenderer" or "simple_mean" in z.files:
+        # (tests/heart renders an area light through SimpleRenderer: random, so not comparable image to image)
+        if "simple_mean" in z.files or (meta["renderer"] == "SimpleRenderer" and int(z["draws"].max()) == 0):
             out.append((meta["name"], p))
     return out
 
 
 DET = _deterministic()
-# pixels (of 240 - 384) allowed to differ by more than 2e-3
-ALLOW = {"SDF_SphereRepetition": 40, "refraction": 12, "refraction_simple": 8, "diamond": 12, "SDF_RecursiveUnionTest": 10 ** 6}
+# pixels (of 240 - 384) allowed to differ by more than 2e-3.  Measured on a B200 (profiles/r2_refjs_cuda_vs_reference.jsonl,
+# tools/gpu_refjs_report.py): 14 of the 19 scenes agree to 2e-5 everywhere (118 - 160 dB); ASimpleScene and Aggregates differ on
+# 4 pixels of image row H/2, where the camera ray is exactly horizontal and meets the checkerboard plane at the horizon;
+# SDF_Menger on 1; SDF_SphereRepetition (the mirror lattice) on 11.
+ALLOW = {"SDF_SphereRepetition": 40, "ASimpleScene": 8, "Aggregates": 8}
 
 
 @pytest.mark.parametrize("name,path", DET, ids=[d[0] for d in DET])
