@@ -1,8 +1,6 @@
 // TEST INFRASTRUCTURE — CPU restatement oracle (see oracle_math.h header).
-// PARITY PARTLY PINNED: the reference has no machine-checked tests; the one output of the reference
-// itself whose scene file still matches (its tests/tie_fighter screenshots) is matched to <= 2 grey
-// levels on 304 000 comparable pixels (tests/test_reference_screenshot.py); everything else is pinned
-// only by formula-level KATs.
+// PARITY PINNED TO THE REFERENCE ITSELF (see oracle_math.h): bit-identical to runs of the reference's own sources
+// (oracle/jsvm) on 29 of its demo scenes — tests/test_refjs_pin.py.
 //
 // Restates, function by function, the reference's CPU render path:
 //   src/renderers.js  src/cameras.js  src/world.js  src/aggregates.js

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE — ctypes wrapper of the CPU restatement oracle
 (oracle/oracle.cpp).  Import only from tests/, __graft_entry__.smoke() and
-bench.py's cpu_baseline / --impl reference legs.  PARITY PARTLY PINNED (see
-oracle_math.h)."""
+bench.py's cpu_baseline / --impl reference legs.  PARITY PINNED to runs of the reference's own sources (see
+oracle_math.h, tests/test_refjs_pin.py)."""
 from __future__ import annotations
 
 import ctypes as C

@@ -1,15 +1,14 @@
 // TEST INFRASTRUCTURE — CPU restatement oracle of alitteneker/jsraytracer's
 // render path.  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may use anything under oracle/.
-// PARITY PARTLY PINNED: the reference ships no golden vectors or assertions for
-// this path and no JavaScript engine exists in this image,
-// so this restatement cannot be checked against the reference running.  It is
-// pinned by (i) the reference's own committed screenshots of tests/tie_fighter
-// (camera, Plane, point-light Phong, BVH shadow rays, resolve: bit-identical on
-// 95 % and within 2 levels on 100 % of the 304 000 comparable pixels —
-// tests/test_reference_screenshot.py) and (ii) formula-level known-answer tests
-// (tests/test_oracle_kat.py).  SDF, path-tracing scatter, Fresnel, DOF and
-// area-light sampling have no reference output to compare with: UNPINNED.
+// PARITY PINNED TO THE REFERENCE ITSELF: the reference ships no golden vectors and the image has
+// no JavaScript engine, so the repo brings one (oracle/jsvm) that executes the reference's unmodified src/*.js and
+// tests/*/test.mjs; this restatement reproduces those runs BIT FOR BIT — every f32 colour, every ImageData byte — on 29
+// of the reference's demo scenes (analytic, BVH meshes with vertex normals, SDF, Fresnel, path tracing, area lights,
+// depth of field): tests/test_refjs_pin.py, fixtures tests/golden/refjs_*.npz, generator oracle/refjs_golden.py.
+// Also pinned by the reference's committed tests/tie_fighter screenshots (tests/test_reference_screenshot.py) and by
+// formula-level known-answer tests (tests/test_oracle_kat.py).  Outside the pin: textures, and dragon / x-wing /
+// starwars (too large for the interpreter; same code paths).  Caveat: sin / cos / pow are glibc's on both sides.
 //
 // Numeric model (reference src/math.js:160 `class Vec extends Float32Array`,
 // :303 `class Mat extends Array`): vectors are f32 storage, every scalar and
