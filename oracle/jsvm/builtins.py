@@ -8,7 +8,7 @@ import re
 import sys
 import time
 
-from .runtime import (UNDEF, JSThrow, JSObject, JSArray, JSTypedArray, JSFunction, NativeFunction, BoundFunction,
+from .runtime import (UNDEF, JSThrow, JSObject, JSArray, JSTypedArray, JSArrayBuffer, JSFunction, NativeFunction, BoundFunction,
                       TYPED_KINDS, typeof, truthy, num_to_str, str_to_num, to_precision, to_fixed, to_int32)
 
 
@@ -725,6 +725,16 @@ def install(vm):
                 if a0 != int(a0) or a0 < 0:
                     vm.throw('RangeError', 'invalid typed array length')
                 return JSTypedArray(p, kind, int(a0))
+            if a0.__class__ is JSArrayBuffer:
+                raw = a0.owner.items.tobytes()
+                size = TYPED_KINDS[kind][1]
+                off = 0 if arg(args, 1) is UNDEF else int(tonum(args[1]))
+                n = (len(raw) - off) // size if arg(args, 2) is UNDEF else int(tonum(args[2]))
+                if off % size or off + n * size > len(raw) or n < 0:
+                    vm.throw('RangeError', 'invalid typed array offset / length')
+                t = JSTypedArray(p, kind, 0)
+                t.items.frombytes(raw[off:off + n * size])
+                return t
             if isinstance(a0, JSObject):
                 if a0.__class__ in (JSArray, JSTypedArray) or hasattr(a0, 'py_iter') or hasattr(a0, 'pygen'):
                     vals = list(vm.iterate(a0))
@@ -771,6 +781,14 @@ def install(vm):
 
     for kind in TYPED_KINDS:
         make_typed(kind)
+
+    ArrayBufferProto = JSObject(ObjectProto)
+
+    def array_buffer_ctor(args, nt):
+        b = JSArrayBuffer(proto_of(nt, ArrayBufferProto))
+        b.owner = JSTypedArray(G['Uint8Array'].props['prototype'], 'Uint8Array', int(tonum(arg(args, 0))))
+        return b
+    make_ctor('ArrayBuffer', ArrayBufferProto, lambda this, a: vm.throw('TypeError', "constructor ArrayBuffer requires 'new'"), array_buffer_ctor)
 
     # ------------------------------------------------------------------------------------------
     # String / Number / Boolean

@@ -11,7 +11,7 @@ import math
 import sys
 
 from .parser import parse, Parser
-from .runtime import (UNDEF, JSThrow, JSObject, JSArray, JSTypedArray, JSFunction, NativeFunction, BoundFunction, Scope,
+from .runtime import (UNDEF, JSThrow, JSObject, JSArray, JSTypedArray, JSArrayBuffer, JSFunction, NativeFunction, BoundFunction, Scope,
                       typeof, truthy, num_to_str, str_to_num, to_int32, to_uint32)
 
 sys.setrecursionlimit(max(sys.getrecursionlimit(), 12000))
@@ -220,7 +220,18 @@ class VM:
             if v is not _MISSING:
                 return v
             o = o.proto
-        # computed on demand: function name / length, Map / Set size
+        # computed on demand: typed-array buffer properties, function name / length, Map / Set size
+        if c is JSTypedArray:
+            if k == 'buffer':
+                b = JSArrayBuffer(self.ObjectProto)
+                b.owner = o0
+                return b
+            if k == 'byteOffset':
+                return 0.0
+            if k == 'byteLength':
+                return float(len(o0.items) * o0.items.itemsize)
+        elif c is JSArrayBuffer and k == 'byteLength':
+            return float(len(o0.owner.items) * o0.owner.items.itemsize)
         if k == 'size' and hasattr(o0, 'data'):
             return float(len(o0.data))
         if (k == 'name' or k == 'length') and c in (JSFunction, NativeFunction, BoundFunction):

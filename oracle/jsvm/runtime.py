@@ -122,6 +122,13 @@ class JSTypedArray(JSObject):
         return (i - self.lo) % self.span + self.lo
 
 
+class JSArrayBuffer(JSObject):
+    """`typedArray.buffer` / `new ArrayBuffer(n)`: the bytes of one owning typed array.  A view constructed over it
+    (`new Uint8Array(buffer, offset, length)`) is a COPY of those bytes — enough for reading, which is all the code run
+    here does with such views."""
+    __slots__ = ('owner',)
+
+
 class JSFunction(JSObject):
     __slots__ = ('name', 'env', 'pnames', 'binder', 'body', 'is_arrow', 'is_gen', 'expr_body', 'home', 'is_class',
                  'parent', 'ctor', 'fields', 'uses_args', 'nparams', 'vm', 'var_names', 'is_derived')

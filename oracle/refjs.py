@@ -60,6 +60,16 @@ _PRELUDE = r"""
 class ImageData {
     constructor(width, height) { this.width = width; this.height = height; this.data = new Uint8ClampedArray(4 * width * height); }
 }
+class OffscreenCanvas {          // src/materials.js:91-96 draws a bitmap and reads the pixels back
+    constructor(width, height) { this.width = width; this.height = height; }
+    getContext(kind) {
+        const canvas = this;
+        return {
+            drawImage(bitmap, x, y) { canvas._bitmap = bitmap; },
+            getImageData(x, y, w, h) { const img = new ImageData(w, h); img.data.set(__decodeImage(canvas._bitmap)); return img; }
+        };
+    }
+}
 class __TapBuffer extends PixelBuffer {
     setColor(x, y, color) {
         const r = super.setColor(x, y, color);
@@ -84,6 +94,8 @@ class RefJS:
         G = vm.root.vars
         G["fetch"] = vm.native("fetch", self._fetch)
         G["__sampleDone"] = vm.native("__sampleDone", self._sample_done)
+        G["createImageBitmap"] = vm.native("createImageBitmap", self._create_image_bitmap)
+        G["__decodeImage"] = vm.native("__decodeImage", self._decode_image)
         for f in SOURCES:
             with open(os.path.join(root, "src", f)) as fh:
                 vm.run(fh.read(), f)
@@ -113,7 +125,34 @@ class RefJS:
             with open(path, encoding="utf8", errors="replace") as fh:
                 return vm.promise_resolve(fh.read())
         resp.props["text"] = vm.native("text", text)
+
+        def blob(this_, a):
+            b = JSObject(vm.ObjectProto)
+            b.props["__path"] = path
+            return vm.promise_resolve(b)
+        resp.props["blob"] = vm.native("blob", blob)
         return vm.promise_resolve(resp)
+
+    def _create_image_bitmap(self, this, args):
+        """the browser's image decoder: PIL here (a JPEG decoded by another library may differ by a grey level; both sides
+        of every comparison get the pixels from this one decode, through the reference's ImageData)"""
+        from PIL import Image
+        vm = self.vm
+        path = vm.get(args[0], "__path")
+        with Image.open(path) as im:
+            w, h = im.size
+        bm = JSObject(vm.ObjectProto)
+        bm.props.update({"width": float(w), "height": float(h), "__path": path})
+        return vm.promise_resolve(bm)
+
+    def _decode_image(self, this, args):
+        from PIL import Image
+        vm = self.vm
+        with Image.open(vm.get(args[0], "__path")) as im:
+            rgba = np.asarray(im.convert("RGBA"), dtype=np.uint8).reshape(-1)
+        t = JSTypedArray(vm.root.vars["Uint8ClampedArray"].props["prototype"], "Uint8ClampedArray", 0)
+        t.items.frombytes(rgba.tobytes())
+        return t
 
     def _require(self, this, args):
         self.vm.throw("Error", "Cannot find module '%s'" % self.vm.tostr(args[0]))
@@ -152,12 +191,13 @@ class RefJS:
 
     def scene_json(self, width=None, height=None, triangle_fix=True):
         """the reference's own wire format of the configured test: `new Serializer(test)`, tests/test_to_json.js:30.
-        triangle_fix: install js/cuda_renderer.js's `installTriangleSerializeFix()` first, as CUDARenderer does — without
-        it the reference's serializer drops the vertex normals its own worker path shades with."""
+        triangle_fix: install js/cuda_renderer.js's `installTriangleSerializeFix()` and `installTextureSerializeFix()`
+        first, as CUDARenderer does — without them the reference's serializer drops the vertex normals its own worker
+        path shades with, and writes a texture's pixels as nothing (a browser ImageData has no own enumerable keys)."""
         if width is not None:
             self.vm.run("__test.width = %d; __test.height = %d;" % (width, height))
         if triangle_fix:
-            self.vm.run("installTriangleSerializeFix();")
+            self.vm.run("installTriangleSerializeFix(); installTextureSerializeFix();")
         return self.vm.eval_expr("JSON.stringify(new Serializer(__test).plain())")
 
     def render_simple(self, width, height):

@@ -29,8 +29,8 @@ GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 # (scene of /root/reference/tests, width, height, passes).  Sizes are small because the interpreter is ~1000x slower than
 # V8; widths differ from heights so that a transposed image cannot pass.  Not covered: dragon / dragon_json / x-wing /
-# starwars (100 000+ triangles: hours in the interpreter), toledo* (asset missing from the reference tree), bottle
-# (needs createImageBitmap to decode a PNG texture).
+# starwars (19 000 - 100 000 triangles: an hour to many hours in the interpreter), toledo* (asset missing from the
+# reference tree).
 TABLE = [
     ("BoxBall", 24, 16, 2), ("BoxBall_DOF", 24, 16, 2), ("BoxBall_path", 20, 12, 1), ("ASimpleScene", 24, 16, 2),
     ("Aggregates", 24, 16, 1), ("AHollowTetrahedron", 24, 16, 1), ("AMultipleBVH", 24, 16, 1),
@@ -40,7 +40,7 @@ TABLE = [
     ("SDF_Simple", 20, 12, 2), ("SDF_BoxBall", 20, 12, 2), ("SDF_Combinations", 20, 12, 1), ("SDF_Menger", 20, 12, 2),
     ("SDF_Sierpinski", 20, 12, 2), ("SDF_SphereRepetition", 20, 12, 1), ("SDF_RecursiveUnionTest", 16, 10, 1),
     ("diamond", 24, 16, 1), ("heart", 24, 16, 1), ("cat", 24, 16, 1), ("utah_teapot", 20, 12, 1),
-    ("bunny", 24, 16, 1), ("bunny_path", 24, 16, 2), ("tie_fighter", 20, 12, 1),
+    ("bunny", 24, 16, 1), ("bunny_path", 24, 16, 2), ("tie_fighter", 20, 12, 1), ("bottle", 24, 16, 1),
 ]
 
 

@@ -51,6 +51,8 @@ def _diff(a, b, path, out):
         else:
             for i, (x, y) in enumerate(zip(a, b)):
                 _diff(x, y, path + "/%d" % i, out)
+    elif (a, b) == ("ImageDataWire", "ImageData") and path.endswith("/_imgdata/_t/0"):
+        pass        # the serialising stand-in of a texture's pixels: its class name in js/cuda_renderer.js vs in the mirror (readers ignore it)
     elif a != b:
         out.append((path, a, b))
 
