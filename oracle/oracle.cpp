@@ -1085,6 +1085,7 @@ int orc_primary_hits(void* h, int W, int H, int32_t* prim_id, double* tout, int 
 // [first_pass, first_pass+n_passes): `sum` (W*H*3 f32, row-major) is the
 // reference's `buffer[px][py]` and is accumulated in f32 like `Vec.plus`.
 // flags bit0: no pixel jitter (SimpleRenderer sampling, :21-25).  bit1: tape mode (see Ctx).
+// bit2: RandomMultisamplingRenderer (:47-63) — `sum` then holds each pixel's colour, not a sum over passes.
 // counters[22]: rays[3], bvh_nodes[3], bvh_prims[3], top_tests[3], sdf_evals[3], shaded_hits, wide4[3], wide8[3]
 int orc_render(void* h, int W, int H, int first_pass, int n_passes, uint64_t seed, int flags, int x_offset, int x_delt,
                float* sum, int nthreads, uint64_t* counters) {
@@ -1102,6 +1103,25 @@ int orc_render(void* h, int W, int H, int first_pass, int n_passes, uint64_t see
                 const uint32_t pixel = (uint32_t)(py * W + px);
                 const double x = 2 * ((double)px / W) - 1, y = -2 * ((double)py / H) + 1;
                 float* acc = sum + (size_t)pixel * 3;
+                if (flags & 4) {
+                    // RandomMultisamplingRenderer.getPixelColor (src/renderers.js:52-62): all samples of a pixel inside one call —
+                    // `color = color.plus(world.color(...).times(1 / spp))`, every Vec op storing f32 — then ONE setColor; in tape
+                    // mode the pixel's samples share one stream, the way consecutive Math.random() calls do.  `sum` receives the
+                    // pixel's colour itself.
+                    if (flags & 2) { ctx.tape = true; ctx.tape_state = rng_tape_seed(seed, pixel, (uint32_t)first_pass); }
+                    float col[3] = {0, 0, 0};
+                    const double inv = 1.0 / n_passes;
+                    for (int iter = first_pass; iter < first_pass + n_passes; ++iter) {
+                        ctx.sample_key = rng_sample_key(seed, pixel, (uint32_t)iter);
+                        const double jx = ctx.u(1, DIM_JITTER_X), jy = ctx.u(1, DIM_JITTER_Y);
+                        const double sx = x + pixel_width * (jx - 0.5), sy = y + pixel_height * (jy - 0.5);
+                        ctx.rc = RC_PRIMARY;
+                        const Vec color = s->world.color(s->camera.getRayForPixel(sx, sy, ctx), s->maxRecursionDepth, 0, 1, ctx);
+                        for (int k = 0; k < 3; ++k) col[k] = (float)((double)col[k] + (double)(float)(color.at(k) * inv));
+                    }
+                    for (int k = 0; k < 3; ++k) acc[k] = col[k];
+                    continue;
+                }
                 for (int iter = first_pass; iter < first_pass + n_passes; ++iter) {
                     ctx.sample_key = rng_sample_key(seed, pixel, (uint32_t)iter);
                     if (flags & 2) { ctx.tape = true; ctx.tape_state = rng_tape_seed(seed, pixel, (uint32_t)iter); }

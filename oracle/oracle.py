@@ -99,15 +99,17 @@ class OracleScene:
         return ids.reshape(H, W), t.reshape(H, W), dict(zip(COUNTER_NAMES, cnt.tolist()))
 
     def render(self, n_passes, first_pass=0, seed=1, jitter=True, x_offset=0, x_delt=1, width=None, height=None,
-               threads=None, accum=None, tape=False):
+               threads=None, accum=None, tape=False, random_multisampling=False):
         """Returns (sum buffer (H,W,3) f32, counters dict).  tape: the random numbers of one pixel sample come from one
         sequential stream in call order (what Math.random() is to the reference) instead of the counter-based generator
-        the GPU shares — the mode the oracle is pinned to the reference's own output in (oracle/refjs.py)."""
+        the GPU shares — the mode the oracle is pinned to the reference's own output in (oracle/refjs.py).
+        random_multisampling: RandomMultisamplingRenderer (src/renderers.js:47-63): all n_passes samples of a pixel inside
+        one getPixelColor; the returned buffer then holds each pixel's colour itself."""
         W, H = width or self.width, height or self.height
         if accum is None:
             accum = np.zeros((H, W, 3), dtype=np.float32)
         cnt = np.zeros(22, dtype=np.uint64)
-        rc = self._L.orc_render(self._h, W, H, first_pass, n_passes, seed, (0 if jitter else 1) | (2 if tape else 0), x_offset, x_delt,
+        rc = self._L.orc_render(self._h, W, H, first_pass, n_passes, seed, (0 if jitter else 1) | (2 if tape else 0) | (4 if random_multisampling else 0), x_offset, x_delt,
                                 accum.ctypes.data, threads or default_threads(), cnt.ctypes.data)
         if rc:
             raise RuntimeError("oracle: " + self._L.orc_last_error().decode())

@@ -210,6 +210,16 @@ class RefJS:
         finally:
             self.vm.run("__test.renderer = __saved;")
 
+    def render_random(self, width, height, spp, seed=1):
+        """the same world and camera through the reference's `RandomMultisamplingRenderer` (src/renderers.js:47-63): all
+        samples of a pixel inside one getPixelColor, one setColor per pixel"""
+        self.vm.run("var __saved = __test.renderer;"
+                    "__test.renderer = new RandomMultisamplingRenderer(__saved.world, __saved.camera, %d, __saved.maxRecursionDepth);" % spp)
+        try:
+            return self.render(width, height, 1, seed=seed)
+        finally:
+            self.vm.run("__test.renderer = __saved;")
+
     def render(self, width, height, passes=1, x_offset=0, x_delt=1, seed=1):
         """`test.renderer.render(new PixelBuffer(w, h), 1000, callback, workerIndex, workerCount)`, src/worker.js:26-32.
         Returns (mean (H,W,3) f32 — the colour handed to the last setColor of each pixel, rgba8 (H,W,4) u8, draws per

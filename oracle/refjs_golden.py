@@ -9,6 +9,7 @@ Runs only where /root/reference exists (this container).  Each fixture holds
     mean    (H, W, 3) f32: the colour the reference's render loop hands to PixelBuffer.setColor after the last pass
     rgba8   (H, W, 4) u8:  the ImageData the reference filled
     draws   (H, W) i32:    Math.random() calls of each pixel's last sample
+    random_mean / random_rgba8 / random_spp   (two scenes) the same world through the reference's RandomMultisamplingRenderer
     simple_mean / simple_rgba8   (scenes whose only random numbers are the pixel jitter) the same world and camera through
             the reference's un-jittered SimpleRenderer: a deterministic image the CUDA path is compared with directly
     meta    name, width, height, passes, seed, renderer class, depth, seconds, sha256 of the sources that ran
@@ -44,6 +45,10 @@ TABLE = [
 ]
 
 
+# scenes also rendered through the reference's RandomMultisamplingRenderer (no test.mjs uses it; same world and camera), spp
+RANDOM_RENDERER = {"BoxBall_DOF": 3, "cornell_box_emissive": 2}
+
+
 def sources_digest(root, name):
     from .refjs import SOURCES
     h = hashlib.sha256()
@@ -66,6 +71,9 @@ def make(name, W, H, passes, seed=1):
         smean, srgba, sdraws = r.render_simple(W, H)
         assert sdraws.max() == 0
         extra = dict(simple_mean=smean, simple_rgba8=srgba)
+    if name in RANDOM_RENDERER:
+        rmean, rrgba, _ = r.render_random(W, H, RANDOM_RENDERER[name], seed=seed)
+        extra.update(random_mean=rmean, random_rgba8=rrgba, random_spp=np.array(RANDOM_RENDERER[name]))
     meta = dict(name=name, width=W, height=H, passes=passes if info["renderer"] != "SimpleRenderer" else 1, seed=seed,
                 renderer=info["renderer"], depth=info["maxRecursionDepth"], ref_width=info["width"], ref_height=info["height"],
                 ref_spp=info["samplesPerPixel"], load_s=round(t1 - t0, 1), render_s=round(time.time() - t1, 1),

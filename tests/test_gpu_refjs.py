@@ -82,3 +82,20 @@ def test_primary_hits_agree_with_reference_rays_on_stochastic_scenes():
         ids, t = sc.primary_hits()
         oids, ot, _ = OracleScene(js.decode("utf8")).primary_hits()
         assert int((ids != oids).sum()) <= 2, meta["name"]
+
+
+def test_random_multisampling_renderer_is_the_incremental_mean():
+    """the product renders a RandomMultisamplingRenderer (src/renderers.js:47-63) as incremental passes — the
+    same samples, summed then divided instead of divided then summed.  The oracle's restatement of that renderer (pinned to
+    the reference's own, tests/test_refjs_pin.py) and the CUDA passes agree like any same-RNG pair."""
+    from conftest import psnr, scene_blobs
+    from jsraytracer_b200 import lib
+    from oracle.oracle import OracleScene
+    js, mp = scene_blobs("BoxBall_DOF", width=128, height=96)
+    sc = lib.Scene(mp, lib.FORMAT_MSGPACK, device=0)
+    sc.render(0, 4, seed=3)
+    acc, passes = sc.read_accum()
+    col, _ = OracleScene(js).render(4, seed=3, random_multisampling=True)
+    assert passes == 4
+    g, o = np.clip(acc[..., :3] / 4, 0, 1), np.clip(col, 0, 1)
+    assert psnr(g, o) >= 50.0, "PSNR %.2f dB" % psnr(g, o)

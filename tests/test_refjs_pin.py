@@ -65,6 +65,13 @@ def test_oracle_equals_reference_output(path):
     assert not bad.any(), "%d of %d pixels differ from the reference's own output (max |d| %.3e)" % (
         int(bad.any(-1).sum()), ref.shape[0] * ref.shape[1], float(np.nanmax(np.abs(mean.astype(np.float64) - ref))))
     assert np.array_equal(resolve_rgba8(acc, n), z["rgba8"]), "8-bit image differs from the reference's ImageData"
+    if "random_mean" in z.files:       # the same world through the reference's RandomMultisamplingRenderer (src/renderers.js:47-63)
+        from oracle.oracle import OracleScene
+        spp = int(z["random_spp"])
+        col, _ = OracleScene(js).render(spp, seed=meta["seed"], width=meta["width"], height=meta["height"], threads=1, tape=True,
+                                        random_multisampling=True)
+        assert _same(col, z["random_mean"])
+        assert np.array_equal(resolve_rgba8(col, 1), z["random_rgba8"])
     if "simple_mean" in z.files:       # the same world through the reference's SimpleRenderer (no jitter)
         sacc, smean, _ = _oracle_mean(js, meta, simple=True)
         assert _same(smean, z["simple_mean"])
@@ -85,6 +92,10 @@ def test_fixtures_exercise_random_decisions():
     assert draws["bunny_path"][1] >= 10
 
 
+def test_random_renderer_fixtures_exist():
+    assert sum("random_mean" in np.load(p).files for p in FIXTURES) >= 2
+
+
 def test_live_reference_run_matches_oracle():
     """where the reference tree is present (the build container): run it now, not from a fixture"""
     from oracle import refjs
@@ -100,6 +111,11 @@ def test_live_reference_run_matches_oracle():
     acc, _ = OracleScene(js).render(P, seed=7, width=W, height=H, threads=1, tape=True)
     assert _same((acc.astype(np.float64) * (1.0 / P)).astype(np.float32), mean)
     assert np.array_equal(resolve_rgba8(acc, P), rgba)
+    # one worker of three: columns 1, 4, 7 (src/worker.js:30-32 -> render(img, ..., workerIndex, workerCount))
+    mean2, rgba2, _ = r.render(W, H, P, x_offset=1, x_delt=3, seed=7)
+    acc2, _ = OracleScene(js).render(P, seed=7, width=W, height=H, threads=1, tape=True, x_offset=1, x_delt=3)
+    assert _same((acc2.astype(np.float64) * (1.0 / P)).astype(np.float32), mean2)
+    assert np.array_equal(mean2[:, 1::3], mean[:, 1::3]) and not mean2[:, 0::3].any() and not rgba2[:, 0::3].any()
 
 
 def test_fixtures_are_current():
