@@ -246,7 +246,7 @@ class VM:
         c = o.__class__
         if c is JSArray or c is JSTypedArray:
             if k.__class__ is float:
-                return k == int(k) and 0 <= k < len(o.items) and (c is JSTypedArray or o.items[int(k)] is not _HOLE)
+                return k == int(k) and 0 <= k < len(o.items)
             if k == 'length':
                 return True
             if k.__class__ is str and k.isdigit():
@@ -776,9 +776,6 @@ class VM:
                         seen.add(k)
                         keys.append(k)
                 p = p.proto if isinstance(p, JSObject) else None
-                if p is self.ObjectProto or p is self.ArrayProto:
-                    # built-in prototypes hold only non-enumerable members, except what scripts add (math.js:1-25)
-                    pass
             for k in keys:
                 s = Scope(env) if fresh else env
                 bind(s, k)
@@ -1176,7 +1173,6 @@ class VM:
         plain = not is_arrow and not is_method and not is_gen
         sloppy_this = plain and not strict
         nparams = float(len([p for p in params if p[0] == 'id']))
-        gobj = None
 
         if sloppy_this:
             # sloppy-mode functions see the global object as `this` when called without a receiver
@@ -1219,8 +1215,8 @@ class VM:
                 po.props['constructor'] = f
                 po.hidden = {'constructor'}
                 f.props['prototype'] = po
-            if name and not fctx is None and node[0] == 'function' and not is_method and not is_arrow and name_hint is None:
-                # named function expression: its own name is visible inside
+            if name and not is_method and not is_arrow:
+                # a named function (expression or declaration) sees its own name
                 s = Scope(env)
                 s.vars[name] = f
                 f.env = s
@@ -2034,9 +2030,6 @@ class VM:
 
     def host_import(self, spec):
         self.throw('Error', 'dynamic import is not available: ' + self.tostr(spec))
-
-
-_HOLE = object()
 
 
 def _array_iter(arr):

@@ -29,19 +29,21 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 # (scene of /root/reference/tests, width, height, passes).  Sizes are small because the interpreter is ~1000x slower than
-# V8; widths differ from heights so that a transposed image cannot pass.  Not covered: dragon / dragon_json / x-wing /
+# V8; widths differ from heights so that a transposed image cannot pass; heights are odd where possible so that no image
+# row has camera rays that are exactly horizontal (they meet the ground planes at the horizon: ill-conditioned for any
+# implementation that is compared with a tolerance, like the FP32 device path).  Not covered: dragon / dragon_json / x-wing /
 # starwars (19 000 - 100 000 triangles: an hour to many hours in the interpreter), toledo* (asset missing from the
 # reference tree).
 TABLE = [
-    ("BoxBall", 24, 16, 2), ("BoxBall_DOF", 24, 16, 2), ("BoxBall_path", 20, 12, 1), ("ASimpleScene", 24, 16, 2),
-    ("Aggregates", 24, 16, 1), ("AHollowTetrahedron", 24, 16, 1), ("AMultipleBVH", 24, 16, 1),
-    ("refraction", 24, 16, 2), ("refraction_simple", 24, 16, 2), ("refraction_path", 20, 12, 2),
-    ("cornell_box", 20, 12, 2), ("cornell_box_emissive", 20, 12, 2), ("cornell_box_path", 24, 16, 2),
-    ("spheres010", 24, 16, 1), ("spheres050", 20, 12, 1),
-    ("SDF_Simple", 20, 12, 2), ("SDF_BoxBall", 20, 12, 2), ("SDF_Combinations", 20, 12, 1), ("SDF_Menger", 20, 12, 2),
-    ("SDF_Sierpinski", 20, 12, 2), ("SDF_SphereRepetition", 20, 12, 1), ("SDF_RecursiveUnionTest", 16, 10, 1),
-    ("diamond", 24, 16, 1), ("heart", 24, 16, 1), ("cat", 24, 16, 1), ("utah_teapot", 20, 12, 1),
-    ("bunny", 24, 16, 1), ("bunny_path", 24, 16, 2), ("tie_fighter", 20, 12, 1), ("bottle", 24, 16, 1),
+    ("BoxBall", 48, 31, 3), ("BoxBall_DOF", 48, 31, 3), ("BoxBall_path", 32, 21, 2), ("ASimpleScene", 40, 27, 2),
+    ("Aggregates", 40, 27, 2), ("AHollowTetrahedron", 48, 31, 1), ("AMultipleBVH", 48, 31, 1),
+    ("refraction", 32, 21, 2), ("refraction_simple", 40, 27, 2), ("refraction_path", 24, 15, 2),
+    ("cornell_box", 28, 19, 2), ("cornell_box_emissive", 28, 19, 2), ("cornell_box_path", 24, 16, 2),
+    ("spheres010", 40, 27, 1), ("spheres050", 24, 15, 1),
+    ("SDF_Simple", 40, 27, 2), ("SDF_BoxBall", 32, 21, 2), ("SDF_Combinations", 32, 21, 1), ("SDF_Menger", 20, 12, 2),
+    ("SDF_Sierpinski", 24, 15, 2), ("SDF_SphereRepetition", 24, 15, 1), ("SDF_RecursiveUnionTest", 16, 10, 1),
+    ("diamond", 40, 27, 1), ("heart", 48, 31, 1), ("cat", 48, 31, 1), ("utah_teapot", 32, 21, 1),
+    ("bunny", 48, 31, 1), ("bunny_path", 32, 21, 3), ("tie_fighter", 32, 21, 2), ("bottle", 48, 31, 1),
 ]
 
 
