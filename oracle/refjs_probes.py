@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE — writes tests/golden/refjs_probes.npz: single calls of the reference's own functions (run in
+"""TEST INFRASTRUCTURE — writes tests/golden/probes_refjs.npz: single calls of the reference's own functions (run in
 oracle/jsvm) on random arguments, denser than what a small image reaches:
 
     cast_<scene>      rays (N, 8: origin xyz, direction xyz, minDistance, maxDistance) + intersectTransparent flag ->
@@ -95,7 +95,7 @@ def main():
     if "fmod" not in arrays:
         a, b, out = fmod_probes(RefJS(), rng, 4000)
         arrays["fmod_a"], arrays["fmod_b"], arrays["fmod_out"] = a, b, out
-    np.savez_compressed(os.path.join(GOLDEN, "refjs_probes.npz"), meta=np.array(json.dumps(meta)), **arrays)
+    np.savez_compressed(os.path.join(GOLDEN, "probes_refjs.npz"), meta=np.array(json.dumps(meta)), **arrays)
     print({k: v.shape for k, v in arrays.items()})
 
 

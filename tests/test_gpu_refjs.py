@@ -32,11 +32,16 @@ def _deterministic():
 
 
 DET = _deterministic()
-# pixels (of 240 - 384) allowed to differ by more than 2e-3.  Measured on a B200 (profiles/r2_refjs_cuda_vs_reference.jsonl,
-# tools/gpu_refjs_report.py): 15 of the 20 scenes agree to 2e-5 everywhere (118 - 160 dB); ASimpleScene and Aggregates differ on
-# 4 pixels of image row H/2, where the camera ray is exactly horizontal and meets the checkerboard plane at the horizon;
-# SDF_Menger on 1; SDF_SphereRepetition (the mirror lattice) on 11.
-ALLOW = {"SDF_SphereRepetition": 40, "ASimpleScene": 8, "Aggregates": 8}
+# share of the pixels allowed to differ by more than 2e-3 (at least 3 pixels).  Measured on a B200 at 240 - 384 pixels per image
+# (profiles/r2_refjs_cuda_vs_reference.jsonl, tools/gpu_refjs_report.py): 15 of the 20 scenes agree to 2e-5 everywhere (118 - 160
+# dB); ASimpleScene and Aggregates differed on 4 pixels of the image row whose camera rays are exactly horizontal and meet the
+# checkerboard plane at the horizon (the fixtures have odd heights since, so that no such row exists); SDF_Menger on 1 of 240;
+# SDF_SphereRepetition — the mirror lattice, ill-conditioned in the reference itself (tests/test_gpu_parity.py) — on 11 of 240.
+ALLOW = {"SDF_SphereRepetition": 0.15, "ASimpleScene": 0.01, "Aggregates": 0.01}
+
+
+def _allowed(name, n_pixels):
+    return max(3, int(ALLOW.get(name, 0.005) * n_pixels))
 
 
 @pytest.mark.parametrize("name,path", DET, ids=[d[0] for d in DET])
@@ -57,12 +62,12 @@ def test_cuda_image_equals_reference_simple_renderer(name, path):
     g, r = np.clip(acc[..., :3], 0, 1), np.clip(ref, 0, 1)
     d = np.abs(g.astype(np.float64) - r).max(-1)
     n_bad = int((d > 2e-3).sum())
-    assert n_bad <= ALLOW.get(name, 3), "%d of %d pixels differ from the reference by more than 2e-3 (median %.2e)" % (
+    assert n_bad <= _allowed(name, d.size), "%d of %d pixels differ from the reference by more than 2e-3 (median %.2e)" % (
         n_bad, d.size, float(np.median(d)))
     assert float(np.median(d)) <= 2e-5
     img = sc.resolve_rgba8()
     d8 = np.abs(img.astype(int) - ref8.astype(int)).max(-1)
-    assert int((d8 > 1).sum()) <= ALLOW.get(name, 3), "8-bit image: %d pixels off by more than one grey level" % int((d8 > 1).sum())
+    assert int((d8 > 1).sum()) <= _allowed(name, d.size), "8-bit image: %d pixels off by more than one grey level" % int((d8 > 1).sum())
     assert np.all(img[..., 3] == 255)
 
 
@@ -81,7 +86,7 @@ def test_primary_hits_agree_with_reference_rays_on_stochastic_scenes():
         sc = lib.Scene(js, lib.FORMAT_JSON, device=0)
         ids, t = sc.primary_hits()
         oids, ot, _ = OracleScene(js.decode("utf8")).primary_hits()
-        assert int((ids != oids).sum()) <= 2, meta["name"]
+        assert int((ids != oids).sum()) <= max(2, ids.size // 500), meta["name"]
 
 
 def test_random_multisampling_renderer_is_the_incremental_mean():

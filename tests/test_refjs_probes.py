@@ -1,5 +1,5 @@
 """Single calls of the reference's own functions (run in oracle/jsvm; generator oracle/refjs_probes.py, fixture
-tests/golden/refjs_probes.npz) against the oracle's restatements, for equality: `World.cast` on random rays — closest hit
+tests/golden/probes_refjs.npz) against the oracle's restatements, for equality: `World.cast` on random rays — closest hit
 and shadow-ray windows, normalised and unnormalised directions — through analytic scenes, BVH meshes and SDF scenes;
 `root_sdf.distance` and the SDF normal at random points; `Math.fmod` on arguments that include exact decimal ties."""
 import json
@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-Z = np.load(os.path.join(GOLDEN, "refjs_probes.npz"))
+Z = np.load(os.path.join(GOLDEN, "probes_refjs.npz"))
 META = json.loads(str(Z["meta"]))
 CAST = sorted(k[5:-5] for k in Z.files if k.startswith("cast_") and k.endswith("_rays"))
 SDF = sorted(k[4:-2] for k in Z.files if k.startswith("sdf_") and k.endswith("_p"))

@@ -49,4 +49,7 @@ with open(out, "w") as f:
             "`tests/test_refjs_pin.py`.  `s`: seconds the interpreter took to configure (OBJ parse + `BVHAggregate.build`) + render.\n\n"
             "| scene | renderer | image x passes | triangles | BVH nodes | draws | rays | f32 / u8 | also | s |\n|---|---|---|---|---|---|---|---|---|---|\n")
     f.write("\n".join(rows) + "\n")
+    f.write("\nOne-off runs, not kept as fixtures because of their size (a 23 MB scene document): `tests/x-wing` (18 849 triangles, 10 minutes to\n"
+            "configure in the interpreter), 20x12 x 1 pass, 2-18 draws per sample: f32 colours and ImageData bytes equal the oracle's\n"
+            "(`profiles/r2_refjs_xwing_oneoff.log`, the output of `tools/refjs_compare.py x-wing 20 12 1`).\n")
 print(open(out).read())
