@@ -51,5 +51,7 @@ with open(out, "w") as f:
     f.write("\n".join(rows) + "\n")
     f.write("\nOne-off runs, not kept as fixtures because of their size (a 23 MB scene document): `tests/x-wing` (18 849 triangles, 10 minutes to\n"
             "configure in the interpreter), 20x12 x 1 pass, 2-18 draws per sample: f32 colours and ImageData bytes equal the oracle's\n"
-            "(`profiles/r2_refjs_xwing_oneoff.log`, the output of `tools/refjs_compare.py x-wing 20 12 1`).\n")
+            "(`profiles/r2_refjs_xwing_oneoff.log`, the output of `tools/refjs_compare.py x-wing 20 12 1`); `tests/starwars` (BASELINE's\n"
+            "stand-in for Toledo: x-wing + three tie fighters sharing one kd-tree, depth-of-field camera, three area lights + a point\n"
+            "light: 4-124 draws per sample), 20x12 x 1 pass: equal likewise (`profiles/r2_refjs_starwars_oneoff.log`).\n")
 print(open(out).read())
