@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
+#include <cstdio>
 #include "../../include/jsrt.h"
 #include "host_scene.h"
 #include "render.h"
@@ -50,8 +52,16 @@ int jsrt_device_count(void) { return deviceCount(); }
 jsrt_scene* jsrt_scene_create_host(const uint8_t* blob, size_t len, int format) {
     try {
         std::unique_ptr<jsrt_scene> s(new jsrt_scene);
+        const bool timing = getenv("JSRT_HOST_TIMING") != nullptr;     // diagnostics: where scene creation spends its time
+        const auto t0 = std::chrono::steady_clock::now();
         WireDoc doc(blob, len, format);
+        const auto t1 = std::chrono::steady_clock::now();
         flattenScene(doc, s->host);
+        if (timing) {
+            const auto t2 = std::chrono::steady_clock::now();
+            fprintf(stderr, "jsrt: scene blob %.1f MB: parse %.3f s, flatten %.3f s\n", len / 1e6,
+                    std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
+        }
         return s.release();
     } catch (const std::exception& e) { failWith(e); return nullptr; }
 }

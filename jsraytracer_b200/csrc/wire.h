@@ -16,11 +16,18 @@ struct Val {
     enum Type : uint8_t { NIL, BOOL, NUM, STR, ARR, MAP };
     Type type = NIL;
     bool b = false;
+    // MAP only, filled by WireDoc::indexGraph: which pair holds the serializer's `_t` / `_v` keys (the flattener asks for them
+    // tens of millions of times on a 100 000-triangle scene).  kKeyUnknown: not indexed, scan; kKeyAbsent: the map has no such key.
+    static constexpr uint8_t kKeyUnknown = 255, kKeyAbsent = 254;
+    uint8_t t_at = kKeyUnknown, v_at = kKeyUnknown;
     uint32_t count = 0;      // ARR: elements; MAP: pairs; STR: byte length
-    double num = 0;
-    uint64_t first = 0;      // ARR/MAP: arena index of the first child (MAP: key,value,key,value...)
-    const char* str = nullptr;
+    union {                  // by type: 16 bytes per value instead of 32 (a 100 000-triangle scene is ~50 M values)
+        double num = 0;      // NUM
+        uint64_t first;      // ARR/MAP: arena index of the first child (MAP: key,value,key,value...)
+        const char* str;     // STR: points into the caller's blob
+    };
 };
+static_assert(sizeof(Val) == 16, "Val is meant to stay two words");
 
 class WireDoc {
 public:
@@ -56,15 +63,19 @@ public:
 
 private:
     std::vector<Val> arena_;
+    std::vector<Val> scratch_;     // children of the containers being parsed (one shared stack instead of a vector per container)
     Val root_;
-    std::unordered_map<long long, const Val*> refs_;
+    std::vector<const Val*> ref_table_;                   // _r id -> defining object, for the dense ids the serializer writes
+    std::unordered_map<long long, const Val*> refs_;     // ... and for any other id
     std::vector<std::string> typenames_;
     std::string empty_;
 
     Val parseJson(const char*& p, const char* e, int depth);
     Val parseMsgpack(const uint8_t*& p, const uint8_t* e, int depth);
-    uint64_t commit(const std::vector<Val>& kids);
+    uint64_t commit(size_t scratch_start);
     void indexGraph();
+    const Val* tOf(const Val* map) const;      // value of the `_t` / `_v` key of a MAP (nullptr if absent), through the index
+    const Val* vOf(const Val* map) const;
 };
 
 [[noreturn]] inline void fail(const std::string& m) { throw std::runtime_error(m); }
