@@ -37,6 +37,10 @@ WORKLOAD = "tests/bunny_path 1920x1080 aspect 16/9 depth 4 (BASELINE configs[2];
 METRIC = "Mrays/s at 1080p on bunny_path"
 
 
+# what makes the "port" a fair stand-in for the reference's own CPU implementation
+PORT_PINNED = ("bit-identical (every f32 colour, every ImageData byte) to the reference's unmodified sources run in oracle/jsvm on 30 of its "
+               "demo scenes incl. bunny_path: tests/test_refjs_pin.py, profiles/r2_refjs_pin.md")
+
 def is_headline(args):
     return args.scene == "bunny_path" and args.width == 1920 and args.height == 1080
 
@@ -134,7 +138,8 @@ def run_reference(args):
         "config": common_config(args),
         "run": {"step": "1 full-frame pass per step (bounded sample of the workload)", "cuda_library_loaded": _lib._LIB is not None},
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                         "sample": "%d full-frame passes; C++ restatement of the reference's JS algorithm (no JS engine in this image)" % args.steps},
+                         "sample": "%d full-frame passes; C++ restatement of the reference's JS algorithm (the image has no JS engine; oracle/jsvm runs the reference ~1000x slower than V8 and is a checker, not a baseline)" % args.steps,
+                         "pinned": PORT_PINNED},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -299,7 +304,8 @@ def run_ours(args):
         cpasses = args.cpu_passes
         crays, cdt, threads, ocnt = cpu_reference_run(ser, args, cpasses)
         cpu = {"value": crays / cdt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-               "sample": "%d full-frame passes of the same workload on the C++ restatement oracle (%.1f s)" % (cpasses, cdt)}
+               "sample": "%d full-frame passes of the same workload on the C++ restatement oracle (%.1f s)" % (cpasses, cdt),
+               "pinned": PORT_PINNED}
     else:
         _, _, _, ocnt = cpu_reference_run(ser, args, 1)       # counts only (one pass, untimed leg)
 
