@@ -3,7 +3,7 @@
 // cpu_baseline / --impl reference legs may use anything under oracle/.
 // PARITY PINNED TO THE REFERENCE ITSELF: the reference ships no golden vectors and the image has
 // no JavaScript engine, so the repo brings one (oracle/jsvm) that executes the reference's unmodified src/*.js and
-// tests/*/test.mjs; this restatement reproduces those runs BIT FOR BIT — every f32 colour, every ImageData byte — on 30
+// tests/*/test.mjs; this restatement reproduces those runs BIT FOR BIT — every f32 colour, every ImageData byte — on 31
 // of the reference's demo scenes (analytic, BVH meshes with vertex normals, SDF, Fresnel, path tracing, area lights,
 // depth of field, textures): tests/test_refjs_pin.py, fixtures tests/golden/refjs_*.npz, generator oracle/refjs_golden.py.
 // Also pinned by the reference's committed tests/tie_fighter screenshots (tests/test_reference_screenshot.py) and by

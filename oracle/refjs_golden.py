@@ -39,7 +39,7 @@ TABLE = [
     ("Aggregates", 40, 27, 2), ("AHollowTetrahedron", 48, 31, 1), ("AMultipleBVH", 48, 31, 1),
     ("refraction", 32, 21, 2), ("refraction_simple", 40, 27, 2), ("refraction_path", 24, 15, 2),
     ("cornell_box", 28, 19, 2), ("cornell_box_emissive", 28, 19, 2), ("cornell_box_path", 24, 16, 2),
-    ("spheres010", 40, 27, 1), ("spheres050", 24, 15, 1),
+    ("spheres010", 40, 27, 1), ("spheres050", 24, 15, 1), ("spheres100", 20, 13, 1),
     ("SDF_Simple", 40, 27, 2), ("SDF_BoxBall", 32, 21, 2), ("SDF_Combinations", 32, 21, 1), ("SDF_Menger", 20, 12, 2),
     ("SDF_Sierpinski", 24, 15, 2), ("SDF_SphereRepetition", 24, 15, 1), ("SDF_RecursiveUnionTest", 16, 10, 1),
     ("diamond", 40, 27, 1), ("heart", 48, 31, 1), ("cat", 48, 31, 1), ("utah_teapot", 32, 21, 1),
