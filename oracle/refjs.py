@@ -80,6 +80,14 @@ class __TapBuffer extends PixelBuffer {
 """
 
 
+def test_dir(root, name):
+    """tests/<name> of the reference — or, for `extra_<x>`, a scene this repository wrote out of the reference's classes to
+    reach what none of the reference's own scenes uses (tests/golden/extra_scenes/<x>/test.mjs)"""
+    if name.startswith("extra_"):
+        return os.path.join(_REPO, "tests", "golden", "extra_scenes", name[6:])
+    return os.path.join(root, "tests", name)
+
+
 def available():
     return os.path.isdir(os.path.join(REF_ROOT, "src")) and os.path.isdir(os.path.join(REF_ROOT, "tests"))
 
@@ -166,7 +174,7 @@ class RefJS:
     def load_test(self, name, config_seed=12345):
         """`import(testName).then(module => module.configureTest(test => ...))`, src/worker.js:23-24"""
         vm = self.vm
-        self.cwd = os.path.join(self.root, "tests", name)
+        self.cwd = test_dir(self.root, name)
         self.tape.seed(config_seed)          # scenes that place objects with Math.random() (tests/spheres*) stay reproducible
         with open(os.path.join(self.cwd, "test.mjs")) as fh:
             vm.run(fh.read(), name + "/test.mjs")
