@@ -12,5 +12,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
 tools/gpu_ncu.sh "$tag" > gpurun_out/${tag}_gpu_ncu.log 2>&1
 tools/gpu_scene_table.sh "$tag" 2>&1 | tail -9
+python tools/gpu_refjs_report.py > gpurun_out/${tag}_refjs_cuda_vs_reference.jsonl 2>&1    # CUDA path vs the reference's own images
 cut -c1-400 gpurun_out/${tag}_bench_n1.json
 # afterwards, here:  ncu -i gpurun_out/prof_<tag>.ncu-rep --page raw --csv > x.csv && python tools/ncu_digest.py x.csv
