@@ -9,7 +9,7 @@ import sys
 import time
 
 from .runtime import (UNDEF, JSThrow, JSObject, JSArray, JSTypedArray, JSArrayBuffer, JSFunction, NativeFunction, BoundFunction,
-                      TYPED_KINDS, typeof, truthy, num_to_str, str_to_num, to_precision, to_fixed, to_int32)
+                      TYPED_KINDS, typeof, truthy, num_to_str, str_to_num, to_precision, to_fixed)
 
 
 class JSRegExp(JSObject):
@@ -80,9 +80,6 @@ def install(vm):
 
     def arg(args, i):
         return args[i] if i < len(args) else UNDEF
-
-    def new_proto(parent=ObjectProto):
-        return JSObject(parent)
 
     def make_ctor(name, proto, call_fn, ctor_fn, parent_ctor=None):
         c = native(name, call_fn, ctor_fn)

@@ -19,7 +19,7 @@ import os
 
 import numpy as np
 
-from .jsvm import VM, UNDEF, JSThrow, JSObject, JSArray, JSTypedArray
+from .jsvm import VM, UNDEF, JSObject, JSTypedArray
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_ROOT = os.environ.get("JSRT_REFERENCE_ROOT", "/root/reference")
