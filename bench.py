@@ -38,7 +38,7 @@ METRIC = "Mrays/s at 1080p on bunny_path"
 
 
 # what makes the "port" a fair stand-in for the reference's own CPU implementation
-PORT_PINNED = ("bit-identical (every f32 colour, every ImageData byte) to the reference's unmodified sources run in oracle/jsvm on 31 of its "
+PORT_PINNED = ("bit-identical (every f32 colour, every ImageData byte) to the reference's unmodified sources run in oracle/jsvm on 34 of its 37 "
                "demo scenes incl. bunny_path: tests/test_refjs_pin.py, profiles/r2_refjs_pin.md")
 
 def is_headline(args):

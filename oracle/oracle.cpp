@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE — CPU restatement oracle (see oracle_math.h header).
 // PARITY PINNED TO THE REFERENCE ITSELF (see oracle_math.h): bit-identical to runs of the reference's own sources
-// (oracle/jsvm) on 31 of its demo scenes — tests/test_refjs_pin.py.
+// (oracle/jsvm) on 34 of its 37 demo scenes (31 as fixtures) — tests/test_refjs_pin.py.
 //
 // Restates, function by function, the reference's CPU render path:
 //   src/renderers.js  src/cameras.js  src/world.js  src/aggregates.js

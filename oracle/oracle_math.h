@@ -3,12 +3,12 @@
 // cpu_baseline / --impl reference legs may use anything under oracle/.
 // PARITY PINNED TO THE REFERENCE ITSELF: the reference ships no golden vectors and the image has
 // no JavaScript engine, so the repo brings one (oracle/jsvm) that executes the reference's unmodified src/*.js and
-// tests/*/test.mjs; this restatement reproduces those runs BIT FOR BIT — every f32 colour, every ImageData byte — on 31
-// of the reference's demo scenes (analytic, BVH meshes with vertex normals, SDF, Fresnel, path tracing, area lights,
-// depth of field, textures): tests/test_refjs_pin.py, fixtures tests/golden/refjs_*.npz, generator oracle/refjs_golden.py.
+// tests/*/test.mjs; this restatement reproduces those runs BIT FOR BIT — every f32 colour, every ImageData byte — on 34
+// of the reference's 37 demo scenes, 31 as committed fixtures (analytic, BVH meshes with vertex normals, SDF, Fresnel, path
+// tracing, area lights, depth of field, textures): tests/test_refjs_pin.py, fixtures tests/golden/refjs_*.npz, generator oracle/refjs_golden.py.
 // Also pinned by the reference's committed tests/tie_fighter screenshots (tests/test_reference_screenshot.py) and by
-// formula-level known-answer tests (tests/test_oracle_kat.py).  Outside the pin: dragon / x-wing /
-// starwars (too large for the interpreter; same code paths).  Caveat: sin / cos / pow are glibc's on both sides.
+// formula-level known-answer tests (tests/test_oracle_kat.py).  Run once, too large to keep as fixtures: dragon / x-wing /
+// starwars (profiles/r2_refjs_*_oneoff.log); the three scenes left cannot run from the reference tree.  Caveat: sin / cos / pow are glibc's on both sides.
 //
 // Numeric model (reference src/math.js:160 `class Vec extends Float32Array`,
 // :303 `class Mat extends Array`): vectors are f32 storage, every scalar and

@@ -1,5 +1,5 @@
 // NOT a scene of the reference: written for this repository in the shape of the reference's tests/*/test.mjs, out of the
-// reference's own classes, to reach what none of its 39 demo scenes uses — TransparentMaterial, SolidColorMaterial,
+// reference's own classes, to reach what none of its 37 demo scenes uses — TransparentMaterial, SolidColorMaterial,
 // PositionalUVMaterial, RoundSDF, a Circle area light, TextureMaterialColor in "nearest" mode and with wrapped
 // coordinates, a texture under a ScaledMaterialColor, nested checkerboards, Cylinder under a Fresnel material, a background colour.
 // Run by oracle/refjs.py like any other test (fixture tests/golden/refjs_extra_materials.npz).

@@ -1,5 +1,5 @@
 // NOT a scene of the reference: written for this repository in the shape of the reference's tests/*/test.mjs, out of the
-// reference's own classes, to reach what none of its 39 demo scenes uses — TransparentMaterial, SolidColorMaterial,
+// reference's own classes, to reach what none of its 37 demo scenes uses — TransparentMaterial, SolidColorMaterial,
 // PositionalUVMaterial, RoundSDF, TextureMaterialColor in "nearest" mode and with wrapped
 // coordinates, a texture under a ScaledMaterialColor, nested checkerboards, Cylinder under a Fresnel material, a background colour.
 // This variant has point lights only: no random decisions, so the CUDA path can be compared with the reference's image of it.

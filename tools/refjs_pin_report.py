@@ -53,5 +53,8 @@ with open(out, "w") as f:
             "configure in the interpreter), 20x12 x 1 pass, 2-18 draws per sample: f32 colours and ImageData bytes equal the oracle's\n"
             "(`profiles/r2_refjs_xwing_oneoff.log`, the output of `tools/refjs_compare.py x-wing 20 12 1`); `tests/starwars` (BASELINE's\n"
             "stand-in for Toledo: x-wing + three tie fighters sharing one kd-tree, depth-of-field camera, three area lights + a point\n"
-            "light: 4-124 draws per sample), 20x12 x 1 pass: equal likewise (`profiles/r2_refjs_starwars_oneoff.log`).\n")
+            "light: 4-124 draws per sample), 20x12 x 1 pass: equal likewise (`profiles/r2_refjs_starwars_oneoff.log`); `tests/dragon` (99 968\n"
+            "triangles: one hour to configure, 106 MB document), 20x12 x 1 pass: equal likewise (`profiles/r2_refjs_dragon_oneoff.log`).\n"
+            "With these, 34 of the 37 scenes of the reference's tests/list.json are pinned; toledo, toledo_json and dragon_json cannot run\n"
+            "from the reference tree (asset / test.json absent).\n")
 print(open(out).read())
