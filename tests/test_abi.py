@@ -113,3 +113,35 @@ def test_degenerate_scenes_flatten_and_render_in_the_oracle():
         d["_v"][key] = bad
         with pytest.raises(lib.JsrtError, match="width|height"):
             lib.Scene(json.dumps(d), lib.FORMAT_JSON, device=None)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ (the C++ restatement, the JavaScript interpreter, the reference runner) is test infrastructure: nothing under
+    jsraytracer_b200/ or js/ may import, load or name it; bench.py and __graft_entry__ use it only in the legs the contract
+    allows (cpu_baseline / --impl reference / smoke's checker)."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    offenders = []
+    for base in ("jsraytracer_b200", "js", "include"):
+        for dirpath, _, files in os.walk(os.path.join(root, base)):
+            for f in files:
+                if not f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".js", ".cc")):
+                    continue
+                text = open(os.path.join(dirpath, f), encoding="utf8", errors="replace").read()
+                if re.search(r"(from|import)\s+oracle\b|liboracle|oracle/|oracle\.(oracle|refjs|jsvm)", text):
+                    # comments that cite the oracle as the checker are fine; code that reaches it is not
+                    code = "\n".join(l for l in text.splitlines() if not l.strip().startswith(("#", "//", "*", '"""')))
+                    if re.search(r"(from|import)\s+oracle\b|liboracle|dlopen\([^)]*oracle|CDLL\([^)]*oracle", code):
+                        offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+    # bench.py: the oracle is reached from exactly two functions — the cpu_baseline leg and the --impl reference arm
+    import ast
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    where = set()
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for n in ast.walk(fn):
+            if isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle":
+                where.add(fn.name)
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n)]
+    assert where == {"cpu_reference_run", "run_reference"} and not top
