@@ -1489,6 +1489,14 @@ def install(vm):
     Symbol.props['iterator'] = '@@iterator'
     G['Symbol'] = Symbol
 
+    # eval: global (indirect) evaluation of an expression — what src/serializer.js:109 does with a class name
+    def global_eval(this, args):
+        src = arg(args, 0)
+        if src.__class__ is not str:
+            return src
+        return vm.eval_expr(src)
+    G['eval'] = native('eval', global_eval)
+
     vm.native = native
     vm.make_ctor = make_ctor
     vm.proto_of = proto_of

@@ -188,6 +188,14 @@ class RefJS:
         self.test = t
         return self.info()
 
+    def load_wire(self, json_text):
+        """`Serializer.deserializeJSON(text)` — how the reference's `*_json` scenes come to life (tests/dragon_json/test.mjs:1-9)"""
+        vm = self.vm
+        vm.root.vars["__wire_text"] = json_text
+        vm.run("var __test = Serializer.deserializeJSON(__wire_text);", "<deserialize>")
+        self.test = vm.root.vars["__test"]
+        return self.info()
+
     def info(self):
         ev = self.vm.eval_expr
         return {
