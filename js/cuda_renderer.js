@@ -12,8 +12,10 @@
 // the N-API addon (js/napi/jsrt_addon.cc -> include/jsrt.h); all passes run on the GPU with the
 // accumulation buffer resident in HBM.
 //
-// NOTE: no JavaScript engine exists in the build image, so this file is exercised only through
-// its Python twin (jsraytracer_b200/renderers.py, same logic over the same C ABI).  It is loaded
+// NOTE: no Node exists in the build image.  This file is executed by the repository's own JavaScript
+// interpreter (oracle/jsvm, test infrastructure) next to the reference's unmodified sources, with the
+// addon's entry points supplied by Python: tests/test_js_host_in_vm.py; its Python twin
+// (jsraytracer_b200/renderers.py, same logic over the same C ABI) is what the GPU tests drive.  It is loaded
 // like the reference's sources (tests/test_to_json.js:7-22 runs them with vm.runInThisContext), so
 // it uses the reference's globals (Serializer, Triangle, IncrementalMultisamplingRenderer).
 "use strict";
