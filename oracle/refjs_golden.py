@@ -46,6 +46,8 @@ TABLE = [
     ("bunny", 48, 31, 1), ("bunny_path", 32, 21, 3), ("tie_fighter", 32, 21, 2), ("bottle", 48, 31, 1),
     # not the reference's: tests/golden/extra_scenes/materials/test.mjs, the reference's classes its own scenes leave unused
     ("extra_materials", 42, 27, 3), ("extra_materials_whitted", 48, 31, 2),
+    # ... and aggregates nested in ways its API allows and its scenes never do (the twin of scenes.nested_aggregates)
+    ("extra_nested_aggregates", 48, 31, 2),
 ]
 
 
