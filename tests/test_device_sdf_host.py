@@ -1,0 +1,117 @@
+"""The device's SDF distance function — bytecode compiler (csrc/sdf_compile.cpp) + interpreter (`sdf_eval`,
+csrc/device_math.cuh) — checked ON THE CPU against the reference's own `root_sdf.distance`.
+
+`sdf_eval` is written in the reference's arithmetic (f32 vectors, f64 scalars, un-contracted operations) and is plain
+C++ apart from a dozen CUDA spellings.  This test cuts the block from `xf64_apply` to the end of `sdf_eval` out of
+device_math.cuh as it is, compiles it for the host behind shims for those spellings (`__dmul_rn` -> `*` under
+-ffp-contract=off, `__ldg(p)` -> `*p`, `float3`, `__hiloint2double`, ...), links it with the product's real wire reader,
+flattener and SDF compiler, and evaluates the compiled program of every SDF fixture scene at the probe points of
+tests/golden/probes_refjs.npz, where the reference's own sources (run in oracle/jsvm) returned `root_sdf.distance(p)`.
+The bar is equality of every double."""
+import ctypes
+import json
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "..", "jsraytracer_b200", "csrc")
+
+SHIM = r"""
+#define _GNU_SOURCE 1
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+#include "host_scene.h"
+using namespace jsrt;
+using std::isfinite; using std::isinf;
+struct float3 { float x, y, z; };
+struct float4 { float x, y, z, w; };
+struct int4 { int x, y, z, w; };
+struct double2 { double x, y; };
+#define __device__
+#define __noinline__
+#define JSRT_DEV static inline
+#define CUDART_NAN (std::numeric_limits<double>::quiet_NaN())
+#define CUDART_INF (std::numeric_limits<double>::infinity())
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline float3 f3(float x, float y, float z) { return float3{x, y, z}; }
+// IEEE round-to-nearest single operations that the compiler must not contract: this file is built with -ffp-contract=off
+static inline double dmul(double a, double b) { return a * b; }
+static inline double dadd(double a, double b) { return a + b; }
+static inline double dsub(double a, double b) { return a - b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline double ddot3(double ax, double ay, double az, double bx, double by, double bz) { return dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz)); }
+static inline double ddot4(double ax, double ay, double az, double aw, double bx, double by, double bz, double bw) {
+    return dadd(dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz)), dmul(aw, bw));
+}
+static inline double jsd_min(double a, double b) { return (a != a || b != b) ? CUDART_NAN : fmin(a, b); }
+static inline double jsd_max(double a, double b) { return (a != a || b != b) ? CUDART_NAN : fmax(a, b); }
+static inline int __double2hiint(double x) { uint64_t u; memcpy(&u, &x, 8); return (int)(u >> 32); }
+static inline double __hiloint2double(int hi, int lo) { uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double d; memcpy(&d, &u, 8); return d; }
+"""
+
+DRIVER = r"""
+extern "C" int dev_sdf_probe(const char* blob, size_t len, int n, const double* pts, double* out) {
+    try {
+        WireDoc doc((const uint8_t*)blob, len, 0);
+        HostScene hs;
+        flattenScene(doc, hs);
+        if (hs.sdfs.empty()) return -1;
+        const SdfProgram& pr = hs.sdfs[0];
+        const SdfInstr* prog = hs.sdf_code.data() + pr.first_instr;
+        for (int i = 0; i < n; ++i) {
+            const float3 p = f3((float)pts[3 * i], (float)pts[3 * i + 1], (float)pts[3 * i + 2]);
+            out[2 * i] = sdf_eval<1>(prog, hs.xforms64.data(), p);        // the build with the fused Menger step inlined
+            out[2 * i + 1] = sdf_eval<-1>(prog, hs.xforms64.data(), p);   // ... and the one that calls it
+        }
+        return pr.instr_count;
+    } catch (const std::exception&) { return -2; }
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def dev(tmp_path_factory):
+    text = open(os.path.join(CSRC, "device_math.cuh")).read()
+    a = text.index("JSRT_DEV float3 xf64_apply(")
+    b = text.index("// AABB.get_intersects in the reference's arithmetic (f32 vectors, f64 scalars); the SDF")
+    block = text[a:b]
+    assert "double sdf_eval(" in block and "sdf_rtu_cross" in block and "js_fmod_pow2" in block
+    d = tmp_path_factory.mktemp("dev_sdf")
+    cpp = d / "dev_sdf.cpp"
+    cpp.write_text(SHIM + block + DRIVER)
+    so = d / "dev_sdf.so"
+    srcs = [os.path.join(CSRC, f) for f in ("wire.cpp", "scene_flatten.cpp", "sdf_compile.cpp", "bvh_build.cpp")]
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-I" + CSRC,
+                           "-o", str(so), str(cpp)] + srcs)
+    L = ctypes.CDLL(str(so))
+    L.dev_sdf_probe.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    return L
+
+
+Z = np.load(os.path.join(HERE, "golden", "probes_refjs.npz"))
+SCENES = sorted(k[4:-2] for k in Z.files if k.startswith("sdf_") and k.endswith("_p"))
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_device_sdf_distance_equals_reference(dev, name):
+    z = np.load(os.path.join(HERE, "golden", "refjs_%s.npz" % name))
+    blob = zlib.decompress(z["json"].tobytes())
+    pts = np.ascontiguousarray(Z["sdf_%s_p" % name], dtype=np.float64)
+    want = Z["sdf_%s_out" % name][:, 0]
+    out = np.zeros((len(pts), 2))
+    n_instr = dev.dev_sdf_probe(blob, len(blob), len(pts), pts.ctypes.data, out.ctypes.data)
+    assert n_instr > 0, "flatten / compile failed (%d)" % n_instr
+    for col, build in ((0, "RTU inlined"), (1, "RTU called")):
+        got = out[:, col]
+        bad = np.nonzero(~((got == want) | (np.isnan(got) & np.isnan(want))))[0]
+        assert bad.size == 0, "%s, %s: %d of %d points differ, e.g. p=%s reference %r device %r" % (
+            name, build, bad.size, len(pts), pts[bad[0]].tolist(), float(want[bad[0]]), float(got[bad[0]]))
