@@ -216,6 +216,20 @@ class RefJS:
             self.vm.run("installTriangleSerializeFix(); installTextureSerializeFix();")
         return self.vm.eval_expr("JSON.stringify(new Serializer(__test).plain())")
 
+    def camera_rays(self, width, height, passes, sample_random):
+        """the camera rays of the reference's own render loop (src/renderers.js:87-98 -> camera.getRayForPixel): the world is
+        replaced by a stub whose color() records the ray it is handed; returns (passes, H, W, 8): origin xyzw, direction xyzw"""
+        vm = self.vm
+        vm.run("var __rays = []; var __savedWorld = __test.renderer.world;"
+               "__test.renderer.world = { color: function (ray, depth) { __rays.push(Array.from(ray.origin).concat(Array.from(ray.direction))); return Vec.of(0, 0, 0); } };")
+        try:
+            self.render(width, height, passes, sample_random=sample_random)
+        finally:
+            vm.run("__test.renderer.world = __savedWorld;")
+        rays = np.array([r.items for r in vm.eval_expr("__rays").items], dtype=np.float64)
+        # render order: pass, column, row
+        return rays.reshape(passes, width, height, 8).transpose(0, 2, 1, 3)
+
     def render_simple(self, width, height):
         """the same world and camera through the reference's un-jittered `SimpleRenderer` (src/renderers.js:1-45) — for a
         scene without random decisions this is a deterministic image that any implementation can be compared with"""
@@ -236,8 +250,9 @@ class RefJS:
         finally:
             self.vm.run("__test.renderer = __saved;")
 
-    def render(self, width, height, passes=1, x_offset=0, x_delt=1, seed=1):
+    def render(self, width, height, passes=1, x_offset=0, x_delt=1, seed=1, sample_random=None):
         """`test.renderer.render(new PixelBuffer(w, h), 1000, callback, workerIndex, workerCount)`, src/worker.js:26-32.
+        sample_random(pixel, pass) -> iterable of floats: what Math.random() returns during that sample, instead of the tape.
         Returns (mean (H,W,3) f32 — the colour handed to the last setColor of each pixel, rgba8 (H,W,4) u8, draws per
         sample (H,W) of the last pass)."""
         vm = self.vm
@@ -257,8 +272,16 @@ class RefJS:
 
         def arm(i):
             it, px, py = order[i]
-            tape.seed(tape_seed(seed, py * width + px, it))
             tape.draws = 0
+            if sample_random is not None:
+                vals = iter(sample_random(py * width + px, it))
+
+                def rnd():
+                    tape.draws += 1
+                    return float(next(vals))
+                vm.random = rnd
+                return
+            tape.seed(tape_seed(seed, py * width + px, it))
 
         def on_sample(x, y, color):
             i = state["i"]
@@ -279,6 +302,7 @@ class RefJS:
                    % (width, height, x_offset, x_delt), "<render>")
         finally:
             self._on_sample = None
+            vm.random = tape
         if state["i"] != len(order):
             raise RuntimeError("renderer finished %d samples, expected %d" % (state["i"], len(order)))
         data = vm.eval_expr("__buf.imgdata.data")

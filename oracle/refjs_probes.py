@@ -76,6 +76,26 @@ def fmod_probes(r, rng, n):
     return a, b, out
 
 
+def camera_probes(out_path):
+    """camera rays of the reference's render loop when Math.random() returns what the device's counter-based generator
+    returns for (seed, pixel, pass, node 1, dims 0..3) — so that the device's camera_ray() can be compared ray by ray (the
+    scene documents are those of tests/golden/refjs_<scene>.npz: a camera does not depend on the image size)"""
+    from . import oracle as orc
+    L = orc.lib()
+    arrays = {}
+    for name, W, H, P, seed in (("BoxBall", 13, 9, 2, 1), ("BoxBall_DOF", 13, 9, 2, 5), ("bunny_path", 11, 7, 1, 9), ("cornell_box_path", 8, 8, 1, 2)):
+        r = RefJS()
+        r.load_test(name)
+
+        def rnd(pixel, pass_, seed=seed):
+            return [L.orc_kat_rng(seed, pixel, pass_, 1, d) for d in range(4)]
+        rays = r.camera_rays(W, H, P, rnd)
+        arrays["cam_%s_rays" % name] = rays
+        arrays["cam_%s_meta" % name] = np.array([W, H, P, seed])
+        print(name, rays.shape, flush=True)
+    np.savez_compressed(out_path, **arrays)
+
+
 def main():
     rng = np.random.default_rng(20241019)
     arrays = {}
@@ -100,4 +120,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    if "camera" in sys.argv[1:]:
+        camera_probes(os.path.join(GOLDEN, "probes_camera_refjs.npz"))
+    else:
+        main()
