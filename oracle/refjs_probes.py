@@ -96,6 +96,33 @@ def camera_probes(out_path):
     np.savez_compressed(out_path, **arrays)
 
 
+def sdf_hit_probes(out_path):
+    """`SDFGeometry.intersect(ray, minDistance, maxDistance)` (src/sdf.js:12-40, the sphere-tracing march) on rays in the
+    geometry's own space, aimed at its bounding box from outside and from inside"""
+    rng = np.random.default_rng(77)
+    arrays = {}
+    for name in SDF_SCENES:
+        r = RefJS()
+        r.load_test(name)
+        vm = r.vm
+        idx = int(vm.eval_expr("__test.renderer.world.objects.findIndex(o => o.geometry instanceof SDFGeometry)"))
+        fn = vm.eval_expr("(function(i, ox, oy, oz, dx, dy, dz, lo, hi) { return __test.renderer.world.objects[i].geometry.intersect("
+                          "new Ray(Vec.of(ox, oy, oz, 1), Vec.of(dx, dy, dz, 0)), lo, hi); })")
+        n = 60 if name == "SDF_Menger" else 160
+        rays = np.zeros((n, 8))
+        out = np.zeros(n)
+        for i in range(n):
+            o = f32(rng.normal(0, 1, 3) * (3.0 if i % 3 else 0.4))
+            target = rng.normal(0, 0.5, 3)
+            d = f32((target - o) * rng.uniform(0.2, 3.0))               # unnormalised on purpose
+            lo, hi = (0.0001, float("inf")) if i % 4 else (0.0001, 1.0)
+            rays[i] = [*o, *d, lo, hi]
+            out[i] = vm.call(fn, None, [float(idx), *map(float, o), *map(float, d), lo, hi])
+        arrays["hit_%s_rays" % name], arrays["hit_%s_t" % name] = rays, out
+        print(name, int(np.isfinite(out).sum()), "hits of", n, flush=True)
+    np.savez_compressed(out_path, **arrays)
+
+
 def main():
     rng = np.random.default_rng(20241019)
     arrays = {}
@@ -121,7 +148,9 @@ def main():
 
 if __name__ == "__main__":
     import sys
-    if "camera" in sys.argv[1:]:
+    if "sdfhit" in sys.argv[1:]:
+        sdf_hit_probes(os.path.join(GOLDEN, "probes_sdfhit_refjs.npz"))
+    elif "camera" in sys.argv[1:]:
         camera_probes(os.path.join(GOLDEN, "probes_camera_refjs.npz"))
     else:
         main()

@@ -75,6 +75,25 @@ extern "C" int dev_sdf_probe(const char* blob, size_t len, int n, const double* 
         return pr.instr_count;
     } catch (const std::exception&) { return -2; }
 }
+
+// SDFGeometry.intersect: the sphere-tracing march (sdf_intersect) over the same compiled program
+extern "C" int dev_sdf_hits(const char* blob, size_t len, int n, const double* rays, double* out) {
+    try {
+        WireDoc doc((const uint8_t*)blob, len, 0);
+        HostScene hs;
+        flattenScene(doc, hs);
+        if (hs.sdfs.empty()) return -1;
+        const SdfProgram& pr = hs.sdfs[0];
+        for (int i = 0; i < n; ++i) {
+            const double* r = rays + 8 * i;
+            unsigned long long evals = 0;
+            out[2 * i] = sdf_intersect(pr, hs.sdf_code.data(), hs.xforms64.data(), f3((float)r[0], (float)r[1], (float)r[2]),
+                                       f3((float)r[3], (float)r[4], (float)r[5]), r[6], r[7], &evals);
+            out[2 * i + 1] = (double)evals;
+        }
+        return pr.max_samples;
+    } catch (const std::exception&) { return -2; }
+}
 """
 
 
@@ -82,9 +101,9 @@ extern "C" int dev_sdf_probe(const char* blob, size_t len, int n, const double* 
 def dev(tmp_path_factory):
     text = open(os.path.join(CSRC, "device_math.cuh")).read()
     a = text.index("JSRT_DEV float3 xf64_apply(")
-    b = text.index("// AABB.get_intersects in the reference's arithmetic (f32 vectors, f64 scalars); the SDF")
+    b = text.rindex("}  // namespace jsrt")
     block = text[a:b]
-    assert "double sdf_eval(" in block and "sdf_rtu_cross" in block and "js_fmod_pow2" in block
+    assert "double sdf_eval(" in block and "sdf_rtu_cross" in block and "js_fmod_pow2" in block and "double sdf_intersect(" in block
     d = tmp_path_factory.mktemp("dev_sdf")
     cpp = d / "dev_sdf.cpp"
     cpp.write_text(SHIM + block + DRIVER)
@@ -94,6 +113,7 @@ def dev(tmp_path_factory):
                            "-o", str(so), str(cpp)] + srcs)
     L = ctypes.CDLL(str(so))
     L.dev_sdf_probe.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    L.dev_sdf_hits.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     return L
 
 
@@ -115,3 +135,26 @@ def test_device_sdf_distance_equals_reference(dev, name):
         bad = np.nonzero(~((got == want) | (np.isnan(got) & np.isnan(want))))[0]
         assert bad.size == 0, "%s, %s: %d of %d points differ, e.g. p=%s reference %r device %r" % (
             name, build, bad.size, len(pts), pts[bad[0]].tolist(), float(want[bad[0]]), float(got[bad[0]]))
+
+
+ZH = np.load(os.path.join(HERE, "golden", "probes_sdfhit_refjs.npz"))
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_device_sdf_march_equals_reference_intersect(dev, name):
+    """`SDFGeometry.intersect` (src/sdf.js:12-40): bounding-box clip, march, epsilon stop, trace-distance and window exits —
+    the hit parameter t of the device's `sdf_intersect` equals the reference's on every probe ray, misses are misses"""
+    z = np.load(os.path.join(HERE, "golden", "refjs_%s.npz" % name))
+    blob = zlib.decompress(z["json"].tobytes())
+    rays = np.ascontiguousarray(ZH["hit_%s_rays" % name], dtype=np.float64)
+    want = ZH["hit_%s_t" % name]
+    out = np.zeros((len(rays), 2))
+    assert dev.dev_sdf_hits(blob, len(blob), len(rays), rays.ctypes.data, out.ctypes.data) > 0
+    got = out[:, 0]
+    miss_w, miss_g = ~np.isfinite(want), ~np.isfinite(got)
+    assert np.array_equal(miss_w, miss_g), "hit / miss differs on rays %s" % np.nonzero(miss_w != miss_g)[0][:5].tolist()
+    bad = np.nonzero(~miss_w & (got != want))[0]
+    assert bad.size == 0, "%d of %d hits differ, e.g. ray %s reference t %r device t %r" % (
+        bad.size, int((~miss_w).sum()), rays[bad[0]].tolist(), float(want[bad[0]]), float(got[bad[0]]))
+    if int((~miss_w).sum()) > 5:
+        assert out[:, 1].max() > 5      # the march really marched
