@@ -59,6 +59,27 @@ static inline double __hiloint2double(int hi, int lo) { uint64_t u = ((uint64_t)
 """
 
 DRIVER = r"""
+// the forward-difference normal of SDFGeometry.materialData (src/sdf.js:41-47): the statements of shade.cuh's G_SDF case
+struct ScShim { const SdfInstr* sdf_code; const Xform64* xforms64; };
+static float3 dev_sdf_normal(const ScShim& sc, const SdfProgram& pr, float3 lp) {
+    float3 n;
+@NORMAL_BLOCK@
+    return n;
+}
+extern "C" int dev_sdf_normals(const char* blob, size_t len, int n, const double* pts, double* out) {
+    try {
+        WireDoc doc((const uint8_t*)blob, len, 0);
+        HostScene hs;
+        flattenScene(doc, hs);
+        if (hs.sdfs.empty()) return -1;
+        const ScShim sc{hs.sdf_code.data(), hs.xforms64.data()};
+        for (int i = 0; i < n; ++i) {
+            const float3 v = dev_sdf_normal(sc, hs.sdfs[0], f3((float)pts[3 * i], (float)pts[3 * i + 1], (float)pts[3 * i + 2]));
+            out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+        }
+        return 1;
+    } catch (const std::exception&) { return -2; }
+}
 extern "C" int dev_sdf_probe(const char* blob, size_t len, int n, const double* pts, double* out) {
     try {
         WireDoc doc((const uint8_t*)blob, len, 0);
@@ -104,15 +125,21 @@ def dev(tmp_path_factory):
     b = text.rindex("}  // namespace jsrt")
     block = text[a:b]
     assert "double sdf_eval(" in block and "sdf_rtu_cross" in block and "js_fmod_pow2" in block and "double sdf_intersect(" in block
+    shade = open(os.path.join(CSRC, "shade.cuh")).read()
+    na = shade.index("            const SdfInstr* prog = sc.sdf_code + pr.first_instr;")
+    nb = shade.index("\n", shade.index("n = (nn > 0.00001) ?", na)) + 1
+    normal_block = shade[na:nb]
+    assert normal_block.count("sdf_eval(") == 4
     d = tmp_path_factory.mktemp("dev_sdf")
     cpp = d / "dev_sdf.cpp"
-    cpp.write_text(SHIM + block + DRIVER)
+    cpp.write_text(SHIM + block + DRIVER.replace("@NORMAL_BLOCK@", normal_block))
     so = d / "dev_sdf.so"
     srcs = [os.path.join(CSRC, f) for f in ("wire.cpp", "scene_flatten.cpp", "sdf_compile.cpp", "bvh_build.cpp")]
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-I" + CSRC,
                            "-o", str(so), str(cpp)] + srcs)
     L = ctypes.CDLL(str(so))
     L.dev_sdf_probe.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    L.dev_sdf_normals.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     L.dev_sdf_hits.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     return L
 
@@ -158,3 +185,18 @@ def test_device_sdf_march_equals_reference_intersect(dev, name):
         bad.size, int((~miss_w).sum()), rays[bad[0]].tolist(), float(want[bad[0]]), float(got[bad[0]]))
     if int((~miss_w).sum()) > 5:
         assert out[:, 1].max() > 5      # the march really marched
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_device_sdf_normal_equals_reference_material_data(dev, name):
+    """the normal of `SDFGeometry.materialData` (src/sdf.js:41-47: three forward differences over `normal_step_size`, then
+    `normalized()`): the statements of shade.cuh's G_SDF case, cut out as they are, give the reference's f32 normal"""
+    z = np.load(os.path.join(HERE, "golden", "refjs_%s.npz" % name))
+    blob = zlib.decompress(z["json"].tobytes())
+    pts = np.ascontiguousarray(Z["sdf_%s_p" % name], dtype=np.float64)
+    want = Z["sdf_%s_out" % name][:, 1:4]
+    out = np.zeros((len(pts), 3))
+    assert dev.dev_sdf_normals(blob, len(blob), len(pts), pts.ctypes.data, out.ctypes.data) == 1
+    bad = np.nonzero(~((out == want) | (np.isnan(out) & np.isnan(want))).all(-1))[0]
+    assert bad.size == 0, "%d of %d normals differ, e.g. p=%s reference %s device %s" % (
+        bad.size, len(pts), pts[bad[0]].tolist(), want[bad[0]].tolist(), out[bad[0]].tolist())
