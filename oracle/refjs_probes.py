@@ -123,6 +123,27 @@ def sdf_hit_probes(out_path):
     np.savez_compressed(out_path, **arrays)
 
 
+def texture_probes(out_path):
+    """`TextureMaterialColor.color({UV})` (src/materials.js:101-130) of the two textures of the extra materials scene — bilinear
+    with wrapped coordinates, nearest with clamped ones — at random and at edge-case UVs"""
+    rng = np.random.default_rng(5)
+    r = RefJS()
+    r.load_test("extra_materials_whitted")
+    vm = r.vm
+    fn = vm.eval_expr("(function(tex, u, v) { return Array.from(tex.color({UV: Vec.of(u, v)})); })")
+    texs = {"bilinear_wrap": vm.eval_expr("__test.renderer.world.objects[0].material.baseMaterial.diffusivity"),
+            "nearest_clamp": vm.eval_expr("__test.renderer.world.objects[2].material._color")}
+    edge = [0.0, 1.0, 0.5, 0.0625, 0.125, 0.9375, 0.25, 0.75, -0.0, 1e-9, 1 - 1e-9, -1.0, 2.0, 0.0624999, 0.1875]
+    uv = [(a, b) for a in edge for b in edge[:6]] + [tuple(x) for x in rng.uniform(-2.5, 2.5, (400, 2))] + [tuple(x) for x in rng.uniform(0, 1, (300, 2))]
+    uv = f32(np.array(uv))
+    arrays = {"uv": uv}
+    for k, t in texs.items():
+        assert vm.eval_expr("(function(t) { return t instanceof TextureMaterialColor; })").__class__ is not None
+        arrays["tex_" + k] = np.array([vm.call(fn, None, [t, float(a), float(b)]).items for a, b in uv])
+    np.savez_compressed(out_path, **arrays)
+    print({k: v.shape for k, v in arrays.items()})
+
+
 def main():
     rng = np.random.default_rng(20241019)
     arrays = {}
@@ -148,7 +169,9 @@ def main():
 
 if __name__ == "__main__":
     import sys
-    if "sdfhit" in sys.argv[1:]:
+    if "texture" in sys.argv[1:]:
+        texture_probes(os.path.join(GOLDEN, "probes_texture_refjs.npz"))
+    elif "sdfhit" in sys.argv[1:]:
         sdf_hit_probes(os.path.join(GOLDEN, "probes_sdfhit_refjs.npz"))
     elif "camera" in sys.argv[1:]:
         camera_probes(os.path.join(GOLDEN, "probes_camera_refjs.npz"))
