@@ -144,6 +144,24 @@ def texture_probes(out_path):
     print({k: v.shape for k, v in arrays.items()})
 
 
+def sdf_material_probes(out_path):
+    """`root_sdf.getMaterialData(p)` (src/sdf.js: per-leaf basecolor, SphereSDF UVs, the selection rules of Union /
+    Intersection / Difference and the blends of their smooth variants) at the probe points of probes_refjs.npz"""
+    pts_all = np.load(os.path.join(GOLDEN, "probes_refjs.npz"))
+    arrays = {}
+    for name in SDF_SCENES:
+        r = RefJS()
+        r.load_test(name)
+        vm = r.vm
+        idx = int(vm.eval_expr("__test.renderer.world.objects.findIndex(o => o.geometry instanceof SDFGeometry)"))
+        fn = vm.eval_expr("(function(i, x, y, z) { const m = __test.renderer.world.objects[i].geometry.root_sdf.getMaterialData(Vec.of(x, y, z, 1));"
+                          " const b = m.basecolor, u = m.UV; return [b ? b[0] : NaN, b ? b[1] : NaN, b ? b[2] : NaN, u ? u[0] : NaN, u ? u[1] : NaN]; })")
+        pts = pts_all["sdf_%s_p" % name]
+        arrays["mat_%s" % name] = np.array([vm.call(fn, None, [float(idx), *map(float, p)]).items for p in pts])
+        print(name, arrays["mat_%s" % name][:2].tolist(), flush=True)
+    np.savez_compressed(out_path, **arrays)
+
+
 def main():
     rng = np.random.default_rng(20241019)
     arrays = {}
@@ -169,7 +187,9 @@ def main():
 
 if __name__ == "__main__":
     import sys
-    if "texture" in sys.argv[1:]:
+    if "sdfmat" in sys.argv[1:]:
+        sdf_material_probes(os.path.join(GOLDEN, "probes_sdfmat_refjs.npz"))
+    elif "texture" in sys.argv[1:]:
         texture_probes(os.path.join(GOLDEN, "probes_texture_refjs.npz"))
     elif "sdfhit" in sys.argv[1:]:
         sdf_hit_probes(os.path.join(GOLDEN, "probes_sdfhit_refjs.npz"))

@@ -34,6 +34,9 @@ struct float3 { float x, y, z; };
 struct float4 { float x, y, z, w; };
 struct int4 { int x, y, z, w; };
 struct double2 { double x, y; };
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+struct DeviceScene { const SdfInstr* sdf_code; const Xform64* xforms64; };       // the two members the SDF material program reads
 #define __device__
 #define __noinline__
 #define JSRT_DEV static inline
@@ -59,6 +62,25 @@ static inline double __hiloint2double(int hi, int lo) { uint64_t u = ((uint64_t)
 """
 
 DRIVER = r"""
+@MATERIAL_BLOCK@
+// root_sdf.getMaterialData(p): the material program of the scene's SDF (uniform basecolor: the program's `base`)
+extern "C" int dev_sdf_materials(const char* blob, size_t len, int n, const double* pts, double* out) {
+    try {
+        WireDoc doc((const uint8_t*)blob, len, 0);
+        HostScene hs;
+        flattenScene(doc, hs);
+        if (hs.sdfs.empty()) return -1;
+        const SdfProgram& pr = hs.sdfs[0];
+        const DeviceScene sc{hs.sdf_code.data(), hs.xforms64.data()};
+        for (int i = 0; i < n; ++i) {
+            float3 base = f3(pr.base[0], pr.base[1], pr.base[2]); float2 uv = make_float2(0.f, 0.f); bool has_uv = false;
+            if (pr.mat_first >= 0) sdf_material(sc, pr.mat_first, f3((float)pts[3 * i], (float)pts[3 * i + 1], (float)pts[3 * i + 2]), base, uv, has_uv);
+            double* o = out + 5 * i;
+            o[0] = base.x; o[1] = base.y; o[2] = base.z; o[3] = has_uv ? uv.x : CUDART_NAN; o[4] = has_uv ? uv.y : CUDART_NAN;
+        }
+        return pr.mat_first >= 0 ? 2 : 1;
+    } catch (const std::exception&) { return -2; }
+}
 // the forward-difference normal of SDFGeometry.materialData (src/sdf.js:41-47): the statements of shade.cuh's G_SDF case
 struct ScShim { const SdfInstr* sdf_code; const Xform64* xforms64; };
 static float3 dev_sdf_normal(const ScShim& sc, const SdfProgram& pr, float3 lp) {
@@ -130,15 +152,20 @@ def dev(tmp_path_factory):
     nb = shade.index("\n", shade.index("n = (nn > 0.00001) ?", na)) + 1
     normal_block = shade[na:nb]
     assert normal_block.count("sdf_eval(") == 4
+    ma = shade.index("struct SdfMat {")
+    mb = shade.index("// geometry.materialData in the primitive's local space")
+    material_block = shade[ma:mb]
+    assert "void sdf_material(" in material_block
     d = tmp_path_factory.mktemp("dev_sdf")
     cpp = d / "dev_sdf.cpp"
-    cpp.write_text(SHIM + block + DRIVER.replace("@NORMAL_BLOCK@", normal_block))
+    cpp.write_text(SHIM + block + DRIVER.replace("@NORMAL_BLOCK@", normal_block).replace("@MATERIAL_BLOCK@", material_block))
     so = d / "dev_sdf.so"
     srcs = [os.path.join(CSRC, f) for f in ("wire.cpp", "scene_flatten.cpp", "sdf_compile.cpp", "bvh_build.cpp")]
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-I" + CSRC,
                            "-o", str(so), str(cpp)] + srcs)
     L = ctypes.CDLL(str(so))
     L.dev_sdf_probe.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    L.dev_sdf_materials.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     L.dev_sdf_normals.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     L.dev_sdf_hits.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     return L
@@ -200,3 +227,27 @@ def test_device_sdf_normal_equals_reference_material_data(dev, name):
     bad = np.nonzero(~((out == want) | (np.isnan(out) & np.isnan(want))).all(-1))[0]
     assert bad.size == 0, "%d of %d normals differ, e.g. p=%s reference %s device %s" % (
         bad.size, len(pts), pts[bad[0]].tolist(), want[bad[0]].tolist(), out[bad[0]].tolist())
+
+
+ZM = np.load(os.path.join(HERE, "golden", "probes_sdfmat_refjs.npz"))
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_device_sdf_material_equals_reference_get_material_data(dev, name):
+    """`root_sdf.getMaterialData(p)`: the leaf whose distance wins a Union / Intersection / Difference, the blends of the smooth
+    variants, SphereSDF's spherical UVs — sdf_compile.cpp's material program run by shade.cuh's `sdf_material` gives the
+    reference's basecolor and UV (f32) at every probe point"""
+    z = np.load(os.path.join(HERE, "golden", "refjs_%s.npz" % name))
+    blob = zlib.decompress(z["json"].tobytes())
+    pts = np.ascontiguousarray(Z["sdf_%s_p" % name], dtype=np.float64)
+    want = ZM["mat_%s" % name]
+    out = np.zeros((len(pts), 5))
+    kind = dev.dev_sdf_materials(blob, len(blob), len(pts), pts.ctypes.data, out.ctypes.data)
+    assert kind in (1, 2)
+    want = want.copy()
+    want[np.isnan(want[:, 0]), 0:3] = 1.0                 # no basecolor in the data: PhongMaterial falls back to (1, 1, 1), src/materials.js:223
+    bad = np.nonzero(~((out == want) | (np.isnan(out) & np.isnan(want))).all(-1))[0]
+    assert bad.size == 0, "%d of %d points differ, e.g. p=%s reference %s device %s" % (
+        bad.size, len(pts), pts[bad[0]].tolist(), want[bad[0]].tolist(), out[bad[0]].tolist())
+    if name == "SDF_Combinations":
+        assert kind == 2 and len({tuple(r) for r in want[:, :3].tolist()}) >= 2        # several leaf colours are really selected
